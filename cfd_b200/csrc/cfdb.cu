@@ -1,0 +1,1239 @@
+// libcfdb200.so — context, time loop and C ABI (include/cfdb.h) on top of kernels.cuh.
+// Compiled for sm_100a only, with -fmad=false (see exact.cuh).  No CPU fallback anywhere.
+#include "../../include/cfdb.h"
+#include "host_topology.h"
+#include "kernels.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using std::vector;
+
+static thread_local std::string g_err;
+static int fail(const std::string& m) {
+    g_err = m;
+    return 1;
+}
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t _e = (call);                                                                        \
+        if (_e != cudaSuccess)                                                                          \
+            return fail(std::string(#call) + ": " + cudaGetErrorString(_e) + " @" + std::to_string(__LINE__)); \
+    } while (0)
+#define TRY(call)                \
+    do {                         \
+        int _r = (call);         \
+        if (_r) return _r;       \
+    } while (0)
+
+template <class T>
+struct DBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    int alloc(size_t count) {
+        if (count <= n && p) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+        if (count == 0) return 0;
+        CK(cudaMalloc(&p, count * sizeof(T)));
+        n = count;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+enum KernelId {
+    K_DERIV, K_MASAS, K_NORMALES, K_DELTAT, K_DTLOGIC, K_DTL, K_ESTAB, K_CALCRHS, K_NODE, K_DOT, K_NORMS, K_SPMV,
+    K_VEC, K_FIXROWS, K_SCALAR, K_LAPLACE, K_TRANSF, K_MOVE, K_FORCES, K_GCL, K_LAYOUT, K_FILL, K_COUNT
+};
+static const char* kKernelNames[K_COUNT] = {"deriv", "masas", "normales", "deltat", "dt_logic", "dtl", "estab",
+                                            "calcrhs_elem", "node_update", "dot", "norms", "spmv", "vec", "fixrows",
+                                            "scalar", "laplace", "transf", "move_apply", "forces", "gcl", "layout", "fill"};
+
+struct cfdb_ctx {
+    int device = 0;
+    cudaStream_t st = nullptr;
+    cfdb_params par{};
+    int npoin = 0, nelem = 0;
+    // host copies of integer artefacts (API layout: 1-based)
+    vector<int32_t> h_inpoel, esup1, esup2, psup1, psup2, lap_idx, lap_rowptr, h_eslot;
+    vector<int32_t> h_wall, h_wn_node, h_ilaux, h_fixidx_last;
+    int nnz = 0, maxrow = 0, nwn = 0, nb = 0, nmove = 0, nnmove = 0, nset = 0, nse = 0;
+    bool ale = false;  // mesh can move (body sets present or W set by the caller)
+    // device: mesh
+    DBuf<int> inp, d_esup2, eslot, d_lap_idx, d_lap_rowptr, wall, wn_node, wn_ptr, wn_edge, wn_valid;
+    DBuf<unsigned char> lpos, bcflag;
+    DBuf<double> X, Y, X1, Y1, area, HH, HHX, HHY, dNx, dNy, M;
+    // device: state
+    DBuf<double> U, U1, RHS, RHS1, RHS2, RHS3, UN, VEL_X, VEL_Y, W_X, W_Y, P, T, RHO, E, RMACH, GAMM;
+    DBuf<double> SHOC, TS1, TS2, TS3, DT, DTL, EC, FC;
+    // device: BC tables
+    DBuf<int> bc_node, bc_kind, bc_wslot;
+    DBuf<double> bc_vx, bc_vy, bc_rho, bc_T, wn_x, wn_y;
+    // device: laplace / bicg / mesh motion
+    DBuf<double> lap_sparse, lap_diag, by, bp, br, bz, bb, xpos, ypos, dxpos, dypos, pos_aux, xref, yref;
+    DBuf<int> ilaux, ilaux_last, se_node, se_set, set_ptr, set_n1, set_n2;
+    // gcl
+    DBuf<double> W_x_old, W_y_old, area_old;
+    // reductions / scalars
+    DBuf<double> redA, redB, tmpA, tmpB, tmpC;
+    DBuf<int> flags;
+    k::Scal* sc = nullptr;
+    k::Scal* h_sc = nullptr;  // pinned
+    // host mirror of loop scalars
+    int h_iter = 0;
+    int iterprint = 0;
+    double DISN[2] = {0, 0};
+    int bicg_iters[2] = {0, 0};
+    bool theta_nonzero = false;
+    bool u1_is_u = false;  // after U = U1 (ns2DComp.ALE.f90:277-281) the two arrays are one buffer
+    // profiling
+    bool prof = false;
+    int64_t launches = 0;
+    struct Pending { int id; cudaEvent_t a, b; };
+    vector<Pending> pending;
+    vector<cudaEvent_t> evpool;
+    double prof_ms[K_COUNT] = {0};
+    int64_t prof_n[K_COUNT] = {0};
+};
+
+static inline int grid_for(long n, int block) { return (int)((n + block - 1) / block); }
+
+static int prof_begin(cfdb_ctx* c, int id, cudaEvent_t* a, cudaEvent_t* b) {
+    c->launches++;
+    if (!c->prof) return 0;
+    for (int i = 0; i < 2; ++i) {
+        cudaEvent_t e;
+        if (c->evpool.empty()) {
+            CK(cudaEventCreate(&e));
+        } else {
+            e = c->evpool.back();
+            c->evpool.pop_back();
+        }
+        (i ? *b : *a) = e;
+    }
+    CK(cudaEventRecord(*a, c->st));
+    (void)id;
+    return 0;
+}
+static int prof_end(cfdb_ctx* c, int id, cudaEvent_t a, cudaEvent_t b) {
+    if (!c->prof) return 0;
+    CK(cudaEventRecord(b, c->st));
+    c->pending.push_back({id, a, b});
+    return 0;
+}
+static int prof_resolve(cfdb_ctx* c) {
+    if (c->pending.empty()) return 0;
+    CK(cudaStreamSynchronize(c->st));
+    for (auto& p : c->pending) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, p.a, p.b));
+        c->prof_ms[p.id] += ms;
+        c->prof_n[p.id] += 1;
+        c->evpool.push_back(p.a);
+        c->evpool.push_back(p.b);
+    }
+    c->pending.clear();
+    return 0;
+}
+#define LAUNCH(id, kernel, grid, block, ...)                                  \
+    do {                                                                      \
+        cudaEvent_t _a = nullptr, _b = nullptr;                               \
+        TRY(prof_begin(c, id, &_a, &_b));                                     \
+        kernel<<<(grid), (block), 0, c->st>>>(__VA_ARGS__);                   \
+        CK(cudaGetLastError());                                               \
+        TRY(prof_end(c, id, _a, _b));                                         \
+    } while (0)
+
+template <class T>
+static int upload(cfdb_ctx* c, DBuf<T>& d, const T* h, size_t n) {
+    TRY(d.alloc(n));
+    if (n) CK(cudaMemcpyAsync(d.p, h, n * sizeof(T), cudaMemcpyHostToDevice, c->st));
+    return 0;
+}
+template <class T>
+static int upload(cfdb_ctx* c, DBuf<T>& d, const vector<T>& h) {
+    return upload(c, d, h.data(), h.size());
+}
+template <class T>
+static int zero(cfdb_ctx* c, DBuf<T>& d, size_t n) {
+    TRY(d.alloc(n));
+    if (n) CK(cudaMemsetAsync(d.p, 0, n * sizeof(T), c->st));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" const char* cfdb_last_error(void) { return g_err.c_str(); }
+extern "C" int cfdb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+extern "C" int cfdb_get_esup(const int32_t* inpoel, int32_t nelem, int32_t npoin, int32_t* esup1, int32_t* esup2) {
+    vector<int32_t> e1, e2;
+    topo::build_esup(inpoel, nelem, npoin, e1, e2, nullptr);
+    std::copy(e1.begin(), e1.end(), esup1);
+    std::copy(e2.begin(), e2.end(), esup2);
+    return 0;
+}
+extern "C" int cfdb_get_psup(const int32_t* inpoel, int32_t nelem, int32_t npoin, int32_t* psup1, int32_t cap,
+                             int32_t* psup2, int32_t* count) {
+    vector<int32_t> e1, e2, p1, p2;
+    topo::build_esup(inpoel, nelem, npoin, e1, e2, nullptr);
+    topo::build_psup(inpoel, npoin, e1, e2, p1, p2);
+    *count = (int32_t)p1.size();
+    std::copy(p2.begin(), p2.end(), psup2);
+    if ((int)p1.size() > cap) return fail("cfdb_get_psup: capacity too small");
+    std::copy(p1.begin(), p1.end(), psup1);
+    return 0;
+}
+
+static int build_bc_tables(cfdb_ctx* c, const cfdb_bc* bc) {
+    const int P = c->npoin;
+    static const cfdb_bc empty{};
+    if (!bc) bc = &empty;
+    // wall nodes: unique sorted; CSR of wall edges per node in ascending edge order
+    c->h_wall.assign(bc->wall, bc->wall + 2 * (size_t)bc->nwall);
+    vector<int32_t> wcount((size_t)P + 1, 0);
+    for (int i = 0; i < bc->nwall; ++i) {
+        int a = bc->wall[2 * i], b = bc->wall[2 * i + 1];
+        if (a < 1 || a > P || b < 1 || b > P) return fail("wall edge node out of range");
+        wcount[a]++;
+        if (b != a) wcount[b]++;
+    }
+    vector<int32_t> wn_slot((size_t)P + 1, -1), wn_node, wn_ptr(1, 0);
+    for (int n = 1; n <= P; ++n)
+        if (wcount[n]) {
+            wn_slot[n] = (int)wn_node.size();
+            wn_node.push_back(n - 1);
+            wn_ptr.push_back(wn_ptr.back() + wcount[n]);
+        }
+    vector<int32_t> wn_edge(wn_ptr.back()), cur(wn_ptr.begin(), wn_ptr.end() - 1);
+    for (int i = 0; i < bc->nwall; ++i) {
+        int a = bc->wall[2 * i], b = bc->wall[2 * i + 1];
+        wn_edge[cur[wn_slot[a]]++] = i;
+        if (b != a) wn_edge[cur[wn_slot[b]]++] = i;
+    }
+    c->nwn = (int)wn_node.size();
+    c->h_wn_node = wn_node;
+    vector<int32_t> wall0(c->h_wall);
+    for (auto& v : wall0) v -= 1;
+    TRY(upload(c, c->wall, wall0));
+    TRY(upload(c, c->wn_node, wn_node));
+    TRY(upload(c, c->wn_ptr, wn_ptr));
+    TRY(upload(c, c->wn_edge, wn_edge));
+    TRY(zero(c, c->wn_x, (size_t)c->nwn));
+    TRY(zero(c, c->wn_y, (size_t)c->nwn));
+    TRY(zero(c, c->wn_valid, (size_t)c->nwn));
+    // per-node BC table, lists applied in order so the last entry wins
+    vector<unsigned char> flag((size_t)P, 0);
+    vector<double> vx((size_t)P, 0), vy((size_t)P, 0), rho((size_t)P, 0), tf((size_t)P, 0);
+    auto chk = [&](int n) { return n >= 1 && n <= P; };
+    for (int i = 0; i < bc->nfixv; ++i) {
+        int n = bc->ifixv_node[i];
+        if (!chk(n)) return fail("ifixv_node out of range");
+        flag[n - 1] |= 1; vx[n - 1] = bc->rfixv_valuex[i]; vy[n - 1] = bc->rfixv_valuey[i];
+    }
+    for (int n : wn_node) flag[n] |= 2;
+    for (int i = 0; i < bc->nfixrho; ++i) {
+        int n = bc->ifixrho_node[i];
+        if (!chk(n)) return fail("ifixrho_node out of range");
+        flag[n - 1] |= 4; rho[n - 1] = bc->rfixrho_value[i];
+    }
+    for (int i = 0; i < bc->nfixt; ++i) {
+        int n = bc->ifixt_node[i];
+        if (!chk(n)) return fail("ifixt_node out of range");
+        flag[n - 1] |= 8; tf[n - 1] = bc->rfixt_value[i];
+    }
+    vector<int32_t> bnode, bkind, bw;
+    vector<double> bvx, bvy, brho, bT;
+    for (int n = 0; n < P; ++n)
+        if (flag[n]) {
+            bnode.push_back(n); bkind.push_back(flag[n]); bw.push_back(wn_slot[n + 1]);
+            bvx.push_back(vx[n]); bvy.push_back(vy[n]); brho.push_back(rho[n]); bT.push_back(tf[n]);
+        }
+    c->nb = (int)bnode.size();
+    TRY(upload(c, c->bcflag, flag));
+    TRY(upload(c, c->bc_node, bnode)); TRY(upload(c, c->bc_kind, bkind)); TRY(upload(c, c->bc_wslot, bw));
+    TRY(upload(c, c->bc_vx, bvx)); TRY(upload(c, c->bc_vy, bvy)); TRY(upload(c, c->bc_rho, brho)); TRY(upload(c, c->bc_T, bT));
+    // mesh-motion lists: ilaux = [I_M; IFM] (dataLoader.f90:258-268), body sets grouped by id (:208-215)
+    c->nmove = bc->nmove;
+    c->nnmove = bc->nmove + bc->nfix_move;
+    c->h_ilaux.assign(bc->i_m, bc->i_m + bc->nmove);
+    c->h_ilaux.insert(c->h_ilaux.end(), bc->ifm, bc->ifm + bc->nfix_move);
+    for (int n : c->h_ilaux)
+        if (!chk(n)) return fail("I_M/IFM node out of range");
+    vector<int32_t> il0(c->h_ilaux), last;
+    topo::last_wins(c->h_ilaux.data(), c->nnmove, P, last);
+    for (auto& v : il0) v -= 1;
+    TRY(upload(c, c->ilaux, il0));
+    TRY(upload(c, c->ilaux_last, last));
+    int nset = 0;
+    for (int i = 0; i < bc->nsets; ++i) {
+        if (bc->iset_id[i] < 1 || bc->iset_id[i] > 10) return fail("set id out of range (1..10)");
+        nset = std::max(nset, bc->iset_id[i]);
+    }
+    c->nset = nset;
+    vector<int32_t> sptr((size_t)nset + 1, 0), n1, n2, se_node, se_set;
+    for (int s = 1; s <= nset; ++s) {
+        for (int i = 0; i < bc->nsets; ++i)
+            if (bc->iset_id[i] == s) {
+                n1.push_back(bc->iset_n1[i] - 1); n2.push_back(bc->iset_n2[i] - 1);
+                se_node.push_back(bc->iset_n1[i] - 1); se_set.push_back(s - 1);
+                se_node.push_back(bc->iset_n2[i] - 1); se_set.push_back(s - 1);
+            }
+        sptr[s] = (int)n1.size();
+    }
+    c->nse = (int)se_node.size();
+    c->ale = c->nse > 0;
+    TRY(upload(c, c->set_ptr, sptr)); TRY(upload(c, c->set_n1, n1)); TRY(upload(c, c->set_n2, n2));
+    TRY(upload(c, c->se_node, se_node)); TRY(upload(c, c->se_set, se_set));
+    return 0;
+}
+
+extern "C" int cfdb_create(cfdb_ctx** out, const cfdb_params* par, int32_t npoin, int32_t nelem, const double* X,
+                           const double* Y, const int32_t* inpoel, const cfdb_bc* bc, int device) {
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail("cfdb_create: no CUDA device available (libcfdb200 has no CPU path)");
+    if (device < 0 || device >= ndev) return fail("cfdb_create: bad device index");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail("cfdb_create: device is not sm_100 (this library is built for sm_100a only)");
+    if (npoin < 1 || nelem < 1) return fail("cfdb_create: empty mesh");
+    for (size_t k = 0; k < 3 * (size_t)nelem; ++k)
+        if (inpoel[k] < 1 || inpoel[k] > npoin) return fail("cfdb_create: inpoel entry out of range");
+    CK(cudaSetDevice(device));
+    cfdb_ctx* c = new cfdb_ctx();
+    c->device = device;
+    c->par = *par;
+    c->npoin = npoin;
+    c->nelem = nelem;
+    auto bail = [&](int r) { cfdb_destroy(c); return r; };
+    if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) return bail(fail("stream create failed"));
+    const size_t P = npoin, E = nelem;
+    c->h_inpoel.assign(inpoel, inpoel + 3 * E);
+    // topology
+    topo::build_esup(inpoel, nelem, npoin, c->esup1, c->esup2, &c->h_eslot);
+    topo::build_psup(inpoel, npoin, c->esup1, c->esup2, c->psup1, c->psup2);
+    topo::build_lap_pattern(npoin, c->psup1, c->psup2, c->lap_idx, c->lap_rowptr);
+    c->nnz = c->lap_rowptr[npoin];
+    vector<uint8_t> lpos;
+    topo::build_lap_pos(inpoel, npoin, c->esup1, c->esup2, c->lap_idx, c->lap_rowptr, lpos, c->maxrow);
+    if (c->maxrow > 32) return bail(fail("node valence above 31 is not supported"));
+    vector<int32_t> inp_soa(3 * E), idx0(c->lap_idx);
+    for (size_t e = 0; e < E; ++e)
+        for (int i = 0; i < 3; ++i) inp_soa[i * E + e] = inpoel[3 * e + i] - 1;
+    for (auto& v : idx0) v -= 1;
+#define B(x)                    \
+    do {                        \
+        int _r = (x);           \
+        if (_r) return bail(_r); \
+    } while (0)
+    B(upload(c, c->inp, inp_soa));
+    B(upload(c, c->d_esup2, c->esup2));
+    B(upload(c, c->eslot, c->h_eslot));
+    B(upload(c, c->d_lap_idx, idx0));
+    B(upload(c, c->d_lap_rowptr, c->lap_rowptr));
+    B(upload(c, c->lpos, lpos));
+    B(upload(c, c->X, X, P));
+    B(upload(c, c->Y, Y, P));
+    for (auto* d : {&c->X1, &c->Y1, &c->M, &c->VEL_X, &c->VEL_Y, &c->W_X, &c->W_Y, &c->P, &c->T, &c->RHO, &c->E, &c->RMACH,
+                    &c->GAMM, &c->lap_diag, &c->by, &c->bp, &c->br, &c->bz, &c->bb, &c->xpos, &c->ypos, &c->dxpos,
+                    &c->dypos, &c->pos_aux, &c->W_x_old, &c->W_y_old, &c->tmpA, &c->tmpB, &c->tmpC})
+        B(zero(c, *d, P));
+    for (auto* d : {&c->U, &c->U1, &c->RHS, &c->RHS1, &c->RHS2, &c->RHS3, &c->UN}) B(zero(c, *d, 4 * P));
+    for (auto* d : {&c->area, &c->HH, &c->HHX, &c->HHY, &c->SHOC, &c->TS1, &c->TS2, &c->TS3, &c->DT, &c->DTL, &c->area_old})
+        B(zero(c, *d, E));
+    B(zero(c, c->dNx, 3 * E));
+    B(zero(c, c->dNy, 3 * E));
+    B(zero(c, c->EC, 12 * E));
+    B(zero(c, c->lap_sparse, (size_t)c->nnz));
+    size_t nchunk = (std::max(P, E) + 4095) / 4096;
+    B(zero(c, c->redA, 8 * nchunk + 8));
+    B(zero(c, c->redB, 8 * ((nchunk + 4095) / 4096) + 8));
+    B(zero(c, c->flags, 4));
+    c->par.XREF[1] = 1.4;  // meshMove.f90:58 overwrites set 2's reference point before its first use
+    c->par.YREF[1] = 0.0;
+    B(upload(c, c->xref, c->par.XREF, 10));
+    B(upload(c, c->yref, c->par.YREF, 10));
+    B(build_bc_tables(c, bc));
+    if (c->ale) B(zero(c, c->FC, 12 * E));
+    if (cudaMalloc(&c->sc, sizeof(k::Scal)) != cudaSuccess) return bail(fail("cudaMalloc Scal failed"));
+    if (cudaMemsetAsync(c->sc, 0, sizeof(k::Scal), c->st) != cudaSuccess) return bail(fail("memset Scal failed"));
+    if (cudaMallocHost(&c->h_sc, sizeof(k::Scal)) != cudaSuccess) return bail(fail("cudaMallocHost failed"));
+    if (cudaStreamSynchronize(c->st) != cudaSuccess) return bail(fail("sync after create failed"));
+#undef B
+    *out = c;
+    return 0;
+}
+
+extern "C" void cfdb_destroy(cfdb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->st) cudaStreamSynchronize(c->st);
+    for (auto* d : {&c->inp, &c->d_esup2, &c->eslot, &c->d_lap_idx, &c->d_lap_rowptr, &c->wall, &c->wn_node, &c->wn_ptr,
+                    &c->wn_edge, &c->wn_valid, &c->bc_node, &c->bc_kind, &c->bc_wslot, &c->ilaux, &c->ilaux_last, &c->se_node,
+                    &c->se_set, &c->set_ptr, &c->set_n1, &c->set_n2, &c->flags})
+        d->release();
+    c->lpos.release();
+    c->bcflag.release();
+    for (auto* d : {&c->X, &c->Y, &c->X1, &c->Y1, &c->area, &c->HH, &c->HHX, &c->HHY, &c->dNx, &c->dNy, &c->M, &c->U, &c->U1,
+                    &c->RHS, &c->RHS1, &c->RHS2, &c->RHS3, &c->UN, &c->VEL_X, &c->VEL_Y, &c->W_X, &c->W_Y, &c->P, &c->T,
+                    &c->RHO, &c->E, &c->RMACH, &c->GAMM, &c->SHOC, &c->TS1, &c->TS2, &c->TS3, &c->DT, &c->DTL, &c->EC, &c->FC,
+                    &c->bc_vx, &c->bc_vy, &c->bc_rho, &c->bc_T, &c->wn_x, &c->wn_y, &c->lap_sparse, &c->lap_diag, &c->by,
+                    &c->bp, &c->br, &c->bz, &c->bb, &c->xpos, &c->ypos, &c->dxpos, &c->dypos, &c->pos_aux, &c->xref, &c->yref,
+                    &c->W_x_old, &c->W_y_old, &c->area_old, &c->redA, &c->redB, &c->tmpA, &c->tmpB, &c->tmpC})
+        d->release();
+    for (auto& p : c->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (auto e : c->evpool) cudaEventDestroy(e);
+    if (c->sc) cudaFree(c->sc);
+    if (c->h_sc) cudaFreeHost(c->h_sc);
+    if (c->st) cudaStreamDestroy(c->st);
+    delete c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// canonical reduction of nv vectors whose first-level chunk sums are in redA laid out [v][m]
+static int reduce_levels(cfdb_ctx* c, int nv, long m, int slot) {
+    double* in = c->redA.p;
+    double* outb = c->redB.p;
+    while (m > 1) {
+        long m2 = (m + 4095) / 4096;
+        for (int v = 0; v < nv; ++v)
+            LAUNCH(K_DOT, k::dot_chunks, (int)std::min<long>(m2, 1024), 256, m, in + v * m, (const double*)nullptr, outb + v * m2);
+        std::swap(in, outb);
+        m = m2;
+    }
+    CK(cudaMemcpyAsync(&c->sc->red[slot], in, nv * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+    return 0;
+}
+static int dev_dot(cfdb_ctx* c, long n, const double* x, const double* y, int slot) {
+    long m = (n + 4095) / 4096;
+    LAUNCH(K_DOT, k::dot_chunks, (int)std::min<long>(m, 148 * 8), 256, n, x, y, c->redA.p);
+    return reduce_levels(c, 1, m, slot);
+}
+
+static int read_scal(cfdb_ctx* c) {
+    CK(cudaMemcpyAsync(c->h_sc, c->sc, sizeof(k::Scal), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int run_normales(cfdb_ctx* c) {
+    if (c->nwn)
+        LAUNCH(K_NORMALES, k::normales, grid_for(c->nwn, 128), 128, c->nwn, c->wn_node.p, c->wn_ptr.p, c->wn_edge.p,
+               c->wall.p, c->X.p, c->Y.p, c->wn_x.p, c->wn_y.p, c->wn_valid.p);
+    return 0;
+}
+static int run_deriv(cfdb_ctx* c) {
+    LAUNCH(K_SCALAR, k::set_double, 1, 1, &c->sc->HMIN, (double)INFINITY);
+    LAUNCH(K_DERIV, k::deriv, grid_for(c->nelem, 256), 256, c->nelem, c->inp.p, c->X.p, c->Y.p, c->area.p, c->HH.p,
+           c->HHX.p, c->HHY.p, c->dNx.p, c->dNy.p, c->sc);
+    return 0;
+}
+static int run_masas(cfdb_ctx* c) {
+    LAUNCH(K_MASAS, k::masas, grid_for(c->npoin, 256), 256, c->npoin, c->d_esup2.p, c->eslot.p, c->area.p, c->M.p);
+    return 0;
+}
+static int run_laplace(cfdb_ctx* c) {
+    if (c->maxrow <= 12)
+        LAUNCH(K_LAPLACE, k::laplace<12>, grid_for(c->npoin, 128), 128, c->npoin, c->nelem, c->d_esup2.p, c->eslot.p,
+               c->lpos.p, c->inp.p, c->dNx.p, c->dNy.p, c->X.p, c->Y.p, c->d_lap_rowptr.p, c->lap_sparse.p,
+               c->lap_diag.p, c->flags.p);
+    else
+        LAUNCH(K_LAPLACE, k::laplace<32>, grid_for(c->npoin, 128), 128, c->npoin, c->nelem, c->d_esup2.p, c->eslot.p,
+               c->lpos.p, c->inp.p, c->dNx.p, c->dNy.p, c->X.p, c->Y.p, c->d_lap_rowptr.p, c->lap_sparse.p,
+               c->lap_diag.p, c->flags.p);
+    return 0;
+}
+static int run_gcl(cfdb_ctx* c, const double* dt_dev, double dt_const) {
+    LAUNCH(K_GCL, k::gcl, grid_for(c->npoin, 256), 256, c->npoin, c->nelem, c->d_esup2.p, c->eslot.p, c->inp.p, c->dNx.p,
+           c->dNy.p, c->area.p, c->area_old.p, c->W_X.p, c->W_x_old.p, dt_const, dt_dev, c->M.p);
+    return 0;
+}
+
+extern "C" int cfdb_geometry(cfdb_ctx* c, int32_t moving_step) {
+    CK(cudaSetDevice(c->device));
+    const size_t P = c->npoin, E = c->nelem;
+    bool gcl = moving_step && c->par.use_gcl;
+    if (gcl) CK(cudaMemcpyAsync(c->area_old.p, c->area.p, E * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+    TRY(run_normales(c));
+    TRY(run_deriv(c));
+    TRY(run_masas(c));
+    if (gcl) {
+        TRY(run_gcl(c, &c->sc->DTMIN, 0.0));
+        CK(cudaMemcpyAsync(c->W_x_old.p, c->W_X.p, P * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+        CK(cudaMemcpyAsync(c->W_y_old.p, c->W_Y.p, P * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+    }
+    TRY(run_laplace(c));
+    return 0;
+}
+
+extern "C" int cfdb_init(cfdb_ctx* c) {
+    CK(cudaSetDevice(c->device));
+    const cfdb_params& p = c->par;
+    const size_t P = c->npoin;
+    // GAMM = GAMA (ns2DComp.ALE.f90:59); RESTART free-stream branch (:408-420), evaluated on the host in
+    // the reference's order — every node gets the same five numbers
+    double RHOAMB = p.RHO_inf, TAMB = p.T_inf, UAMB = p.U_inf, VAMB = p.V_inf, PAMB = p.RHO_inf * p.FR * p.T_inf;
+    double ENERGIA = PAMB / ((p.GAMA - 1.0) * RHOAMB) + .5 * (UAMB * UAMB + VAMB * VAMB);
+    vector<double> u(4 * P);
+    for (size_t i = 0; i < P; ++i) {
+        u[4 * i] = RHOAMB; u[4 * i + 1] = RHOAMB * UAMB; u[4 * i + 2] = RHOAMB * VAMB; u[4 * i + 3] = ENERGIA * RHOAMB;
+    }
+    TRY(upload(c, c->U, u));
+    LAUNCH(K_FILL, k::fill_const, grid_for(P, 256), 256, (long)P, c->GAMM.p, p.GAMA);
+    LAUNCH(K_FILL, k::fill_const, grid_for(P, 256), 256, (long)P, c->VEL_X.p, UAMB);
+    LAUNCH(K_FILL, k::fill_const, grid_for(P, 256), 256, (long)P, c->VEL_Y.p, VAMB);
+    LAUNCH(K_FILL, k::fill_const, grid_for(P, 256), 256, (long)P, c->T.p, TAMB);
+    LAUNCH(K_FILL, k::fill_const, grid_for(P, 256), 256, (long)P, c->W_X.p, -0.0);  // :121
+    LAUNCH(K_FILL, k::fill_const, grid_for(P, 256), 256, (long)P, c->W_Y.p, 0.0);
+    CK(cudaMemsetAsync(c->sc, 0, sizeof(k::Scal), c->st));
+    LAUNCH(K_SCALAR, k::bandera_inc, 1, 1, c->sc);  // BANDERA = 1 (ns2DComp.ALE.f90:133)
+    TRY(cfdb_geometry(c, 0));
+    CK(cudaMemcpyAsync(c->W_x_old.p, c->W_X.p, P * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+    CK(cudaMemcpyAsync(c->W_y_old.p, c->W_Y.p, P * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+    CK(cudaMemcpyAsync(c->area_old.p, c->area.p, c->nelem * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+    c->h_iter = 0;
+    c->iterprint = 0;
+    c->DISN[0] = c->DISN[1] = 0.0;
+    c->theta_nonzero = false;
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+static k::BcTab bctab(cfdb_ctx* c) {
+    k::BcTab b;
+    b.nb = c->nb; b.node = c->bc_node.p; b.kind = c->bc_kind.p; b.vx = c->bc_vx.p; b.vy = c->bc_vy.p;
+    b.rho = c->bc_rho.p; b.Tfix = c->bc_T.p; b.wslot = c->bc_wslot.p; b.wn_x = c->wn_x.p; b.wn_y = c->wn_y.p;
+    b.wn_valid = c->wn_valid.p;
+    return b;
+}
+
+static int run_estab(cfdb_ctx* c, const double* dtmin_dev) {
+    const cfdb_params& p = c->par;
+    LAUNCH(K_ESTAB, k::estab, grid_for(c->nelem, 256), 256, c->nelem, c->inp.p, c->U.p, c->T.p, c->VEL_X.p, c->VEL_Y.p,
+           c->W_X.p, c->W_Y.p, c->GAMM.p, c->dNx.p, c->dNy.p, p.FR, dtmin_dev, p.RHO_inf, p.T_inf, c->SHOC.p, c->TS1.p,
+           c->TS2.p, c->TS3.p);
+    return 0;
+}
+
+// calcRHS (+FUENTE when `ale`) into the staging buffers
+static int run_calcrhs_elem(cfdb_ctx* c, const k::Gas& g, bool theta, bool ale, const double* dtl_arr, const double* dtl_sc) {
+    const bool visc = g.mu_ref > 2.2250738585072014e-308;  // tiny(0d0), calcRHS.f90:119
+    const int B = 128, G = grid_for(c->nelem, B);
+#define ARGS c->nelem, c->inp.p, c->U.p, c->UN.p, c->T.p, c->W_X.p, c->W_Y.p, c->dNx.p, c->dNy.p, c->area.p, c->SHOC.p, \
+             dtl_arr, dtl_sc, c->TS1.p, c->TS2.p, c->TS3.p, g, c->EC.p, c->FC.p
+    int sel = (visc ? 4 : 0) | (theta ? 2 : 0) | (ale ? 1 : 0);
+    auto kern = k::calcrhs_elem<false, false, false>;
+    switch (sel) {
+        case 0: kern = k::calcrhs_elem<false, false, false>; break;
+        case 1: kern = k::calcrhs_elem<false, false, true>; break;
+        case 2: kern = k::calcrhs_elem<false, true, false>; break;
+        case 3: kern = k::calcrhs_elem<false, true, true>; break;
+        case 4: kern = k::calcrhs_elem<true, false, false>; break;
+        case 5: kern = k::calcrhs_elem<true, false, true>; break;
+        case 6: kern = k::calcrhs_elem<true, true, false>; break;
+        default: kern = k::calcrhs_elem<true, true, true>; break;
+    }
+    LAUNCH(K_CALCRHS, kern, G, B, ARGS);
+#undef ARGS
+    return 0;
+}
+
+static int run_node(cfdb_ctx* c, bool ale, bool update, double rk_fact) {
+    const int B = 256, G = grid_for(c->npoin, B);
+#define ARGS c->npoin, c->d_esup2.p, c->eslot.p, c->EC.p, c->FC.p, c->U.p, c->M.p, c->GAMM.p, c->W_X.p, c->W_Y.p, \
+             c->bcflag.p, bctab(c), rk_fact, c->par.FR, c->U1.p, c->RHS.p, c->RHO.p, c->VEL_X.p, c->VEL_Y.p, c->E.p, \
+             c->P.p, c->T.p, c->RMACH.p
+    auto kern = k::node_update<false, true>;
+    if (ale && update) kern = k::node_update<true, true>;
+    else if (ale) kern = k::node_update<true, false>;
+    else if (!update) kern = k::node_update<false, false>;
+    LAUNCH(K_NODE, kern, G, B, ARGS);
+#undef ARGS
+    return 0;
+}
+
+extern "C" int cfdb_rk_stage(cfdb_ctx* c, int32_t irk) {
+    CK(cudaSetDevice(c->device));
+    const cfdb_params& p = c->par;
+    const int NRK = 4;
+    if (irk < 1 || irk > NRK) return fail("cfdb_rk_stage: irk must be 1..4");
+    double RK_FACT = 1.0 / (NRK + 1 - irk);
+    if (irk == 1) {
+        // cuarto_orden's projection is discarded by UN = 0.0 (subrutinas.f90:673-674)
+        if (c->theta_nonzero) {
+            CK(cudaMemsetAsync(c->UN.p, 0, 4 * (size_t)c->npoin * sizeof(double), c->st));
+            c->theta_nonzero = false;
+        }
+        TRY(run_estab(c, &c->sc->DTMIN));
+    }
+    c->u1_is_u = false;
+    k::Gas g{p.FCv, p.FK, p.FMU, p.GAMA, p.T_inf, p.CTE};
+    const double* dtl_arr = p.ITLOCAL != 0 ? c->DTL.p : nullptr;
+    TRY(run_calcrhs_elem(c, g, false, c->ale, dtl_arr, &c->sc->DTMIN));
+    TRY(run_node(c, c->ale, true, RK_FACT));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// biCG on device arrays (biconjGrad.f90:8-62); host loop control reads err back once per iteration
+static int bicg_dev(cfdb_ctx* c, const double* A, const int* idx, const int* rowptr, const double* diag, double* x,
+                    const double* b, const double* x_fix, const int* fixIdx, const int* fixLast, int npoin, int nfix,
+                    int* iters) {
+    const int B = 256, G = grid_for(npoin, B), GF = grid_for(std::max(nfix, 1), 128);
+    const double tol = 1.e-10;
+    double *y = c->by.p, *p = c->bp.p, *r = c->br.p, *z = c->bz.p;
+    if (nfix) LAUNCH(K_FIXROWS, k::copy1, GF, 128, nfix, fixIdx, fixLast, 1.0, x_fix, x);
+    LAUNCH(K_SPMV, k::spmv, G, B, npoin, A, idx, rowptr, x, y);
+    if (nfix) LAUNCH(K_FIXROWS, k::copy2, GF, 128, nfix, fixIdx, 1.e30, x, y);
+    LAUNCH(K_VEC, k::vecsum, G, B, npoin, (int)k::ALFA_CONST, -1.0, c->sc, y, b, r);
+    if (nfix) LAUNCH(K_FIXROWS, k::assign2, GF, 128, nfix, fixIdx, 0.0, r);
+    TRY(dev_dot(c, npoin, r, r, 0));
+    LAUNCH(K_SCALAR, k::bicg_scalar, 1, 1, c->sc, (int)k::SC_RR, 0);
+    TRY(read_scal(c));
+    if (c->h_sc->rr < tol) { *iters = -1; return 0; }
+    LAUNCH(K_VEC, k::vecdiv, G, B, npoin, r, diag, p);
+    TRY(dev_dot(c, npoin, r, p, 0));
+    LAUNCH(K_SCALAR, k::bicg_scalar, 1, 1, c->sc, (int)k::SC_ERRNEW, 0);
+    LAUNCH(K_SPMV, k::spmv, G, B, npoin, A, idx, rowptr, p, y);
+    if (nfix) LAUNCH(K_FIXROWS, k::copy2, GF, 128, nfix, fixIdx, 1.e30, p, y);
+    TRY(dev_dot(c, npoin, p, y, 1));
+    LAUNCH(K_SCALAR, k::bicg_scalar, 1, 1, c->sc, (int)k::SC_PY_ALFA, 1);
+    LAUNCH(K_VEC, k::vecsum, G, B, npoin, (int)k::ALFA_POS, 0.0, c->sc, p, x, x);
+    TRY(read_scal(c));
+    double err_old = c->h_sc->err_old;
+    int kk = 0;
+    while (std::fabs(err_old) > tol && kk < 1000) {
+        kk++;
+        LAUNCH(K_VEC, k::vecsum, G, B, npoin, (int)k::ALFA_NEG, 0.0, c->sc, y, r, r);
+        LAUNCH(K_VEC, k::vecdiv, G, B, npoin, r, diag, z);
+        TRY(dev_dot(c, npoin, r, z, 0));
+        LAUNCH(K_SCALAR, k::bicg_scalar, 1, 1, c->sc, (int)k::SC_BETA, 0);
+        LAUNCH(K_VEC, k::vecsum, G, B, npoin, (int)k::BETA_POS, 0.0, c->sc, p, z, p);
+        LAUNCH(K_SPMV, k::spmv, G, B, npoin, A, idx, rowptr, p, y);
+        if (nfix) LAUNCH(K_FIXROWS, k::copy2, GF, 128, nfix, fixIdx, 1.e30, p, y);
+        TRY(dev_dot(c, npoin, p, y, 1));
+        LAUNCH(K_SCALAR, k::bicg_scalar, 1, 1, c->sc, (int)k::SC_PY_ALFA, 1);
+        LAUNCH(K_VEC, k::vecsum, G, B, npoin, (int)k::ALFA_POS, 0.0, c->sc, p, x, x);
+        TRY(read_scal(c));
+        err_old = c->h_sc->err_old;
+    }
+    *iters = kk;
+    return 0;
+}
+
+extern "C" int cfdb_fluid_structure(cfdb_ctx* c, double dtmin, double time) {
+    CK(cudaSetDevice(c->device));
+    const int P = c->npoin;
+    (void)dtmin;  // W = XPOS/DTMIN uses the device-resident DTMIN (same value)
+    CK(cudaMemsetAsync(c->dxpos.p, 0, P * sizeof(double), c->st));
+    CK(cudaMemsetAsync(c->dypos.p, 0, P * sizeof(double), c->st));
+    // XREF(2)=1.4, YREF(2)=0 are overwritten on every call (meshMove.f90:58): applied once in cfdb_create
+    if (c->nset)
+        LAUNCH(K_FORCES, k::forces, 1, 32, c->nset, c->set_ptr.p, c->set_n1.p, c->set_n2.p, c->X.p, c->Y.p, c->P.p,
+               c->xref.p, c->yref.p, c->sc);
+    double PI = std::acos(-1.0);
+    double AMPLI = PI / 8.0;
+    double ALPHAV = c->DISN[1], YPOSRV = c->DISN[0];
+    c->DISN[1] = AMPLI * std::sin(10.0 * time);  // :70
+    double ALPHA = c->DISN[1] - ALPHAV, YPOSR = c->DISN[0] - YPOSRV;
+    if (c->nse)
+        LAUNCH(K_TRANSF, k::transf, grid_for(c->nse, 128), 128, c->nse, c->se_node.p, c->se_set.p, std::cos(ALPHA),
+               std::sin(ALPHA), YPOSR, c->xref.p, c->yref.p, c->X.p, c->Y.p, c->dxpos.p, c->dypos.p);
+    for (int dir = 0; dir < 2; ++dir) {
+        double* dpos = dir ? c->dypos.p : c->dxpos.p;
+        double* pos = dir ? c->ypos.p : c->xpos.p;
+        if (c->nnmove)
+            LAUNCH(K_MOVE, k::pos_aux_fill, grid_for(c->nnmove, 128), 128, c->nmove, c->nnmove, c->ilaux.p, dpos, c->pos_aux.p);
+        CK(cudaMemsetAsync(c->bb.p, 0, P * sizeof(double), c->st));
+        TRY(bicg_dev(c, c->lap_sparse.p, c->d_lap_idx.p, c->d_lap_rowptr.p, c->lap_diag.p, pos, c->bb.p, c->pos_aux.p,
+                     c->ilaux.p, c->ilaux_last.p, P, c->nnmove, &c->bicg_iters[dir]));
+        LAUNCH(K_MOVE, k::move_apply, grid_for(P, 256), 256, P, pos, &c->sc->DTMIN, dir ? c->Y.p : c->X.p,
+               dir ? c->Y1.p : c->X1.p, dir ? c->W_Y.p : c->W_X.p);
+    }
+    return 0;
+}
+
+static int run_norms(cfdb_ctx* c) {
+    long m = ((long)c->npoin + 4095) / 4096;
+    LAUNCH(K_NORMS, k::norm_chunks, (int)std::min<long>(m, 148 * 8), 256, (long)c->npoin, c->U.p,
+           c->u1_is_u ? c->U.p : c->U1.p, c->redA.p);
+    TRY(reduce_levels(c, 8, m, 0));
+    CK(cudaMemcpyAsync(c->sc->ER, c->sc->red, 8 * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+    return 0;
+}
+extern "C" int cfdb_residual_norms(cfdb_ctx* c, double er[4], double err[4]) {
+    CK(cudaSetDevice(c->device));
+    TRY(run_norms(c));
+    TRY(read_scal(c));
+    for (int i = 0; i < 4; ++i) { er[i] = c->h_sc->ER[i]; err[i] = c->h_sc->ERR[i]; }
+    return 0;
+}
+
+// one pass of ns2DComp.ALE.f90:138-282
+static int step_once(cfdb_ctx* c) {
+    const cfdb_params& p = c->par;
+    const int E = c->nelem;
+    const size_t P = c->npoin;
+    c->h_iter += 1;
+    LAUNCH(K_DTLOGIC, k::step_begin, 1, 1, c->sc);
+    if (p.ITLOCAL != 0)
+        LAUNCH(K_DELTAT, k::deltat<true>, grid_for(E, 256), 256, E, c->inp.p, c->area.p, c->T.p, c->VEL_X.p, c->VEL_Y.p,
+               c->W_X.p, c->W_Y.p, p.FSAFE, p.T_inf, c->DT.p, c->sc);
+    else
+        LAUNCH(K_DELTAT, k::deltat<false>, grid_for(E, 256), 256, E, c->inp.p, c->area.p, c->T.p, c->VEL_X.p, c->VEL_Y.p,
+               c->W_X.p, c->W_Y.p, p.FSAFE, p.T_inf, c->DT.p, c->sc);
+    LAUNCH(K_DTLOGIC, k::dt_logic, 1, 1, c->sc);
+    if (p.ITLOCAL != 0) {
+        double DTFACT = 1.0 - std::exp(-c->h_iter * 4.6 / p.ITLOCAL);  // :160
+        LAUNCH(K_SCALAR, k::set_double, 1, 1, &c->sc->dtfact, DTFACT);
+        LAUNCH(K_DTL, k::dtl_blend, grid_for(E, 256), 256, E, c->DT.p, c->DTL.p, c->sc, 1);
+    }
+    // U1 = U (:168-172) is dead: every RK stage overwrites U1 from U (subrutinas.f90:697)
+    for (int irk = 1; irk <= 4; ++irk) TRY(cfdb_rk_stage(c, irk));
+    // RHS history copies for BANDERA 2..4 (subrutinas.f90:830-848); BANDERA lives on the device, the kernel
+    // exits at once for any other value
+    LAUNCH(K_FILL, k::rhs_history, grid_for(4 * (long)P, 256), 256, 4 * (long)P, c->sc, c->RHS.p, c->RHS1.p, c->RHS2.p, c->RHS3.p);
+    double dtmin = 0.0, time = 0.0;
+    if (c->nse) {  // pitching law needs TIME on the host (meshMove.f90:70)
+        TRY(read_scal(c));
+        dtmin = c->h_sc->DTMIN;
+        time = c->h_sc->TIME;
+    }
+    TRY(cfdb_fluid_structure(c, dtmin, time));
+    c->iterprint += 1;
+    if (c->iterprint == p.IPRINT || c->h_iter == p.MAXITER) {  // :186-197
+        TRY(run_norms(c));
+        c->iterprint = 0;
+    }
+    LAUNCH(K_SCALAR, k::bandera_inc, 1, 1, c->sc);
+    if (p.MOVING == 1) TRY(cfdb_geometry(c, 1));
+    // U = U1 (:277-281): swap the buffers instead of copying
+    std::swap(c->U.p, c->U1.p);
+    c->u1_is_u = true;
+    (void)P;
+    return 0;
+}
+
+extern "C" int cfdb_step(cfdb_ctx* c, int32_t nsteps) {
+    CK(cudaSetDevice(c->device));
+    for (int i = 0; i < nsteps; ++i) TRY(step_once(c));
+    return 0;
+}
+extern "C" int cfdb_sync(cfdb_ctx* c) {
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->st));
+    TRY(prof_resolve(c));
+    return 0;
+}
+extern "C" void* cfdb_stream(cfdb_ctx* c) { return (void*)c->st; }
+extern "C" int cfdb_profile_enable(cfdb_ctx* c, int32_t on) {
+    TRY(prof_resolve(c));
+    c->prof = on != 0;
+    if (on) {
+        for (int i = 0; i < K_COUNT; ++i) { c->prof_ms[i] = 0; c->prof_n[i] = 0; }
+    }
+    return 0;
+}
+extern "C" int cfdb_profile_get(cfdb_ctx* c, const char* kernel, double* total_ms, int64_t* launches) {
+    TRY(prof_resolve(c));
+    for (int i = 0; i < K_COUNT; ++i)
+        if (!strcmp(kernel, kKernelNames[i])) {
+            *total_ms = c->prof_ms[i];
+            *launches = c->prof_n[i];
+            return 0;
+        }
+    return fail(std::string("unknown kernel name ") + kernel);
+}
+extern "C" int64_t cfdb_launch_count(cfdb_ctx* c) { return c->launches; }
+
+// ---------------------------------------------------------------------------------------------
+// field access
+struct Field {
+    void* dev = nullptr;          // device pointer (doubles or ints)
+    const void* host = nullptr;   // or host-resident integer artefact
+    int64_t count = 0;
+    int kind = 0;                 // 0 f64 plain, 1 f64 (3,E) stored [3][E], 2 int32 host (read-only), 3 computed
+};
+static bool find_field(cfdb_ctx* c, const std::string& n, Field& f) {
+    const int64_t P = c->npoin, E = c->nelem;
+#define FD(name, buf, cnt) if (n == name) { f.dev = c->buf.p; f.count = (cnt); f.kind = 0; return true; }
+#define FS(name, buf) if (n == name) { f.dev = c->buf.p; f.count = 3 * E; f.kind = 1; return true; }
+#define FH(name, vec) if (n == name) { f.host = c->vec.data(); f.count = (int64_t)c->vec.size(); f.kind = 2; return true; }
+    FD("X", X, P) FD("Y", Y, P) FD("X1", X1, P) FD("Y1", Y1, P) FD("M", M, P) FD("area", area, E) FD("HH", HH, E)
+    FD("HHX", HHX, E) FD("HHY", HHY, E) FS("dNx", dNx) FS("dNy", dNy)
+    FD("U", U, 4 * P) FD("U1", U1, 4 * P) FD("RHS", RHS, 4 * P) FD("UN", UN, 4 * P)
+    FD("RHS1", RHS1, 4 * P) FD("RHS2", RHS2, 4 * P) FD("RHS3", RHS3, 4 * P)
+    FD("VEL_X", VEL_X, P) FD("VEL_Y", VEL_Y, P) FD("W_X", W_X, P) FD("W_Y", W_Y, P) FD("P", P, P) FD("T", T, P)
+    FD("RHO", RHO, P) FD("E", E, P) FD("RMACH", RMACH, P) FD("GAMM", GAMM, P)
+    FD("SHOC", SHOC, E) FD("T_SUGN1", TS1, E) FD("T_SUGN2", TS2, E) FD("T_SUGN3", TS3, E) FD("DT", DT, E)
+    FD("lap_sparse", lap_sparse, c->nnz) FD("lap_diag", lap_diag, P) FD("xpos", xpos, P) FD("ypos", ypos, P)
+    FD("dxpos", dxpos, P) FD("dypos", dypos, P) FD("W_x_old", W_x_old, P) FD("W_y_old", W_y_old, P)
+    FD("area_old", area_old, E) FD("EC", EC, 12 * E)
+    FH("inpoel", h_inpoel) FH("esup1", esup1) FH("esup2", esup2) FH("psup1", psup1) FH("psup2", psup2)
+    FH("lap_idx", lap_idx) FH("lap_rowptr", lap_rowptr) FH("ilaux", h_ilaux)
+#undef FD
+#undef FS
+#undef FH
+    if (n == "DTL") { f.count = E; f.kind = 3; return true; }
+    if (n == "n_ipoin" || n == "n_x" || n == "n_y") { f.count = c->nwn; f.kind = 3; return true; }
+    return false;
+}
+extern "C" int64_t cfdb_field_size(cfdb_ctx* c, const char* name) {
+    Field f;
+    if (!find_field(c, name, f)) return -1;
+    return f.count;
+}
+extern "C" int cfdb_get(cfdb_ctx* c, const char* name, void* host, int64_t count) {
+    CK(cudaSetDevice(c->device));
+    Field f;
+    std::string n(name);
+    if (!find_field(c, n, f)) return fail("cfdb_get: unknown field " + n);
+    if (n == "U1" && c->u1_is_u) f.dev = c->U.p;
+    if (count < f.count && f.kind != 3) return fail("cfdb_get: host buffer too small for " + n);
+    if (f.kind == 2) {
+        memcpy(host, f.host, f.count * sizeof(int32_t));
+        return 0;
+    }
+    if (f.kind == 0) {
+        if (f.count) CK(cudaMemcpyAsync(host, f.dev, f.count * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        return 0;
+    }
+    if (f.kind == 1) {
+        const int64_t E = c->nelem;
+        vector<double> tmp(3 * E);
+        CK(cudaMemcpyAsync(tmp.data(), f.dev, 3 * E * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        double* o = (double*)host;
+        for (int64_t e = 0; e < E; ++e)
+            for (int i = 0; i < 3; ++i) o[3 * e + i] = tmp[i * E + e];
+        return 0;
+    }
+    if (n == "DTL") {  // ns2DComp.ALE.f90:159-164
+        if (count < c->nelem) return fail("cfdb_get: host buffer too small for DTL");
+        if (c->par.ITLOCAL != 0) {
+            CK(cudaMemcpyAsync(host, c->DTL.p, c->nelem * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+            CK(cudaStreamSynchronize(c->st));
+        } else {
+            TRY(read_scal(c));
+            for (int e = 0; e < c->nelem; ++e) ((double*)host)[e] = c->h_sc->DTMIN;
+        }
+        return 0;
+    }
+    // compacted normals list in ascending node order (subrutinas.f90:51-63); count returned via n_m scalar
+    vector<double> wx(c->nwn), wy(c->nwn);
+    vector<int> wv(c->nwn);
+    if (c->nwn) {
+        CK(cudaMemcpyAsync(wx.data(), c->wn_x.p, c->nwn * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaMemcpyAsync(wy.data(), c->wn_y.p, c->nwn * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaMemcpyAsync(wv.data(), c->wn_valid.p, c->nwn * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    }
+    CK(cudaStreamSynchronize(c->st));
+    int m = 0;
+    for (int j = 0; j < c->nwn; ++j)
+        if (wv[j]) {
+            if (m >= count) return fail("cfdb_get: host buffer too small for " + n);
+            if (n == "n_ipoin") ((int32_t*)host)[m] = c->h_wn_node[j] + 1;
+            else if (n == "n_x") ((double*)host)[m] = wx[j];
+            else ((double*)host)[m] = wy[j];
+            ++m;
+        }
+    return 0;
+}
+extern "C" int cfdb_set(cfdb_ctx* c, const char* name, const void* host, int64_t count) {
+    CK(cudaSetDevice(c->device));
+    Field f;
+    std::string n(name);
+    if (!find_field(c, n, f)) return fail("cfdb_set: unknown field " + n);
+    if (f.kind >= 2) return fail("cfdb_set: field " + n + " is read-only");
+    if (count != f.count) return fail("cfdb_set: wrong element count for " + n);
+    if (f.kind == 0) {
+        if (f.count) CK(cudaMemcpyAsync(f.dev, host, f.count * sizeof(double), cudaMemcpyHostToDevice, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        if (n == "UN") c->theta_nonzero = true;
+        if (n == "U" && c->u1_is_u) {  // keep U1 == U as in the reference
+            CK(cudaMemcpyAsync(c->U1.p, c->U.p, f.count * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+            CK(cudaStreamSynchronize(c->st));
+        }
+        if (n == "W_X" || n == "W_Y") {
+            if (!c->ale) { c->ale = true; TRY(zero(c, c->FC, 12 * (size_t)c->nelem)); }
+        }
+        return 0;
+    }
+    const int64_t E = c->nelem;
+    vector<double> tmp(3 * E);
+    const double* in = (const double*)host;
+    for (int64_t e = 0; e < E; ++e)
+        for (int i = 0; i < 3; ++i) tmp[i * E + e] = in[3 * e + i];
+    CK(cudaMemcpyAsync(f.dev, tmp.data(), 3 * E * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+extern "C" int cfdb_get_scalar(cfdb_ctx* c, const char* name, double* v) {
+    CK(cudaSetDevice(c->device));
+    TRY(read_scal(c));
+    std::string n(name);
+    const k::Scal& s = *c->h_sc;
+    if (n == "TIME") *v = s.TIME;
+    else if (n == "DTMIN") *v = s.DTMIN;
+    else if (n == "DTMIN1") *v = s.DTMIN1;
+    else if (n == "HMIN") *v = s.HMIN > 1.e10 ? 1.e10 : s.HMIN;  // subrutinas.f90:125
+    else if (n == "ITER") *v = s.ITER;
+    else if (n == "BANDERA") *v = s.BANDERA;
+    else if (n == "bicg_x") *v = c->bicg_iters[0];
+    else if (n == "bicg_y") *v = c->bicg_iters[1];
+    else if (n == "FX1") *v = s.FX[0];
+    else if (n == "FY1") *v = s.FY[0];
+    else if (n == "RM1") *v = s.RM[0];
+    else if (n == "n_m") {
+        vector<int> wv(c->nwn);
+        if (c->nwn) CK(cudaMemcpy(wv.data(), c->wn_valid.p, c->nwn * sizeof(int), cudaMemcpyDeviceToHost));
+        int m = 0;
+        for (int x : wv) m += x;
+        *v = m;
+    } else return fail("cfdb_get_scalar: unknown scalar " + n);
+    return 0;
+}
+extern "C" int cfdb_set_scalar(cfdb_ctx* c, const char* name, double v) {
+    CK(cudaSetDevice(c->device));
+    TRY(read_scal(c));
+    std::string n(name);
+    k::Scal& s = *c->h_sc;
+    if (n == "TIME") s.TIME = v;
+    else if (n == "DTMIN") s.DTMIN = v;
+    else if (n == "DTMIN1") s.DTMIN1 = v;
+    else if (n == "ITER") { s.ITER = (int)v; c->h_iter = (int)v; }
+    else if (n == "BANDERA") s.BANDERA = (int)v;
+    else return fail("cfdb_set_scalar: unknown scalar " + n);
+    CK(cudaMemcpyAsync(c->sc, c->h_sc, sizeof(k::Scal), cudaMemcpyHostToDevice, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// (i) call-site mode
+static int check_mesh(cfdb_ctx* c, int32_t nelem, int32_t npoin, const char* who) {
+    if (nelem != c->nelem || npoin != c->npoin)
+        return fail(std::string(who) + ": nelem/npoin differ from the connectivity this context was created with");
+    return 0;
+}
+static int up_plain(cfdb_ctx* c, double* dev, const double* h, size_t n) {
+    if (n) CK(cudaMemcpyAsync(dev, h, n * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    return 0;
+}
+static int up_soa3(cfdb_ctx* c, double* dev, const double* h) {  // (3,E) host -> [3][E] device, via tmp staging
+    const long E = c->nelem;
+    TRY(c->EC.alloc(12 * (size_t)E));
+    double* stage = c->EC.p;  // EC is free between calls
+    CK(cudaMemcpyAsync(stage, h, 3 * E * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    LAUNCH(K_LAYOUT, k::aos3_to_soa, grid_for(3 * E, 256), 256, E, stage, dev);
+    return 0;
+}
+static int down_soa3(cfdb_ctx* c, const double* dev, double* h) {
+    const long E = c->nelem;
+    double* stage = c->EC.p;
+    LAUNCH(K_LAYOUT, k::soa_to_aos3, grid_for(3 * E, 256), 256, E, dev, stage);
+    CK(cudaMemcpyAsync(h, stage, 3 * E * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    return 0;
+}
+static int down_plain(cfdb_ctx* c, const double* dev, double* h, size_t n) {
+    if (n) CK(cudaMemcpyAsync(h, dev, n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    return 0;
+}
+
+extern "C" int cfdb_calcrhs(cfdb_ctx* c, double* rhs, const double* U, const double* theta, const double* T,
+                            const double* dNx, const double* dNy, const double* area, const double* shoc,
+                            const double* dtl, const double* ts1, const double* ts2, const double* ts3,
+                            const int32_t* inpoel, int32_t nelem, int32_t npoin, double Cv, double lambda_ref,
+                            double mu_ref, double gamma0, double T_inf, double cte) {
+    CK(cudaSetDevice(c->device));
+    TRY(check_mesh(c, nelem, npoin, "cfdb_calcrhs"));
+    (void)inpoel;
+    const size_t P = npoin, E = nelem;
+    TRY(up_soa3(c, c->dNx.p, dNx));
+    TRY(up_soa3(c, c->dNy.p, dNy));
+    TRY(up_plain(c, c->U.p, U, 4 * P));
+    TRY(up_plain(c, c->UN.p, theta, 4 * P));
+    TRY(up_plain(c, c->T.p, T, P));
+    TRY(up_plain(c, c->area.p, area, E));
+    TRY(up_plain(c, c->SHOC.p, shoc, E));
+    TRY(up_plain(c, c->DTL.p, dtl, E));
+    TRY(up_plain(c, c->TS1.p, ts1, E));
+    TRY(up_plain(c, c->TS2.p, ts2, E));
+    TRY(up_plain(c, c->TS3.p, ts3, E));
+    c->theta_nonzero = true;
+    k::Gas g{Cv, lambda_ref, mu_ref, gamma0, T_inf, cte};
+    TRY(run_calcrhs_elem(c, g, true, false, c->DTL.p, nullptr));
+    // rhs is inout: the reference adds onto the caller's array in element order, (((rhs+a1)+a2)+...)
+    TRY(up_plain(c, c->RHS1.p, rhs, 4 * P));
+    LAUNCH(K_NODE, k::node_accumulate, grid_for(npoin, 256), 256, npoin, c->d_esup2.p, c->eslot.p, c->EC.p, c->RHS1.p, c->RHS.p);
+    TRY(down_plain(c, c->RHS.p, rhs, 4 * P));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+extern "C" int cfdb_fuente(cfdb_ctx* c, double* rhs, const double* U, const double* w_x, const double* w_y,
+                           const double* dNx, const double* dNy, const double* area, const double* dtl,
+                           const int32_t* inpoel, int32_t nelem, int32_t npoin) {
+    CK(cudaSetDevice(c->device));
+    TRY(check_mesh(c, nelem, npoin, "cfdb_fuente"));
+    (void)inpoel;
+    const size_t P = npoin, E = nelem;
+    TRY(c->FC.alloc(12 * E));
+    TRY(up_soa3(c, c->dNx.p, dNx));
+    TRY(up_soa3(c, c->dNy.p, dNy));
+    TRY(up_plain(c, c->U.p, U, 4 * P));
+    TRY(up_plain(c, c->W_X.p, w_x, P));
+    TRY(up_plain(c, c->W_Y.p, w_y, P));
+    TRY(up_plain(c, c->area.p, area, E));
+    TRY(up_plain(c, c->DTL.p, dtl, E));
+    k::Gas g{1.0, 0.0, 0.0, 1.4, 1.0, 1.0};
+    // the ALE instantiation writes FC (FUENTE) next to EC (calcRHS, ignored here)
+    TRY(run_calcrhs_elem(c, g, false, true, c->DTL.p, nullptr));
+    TRY(up_plain(c, c->RHS1.p, rhs, 4 * P));
+    LAUNCH(K_NODE, k::node_accumulate, grid_for(npoin, 256), 256, npoin, c->d_esup2.p, c->eslot.p, c->FC.p, c->RHS1.p, c->RHS.p);
+    TRY(down_plain(c, c->RHS.p, rhs, 4 * P));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+extern "C" int cfdb_deltat(cfdb_ctx* c, double* dtmin, double* dt, const int32_t* inpoel, const double* area,
+                           const double* T, const double* vel_x, const double* vel_y, const double* w_x,
+                           const double* w_y, int32_t nelem, int32_t npoin, double FSAFE, double FR, double GAMA,
+                           double T_inf) {
+    CK(cudaSetDevice(c->device));
+    TRY(check_mesh(c, nelem, npoin, "cfdb_deltat"));
+    (void)inpoel; (void)FR; (void)GAMA;  // VC = sqrt(GAMA*FR*T) is dead in the reference (subrutinas.f90:179)
+    const size_t P = npoin, E = nelem;
+    TRY(up_plain(c, c->area.p, area, E));
+    TRY(up_plain(c, c->T.p, T, P));
+    TRY(up_plain(c, c->VEL_X.p, vel_x, P));
+    TRY(up_plain(c, c->VEL_Y.p, vel_y, P));
+    TRY(up_plain(c, c->W_X.p, w_x, P));
+    TRY(up_plain(c, c->W_Y.p, w_y, P));
+    LAUNCH(K_SCALAR, k::set_double, 1, 1, &c->sc->dtmin_acc, 1.e20);
+    LAUNCH(K_DELTAT, k::deltat<true>, grid_for(nelem, 256), 256, nelem, c->inp.p, c->area.p, c->T.p, c->VEL_X.p,
+           c->VEL_Y.p, c->W_X.p, c->W_Y.p, FSAFE, T_inf, c->DT.p, c->sc);
+    LAUNCH(K_DTL, k::dtl_blend, grid_for(nelem, 256), 256, nelem, c->DT.p, c->DTL.p, c->sc, 0);
+    TRY(down_plain(c, c->DT.p, dt, E));
+    TRY(read_scal(c));
+    *dtmin = c->h_sc->dtmin_acc;
+    return 0;
+}
+
+extern "C" int cfdb_estab(cfdb_ctx* c, const double* U, const double* T, const double* vel_x, const double* vel_y,
+                          const double* w_x, const double* w_y, const double* GAMM, const double* dNx,
+                          const double* dNy, const int32_t* inpoel, int32_t nelem, int32_t npoin, double FR,
+                          double DTMIN, double RHOINF, double TINF, double* shoc, double* ts1, double* ts2, double* ts3) {
+    CK(cudaSetDevice(c->device));
+    TRY(check_mesh(c, nelem, npoin, "cfdb_estab"));
+    (void)inpoel;
+    const size_t P = npoin, E = nelem;
+    TRY(up_soa3(c, c->dNx.p, dNx));
+    TRY(up_soa3(c, c->dNy.p, dNy));
+    TRY(up_plain(c, c->U.p, U, 4 * P));
+    TRY(up_plain(c, c->T.p, T, P));
+    TRY(up_plain(c, c->VEL_X.p, vel_x, P));
+    TRY(up_plain(c, c->VEL_Y.p, vel_y, P));
+    TRY(up_plain(c, c->W_X.p, w_x, P));
+    TRY(up_plain(c, c->W_Y.p, w_y, P));
+    TRY(up_plain(c, c->GAMM.p, GAMM, P));
+    LAUNCH(K_SCALAR, k::set_double, 1, 1, &c->sc->red[15], DTMIN);
+    LAUNCH(K_ESTAB, k::estab, grid_for(nelem, 256), 256, nelem, c->inp.p, c->U.p, c->T.p, c->VEL_X.p, c->VEL_Y.p, c->W_X.p,
+           c->W_Y.p, c->GAMM.p, c->dNx.p, c->dNy.p, FR, &c->sc->red[15], RHOINF, TINF, c->SHOC.p, c->TS1.p, c->TS2.p,
+           c->TS3.p);
+    TRY(down_plain(c, c->SHOC.p, shoc, E));
+    TRY(down_plain(c, c->TS1.p, ts1, E));
+    TRY(down_plain(c, c->TS2.p, ts2, E));
+    TRY(down_plain(c, c->TS3.p, ts3, E));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+extern "C" int cfdb_deriv(cfdb_ctx* c, const double* X, const double* Y, const int32_t* inpoel, int32_t nelem,
+                          int32_t npoin, double* area, double* HH, double* HHX, double* HHY, double* dNx, double* dNy,
+                          double* hmin) {
+    CK(cudaSetDevice(c->device));
+    TRY(check_mesh(c, nelem, npoin, "cfdb_deriv"));
+    (void)inpoel;
+    const size_t P = npoin, E = nelem;
+    TRY(up_plain(c, c->X.p, X, P));
+    TRY(up_plain(c, c->Y.p, Y, P));
+    TRY(run_deriv(c));
+    TRY(down_plain(c, c->area.p, area, E));
+    TRY(down_plain(c, c->HH.p, HH, E));
+    TRY(down_plain(c, c->HHX.p, HHX, E));
+    TRY(down_plain(c, c->HHY.p, HHY, E));
+    TRY(down_soa3(c, c->dNx.p, dNx));
+    CK(cudaStreamSynchronize(c->st));
+    TRY(down_soa3(c, c->dNy.p, dNy));
+    TRY(read_scal(c));
+    *hmin = c->h_sc->HMIN > 1.e10 ? 1.e10 : c->h_sc->HMIN;
+    return 0;
+}
+
+extern "C" int cfdb_masas(cfdb_ctx* c, const double* area, const int32_t* inpoel, int32_t nelem, int32_t npoin, double* M) {
+    CK(cudaSetDevice(c->device));
+    TRY(check_mesh(c, nelem, npoin, "cfdb_masas"));
+    (void)inpoel;
+    TRY(up_plain(c, c->area.p, area, nelem));
+    TRY(run_masas(c));
+    TRY(down_plain(c, c->M.p, M, npoin));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+extern "C" int cfdb_normales(cfdb_ctx* c, const int32_t* wall, int32_t nwall, const double* X, const double* Y,
+                             int32_t npoin, int32_t* m_out, int32_t* n_ipoin, double* n_x, double* n_y) {
+    CK(cudaSetDevice(c->device));
+    if (npoin != c->npoin) return fail("cfdb_normales: npoin differs from the context");
+    if (nwall != (int)c->h_wall.size() / 2 || memcmp(wall, c->h_wall.data(), c->h_wall.size() * sizeof(int32_t)))
+        return fail("cfdb_normales: wall list differs from the one the context was created with");
+    TRY(up_plain(c, c->X.p, X, npoin));
+    TRY(up_plain(c, c->Y.p, Y, npoin));
+    TRY(run_normales(c));
+    double m = 0;
+    TRY(cfdb_get_scalar(c, "n_m", &m));
+    *m_out = (int32_t)m;
+    TRY(cfdb_get(c, "n_ipoin", n_ipoin, *m_out));
+    TRY(cfdb_get(c, "n_x", n_x, *m_out));
+    TRY(cfdb_get(c, "n_y", n_y, *m_out));
+    return 0;
+}
+
+extern "C" int cfdb_laplace(cfdb_ctx* c, const int32_t* inpoel, const double* area, const double* dNx, const double* dNy,
+                            const double* X, const double* Y, int32_t nelem, int32_t npoin, double* lap_sparse,
+                            double* lap_diag) {
+    CK(cudaSetDevice(c->device));
+    TRY(check_mesh(c, nelem, npoin, "cfdb_laplace"));
+    (void)inpoel; (void)area;  // `a = area(ielem)` is assigned and never used (mLaplace.f90:37)
+    TRY(up_soa3(c, c->dNx.p, dNx));
+    TRY(up_soa3(c, c->dNy.p, dNy));
+    TRY(up_plain(c, c->X.p, X, npoin));
+    TRY(up_plain(c, c->Y.p, Y, npoin));
+    TRY(run_laplace(c));
+    TRY(down_plain(c, c->lap_sparse.p, lap_sparse, c->nnz));
+    TRY(down_plain(c, c->lap_diag.p, lap_diag, npoin));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+// generic CSR upload for bicg/spmv call-site mode (matrix need not be the context's Laplacian)
+static int up_csr(cfdb_ctx* c, const double* A, const int32_t* idx, const int32_t* rowptr, int npoin, DBuf<double>& dA,
+                  DBuf<int>& dIdx, DBuf<int>& dPtr) {
+    int nnz = rowptr[npoin];
+    vector<int32_t> i0(idx, idx + nnz);
+    for (auto& v : i0) {
+        if (v < 1 || v > npoin) return fail("CSR column index out of range");
+        v -= 1;
+    }
+    TRY(upload(c, dA, A, (size_t)nnz));
+    TRY(upload(c, dIdx, i0));
+    TRY(upload(c, dPtr, rowptr, (size_t)npoin + 1));
+    CK(cudaStreamSynchronize(c->st));  // i0 is a temporary
+    return 0;
+}
+
+extern "C" int cfdb_spmv(cfdb_ctx* c, const double* A, const int32_t* idx, const int32_t* rowptr, const double* v,
+                         double* y, int32_t npoin, int32_t npos) {
+    CK(cudaSetDevice(c->device));
+    if (npoin > c->npoin) return fail("cfdb_spmv: npoin larger than the context");
+    if (npos != rowptr[npoin]) return fail("cfdb_spmv: npos != spRowptr(npoin+1)");
+    DBuf<double> dA;
+    DBuf<int> dIdx, dPtr;
+    int r = up_csr(c, A, idx, rowptr, npoin, dA, dIdx, dPtr);
+    if (!r) r = up_plain(c, c->tmpA.p, v, npoin);
+    if (!r) {
+        auto body = [&]() -> int {
+            LAUNCH(K_SPMV, k::spmv, grid_for(npoin, 256), 256, npoin, dA.p, dIdx.p, dPtr.p, c->tmpA.p, c->tmpB.p);
+            TRY(down_plain(c, c->tmpB.p, y, npoin));
+            CK(cudaStreamSynchronize(c->st));
+            return 0;
+        };
+        r = body();
+    }
+    dA.release(); dIdx.release(); dPtr.release();
+    return r;
+}
+
+extern "C" int cfdb_vecdot(cfdb_ctx* c, int32_t n, const double* x, const double* y, double* result) {
+    CK(cudaSetDevice(c->device));
+    if (n > c->npoin) return fail("cfdb_vecdot: n larger than the context");
+    TRY(up_plain(c, c->tmpA.p, x, n));
+    TRY(up_plain(c, c->tmpB.p, y, n));
+    if (n == 0) { *result = 0.0; return 0; }
+    TRY(dev_dot(c, n, c->tmpA.p, c->tmpB.p, 0));
+    TRY(read_scal(c));
+    *result = c->h_sc->red[0];
+    return 0;
+}
+
+extern "C" int cfdb_bicg(cfdb_ctx* c, const double* A, const int32_t* idx, const int32_t* rowptr, const double* diag,
+                         double* x, const double* b, const double* x_fix, const int32_t* fixIdx, int32_t npoin,
+                         int32_t nfix, int32_t* iters) {
+    CK(cudaSetDevice(c->device));
+    if (npoin != c->npoin) return fail("cfdb_bicg: npoin differs from the context");
+    DBuf<double> dA, dfix;
+    DBuf<int> dIdx, dPtr, dFixIdx, dFixLast;
+    auto body = [&]() -> int {
+        TRY(up_csr(c, A, idx, rowptr, npoin, dA, dIdx, dPtr));
+        vector<int32_t> f0(fixIdx, fixIdx + nfix), last;
+        for (int v : f0)
+            if (v < 1 || v > npoin) return fail("cfdb_bicg: x_fixIdx out of range");
+        topo::last_wins(fixIdx, nfix, npoin, last);
+        for (auto& v : f0) v -= 1;
+        TRY(upload(c, dFixIdx, f0));
+        TRY(upload(c, dFixLast, last));
+        TRY(upload(c, dfix, x_fix, (size_t)nfix));
+        TRY(up_plain(c, c->tmpA.p, x, npoin));
+        TRY(up_plain(c, c->tmpB.p, b, npoin));
+        TRY(up_plain(c, c->tmpC.p, diag, npoin));
+        CK(cudaStreamSynchronize(c->st));
+        int it = 0;
+        TRY(bicg_dev(c, dA.p, dIdx.p, dPtr.p, c->tmpC.p, c->tmpA.p, c->tmpB.p, dfix.p, dFixIdx.p, dFixLast.p, npoin, nfix, &it));
+        *iters = it;
+        TRY(down_plain(c, c->tmpA.p, x, npoin));
+        CK(cudaStreamSynchronize(c->st));
+        return 0;
+    };
+    int r = body();
+    dA.release(); dfix.release(); dIdx.release(); dPtr.release(); dFixIdx.release(); dFixLast.release();
+    return r;
+}
+
+extern "C" int cfdb_gcl_main(cfdb_ctx* c, double* M, const double* W_x, const double* W_y, const double* W_x_old,
+                             const double* W_y_old, const double* area_old, const double* dNx, const double* dNy,
+                             const double* area, const int32_t* inpoel, int32_t nelem, int32_t npoin, double dt) {
+    CK(cudaSetDevice(c->device));
+    TRY(check_mesh(c, nelem, npoin, "cfdb_gcl_main"));
+    (void)inpoel; (void)W_y; (void)W_y_old;  // gcl.f90:38-41 uses W_x for both terms
+    if (!W_x_old || !area_old) return fail("Faltan valores (GCL)");  // gcl.f90:23-25
+    TRY(up_soa3(c, c->dNx.p, dNx));
+    TRY(up_soa3(c, c->dNy.p, dNy));
+    TRY(up_plain(c, c->M.p, M, npoin));
+    TRY(up_plain(c, c->W_X.p, W_x, npoin));
+    TRY(up_plain(c, c->W_x_old.p, W_x_old, npoin));
+    TRY(up_plain(c, c->area.p, area, nelem));
+    TRY(up_plain(c, c->area_old.p, area_old, nelem));
+    TRY(run_gcl(c, nullptr, dt));
+    TRY(down_plain(c, c->M.p, M, npoin));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}

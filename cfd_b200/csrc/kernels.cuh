@@ -1,0 +1,836 @@
+// sm_100a kernels of the flow hot path and the mesh-motion path.  All fp64, no tensor cores
+// (nothing here is a dense contraction); the bound is HBM bandwidth plus the fp64 pipe for
+// calcRHS.  Data layout in HBM:
+//   nodal conserved vectors U,U1,RHS : node-interleaved (4 doubles = one 32-byte sector per
+//                                      node, so a connectivity gather costs one sector);
+//   nodal scalars                    : plain arrays;
+//   element arrays (3,E)             : structure-of-arrays [3][E] so a warp streams them coalesced;
+//   inpoel                           : [3][E] int32, 0-based;
+//   EC / FC                          : staged per-element contributions [E][3][4] (one sector
+//                                      per (element, local node)) consumed by the node kernel in
+//                                      ascending-element order = the reference's 1-thread order.
+#pragma once
+#include "exact.cuh"
+#include <stdint.h>
+
+namespace k {
+
+// device-resident loop scalars (ns2DComp.ALE.f90:109-166) and reduction results
+struct Scal {
+    double dtmin_acc;  // running min of deltat
+    double DTMIN, DTMIN1, TIME, HMIN;
+    double dtfact;     // 1-exp(-ITER*4.6/ITLOCAL), host-computed
+    double red[16];    // canonical reduction results
+    double err_new, err_old, py, alfa, beta, rr;
+    double ER[4], ERR[4];
+    double FX[10], FY[10], RM[10];
+    int ITER, BANDERA, bicg_k, bicg_state;
+};
+
+struct Gas {
+    double Cv, lambda_ref, mu_ref, gamma0, T_inf, cte;
+};
+
+__device__ __forceinline__ void ld4(const double* __restrict__ p, double v[4]) {
+    const double2* q = reinterpret_cast<const double2*>(p);
+    double2 a = __ldg(q), b = __ldg(q + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void st4(double* p, const double v[4]) {
+    double2* q = reinterpret_cast<double2*>(p);
+    q[0] = make_double2(v[0], v[1]);
+    q[1] = make_double2(v[2], v[3]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// deriv  (subrutinas.f90:99-122) : one thread per element
+__global__ void __launch_bounds__(256) deriv(int nelem, const int* __restrict__ inp, const double* __restrict__ X,
+                                              const double* __restrict__ Y, double* __restrict__ area,
+                                              double* __restrict__ HH, double* __restrict__ HHX,
+                                              double* __restrict__ HHY, double* __restrict__ dNx,
+                                              double* __restrict__ dNy, Scal* sc) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    double hh = CUDART_INF;
+    if (e < nelem) {
+        int n1 = inp[e], n2 = inp[nelem + e], n3 = inp[2 * (size_t)nelem + e];
+        double x1 = X[n1], x2 = X[n2], x3 = X[n3], y1 = Y[n1], y2 = Y[n2], y3 = Y[n3];
+        double a = (x2 * y3 + x3 * y1 + x1 * y2 - (x2 * y1 + x3 * y2 + x1 * y3)) / 2.0;
+        area[e] = a;
+        double ta = 2.0 * a;
+        dNx[e] = (y2 - y3) / ta;
+        dNx[nelem + e] = (y3 - y1) / ta;
+        dNx[2 * (size_t)nelem + e] = (y1 - y2) / ta;
+        dNy[e] = (x3 - x2) / ta;
+        dNy[nelem + e] = (x1 - x3) / ta;
+        dNy[2 * (size_t)nelem + e] = (x2 - x1) / ta;
+        hh = sqrt(a);
+        HH[e] = hh;
+        HHX[e] = fabs(ex::fmin2(ex::fmin2(x3 - x2, x1 - x3), x2 - x1));
+        HHY[e] = fabs(ex::fmin2(ex::fmin2(y3 - y2, y1 - y3), y2 - y1));
+    }
+    // hmin = minval(HH) (:124) — exact whatever the order; NaN never wins a '<'
+    __shared__ double sm[256];
+    sm[threadIdx.x] = hh;
+    __syncthreads();
+    for (int s = 128; s >= 1; s >>= 1) {
+        if (threadIdx.x < s) {
+            double o = sm[threadIdx.x + s];
+            if (o < sm[threadIdx.x]) sm[threadIdx.x] = o;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double v = sm[0];
+        unsigned long long* addr = reinterpret_cast<unsigned long long*>(&sc->HMIN);
+        unsigned long long old = *addr;
+        while (v < __longlong_as_double((long long)old)) {
+            unsigned long long assumed = old;
+            old = atomicCAS(addr, assumed, (unsigned long long)__double_as_longlong(v));
+            if (old == assumed) break;
+        }
+    }
+}
+
+// MASAS (subrutinas.f90:137-152) as an ordered node gather over esup
+__global__ void __launch_bounds__(256) masas(int npoin, const int* __restrict__ esup2, const int* __restrict__ eslot,
+                                              const double* __restrict__ area, double* __restrict__ M) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= npoin) return;
+    double m = 0.0;
+    for (int k = esup2[n]; k < esup2[n + 1]; ++k) m = m + area[eslot[k] / 3] / 3.0;
+    M[n] = m;
+}
+
+// normales (subrutinas.f90:26-63) : one thread per wall node, edges in ascending order
+__global__ void normales(int nwn, const int* __restrict__ wn_node, const int* __restrict__ wn_ptr,
+                         const int* __restrict__ wn_edge, const int* __restrict__ wall, const double* __restrict__ X,
+                         const double* __restrict__ Y, double* __restrict__ wn_x, double* __restrict__ wn_y,
+                         int* __restrict__ wn_valid) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nwn) return;
+    double numx = 0.0, numy = 0.0, den = 0.0;
+    for (int k = wn_ptr[j]; k < wn_ptr[j + 1]; ++k) {
+        int iw = wn_edge[k];
+        int a = wall[2 * iw], b = wall[2 * iw + 1];
+        double lx = Y[b] - Y[a];
+        double ly = -(X[b] - X[a]);
+        double l = sqrt(lx * lx + ly * ly);
+        numx = numx + lx; numy = numy + ly; den = den + l;
+    }
+    int valid = 0;
+    double nx = 0.0, ny = 0.0;
+    if (den > 1.e-6) {
+        double lx = numx / den, ly = numy / den;
+        double nrm = sqrt(lx * lx + ly * ly);
+        if (nrm > 0.2) { valid = 1; nx = lx / nrm; ny = ly / nrm; }
+    }
+    (void)wn_node;
+    wn_x[j] = nx; wn_y[j] = ny; wn_valid[j] = valid;
+}
+
+// ---------------------------------------------------------------------------------------------
+// deltat (subrutinas.f90:172-210) : one thread per element + exact global min
+template <bool WRITE_DT>
+__global__ void __launch_bounds__(256) deltat(int nelem, const int* __restrict__ inp, const double* __restrict__ area,
+                                               const double* __restrict__ T, const double* __restrict__ VX,
+                                               const double* __restrict__ VY, const double* __restrict__ WX,
+                                               const double* __restrict__ WY, double FSAFE, double T_inf,
+                                               double* __restrict__ DT, Scal* sc) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    double dte = 1.e20;
+    if (e < nelem) {
+        int n[3] = {inp[e], inp[nelem + e], inp[2 * (size_t)nelem + e]};
+        double T_iel = (T[n[0]] + T[n[1]] + T[n[2]]) / 3.0;
+        double VUMAX = 0.0, VVMAX = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            double VU = fabs(VX[n[i]] - WX[n[i]]);
+            double VV = fabs(VY[n[i]] - WY[n[i]]);
+            if (VU > VUMAX) VUMAX = VU;
+            if (VV > VVMAX) VVMAX = VV;
+        }
+        double HH = sqrt(2.0 * area[e]);
+        double VEL = ex::pow05(VUMAX * VUMAX + VVMAX * VVMAX);
+        double smu = 110.0;
+        double fmu = 0.017 * ex::pow15(T_iel / T_inf) * (T_inf + smu) / (T_iel + smu);
+        double ET = fmu;
+        double Pe = (VEL * HH) / (2.0 * ET);
+        double ALPHA = ex::fmin2(Pe / 3.0, 1.0);
+        double DELTATU = 1.0 / (4.0 * ET / (HH * HH) + ALPHA * VEL / HH);
+        double DELTATC = 1.0 / (4.0 * ET / (HH * HH));
+        double DTELEM = FSAFE / (1.0 / DELTATC + 1.0 / DELTATU);
+        if (WRITE_DT) DT[e] = DTELEM;
+        if (DTELEM < dte) dte = DTELEM;
+    }
+    __shared__ double sm[256];
+    sm[threadIdx.x] = dte;
+    __syncthreads();
+    for (int s = 128; s >= 1; s >>= 1) {
+        if (threadIdx.x < s) {
+            double o = sm[threadIdx.x + s];
+            if (o < sm[threadIdx.x]) sm[threadIdx.x] = o;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double v = sm[0];
+        unsigned long long* addr = reinterpret_cast<unsigned long long*>(&sc->dtmin_acc);
+        unsigned long long old = *addr;
+        while (v < __longlong_as_double((long long)old)) {
+            unsigned long long assumed = old;
+            old = atomicCAS(addr, assumed, (unsigned long long)__double_as_longlong(v));
+            if (old == assumed) break;
+        }
+    }
+}
+
+// start of a pass of the time loop: ITER++ (ns2DComp.ALE.f90:140), reset the running min
+__global__ void step_begin(Scal* sc) {
+    sc->ITER += 1;
+    sc->dtmin_acc = 1.e20;
+}
+// ns2DComp.ALE.f90:146-166 : DTMIN freeze logic, TIME += DTMIN
+__global__ void dt_logic(Scal* sc) {
+    double DTMIN = sc->dtmin_acc;
+    if (sc->BANDERA == 1) { sc->DTMIN1 = DTMIN; sc->BANDERA = 2; }
+    double PORC = fabs((DTMIN - sc->DTMIN1) / DTMIN);
+    if (100.0 * PORC <= 1.0) DTMIN = sc->DTMIN1;
+    else { sc->DTMIN1 = DTMIN; sc->BANDERA = 2; }
+    sc->DTMIN = DTMIN;
+    sc->TIME = sc->TIME + DTMIN;
+}
+// subrutinas.f90:211-215 clamp and ns2DComp.ALE.f90:159-161 local time step blend
+__global__ void dtl_blend(int nelem, double* __restrict__ DT, double* __restrict__ DTL, const Scal* sc, int blend) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nelem) return;
+    double COTA = 10.0 * sc->dtmin_acc;
+    double d = DT[e];
+    if (d > COTA) { d = COTA; DT[e] = d; }
+    if (blend) {
+        double f = sc->dtfact;
+        DTL[e] = sc->DTMIN * f + d * (1.0 - f);
+    }
+}
+__global__ void set_double(double* p, double v) { *p = v; }
+__global__ void bandera_inc(Scal* sc) { sc->BANDERA += 1; }
+// RHS -> RHS3/RHS2/RHS1 when BANDERA is 2/3/4 (subrutinas.f90:830-848)
+__global__ void rhs_history(long n, const Scal* sc, const double* __restrict__ RHS, double* __restrict__ R1,
+                            double* __restrict__ R2, double* __restrict__ R3) {
+    int b = sc->BANDERA;
+    if (b < 2 || b > 4) return;
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double* dst = b == 2 ? R3 : b == 3 ? R2 : R1;
+    dst[i] = RHS[i];
+}
+__global__ void fill(int n, double* __restrict__ a, const double* src) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = *src;
+}
+__global__ void fill_const(long n, double* __restrict__ a, double v) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i < n) a[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ESTAB (subrutinas.f90:349-443) : one thread per element
+__global__ void __launch_bounds__(256) estab(int nelem, const int* __restrict__ inp, const double* __restrict__ U,
+                                              const double* __restrict__ T, const double* __restrict__ VXa,
+                                              const double* __restrict__ VYa, const double* __restrict__ WXa,
+                                              const double* __restrict__ WYa, const double* __restrict__ GAMM,
+                                              const double* __restrict__ dNx, const double* __restrict__ dNy,
+                                              double FR, const double* __restrict__ dtmin_p, double RHOINF,
+                                              double TINF, double* __restrict__ SHOC, double* __restrict__ TS1,
+                                              double* __restrict__ TS2, double* __restrict__ TS3) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nelem) return;
+    const double DTMIN = *dtmin_p;
+    int N1 = inp[e], N2 = inp[nelem + e], N3 = inp[2 * (size_t)nelem + e];
+    double nx[3] = {dNx[e], dNx[nelem + e], dNx[2 * (size_t)nelem + e]};
+    double ny[3] = {dNy[e], dNy[nelem + e], dNy[2 * (size_t)nelem + e]};
+    double GM = (GAMM[N1] + GAMM[N2] + GAMM[N3]) / 3.0;
+    double TAU = 0.0, H_RGNE = 0.0, H_RGN = 0.0, H_JGN = 0.0;
+    double r1 = U[4 * (size_t)N1], r2 = U[4 * (size_t)N2], r3 = U[4 * (size_t)N3];
+    double RHO_ELEM = (r1 + r2 + r3) / 3.0;
+    double VX = (VXa[N1] + VXa[N2] + VXa[N3]) / 3.0;
+    double VY = (VYa[N1] + VYa[N2] + VYa[N3]) / 3.0;
+    double WX = (WXa[N1] + WXa[N2] + WXa[N3]) / 3.0;
+    double WY = (WYa[N1] + WYa[N2] + WYa[N3]) / 3.0;
+    VX = VX - WX; VY = VY - WY;
+    double VEL2 = sqrt(VX * VX + VY * VY);
+    double DRX = r1 * nx[0] + r2 * nx[1] + r3 * nx[2];
+    double DRY = r1 * ny[0] + r2 * ny[1] + r3 * ny[2];
+    double DR2 = sqrt(DRX * DRX + DRY * DRY) + 1.e-20;
+    double t1 = T[N1], t2 = T[N2], t3 = T[N3];
+    double DTX = t1 * nx[0] + t2 * nx[1] + t3 * nx[2];
+    double DTY = t1 * ny[0] + t2 * ny[1] + t3 * ny[2];
+    double DT2 = sqrt(DTX * DTX + DTY * DTY) + 1.e-20;
+    double DUX = VEL2 * nx[0] + VEL2 * nx[1] + VEL2 * nx[2];
+    double DUY = VEL2 * ny[0] + VEL2 * ny[1] + VEL2 * ny[2];
+    double DU2 = sqrt(DUX * DUX + DUY * DUY) + 1.e-20;
+    double RTX = DTX / DT2, RTY = DTY / DT2;
+    double RJX = DRX / DR2, RJY = DRY / DR2;
+    double RUX = DUX / DU2, RUY = DUY / DU2;
+    double TEMP = (t1 + t2 + t3) / 3.0;
+    double C = sqrt(GM * FR * TEMP);
+    double smu = 110.0;
+    double fmu = 0.017 * ex::pow15(TEMP / TINF) * (TINF + smu) / (TEMP + smu);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        double TERM_1 = fabs(VX * nx[i] + VY * ny[i]);
+        double TERM_2 = fabs(RJX * nx[i] + RJY * ny[i]);
+        double H_RGN1 = fabs(RTX * nx[i] + RTY * ny[i]);
+        double H_RGN2 = fabs(RUX * nx[i] + RUY * ny[i]);
+        TAU = TAU + TERM_1 + TERM_2 * C;
+        H_RGNE = H_RGNE + H_RGN1;
+        H_RGN = H_RGN + H_RGN2;
+        H_JGN = H_JGN + TERM_2;
+    }
+    TAU = 1.0 / TAU;
+    H_RGNE = 2.0 / H_RGNE;
+    H_RGN = 2.0 / H_RGN;
+    if (H_RGN > 1.e1) H_RGN = 0.0;
+    H_JGN = 2.0 / H_JGN;
+    if (H_JGN > 1.e1) H_JGN = 0.0;
+    double TR1 = DR2 * H_JGN / RHO_ELEM;
+    double ZZZ = H_JGN / (2.0 * C);
+    SHOC[e] = (TR1 + TR1 * TR1) * .5 * (C * C) * ZZZ;
+    double RESUMEN = 1.0 / (TAU * TAU) + (2.0 / DTMIN) * (2.0 / DTMIN);
+    double RRR = ex::powm05(RESUMEN);
+    double s2 = RRR, s3 = RRR;
+    if (fmu != 0.0) {
+        double TAU_SUNG3 = (H_RGN * H_RGN) / (4.0 * fmu / RHOINF);
+        double TAU_SUNG3_E = (H_RGNE * H_RGNE) / (4.0 * fmu / RHOINF);
+        s2 = ex::powm05(RESUMEN + 1.0 / (TAU_SUNG3 * TAU_SUNG3));
+        s3 = ex::powm05(RESUMEN + 1.0 / (TAU_SUNG3_E * TAU_SUNG3_E));
+    }
+    TS1[e] = RRR; TS2[e] = s2; TS3[e] = s3;
+}
+
+// ---------------------------------------------------------------------------------------------
+// calcRHS (calcRHS.f90:36-141) [+ FUENTE, subrutinas.f90:1060-1078] : one thread per element.
+// Shape-function gradients and the 12+12 contributions stay in registers; the results go to the
+// staging buffers EC/FC, not to RHS: the node kernel sums them in the reference's order.
+template <bool VISC, bool THETA, bool ALE>
+__global__ void __launch_bounds__(128) calcrhs_elem(int nelem, const int* __restrict__ inp, const double* __restrict__ U,
+                                                     const double* __restrict__ TH, const double* __restrict__ T,
+                                                     const double* __restrict__ WXa, const double* __restrict__ WYa,
+                                                     const double* __restrict__ dNx, const double* __restrict__ dNy,
+                                                     const double* __restrict__ area, const double* __restrict__ shoc,
+                                                     const double* __restrict__ dtl_arr, const double* __restrict__ dtl_sc,
+                                                     const double* __restrict__ ts1, const double* __restrict__ ts2,
+                                                     const double* __restrict__ ts3, Gas g, double* __restrict__ EC,
+                                                     double* __restrict__ FC) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nelem) return;
+    const double gamma0 = g.gamma0;
+    int ip[3] = {inp[e], inp[nelem + e], inp[2 * (size_t)nelem + e]};
+    double Nx[3] = {dNx[e], dNx[nelem + e], dNx[2 * (size_t)nelem + e]};
+    double Ny[3] = {dNy[e], dNy[nelem + e], dNy[2 * (size_t)nelem + e]};
+    double Un[3][4];
+    ld4(U + 4 * (size_t)ip[0], Un[0]);
+    ld4(U + 4 * (size_t)ip[1], Un[1]);
+    ld4(U + 4 * (size_t)ip[2], Un[2]);
+    double Ux[4], Uy[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        Ux[i] = Un[0][i] * Nx[0] + Un[1][i] * Nx[1] + Un[2][i] * Nx[2];
+        Uy[i] = Un[0][i] * Ny[0] + Un[1][i] * Ny[1] + Un[2][i] * Ny[2];
+    }
+    const double tau[3] = {ts1[e], ts2[e], ts3[e]};
+    const double nu = shoc[e] * g.cte;
+    const double dtl = dtl_arr ? dtl_arr[e] : *dtl_sc;
+    const double ar = area[e];
+    double mu = 0.0, lambda = 0.0;
+    if (VISC) {
+        double T_avg = (T[ip[0]] + T[ip[1]] + T[ip[2]]) / 3.0;
+        double p15 = ex::pow15(T_avg / g.T_inf);
+        mu = g.mu_ref * p15 * (g.T_inf + 110) / (T_avg + 110);
+        lambda = g.lambda_ref * p15 * (g.T_inf + 194) / (T_avg + 194);
+    }
+    double Th[3][4];
+    if (THETA) {
+        ld4(TH + 4 * (size_t)ip[0], Th[0]);
+        ld4(TH + 4 * (size_t)ip[1], Th[1]);
+        ld4(TH + 4 * (size_t)ip[2], Th[2]);
+    }
+    double rt[3][4];
+#pragma unroll
+    for (int n = 0; n < 3; ++n)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rt[n][i] = 0.0;
+    // nu*(Nx(n)*Ux + Ny(n)*Uy) does not depend on the Gauss point: same expression, same bits
+    double sh[3][4];
+#pragma unroll
+    for (int n = 0; n < 3; ++n)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sh[n][i] = nu * (Nx[n] * Ux[i] + Ny[n] * Uy[i]);
+
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        // N(:,k): zero at local node k, one half elsewhere (calcRHS.f90:18-23)
+        const double Nk[3] = {k == 0 ? 0.0 : .5, k == 1 ? 0.0 : .5, k == 2 ? 0.0 : .5};
+        double U_k[4], th_k[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            U_k[i] = Nk[0] * Un[0][i] + Nk[1] * Un[1][i] + Nk[2] * Un[2][i];
+            th_k[i] = THETA ? (Nk[0] * Th[0][i] + Nk[1] * Th[1][i] + Nk[2] * Th[2][i]) : 0.0;
+        }
+        double rho = U_k[0];
+        double v1 = U_k[1] / rho, v2 = U_k[2] / rho, en = U_k[3] / rho;
+        double V_sq = v1 * v1 + v2 * v2;
+        double A[4];
+        A[0] = Ux[1] + Uy[2];
+        A[1] = (1.0 / 2.0) * Ux[0] * (V_sq * (gamma0 - 1) - 2 * (v1 * v1)) - Ux[1] * v1 * (gamma0 - 3) -
+               Ux[2] * v2 * (gamma0 - 1) + Ux[3] * (gamma0 - 1) - Uy[0] * v1 * v2 + Uy[1] * v2 + Uy[2] * v1;
+        A[2] = -Ux[0] * v1 * v2 + Ux[1] * v2 + Ux[2] * v1 +
+               (1.0 / 2.0) * Uy[0] * (V_sq * (gamma0 - 1) - 2 * (v2 * v2)) - Uy[1] * v1 * (gamma0 - 1) -
+               Uy[2] * v2 * (gamma0 - 3) + Uy[3] * (gamma0 - 1);
+        A[3] = Ux[0] * v1 * (V_sq * (gamma0 - 1) - en * gamma0) -
+               1.0 / 2.0 * Ux[1] * (V_sq * (gamma0 - 1) - 2 * en * gamma0 + 2 * (v1 * v1) * (gamma0 - 1)) -
+               Ux[2] * v1 * v2 * (gamma0 - 1) + Ux[3] * gamma0 * v1 +
+               Uy[0] * v2 * (V_sq * (gamma0 - 1) - en * gamma0) - Uy[1] * v1 * v2 * (gamma0 - 1) -
+               1.0 / 2.0 * Uy[2] * (V_sq * (gamma0 - 1) - 2 * en * gamma0 + 2 * (v2 * v2) * (gamma0 - 1)) +
+               Uy[3] * gamma0 * v2;
+        double At[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) At[i] = th_k[i] + A[i];
+        double A1[4], A2[4];
+        A1[0] = At[1];
+        A1[1] = v1 * (-gamma0 + 3) * At[1] - v2 * (gamma0 - 1) * At[2] + (gamma0 - 1) * At[3] +
+                ((1.0 / 2.0) * V_sq * (gamma0 - 1) - v1 * v1) * At[0];
+        A1[2] = -v1 * v2 * At[0] + v1 * At[2] + v2 * At[1];
+        A1[3] = gamma0 * v1 * At[3] - v1 * v2 * (gamma0 - 1) * At[2] +
+                v1 * (V_sq * (gamma0 - 1) - en * gamma0) * At[0] +
+                (-1.0 / 2.0 * V_sq * (gamma0 - 1) + en * gamma0 - v1 * v1 * (gamma0 - 1)) * At[1];
+        A2[0] = At[2];
+        A2[1] = -v1 * v2 * At[0] + v1 * At[2] + v2 * At[1];
+        A2[2] = -v1 * (gamma0 - 1) * At[1] + v2 * (-gamma0 + 3) * At[2] + (gamma0 - 1) * At[3] +
+                ((1.0 / 2.0) * V_sq * (gamma0 - 1) - v2 * v2) * At[0];
+        A2[3] = gamma0 * v2 * At[3] - v1 * v2 * (gamma0 - 1) * At[1] +
+                v2 * (V_sq * (gamma0 - 1) - en * gamma0) * At[0] +
+                (-1.0 / 2.0 * V_sq * (gamma0 - 1) + en * gamma0 - v2 * v2 * (gamma0 - 1)) * At[2];
+#pragma unroll
+        for (int n = 0; n < 3; ++n)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                rt[n][i] = rt[n][i] + Nk[n] * A[i] + tau[n] * (Nx[n] * A1[i] + Ny[n] * A2[i]) + sh[n][i];
+        if (VISC) {
+            const double Cv = g.Cv;
+            double K1[4], K2[4];
+            K1[1] = (2.0 / 3.0) * mu * (-2 * Ux[0] * v1 + 2 * Ux[1] + Uy[0] * v2 - Uy[2]) / rho;
+            K1[2] = mu * (-Ux[0] * v2 + Ux[2] - Uy[0] * v1 + Uy[1]) / rho;
+            K1[3] = (1.0 / 3.0) *
+                    (Cv * mu * (-Uy[0] * v1 * v2 + 3 * Uy[1] * v2 - 2 * Uy[2] * v1) -
+                     Ux[0] * (Cv * mu * (3 * V_sq + v1 * v1) - 3 * lambda * (V_sq - en)) +
+                     Ux[1] * v1 * (4 * Cv * mu - 3 * lambda) + 3 * Ux[2] * v2 * (Cv * mu - lambda) +
+                     3 * Ux[3] * lambda) /
+                    (Cv * rho);
+            K2[1] = mu * (-Ux[0] * v2 + Ux[2] - Uy[0] * v1 + Uy[1]) / rho;
+            K2[2] = (2.0 / 3.0) * mu * (Ux[0] * v1 - Ux[1] - 2 * Uy[0] * v2 + 2 * Uy[2]) / rho;
+            K2[3] = (1.0 / 3.0) *
+                    (Cv * mu * (-Ux[0] * v1 * v2 - 2 * Ux[1] * v2 + 3 * Ux[2] * v1) -
+                     Uy[0] * (Cv * mu * (3 * V_sq + v2 * v2) - 3 * lambda * (V_sq - en)) +
+                     3 * Uy[1] * v1 * (Cv * mu - lambda) + Uy[2] * v2 * (4 * Cv * mu - 3 * lambda) +
+                     3 * Uy[3] * lambda) /
+                    (Cv * rho);
+#pragma unroll
+            for (int n = 0; n < 3; ++n)
+#pragma unroll
+                for (int i = 1; i < 4; ++i) rt[n][i] = rt[n][i] + (Nx[n] * K1[i] + Ny[n] * K2[i]);
+        }
+    }
+    double* out = EC + 12 * (size_t)e;
+#pragma unroll
+    for (int n = 0; n < 3; ++n) {
+        double v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = rt[n][i] * ar * dtl / 3.0;
+        st4(out + 4 * n, v);
+    }
+    if (ALE) {
+        // FUENTE: sp(:,1)=(.5,.5,0) sp(:,2)=(0,.5,.5) sp(:,3)=(.5,0,.5); sp[c][r] = sp(r+1,c+1)
+        const double sp[3][3] = {{.5, .5, 0.0}, {0.0, .5, .5}, {.5, 0.0, .5}};
+        double AR = ar * dtl / 3.0;
+        double wx[3], wy[3];
+        double wxn[3] = {WXa[ip[0]], WXa[ip[1]], WXa[ip[2]]};
+        double wyn[3] = {WYa[ip[0]], WYa[ip[1]], WYa[ip[2]]};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double sx = 0.0, sy = 0.0;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                sx = sx + sp[c][r] * wxn[r];
+                sy = sy + sp[c][r] * wyn[r];
+            }
+            wx[c] = sx; wy[c] = sy;
+        }
+        double* fo = FC + 12 * (size_t)e;
+#pragma unroll
+        for (int n = 0; n < 3; ++n) {
+            double v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                v[i] = -AR * (sp[0][n] * (Ux[i] * wx[0] + Uy[i] * wy[0]) + sp[1][n] * (Ux[i] * wx[1] + Uy[i] * wy[1]) +
+                              sp[2][n] * (Ux[i] * wx[2] + Uy[i] * wy[2]));
+            st4(fo + 4 * n, v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Node kernel: ordered sum of the staged contributions (= RHS), then the whole nodal chain of RK
+// (subrutinas.f90:695-826): U1 = U - rk/M*RHS, primitives, fixvel -> normalvel -> FIX, conservative.
+struct BcTab {
+    int nb;
+    const int* node;      // sorted unique 0-based node ids carrying any BC
+    const int* kind;      // bit0 fixvel, bit1 wall normal, bit2 fix rho, bit3 fix T
+    const double* vx;
+    const double* vy;
+    const double* rho;
+    const double* Tfix;
+    const int* wslot;     // index into wn_x/wn_y/wn_valid
+    const double* wn_x;
+    const double* wn_y;
+    const int* wn_valid;
+};
+
+template <bool ALE, bool UPDATE>
+__global__ void __launch_bounds__(256) node_update(int npoin, const int* __restrict__ esup2, const int* __restrict__ eslot,
+                                                    const double* __restrict__ EC, const double* __restrict__ FC,
+                                                    const double* __restrict__ U, const double* __restrict__ M,
+                                                    const double* __restrict__ GAMM, const double* __restrict__ WXa,
+                                                    const double* __restrict__ WYa, const unsigned char* __restrict__ bcflag,
+                                                    BcTab bc, double rk_fact, double FR, double* __restrict__ U1,
+                                                    double* __restrict__ RHS, double* __restrict__ RHO,
+                                                    double* __restrict__ VELX, double* __restrict__ VELY,
+                                                    double* __restrict__ Ea, double* __restrict__ Pa,
+                                                    double* __restrict__ Ta, double* __restrict__ RMACH) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= npoin) return;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    const int k0 = esup2[n], k1 = esup2[n + 1];
+    for (int k = k0; k < k1; ++k) {
+        double c[4];
+        ld4(EC + 4 * (size_t)eslot[k], c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = acc[i] + c[i];
+    }
+    if (ALE) {
+        for (int k = k0; k < k1; ++k) {
+            double c[4];
+            ld4(FC + 4 * (size_t)eslot[k], c);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = acc[i] + c[i];
+        }
+    }
+    st4(RHS + 4 * (size_t)n, acc);
+    if (!UPDATE) return;
+    double u[4];
+    ld4(U + 4 * (size_t)n, u);
+    double f = rk_fact / M[n];
+    double u1[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) u1[i] = u[i] - f * acc[i];
+    double gam = GAMM[n];
+    double rho = u1[0];
+    double vx = u1[1] / rho, vy = u1[2] / rho, en = u1[3] / rho;
+    double VEL2 = (vx * vx + vy * vy);
+    double p = rho * (gam - 1.0) * (en - .5 * VEL2);
+    double t = p / (rho * FR);
+    double mach = sqrt(VEL2 / (t * gam * FR));
+    unsigned char fl = bcflag[n];
+    if (fl) {
+        int lo = 0, hi = bc.nb - 1;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (bc.node[mid] < n) lo = mid + 1; else hi = mid;
+        }
+        int kind = bc.kind[lo];
+        if (kind & 1) { vx = bc.vx[lo]; vy = bc.vy[lo]; }                      // fixvel
+        if (kind & 2) {                                                        // normalvel
+            int w = bc.wslot[lo];
+            if (bc.wn_valid[w]) {
+                double nx = bc.wn_x[w], ny = bc.wn_y[w];
+                double wx = WXa[n], wy = WYa[n];
+                double pp = -ny * (vx - wx) + nx * (vy - wy);
+                vx = -ny * pp + wx;
+                vy = nx * pp + wy;
+            }
+        }
+        if (kind & 4) rho = bc.rho[lo];                                        // FIX rho
+        if (kind & 8) {                                                        // FIX T
+            double GM = gam - 1.0;
+            t = bc.Tfix[lo];
+            en = t * FR / GM + .5 * (vx * vx + vy * vy);
+        }
+    }
+    double o[4] = {rho, vx * rho, vy * rho, en * rho};
+    st4(U1 + 4 * (size_t)n, o);
+    RHO[n] = rho; VELX[n] = vx; VELY[n] = vy; Ea[n] = en; Pa[n] = p; Ta[n] = t; RMACH[n] = mach;
+}
+
+// rhs_out = ((rhs_in + c1) + c2) + ... in ascending element order (call-site mode of calcRHS / FUENTE, whose
+// rhs argument is inout)
+__global__ void __launch_bounds__(256) node_accumulate(int npoin, const int* __restrict__ esup2, const int* __restrict__ eslot,
+                                                        const double* __restrict__ C, const double* __restrict__ rhs_in,
+                                                        double* __restrict__ rhs_out) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= npoin) return;
+    double acc[4];
+    ld4(rhs_in + 4 * (size_t)n, acc);
+    for (int k = esup2[n]; k < esup2[n + 1]; ++k) {
+        double c[4];
+        ld4(C + 4 * (size_t)eslot[k], c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = acc[i] + c[i];
+    }
+    st4(rhs_out + 4 * (size_t)n, acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Canonical reductions (oracle/orc_math.h canon_sum): 4096-entry chunks, 256 lanes stride 256
+// ascending, binary tree 128..1, recursive over chunk sums.  One CTA of 256 threads per chunk.
+__device__ __forceinline__ double tree256(double v, double* sm) {
+    sm[threadIdx.x] = v;
+    __syncthreads();
+#pragma unroll
+    for (int s = 128; s >= 1; s >>= 1) {
+        if (threadIdx.x < s) sm[threadIdx.x] = sm[threadIdx.x] + sm[threadIdx.x + s];
+        __syncthreads();
+    }
+    double r = sm[0];
+    __syncthreads();
+    return r;
+}
+// out[c] = chunk sum of x[i]*y[i]   (y==nullptr: of x[i])
+__global__ void __launch_bounds__(256) dot_chunks(long n, const double* __restrict__ x, const double* __restrict__ y,
+                                                   double* __restrict__ out) {
+    __shared__ double sm[256];
+    long nchunk = (n + 4095) / 4096;
+    for (long c = blockIdx.x; c < nchunk; c += gridDim.x) {
+        long lo = c * 4096, hi = lo + 4096 < n ? lo + 4096 : n;
+        double acc = 0.0;
+        for (long i = lo + threadIdx.x; i < hi; i += 256) acc = acc + (y ? x[i] * y[i] : x[i]);
+        double r = tree256(acc, sm);
+        if (threadIdx.x == 0) out[c] = r;
+    }
+}
+// residual norms (ns2DComp.ALE.f90:193-196): out[v*nchunk + c], v = 0..3 ER, 4..7 ERR
+__global__ void __launch_bounds__(256) norm_chunks(long npoin, const double* __restrict__ U, const double* __restrict__ U1,
+                                                    double* __restrict__ out) {
+    __shared__ double sm[256];
+    long nchunk = (npoin + 4095) / 4096;
+    for (long c = blockIdx.x; c < nchunk; c += gridDim.x) {
+        long lo = c * 4096, hi = lo + 4096 < npoin ? lo + 4096 : npoin;
+        double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (long i = lo + threadIdx.x; i < hi; i += 256) {
+            double u[4], w[4];
+            ld4(U + 4 * i, u);
+            ld4(U1 + 4 * i, w);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                double d = u[q] - w[q];
+                a[q] = a[q] + d * d;
+                a[4 + q] = a[4 + q] + w[q] * w[q];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            double r = tree256(a[q], sm);
+            if (threadIdx.x == 0) out[q * nchunk + c] = r;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// BiCG building blocks (biconjGrad.f90:64-190).  Row-sequential SpMV: one thread per row keeps the
+// reference's summation order inside a row.
+__global__ void __launch_bounds__(256) spmv(int npoin, const double* __restrict__ A, const int* __restrict__ idx,
+                                             const int* __restrict__ rowptr, const double* __restrict__ v,
+                                             double* __restrict__ y) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npoin) return;
+    double dot = 0.0;
+    for (int j = rowptr[i]; j < rowptr[i + 1]; ++j) dot = dot + A[j] * v[idx[j]];
+    y[i] = dot;
+}
+enum { ALFA_CONST = 0, ALFA_POS = 1, ALFA_NEG = 2, BETA_POS = 3 };
+// z = alfa*x + y  with alfa taken from the device scalars (vecsum, :79)
+__global__ void __launch_bounds__(256) vecsum(int n, int mode, double aconst, const Scal* sc, const double* __restrict__ x,
+                                               const double* __restrict__ y, double* __restrict__ z) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double a = mode == ALFA_CONST ? aconst : mode == ALFA_POS ? sc->alfa : mode == ALFA_NEG ? -sc->alfa : sc->beta;
+    z[i] = a * x[i] + y[i];
+}
+__global__ void __launch_bounds__(256) vecdiv(int n, const double* __restrict__ x, const double* __restrict__ y,
+                                               double* __restrict__ z) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) z[i] = x[i] / y[i];
+}
+// y(idx) = alfa*x(idx)  (copy2 :137) ; y(idx)=alfa*xs(:) (copy1 :122) ; y(idx)=scal (assign2 :109)
+// duplicates in idx: every duplicate writes the value of the LAST list entry (last-wins table)
+__global__ void copy2(int m, const int* __restrict__ idx, double alfa, const double* __restrict__ x, double* __restrict__ y) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) y[idx[i]] = alfa * x[idx[i]];
+}
+__global__ void copy1(int m, const int* __restrict__ idx, const int* __restrict__ last, double alfa,
+                      const double* __restrict__ xs, double* __restrict__ y) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) y[idx[i]] = alfa * xs[last[i]];
+}
+__global__ void assign2(int m, const int* __restrict__ idx, double v, double* __restrict__ y) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) y[idx[i]] = v;
+}
+// scalar algebra of biCG on the device (one thread)
+enum { SC_RR = 0, SC_ERRNEW = 1, SC_PY_ALFA = 2, SC_BETA = 3 };
+__global__ void bicg_scalar(Scal* sc, int what, int slot) {
+    double v = sc->red[slot];
+    if (what == SC_RR) sc->rr = v;
+    else if (what == SC_ERRNEW) sc->err_new = v;
+    else if (what == SC_PY_ALFA) { sc->py = v; sc->alfa = sc->err_new / v; sc->err_old = sc->err_new; }
+    else if (what == SC_BETA) { sc->err_new = v; sc->beta = v / sc->err_old; }
+}
+
+// laplace values (mLaplace.f90:34-57): one thread per node, elements in esup order, row kept in
+// registers/local memory; pos[k][j] = position inside the row of local node j of esup entry k.
+template <int MAXROW>
+__global__ void __launch_bounds__(128) laplace(int npoin, int nelem, const int* __restrict__ esup2,
+                                                const int* __restrict__ eslot, const unsigned char* __restrict__ lpos,
+                                                const int* __restrict__ inp, const double* __restrict__ dNx,
+                                                const double* __restrict__ dNy, const double* __restrict__ X,
+                                                const double* __restrict__ Y, const int* __restrict__ rowptr,
+                                                double* __restrict__ A, double* __restrict__ diag, int* overflow) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= npoin) return;
+    const double TWOSQRT3 = 3.46410161513775;
+    int r0 = rowptr[n], len = rowptr[n + 1] - r0;
+    if (len > MAXROW) { atomicExch(overflow, 1); return; }
+    double row[MAXROW];
+#pragma unroll
+    for (int j = 0; j < MAXROW; ++j) row[j] = 0.0;
+    for (int k = esup2[n]; k < esup2[n + 1]; ++k) {
+        int slot = eslot[k];
+        int e = slot / 3, i = slot - 3 * e;
+        int nn[3] = {inp[e], inp[nelem + e], inp[2 * (size_t)nelem + e]};
+        double X3[3] = {X[nn[0]], X[nn[1]], X[nn[2]]}, Y3[3] = {Y[nn[0]], Y[nn[1]], Y[nn[2]]};
+        double area = X3[1] * Y3[2] + X3[2] * Y3[0] + X3[0] * Y3[1] - (X3[1] * Y3[0] + X3[2] * Y3[1] + X3[0] * Y3[2]);
+        double l1 = (X3[2] - X3[1]) * (X3[2] - X3[1]) + (Y3[2] - Y3[1]) * (Y3[2] - Y3[1]);
+        double l2 = (X3[0] - X3[2]) * (X3[0] - X3[2]) + (Y3[0] - Y3[2]) * (Y3[0] - Y3[2]);
+        double l3 = (X3[1] - X3[0]) * (X3[1] - X3[0]) + (Y3[1] - Y3[0]) * (Y3[1] - Y3[0]);
+        double l = l1 + l2 + l3;
+        double m = TWOSQRT3 * area / l;
+        double q = 1 / (m * m);
+        double nxi = dNx[(size_t)i * nelem + e], nyi = dNy[(size_t)i * nelem + e];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            double v = (nxi * dNx[(size_t)j * nelem + e] + nyi * dNy[(size_t)j * nelem + e]) * q;
+            int pos = lpos[3 * (size_t)k + j];
+#pragma unroll
+            for (int t = 0; t < MAXROW; ++t)
+                if (t == pos) row[t] = row[t] + v;
+        }
+    }
+    for (int j = 0; j < len; ++j)
+#pragma unroll
+        for (int t = 0; t < MAXROW; ++t)
+            if (t == j) A[r0 + j] = row[t];
+    diag[n] = row[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// mesh motion (meshMove.f90)
+// TRANSF (:369-392): rigid rotation displacement of the set nodes; cos/sin come from the host libm
+__global__ void transf(int nse, const int* __restrict__ sn, const int* __restrict__ sset, double ca, double sa, double yposr,
+                       const double* __restrict__ xref, const double* __restrict__ yref, const double* __restrict__ X,
+                       const double* __restrict__ Y, double* __restrict__ dxpos, double* __restrict__ dypos) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nse) return;
+    int n = sn[i], s = sset[i];
+    double DISTX = X[n] - xref[s];
+    double DISTY = Y[n] - yref[s] + yposr;
+    dxpos[n] = ca * DISTX + sa * DISTY - DISTX;
+    dypos[n] = -sa * DISTX + ca * DISTY - DISTY + yposr;
+}
+// pos_aux(1:nmove) = DXPOS(ilaux) ; pos_aux(nmove+1:nnmove) = 0  (:79-89)
+__global__ void pos_aux_fill(int nmove, int nnmove, const int* __restrict__ ilaux, const double* __restrict__ dpos,
+                             double* __restrict__ pos_aux) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnmove) return;
+    pos_aux[i] = i < nmove ? dpos[ilaux[i]] : 0.0;
+}
+// X += XPOS ; X1 += XPOS ; W_X = XPOS/DTMIN  (:99-105)
+__global__ void __launch_bounds__(256) move_apply(int npoin, const double* __restrict__ pos, const double* __restrict__ dtmin_p,
+                                                   double* __restrict__ X, double* __restrict__ X1, double* __restrict__ W) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npoin) return;
+    double d = pos[i];
+    X[i] = X[i] + d;
+    X1[i] = X1[i] + d;
+    W[i] = d / *dtmin_p;
+}
+// FORCES (:171-192): sequential sums over the (few thousand) body edges of each set; one thread per
+// set keeps the reference order exactly.
+__global__ void forces(int nset, const int* __restrict__ sptr, const int* __restrict__ n1a, const int* __restrict__ n2a,
+                       const double* __restrict__ X, const double* __restrict__ Y, const double* __restrict__ P,
+                       const double* __restrict__ xref, const double* __restrict__ yref, Scal* sc) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nset) return;
+    double fx = 0.0, fy = 0.0, rm = 0.0;
+    for (int k = sptr[s]; k < sptr[s + 1]; ++k) {
+        int N1 = n1a[k], N2 = n2a[k];
+        double D_PRESS = (P[N1] + P[N2]) / 2.0;
+        double RLX = X[N1] - X[N2];
+        double RLY = Y[N2] - Y[N1];
+        double DFX = D_PRESS * RLY, DFY = D_PRESS * RLX;
+        fx = fx + DFX;
+        fy = fy + DFY;
+        double XC = (X[N1] + X[N2]) / 2.0, YC = (Y[N2] + Y[N1]) / 2.0;
+        rm = rm + DFY * (XC - xref[s]) - DFX * (YC - yref[s]);
+    }
+    sc->FX[s] = fx; sc->FY[s] = fy; sc->RM[s] = rm;
+}
+
+// gcl_mod::main (gcl.f90:29-45) as an ordered node gather; W_x appears twice as written (:38-41)
+__global__ void __launch_bounds__(256) gcl(int npoin, int nelem, const int* __restrict__ esup2, const int* __restrict__ eslot,
+                                            const int* __restrict__ inp, const double* __restrict__ dNx,
+                                            const double* __restrict__ dNy, const double* __restrict__ area,
+                                            const double* __restrict__ area_old, const double* __restrict__ Wx,
+                                            const double* __restrict__ Wx_old, double dt_const, const double* __restrict__ dt_p,
+                                            double* __restrict__ M) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= npoin) return;
+    double dt = dt_p ? *dt_p : dt_const;
+    double tot1 = 0.0, tot2 = 0.0;
+    for (int k = esup2[n]; k < esup2[n + 1]; ++k) {
+        int e = eslot[k] / 3;
+        int nn[3] = {inp[e], inp[nelem + e], inp[2 * (size_t)nelem + e]};
+        double nx[3] = {dNx[e], dNx[nelem + e], dNx[2 * (size_t)nelem + e]};
+        double ny[3] = {dNy[e], dNy[nelem + e], dNy[2 * (size_t)nelem + e]};
+        double w1 = Wx[nn[0]], w2 = Wx[nn[1]], w3 = Wx[nn[2]];
+        double o1 = Wx_old[nn[0]], o2 = Wx_old[nn[1]], o3 = Wx_old[nn[2]];
+        double divW = nx[0] * w1 + nx[1] * w2 + nx[2] * w3 + ny[0] * w1 + ny[1] * w2 + ny[2] * w3;
+        double divW_old = nx[0] * o1 + nx[1] * o2 + nx[2] * o3 + ny[0] * o1 + ny[1] * o2 + ny[2] * o3;
+        tot1 = tot1 + divW * area[e] / 3.0;
+        tot2 = tot2 + divW_old * area_old[e] / 3.0;
+    }
+    M[n] = M[n] + dt * (tot1 + tot2) / 2.0;
+}
+
+// layout helpers: (3,E) interleaved <-> [3][E]
+__global__ void aos3_to_soa(long nelem, const double* __restrict__ in, double* __restrict__ out) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= 3 * nelem) return;
+    long e = i / 3, c = i - 3 * e;
+    out[c * nelem + e] = in[i];
+}
+__global__ void soa_to_aos3(long nelem, const double* __restrict__ in, double* __restrict__ out) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= 3 * nelem) return;
+    long e = i / 3, c = i - 3 * e;
+    out[i] = in[c * nelem + e];
+}
+
+}  // namespace k

@@ -1,0 +1,189 @@
+"""NSComp2D — the reference's driver (PROGRAM NSComp2D, ns2DComp.ALE.f90:8-389) on the GPU.
+
+Mirrors the reference's call structure: `readInputData`/`loadMeshData` are `deck.read_deck` +
+`deck.load`; the constructor does what the program does before its time loop (allocate, RESTART
+free-stream branch, NORMALES, DERIV, MASAS, laplace); `step(n)` is n passes of the loop; the
+reference subroutines are reachable one by one (`rk_stage`, `geometry`, `fluid_structure`,
+`residual_norms`) and in call-site form with host arrays (`calcrhs`, `fuente`, `deltat`,
+`estab`, `deriv`, `masas`, `normales`, `laplace`, `bicg`, `spmv`, `vecdot`, `gcl_main`).
+All state lives in HBM inside libcfdb200.so; numpy arrays only cross at get/set.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import capi
+from .deck import LoadedCase
+
+_INT_FIELDS = {"inpoel", "esup1", "esup2", "psup1", "psup2", "lap_idx", "lap_rowptr", "ilaux", "n_ipoin"}
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class NSComp2D:
+    def __init__(self, lc: LoadedCase, device: int = 0, use_gcl: int = 0, init: bool = True):
+        self.L = capi.lib()
+        self.lc = lc
+        s = lc.sets
+        self._keep = [np.ascontiguousarray(s[:, k]) for k in range(4)] if s.size else [np.zeros(0, np.int32)] * 4
+        bc = capi.BC(
+            lc.ifixrho_node.size, _vp(lc.ifixrho_node), _vp(lc.rfixrho_value),
+            lc.ifixv_node.size, _vp(lc.ifixv_node), _vp(lc.rfixv_valuex), _vp(lc.rfixv_valuey),
+            lc.wall.shape[0], _vp(lc.wall),
+            lc.ifixt_node.size, _vp(lc.ifixt_node), _vp(lc.rfixt_value),
+            s.shape[0], _vp(self._keep[1]), _vp(self._keep[2]), _vp(self._keep[0]), _vp(self._keep[3]),
+            lc.i_m.size, _vp(lc.i_m), lc.ifm.size, _vp(lc.ifm),
+        )
+        self.par = capi.make_params(lc.par, use_gcl)
+        self.h = C.c_void_p()
+        capi.check(self.L.cfdb_create(C.byref(self.h), C.byref(self.par), lc.npoin, lc.nelem, lc.X, lc.Y, lc.inpoel,
+                                      C.byref(bc), device))
+        self.npoin, self.nelem = lc.npoin, lc.nelem
+        if init:
+            capi.check(self.L.cfdb_init(self.h))
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.L.cfdb_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- resident mode -------------------------------------------------------------------
+    def step(self, n=1):
+        capi.check(self.L.cfdb_step(self.h, n))
+
+    def sync(self):
+        capi.check(self.L.cfdb_sync(self.h))
+
+    def rk_stage(self, irk):
+        capi.check(self.L.cfdb_rk_stage(self.h, irk))
+
+    def geometry(self, moving_step=0):
+        capi.check(self.L.cfdb_geometry(self.h, moving_step))
+
+    def fluid_structure(self, dtmin, time):
+        capi.check(self.L.cfdb_fluid_structure(self.h, dtmin, time))
+
+    def norms(self):
+        er, err = np.zeros(4), np.zeros(4)
+        capi.check(self.L.cfdb_residual_norms(self.h, er, err))
+        return er, err
+
+    def get(self, name):
+        n = self.L.cfdb_field_size(self.h, name.encode())
+        if n < 0:
+            raise KeyError(name)
+        if name in ("n_ipoin", "n_x", "n_y"):
+            n = int(self.scalar("n_m"))
+        a = np.zeros(n, np.int32 if name in _INT_FIELDS else np.float64)
+        capi.check(self.L.cfdb_get(self.h, name.encode(), _vp(a), n))
+        return a
+
+    def set(self, name, value):
+        a = np.ascontiguousarray(np.asarray(value, np.float64).ravel())
+        capi.check(self.L.cfdb_set(self.h, name.encode(), _vp(a), a.size))
+
+    def scalar(self, name):
+        v = C.c_double()
+        capi.check(self.L.cfdb_get_scalar(self.h, name.encode(), C.byref(v)))
+        return v.value
+
+    def set_scalar(self, name, v):
+        capi.check(self.L.cfdb_set_scalar(self.h, name.encode(), float(v)))
+
+    @property
+    def stream(self):
+        return self.L.cfdb_stream(self.h)
+
+    def profile(self, on=True):
+        capi.check(self.L.cfdb_profile_enable(self.h, 1 if on else 0))
+
+    def profile_get(self, kernel):
+        ms, n = C.c_double(), C.c_int64()
+        capi.check(self.L.cfdb_profile_get(self.h, kernel.encode(), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def launch_count(self):
+        return self.L.cfdb_launch_count(self.h)
+
+    def convergence(self):
+        """sqrt(ER_i/ERR_i), the four columns of <name>.cnv (ns2DComp.ALE.f90:199)."""
+        er, err = self.norms()
+        return [math.sqrt(a / b) if b != 0 else float("nan") for a, b in zip(er, err)]
+
+    # ---- call-site mode (host arrays, reference argument order) ------------------------------
+    def calcrhs(self, rhs, U, theta, T, dNx, dNy, area, shoc, dtl, ts1, ts2, ts3, Cv, lambda_ref, mu_ref, gamma0, T_inf, cte):
+        capi.check(self.L.cfdb_calcrhs(self.h, rhs, U, theta, T, dNx, dNy, area, shoc, dtl, ts1, ts2, ts3, self.lc.inpoel,
+                                       self.nelem, self.npoin, Cv, lambda_ref, mu_ref, gamma0, T_inf, cte))
+        return rhs
+
+    def fuente(self, rhs, U, w_x, w_y, dNx, dNy, area, dtl):
+        capi.check(self.L.cfdb_fuente(self.h, rhs, U, w_x, w_y, dNx, dNy, area, dtl, self.lc.inpoel, self.nelem, self.npoin))
+        return rhs
+
+    def deltat(self, area, T, vel_x, vel_y, w_x, w_y, FSAFE, FR, GAMA, T_inf):
+        dtmin, dt = np.zeros(1), np.zeros(self.nelem)
+        capi.check(self.L.cfdb_deltat(self.h, dtmin, dt, self.lc.inpoel, area, T, vel_x, vel_y, w_x, w_y, self.nelem,
+                                      self.npoin, FSAFE, FR, GAMA, T_inf))
+        return dtmin[0], dt
+
+    def estab(self, U, T, vel_x, vel_y, w_x, w_y, GAMM, dNx, dNy, FR, DTMIN, RHOINF, TINF):
+        out = [np.zeros(self.nelem) for _ in range(4)]
+        capi.check(self.L.cfdb_estab(self.h, U, T, vel_x, vel_y, w_x, w_y, GAMM, dNx, dNy, self.lc.inpoel, self.nelem,
+                                     self.npoin, FR, DTMIN, RHOINF, TINF, *out))
+        return out
+
+    def deriv(self, X, Y):
+        E = self.nelem
+        area, HH, HHX, HHY, dNx, dNy, hmin = (np.zeros(E), np.zeros(E), np.zeros(E), np.zeros(E), np.zeros(3 * E),
+                                              np.zeros(3 * E), np.zeros(1))
+        capi.check(self.L.cfdb_deriv(self.h, X, Y, self.lc.inpoel, E, self.npoin, area, HH, HHX, HHY, dNx, dNy, hmin))
+        return area, HH, HHX, HHY, dNx, dNy, hmin[0]
+
+    def masas(self, area):
+        M = np.zeros(self.npoin)
+        capi.check(self.L.cfdb_masas(self.h, area, self.lc.inpoel, self.nelem, self.npoin, M))
+        return M
+
+    def normales(self, X, Y):
+        m = C.c_int32()
+        nw = max(1, 2 * self.lc.wall.shape[0])
+        ip, nx, ny = np.zeros(nw, np.int32), np.zeros(nw), np.zeros(nw)
+        capi.check(self.L.cfdb_normales(self.h, self.lc.wall, self.lc.wall.shape[0], X, Y, self.npoin, C.byref(m), ip, nx, ny))
+        return m.value, ip[: m.value], nx[: m.value], ny[: m.value]
+
+    def laplace(self, area, dNx, dNy, X, Y):
+        nnz = self.L.cfdb_field_size(self.h, b"lap_sparse")
+        sp, dg = np.zeros(nnz), np.zeros(self.npoin)
+        capi.check(self.L.cfdb_laplace(self.h, self.lc.inpoel, area, dNx, dNy, X, Y, self.nelem, self.npoin, sp, dg))
+        return sp, dg
+
+    def bicg(self, A, idx, rowptr, diag, x, b, x_fix, fix_idx):
+        it = C.c_int32()
+        capi.check(self.L.cfdb_bicg(self.h, A, idx, rowptr, diag, x, b, x_fix, fix_idx, self.npoin, fix_idx.size, C.byref(it)))
+        return it.value
+
+    def spmv(self, A, idx, rowptr, v):
+        y = np.zeros(v.size)
+        capi.check(self.L.cfdb_spmv(self.h, A, idx, rowptr, v, y, v.size, int(rowptr[v.size])))
+        return y
+
+    def vecdot(self, x, y):
+        r = C.c_double()
+        capi.check(self.L.cfdb_vecdot(self.h, x.size, x, y, C.byref(r)))
+        return r.value
+
+    def gcl_main(self, M, W_x, W_y, W_x_old, W_y_old, area_old, dNx, dNy, area, dt):
+        capi.check(self.L.cfdb_gcl_main(self.h, M, W_x, W_y, W_x_old, W_y_old, area_old, dNx, dNy, area, self.lc.inpoel,
+                                        self.nelem, self.npoin, dt))
+        return M

@@ -1,0 +1,1019 @@
+// ORACLE — CPU restatement of the per-timestep hot path of chanshing/cfd.
+//
+// TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is linked, imported or executed by the
+// product (cfd_b200/, include/); only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may use it, and there only as the checker / baseline.
+//
+// PARITY UNPINNED: the reference ships no tests, golden vectors or input decks
+// and cannot be compiled here (no Fortran compiler in the image), so this
+// restatement is pinned only by (1) analytic invariants checked in tests/test_oracle_*.py and
+// (2) golden vectors generated from this file itself (tests/golden/, guards refactors).
+//
+// Conventions kept from the Fortran: arrays are column-major, U(4,npoin) = 4 consecutive
+// doubles per node, inpoel(3,nelem) = 3 consecutive int32 per element, all node/element ids
+// stored 1-based; CSR rowptr 0-based offsets, column ids 1-based, diagonal first.
+// Each function cites the reference lines it follows.  Evaluation order is the source's
+// left-to-right order; compile with -O2 -ffp-contract=off (see orc_math.h).
+//
+// Two scatter modes: seq (default, element order = the reference at one thread, the truth
+// for verification) and omp (ORC_OMP builds: `#pragma omp atomic` like the reference's
+// !$OMP ATOMIC sites — timing only, summation order undefined).
+#include "orc_math.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#ifdef ORC_OMP
+#include <omp.h>
+#define OMP_FOR _Pragma("omp parallel for schedule(static)")
+#define OMP_ATOMIC _Pragma("omp atomic")
+#else
+#define OMP_FOR
+#define OMP_ATOMIC
+#endif
+
+using std::vector;
+
+namespace orc {
+
+// ------------------------------------------------------------------------------------------
+// pointNeighbor.f90:5-43  getEsup — elements surrounding points (histogram, scan, fill)
+// esup2[0..npoin] 0-based offsets, esup1 1-based element ids in ascending order per node.
+static void get_esup(const int* inpoel, int nelem, int npoin, vector<int>& esup1, vector<int>& esup2) {
+    esup2.assign(npoin + 1, 0);
+    for (int ie = 0; ie < nelem; ++ie)
+        for (int i = 0; i < 3; ++i) esup2[inpoel[3 * ie + i]] += 1;  // index ipoi1 = node+1 (1-based) == node (0-based)+1
+    for (int ip = 1; ip <= npoin; ++ip) esup2[ip] += esup2[ip - 1];
+    esup1.assign(esup2[npoin], 0);
+    // fill using esup2 as running cursor shifted by one (pointNeighbor.f90:29-36)
+    vector<int> cur(esup2.begin(), esup2.end() - 1);
+    for (int ie = 0; ie < nelem; ++ie)
+        for (int i = 0; i < 3; ++i) {
+            int ip = inpoel[3 * ie + i] - 1;
+            esup1[cur[ip]++] = ie + 1;
+        }
+}
+
+// pointNeighbor.f90:45-91  getPsup — points surrounding points, first-encounter order
+static void get_psup(const int* inpoel, int nelem, int npoin, const vector<int>& esup1,
+                     const vector<int>& esup2, vector<int>& psup1, vector<int>& psup2) {
+    (void)nelem;
+    vector<int> lpoin(npoin, 0);
+    psup2.assign(npoin + 1, 0);
+    psup1.clear();
+    for (int ip = 1; ip <= npoin; ++ip) {
+        for (int k = esup2[ip - 1]; k < esup2[ip]; ++k) {
+            int ie = esup1[k];
+            for (int i = 0; i < 3; ++i) {
+                int jp = inpoel[3 * (ie - 1) + i];
+                if (jp != ip && lpoin[jp - 1] != ip) {
+                    psup1.push_back(jp);
+                    lpoin[jp - 1] = ip;
+                }
+            }
+        }
+        psup2[ip] = (int)psup1.size();
+    }
+}
+
+#include "smoothing.inc"
+
+// ------------------------------------------------------------------------------------------
+// subrutinas.f90:88-126  deriv
+static void deriv(const double* X, const double* Y, const int* inpoel, int nelem, double* area,
+                  double* HH, double* HHX, double* HHY, double* dNx, double* dNy, double* hmin) {
+    OMP_FOR
+    for (int ie = 0; ie < nelem; ++ie) {
+        double x1 = X[inpoel[3 * ie] - 1], x2 = X[inpoel[3 * ie + 1] - 1], x3 = X[inpoel[3 * ie + 2] - 1];
+        double y1 = Y[inpoel[3 * ie] - 1], y2 = Y[inpoel[3 * ie + 1] - 1], y3 = Y[inpoel[3 * ie + 2] - 1];
+        double a = (x2 * y3 + x3 * y1 + x1 * y2 - (x2 * y1 + x3 * y2 + x1 * y3)) / 2.0;  // :106-107
+        area[ie] = a;
+        dNx[3 * ie + 0] = (y2 - y3) / (2.0 * a);  // :110-115
+        dNx[3 * ie + 1] = (y3 - y1) / (2.0 * a);
+        dNx[3 * ie + 2] = (y1 - y2) / (2.0 * a);
+        dNy[3 * ie + 0] = (x3 - x2) / (2.0 * a);
+        dNy[3 * ie + 1] = (x1 - x3) / (2.0 * a);
+        dNy[3 * ie + 2] = (x2 - x1) / (2.0 * a);
+        HH[ie] = std::sqrt(a);                    // :117
+        HHX[ie] = std::fabs(std::min(std::min(x3 - x2, x1 - x3), x2 - x1));  // :118
+        HHY[ie] = std::fabs(std::min(std::min(y3 - y2, y1 - y3), y2 - y1));  // :119
+    }
+    double h = HH[0];
+    for (int ie = 1; ie < nelem; ++ie) h = HH[ie] < h ? HH[ie] : h;  // minval :124
+    if (h > 1.e10) h = 1.e10;
+    *hmin = h;
+}
+
+// subrutinas.f90:128-153  MASAS
+static void masas(const double* area, const int* inpoel, int nelem, int npoin, double* M) {
+    for (int ip = 0; ip < npoin; ++ip) M[ip] = 0.0;
+    OMP_FOR
+    for (int ie = 0; ie < nelem; ++ie)
+        for (int i = 0; i < 3; ++i) {
+            OMP_ATOMIC
+            M[inpoel[3 * ie + i] - 1] += area[ie] / 3.0;
+        }
+}
+
+// subrutinas.f90:7-64  normales; returns m, fills n_ipoin(1-based ids), n_x, n_y
+static int normales(const int* wall, int nwall, const double* X, const double* Y, int npoin,
+                    int* n_ipoin, double* n_x, double* n_y) {
+    vector<double> numx(npoin, 0.0), numy(npoin, 0.0), den(npoin, 0.0);
+    for (int iw = 0; iw < nwall; ++iw) {
+        int a = wall[2 * iw] - 1, b = wall[2 * iw + 1] - 1;
+        double lx = Y[b] - Y[a];
+        double ly = -(X[b] - X[a]);
+        double l = std::sqrt(lx * lx + ly * ly);
+        numx[a] += lx; numy[a] += ly; den[a] += l;
+        numx[b] += lx; numy[b] += ly; den[b] += l;
+    }
+    int m = 0;
+    for (int ip = 0; ip < npoin; ++ip) {
+        if (den[ip] > 1.e-6) {
+            double lx = numx[ip] / den[ip], ly = numy[ip] / den[ip];
+            double nrm = std::sqrt(lx * lx + ly * ly);
+            if (nrm > 0.2) {
+                n_ipoin[m] = ip + 1;
+                n_x[m] = lx / nrm;
+                n_y[m] = ly / nrm;
+                ++m;
+            }
+        }
+    }
+    return m;
+}
+
+// subrutinas.f90:66-85  normalvel
+static void normalvel(int m, const int* n_ipoin, const double* n_x, const double* n_y, double* vel_x,
+                      double* vel_y, const double* w_x, const double* w_y) {
+    for (int i = 0; i < m; ++i) {
+        int ip = n_ipoin[i] - 1;
+        double vx = vel_x[ip], vy = vel_y[ip], wx = w_x[ip], wy = w_y[ip];
+        double p = -n_y[i] * (vx - wx) + n_x[i] * (vy - wy);
+        vel_x[ip] = -n_y[i] * p + wx;
+        vel_y[ip] = n_x[i] * p + wy;
+    }
+}
+
+// subrutinas.f90:155-218  deltat
+static void deltat(int nelem, const int* inpoel, const double* area, const double* T, const double* VEL_X,
+                   const double* VEL_Y, const double* W_X, const double* W_Y, double FSAFE, double FR,
+                   double GAMA, double T_inf, double* DT, double* dtmin_out) {
+    double DTMIN = 1.e20;
+    for (int ie = 0; ie < nelem; ++ie) {
+        double VUMAX = 0.0, VVMAX = 0.0;
+        int n1 = inpoel[3 * ie] - 1, n2 = inpoel[3 * ie + 1] - 1, n3 = inpoel[3 * ie + 2] - 1;
+        double T_iel = (T[n1] + T[n2] + T[n3]) / 3.0;
+        // VC = DSQRT(GAMA*FR*T_iel) is computed and never used (:179)
+        (void)GAMA; (void)FR;
+        for (int i = 0; i < 3; ++i) {
+            int ip = inpoel[3 * ie + i] - 1;
+            double VU = std::fabs(VEL_X[ip] - W_X[ip]);
+            double VV = std::fabs(VEL_Y[ip] - W_Y[ip]);
+            if (VU > VUMAX) VUMAX = VU;
+            if (VV > VVMAX) VVMAX = VV;
+        }
+        double HH = std::sqrt(2.0 * area[ie]);
+        double VEL = pow05(VUMAX * VUMAX + VVMAX * VVMAX);  // (..)**.5D0 :194
+        double smu = 110.0;
+        double fmu = 0.017 * pow15(T_iel / T_inf) * (T_inf + smu) / (T_iel + smu);  // :196
+        double ET = fmu;
+        double Pe = (VEL * HH) / (2.0 * ET);
+        double q = Pe / 3.0;
+        double ALPHA = q < 1.0 ? q : 1.0;                               // MIN(Pe/3,1) :201
+        double DELTATU = 1.0 / (4.0 * ET / (HH * HH) + ALPHA * VEL / HH);  // :203
+        double DELTATC = 1.0 / (4.0 * ET / (HH * HH));                  // :204
+        double DTELEM = FSAFE / (1.0 / DELTATC + 1.0 / DELTATU);        // :206
+        DT[ie] = DTELEM;
+        if (DTELEM < DTMIN) DTMIN = DTELEM;
+    }
+    double COTA = 10.0 * DTMIN;
+    for (int ie = 0; ie < nelem; ++ie)
+        if (DT[ie] > COTA) DT[ie] = COTA;
+    *dtmin_out = DTMIN;
+}
+
+// subrutinas.f90:332-446  ESTAB  (RMU is an unused dummy; UINF,VINF only feed a dead VEL2 :347)
+static void estab(int nelem, const int* inpoel, const double* U, const double* T, const double* VEL_X,
+                  const double* VEL_Y, const double* W_X, const double* W_Y, const double* GAMM,
+                  const double* dNx, const double* dNy, double FR, double DTMIN, double RHOINF, double TINF,
+                  double* SHOC, double* T_SUGN1, double* T_SUGN2, double* T_SUGN3) {
+    OMP_FOR
+    for (int ie = 0; ie < nelem; ++ie) {
+        int N1 = inpoel[3 * ie] - 1, N2 = inpoel[3 * ie + 1] - 1, N3 = inpoel[3 * ie + 2] - 1;
+        const double* nx = dNx + 3 * ie;
+        const double* ny = dNy + 3 * ie;
+        double GM = (GAMM[N1] + GAMM[N2] + GAMM[N3]) / 3.0;
+        double TAU = 0.0, H_RGNE = 0.0, H_RGN = 0.0, H_JGN = 0.0;
+        double RHO_ELEM = (U[4 * N1] + U[4 * N2] + U[4 * N3]) / 3.0;
+        double VX = (VEL_X[N1] + VEL_X[N2] + VEL_X[N3]) / 3.0;
+        double VY = (VEL_Y[N1] + VEL_Y[N2] + VEL_Y[N3]) / 3.0;
+        double WX = (W_X[N1] + W_X[N2] + W_X[N3]) / 3.0;
+        double WY = (W_Y[N1] + W_Y[N2] + W_Y[N3]) / 3.0;
+        VX = VX - WX; VY = VY - WY;
+        double VEL2 = std::sqrt(VX * VX + VY * VY);
+        double DRX = U[4 * N1] * nx[0] + U[4 * N2] * nx[1] + U[4 * N3] * nx[2];  // :372
+        double DRY = U[4 * N1] * ny[0] + U[4 * N2] * ny[1] + U[4 * N3] * ny[2];
+        double DR2 = std::sqrt(DRX * DRX + DRY * DRY) + 1.e-20;
+        double DTX = T[N1] * nx[0] + T[N2] * nx[1] + T[N3] * nx[2];              // :376
+        double DTY = T[N1] * ny[0] + T[N2] * ny[1] + T[N3] * ny[2];
+        double DT2 = std::sqrt(DTX * DTX + DTY * DTY) + 1.e-20;
+        double DUX = VEL2 * nx[0] + VEL2 * nx[1] + VEL2 * nx[2];                 // :380 (noise, F9)
+        double DUY = VEL2 * ny[0] + VEL2 * ny[1] + VEL2 * ny[2];
+        double DU2 = std::sqrt(DUX * DUX + DUY * DUY) + 1.e-20;
+        double RTX = DTX / DT2, RTY = DTY / DT2;
+        double RJX = DRX / DR2, RJY = DRY / DR2;
+        double RUX = DUX / DU2, RUY = DUY / DU2;
+        double TEMP = (T[N1] + T[N2] + T[N3]) / 3.0;
+        double C = std::sqrt(GM * FR * TEMP);
+        double smu = 110.0;
+        double fmu = 0.017 * pow15(TEMP / TINF) * (TINF + smu) / (TEMP + smu);   // :400
+        for (int i = 0; i < 3; ++i) {
+            double TERM_1 = std::fabs(VX * nx[i] + VY * ny[i]);
+            double TERM_2 = std::fabs(RJX * nx[i] + RJY * ny[i]);
+            double H_RGN1 = std::fabs(RTX * nx[i] + RTY * ny[i]);
+            double H_RGN2 = std::fabs(RUX * nx[i] + RUY * ny[i]);
+            TAU = TAU + TERM_1 + TERM_2 * C;
+            H_RGNE = H_RGNE + H_RGN1;
+            H_RGN = H_RGN + H_RGN2;
+            H_JGN = H_JGN + TERM_2;
+        }
+        TAU = 1.0 / TAU;
+        H_RGNE = 2.0 / H_RGNE;
+        H_RGN = 2.0 / H_RGN;
+        if (H_RGN > 1.e1) H_RGN = 0.0;
+        H_JGN = 2.0 / H_JGN;
+        if (H_JGN > 1.e1) H_JGN = 0.0;
+        double TR1 = DR2 * H_JGN / RHO_ELEM;
+        double ZZZ = H_JGN / (2.0 * C);
+        SHOC[ie] = (TR1 + TR1 * TR1) * .5 * (C * C) * ZZZ;                       // :426
+        double RESUMEN = 1.0 / (TAU * TAU) + (2.0 / DTMIN) * (2.0 / DTMIN);      // :428
+        double RRR = powm05(RESUMEN);
+        T_SUGN1[ie] = RRR; T_SUGN2[ie] = RRR; T_SUGN3[ie] = RRR;
+        if (fmu != 0.0) {
+            double TAU_SUNG3 = (H_RGN * H_RGN) / (4.0 * fmu / RHOINF);
+            double TAU_SUNG3_E = (H_RGNE * H_RGNE) / (4.0 * fmu / RHOINF);
+            T_SUGN2[ie] = powm05(RESUMEN + 1.0 / (TAU_SUNG3 * TAU_SUNG3));
+            T_SUGN3[ie] = powm05(RESUMEN + 1.0 / (TAU_SUNG3_E * TAU_SUNG3_E));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// calcRHS.f90:36-151  — per-element contribution rhs_tmp(4,3) (before the scatter)
+struct GasK { double Cv, lambda_ref, mu_ref, gamma0, T_inf, cte; };
+
+static inline void calcrhs_elem(const GasK& g, const double* U, const double* theta, const double* T,
+                                const int* ip3, const double* Nx, const double* Ny, double area, double shoc,
+                                double dtl, double tau1, double tau2, double tau3, double rt[3][4]) {
+    static const double N[3][3] = {{0.0, .5, .5}, {.5, 0.0, .5}, {.5, .5, 0.0}};  // N(:,k) columns :18-23
+    const double gamma0 = g.gamma0, Cv = g.Cv;
+    const double* U1 = U + 4 * (ip3[0] - 1);
+    const double* U2 = U + 4 * (ip3[1] - 1);
+    const double* U3 = U + 4 * (ip3[2] - 1);
+    const double* th1 = theta + 4 * (ip3[0] - 1);
+    const double* th2 = theta + 4 * (ip3[1] - 1);
+    const double* th3 = theta + 4 * (ip3[2] - 1);
+    double Ux[4], Uy[4];
+    for (int i = 0; i < 4; ++i) {
+        rt[0][i] = rt[1][i] = rt[2][i] = 0.0;
+        Ux[i] = U1[i] * Nx[0] + U2[i] * Nx[1] + U3[i] * Nx[2];  // :43
+        Uy[i] = U1[i] * Ny[0] + U2[i] * Ny[1] + U3[i] * Ny[2];  // :44
+    }
+    const double tau[3] = {tau1, tau2, tau3};
+    double nu = shoc * g.cte;
+    double T_avg = (T[ip3[0] - 1] + T[ip3[1] - 1] + T[ip3[2] - 1]) / 3.0;
+    double p15 = pow15(T_avg / g.T_inf);
+    double mu = g.mu_ref * p15 * (g.T_inf + 110) / (T_avg + 110);          // :50
+    double lambda = g.lambda_ref * p15 * (g.T_inf + 194) / (T_avg + 194);  // :51
+    for (int k = 0; k < 3; ++k) {
+        double U_k[4], theta_k[4];
+        for (int i = 0; i < 4; ++i) {
+            U_k[i] = N[k][0] * U1[i] + N[k][1] * U2[i] + N[k][2] * U3[i];          // :53-56
+            theta_k[i] = N[k][0] * th1[i] + N[k][1] * th2[i] + N[k][2] * th3[i];   // :57-60
+        }
+        double rho = U_k[0];
+        double v1 = U_k[1] / rho, v2 = U_k[2] / rho, e = U_k[3] / rho;
+        double V_sq = v1 * v1 + v2 * v2;
+        double A[4];  // AiUi :73-84
+        A[0] = Ux[1] + Uy[2];
+        A[1] = (1.0 / 2.0) * Ux[0] * (V_sq * (gamma0 - 1) - 2 * (v1 * v1)) - Ux[1] * v1 * (gamma0 - 3) -
+               Ux[2] * v2 * (gamma0 - 1) + Ux[3] * (gamma0 - 1) - Uy[0] * v1 * v2 + Uy[1] * v2 + Uy[2] * v1;
+        A[2] = -Ux[0] * v1 * v2 + Ux[1] * v2 + Ux[2] * v1 +
+               (1.0 / 2.0) * Uy[0] * (V_sq * (gamma0 - 1) - 2 * (v2 * v2)) - Uy[1] * v1 * (gamma0 - 1) -
+               Uy[2] * v2 * (gamma0 - 3) + Uy[3] * (gamma0 - 1);
+        A[3] = Ux[0] * v1 * (V_sq * (gamma0 - 1) - e * gamma0) -
+               1.0 / 2.0 * Ux[1] * (V_sq * (gamma0 - 1) - 2 * e * gamma0 + 2 * (v1 * v1) * (gamma0 - 1)) -
+               Ux[2] * v1 * v2 * (gamma0 - 1) + Ux[3] * gamma0 * v1 +
+               Uy[0] * v2 * (V_sq * (gamma0 - 1) - e * gamma0) - Uy[1] * v1 * v2 * (gamma0 - 1) -
+               1.0 / 2.0 * Uy[2] * (V_sq * (gamma0 - 1) - 2 * e * gamma0 + 2 * (v2 * v2) * (gamma0 - 1)) +
+               Uy[3] * gamma0 * v2;
+        double At[4];  // AiUi_theta :86
+        for (int i = 0; i < 4; ++i) At[i] = +theta_k[i] + A[i];
+        double A1[4], A2[4];  // :88-107
+        A1[0] = At[1];
+        A1[1] = v1 * (-gamma0 + 3) * At[1] - v2 * (gamma0 - 1) * At[2] + (gamma0 - 1) * At[3] +
+                ((1.0 / 2.0) * V_sq * (gamma0 - 1) - v1 * v1) * At[0];
+        A1[2] = -v1 * v2 * At[0] + v1 * At[2] + v2 * At[1];
+        A1[3] = gamma0 * v1 * At[3] - v1 * v2 * (gamma0 - 1) * At[2] +
+                v1 * (V_sq * (gamma0 - 1) - e * gamma0) * At[0] +
+                (-1.0 / 2.0 * V_sq * (gamma0 - 1) + e * gamma0 - v1 * v1 * (gamma0 - 1)) * At[1];
+        A2[0] = At[2];
+        A2[1] = -v1 * v2 * At[0] + v1 * At[2] + v2 * At[1];
+        A2[2] = -v1 * (gamma0 - 1) * At[1] + v2 * (-gamma0 + 3) * At[2] + (gamma0 - 1) * At[3] +
+                ((1.0 / 2.0) * V_sq * (gamma0 - 1) - v2 * v2) * At[0];
+        A2[3] = gamma0 * v2 * At[3] - v1 * v2 * (gamma0 - 1) * At[1] +
+                v2 * (V_sq * (gamma0 - 1) - e * gamma0) * At[0] +
+                (-1.0 / 2.0 * V_sq * (gamma0 - 1) + e * gamma0 - v2 * v2 * (gamma0 - 1)) * At[2];
+        for (int n = 0; n < 3; ++n)  // :109-117
+            for (int i = 0; i < 4; ++i)
+                rt[n][i] = rt[n][i] + N[k][n] * A[i] + tau[n] * (Nx[n] * A1[i] + Ny[n] * A2[i]) +
+                           nu * (Nx[n] * Ux[i] + Ny[n] * Uy[i]);
+        if (g.mu_ref > std::numeric_limits<double>::min()) {  // tiny(0d0) :119
+            double K1[4], K2[4];
+            K1[1] = (2.0 / 3.0) * mu * (-2 * Ux[0] * v1 + 2 * Ux[1] + Uy[0] * v2 - Uy[2]) / rho;
+            K1[2] = mu * (-Ux[0] * v2 + Ux[2] - Uy[0] * v1 + Uy[1]) / rho;
+            K1[3] = (1.0 / 3.0) *
+                    (Cv * mu * (-Uy[0] * v1 * v2 + 3 * Uy[1] * v2 - 2 * Uy[2] * v1) -
+                     Ux[0] * (Cv * mu * (3 * V_sq + v1 * v1) - 3 * lambda * (V_sq - e)) +
+                     Ux[1] * v1 * (4 * Cv * mu - 3 * lambda) + 3 * Ux[2] * v2 * (Cv * mu - lambda) +
+                     3 * Ux[3] * lambda) /
+                    (Cv * rho);
+            K2[1] = mu * (-Ux[0] * v2 + Ux[2] - Uy[0] * v1 + Uy[1]) / rho;
+            K2[2] = (2.0 / 3.0) * mu * (Ux[0] * v1 - Ux[1] - 2 * Uy[0] * v2 + 2 * Uy[2]) / rho;
+            K2[3] = (1.0 / 3.0) *
+                    (Cv * mu * (-Ux[0] * v1 * v2 - 2 * Ux[1] * v2 + 3 * Ux[2] * v1) -
+                     Uy[0] * (Cv * mu * (3 * V_sq + v2 * v2) - 3 * lambda * (V_sq - e)) +
+                     3 * Uy[1] * v1 * (Cv * mu - lambda) + Uy[2] * v2 * (4 * Cv * mu - 3 * lambda) +
+                     3 * Uy[3] * lambda) /
+                    (Cv * rho);
+            for (int n = 0; n < 3; ++n)  // :134-136
+                for (int i = 1; i < 4; ++i) rt[n][i] = rt[n][i] + (Nx[n] * K1[i] + Ny[n] * K2[i]);
+        }
+    }
+    for (int n = 0; n < 3; ++n)
+        for (int i = 0; i < 4; ++i) rt[n][i] = rt[n][i] * area * dtl / 3.0;  // :141
+}
+
+// calcRHS.f90:4-154  (rhs is inout, pre-zeroed by the caller subrutinas.f90:679-683)
+static void calcrhs(const GasK& g, double* rhs, const double* U, const double* theta, const double* T,
+                    const double* dNx, const double* dNy, const double* area, const double* shoc,
+                    const double* dtl, const double* ts1, const double* ts2, const double* ts3,
+                    const int* inpoel, int nelem) {
+    OMP_FOR
+    for (int ie = 0; ie < nelem; ++ie) {
+        double rt[3][4];
+        calcrhs_elem(g, U, theta, T, inpoel + 3 * ie, dNx + 3 * ie, dNy + 3 * ie, area[ie], shoc[ie], dtl[ie],
+                     ts1[ie], ts2[ie], ts3[ie], rt);
+        for (int i = 0; i < 4; ++i)
+            for (int n = 0; n < 3; ++n) {  // :143-150 (i outer, node inner)
+                OMP_ATOMIC
+                rhs[4 * (inpoel[3 * ie + n] - 1) + i] += rt[n][i];
+            }
+    }
+}
+
+// subrutinas.f90:1036-1094  FUENTE — per-element contribution
+static inline void fuente_elem(const double* U, const double* w_x, const double* w_y, const int* ip3,
+                               const double* Nx, const double* Ny, double area, double dtl, double rt[3][4]) {
+    // sp(:,1)=(.5,.5,0) sp(:,2)=(0,.5,.5) sp(:,3)=(.5,0,.5)  (:1052-1054); sp[c][r] = sp(r+1,c+1)
+    static const double sp[3][3] = {{.5, .5, 0.0}, {0.0, .5, .5}, {.5, 0.0, .5}};
+    const double* U1 = U + 4 * (ip3[0] - 1);
+    const double* U2 = U + 4 * (ip3[1] - 1);
+    const double* U3 = U + 4 * (ip3[2] - 1);
+    double Ux[4], Uy[4];
+    for (int i = 0; i < 4; ++i) {
+        Ux[i] = U1[i] * Nx[0] + U2[i] * Nx[1] + U3[i] * Nx[2];
+        Uy[i] = U1[i] * Ny[0] + U2[i] * Ny[1] + U3[i] * Ny[2];
+    }
+    double AR = area * dtl / 3.0;
+    double wx[3], wy[3];
+    for (int c = 0; c < 3; ++c) {  // sum() = sequential from zero
+        double sx = 0.0, sy = 0.0;
+        for (int r = 0; r < 3; ++r) {
+            sx = sx + sp[c][r] * w_x[ip3[r] - 1];
+            sy = sy + sp[c][r] * w_y[ip3[r] - 1];
+        }
+        wx[c] = sx; wy[c] = sy;
+    }
+    for (int n = 0; n < 3; ++n)
+        for (int i = 0; i < 4; ++i)
+            rt[n][i] = -AR * (sp[0][n] * (Ux[i] * wx[0] + Uy[i] * wy[0]) + sp[1][n] * (Ux[i] * wx[1] + Uy[i] * wy[1]) +
+                              sp[2][n] * (Ux[i] * wx[2] + Uy[i] * wy[2]));
+}
+
+static void fuente(double* rhs, const double* U, const double* w_x, const double* w_y, const double* dNx,
+                   const double* dNy, const double* area, const double* dtl, const int* inpoel, int nelem) {
+    OMP_FOR
+    for (int ie = 0; ie < nelem; ++ie) {
+        double rt[3][4];
+        fuente_elem(U, w_x, w_y, inpoel + 3 * ie, dNx + 3 * ie, dNy + 3 * ie, area[ie], dtl[ie], rt);
+        for (int n = 0; n < 3; ++n)
+            for (int i = 0; i < 4; ++i) {  // :1080-1089 (node outer, eqn inner)
+                OMP_ATOMIC
+                rhs[4 * (inpoel[3 * ie + n] - 1) + i] += rt[n][i];
+            }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// mLaplace.f90:96-108  mu
+static inline double mu_metric(const double* X3, const double* Y3) {
+    const double TWOSQRT3 = 3.46410161513775;
+    double area = X3[1] * Y3[2] + X3[2] * Y3[0] + X3[0] * Y3[1] - (X3[1] * Y3[0] + X3[2] * Y3[1] + X3[0] * Y3[2]);
+    double l1 = (X3[2] - X3[1]) * (X3[2] - X3[1]) + (Y3[2] - Y3[1]) * (Y3[2] - Y3[1]);
+    double l2 = (X3[0] - X3[2]) * (X3[0] - X3[2]) + (Y3[0] - Y3[2]) * (Y3[0] - Y3[2]);
+    double l3 = (X3[1] - X3[0]) * (X3[1] - X3[0]) + (Y3[1] - Y3[0]) * (Y3[1] - Y3[0]);
+    double l = l1 + l2 + l3;
+    return TWOSQRT3 * area / l;
+}
+
+// mLaplace.f90:60-94  initialize — CSR pattern from psup (diag first)
+static void laplace_init(int npoin, const vector<int>& psup1, const vector<int>& psup2, vector<int>& lap_idx,
+                         vector<int>& lap_rowptr) {
+    lap_rowptr.assign(npoin + 1, 0);
+    for (int i = 2; i <= npoin + 1; ++i) lap_rowptr[i - 1] = psup2[i - 1] + i - 1;
+    lap_idx.assign(psup1.size() + npoin, 0);
+    for (int ip = 1; ip <= npoin; ++ip) {
+        lap_idx[lap_rowptr[ip - 1]] = ip;
+        int ipsup = psup2[ip - 1];
+        for (int i = lap_rowptr[ip - 1] + 1; i < lap_rowptr[ip]; ++i) lap_idx[i] = psup1[ipsup++];
+    }
+}
+
+// mLaplace.f90:7-58  laplace values (node-gather over esup, pattern search, F10 race irrelevant at 1 thread)
+static void laplace(const int* inpoel, const double* dNx, const double* dNy, const double* X, const double* Y,
+                    int npoin, const vector<int>& esup1, const vector<int>& esup2, const vector<int>& lap_idx,
+                    const vector<int>& lap_rowptr, double* lap_sparse, double* lap_diag) {
+    for (int k = 0; k < lap_rowptr[npoin]; ++k) lap_sparse[k] = 0.0;
+    OMP_FOR
+    for (int ip = 1; ip <= npoin; ++ip) {
+        for (int ies = esup2[ip - 1]; ies < esup2[ip]; ++ies) {
+            int ie = esup1[ies] - 1;
+            double X3[3], Y3[3];
+            for (int i = 0; i < 3; ++i) { X3[i] = X[inpoel[3 * ie + i] - 1]; Y3[i] = Y[inpoel[3 * ie + i] - 1]; }
+            double m = mu_metric(X3, Y3);
+            double q = 1 / (m * m);
+            for (int i = 0; i < 3; ++i) {
+                if (inpoel[3 * ie + i] == ip) {
+                    for (int j = 0; j < 3; ++j) {
+                        int kp = inpoel[3 * ie + j];
+                        for (int k = lap_rowptr[ip - 1]; k < lap_rowptr[ip]; ++k)
+                            if (lap_idx[k] == kp)
+                                lap_sparse[k] = lap_sparse[k] + (dNx[3 * ie + i] * dNx[3 * ie + j] + dNy[3 * ie + i] * dNy[3 * ie + j]) * q;
+                    }
+                }
+            }
+        }
+        lap_diag[ip - 1] = lap_sparse[lap_rowptr[ip - 1]];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// biconjGrad.f90:171-190 SpMV
+static void spmv(const double* A, const int* idx, const int* rowptr, const double* v, double* y, int npoin) {
+    OMP_FOR
+    for (int i = 0; i < npoin; ++i) {
+        double dot = 0.0;
+        for (int j = rowptr[i]; j < rowptr[i + 1]; ++j) dot = dot + A[j] * v[idx[j] - 1];
+        y[i] = dot;
+    }
+}
+static double vecdot(int n, const double* x, const double* y) {  // :153-169, canonical order (orc_math.h)
+    return canon_sum(n, [&](long i) { return x[i] * y[i]; });
+}
+
+// biconjGrad.f90:8-62  biCG; returns iteration count k (or -1 on the early return :35)
+static int bicg(const double* A, const int* idx, const int* rowptr, const double* diag, double* x,
+                const double* b, const double* x_fix, const int* fixIdx, int npoin, int nfix,
+                vector<double>& y, vector<double>& p, vector<double>& r, vector<double>& z) {
+    y.resize(npoin); p.resize(npoin); r.resize(npoin); z.resize(npoin);
+    int k = 0;
+    const double tol = 1.e-10;
+    for (int i = 0; i < nfix; ++i) x[fixIdx[i] - 1] = 1.0 * x_fix[i];              // copy1 :28
+    spmv(A, idx, rowptr, x, y.data(), npoin);                                    // :29
+    for (int i = 0; i < nfix; ++i) y[fixIdx[i] - 1] = 1.e30 * x[fixIdx[i] - 1];    // copy2 :31
+    for (int i = 0; i < npoin; ++i) r[i] = -1.0 * y[i] + b[i];                    // vecsum :32
+    for (int i = 0; i < nfix; ++i) r[fixIdx[i] - 1] = 0.0;                        // assign2 :33
+    if (vecdot(npoin, r.data(), r.data()) < tol) return -1;                      // :35
+    for (int i = 0; i < npoin; ++i) p[i] = r[i] / diag[i];                        // vecdiv :37
+    double err_new = vecdot(npoin, r.data(), p.data());
+    spmv(A, idx, rowptr, p.data(), y.data(), npoin);
+    for (int i = 0; i < nfix; ++i) y[fixIdx[i] - 1] = 1.e30 * p[fixIdx[i] - 1];
+    double py = vecdot(npoin, p.data(), y.data());
+    double alfa = err_new / py;
+    for (int i = 0; i < npoin; ++i) x[i] = alfa * p[i] + x[i];                    // :44
+    double err_old = err_new;
+    while (std::fabs(err_old) > tol && k < 1000) {                               // :47
+        k = k + 1;
+        for (int i = 0; i < npoin; ++i) r[i] = -alfa * y[i] + r[i];
+        for (int i = 0; i < npoin; ++i) z[i] = r[i] / diag[i];
+        err_new = vecdot(npoin, r.data(), z.data());
+        double beta = err_new / err_old;
+        for (int i = 0; i < npoin; ++i) p[i] = beta * p[i] + z[i];
+        spmv(A, idx, rowptr, p.data(), y.data(), npoin);
+        for (int i = 0; i < nfix; ++i) y[fixIdx[i] - 1] = 1.e30 * p[fixIdx[i] - 1];
+        py = vecdot(npoin, p.data(), y.data());
+        alfa = err_new / py;
+        for (int i = 0; i < npoin; ++i) x[i] = alfa * p[i] + x[i];
+        err_old = err_new;
+    }
+    return k;
+}
+
+// gcl.f90:8-46  gcl_mod::main (orphan in the reference, F5; W_x used twice as written :38-41)
+static void gcl_main(double* M, const double* W_x, const double* W_y, const double* W_x_old,
+                     const double* W_y_old, const double* area_old, const double* dNx, const double* dNy,
+                     const double* area, const int* inpoel, int nelem, int npoin, double dt) {
+    (void)W_y; (void)W_y_old;
+    vector<double> tot1(npoin, 0.0), tot2(npoin, 0.0);
+    for (int ie = 0; ie < nelem; ++ie) {
+        const int* ip = inpoel + 3 * ie;
+        const double* nx = dNx + 3 * ie;
+        const double* ny = dNy + 3 * ie;
+        double w1 = W_x[ip[0] - 1], w2 = W_x[ip[1] - 1], w3 = W_x[ip[2] - 1];
+        double o1 = W_x_old[ip[0] - 1], o2 = W_x_old[ip[1] - 1], o3 = W_x_old[ip[2] - 1];
+        double divW = nx[0] * w1 + nx[1] * w2 + nx[2] * w3 + ny[0] * w1 + ny[1] * w2 + ny[2] * w3;
+        double divW_old = nx[0] * o1 + nx[1] * o2 + nx[2] * o3 + ny[0] * o1 + ny[1] * o2 + ny[2] * o3;
+        for (int i = 0; i < 3; ++i) {
+            tot1[ip[i] - 1] = tot1[ip[i] - 1] + divW * area[ie] / 3.0;
+            tot2[ip[i] - 1] = tot2[ip[i] - 1] + divW_old * area_old[ie] / 3.0;
+        }
+    }
+    for (int i = 0; i < npoin; ++i) M[i] = M[i] + dt * (tot1[i] + tot2[i]) / 2.0;
+}
+
+// ------------------------------------------------------------------------------------------
+// The driver state: module arrays of commonModules.f90 / dataLoader.f90:68-93 plus the locals of
+// PROGRAM NSComp2D (ns2DComp.ALE.f90:23-33).
+struct Params {  // InputData, dataLoader.f90:1-15 (CTE already inverted :59)
+    double FSAFE, U_inf, V_inf, MACH_inf, T_inf, RHO_inf, P_inf, C_inf;
+    double FMU, FGX, FGY, QH, FK, FR, FCv, GAMA, CTE;
+    double XREF[10], YREF[10];
+    int IRESTART, MAXITER, IPRINT, MOVIE, ITLOCAL, MOVING, NGAS, use_gcl;
+};
+
+struct Solver {
+    Params par;
+    int npoin = 0, nelem = 0;
+    vector<int> inpoel;
+    vector<double> X, Y, HHX, HHY, HH, M, area, dNx, dNy;
+    // BC lists (post-processed values, dataLoader.f90:121-268)
+    vector<int> ifixrho_node, ifixv_node, ifixt_node, wall, i_m, ifm, ilaux;
+    vector<double> rfixrho_value, rfixv_valuex, rfixv_valuey, rfixt_value;
+    int nset_numb = 0;
+    vector<int> set_n1[10], set_n2[10], set_el[10];
+    // state
+    vector<double> VEL_X, VEL_Y, W_X, W_Y, U, U1, RHS, RHS1, RHS2, RHS3, UN, P, T, RHO, E, RMACH;
+    vector<double> SHOC, T_SUGN1, T_SUGN2, T_SUGN3, GAMM, DTL, DT, X1, Y1;
+    // topology / laplace
+    vector<int> esup1, esup2, psup1, psup2, lap_idx, lap_rowptr;
+    vector<double> lap_sparse, lap_diag;
+    // normales
+    int n_m = 0;
+    vector<int> n_ipoin;
+    vector<double> n_x, n_y;
+    // meshMove
+    vector<double> b, pos_aux, dxpos, dypos, xpos, ypos, by, bp, br, bz;
+    double DISN[2] = {0, 0};
+    double FX[10], FY[10], RM[10];
+    // gcl
+    vector<double> W_x_old, W_y_old, area_old;
+    // loop scalars (ns2DComp.ALE.f90:109-134)
+    double TIME = 0, DTMIN = 0, DTMIN1 = 0, HMIN = 0;
+    int ITER = 0, BANDERA = 1, ITERPRINT = 0, norms_every_step = 1;
+    int last_bicg_iters[2] = {0, 0};
+    double ER[4], ERR[4];
+};
+
+// ns2DComp.ALE.f90:404-420  RESTART, free-stream branch
+static void restart_freestream(Solver& s) {
+    const Params& p = s.par;
+    double RHOAMB = p.RHO_inf, TAMB = p.T_inf, UAMB = p.U_inf, VAMB = p.V_inf, PAMB = p.RHO_inf * p.FR * p.T_inf;
+    for (int i = 0; i < s.npoin; ++i) {
+        s.U[4 * i] = RHOAMB;
+        s.U[4 * i + 1] = RHOAMB * UAMB;
+        s.U[4 * i + 2] = RHOAMB * VAMB;
+        double ENERGIA = PAMB / ((s.GAMM[i] - 1.0) * RHOAMB) + .5 * (UAMB * UAMB + VAMB * VAMB);
+        s.U[4 * i + 3] = ENERGIA * RHOAMB;
+        s.VEL_X[i] = UAMB; s.VEL_Y[i] = VAMB; s.T[i] = TAMB;
+    }
+}
+
+// NORMALES, DERIV, MASAS, laplace  (ns2DComp.ALE.f90:88-100 at init, :262-274 every step if MOVING).
+// GCL (gcl.f90, orphan in the reference — SURVEY.md F5) is wired at its natural site behind
+// par.use_gcl (default 0): putArea before DERIV, main after MASAS, putW afterwards.
+static void geometry(Solver& s, bool moving_step) {
+    bool gcl = moving_step && s.par.use_gcl;
+    if (gcl) s.area_old = s.area;  // gcl.f90:56-62 putArea
+    s.n_m = normales(s.wall.data(), (int)s.wall.size() / 2, s.X.data(), s.Y.data(), s.npoin, s.n_ipoin.data(),
+                     s.n_x.data(), s.n_y.data());
+    deriv(s.X.data(), s.Y.data(), s.inpoel.data(), s.nelem, s.area.data(), s.HH.data(), s.HHX.data(), s.HHY.data(),
+          s.dNx.data(), s.dNy.data(), &s.HMIN);
+    masas(s.area.data(), s.inpoel.data(), s.nelem, s.npoin, s.M.data());
+    if (gcl) {
+        gcl_main(s.M.data(), s.W_X.data(), s.W_Y.data(), s.W_x_old.data(), s.W_y_old.data(), s.area_old.data(),
+                 s.dNx.data(), s.dNy.data(), s.area.data(), s.inpoel.data(), s.nelem, s.npoin, s.DTMIN);
+        s.W_x_old = s.W_X; s.W_y_old = s.W_Y;  // gcl.f90:47-55 putW
+    }
+    laplace(s.inpoel.data(), s.dNx.data(), s.dNy.data(), s.X.data(), s.Y.data(), s.npoin, s.esup1, s.esup2, s.lap_idx,
+            s.lap_rowptr, s.lap_sparse.data(), s.lap_diag.data());
+}
+
+// subrutinas.f90:645-849  RK  (one stage = body of the IRK loop)
+static void rk_stage(Solver& s, int IRK, int NRK) {
+    const Params& p = s.par;
+    const int npoin = s.npoin, nelem = s.nelem;
+    double RK_FACT = 1.0 / (NRK + 1 - IRK);
+    if (IRK == 1) {
+        // cuarto_orden result is discarded: UN = 0.0 (:673-674, F7)
+        std::fill(s.UN.begin(), s.UN.end(), 0.0);
+        estab(nelem, s.inpoel.data(), s.U.data(), s.T.data(), s.VEL_X.data(), s.VEL_Y.data(), s.W_X.data(),
+              s.W_Y.data(), s.GAMM.data(), s.dNx.data(), s.dNy.data(), p.FR, s.DTMIN, p.RHO_inf, p.T_inf,
+              s.SHOC.data(), s.T_SUGN1.data(), s.T_SUGN2.data(), s.T_SUGN3.data());
+    }
+    std::fill(s.RHS.begin(), s.RHS.end(), 0.0);
+    GasK g{p.FCv, p.FK, p.FMU, p.GAMA, p.T_inf, p.CTE};
+    calcrhs(g, s.RHS.data(), s.U.data(), s.UN.data(), s.T.data(), s.dNx.data(), s.dNy.data(), s.area.data(),
+            s.SHOC.data(), s.DTL.data(), s.T_SUGN1.data(), s.T_SUGN2.data(), s.T_SUGN3.data(), s.inpoel.data(), nelem);
+    fuente(s.RHS.data(), s.U.data(), s.W_X.data(), s.W_Y.data(), s.dNx.data(), s.dNy.data(), s.area.data(),
+           s.DTL.data(), s.inpoel.data(), nelem);
+    OMP_FOR
+    for (int ip = 0; ip < npoin; ++ip) {
+        double f = RK_FACT / s.M[ip];
+        for (int i = 0; i < 4; ++i) s.U1[4 * ip + i] = s.U[4 * ip + i] - f * s.RHS[4 * ip + i];  // :697
+    }
+    OMP_FOR
+    for (int ip = 0; ip < npoin; ++ip) {  // :708-717 (NGAS==0)
+        s.RHO[ip] = s.U1[4 * ip];
+        s.VEL_X[ip] = s.U1[4 * ip + 1] / s.RHO[ip];
+        s.VEL_Y[ip] = s.U1[4 * ip + 2] / s.RHO[ip];
+        s.E[ip] = s.U1[4 * ip + 3] / s.RHO[ip];
+        double VEL2 = (s.VEL_X[ip] * s.VEL_X[ip] + s.VEL_Y[ip] * s.VEL_Y[ip]);
+        s.P[ip] = s.RHO[ip] * (s.GAMM[ip] - 1.0) * (s.E[ip] - .5 * VEL2);
+        s.T[ip] = s.P[ip] / (s.RHO[ip] * p.FR);
+        s.RMACH[ip] = std::sqrt(VEL2 / (s.T[ip] * s.GAMM[ip] * p.FR));
+    }
+    // fixvel :601-616
+    for (size_t i = 0; i < s.ifixv_node.size(); ++i) {
+        int j = s.ifixv_node[i] - 1;
+        s.VEL_X[j] = s.rfixv_valuex[i];
+        s.VEL_Y[j] = s.rfixv_valuey[i];
+    }
+    normalvel(s.n_m, s.n_ipoin.data(), s.n_x.data(), s.n_y.data(), s.VEL_X.data(), s.VEL_Y.data(), s.W_X.data(),
+              s.W_Y.data());
+    // FIX :618-643
+    for (size_t i = 0; i < s.ifixrho_node.size(); ++i) s.RHO[s.ifixrho_node[i] - 1] = s.rfixrho_value[i];
+    for (size_t i = 0; i < s.ifixt_node.size(); ++i) {
+        int j = s.ifixt_node[i] - 1;
+        double GM = s.GAMM[j] - 1.0;
+        s.T[j] = s.rfixt_value[i];
+        s.E[j] = s.T[j] * p.FR / GM + .5 * (s.VEL_X[j] * s.VEL_X[j] + s.VEL_Y[j] * s.VEL_Y[j]);
+    }
+    OMP_FOR
+    for (int ip = 0; ip < npoin; ++ip) {  // :820-825
+        s.U1[4 * ip] = s.RHO[ip];
+        s.U1[4 * ip + 1] = s.VEL_X[ip] * s.RHO[ip];
+        s.U1[4 * ip + 2] = s.VEL_Y[ip] * s.RHO[ip];
+        s.U1[4 * ip + 3] = s.E[ip] * s.RHO[ip];
+    }
+}
+
+static void rk(Solver& s, int NRK) {
+    for (int IRK = 1; IRK <= NRK; ++IRK) rk_stage(s, IRK, NRK);
+    if (s.BANDERA == 2) s.RHS3 = s.RHS;       // :830-848
+    else if (s.BANDERA == 3) s.RHS2 = s.RHS;
+    else if (s.BANDERA == 4) s.RHS1 = s.RHS;
+}
+
+// meshMove.f90:153-194  FORCES
+static void forces(Solver& s) {
+    for (int is = 0; is < s.nset_numb; ++is) {
+        s.FX[is] = s.FY[is] = s.RM[is] = 0.0;
+        for (size_t ii = 0; ii < s.set_n1[is].size(); ++ii) {
+            int N1 = s.set_n1[is][ii] - 1, N2 = s.set_n2[is][ii] - 1;
+            double D_PRESS = (s.P[N1] + s.P[N2]) / 2.0;
+            double RLX = s.X[N1] - s.X[N2];
+            double RLY = s.Y[N2] - s.Y[N1];
+            double DFX = D_PRESS * RLY, DFY = D_PRESS * RLX;
+            s.FX[is] = s.FX[is] + DFX;
+            s.FY[is] = s.FY[is] + DFY;
+            double XC = (s.X[N1] + s.X[N2]) / 2.0, YC = (s.Y[N2] + s.Y[N1]) / 2.0;
+            s.RM[is] = s.RM[is] + DFY * (XC - s.par.XREF[is]) - DFX * (YC - s.par.YREF[is]);
+        }
+    }
+}
+
+// meshMove.f90:369-392  TRANSF
+static void transf(Solver& s, double ALPHA, double YPOSR) {
+    for (int is = 0; is < s.nset_numb; ++is)
+        for (size_t ii = 0; ii < s.set_n1[is].size(); ++ii)
+            for (int jj = 0; jj < 2; ++jj) {
+                int n = (jj == 0 ? s.set_n1[is][ii] : s.set_n2[is][ii]) - 1;
+                double DISTX = s.X[n] - s.par.XREF[is];
+                double DISTY = s.Y[n] - s.par.YREF[is] + YPOSR;
+                s.dxpos[n] = std::cos(ALPHA) * DISTX + std::sin(ALPHA) * DISTY - DISTX;
+                s.dypos[n] = -std::sin(ALPHA) * DISTX + std::cos(ALPHA) * DISTY - DISTY + YPOSR;
+            }
+}
+
+// meshMove.f90:28-142  fluidStructure
+static void fluid_structure(Solver& s, double dtmin, double time) {
+    const int npoin = s.npoin;
+    const int nmove = (int)s.i_m.size(), nfix_move = (int)s.ifm.size(), nnmove = nmove + nfix_move;
+    std::fill(s.dxpos.begin(), s.dxpos.end(), 0.0);
+    std::fill(s.dypos.begin(), s.dypos.end(), 0.0);
+    double PI = std::acos(-1.0);
+    double AMPLI = PI / 8.0;
+    s.par.XREF[1] = 1.4; s.par.YREF[1] = 0.0;  // :58
+    forces(s);
+    double ALPHAV = s.DISN[1], YPOSRV = s.DISN[0];
+    s.DISN[1] = AMPLI * std::sin(10.0 * time);  // :70
+    double ALPHA = s.DISN[1] - ALPHAV, YPOSR = s.DISN[0] - YPOSRV;
+    transf(s, ALPHA, YPOSR);
+    for (int i = nmove; i < nnmove; ++i) s.pos_aux[i] = 0.0;
+    for (int i = 0; i < nmove; ++i) s.pos_aux[i] = s.dxpos[s.ilaux[i] - 1];
+    std::fill(s.b.begin(), s.b.end(), 0.0);
+    s.last_bicg_iters[0] = bicg(s.lap_sparse.data(), s.lap_idx.data(), s.lap_rowptr.data(), s.lap_diag.data(),
+                                s.xpos.data(), s.b.data(), s.pos_aux.data(), s.ilaux.data(), npoin, nnmove, s.by, s.bp, s.br, s.bz);
+    for (int i = 0; i < npoin; ++i) {
+        s.X[i] = s.X[i] + s.xpos[i];
+        s.X1[i] = s.X1[i] + s.xpos[i];
+        s.W_X[i] = s.xpos[i] / dtmin;
+    }
+    for (int i = 0; i < nmove; ++i) s.pos_aux[i] = s.dypos[s.ilaux[i] - 1];
+    std::fill(s.b.begin(), s.b.end(), 0.0);
+    s.last_bicg_iters[1] = bicg(s.lap_sparse.data(), s.lap_idx.data(), s.lap_rowptr.data(), s.lap_diag.data(),
+                                s.ypos.data(), s.b.data(), s.pos_aux.data(), s.ilaux.data(), npoin, nnmove, s.by, s.bp, s.br, s.bz);
+    for (int i = 0; i < npoin; ++i) {
+        s.Y[i] = s.Y[i] + s.ypos[i];
+        s.Y1[i] = s.Y1[i] + s.ypos[i];
+        s.W_Y[i] = s.ypos[i] / dtmin;
+    }
+}
+
+// ns2DComp.ALE.f90:191-197  residual norms (canonical reduction order)
+static void residual_norms(Solver& s) {
+    for (int c = 0; c < 4; ++c) {
+        s.ER[c] = canon_sum(s.npoin, [&](long i) { double d = s.U[4 * i + c] - s.U1[4 * i + c]; return d * d; });
+        s.ERR[c] = canon_sum(s.npoin, [&](long i) { return s.U1[4 * i + c] * s.U1[4 * i + c]; });
+    }
+}
+
+// ns2DComp.ALE.f90:138-282  one pass of the time loop
+static void step(Solver& s) {
+    const Params& p = s.par;
+    s.ITER += 1;
+    deltat(s.nelem, s.inpoel.data(), s.area.data(), s.T.data(), s.VEL_X.data(), s.VEL_Y.data(), s.W_X.data(),
+           s.W_Y.data(), p.FSAFE, p.FR, p.GAMA, p.T_inf, s.DT.data(), &s.DTMIN);
+    if (s.BANDERA == 1) { s.DTMIN1 = s.DTMIN; s.BANDERA = 2; }
+    double PORC = std::fabs((s.DTMIN - s.DTMIN1) / s.DTMIN);
+    if (100.0 * PORC <= 1.0) s.DTMIN = s.DTMIN1;
+    else { s.DTMIN1 = s.DTMIN; s.BANDERA = 2; }
+    if (p.ITLOCAL != 0) {
+        double DTFACT = 1.0 - std::exp(-s.ITER * 4.6 / p.ITLOCAL);
+        for (int ie = 0; ie < s.nelem; ++ie) s.DTL[ie] = s.DTMIN * DTFACT + s.DT[ie] * (1.0 - DTFACT);
+    } else {
+        std::fill(s.DTL.begin(), s.DTL.end(), s.DTMIN);
+    }
+    s.TIME = s.TIME + s.DTMIN;
+    s.U1 = s.U;
+    rk(s, 4);
+    fluid_structure(s, s.DTMIN, s.TIME);
+    s.ITERPRINT += 1;
+    if (s.ITERPRINT == p.IPRINT || s.ITER == p.MAXITER || s.norms_every_step) {  // :186-197
+        residual_norms(s);
+        if (s.ITERPRINT == p.IPRINT || s.ITER == p.MAXITER) s.ITERPRINT = 0;
+    }
+    s.BANDERA += 1;
+    if (p.MOVING == 1) geometry(s, true);
+    s.U = s.U1;
+}
+
+}  // namespace orc
+
+// ------------------------------------------------------------------------------------------
+// C API for ctypes (tests) and for bench.py's cpu_baseline leg.
+using namespace orc;
+
+extern "C" {
+
+struct orc_bc {
+    int nfixrho; const int* ifixrho_node; const double* rfixrho_value;
+    int nfixv; const int* ifixv_node; const double* rfixv_valuex; const double* rfixv_valuey;
+    int nwall; const int* wall;
+    int nfixt; const int* ifixt_node; const double* rfixt_value;
+    int nsets; const int* iset_n1; const int* iset_n2; const int* iset_elem; const int* iset_id;
+    int nmove; const int* i_m;
+    int nfix_move; const int* ifm;
+};
+
+void orc_get_esup(const int* inpoel, int nelem, int npoin, int* esup1, int* esup2) {
+    vector<int> e1, e2;
+    get_esup(inpoel, nelem, npoin, e1, e2);
+    std::copy(e1.begin(), e1.end(), esup1);
+    std::copy(e2.begin(), e2.end(), esup2);
+}
+int orc_get_psup(const int* inpoel, int nelem, int npoin, int* psup1, int cap, int* psup2) {
+    vector<int> e1, e2, p1, p2;
+    get_esup(inpoel, nelem, npoin, e1, e2);
+    get_psup(inpoel, nelem, npoin, e1, e2, p1, p2);
+    if ((int)p1.size() <= cap) std::copy(p1.begin(), p1.end(), psup1);
+    std::copy(p2.begin(), p2.end(), psup2);
+    return (int)p1.size();
+}
+void orc_deriv(const double* X, const double* Y, const int* inpoel, int nelem, double* area, double* HH,
+               double* HHX, double* HHY, double* dNx, double* dNy, double* hmin) {
+    deriv(X, Y, inpoel, nelem, area, HH, HHX, HHY, dNx, dNy, hmin);
+}
+void orc_masas(const double* area, const int* inpoel, int nelem, int npoin, double* M) {
+    masas(area, inpoel, nelem, npoin, M);
+}
+int orc_normales(const int* wall, int nwall, const double* X, const double* Y, int npoin, int* n_ipoin,
+                 double* n_x, double* n_y) {
+    return normales(wall, nwall, X, Y, npoin, n_ipoin, n_x, n_y);
+}
+void orc_deltat(int nelem, const int* inpoel, const double* area, const double* T, const double* VEL_X,
+                const double* VEL_Y, const double* W_X, const double* W_Y, double FSAFE, double FR, double GAMA,
+                double T_inf, double* DT, double* dtmin) {
+    deltat(nelem, inpoel, area, T, VEL_X, VEL_Y, W_X, W_Y, FSAFE, FR, GAMA, T_inf, DT, dtmin);
+}
+void orc_estab(int nelem, const int* inpoel, const double* U, const double* T, const double* VEL_X,
+               const double* VEL_Y, const double* W_X, const double* W_Y, const double* GAMM, const double* dNx,
+               const double* dNy, double FR, double DTMIN, double RHOINF, double TINF, double* SHOC, double* T1,
+               double* T2, double* T3) {
+    estab(nelem, inpoel, U, T, VEL_X, VEL_Y, W_X, W_Y, GAMM, dNx, dNy, FR, DTMIN, RHOINF, TINF, SHOC, T1, T2, T3);
+}
+void orc_calcrhs(double* rhs, const double* U, const double* theta, const double* T, const double* dNx,
+                 const double* dNy, const double* area, const double* shoc, const double* dtl, const double* ts1,
+                 const double* ts2, const double* ts3, const int* inpoel, int nelem, int npoin, double Cv,
+                 double lambda_ref, double mu_ref, double gamma0, double T_inf, double cte) {
+    (void)npoin;
+    GasK g{Cv, lambda_ref, mu_ref, gamma0, T_inf, cte};
+    calcrhs(g, rhs, U, theta, T, dNx, dNy, area, shoc, dtl, ts1, ts2, ts3, inpoel, nelem);
+}
+void orc_fuente(double* rhs, const double* U, const double* w_x, const double* w_y, const double* dNx,
+                const double* dNy, const double* area, const double* dtl, const int* inpoel, int nelem) {
+    fuente(rhs, U, w_x, w_y, dNx, dNy, area, dtl, inpoel, nelem);
+}
+void orc_spmv(const double* A, const int* idx, const int* rowptr, const double* v, double* y, int npoin) {
+    spmv(A, idx, rowptr, v, y, npoin);
+}
+double orc_vecdot(int n, const double* x, const double* y) { return vecdot(n, x, y); }
+int orc_bicg(const double* A, const int* idx, const int* rowptr, const double* diag, double* x, const double* b,
+             const double* x_fix, const int* fixIdx, int npoin, int nfix) {
+    vector<double> y, p, r, z;
+    return bicg(A, idx, rowptr, diag, x, b, x_fix, fixIdx, npoin, nfix, y, p, r, z);
+}
+// returns nnz; lap_idx/lap_sparse sized psup+npoin by the caller (pass cap)
+int orc_laplace(const int* inpoel, const double* dNx, const double* dNy, const double* X, const double* Y,
+                int nelem, int npoin, int* lap_idx, int* lap_rowptr, double* lap_sparse, double* lap_diag, int cap) {
+    vector<int> e1, e2, p1, p2, li, lr;
+    get_esup(inpoel, nelem, npoin, e1, e2);
+    get_psup(inpoel, nelem, npoin, e1, e2, p1, p2);
+    laplace_init(npoin, p1, p2, li, lr);
+    int nnz = lr[npoin];
+    std::copy(lr.begin(), lr.end(), lap_rowptr);
+    if (nnz > cap) return nnz;
+    std::copy(li.begin(), li.end(), lap_idx);
+    laplace(inpoel, dNx, dNy, X, Y, npoin, e1, e2, li, lr, lap_sparse, lap_diag);
+    return nnz;
+}
+void orc_gcl_main(double* M, const double* W_x, const double* W_y, const double* W_x_old, const double* W_y_old,
+                  const double* area_old, const double* dNx, const double* dNy, const double* area,
+                  const int* inpoel, int nelem, int npoin, double dt) {
+    gcl_main(M, W_x, W_y, W_x_old, W_y_old, area_old, dNx, dNy, area, inpoel, nelem, npoin, dt);
+}
+int orc_smoothing(double* X, double* Y, const int* inpoel, const unsigned char* fixed, int npoin, int nelem) {
+    return smoothing(X, Y, inpoel, fixed, npoin, nelem);
+}
+double orc_pow15(double x) { return pow15(x); }
+double orc_pow05(double x) { return pow05(x); }
+double orc_powm05(double x) { return powm05(x); }
+double orc_canon_sum(long n, const double* v) { return canon_sum(n, [&](long i) { return v[i]; }); }
+
+// ---- full solver -------------------------------------------------------------------------
+void* orc_create(const Params* par, int npoin, int nelem, const double* X, const double* Y, const int* inpoel,
+                 const orc_bc* bc) {
+    Solver* s = new Solver();
+    s->par = *par;
+    s->npoin = npoin; s->nelem = nelem;
+    s->X.assign(X, X + npoin); s->Y.assign(Y, Y + npoin);
+    s->inpoel.assign(inpoel, inpoel + 3 * (size_t)nelem);
+    s->ifixrho_node.assign(bc->ifixrho_node, bc->ifixrho_node + bc->nfixrho);
+    s->rfixrho_value.assign(bc->rfixrho_value, bc->rfixrho_value + bc->nfixrho);
+    s->ifixv_node.assign(bc->ifixv_node, bc->ifixv_node + bc->nfixv);
+    s->rfixv_valuex.assign(bc->rfixv_valuex, bc->rfixv_valuex + bc->nfixv);
+    s->rfixv_valuey.assign(bc->rfixv_valuey, bc->rfixv_valuey + bc->nfixv);
+    s->wall.assign(bc->wall, bc->wall + 2 * (size_t)bc->nwall);
+    s->ifixt_node.assign(bc->ifixt_node, bc->ifixt_node + bc->nfixt);
+    s->rfixt_value.assign(bc->rfixt_value, bc->rfixt_value + bc->nfixt);
+    for (int i = 0; i < bc->nsets; ++i) {  // dataLoader.f90:208-215
+        int id = bc->iset_id[i];
+        if (id > s->nset_numb) s->nset_numb = id;
+        s->set_n1[id - 1].push_back(bc->iset_n1[i]);
+        s->set_n2[id - 1].push_back(bc->iset_n2[i]);
+        s->set_el[id - 1].push_back(bc->iset_elem[i]);
+    }
+    s->i_m.assign(bc->i_m, bc->i_m + bc->nmove);
+    s->ifm.assign(bc->ifm, bc->ifm + bc->nfix_move);
+    s->ilaux = s->i_m;  // dataLoader.f90:258-268
+    s->ilaux.insert(s->ilaux.end(), s->ifm.begin(), s->ifm.end());
+    size_t P = npoin, E = nelem;
+    for (auto* v : {&s->HHX, &s->HHY, &s->HH, &s->area, &s->SHOC, &s->T_SUGN1, &s->T_SUGN2, &s->T_SUGN3, &s->DTL, &s->DT})
+        v->assign(E, 0.0);
+    s->dNx.assign(3 * E, 0.0); s->dNy.assign(3 * E, 0.0);
+    for (auto* v : {&s->M, &s->VEL_X, &s->VEL_Y, &s->W_X, &s->W_Y, &s->P, &s->T, &s->RHO, &s->E, &s->RMACH, &s->GAMM,
+                    &s->X1, &s->Y1, &s->b, &s->pos_aux, &s->dxpos, &s->dypos, &s->xpos, &s->ypos, &s->n_x, &s->n_y})
+        v->assign(P, 0.0);
+    for (auto* v : {&s->U, &s->U1, &s->RHS, &s->RHS1, &s->RHS2, &s->RHS3, &s->UN}) v->assign(4 * P, 0.0);
+    s->n_ipoin.assign(P, 0);
+    return s;
+}
+void orc_destroy(void* h) { delete (Solver*)h; }
+
+// ns2DComp.ALE.f90:59-134 (without smoothing — orc_smoothing is applied to X,Y by the caller beforehand)
+void orc_init(void* h) {
+    Solver& s = *(Solver*)h;
+    std::fill(s.GAMM.begin(), s.GAMM.end(), s.par.GAMA);
+    restart_freestream(s);
+    get_esup(s.inpoel.data(), s.nelem, s.npoin, s.esup1, s.esup2);
+    get_psup(s.inpoel.data(), s.nelem, s.npoin, s.esup1, s.esup2, s.psup1, s.psup2);
+    laplace_init(s.npoin, s.psup1, s.psup2, s.lap_idx, s.lap_rowptr);
+    s.lap_sparse.assign(s.lap_idx.size(), 0.0);
+    s.lap_diag.assign(s.npoin, 0.0);
+    geometry(s, false);
+    s.TIME = 0; s.ITER = 0; s.DTMIN = 0; s.BANDERA = 1; s.ITERPRINT = 0;
+    std::fill(s.W_X.begin(), s.W_X.end(), -0.0);  // :121
+    std::fill(s.W_Y.begin(), s.W_Y.end(), 0.0);
+    s.W_x_old = s.W_X; s.W_y_old = s.W_Y; s.area_old = s.area;
+    s.DISN[0] = s.DISN[1] = 0.0;                  // setNewmarkCondition meshMove.f90:15-26
+}
+void orc_step(void* h, int n) { for (int i = 0; i < n; ++i) step(*(Solver*)h); }
+void orc_rk_stage(void* h, int irk) { rk_stage(*(Solver*)h, irk, 4); }
+void orc_geometry(void* h, int moving_step) { geometry(*(Solver*)h, moving_step != 0); }
+void orc_fluid_structure(void* h, double dtmin, double time) { fluid_structure(*(Solver*)h, dtmin, time); }
+void orc_residual_norms(void* h, double* er, double* err) {
+    Solver& s = *(Solver*)h;
+    residual_norms(s);
+    for (int i = 0; i < 4; ++i) { er[i] = s.ER[i]; err[i] = s.ERR[i]; }
+}
+
+// field access by name: returns pointer + length (elements); type 0=double 1=int
+int orc_field(void* h, const char* name, void** ptr, long* len) {
+    Solver& s = *(Solver*)h;
+    std::string n(name);
+#define DF(nm) if (n == #nm) { *ptr = s.nm.data(); *len = (long)s.nm.size(); return 0; }
+#define IF(nm) if (n == #nm) { *ptr = s.nm.data(); *len = (long)s.nm.size(); return 1; }
+    DF(X) DF(Y) DF(HHX) DF(HHY) DF(HH) DF(M) DF(area) DF(dNx) DF(dNy)
+    DF(VEL_X) DF(VEL_Y) DF(W_X) DF(W_Y) DF(U) DF(U1) DF(RHS) DF(RHS1) DF(RHS2) DF(RHS3) DF(UN)
+    DF(P) DF(T) DF(RHO) DF(E) DF(RMACH) DF(SHOC) DF(T_SUGN1) DF(T_SUGN2) DF(T_SUGN3) DF(GAMM) DF(DTL) DF(DT)
+    DF(X1) DF(Y1) DF(lap_sparse) DF(lap_diag) DF(n_x) DF(n_y) DF(xpos) DF(ypos) DF(dxpos) DF(dypos)
+    DF(W_x_old) DF(W_y_old) DF(area_old)
+    IF(inpoel) IF(esup1) IF(esup2) IF(psup1) IF(psup2) IF(lap_idx) IF(lap_rowptr) IF(n_ipoin) IF(ilaux)
+#undef DF
+#undef IF
+    return -1;
+}
+// scalars: TIME DTMIN DTMIN1 HMIN ITER BANDERA n_m bicg_x bicg_y FX1 FY1 RM1
+double orc_scalar(void* h, const char* name) {
+    Solver& s = *(Solver*)h;
+    std::string n(name);
+    if (n == "TIME") return s.TIME;
+    if (n == "DTMIN") return s.DTMIN;
+    if (n == "DTMIN1") return s.DTMIN1;
+    if (n == "HMIN") return s.HMIN;
+    if (n == "ITER") return s.ITER;
+    if (n == "BANDERA") return s.BANDERA;
+    if (n == "n_m") return s.n_m;
+    if (n == "bicg_x") return s.last_bicg_iters[0];
+    if (n == "bicg_y") return s.last_bicg_iters[1];
+    if (n == "FX1") return s.FX[0];
+    if (n == "FY1") return s.FY[0];
+    if (n == "RM1") return s.RM[0];
+    return std::nan("");
+}
+void orc_set_scalar(void* h, const char* name, double v) {
+    Solver& s = *(Solver*)h;
+    std::string n(name);
+    if (n == "TIME") s.TIME = v;
+    else if (n == "DTMIN") s.DTMIN = v;
+    else if (n == "DTMIN1") s.DTMIN1 = v;
+    else if (n == "ITER") s.ITER = (int)v;
+    else if (n == "BANDERA") s.BANDERA = (int)v;
+    else if (n == "norms_every_step") s.norms_every_step = (int)v;
+}
+int orc_omp_threads() {
+#ifdef ORC_OMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+}  // extern "C"
