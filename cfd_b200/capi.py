@@ -82,7 +82,7 @@ def lib():
     L.cfdb_launch_count.restype = i64
     L.cfdb_calcrhs.argtypes = [vp] + [_dp] * 12 + [_ip, i32, i32] + [d] * 6
     L.cfdb_fuente.argtypes = [vp] + [_dp] * 8 + [_ip, i32, i32]
-    L.cfdb_deltat.argtypes = [vp, _dp, _dp, _ip] + [_dp] * 7 + [i32, i32] + [d] * 4
+    L.cfdb_deltat.argtypes = [vp, _dp, _dp, _ip] + [_dp] * 6 + [i32, i32] + [d] * 4
     L.cfdb_estab.argtypes = [vp] + [_dp] * 9 + [_ip, i32, i32] + [d] * 4 + [_dp] * 4
     L.cfdb_deriv.argtypes = [vp, _dp, _dp, _ip, i32, i32] + [_dp] * 7
     L.cfdb_masas.argtypes = [vp, _dp, _ip, i32, i32, _dp]

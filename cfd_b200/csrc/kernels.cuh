@@ -286,23 +286,30 @@ __global__ void __launch_bounds__(256) estab(int nelem, const int* __restrict__ 
         H_RGN = H_RGN + H_RGN2;
         H_JGN = H_JGN + TERM_2;
     }
-    TAU = 1.0 / TAU;
-    H_RGNE = 2.0 / H_RGNE;
-    H_RGN = 2.0 / H_RGN;
+    // the sums are >= +0; x/(+0) = +Inf is taken directly instead of through the division's slow path
+    TAU = TAU == 0.0 ? CUDART_INF : 1.0 / TAU;
+    H_RGNE = H_RGNE == 0.0 ? CUDART_INF : 2.0 / H_RGNE;
+    H_RGN = H_RGN == 0.0 ? CUDART_INF : 2.0 / H_RGN;
     if (H_RGN > 1.e1) H_RGN = 0.0;
-    H_JGN = 2.0 / H_JGN;
+    H_JGN = H_JGN == 0.0 ? CUDART_INF : 2.0 / H_JGN;
     if (H_JGN > 1.e1) H_JGN = 0.0;
     double TR1 = DR2 * H_JGN / RHO_ELEM;
     double ZZZ = H_JGN / (2.0 * C);
     SHOC[e] = (TR1 + TR1 * TR1) * .5 * (C * C) * ZZZ;
-    double RESUMEN = 1.0 / (TAU * TAU) + (2.0 / DTMIN) * (2.0 / DTMIN);
+    double tt = TAU * TAU;
+    double RESUMEN = (tt == CUDART_INF ? 0.0 : 1.0 / tt) + (2.0 / DTMIN) * (2.0 / DTMIN);
     double RRR = ex::powm05(RESUMEN);
     double s2 = RRR, s3 = RRR;
     if (fmu != 0.0) {
-        double TAU_SUNG3 = (H_RGN * H_RGN) / (4.0 * fmu / RHOINF);
-        double TAU_SUNG3_E = (H_RGNE * H_RGNE) / (4.0 * fmu / RHOINF);
-        s2 = ex::powm05(RESUMEN + 1.0 / (TAU_SUNG3 * TAU_SUNG3));
-        s3 = ex::powm05(RESUMEN + 1.0 / (TAU_SUNG3_E * TAU_SUNG3_E));
+        double den = 4.0 * fmu / RHOINF;
+        double TAU_SUNG3 = (H_RGN * H_RGN) / den;
+        double TAU_SUNG3_E = (H_RGNE * H_RGNE) / den;
+        double q2 = TAU_SUNG3 * TAU_SUNG3, q3 = TAU_SUNG3_E * TAU_SUNG3_E;
+        // 1/(+0) = +Inf and 1/(+Inf) = +0 taken directly (q2,q3 are squares: never negative)
+        double i2 = q2 == 0.0 ? CUDART_INF : (q2 == CUDART_INF ? 0.0 : 1.0 / q2);
+        double i3 = q3 == 0.0 ? CUDART_INF : (q3 == CUDART_INF ? 0.0 : 1.0 / q3);
+        s2 = ex::powm05(RESUMEN + i2);
+        s3 = ex::powm05(RESUMEN + i3);
     }
     TS1[e] = RRR; TS2[e] = s2; TS3[e] = s3;
 }
@@ -311,8 +318,8 @@ __global__ void __launch_bounds__(256) estab(int nelem, const int* __restrict__ 
 // calcRHS (calcRHS.f90:36-141) [+ FUENTE, subrutinas.f90:1060-1078] : one thread per element.
 // Shape-function gradients and the 12+12 contributions stay in registers; the results go to the
 // staging buffers EC/FC, not to RHS: the node kernel sums them in the reference's order.
-template <bool VISC, bool THETA, bool ALE>
-__global__ void __launch_bounds__(128) calcrhs_elem(int nelem, const int* __restrict__ inp, const double* __restrict__ U,
+template <bool VISC, bool THETA, bool ALE, int MINB>
+__global__ void __launch_bounds__(128, MINB) calcrhs_elem(int e0, int e1, int nelem, const int* __restrict__ inp, const double* __restrict__ U,
                                                      const double* __restrict__ TH, const double* __restrict__ T,
                                                      const double* __restrict__ WXa, const double* __restrict__ WYa,
                                                      const double* __restrict__ dNx, const double* __restrict__ dNy,
@@ -321,8 +328,8 @@ __global__ void __launch_bounds__(128) calcrhs_elem(int nelem, const int* __rest
                                                      const double* __restrict__ ts1, const double* __restrict__ ts2,
                                                      const double* __restrict__ ts3, Gas g, double* __restrict__ EC,
                                                      double* __restrict__ FC) {
-    int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= nelem) return;
+    int e = e0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= e1) return;
     const double gamma0 = g.gamma0;
     int ip[3] = {inp[e], inp[nelem + e], inp[2 * (size_t)nelem + e]};
     double Nx[3] = {dNx[e], dNx[nelem + e], dNx[2 * (size_t)nelem + e]};
@@ -343,7 +350,7 @@ __global__ void __launch_bounds__(128) calcrhs_elem(int nelem, const int* __rest
     const double ar = area[e];
     double mu = 0.0, lambda = 0.0;
     if (VISC) {
-        double T_avg = (T[ip[0]] + T[ip[1]] + T[ip[2]]) / 3.0;
+        double T_avg = ex::div3(T[ip[0]] + T[ip[1]] + T[ip[2]]);
         double p15 = ex::pow15(T_avg / g.T_inf);
         mu = g.mu_ref * p15 * (g.T_inf + 110) / (T_avg + 110);
         lambda = g.lambda_ref * p15 * (g.T_inf + 194) / (T_avg + 194);
@@ -445,13 +452,13 @@ __global__ void __launch_bounds__(128) calcrhs_elem(int nelem, const int* __rest
     for (int n = 0; n < 3; ++n) {
         double v[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = rt[n][i] * ar * dtl / 3.0;
+        for (int i = 0; i < 4; ++i) v[i] = ex::div3(rt[n][i] * ar * dtl);
         st4(out + 4 * n, v);
     }
     if (ALE) {
         // FUENTE: sp(:,1)=(.5,.5,0) sp(:,2)=(0,.5,.5) sp(:,3)=(.5,0,.5); sp[c][r] = sp(r+1,c+1)
         const double sp[3][3] = {{.5, .5, 0.0}, {0.0, .5, .5}, {.5, 0.0, .5}};
-        double AR = ar * dtl / 3.0;
+        double AR = ex::div3(ar * dtl);
         double wx[3], wy[3];
         double wxn[3] = {WXa[ip[0]], WXa[ip[1]], WXa[ip[2]]};
         double wyn[3] = {WYa[ip[0]], WYa[ip[1]], WYa[ip[2]]};
@@ -496,7 +503,7 @@ struct BcTab {
 };
 
 template <bool ALE, bool UPDATE>
-__global__ void __launch_bounds__(256) node_update(int npoin, const int* __restrict__ esup2, const int* __restrict__ eslot,
+__global__ void __launch_bounds__(256) node_update(int n0, int n1, const int* __restrict__ esup2, const int* __restrict__ eslot,
                                                     const double* __restrict__ EC, const double* __restrict__ FC,
                                                     const double* __restrict__ U, const double* __restrict__ M,
                                                     const double* __restrict__ GAMM, const double* __restrict__ WXa,
@@ -506,8 +513,8 @@ __global__ void __launch_bounds__(256) node_update(int npoin, const int* __restr
                                                     double* __restrict__ VELX, double* __restrict__ VELY,
                                                     double* __restrict__ Ea, double* __restrict__ Pa,
                                                     double* __restrict__ Ta, double* __restrict__ RMACH) {
-    int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= npoin) return;
+    int n = n0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n1) return;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     const int k0 = esup2[n], k1 = esup2[n + 1];
     for (int k = k0; k < k1; ++k) {

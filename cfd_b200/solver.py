@@ -89,6 +89,15 @@ class NSComp2D:
         capi.check(self.L.cfdb_get(self.h, name.encode(), _vp(a), n))
         return a
 
+    def get_into(self, name, out):
+        """Download straight into a caller-owned (e.g. pinned) contiguous numpy buffer."""
+        capi.check(self.L.cfdb_get(self.h, name.encode(), _vp(out), out.size))
+        return out
+
+    def set_from(self, name, a):
+        """Upload straight from a caller-owned (e.g. pinned) contiguous float64 numpy buffer."""
+        capi.check(self.L.cfdb_set(self.h, name.encode(), _vp(a), a.size))
+
     def set(self, name, value):
         a = np.ascontiguousarray(np.asarray(value, np.float64).ravel())
         capi.check(self.L.cfdb_set(self.h, name.encode(), _vp(a), a.size))
