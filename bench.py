@@ -178,12 +178,20 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     # ---- workload: this rank's sub-domain (weak scaling: fixed work per GPU) --------------------
+    # The global mesh is `world` 16 M-triangle strips stacked in y; each rank builds only its window of it
+    # (cfd_b200/partition.py), computes its own range plus a one-element ghost layer, and refreshes ghost nodes
+    # over NCCL after every RK stage.
     t_gen = time.perf_counter()
-    raw = meshgen.square(n=args.n, seed=12345 + rank, IPRINT=10**9, MAXITER=10**9)
-    lc = deck.load(raw)
-    E, P = lc.nelem, lc.npoin
-    g = NSComp2D(lc, device=local)
-    for k, v in meshgen.density_bump(lc).items():
+    from cfd_b200 import partition
+    from cfd_b200.dist import make_rank_solver
+
+    win = partition.square_window(args.n, world, rank, IPRINT=10**9, MAXITER=10**9)
+    g, part = make_rank_solver(win, rank, world, local, dist if world > 1 else None)
+    lc = part.lc
+    E = 2 * (args.n - 1) ** 2          # elements of this rank's own range (global elements / world)
+    P = part.n_owned
+    bump = meshgen.density_bump(lc, x0=0.5, y0=0.5 * world, sigma=0.15)
+    for k, v in bump.items():
         g.set(k, v)
     t_gen = time.perf_counter() - t_gen
     stream = torch.cuda.ExternalStream(g.stream, device=torch.device("cuda", local))
@@ -247,7 +255,7 @@ def main():
     if not args.no_e2e:
         names = ["U", "T", "VEL_X", "VEL_Y"]
         host = {nme: torch.empty(g.L.cfdb_field_size(g.h, nme.encode()), dtype=torch.float64, pin_memory=True) for nme in names}
-        out = torch.empty(4 * P, dtype=torch.float64, pin_memory=True)
+        out = torch.empty(host["U"].numel(), dtype=torch.float64, pin_memory=True)
         for nme in names:
             host[nme].numpy()[:] = g.get(nme)
         h2d = sum(8 * h.numel() for h in host.values())
@@ -292,10 +300,12 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"square16M: {E}-triangle / {P}-node jittered-lattice Delaunay-diagonal mesh per GPU "
+            "config": {"workload": f"square16M: {E}-triangle / {P}-node jittered-lattice Delaunay-diagonal strip per GPU "
                                    "(BASELINE configs[4]; the mesh north_star's target is stated on), Euler, fixed mesh, "
                                    "density-bump initial state", "l2": "inputs larger than L2 (no flush needed)",
-                       "elements_per_gpu": E, "element_stage_updates_per_s": 4 * value, "setup_s": t_gen},
+                       "elements_per_gpu": E, "local_elements_incl_ghost_layer": lc.nelem,
+                       "parallelism": f"{world} contiguous strips, owner-computes + NCCL ghost refresh per RK stage",
+                       "element_stage_updates_per_s": 4 * value, "setup_s": t_gen},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": launches,
         }))
     if world > 1:

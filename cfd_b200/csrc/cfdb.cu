@@ -4,6 +4,8 @@
 #include "host_topology.h"
 #include "kernels.cuh"
 
+#include <nccl.h>
+
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -24,6 +26,12 @@ static int fail(const std::string& m) {
         cudaError_t _e = (call);                                                                        \
         if (_e != cudaSuccess)                                                                          \
             return fail(std::string(#call) + ": " + cudaGetErrorString(_e) + " @" + std::to_string(__LINE__)); \
+    } while (0)
+#define NK(call)                                                                                        \
+    do {                                                                                                \
+        ncclResult_t _e = (call);                                                                       \
+        if (_e != ncclSuccess)                                                                          \
+            return fail(std::string(#call) + ": " + ncclGetErrorString(_e) + " @" + std::to_string(__LINE__)); \
     } while (0)
 #define TRY(call)                \
     do {                         \
@@ -54,11 +62,11 @@ struct DBuf {
 
 enum KernelId {
     K_DERIV, K_MASAS, K_NORMALES, K_DELTAT, K_DTLOGIC, K_DTL, K_ESTAB, K_CALCRHS, K_NODE, K_DOT, K_NORMS, K_SPMV,
-    K_VEC, K_FIXROWS, K_SCALAR, K_LAPLACE, K_TRANSF, K_MOVE, K_FORCES, K_GCL, K_LAYOUT, K_FILL, K_COUNT
+    K_VEC, K_FIXROWS, K_SCALAR, K_LAPLACE, K_TRANSF, K_MOVE, K_FORCES, K_GCL, K_LAYOUT, K_FILL, K_HALO, K_COUNT
 };
 static const char* kKernelNames[K_COUNT] = {"deriv", "masas", "normales", "deltat", "dt_logic", "dtl", "estab",
                                             "calcrhs_elem", "node_update", "dot", "norms", "spmv", "vec", "fixrows",
-                                            "scalar", "laplace", "transf", "move_apply", "forces", "gcl", "layout", "fill"};
+                                            "scalar", "laplace", "transf", "move_apply", "forces", "gcl", "layout", "fill", "halo"};
 
 struct cfdb_ctx {
     int device = 0;
@@ -101,6 +109,13 @@ struct cfdb_ctx {
     int bicg_iters[2] = {0, 0};
     bool theta_nonzero = false;
     bool u1_is_u = false;  // after U = U1 (ns2DComp.ALE.f90:277-281) the two arrays are one buffer
+    // multi-GPU (one rank per context)
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+    int n_owned = 0;           // reductions run over local nodes [0,n_owned)
+    vector<int> nb_rank, send_ptr, recv_ptr;
+    DBuf<int> send_idx, recv_idx;
+    DBuf<double> sendbuf, recvbuf;
     // profiling
     bool prof = false;
     int64_t launches = 0;
@@ -327,6 +342,7 @@ extern "C" int cfdb_create(cfdb_ctx** out, const cfdb_params* par, int32_t npoin
     c->par = *par;
     c->npoin = npoin;
     c->nelem = nelem;
+    c->n_owned = npoin;
     auto bail = [&](int r) { cfdb_destroy(c); return r; };
     {
         int lo = 0, hi = 0;
@@ -423,6 +439,8 @@ extern "C" void cfdb_destroy(cfdb_ctx* c) {
     cudaSetDevice(c->device);
     if (c->st) cudaStreamSynchronize(c->st);
     if (c->st2) cudaStreamSynchronize(c->st2);
+    if (c->comm) ncclCommDestroy(c->comm);
+    c->send_idx.release(); c->recv_idx.release(); c->sendbuf.release(); c->recvbuf.release();
     for (auto e : c->chunk_ev) cudaEventDestroy(e);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->st2) cudaStreamDestroy(c->st2);
@@ -448,6 +466,86 @@ extern "C" void cfdb_destroy(cfdb_ctx* c) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// multi-GPU plumbing: ghost refresh (packed ncclSend/ncclRecv per neighbour) and tiny all-reduces
+extern "C" int cfdb_nccl_unique_id(void* out128) {
+    ncclUniqueId id;
+    NK(ncclGetUniqueId(&id));
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    memcpy(out128, &id, 128);
+    return 0;
+}
+extern "C" int cfdb_comm_init(cfdb_ctx* c, const void* uid128, int32_t rank, int32_t nranks) {
+    CK(cudaSetDevice(c->device));
+    if (c->comm) return fail("cfdb_comm_init: communicator already initialised");
+    ncclUniqueId id;
+    memcpy(&id, uid128, 128);
+    NK(ncclCommInitRank(&c->comm, nranks, id, rank));
+    c->rank = rank;
+    c->nranks = nranks;
+    return 0;
+}
+extern "C" int cfdb_set_halo(cfdb_ctx* c, int32_t n_owned, int32_t nneigh, const int32_t* neigh_rank,
+                             const int32_t* send_ptr, const int32_t* send_idx, const int32_t* recv_ptr,
+                             const int32_t* recv_idx) {
+    CK(cudaSetDevice(c->device));
+    if (n_owned < 0 || n_owned > c->npoin) return fail("cfdb_set_halo: n_owned out of range");
+    c->n_owned = n_owned;
+    c->nb_rank.assign(neigh_rank, neigh_rank + nneigh);
+    c->send_ptr.assign(send_ptr, send_ptr + nneigh + 1);
+    c->recv_ptr.assign(recv_ptr, recv_ptr + nneigh + 1);
+    for (int i = 0; i < c->send_ptr[nneigh]; ++i)
+        if (send_idx[i] < 0 || send_idx[i] >= n_owned) return fail("cfdb_set_halo: send list must name owned nodes");
+    for (int i = 0; i < c->recv_ptr[nneigh]; ++i)
+        if (recv_idx[i] < n_owned || recv_idx[i] >= c->npoin) return fail("cfdb_set_halo: receive list must name ghost nodes");
+    TRY(upload(c, c->send_idx, send_idx, (size_t)c->send_ptr[nneigh]));
+    TRY(upload(c, c->recv_idx, recv_idx, (size_t)c->recv_ptr[nneigh]));
+    TRY(c->sendbuf.alloc(7 * (size_t)c->send_ptr[nneigh] + 8));
+    TRY(c->recvbuf.alloc(7 * (size_t)c->recv_ptr[nneigh] + 8));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+// exchange `w` doubles per node between sendbuf and recvbuf (already packed / to be unpacked by the caller)
+static int halo_sendrecv(cfdb_ctx* c, int w) {
+    const int nn = (int)c->nb_rank.size();
+    if (!nn) return 0;
+    if (!c->comm) return fail("halo exchange requested but cfdb_comm_init was not called");
+    NK(ncclGroupStart());
+    for (int k = 0; k < nn; ++k) {
+        int ns = c->send_ptr[k + 1] - c->send_ptr[k], nr = c->recv_ptr[k + 1] - c->recv_ptr[k];
+        if (ns) NK(ncclSend(c->sendbuf.p + (size_t)w * c->send_ptr[k], (size_t)w * ns, ncclDouble, c->nb_rank[k], c->comm, c->st));
+        if (nr) NK(ncclRecv(c->recvbuf.p + (size_t)w * c->recv_ptr[k], (size_t)w * nr, ncclDouble, c->nb_rank[k], c->comm, c->st));
+    }
+    NK(ncclGroupEnd());
+    c->launches += 1;
+    return 0;
+}
+static int halo_vec(cfdb_ctx* c, double* v, int w) {
+    const int nn = (int)c->nb_rank.size();
+    if (!nn) return 0;
+    int ms = c->send_ptr[nn], mr = c->recv_ptr[nn];
+    if (ms) LAUNCH(K_HALO, k::halo_pack, grid_for((long)ms * w, 128), 128, ms, w, c->send_idx.p, v, c->sendbuf.p);
+    TRY(halo_sendrecv(c, w));
+    if (mr) LAUNCH(K_HALO, k::halo_unpack, grid_for((long)mr * w, 128), 128, mr, w, c->recv_idx.p, c->recvbuf.p, v);
+    return 0;
+}
+// ghosts of U1, T, VEL_X, VEL_Y in one message per neighbour (after every RK stage)
+static int halo_state(cfdb_ctx* c) {
+    const int nn = (int)c->nb_rank.size();
+    if (!nn) return 0;
+    int ms = c->send_ptr[nn], mr = c->recv_ptr[nn];
+    if (ms) LAUNCH(K_HALO, k::halo_pack_state, grid_for(ms, 128), 128, ms, c->send_idx.p, c->U1.p, c->T.p, c->VEL_X.p, c->VEL_Y.p, c->sendbuf.p);
+    TRY(halo_sendrecv(c, 7));
+    if (mr) LAUNCH(K_HALO, k::halo_unpack_state, grid_for(mr, 128), 128, mr, c->recv_idx.p, c->recvbuf.p, c->U1.p, c->T.p, c->VEL_X.p, c->VEL_Y.p);
+    return 0;
+}
+static int allreduce(cfdb_ctx* c, double* dev, int count, ncclRedOp_t op) {
+    if (c->nranks <= 1) return 0;
+    NK(ncclAllReduce(dev, dev, count, ncclDouble, op, c->comm, c->st));
+    c->launches += 1;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // canonical reduction of nv vectors whose first-level chunk sums are in redA laid out [v][m]
 static int reduce_levels(cfdb_ctx* c, int nv, long m, int slot) {
     double* in = c->redA.p;
@@ -460,6 +558,7 @@ static int reduce_levels(cfdb_ctx* c, int nv, long m, int slot) {
         m = m2;
     }
     CK(cudaMemcpyAsync(&c->sc->red[slot], in, nv * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+    TRY(allreduce(c, &c->sc->red[slot], nv, ncclSum));  // multi-rank: sum of the per-rank canonical sums
     return 0;
 }
 static int dev_dot(cfdb_ctx* c, long n, const double* x, const double* y, int slot) {
@@ -485,6 +584,7 @@ static int run_deriv(cfdb_ctx* c) {
     LAUNCH(K_SCALAR, k::set_double, 1, 1, &c->sc->HMIN, (double)INFINITY);
     LAUNCH(K_DERIV, k::deriv, grid_for(c->nelem, 256), 256, c->nelem, c->inp.p, c->X.p, c->Y.p, c->area.p, c->HH.p,
            c->HHX.p, c->HHY.p, c->dNx.p, c->dNy.p, c->sc);
+    TRY(allreduce(c, &c->sc->HMIN, 1, ncclMin));
     return 0;
 }
 static int run_masas(cfdb_ctx* c) {
@@ -644,6 +744,7 @@ extern "C" int cfdb_rk_stage(cfdb_ctx* c, int32_t irk) {
     if (nch <= 1) {
         TRY(run_calcrhs_elem(c, g, false, c->ale, dtl_arr, &c->sc->DTMIN));
         TRY(run_node(c, c->st, c->ale, true, RK_FACT));
+        TRY(halo_state(c));
         return 0;
     }
     // software pipeline: the (memory-bound) node kernel of chunk k runs on st2 while the (fp64-bound) element
@@ -658,6 +759,7 @@ extern "C" int cfdb_rk_stage(cfdb_ctx* c, int32_t irk) {
     }
     CK(cudaEventRecord(c->ev_join, c->st2));
     CK(cudaStreamWaitEvent(c->st, c->ev_join, 0));
+    TRY(halo_state(c));
     return 0;
 }
 
@@ -669,21 +771,24 @@ static int bicg_dev(cfdb_ctx* c, const double* A, const int* idx, const int* row
     const int B = 256, G = grid_for(npoin, B), GF = grid_for(std::max(nfix, 1), 128);
     const double tol = 1.e-10;
     double *y = c->by.p, *p = c->bp.p, *r = c->br.p, *z = c->bz.p;
+    const int nred = (c->nranks > 1 && npoin == c->npoin) ? c->n_owned : npoin;  // inner products over owned nodes
     if (nfix) LAUNCH(K_FIXROWS, k::copy1, GF, 128, nfix, fixIdx, fixLast, 1.0, x_fix, x);
+    TRY(halo_vec(c, x, 1));
     LAUNCH(K_SPMV, k::spmv, G, B, npoin, A, idx, rowptr, x, y);
     if (nfix) LAUNCH(K_FIXROWS, k::copy2, GF, 128, nfix, fixIdx, 1.e30, x, y);
     LAUNCH(K_VEC, k::vecsum, G, B, npoin, (int)k::ALFA_CONST, -1.0, c->sc, y, b, r);
     if (nfix) LAUNCH(K_FIXROWS, k::assign2, GF, 128, nfix, fixIdx, 0.0, r);
-    TRY(dev_dot(c, npoin, r, r, 0));
+    TRY(dev_dot(c, nred, r, r, 0));
     LAUNCH(K_SCALAR, k::bicg_scalar, 1, 1, c->sc, (int)k::SC_RR, 0);
     TRY(read_scal(c));
-    if (c->h_sc->rr < tol) { *iters = -1; return 0; }
+    if (c->h_sc->rr < tol) { *iters = -1; return halo_vec(c, x, 1); }
     LAUNCH(K_VEC, k::vecdiv, G, B, npoin, r, diag, p);
-    TRY(dev_dot(c, npoin, r, p, 0));
+    TRY(dev_dot(c, nred, r, p, 0));
     LAUNCH(K_SCALAR, k::bicg_scalar, 1, 1, c->sc, (int)k::SC_ERRNEW, 0);
+    TRY(halo_vec(c, p, 1));
     LAUNCH(K_SPMV, k::spmv, G, B, npoin, A, idx, rowptr, p, y);
     if (nfix) LAUNCH(K_FIXROWS, k::copy2, GF, 128, nfix, fixIdx, 1.e30, p, y);
-    TRY(dev_dot(c, npoin, p, y, 1));
+    TRY(dev_dot(c, nred, p, y, 1));
     LAUNCH(K_SCALAR, k::bicg_scalar, 1, 1, c->sc, (int)k::SC_PY_ALFA, 1);
     LAUNCH(K_VEC, k::vecsum, G, B, npoin, (int)k::ALFA_POS, 0.0, c->sc, p, x, x);
     TRY(read_scal(c));
@@ -693,18 +798,20 @@ static int bicg_dev(cfdb_ctx* c, const double* A, const int* idx, const int* row
         kk++;
         LAUNCH(K_VEC, k::vecsum, G, B, npoin, (int)k::ALFA_NEG, 0.0, c->sc, y, r, r);
         LAUNCH(K_VEC, k::vecdiv, G, B, npoin, r, diag, z);
-        TRY(dev_dot(c, npoin, r, z, 0));
+        TRY(dev_dot(c, nred, r, z, 0));
         LAUNCH(K_SCALAR, k::bicg_scalar, 1, 1, c->sc, (int)k::SC_BETA, 0);
         LAUNCH(K_VEC, k::vecsum, G, B, npoin, (int)k::BETA_POS, 0.0, c->sc, p, z, p);
+        TRY(halo_vec(c, p, 1));
         LAUNCH(K_SPMV, k::spmv, G, B, npoin, A, idx, rowptr, p, y);
         if (nfix) LAUNCH(K_FIXROWS, k::copy2, GF, 128, nfix, fixIdx, 1.e30, p, y);
-        TRY(dev_dot(c, npoin, p, y, 1));
+        TRY(dev_dot(c, nred, p, y, 1));
         LAUNCH(K_SCALAR, k::bicg_scalar, 1, 1, c->sc, (int)k::SC_PY_ALFA, 1);
         LAUNCH(K_VEC, k::vecsum, G, B, npoin, (int)k::ALFA_POS, 0.0, c->sc, p, x, x);
         TRY(read_scal(c));
         err_old = c->h_sc->err_old;
     }
     *iters = kk;
+    TRY(halo_vec(c, x, 1));  // ghosts of the solution (the caller moves ghost nodes with it)
     return 0;
 }
 
@@ -716,8 +823,11 @@ extern "C" int cfdb_fluid_structure(cfdb_ctx* c, double dtmin, double time) {
     CK(cudaMemsetAsync(c->dypos.p, 0, P * sizeof(double), c->st));
     // XREF(2)=1.4, YREF(2)=0 are overwritten on every call (meshMove.f90:58): applied once in cfdb_create
     if (c->nset)
-        LAUNCH(K_FORCES, k::forces, 1, 32, c->nset, c->set_ptr.p, c->set_n1.p, c->set_n2.p, c->X.p, c->Y.p, c->P.p,
+    {
+        LAUNCH(K_FORCES, k::forces, 1, 32, c->nset, c->n_owned, c->set_ptr.p, c->set_n1.p, c->set_n2.p, c->X.p, c->Y.p, c->P.p,
                c->xref.p, c->yref.p, c->sc);
+        TRY(allreduce(c, c->sc->FX, 30, ncclSum));  // FX,FY,RM are contiguous in Scal
+    }
     double PI = std::acos(-1.0);
     double AMPLI = PI / 8.0;
     double ALPHAV = c->DISN[1], YPOSRV = c->DISN[0];
@@ -741,8 +851,8 @@ extern "C" int cfdb_fluid_structure(cfdb_ctx* c, double dtmin, double time) {
 }
 
 static int run_norms(cfdb_ctx* c) {
-    long m = ((long)c->npoin + 4095) / 4096;
-    LAUNCH(K_NORMS, k::norm_chunks, (int)std::min<long>(m, 148 * 8), 256, (long)c->npoin, c->U.p,
+    long m = ((long)c->n_owned + 4095) / 4096;
+    LAUNCH(K_NORMS, k::norm_chunks, (int)std::min<long>(m, 148 * 8), 256, (long)c->n_owned, c->U.p,
            c->u1_is_u ? c->U.p : c->U1.p, c->redA.p);
     TRY(reduce_levels(c, 8, m, 0));
     CK(cudaMemcpyAsync(c->sc->ER, c->sc->red, 8 * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
@@ -769,6 +879,7 @@ static int step_once(cfdb_ctx* c) {
     else
         LAUNCH(K_DELTAT, k::deltat<false>, grid_for(E, 256), 256, E, c->inp.p, c->area.p, c->T.p, c->VEL_X.p, c->VEL_Y.p,
                c->W_X.p, c->W_Y.p, p.FSAFE, p.T_inf, c->DT.p, c->sc);
+    TRY(allreduce(c, &c->sc->dtmin_acc, 1, ncclMin));
     LAUNCH(K_DTLOGIC, k::dt_logic, 1, 1, c->sc);
     if (p.ITLOCAL != 0) {
         double DTFACT = 1.0 - std::exp(-c->h_iter * 4.6 / p.ITLOCAL);  // :160
@@ -835,6 +946,8 @@ extern "C" int64_t cfdb_launch_count(cfdb_ctx* c) { return c->launches; }
 
 // ---------------------------------------------------------------------------------------------
 // field access
+struct Field;
+static bool find_field(cfdb_ctx* c, const std::string& n, Field& f);
 struct Field {
     void* dev = nullptr;          // device pointer (doubles or ints)
     const void* host = nullptr;   // or host-resident integer artefact
@@ -864,6 +977,17 @@ static bool find_field(cfdb_ctx* c, const std::string& n, Field& f) {
     if (n == "DTL") { f.count = E; f.kind = 3; return true; }
     if (n == "n_ipoin" || n == "n_x" || n == "n_y") { f.count = c->nwn; f.kind = 3; return true; }
     return false;
+}
+extern "C" int cfdb_halo_exchange(cfdb_ctx* c, const char* name) {
+    CK(cudaSetDevice(c->device));
+    Field f;
+    std::string n(name);
+    if (!find_field(c, n, f) || f.kind != 0) return fail("cfdb_halo_exchange: not a nodal float64 field: " + n);
+    int w = f.count == 4 * (int64_t)c->npoin ? 4 : (f.count == c->npoin ? 1 : 0);
+    if (!w) return fail("cfdb_halo_exchange: not a nodal field: " + n);
+    TRY(halo_vec(c, (double*)f.dev, w));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
 }
 extern "C" int64_t cfdb_field_size(cfdb_ctx* c, const char* name) {
     Field f;

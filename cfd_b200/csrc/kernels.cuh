@@ -780,7 +780,7 @@ __global__ void __launch_bounds__(256) move_apply(int npoin, const double* __res
 }
 // FORCES (:171-192): sequential sums over the (few thousand) body edges of each set; one thread per
 // set keeps the reference order exactly.
-__global__ void forces(int nset, const int* __restrict__ sptr, const int* __restrict__ n1a, const int* __restrict__ n2a,
+__global__ void forces(int nset, int n_owned, const int* __restrict__ sptr, const int* __restrict__ n1a, const int* __restrict__ n2a,
                        const double* __restrict__ X, const double* __restrict__ Y, const double* __restrict__ P,
                        const double* __restrict__ xref, const double* __restrict__ yref, Scal* sc) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -788,6 +788,7 @@ __global__ void forces(int nset, const int* __restrict__ sptr, const int* __rest
     double fx = 0.0, fy = 0.0, rm = 0.0;
     for (int k = sptr[s]; k < sptr[s + 1]; ++k) {
         int N1 = n1a[k], N2 = n2a[k];
+        if (N1 >= n_owned) continue;  // multi-rank: an edge is summed by the rank owning its first node
         double D_PRESS = (P[N1] + P[N2]) / 2.0;
         double RLX = X[N1] - X[N2];
         double RLY = Y[N2] - Y[N1];
@@ -824,6 +825,41 @@ __global__ void __launch_bounds__(256) gcl(int npoin, int nelem, const int* __re
         tot2 = tot2 + divW_old * area_old[e] / 3.0;
     }
     M[n] = M[n] + dt * (tot1 + tot2) / 2.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ghost exchange packing: 7 doubles per node (U1(4), T, VEL_X, VEL_Y) or one double
+__global__ void halo_pack_state(int m, const int* __restrict__ idx, const double* __restrict__ U1, const double* __restrict__ T,
+                                const double* __restrict__ VX, const double* __restrict__ VY, double* __restrict__ buf) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    int n = idx[i];
+    double u[4];
+    ld4(U1 + 4 * (size_t)n, u);
+    double* b = buf + 7 * (size_t)i;
+    b[0] = u[0]; b[1] = u[1]; b[2] = u[2]; b[3] = u[3]; b[4] = T[n]; b[5] = VX[n]; b[6] = VY[n];
+}
+__global__ void halo_unpack_state(int m, const int* __restrict__ idx, const double* __restrict__ buf, double* __restrict__ U1,
+                                  double* __restrict__ T, double* __restrict__ VX, double* __restrict__ VY) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    int n = idx[i];
+    const double* b = buf + 7 * (size_t)i;
+    double u[4] = {b[0], b[1], b[2], b[3]};
+    st4(U1 + 4 * (size_t)n, u);
+    T[n] = b[4]; VX[n] = b[5]; VY[n] = b[6];
+}
+__global__ void halo_pack(int m, int w, const int* __restrict__ idx, const double* __restrict__ v, double* __restrict__ buf) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m * w) return;
+    int k = i / w, q = i - k * w;
+    buf[i] = v[(size_t)idx[k] * w + q];
+}
+__global__ void halo_unpack(int m, int w, const int* __restrict__ idx, const double* __restrict__ buf, double* __restrict__ v) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m * w) return;
+    int k = i / w, q = i - k * w;
+    v[(size_t)idx[k] * w + q] = buf[i];
 }
 
 // layout helpers: (3,E) interleaved <-> [3][E]

@@ -209,3 +209,56 @@ def density_bump(lc, amp=0.1, x0=None, y0=None, sigma=None):
     e = pres / ((p["GAMA"] - 1.0) * rho) + 0.5 * (u * u + v * v)
     U = np.stack([rho, rho * u, rho * v, rho * e], 1)
     return dict(U=np.ascontiguousarray(U), T=pres / (rho * p["FR"]), VEL_X=np.full(X.size, u), VEL_Y=np.full(X.size, v))
+
+
+# ---- strip-decomposable square (multi-GPU weak scaling) -------------------------------------------------------
+def _rows_lattice(nx, j0, j1, ny_total, jitter, seed):
+    """Rows j0..j1 (inclusive) of an nx x ny_total jittered lattice with spacing h = 1/(nx-1).
+    Every row has its own RNG stream, so any window of rows reproduces the global mesh exactly."""
+    h = 1.0 / (nx - 1)
+    rows = np.arange(j0, j1 + 1)
+    x = np.tile(np.arange(nx, dtype=np.float64) * h, (rows.size, 1))
+    y = np.repeat((rows.astype(np.float64) * h)[:, None], nx, axis=1)
+    for k, j in enumerate(rows):
+        rng = np.random.default_rng([seed, int(j)])
+        jx = rng.uniform(-jitter, jitter, nx) * h
+        jy = rng.uniform(-jitter, jitter, nx) * h
+        jx[0] = jx[-1] = 0.0
+        jy[0] = jy[-1] = 0.0
+        if j == 0 or j == ny_total - 1:
+            jx[:] = 0.0
+            jy[:] = 0.0
+        x[k] += jx
+        y[k] += jy
+    return x, y
+
+
+def square_rows(n, nranks, rank, mach=0.5, jitter=0.3, seed=12345, name="square", all_rows=False, **kw):
+    """Window (own quad rows +-1) of the `nranks`-strip square mesh; returns (RawCase, first global row)."""
+    nx = n
+    ny_total = nranks * (n - 1) + 1
+    j0 = 0 if all_rows else max(0, rank * (n - 1) - 1)
+    j1 = ny_total - 1 if all_rows else min(ny_total - 1, (rank + 1) * (n - 1) + 1)
+    x, y = _rows_lattice(nx, j0, j1, ny_total, jitter, seed)
+    nrows = j1 - j0 + 1
+    inpoel = _triangulate(x, y, nx, nrows)
+    left = (np.arange(nrows) * nx + 1).astype(I32)
+    right = (np.arange(nrows) * nx + nx).astype(I32)
+    walls = []
+    if j0 == 0:
+        walls.append(_boundary_edges_row(nx, 0))
+    if j1 == ny_total - 1:
+        walls.append(_boundary_edges_row(nx, nrows - 1, reverse=True))
+    wall = np.concatenate(walls).astype(I32) if walls else np.zeros((0, 2), I32)
+    bnd = np.unique(np.concatenate([wall.ravel(), left, right])).astype(I32)
+    raw = RawCase(
+        name=name, X=x.ravel().copy(), Y=y.ravel().copy(), inpoel=inpoel, MACH_inf=mach,
+        fixrho=(left, np.ones(left.size)), fixvi=(left, np.ones(left.size), np.ones(left.size)),
+        wall=wall, ifm=bnd, **kw,
+    )
+    return raw, j0
+
+
+def square_global(n, nranks, **kw):
+    """The whole `nranks`-strip square mesh in one piece (tests; small sizes)."""
+    return square_rows(n, nranks, 0, all_rows=True, **kw)[0]

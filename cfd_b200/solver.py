@@ -58,6 +58,27 @@ class NSComp2D:
         except Exception:
             pass
 
+    # ---- multi-GPU -----------------------------------------------------------------------------
+    def attach_partition(self, part):
+        """Register the ghost-exchange lists of a cfd_b200.partition.LocalPart (this context holds part.lc)."""
+        ranks, sp, si, rp, ri = part.halo_arrays()
+        self._halo_keep = (ranks, sp, si, rp, ri)
+        capi.check(self.L.cfdb_set_halo(self.h, part.n_owned, ranks.size, ranks, sp, si, rp, ri))
+        self.part = part
+
+    def comm_init(self, uid: bytes, rank: int, nranks: int):
+        buf = C.create_string_buffer(uid, 128)
+        capi.check(self.L.cfdb_comm_init(self.h, C.cast(buf, C.c_void_p), rank, nranks))
+
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        capi.check(capi.lib().cfdb_nccl_unique_id(C.cast(buf, C.c_void_p)))
+        return buf.raw
+
+    def halo_exchange(self, name):
+        capi.check(self.L.cfdb_halo_exchange(self.h, name.encode()))
+
     # ---- resident mode -------------------------------------------------------------------
     def step(self, n=1):
         capi.check(self.L.cfdb_step(self.h, n))

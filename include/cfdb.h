@@ -90,6 +90,19 @@ int cfdb_profile_enable(cfdb_ctx* ctx, int32_t on);
 int cfdb_profile_get(cfdb_ctx* ctx, const char* kernel, double* total_ms, int64_t* launches);
 int64_t cfdb_launch_count(cfdb_ctx* ctx);                    /* kernels launched since create */
 
+/* ---- multi-GPU: one context per rank/GPU on a sub-domain built by cfd_b200/partition.py ------------
+ * (new: the reference is single-process.)  Rank r computes every element touching a node it owns, so
+ * owned-node sums are complete and bit-identical to the single-GPU run; ghost nodes are refreshed from their
+ * owners after every RK stage (ncclSend/ncclRecv, one packed message per neighbour); DTMIN is an
+ * ncclAllReduce(min); biCG inner products and the residual norms are ncclAllReduce(sum) of per-rank
+ * canonical sums over owned nodes.  Local numbering: owned nodes first. */
+int cfdb_nccl_unique_id(void* out128);                       /* ncclGetUniqueId on one rank; broadcast it yourself */
+int cfdb_comm_init(cfdb_ctx* ctx, const void* uid128, int32_t rank, int32_t nranks);
+int cfdb_set_halo(cfdb_ctx* ctx, int32_t n_owned, int32_t nneigh, const int32_t* neigh_rank,
+                  const int32_t* send_ptr, const int32_t* send_idx, const int32_t* recv_ptr,
+                  const int32_t* recv_idx);                  /* 0-based local node ids, CSR per neighbour */
+int cfdb_halo_exchange(cfdb_ctx* ctx, const char* field);    /* refresh the ghosts of one nodal field ("T", "U", ...) */
+
 /* ---- (i) call-site mode: one entry point per reference subroutine, host pointers ------------ */
 /* calcRHS_mod::calcRHS, calcRHS.f90:4 (module inputs FCV,FK,FMU,gama,T_inf,cte and T(:) made explicit) */
 int cfdb_calcrhs(cfdb_ctx* ctx, double* rhs, const double* U, const double* theta, const double* T,

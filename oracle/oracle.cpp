@@ -685,12 +685,6 @@ static void rk_stage(Solver& s, int IRK, int NRK) {
     }
 }
 
-static void rk(Solver& s, int NRK) {
-    for (int IRK = 1; IRK <= NRK; ++IRK) rk_stage(s, IRK, NRK);
-    if (s.BANDERA == 2) s.RHS3 = s.RHS;       // :830-848
-    else if (s.BANDERA == 3) s.RHS2 = s.RHS;
-    else if (s.BANDERA == 4) s.RHS1 = s.RHS;
-}
 
 // meshMove.f90:153-194  FORCES
 static void forces(Solver& s) {
@@ -766,12 +760,26 @@ static void residual_norms(Solver& s) {
     }
 }
 
-// ns2DComp.ALE.f90:138-282  one pass of the time loop
-static void step(Solver& s) {
+// ns2DComp.ALE.f90:138-282  one pass of the time loop, in three pieces so that a multi-rank harness
+// (tests/test_partition_gloo.py) can put its exchanges where the GPU path has them:
+//   part1: ITER++, DELTAT                              (then: global min of DTMIN over ranks)
+//   part2: DTMIN freeze logic, DTL, TIME, U1=U         (then: 4 x rk_stage, ghost exchange after each)
+//   part3: fluidStructure, residual norms, BANDERA++, geometry if MOVING, U=U1
+static double step_part1(Solver& s) {
     const Params& p = s.par;
     s.ITER += 1;
     deltat(s.nelem, s.inpoel.data(), s.area.data(), s.T.data(), s.VEL_X.data(), s.VEL_Y.data(), s.W_X.data(),
            s.W_Y.data(), p.FSAFE, p.FR, p.GAMA, p.T_inf, s.DT.data(), &s.DTMIN);
+    return s.DTMIN;
+}
+static void step_part2(Solver& s, double dtmin_global) {
+    const Params& p = s.par;
+    if (dtmin_global != s.DTMIN) {  // multi-rank: the clamp DT <= 10*DTMIN (subrutinas.f90:211-215) uses the global min
+        double COTA = 10.0 * dtmin_global;
+        for (int ie = 0; ie < s.nelem; ++ie)
+            if (s.DT[ie] > COTA) s.DT[ie] = COTA;
+    }
+    s.DTMIN = dtmin_global;
     if (s.BANDERA == 1) { s.DTMIN1 = s.DTMIN; s.BANDERA = 2; }
     double PORC = std::fabs((s.DTMIN - s.DTMIN1) / s.DTMIN);
     if (100.0 * PORC <= 1.0) s.DTMIN = s.DTMIN1;
@@ -784,7 +792,12 @@ static void step(Solver& s) {
     }
     s.TIME = s.TIME + s.DTMIN;
     s.U1 = s.U;
-    rk(s, 4);
+}
+static void step_part3(Solver& s) {
+    const Params& p = s.par;
+    if (s.BANDERA == 2) s.RHS3 = s.RHS;       // subrutinas.f90:830-848 (end of RK)
+    else if (s.BANDERA == 3) s.RHS2 = s.RHS;
+    else if (s.BANDERA == 4) s.RHS1 = s.RHS;
     fluid_structure(s, s.DTMIN, s.TIME);
     s.ITERPRINT += 1;
     if (s.ITERPRINT == p.IPRINT || s.ITER == p.MAXITER || s.norms_every_step) {  // :186-197
@@ -794,6 +807,12 @@ static void step(Solver& s) {
     s.BANDERA += 1;
     if (p.MOVING == 1) geometry(s, true);
     s.U = s.U1;
+}
+static void step(Solver& s) {
+    double d = step_part1(s);
+    step_part2(s, d);
+    for (int IRK = 1; IRK <= 4; ++IRK) rk_stage(s, IRK, 4);
+    step_part3(s);
 }
 
 }  // namespace orc
@@ -956,6 +975,9 @@ void orc_init(void* h) {
     s.DISN[0] = s.DISN[1] = 0.0;                  // setNewmarkCondition meshMove.f90:15-26
 }
 void orc_step(void* h, int n) { for (int i = 0; i < n; ++i) step(*(Solver*)h); }
+double orc_step_part1(void* h) { return step_part1(*(Solver*)h); }
+void orc_step_part2(void* h, double dtmin_global) { step_part2(*(Solver*)h, dtmin_global); }
+void orc_step_part3(void* h) { step_part3(*(Solver*)h); }
 void orc_rk_stage(void* h, int irk) { rk_stage(*(Solver*)h, irk, 4); }
 void orc_geometry(void* h, int moving_step) { geometry(*(Solver*)h, moving_step != 0); }
 void orc_fluid_structure(void* h, double dtmin, double time) { fluid_structure(*(Solver*)h, dtmin, time); }

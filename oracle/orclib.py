@@ -58,6 +58,10 @@ def lib(omp=False):
         getattr(L, f).restype = None
     L.orc_step.argtypes = [C.c_void_p, C.c_int]
     L.orc_rk_stage.argtypes = [C.c_void_p, C.c_int]
+    L.orc_step_part1.argtypes = [C.c_void_p]
+    L.orc_step_part1.restype = C.c_double
+    L.orc_step_part2.argtypes = [C.c_void_p, C.c_double]
+    L.orc_step_part3.argtypes = [C.c_void_p]
     L.orc_geometry.argtypes = [C.c_void_p, C.c_int]
     L.orc_fluid_structure.argtypes = [C.c_void_p, C.c_double, C.c_double]
     L.orc_residual_norms.argtypes = [C.c_void_p, _dp, _dp]
@@ -163,6 +167,15 @@ class Oracle:
 
     def rk_stage(self, irk):
         self.L.orc_rk_stage(self.h, irk)
+
+    def step_part1(self):
+        return self.L.orc_step_part1(self.h)
+
+    def step_part2(self, dtmin_global):
+        self.L.orc_step_part2(self.h, dtmin_global)
+
+    def step_part3(self):
+        self.L.orc_step_part3(self.h)
 
     def norms(self):
         er, err = np.zeros(4), np.zeros(4)
