@@ -112,7 +112,7 @@ def cpu_oracle_throughput(n_lattice, steps, warmup=1):
     return lc.nelem * steps / dt, o.L.orc_omp_threads(), lc.nelem, dt
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, out):
     if rank != 0:
         return
     n = args.ref_n
@@ -140,10 +140,13 @@ def run_reference(args, rank):
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "C++ restatement of chanshing/cfd (oracle/), not the Fortran binary: no Fortran compiler in the image",
-    }))
+    }), file=out, flush=True)
 
 
 def main():
+    # stdout carries exactly one JSON line: libraries that chat on fd 1 (NCCL prints its version there) go to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -161,7 +164,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, real_stdout)
         return
 
     import torch
@@ -190,7 +193,7 @@ def main():
     lc = part.lc
     E = 2 * (args.n - 1) ** 2          # elements of this rank's own range (global elements / world)
     P = part.n_owned
-    bump = meshgen.density_bump(lc, x0=0.5, y0=0.5 * world, sigma=0.15)
+    bump = meshgen.density_bump(lc, x0=0.5, y0=0.5, sigma=0.15, period_y=1.0)  # one bump per strip
     for k, v in bump.items():
         g.set(k, v)
     t_gen = time.perf_counter() - t_gen
@@ -307,7 +310,7 @@ def main():
                        "parallelism": f"{world} contiguous strips, owner-computes + NCCL ghost refresh per RK stage",
                        "element_stage_updates_per_s": 4 * value, "setup_s": t_gen},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": launches,
-        }))
+        }), file=real_stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

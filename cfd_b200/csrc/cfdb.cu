@@ -822,9 +822,9 @@ extern "C" int cfdb_fluid_structure(cfdb_ctx* c, double dtmin, double time) {
     CK(cudaMemsetAsync(c->dxpos.p, 0, P * sizeof(double), c->st));
     CK(cudaMemsetAsync(c->dypos.p, 0, P * sizeof(double), c->st));
     // XREF(2)=1.4, YREF(2)=0 are overwritten on every call (meshMove.f90:58): applied once in cfdb_create
-    if (c->nset)
-    {
-        LAUNCH(K_FORCES, k::forces, 1, 32, c->nset, c->n_owned, c->set_ptr.p, c->set_n1.p, c->set_n2.p, c->X.p, c->Y.p, c->P.p,
+    if (c->nset || c->nranks > 1) {  // every rank joins the all-reduce, with or without body edges of its own
+        CK(cudaMemsetAsync(c->sc->FX, 0, 30 * sizeof(double), c->st));
+        if (c->nset) LAUNCH(K_FORCES, k::forces, 1, 32, c->nset, c->n_owned, c->set_ptr.p, c->set_n1.p, c->set_n2.p, c->X.p, c->Y.p, c->P.p,
                c->xref.p, c->yref.p, c->sc);
         TRY(allreduce(c, c->sc->FX, 30, ncclSum));  // FX,FY,RM are contiguous in Scal
     }

@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(128, MINB) calcrhs_elem(int e0, int e1, int ne
             th_k[i] = THETA ? (Nk[0] * Th[0][i] + Nk[1] * Th[1][i] + Nk[2] * Th[2][i]) : 0.0;
         }
         double rho = U_k[0];
-        double v1 = U_k[1] / rho, v2 = U_k[2] / rho, en = U_k[3] / rho;
+        double v1 = ex::divz(U_k[1], rho), v2 = ex::divz(U_k[2], rho), en = U_k[3] / rho;
         double V_sq = v1 * v1 + v2 * v2;
         double A[4];
         A[0] = Ux[1] + Uy[2];

@@ -193,7 +193,7 @@ def retriangulate_delaunay(raw: RawCase, inside=None) -> RawCase:
     return raw
 
 
-def density_bump(lc, amp=0.1, x0=None, y0=None, sigma=None):
+def density_bump(lc, amp=0.1, x0=None, y0=None, sigma=None, period_y=None):
     """Smooth initial density perturbation at free-stream pressure and velocity.
 
     Returns dict(U, T, VEL_X, VEL_Y) to be set on both the oracle and the CUDA solver after init.
@@ -203,7 +203,10 @@ def density_bump(lc, amp=0.1, x0=None, y0=None, sigma=None):
     x0 = 0.5 * (X.min() + X.max()) if x0 is None else x0
     y0 = 0.5 * (Y.min() + Y.max()) if y0 is None else y0
     sigma = 0.15 * min(X.max() - X.min(), Y.max() - Y.min()) if sigma is None else sigma
-    rho = p["RHO_inf"] * (1.0 + amp * np.exp(-((X - x0) ** 2 + (Y - y0) ** 2) / sigma**2))
+    dy = Y - y0
+    if period_y:  # one bump per strip of height period_y (multi-GPU weak scaling: same flow on every rank)
+        dy = (Y - np.floor(Y / period_y) * period_y) - y0
+    rho = p["RHO_inf"] * (1.0 + amp * np.exp(-((X - x0) ** 2 + dy**2) / sigma**2))
     pres = p["RHO_inf"] * p["FR"] * p["T_inf"]
     u, v = p["U_inf"], p["V_inf"]
     e = pres / ((p["GAMA"] - 1.0) * rho) + 0.5 * (u * u + v * v)

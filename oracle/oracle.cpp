@@ -912,6 +912,24 @@ void orc_gcl_main(double* M, const double* W_x, const double* W_y, const double*
 int orc_smoothing(double* X, double* Y, const int* inpoel, const unsigned char* fixed, int npoin, int nelem) {
     return smoothing(X, Y, inpoel, fixed, npoin, nelem);
 }
+// x/3 by the three-operation sequence the CUDA kernels use (exact.cuh div3): number of inputs, out of n random
+// normal doubles, for which it differs from the IEEE quotient (must be 0)
+long orc_div3_mismatches(long n, unsigned long long seed) {
+    const double z = 0.33333333333333331482961625624739;
+    unsigned long long s = seed ? seed : 88172645463325252ull;
+    long bad = 0;
+    for (long i = 0; i < n; ++i) {
+        s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+        unsigned long long bits = (s & 0x800fffffffffffffull) | ((unsigned long long)(64 + (s >> 52) % 1920) << 52);
+        double x;
+        memcpy(&x, &bits, 8);
+        double q = x * z;
+        double r = __builtin_fma(-3.0, q, x);
+        double d = __builtin_fma(r, z, q);
+        if (d != x / 3.0) ++bad;
+    }
+    return bad;
+}
 double orc_pow15(double x) { return pow15(x); }
 double orc_pow05(double x) { return pow05(x); }
 double orc_powm05(double x) { return powm05(x); }

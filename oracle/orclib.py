@@ -72,6 +72,8 @@ def lib(omp=False):
     for f in ("orc_pow15", "orc_pow05", "orc_powm05"):
         getattr(L, f).argtypes = [C.c_double]
         getattr(L, f).restype = C.c_double
+    L.orc_div3_mismatches.argtypes = [C.c_long, C.c_ulonglong]
+    L.orc_div3_mismatches.restype = C.c_long
     L.orc_canon_sum.argtypes = [C.c_long, _dp]
     L.orc_canon_sum.restype = C.c_double
     L.orc_vecdot.argtypes = [C.c_int, _dp, _dp]

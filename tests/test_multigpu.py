@@ -24,5 +24,5 @@ def test_two_ranks_match_undivided_oracle(case):
     world = 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", "29611", os.path.join(ROOT, "tests", "mg_worker.py"), case, "6"]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=180)
     assert r.returncode == 0 and "MULTIGPU_OK" in r.stdout, r.stdout[-4000:]
