@@ -749,6 +749,15 @@ extern "C" int cfdb_rk_stage(cfdb_ctx* c, int32_t irk) {
     }
     // software pipeline: the (memory-bound) node kernel of chunk k runs on st2 while the (fp64-bound) element
     // kernel of chunk k+1 runs on st; st2 joins st at the end of the stage
+    static const bool seq = getenv("CFDB_CHUNK_SEQ") != nullptr;  // same stream: L2-blocking only, no overlap
+    if (seq) {
+        for (int kc = 0; kc < nch; ++kc) {
+            TRY(run_calcrhs_elem(c, g, false, c->ale, dtl_arr, &c->sc->DTMIN, c->chunk_e[kc], c->chunk_e[kc + 1]));
+            TRY(run_node(c, c->st, c->ale, true, RK_FACT, c->chunk_n[kc], c->chunk_n[kc + 1]));
+        }
+        TRY(halo_state(c));
+        return 0;
+    }
     for (int kc = 0; kc < nch; ++kc) {
         TRY(run_calcrhs_elem(c, g, false, c->ale, dtl_arr, &c->sc->DTMIN, c->chunk_e[kc], c->chunk_e[kc + 1]));
         if (c->chunk_n[kc + 1] > c->chunk_n[kc]) {
