@@ -875,6 +875,13 @@ extern "C" int cfdb_residual_norms(cfdb_ctx* c, double er[4], double err[4]) {
     return 0;
 }
 
+extern "C" int cfdb_step_norms(cfdb_ctx* c, double er[4], double err[4]) {
+    CK(cudaSetDevice(c->device));
+    TRY(read_scal(c));
+    for (int i = 0; i < 4; ++i) { er[i] = c->h_sc->ER[i]; err[i] = c->h_sc->ERR[i]; }
+    return 0;
+}
+
 // one pass of ns2DComp.ALE.f90:138-282
 static int step_once(cfdb_ctx* c) {
     const cfdb_params& p = c->par;

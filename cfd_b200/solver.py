@@ -100,6 +100,12 @@ class NSComp2D:
         capi.check(self.L.cfdb_residual_norms(self.h, er, err))
         return er, err
 
+    def step_norms(self):
+        """ER, ERR as evaluated inside the last print step of cfdb_step (before U = U1)."""
+        er, err = np.zeros(4), np.zeros(4)
+        capi.check(self.L.cfdb_step_norms(self.h, er, err))
+        return er, err
+
     def get(self, name):
         n = self.L.cfdb_field_size(self.h, name.encode())
         if n < 0:

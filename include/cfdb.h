@@ -75,7 +75,9 @@ int cfdb_sync(cfdb_ctx* ctx);
 int cfdb_rk_stage(cfdb_ctx* ctx, int32_t irk);               /* body of RK's IRK loop, subrutinas.f90:667-828 */
 int cfdb_geometry(cfdb_ctx* ctx, int32_t moving_step);       /* NORMALES, DERIV, MASAS[, gcl], laplace */
 int cfdb_fluid_structure(cfdb_ctx* ctx, double dtmin, double time); /* meshMove.f90:28-142 */
-int cfdb_residual_norms(cfdb_ctx* ctx, double er[4], double err[4]); /* ns2DComp.ALE.f90:191-197 */
+int cfdb_residual_norms(cfdb_ctx* ctx, double er[4], double err[4]); /* ns2DComp.ALE.f90:191-197, evaluated now */
+/* the norms cfdb_step evaluated on its last print step (ITERPRINT==IPRINT or ITER==MAXITER, :186), i.e. before U=U1 */
+int cfdb_step_norms(cfdb_ctx* ctx, double er[4], double err[4]);
 /* field transfer by Fortran variable name ("U","U1","RHS","T","VEL_X","X","inpoel","esup1","lap_idx",...);
  * count = number of elements of the host buffer (checked).  Layout/1-basing as in the header comment. */
 int cfdb_get(cfdb_ctx* ctx, const char* name, void* host, int64_t count);

@@ -1,0 +1,70 @@
+"""host/ns2dcomp — the C++ mirror of PROGRAM NSComp2D: deck reading, smoothing (CPU), and the run itself (GPU)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from cfd_b200 import deck, meshgen
+from conftest import assert_bit_equal
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "host", "ns2dcomp")
+
+
+def _build():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "host")], stdout=subprocess.DEVNULL)
+
+
+def test_deck_reader_and_smoothing_match_oracle(tmp_path):
+    from oracle import orclib
+
+    _build()
+    raw = meshgen.channel(nx=25, ny=9, jitter=0.42, seed=5, mach=0.7, CTE=2.0)
+    raw.fixv = np.array([30, 31], np.int32)
+    deck.write_deck(raw, str(tmp_path))
+    fx, fy = str(tmp_path / "x.bin"), str(tmp_path / "y.bin")
+    r = subprocess.run([EXE, str(tmp_path), "--check-deck", "--dump", "X:" + fx, "--dump", "Y:" + fy], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lc = deck.load(raw)
+    assert f"U_inf={lc.par['U_inf']!r}" in r.stdout.replace("U_inf=", "U_inf=") or repr(lc.par["U_inf"])[:15] in r.stdout
+    assert f"nfixv={lc.ifixv_node.size} " in r.stdout and f"nfixt={lc.ifixt_node.size} " in r.stdout
+    X, Y = lc.X.copy(), lc.Y.copy()
+    sweeps = orclib.lib().orc_smoothing(X, Y, lc.inpoel, lc.smooth_fix, lc.npoin, lc.nelem)
+    assert f"sweeps:{sweeps}" in r.stdout and sweeps > 0
+    assert_bit_equal(np.fromfile(fx), X, "smoothed X")
+    assert_bit_equal(np.fromfile(fy), Y, "smoothed Y")
+
+
+def test_bad_deck_stops(tmp_path):
+    _build()
+    r = subprocess.run([EXE, str(tmp_path), "--check-deck"], capture_output=True, text=True)
+    assert r.returncode != 0 and "EULER.DAT" in r.stderr
+
+
+@pytest.mark.gpu
+def test_driver_run_matches_oracle(tmp_path):
+    from oracle import orclib
+    from oracle.orclib import Oracle
+
+    _build()
+    raw = meshgen.channel(nx=41, ny=13, jitter=0.4, seed=9, MAXITER=12, IPRINT=5, FMU=1.8e-5, FK=0.0257)
+    deck.write_deck(raw, str(tmp_path))
+    fu = str(tmp_path / "u.bin")
+    r = subprocess.run([EXE, str(tmp_path), "--dump", "U:" + fu], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lc = deck.load(deck.read_deck(str(tmp_path)))
+    orclib.lib().orc_smoothing(lc.X, lc.Y, lc.inpoel, lc.smooth_fix, lc.npoin, lc.nelem)
+    o = Oracle(lc)
+    o.set_scalar("norms_every_step", 0)
+    rows = []
+    for it in range(1, 13):
+        o.step(1)
+        if it % 5 == 0 or it == 12:
+            rows.append((it, o.scalar("TIME")))
+    assert_bit_equal(np.fromfile(fu), o.get("U"), "U after 12 steps")
+    cnv = [l.split() for l in open(tmp_path / "channel.cnv").read().strip().split("\n")]
+    assert [int(c[0]) for c in cnv] == [5, 10, 12]
+    for c, (it, t) in zip(cnv, rows):
+        assert abs(float(c[1]) - t) <= 1e-6 * t
+        assert all(0 < float(v) < 1 for v in c[2:6])
