@@ -75,6 +75,9 @@ struct cfdb_ctx {
     vector<int> chunk_e, chunk_n;          // element / node range boundaries of the stage pipeline (nchunk+1 each)
     vector<cudaEvent_t> chunk_ev;
     cudaEvent_t ev_join = nullptr;
+    cudaEvent_t ev_elem[4] = {nullptr, nullptr, nullptr, nullptr}, ev_node[4] = {nullptr, nullptr, nullptr, nullptr};
+    double* ECcur = nullptr;  // staging buffers the element / node kernels use right now (double-buffered when
+    double* FCcur = nullptr;  // node_update(k) overlaps calcrhs_elem(k+1))
     cfdb_params par{};
     int npoin = 0, nelem = 0;
     // host copies of integer artefacts (API layout: 1-based)
@@ -88,11 +91,13 @@ struct cfdb_ctx {
     DBuf<double> X, Y, X1, Y1, area, HH, HHX, HHY, dNx, dNy, M;
     // device: state
     DBuf<double> U, U1, RHS, RHS1, RHS2, RHS3, UN, VEL_X, VEL_Y, W_X, W_Y, P, T, RHO, E, RMACH, GAMM;
-    DBuf<double> SHOC, TS1, TS2, TS3, DT, DTL, EC, FC;
+    DBuf<double> SHOC, TS1, TS2, TS3, DT, DTL, EC, FC, EC2, FC2;
     // device: BC tables
     DBuf<int> bc_node, bc_kind, bc_wslot;
     DBuf<double> bc_vx, bc_vy, bc_rho, bc_T, wn_x, wn_y;
     // device: laplace / bicg / mesh motion
+    DBuf<unsigned char> isfix;
+    DBuf<double> bp2;
     DBuf<double> lap_sparse, lap_diag, by, bp, br, bz, bb, xpos, ypos, dxpos, dypos, pos_aux, xref, yref;
     DBuf<int> ilaux, ilaux_last, se_node, se_set, set_ptr, set_n1, set_n2;
     // gcl
@@ -350,6 +355,10 @@ extern "C" int cfdb_create(cfdb_ctx** out, const cfdb_params* par, int32_t npoin
         if (cudaStreamCreateWithPriority(&c->st, cudaStreamNonBlocking, lo) != cudaSuccess) return bail(fail("stream create failed"));
         if (cudaStreamCreateWithPriority(&c->st2, cudaStreamNonBlocking, hi) != cudaSuccess) return bail(fail("stream create failed"));
         if (cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) return bail(fail("event create failed"));
+        for (int i = 0; i < 4; ++i)
+            if (cudaEventCreateWithFlags(&c->ev_elem[i], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&c->ev_node[i], cudaEventDisableTiming) != cudaSuccess)
+                return bail(fail("event create failed"));
     }
     const size_t P = npoin, E = nelem;
     c->h_inpoel.assign(inpoel, inpoel + 3 * E);
@@ -405,7 +414,7 @@ extern "C" int cfdb_create(cfdb_ctx** out, const cfdb_params* par, int32_t npoin
     B(upload(c, c->X, X, P));
     B(upload(c, c->Y, Y, P));
     for (auto* d : {&c->X1, &c->Y1, &c->M, &c->VEL_X, &c->VEL_Y, &c->W_X, &c->W_Y, &c->P, &c->T, &c->RHO, &c->E, &c->RMACH,
-                    &c->GAMM, &c->lap_diag, &c->by, &c->bp, &c->br, &c->bz, &c->bb, &c->xpos, &c->ypos, &c->dxpos,
+                    &c->GAMM, &c->lap_diag, &c->by, &c->bp, &c->bp2, &c->br, &c->bz, &c->bb, &c->xpos, &c->ypos, &c->dxpos,
                     &c->dypos, &c->pos_aux, &c->W_x_old, &c->W_y_old, &c->tmpA, &c->tmpB, &c->tmpC})
         B(zero(c, *d, P));
     for (auto* d : {&c->U, &c->U1, &c->RHS, &c->RHS1, &c->RHS2, &c->RHS3, &c->UN}) B(zero(c, *d, 4 * P));
@@ -443,6 +452,8 @@ extern "C" void cfdb_destroy(cfdb_ctx* c) {
     c->send_idx.release(); c->recv_idx.release(); c->sendbuf.release(); c->recvbuf.release();
     for (auto e : c->chunk_ev) cudaEventDestroy(e);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    for (int i = 0; i < 4; ++i) { if (c->ev_elem[i]) cudaEventDestroy(c->ev_elem[i]); if (c->ev_node[i]) cudaEventDestroy(c->ev_node[i]); }
+    c->EC2.release(); c->FC2.release();
     if (c->st2) cudaStreamDestroy(c->st2);
     for (auto* d : {&c->inp, &c->d_esup2, &c->eslot, &c->d_lap_idx, &c->d_lap_rowptr, &c->wall, &c->wn_node, &c->wn_ptr,
                     &c->wn_edge, &c->wn_valid, &c->bc_node, &c->bc_kind, &c->bc_wslot, &c->ilaux, &c->ilaux_last, &c->se_node,
@@ -450,6 +461,8 @@ extern "C" void cfdb_destroy(cfdb_ctx* c) {
         d->release();
     c->lpos.release();
     c->bcflag.release();
+    c->isfix.release();
+    c->bp2.release();
     for (auto* d : {&c->X, &c->Y, &c->X1, &c->Y1, &c->area, &c->HH, &c->HHX, &c->HHY, &c->dNx, &c->dNy, &c->M, &c->U, &c->U1,
                     &c->RHS, &c->RHS1, &c->RHS2, &c->RHS3, &c->UN, &c->VEL_X, &c->VEL_Y, &c->W_X, &c->W_Y, &c->P, &c->T,
                     &c->RHO, &c->E, &c->RMACH, &c->GAMM, &c->SHOC, &c->TS1, &c->TS2, &c->TS3, &c->DT, &c->DTL, &c->EC, &c->FC,
@@ -505,15 +518,15 @@ extern "C" int cfdb_set_halo(cfdb_ctx* c, int32_t n_owned, int32_t nneigh, const
     return 0;
 }
 // exchange `w` doubles per node between sendbuf and recvbuf (already packed / to be unpacked by the caller)
-static int halo_sendrecv(cfdb_ctx* c, int w) {
+static int halo_sendrecv(cfdb_ctx* c, int w, cudaStream_t st) {
     const int nn = (int)c->nb_rank.size();
     if (!nn) return 0;
     if (!c->comm) return fail("halo exchange requested but cfdb_comm_init was not called");
     NK(ncclGroupStart());
     for (int k = 0; k < nn; ++k) {
         int ns = c->send_ptr[k + 1] - c->send_ptr[k], nr = c->recv_ptr[k + 1] - c->recv_ptr[k];
-        if (ns) NK(ncclSend(c->sendbuf.p + (size_t)w * c->send_ptr[k], (size_t)w * ns, ncclDouble, c->nb_rank[k], c->comm, c->st));
-        if (nr) NK(ncclRecv(c->recvbuf.p + (size_t)w * c->recv_ptr[k], (size_t)w * nr, ncclDouble, c->nb_rank[k], c->comm, c->st));
+        if (ns) NK(ncclSend(c->sendbuf.p + (size_t)w * c->send_ptr[k], (size_t)w * ns, ncclDouble, c->nb_rank[k], c->comm, st));
+        if (nr) NK(ncclRecv(c->recvbuf.p + (size_t)w * c->recv_ptr[k], (size_t)w * nr, ncclDouble, c->nb_rank[k], c->comm, st));
     }
     NK(ncclGroupEnd());
     c->launches += 1;
@@ -524,18 +537,19 @@ static int halo_vec(cfdb_ctx* c, double* v, int w) {
     if (!nn) return 0;
     int ms = c->send_ptr[nn], mr = c->recv_ptr[nn];
     if (ms) LAUNCH(K_HALO, k::halo_pack, grid_for((long)ms * w, 128), 128, ms, w, c->send_idx.p, v, c->sendbuf.p);
-    TRY(halo_sendrecv(c, w));
+    TRY(halo_sendrecv(c, w, c->st));
     if (mr) LAUNCH(K_HALO, k::halo_unpack, grid_for((long)mr * w, 128), 128, mr, w, c->recv_idx.p, c->recvbuf.p, v);
     return 0;
 }
 // ghosts of U1, T, VEL_X, VEL_Y in one message per neighbour (after every RK stage)
-static int halo_state(cfdb_ctx* c) {
+static int halo_state(cfdb_ctx* c, cudaStream_t st = nullptr) {
     const int nn = (int)c->nb_rank.size();
     if (!nn) return 0;
+    if (!st) st = c->st;
     int ms = c->send_ptr[nn], mr = c->recv_ptr[nn];
-    if (ms) LAUNCH(K_HALO, k::halo_pack_state, grid_for(ms, 128), 128, ms, c->send_idx.p, c->U1.p, c->T.p, c->VEL_X.p, c->VEL_Y.p, c->sendbuf.p);
-    TRY(halo_sendrecv(c, 7));
-    if (mr) LAUNCH(K_HALO, k::halo_unpack_state, grid_for(mr, 128), 128, mr, c->recv_idx.p, c->recvbuf.p, c->U1.p, c->T.p, c->VEL_X.p, c->VEL_Y.p);
+    if (ms) LAUNCH_ON(st, K_HALO, k::halo_pack_state, grid_for(ms, 128), 128, ms, c->send_idx.p, c->U1.p, c->T.p, c->VEL_X.p, c->VEL_Y.p, c->sendbuf.p);
+    TRY(halo_sendrecv(c, 7, st));
+    if (mr) LAUNCH_ON(st, K_HALO, k::halo_unpack_state, grid_for(mr, 128), 128, mr, c->recv_idx.p, c->recvbuf.p, c->U1.p, c->T.p, c->VEL_X.p, c->VEL_Y.p);
     return 0;
 }
 static int allreduce(cfdb_ctx* c, double* dev, int count, ncclRedOp_t op) {
@@ -669,7 +683,13 @@ static k::BcTab bctab(cfdb_ctx* c) {
 
 static int run_estab(cfdb_ctx* c, const double* dtmin_dev) {
     const cfdb_params& p = c->par;
-    LAUNCH(K_ESTAB, k::estab, grid_for(c->nelem, 256), 256, c->nelem, c->inp.p, c->U.p, c->T.p, c->VEL_X.p, c->VEL_Y.p,
+    static int minb = getenv("CFDB_ESTAB_MINB") ? atoi(getenv("CFDB_ESTAB_MINB")) : 5;  // 48 regs, 40 warps/SM: 1.01 ms vs 1.29
+    auto kern = k::estab<3>;
+    if (minb == 4) kern = k::estab<4>;
+    else if (minb == 5) kern = k::estab<5>;
+    else if (minb == 6) kern = k::estab<6>;
+    else if (minb == 2) kern = k::estab<2>;
+    LAUNCH(K_ESTAB, kern, grid_for(c->nelem, 256), 256, c->nelem, c->inp.p, c->U.p, c->T.p, c->VEL_X.p, c->VEL_Y.p,
            c->W_X.p, c->W_Y.p, c->GAMM.p, c->dNx.p, c->dNy.p, p.FR, dtmin_dev, p.RHO_inf, p.T_inf, c->SHOC.p, c->TS1.p,
            c->TS2.p, c->TS3.p);
     return 0;
@@ -683,7 +703,32 @@ static int run_calcrhs_elem(cfdb_ctx* c, const k::Gas& g, bool theta, bool ale, 
     if (e1 <= e0) return 0;
     const int B = 128, G = grid_for(e1 - e0, B);
 #define ARGS e0, e1, c->nelem, c->inp.p, c->U.p, c->UN.p, c->T.p, c->W_X.p, c->W_Y.p, c->dNx.p, c->dNy.p, c->area.p, c->SHOC.p, \
-             dtl_arr, dtl_sc, c->TS1.p, c->TS2.p, c->TS3.p, g, c->EC.p, c->FC.p
+             dtl_arr, dtl_sc, c->TS1.p, c->TS2.p, c->TS3.p, g, (c->ECcur ? c->ECcur : c->EC.p), (c->FCcur ? c->FCcur : c->FC.p)
+    // persistent cp.async-pipelined variant: whole-mesh launches on fixed meshes with theta = 0
+    static const int pipe = getenv("CFDB_CALCRHS_PIPE") ? atoi(getenv("CFDB_CALCRHS_PIPE")) : 0;
+    if (pipe && !theta && !ale && e0 == 0 && e1 == c->nelem) {
+        int nsm = 148;
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
+        const int ntiles = (c->nelem + 127) / 128;
+#define PIPE_LAUNCH(V, M)                                                                                         \
+        {                                                                                                         \
+            auto kp = k::calcrhs_pipe<V, M>;                                                                      \
+            const int smem = 2 * k::PipeLayout<V>::kStageBytes;                                                   \
+            CK(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                      \
+            int grid = std::min(ntiles, nsm * M);                                                                 \
+            cudaEvent_t _a = nullptr, _b = nullptr;                                                               \
+            TRY(prof_begin(c, c->st, K_CALCRHS, &_a, &_b));                                                       \
+            kp<<<grid, 128, smem, c->st>>>(c->nelem, c->inp.p, c->U.p, c->T.p, c->dNx.p, c->dNy.p, c->area.p,     \
+                                           c->SHOC.p, dtl_arr, dtl_sc, c->TS1.p, c->TS2.p, c->TS3.p, g,           \
+                                           (c->ECcur ? c->ECcur : c->EC.p));                                      \
+            CK(cudaGetLastError());                                                                               \
+            TRY(prof_end(c, c->st, K_CALCRHS, _a, _b));                                                           \
+        }
+        if (visc) { if (pipe == 4) PIPE_LAUNCH(true, 4) else PIPE_LAUNCH(true, 3) }
+        else { if (pipe == 4) PIPE_LAUNCH(false, 4) else PIPE_LAUNCH(false, 3) }
+#undef PIPE_LAUNCH
+        return 0;
+    }
     int sel = (visc ? 4 : 0) | (theta ? 2 : 0) | (ale ? 1 : 0);
     static int minb = getenv("CFDB_CALCRHS_MINB") ? atoi(getenv("CFDB_CALCRHS_MINB")) : 3;
 #define PICK(M)                                                                 \
@@ -702,6 +747,13 @@ static int run_calcrhs_elem(cfdb_ctx* c, const k::Gas& g, bool theta, bool ale, 
                  const double*, k::Gas, double*, double*) = nullptr;
     if (minb == 3) { PICK(3) } else if (minb == 4) { PICK(4) } else if (minb == 2) { PICK(2) } else { PICK(1) }
 #undef PICK
+    // experiment: 64-thread CTAs, 7 per SM (<=146 registers, 14 warps/SM)
+    static const bool bs64 = getenv("CFDB_CALCRHS_BS64") != nullptr;
+    if (bs64 && sel == 0) {
+        kern = k::calcrhs_elem<false, false, false, 7, 64>;
+        LAUNCH(K_CALCRHS, kern, grid_for(e1 - e0, 64), 64, ARGS);
+        return 0;
+    }
     LAUNCH(K_CALCRHS, kern, G, B, ARGS);
 #undef ARGS
     return 0;
@@ -711,7 +763,7 @@ static int run_node(cfdb_ctx* c, cudaStream_t st, bool ale, bool update, double 
     if (n1 < 0) n1 = c->npoin;
     if (n1 <= n0) return 0;
     const int B = 256, G = grid_for(n1 - n0, B);
-#define ARGS n0, n1, c->d_esup2.p, c->eslot.p, c->EC.p, c->FC.p, c->U.p, c->M.p, c->GAMM.p, c->W_X.p, c->W_Y.p, \
+#define ARGS n0, n1, c->d_esup2.p, c->eslot.p, (c->ECcur ? c->ECcur : c->EC.p), (c->FCcur ? c->FCcur : c->FC.p), c->U.p, c->M.p, c->GAMM.p, c->W_X.p, c->W_Y.p, \
              c->bcflag.p, bctab(c), rk_fact, c->par.FR, c->U1.p, c->RHS.p, c->RHO.p, c->VEL_X.p, c->VEL_Y.p, c->E.p, \
              c->P.p, c->T.p, c->RMACH.p
     auto kern = k::node_update<false, true>;
@@ -772,6 +824,52 @@ extern "C" int cfdb_rk_stage(cfdb_ctx* c, int32_t irk) {
     return 0;
 }
 
+// RK (subrutinas.f90:645-849) inside the time loop.  When calcRHS does not read anything the nodal chain writes
+// (Euler: mu_ref <= tiny, so T is not read; U, dtl, SHOC, T_SUGN are step constants), node_update(k) on st2
+// overlaps calcrhs_elem(k+1) on st: the memory-bound node kernel hides behind the fp64-bound element kernel.
+// Needs the staging buffers double-buffered.  Same kernels, same order of arithmetic: results are unchanged.
+static int run_rk(cfdb_ctx* c) {
+    const cfdb_params& p = c->par;
+    // measured on B200 (16 M triangles): 9.30 ms/step with the overlap, 9.32 without — the two kernels compete for
+    // the same SM residency — so it is opt-in (CFDB_STAGE_OVERLAP=1)
+    static const bool no_ovl = getenv("CFDB_STAGE_OVERLAP") == nullptr;
+    const bool visc = p.FMU > 2.2250738585072014e-308;
+    if (visc || no_ovl || c->chunk_ev.size() > 1) {
+        for (int irk = 1; irk <= 4; ++irk) TRY(cfdb_rk_stage(c, irk));
+        return 0;
+    }
+    const size_t E = c->nelem;
+    TRY(c->EC2.alloc(12 * E));
+    if (c->ale) TRY(c->FC2.alloc(12 * E));
+    if (c->theta_nonzero) {
+        CK(cudaMemsetAsync(c->UN.p, 0, 4 * (size_t)c->npoin * sizeof(double), c->st));
+        c->theta_nonzero = false;
+    }
+    TRY(run_estab(c, &c->sc->DTMIN));
+    c->u1_is_u = false;
+    k::Gas g{p.FCv, p.FK, p.FMU, p.GAMA, p.T_inf, p.CTE};
+    const double* dtl_arr = p.ITLOCAL != 0 ? c->DTL.p : nullptr;
+    int rc = 0;
+    for (int irk = 1; irk <= 4 && !rc; ++irk) {
+        const int b = (irk - 1) & 1;
+        c->ECcur = b ? c->EC2.p : c->EC.p;
+        c->FCcur = c->ale ? (b ? c->FC2.p : c->FC.p) : nullptr;
+        if (irk >= 3) CK(cudaStreamWaitEvent(c->st, c->ev_node[irk - 3], 0));  // node(irk-2) has consumed this buffer
+        rc = run_calcrhs_elem(c, g, false, c->ale, dtl_arr, &c->sc->DTMIN);
+        if (rc) break;
+        CK(cudaEventRecord(c->ev_elem[irk - 1], c->st));
+        CK(cudaStreamWaitEvent(c->st2, c->ev_elem[irk - 1], 0));
+        rc = run_node(c, c->st2, c->ale, true, 1.0 / (4 + 1 - irk));
+        if (!rc) rc = halo_state(c, c->st2);
+        CK(cudaEventRecord(c->ev_node[irk - 1], c->st2));
+    }
+    c->ECcur = nullptr;
+    c->FCcur = nullptr;
+    if (rc) return rc;
+    CK(cudaStreamWaitEvent(c->st, c->ev_node[3], 0));
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // biCG on device arrays (biconjGrad.f90:8-62); host loop control reads err back once per iteration
 static int bicg_dev(cfdb_ctx* c, const double* A, const int* idx, const int* rowptr, const double* diag, double* x,
@@ -800,9 +898,41 @@ static int bicg_dev(cfdb_ctx* c, const double* A, const int* idx, const int* row
     TRY(dev_dot(c, nred, p, y, 1));
     LAUNCH(K_SCALAR, k::bicg_scalar, 1, 1, c->sc, (int)k::SC_PY_ALFA, 1);
     LAUNCH(K_VEC, k::vecsum, G, B, npoin, (int)k::ALFA_POS, 0.0, c->sc, p, x, x);
+    // while loop (:47-61): fused iterations, enqueued in batches; the loop condition lives on the device
+    static const bool unfused = getenv("CFDB_BICG_UNFUSED") != nullptr;
+    int kk = 0;
+    if (!unfused) {
+        TRY(c->isfix.alloc((size_t)c->npoin > (size_t)npoin ? c->npoin : npoin));
+        CK(cudaMemsetAsync(c->isfix.p, 0, npoin, c->st));
+        if (nfix) LAUNCH(K_FIXROWS, k::mark_fixed, GF, 128, nfix, fixIdx, c->isfix.p);
+        LAUNCH(K_SCALAR, k::bicg_fused_scalar, 1, 1, c->sc, (int)k::SCF_START, 0);
+        const long nch = ((long)npoin + 4095) / 4096, mred = ((long)nred + 4095) / 4096;
+        const int GB = (int)std::min<long>(nch, 148 * 8);
+        double* pa = p;         // current p
+        double* pb = c->bp2.p;  // next p
+        int batch = 1;  // 1, 2, 4, 8, 16, 16, ...: most mesh solves need a handful of iterations (absolute tolerance)
+        for (int done = 0; done < 1000; batch = std::min(2 * batch, 16)) {
+            for (int it = 0; it < batch; ++it, ++done) {
+                LAUNCH(K_VEC, k::bicg_k1, GB, 256, npoin, nred, c->sc, y, diag, pa, x, r, z, c->redA.p);
+                TRY(reduce_levels(c, 1, mred, 0));
+                LAUNCH(K_SCALAR, k::bicg_fused_scalar, 1, 1, c->sc, (int)k::SCF_BETA, 0);
+                TRY(halo_vec(c, z, 1));
+                LAUNCH(K_SPMV, k::bicg_k2, GB, 256, npoin, nred, c->sc, A, idx, rowptr, c->isfix.p, pa, z, pb, y, c->redA.p);
+                TRY(reduce_levels(c, 1, mred, 1));
+                LAUNCH(K_SCALAR, k::bicg_fused_scalar, 1, 1, c->sc, (int)k::SCF_ALFA, 1);
+                std::swap(pa, pb);
+            }
+            TRY(read_scal(c));
+            if (!c->h_sc->bicg_state) break;
+        }
+        // the last x = alfa*p + x may still be pending: one more k1 applies it (no-op otherwise)
+        LAUNCH(K_VEC, k::bicg_k1, GB, 256, npoin, nred, c->sc, y, diag, pa, x, r, z, c->redA.p);
+        LAUNCH(K_SCALAR, k::bicg_fused_scalar, 1, 1, c->sc, (int)k::SCF_FLUSHED, 0);
+        TRY(read_scal(c));
+        kk = c->h_sc->bicg_k;
+    } else {
     TRY(read_scal(c));
     double err_old = c->h_sc->err_old;
-    int kk = 0;
     while (std::fabs(err_old) > tol && kk < 1000) {
         kk++;
         LAUNCH(K_VEC, k::vecsum, G, B, npoin, (int)k::ALFA_NEG, 0.0, c->sc, y, r, r);
@@ -818,6 +948,7 @@ static int bicg_dev(cfdb_ctx* c, const double* A, const int* idx, const int* row
         LAUNCH(K_VEC, k::vecsum, G, B, npoin, (int)k::ALFA_POS, 0.0, c->sc, p, x, x);
         TRY(read_scal(c));
         err_old = c->h_sc->err_old;
+    }
     }
     *iters = kk;
     TRY(halo_vec(c, x, 1));  // ghosts of the solution (the caller moves ghost nodes with it)
@@ -903,7 +1034,7 @@ static int step_once(cfdb_ctx* c) {
         LAUNCH(K_DTL, k::dtl_blend, grid_for(E, 256), 256, E, c->DT.p, c->DTL.p, c->sc, 1);
     }
     // U1 = U (:168-172) is dead: every RK stage overwrites U1 from U (subrutinas.f90:697)
-    for (int irk = 1; irk <= 4; ++irk) TRY(cfdb_rk_stage(c, irk));
+    TRY(run_rk(c));
     // RHS history copies for BANDERA 2..4 (subrutinas.f90:830-848); BANDERA lives on the device, the kernel
     // exits at once for any other value
     LAUNCH(K_FILL, k::rhs_history, grid_for(4 * (long)P, 256), 256, 4 * (long)P, c->sc, c->RHS.p, c->RHS1.p, c->RHS2.p, c->RHS3.p);
@@ -1266,7 +1397,7 @@ extern "C" int cfdb_estab(cfdb_ctx* c, const double* U, const double* T, const d
     TRY(up_plain(c, c->W_Y.p, w_y, P));
     TRY(up_plain(c, c->GAMM.p, GAMM, P));
     LAUNCH(K_SCALAR, k::set_double, 1, 1, &c->sc->red[15], DTMIN);
-    LAUNCH(K_ESTAB, k::estab, grid_for(nelem, 256), 256, nelem, c->inp.p, c->U.p, c->T.p, c->VEL_X.p, c->VEL_Y.p, c->W_X.p,
+    LAUNCH(K_ESTAB, k::estab<3>, grid_for(nelem, 256), 256, nelem, c->inp.p, c->U.p, c->T.p, c->VEL_X.p, c->VEL_Y.p, c->W_X.p,
            c->W_Y.p, c->GAMM.p, c->dNx.p, c->dNy.p, FR, &c->sc->red[15], RHOINF, TINF, c->SHOC.p, c->TS1.p, c->TS2.p,
            c->TS3.p);
     TRY(down_plain(c, c->SHOC.p, shoc, E));

@@ -24,7 +24,7 @@ struct Scal {
     double err_new, err_old, py, alfa, beta, rr;
     double ER[4], ERR[4];
     double FX[10], FY[10], RM[10];
-    int ITER, BANDERA, bicg_k, bicg_state;
+    int ITER, BANDERA, bicg_k, bicg_state, bicg_xpend, pad_;
 };
 
 struct Gas {
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(256) masas(int npoin, const int* __restrict__ 
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= npoin) return;
     double m = 0.0;
-    for (int k = esup2[n]; k < esup2[n + 1]; ++k) m = m + area[eslot[k] / 3] / 3.0;
+    for (int k = esup2[n]; k < esup2[n + 1]; ++k) m = m + ex::div3(area[eslot[k] / 3]);
     M[n] = m;
 }
 
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256) deltat(int nelem, const int* __restrict__
     double dte = 1.e20;
     if (e < nelem) {
         int n[3] = {inp[e], inp[nelem + e], inp[2 * (size_t)nelem + e]};
-        double T_iel = (T[n[0]] + T[n[1]] + T[n[2]]) / 3.0;
+        double T_iel = ex::div3(T[n[0]] + T[n[1]] + T[n[2]]);
         double VUMAX = 0.0, VVMAX = 0.0;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256) deltat(int nelem, const int* __restrict__
         double fmu = 0.017 * ex::pow15(T_iel / T_inf) * (T_inf + smu) / (T_iel + smu);
         double ET = fmu;
         double Pe = (VEL * HH) / (2.0 * ET);
-        double ALPHA = ex::fmin2(Pe / 3.0, 1.0);
+        double ALPHA = ex::fmin2(ex::div3(Pe), 1.0);
         double DELTATU = 1.0 / (4.0 * ET / (HH * HH) + ALPHA * VEL / HH);
         double DELTATC = 1.0 / (4.0 * ET / (HH * HH));
         double DTELEM = FSAFE / (1.0 / DELTATC + 1.0 / DELTATU);
@@ -234,7 +234,8 @@ __global__ void fill_const(long n, double* __restrict__ a, double v) {
 
 // ---------------------------------------------------------------------------------------------
 // ESTAB (subrutinas.f90:349-443) : one thread per element
-__global__ void __launch_bounds__(256) estab(int nelem, const int* __restrict__ inp, const double* __restrict__ U,
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) estab(int nelem, const int* __restrict__ inp, const double* __restrict__ U,
                                               const double* __restrict__ T, const double* __restrict__ VXa,
                                               const double* __restrict__ VYa, const double* __restrict__ WXa,
                                               const double* __restrict__ WYa, const double* __restrict__ GAMM,
@@ -248,14 +249,14 @@ __global__ void __launch_bounds__(256) estab(int nelem, const int* __restrict__ 
     int N1 = inp[e], N2 = inp[nelem + e], N3 = inp[2 * (size_t)nelem + e];
     double nx[3] = {dNx[e], dNx[nelem + e], dNx[2 * (size_t)nelem + e]};
     double ny[3] = {dNy[e], dNy[nelem + e], dNy[2 * (size_t)nelem + e]};
-    double GM = (GAMM[N1] + GAMM[N2] + GAMM[N3]) / 3.0;
+    double GM = ex::div3(GAMM[N1] + GAMM[N2] + GAMM[N3]);
     double TAU = 0.0, H_RGNE = 0.0, H_RGN = 0.0, H_JGN = 0.0;
     double r1 = U[4 * (size_t)N1], r2 = U[4 * (size_t)N2], r3 = U[4 * (size_t)N3];
-    double RHO_ELEM = (r1 + r2 + r3) / 3.0;
-    double VX = (VXa[N1] + VXa[N2] + VXa[N3]) / 3.0;
-    double VY = (VYa[N1] + VYa[N2] + VYa[N3]) / 3.0;
-    double WX = (WXa[N1] + WXa[N2] + WXa[N3]) / 3.0;
-    double WY = (WYa[N1] + WYa[N2] + WYa[N3]) / 3.0;
+    double RHO_ELEM = ex::div3(r1 + r2 + r3);
+    double VX = ex::div3(VXa[N1] + VXa[N2] + VXa[N3]);
+    double VY = ex::div3(VYa[N1] + VYa[N2] + VYa[N3]);
+    double WX = ex::div3(WXa[N1] + WXa[N2] + WXa[N3]);
+    double WY = ex::div3(WYa[N1] + WYa[N2] + WYa[N3]);
     VX = VX - WX; VY = VY - WY;
     double VEL2 = sqrt(VX * VX + VY * VY);
     double DRX = r1 * nx[0] + r2 * nx[1] + r3 * nx[2];
@@ -271,7 +272,7 @@ __global__ void __launch_bounds__(256) estab(int nelem, const int* __restrict__ 
     double RTX = DTX / DT2, RTY = DTY / DT2;
     double RJX = DRX / DR2, RJY = DRY / DR2;
     double RUX = DUX / DU2, RUY = DUY / DU2;
-    double TEMP = (t1 + t2 + t3) / 3.0;
+    double TEMP = ex::div3(t1 + t2 + t3);
     double C = sqrt(GM * FR * TEMP);
     double smu = 110.0;
     double fmu = 0.017 * ex::pow15(TEMP / TINF) * (TINF + smu) / (TEMP + smu);
@@ -315,53 +316,28 @@ __global__ void __launch_bounds__(256) estab(int nelem, const int* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
-// calcRHS (calcRHS.f90:36-141) [+ FUENTE, subrutinas.f90:1060-1078] : one thread per element.
-// Shape-function gradients and the 12+12 contributions stay in registers; the results go to the
-// staging buffers EC/FC, not to RHS: the node kernel sums them in the reference's order.
-template <bool VISC, bool THETA, bool ALE, int MINB>
-__global__ void __launch_bounds__(128, MINB) calcrhs_elem(int e0, int e1, int nelem, const int* __restrict__ inp, const double* __restrict__ U,
-                                                     const double* __restrict__ TH, const double* __restrict__ T,
-                                                     const double* __restrict__ WXa, const double* __restrict__ WYa,
-                                                     const double* __restrict__ dNx, const double* __restrict__ dNy,
-                                                     const double* __restrict__ area, const double* __restrict__ shoc,
-                                                     const double* __restrict__ dtl_arr, const double* __restrict__ dtl_sc,
-                                                     const double* __restrict__ ts1, const double* __restrict__ ts2,
-                                                     const double* __restrict__ ts3, Gas g, double* __restrict__ EC,
-                                                     double* __restrict__ FC) {
-    int e = e0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= e1) return;
+// calcRHS (calcRHS.f90:36-141): the arithmetic of one element, shared by the direct and the cp.async-pipelined
+// kernels.  Inputs are the gathered nodal values and the element's stream data; rt(3 nodes, 4 eqns) is the
+// contribution before the scatter.  Evaluation order is the source's (see exact.cuh).
+template <bool VISC, bool THETA>
+__device__ __forceinline__ void calcrhs_body(const Gas& g, const double (&Un)[3][4], const double (&Th)[3][4],
+                                             const double (&Tn)[3], const double (&Nx)[3], const double (&Ny)[3],
+                                             const double (&tau)[3], double shoc_e, double (&Ux)[4], double (&Uy)[4],
+                                             double (&rt)[3][4]) {
     const double gamma0 = g.gamma0;
-    int ip[3] = {inp[e], inp[nelem + e], inp[2 * (size_t)nelem + e]};
-    double Nx[3] = {dNx[e], dNx[nelem + e], dNx[2 * (size_t)nelem + e]};
-    double Ny[3] = {dNy[e], dNy[nelem + e], dNy[2 * (size_t)nelem + e]};
-    double Un[3][4];
-    ld4(U + 4 * (size_t)ip[0], Un[0]);
-    ld4(U + 4 * (size_t)ip[1], Un[1]);
-    ld4(U + 4 * (size_t)ip[2], Un[2]);
-    double Ux[4], Uy[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         Ux[i] = Un[0][i] * Nx[0] + Un[1][i] * Nx[1] + Un[2][i] * Nx[2];
         Uy[i] = Un[0][i] * Ny[0] + Un[1][i] * Ny[1] + Un[2][i] * Ny[2];
     }
-    const double tau[3] = {ts1[e], ts2[e], ts3[e]};
-    const double nu = shoc[e] * g.cte;
-    const double dtl = dtl_arr ? dtl_arr[e] : *dtl_sc;
-    const double ar = area[e];
+    const double nu = shoc_e * g.cte;
     double mu = 0.0, lambda = 0.0;
     if (VISC) {
-        double T_avg = ex::div3(T[ip[0]] + T[ip[1]] + T[ip[2]]);
+        double T_avg = ex::div3(Tn[0] + Tn[1] + Tn[2]);
         double p15 = ex::pow15(T_avg / g.T_inf);
         mu = g.mu_ref * p15 * (g.T_inf + 110) / (T_avg + 110);
         lambda = g.lambda_ref * p15 * (g.T_inf + 194) / (T_avg + 194);
     }
-    double Th[3][4];
-    if (THETA) {
-        ld4(TH + 4 * (size_t)ip[0], Th[0]);
-        ld4(TH + 4 * (size_t)ip[1], Th[1]);
-        ld4(TH + 4 * (size_t)ip[2], Th[2]);
-    }
-    double rt[3][4];
 #pragma unroll
     for (int n = 0; n < 3; ++n)
 #pragma unroll
@@ -447,6 +423,41 @@ __global__ void __launch_bounds__(128, MINB) calcrhs_elem(int e0, int e1, int ne
                 for (int i = 1; i < 4; ++i) rt[n][i] = rt[n][i] + (Nx[n] * K1[i] + Ny[n] * K2[i]);
         }
     }
+}
+
+// calcRHS [+ FUENTE, subrutinas.f90:1060-1078] : one thread per element, direct loads.
+// Shape-function gradients and the 12+12 contributions stay in registers; the results go to the
+// staging buffers EC/FC, not to RHS: the node kernel sums them in the reference's order.
+template <bool VISC, bool THETA, bool ALE, int MINB, int BS = 128>
+__global__ void __launch_bounds__(BS, MINB) calcrhs_elem(int e0, int e1, int nelem, const int* __restrict__ inp, const double* __restrict__ U,
+                                                     const double* __restrict__ TH, const double* __restrict__ T,
+                                                     const double* __restrict__ WXa, const double* __restrict__ WYa,
+                                                     const double* __restrict__ dNx, const double* __restrict__ dNy,
+                                                     const double* __restrict__ area, const double* __restrict__ shoc,
+                                                     const double* __restrict__ dtl_arr, const double* __restrict__ dtl_sc,
+                                                     const double* __restrict__ ts1, const double* __restrict__ ts2,
+                                                     const double* __restrict__ ts3, Gas g, double* __restrict__ EC,
+                                                     double* __restrict__ FC) {
+    int e = e0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= e1) return;
+    int ip[3] = {inp[e], inp[nelem + e], inp[2 * (size_t)nelem + e]};
+    double Nx[3] = {dNx[e], dNx[nelem + e], dNx[2 * (size_t)nelem + e]};
+    double Ny[3] = {dNy[e], dNy[nelem + e], dNy[2 * (size_t)nelem + e]};
+    double Un[3][4], Th[3][4], Tn[3] = {0.0, 0.0, 0.0};
+    ld4(U + 4 * (size_t)ip[0], Un[0]);
+    ld4(U + 4 * (size_t)ip[1], Un[1]);
+    ld4(U + 4 * (size_t)ip[2], Un[2]);
+    if (VISC) { Tn[0] = T[ip[0]]; Tn[1] = T[ip[1]]; Tn[2] = T[ip[2]]; }
+    if (THETA) {
+        ld4(TH + 4 * (size_t)ip[0], Th[0]);
+        ld4(TH + 4 * (size_t)ip[1], Th[1]);
+        ld4(TH + 4 * (size_t)ip[2], Th[2]);
+    }
+    const double tau[3] = {ts1[e], ts2[e], ts3[e]};
+    const double dtl = dtl_arr ? dtl_arr[e] : *dtl_sc;
+    const double ar = area[e];
+    double Ux[4], Uy[4], rt[3][4];
+    calcrhs_body<VISC, THETA>(g, Un, Th, Tn, Nx, Ny, tau, shoc[e], Ux, Uy, rt);
     double* out = EC + 12 * (size_t)e;
 #pragma unroll
     for (int n = 0; n < 3; ++n) {
@@ -483,6 +494,112 @@ __global__ void __launch_bounds__(128, MINB) calcrhs_elem(int e0, int e1, int ne
             st4(fo + 4 * n, v);
         }
     }
+}
+
+// calcRHS, persistent + software-pipelined variant (fixed meshes, theta = 0).  The grid is a multiple of the SM
+// count; every CTA walks tiles of 128 elements.  While a thread computes element e of tile t, the inputs of its
+// element of tile t+1 are already in flight to shared memory (cp.async: the element stream coalesced, the nodal
+// gathers by index) and the connectivity of tile t+2 is in flight to registers, so the fp64 pipe is not left idle
+// while a warp waits for HBM at the top of the kernel.  A thread only ever reads the shared-memory slots it
+// filled itself, so there is no block-level barrier.  Arithmetic: calcrhs_body, unchanged.
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <bool VISC>
+struct PipeLayout {
+    // per stage, per thread: 6 x 16 B (U of 3 nodes) + 12 (Nx,Ny,area,shoc,ts1-3,dtl) + 3 (T) doubles
+    static constexpr int kD2 = 6;
+    static constexpr int kD1 = 12 + (VISC ? 3 : 0);
+    static constexpr int kStageBytes = 128 * (kD2 * 16 + kD1 * 8);
+};
+
+template <bool VISC, int MINB>
+__global__ void __launch_bounds__(128, MINB) calcrhs_pipe(int nelem, const int* __restrict__ inp, const double* __restrict__ U,
+                                                           const double* __restrict__ T, const double* __restrict__ dNx,
+                                                           const double* __restrict__ dNy, const double* __restrict__ area,
+                                                           const double* __restrict__ shoc, const double* __restrict__ dtl_arr,
+                                                           const double* __restrict__ dtl_sc, const double* __restrict__ ts1,
+                                                           const double* __restrict__ ts2, const double* __restrict__ ts3, Gas g,
+                                                           double* __restrict__ EC) {
+    using L = PipeLayout<VISC>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int ntiles = (nelem + 127) / 128;
+    const size_t NE = (size_t)nelem;
+    auto d2 = [&](int stage, int slot) { return reinterpret_cast<double2*>(smem_raw + (size_t)stage * L::kStageBytes) + slot * 128 + tid; };
+    auto d1 = [&](int stage, int slot) {
+        return reinterpret_cast<double*>(smem_raw + (size_t)stage * L::kStageBytes + 128 * L::kD2 * 16) + slot * 128 + tid;
+    };
+    auto load_idx = [&](int tile, int (&ip)[3]) {
+        int e = tile * 128 + tid;
+        if (tile < ntiles && e < nelem) { ip[0] = inp[e]; ip[1] = inp[NE + e]; ip[2] = inp[2 * NE + e]; }
+    };
+    auto issue = [&](int tile, int stage, const int (&ip)[3]) {
+        int e = tile * 128 + tid;
+        if (tile < ntiles && e < nelem) {
+#pragma unroll
+            for (int n = 0; n < 3; ++n) {
+                const double* u = U + 4 * (size_t)ip[n];
+                cp_async16(d2(stage, 2 * n), u);
+                cp_async16(d2(stage, 2 * n + 1), u + 2);
+                cp_async8(d1(stage, n), dNx + n * NE + e);
+                cp_async8(d1(stage, 3 + n), dNy + n * NE + e);
+                if (VISC) cp_async8(d1(stage, 12 + n), T + ip[n]);
+            }
+            cp_async8(d1(stage, 6), area + e);
+            cp_async8(d1(stage, 7), shoc + e);
+            cp_async8(d1(stage, 8), ts1 + e);
+            cp_async8(d1(stage, 9), ts2 + e);
+            cp_async8(d1(stage, 10), ts3 + e);
+            if (dtl_arr) cp_async8(d1(stage, 11), dtl_arr + e);
+        }
+        cp_async_commit();
+    };
+    int t = blockIdx.x, tn = t + gridDim.x, stage = 0;
+    int ipC[3] = {0, 0, 0}, ipN[3] = {0, 0, 0};
+    load_idx(t, ipC);
+    issue(t, 0, ipC);
+    load_idx(tn, ipN);
+    const double dtl_uniform = dtl_arr ? 0.0 : *dtl_sc;
+    for (; t < ntiles; t = tn, tn += gridDim.x, stage ^= 1) {
+        issue(tn, stage ^ 1, ipN);
+        load_idx(tn + gridDim.x, ipN);  // consumed by the issue of the next iteration
+        cp_async_wait<1>();
+        int e = t * 128 + tid;
+        if (e >= nelem) continue;
+        double Un[3][4], Th[3][4], Tn[3] = {0.0, 0.0, 0.0}, Nx[3], Ny[3], tau[3];
+#pragma unroll
+        for (int n = 0; n < 3; ++n) {
+            double2 a = *d2(stage, 2 * n), b = *d2(stage, 2 * n + 1);
+            Un[n][0] = a.x; Un[n][1] = a.y; Un[n][2] = b.x; Un[n][3] = b.y;
+            Nx[n] = *d1(stage, n);
+            Ny[n] = *d1(stage, 3 + n);
+            tau[n] = *d1(stage, 8 + n);
+            if (VISC) Tn[n] = *d1(stage, 12 + n);
+        }
+        const double ar = *d1(stage, 6), sh_e = *d1(stage, 7);
+        const double dtl = dtl_arr ? *d1(stage, 11) : dtl_uniform;
+        double Ux[4], Uy[4], rt[3][4];
+        calcrhs_body<VISC, false>(g, Un, Th, Tn, Nx, Ny, tau, sh_e, Ux, Uy, rt);
+        double* out = EC + 12 * (size_t)e;
+#pragma unroll
+        for (int n = 0; n < 3; ++n) {
+            double v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = ex::div3(rt[n][i] * ar * dtl);
+            st4(out + 4 * n, v);
+        }
+    }
+    cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -701,6 +818,99 @@ __global__ void bicg_scalar(Scal* sc, int what, int slot) {
     else if (what == SC_BETA) { sc->err_new = v; sc->beta = v / sc->err_old; }
 }
 
+// ---- fused biCG iteration (biconjGrad.f90:47-61), two vector kernels per iteration -------------------------
+// bicg_state: 1 while the loop condition `abs(err_old) > tol .and. k < 1000` holds; bicg_xpend: the `x = alfa*p + x`
+// of the previous iteration (:59) is applied at the start of the next kernel.  Kernels launched after the loop
+// has ended on the device are no-ops, so the host can enqueue iterations in batches without reading back.
+// k1:  x += alfa*p (deferred :59) ; r = -alfa*y + r (:49) ; z = r/diag (:50) ; chunk sums of r.z (:51)
+__global__ void __launch_bounds__(256) bicg_k1(int n, int nred, const Scal* sc, const double* __restrict__ y,
+                                                const double* __restrict__ diag, const double* __restrict__ p,
+                                                double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
+                                                double* __restrict__ partial) {
+    __shared__ double sm[256];
+    const int active = sc->bicg_state, xp = sc->bicg_xpend;
+    if (!active && !xp) return;
+    const double alfa = sc->alfa;
+    long nchunk = ((long)n + 4095) / 4096, mred = ((long)nred + 4095) / 4096;
+    for (long c = blockIdx.x; c < nchunk; c += gridDim.x) {
+        long lo = c * 4096, hi = lo + 4096 < n ? lo + 4096 : n;
+        double acc = 0.0;
+        for (long i = lo + threadIdx.x; i < hi; i += 256) {
+            if (xp) x[i] = alfa * p[i] + x[i];
+            if (active) {
+                double ri = -alfa * y[i] + r[i];
+                double zi = ri / diag[i];
+                r[i] = ri;
+                z[i] = zi;
+                if (i < nred) acc = acc + ri * zi;
+            }
+        }
+        if (active && c < mred) {
+            double t = tree256(acc, sm);
+            if (threadIdx.x == 0) partial[c] = t;
+        }
+    }
+}
+// k2:  p = beta*p + z (:53, recomputed at the neighbours: same expression, same bits) ; y = A p (:54) ;
+//      y(fix) = 1e30*p(fix) (:56) ; chunk sums of p.y (:57).  One thread per row keeps the row order of SpMV.
+__global__ void __launch_bounds__(256) bicg_k2(int n, int nred, const Scal* sc, const double* __restrict__ A,
+                                                const int* __restrict__ idx, const int* __restrict__ rowptr,
+                                                const unsigned char* __restrict__ isfix, const double* __restrict__ p_old,
+                                                const double* __restrict__ z, double* __restrict__ p_new,
+                                                double* __restrict__ y, double* __restrict__ partial) {
+    __shared__ double sm[256];
+    if (!sc->bicg_state) return;
+    const double beta = sc->beta;
+    long nchunk = ((long)n + 4095) / 4096, mred = ((long)nred + 4095) / 4096;
+    for (long c = blockIdx.x; c < nchunk; c += gridDim.x) {
+        long lo = c * 4096, hi = lo + 4096 < n ? lo + 4096 : n;
+        double acc = 0.0;
+        for (long i = lo + threadIdx.x; i < hi; i += 256) {
+            double pn = beta * p_old[i] + z[i];
+            double dot = 0.0;
+            for (int j = rowptr[i]; j < rowptr[i + 1]; ++j) {
+                int col = idx[j];
+                dot = dot + A[j] * (beta * p_old[col] + z[col]);
+            }
+            if (isfix[i]) dot = 1.e30 * pn;
+            p_new[i] = pn;
+            y[i] = dot;
+            if (i < nred) acc = acc + pn * dot;
+        }
+        if (c < mred) {
+            double t = tree256(acc, sm);
+            if (threadIdx.x == 0) partial[c] = t;
+        }
+    }
+}
+enum { SCF_BETA = 0, SCF_ALFA = 1, SCF_START = 2, SCF_FLUSHED = 3 };
+__global__ void bicg_fused_scalar(Scal* sc, int what, int slot) {
+    if (what == SCF_START) {  // after the prologue (:37-45): enter the while loop or not
+        sc->bicg_k = 0;
+        sc->bicg_xpend = 0;
+        sc->bicg_state = fabs(sc->err_old) > 1.e-10 ? 1 : 0;
+        return;
+    }
+    if (what == SCF_FLUSHED) { sc->bicg_xpend = 0; return; }
+    if (!sc->bicg_state) { if (what == SCF_ALFA) sc->bicg_xpend = 0; return; }
+    double v = sc->red[slot];
+    if (what == SCF_BETA) {
+        sc->bicg_k += 1;                      // :48
+        sc->err_new = v;                      // :51
+        sc->beta = v / sc->err_old;           // :52
+    } else {
+        sc->py = v;                           // :57
+        sc->alfa = sc->err_new / v;           // :58
+        sc->err_old = sc->err_new;            // :60
+        sc->bicg_xpend = 1;                   // :59, applied by the next bicg_k1
+        sc->bicg_state = (fabs(sc->err_old) > 1.e-10 && sc->bicg_k < 1000) ? 1 : 0;  // :47
+    }
+}
+__global__ void mark_fixed(int m, const int* __restrict__ idx, unsigned char* __restrict__ flag) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) flag[idx[i]] = 1;
+}
+
 // laplace values (mLaplace.f90:34-57): one thread per node, elements in esup order, row kept in
 // registers/local memory; pos[k][j] = position inside the row of local node j of esup entry k.
 template <int MAXROW>
@@ -821,8 +1031,8 @@ __global__ void __launch_bounds__(256) gcl(int npoin, int nelem, const int* __re
         double o1 = Wx_old[nn[0]], o2 = Wx_old[nn[1]], o3 = Wx_old[nn[2]];
         double divW = nx[0] * w1 + nx[1] * w2 + nx[2] * w3 + ny[0] * w1 + ny[1] * w2 + ny[2] * w3;
         double divW_old = nx[0] * o1 + nx[1] * o2 + nx[2] * o3 + ny[0] * o1 + ny[1] * o2 + ny[2] * o3;
-        tot1 = tot1 + divW * area[e] / 3.0;
-        tot2 = tot2 + divW_old * area_old[e] / 3.0;
+        tot1 = tot1 + ex::div3(divW * area[e]);
+        tot2 = tot2 + ex::div3(divW_old * area_old[e]);
     }
     M[n] = M[n] + dt * (tot1 + tot2) / 2.0;
 }

@@ -263,3 +263,30 @@ def test_free_stream_is_preserved(cases):
     U = g.get("U").reshape(-1, 4)
     scale = np.array([U0[:, 0].max(), U0[:, 1].max(), U0[:, 1].max(), U0[:, 3].max()])
     assert np.max(np.abs(U - U0) / scale) < 1e-10
+
+
+def test_config1_channel_1000_steps():
+    """BASELINE config 1: ~10k-node channel, fixed mesh, 1000 explicit SUPG steps.  north_star asks for <=1e-11 on the
+    per-step residual and <=1e-8 on conserved variables after 1000 steps; the build delivers bit-identity."""
+    from cfd_b200 import deck, meshgen
+    from cfd_b200.solver import NSComp2D
+    from oracle.orclib import Oracle
+
+    lc = deck.load(meshgen.channel(nx=201, ny=51, MAXITER=1000, IPRINT=250))
+    g, o = NSComp2D(lc), Oracle(lc)
+    o.set_scalar("norms_every_step", 0)
+    for k, v in meshgen.density_bump(lc).items():
+        g.set(k, v)
+        o.set(k, v)
+    for _ in range(4):
+        g.step(250)
+        o.step(250)
+        er_g, err_g = g.step_norms()          # the .cnv columns of this print step (ns2DComp.ALE.f90:191-199)
+        conv = np.sqrt(er_g / err_g)
+        assert np.all(np.isfinite(conv)) and np.all(conv < 1.0)
+        assert_bit_equal(g.get("U"), o.get("U"), f"U@{int(o.scalar('ITER'))}")
+    assert g.scalar("ITER") == 1000 and g.scalar("TIME") == o.scalar("TIME")
+    for n in ("U", "T", "P", "RMACH", "RHS", "SHOC", "T_SUGN2"):
+        assert_bit_equal(g.get(n), o.get(n), n)
+    U, Uo = g.get("U").reshape(-1, 4), o.get("U").reshape(-1, 4)
+    assert np.max(np.abs(U - Uo) / np.abs(Uo).max(0)) <= 1e-8   # the stated tolerance, met with margin (exactly 0)
