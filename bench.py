@@ -113,14 +113,14 @@ def cpu_oracle_throughput(n_lattice, steps, warmup=1):
 
 
 def run_reference(args, rank, out):
+    """Reference arm: the CPU implementation of the path (oracle OpenMP build = C++ restatement of chanshing/cfd with
+    the reference's own pragmas/atomics; the Fortran original cannot be built here) on all host cores, bounded sample."""
     if rank != 0:
         return
-    n = args.ref_n
-    t_all = []
-    val, cores, nelem, _ = cpu_oracle_throughput(n, 1, warmup=args.warmup)  # warm-up pass (also pages in)
     from cfd_b200 import deck, meshgen
     from oracle.orclib import Oracle
 
+    n = args.ref_n
     lc = deck.load(meshgen.square(n=n, IPRINT=10**9, MAXITER=10**9))
     o = Oracle(lc, omp=True)
     o.set_scalar("norms_every_step", 0)
@@ -131,12 +131,13 @@ def run_reference(args, rank, out):
     o.step(args.steps)
     dt = time.perf_counter() - t0
     val = lc.nelem * args.steps / dt
-    sample = f"{lc.nelem}-triangle square mesh (lattice {n}), {args.steps} steps, oracle OpenMP build"
+    cores = o.L.orc_omp_threads()
+    sample = f"{lc.nelem}-triangle square mesh (lattice {n}), {args.steps} steps in {dt:.1f} s, oracle OpenMP build, {cores} threads"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"square mesh, bounded CPU sample of the GPU arm's workload: {sample}"},
+        "config": {"workload": f"bounded CPU sample of the GPU arm's workload (same generator, same flow): {sample}"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "C++ restatement of chanshing/cfd (oracle/), not the Fortran binary: no Fortran compiler in the image",
@@ -153,8 +154,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--n", type=int, default=2829, help="lattice nodes per side per GPU (2829 -> 16.0 M triangles)")
-    ap.add_argument("--ref-n", type=int, default=501, help="lattice of the bounded CPU sample (501 -> 0.5 M triangles)")
-    ap.add_argument("--cpu-steps", type=int, default=5)
+    ap.add_argument("--ref-n", type=int, default=1415, help="lattice of the bounded CPU sample (1415 -> 4.0 M triangles)")
+    ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -241,9 +242,14 @@ def main():
     dom_bytes = BYTES_STAGE_CALCRHS if dom == "calcrhs_elem" else BYTES_STAGE_UPDATE
     achieved = dom_bytes * E / (prof[dom]["avg_ms"] * 1e-3) / 1e9
     stage_achieved = (BYTES_STAGE_CALCRHS + BYTES_STAGE_UPDATE) * E / (stage_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")   # dram__bytes_read+write per launch from the committed ncu capture
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get(dom)
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": None, "peak_source": peak_src,
+        "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes_per_element": dom_bytes,
         "stage": {"kernels": "calcrhs_elem+node_update", "bytes_per_element_stage": BYTES_STAGE_CALCRHS + BYTES_STAGE_UPDATE,
                   "ms": stage_ms, "achieved": stage_achieved, "frac": stage_achieved / peak,

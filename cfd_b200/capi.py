@@ -19,7 +19,7 @@ SYMBOLS = [
     "cfdb_rk_stage", "cfdb_geometry", "cfdb_fluid_structure", "cfdb_residual_norms", "cfdb_step_norms", "cfdb_get", "cfdb_set",
     "cfdb_field_size", "cfdb_get_scalar", "cfdb_set_scalar", "cfdb_stream", "cfdb_profile_enable", "cfdb_profile_get",
     "cfdb_launch_count", "cfdb_nccl_unique_id", "cfdb_comm_init", "cfdb_set_halo", "cfdb_halo_exchange", "cfdb_calcrhs", "cfdb_fuente", "cfdb_deltat", "cfdb_estab", "cfdb_deriv", "cfdb_masas",
-    "cfdb_normales", "cfdb_laplace", "cfdb_bicg", "cfdb_spmv", "cfdb_vecdot", "cfdb_gcl_main", "cfdb_get_esup",
+    "cfdb_normales", "cfdb_laplace", "cfdb_bicg", "cfdb_spmv", "cfdb_vecdot", "cfdb_gcl_main", "cfdb_selftest", "cfdb_get_esup",
     "cfdb_get_psup",
 ]
 
@@ -97,6 +97,7 @@ def lib():
     L.cfdb_spmv.argtypes = [vp, _dp, _ip, _ip, _dp, _dp, i32, i32]
     L.cfdb_vecdot.argtypes = [vp, i32, _dp, _dp, C.POINTER(d)]
     L.cfdb_gcl_main.argtypes = [vp] + [_dp] * 9 + [_ip, i32, i32, d]
+    L.cfdb_selftest.argtypes = [vp, i32, i64, C.c_uint64, C.POINTER(i64)]
     L.cfdb_get_esup.argtypes = [_ip, i32, i32, _ip, _ip]
     L.cfdb_get_psup.argtypes = [_ip, i32, i32, _ip, i32, _ip, C.POINTER(i32)]
     _lib = L

@@ -1006,6 +1006,20 @@ extern "C" int cfdb_residual_norms(cfdb_ctx* c, double er[4], double err[4]) {
     return 0;
 }
 
+extern "C" int cfdb_selftest(cfdb_ctx* c, int32_t which, int64_t n, uint64_t seed, int64_t* mismatches) {
+    CK(cudaSetDevice(c->device));
+    unsigned long long* d = nullptr;
+    CK(cudaMalloc(&d, sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(d, 0, sizeof(unsigned long long), c->st));
+    LAUNCH(K_FILL, k::selftest, 148 * 8, 256, (int)which, (long)n, (unsigned long long)seed, d);
+    unsigned long long h = 0;
+    CK(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    cudaFree(d);
+    *mismatches = (int64_t)h;
+    return 0;
+}
+
 extern "C" int cfdb_step_norms(cfdb_ctx* c, double er[4], double err[4]) {
     CK(cudaSetDevice(c->device));
     TRY(read_scal(c));

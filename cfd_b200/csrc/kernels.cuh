@@ -360,6 +360,8 @@ __device__ __forceinline__ void calcrhs_body(const Gas& g, const double (&Un)[3]
             th_k[i] = THETA ? (Nk[0] * Th[0][i] + Nk[1] * Th[1][i] + Nk[2] * Th[2][i]) : 0.0;
         }
         double rho = U_k[0];
+        // (ex::DivBy — one reciprocal refinement shared by the three quotients — is exact but measured slower here:
+        // 1.275 ms against 1.186 ms per launch; its fallback branches cost more than the 13 fp64 instructions saved)
         double v1 = ex::divz(U_k[1], rho), v2 = ex::divz(U_k[2], rho), en = U_k[3] / rho;
         double V_sq = v1 * v1 + v2 * v2;
         double A[4];
@@ -1070,6 +1072,36 @@ __global__ void halo_unpack(int m, int w, const int* __restrict__ idx, const dou
     if (i >= m * w) return;
     int k = i / w, q = i - k * w;
     v[(size_t)idx[k] * w + q] = buf[i];
+}
+
+// device self-test of the exactness helpers against the plain IEEE operations (cfdb_selftest)
+__global__ void selftest(int which, long n, unsigned long long seed, unsigned long long* mismatches) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    unsigned long long bad = 0;
+    for (; i < n; i += (long)gridDim.x * blockDim.x) {
+        unsigned long long s = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
+        auto next = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; };
+        next();
+        // operands: random sign/mantissa, exponent within +-2^40 of 1 most of the time, anywhere sometimes
+        auto rnd = [&]() {
+            unsigned long long r = next();
+            unsigned long long ex = (r >> 60) ? 1023 - 40 + (next() % 81) : next() % 2047;
+            return __longlong_as_double((long long)((r & 0x800fffffffffffffull) | (ex << 52)));
+        };
+        double a = rnd(), b = rnd();
+        if (which == 0) {
+            ex::DivBy d(b);
+            double q = d(a), t = a / b;
+            if (__double_as_longlong(q) != __double_as_longlong(t) && !(q != q && t != t)) ++bad;
+        } else if (which == 1) {
+            double q = ex::div3(a), t = a / 3.0;
+            if (__double_as_longlong(q) != __double_as_longlong(t) && !(q != q && t != t)) ++bad;
+        } else {
+            double q = ex::divz(a, b), t = a / b;
+            if (__double_as_longlong(q) != __double_as_longlong(t) && !(q != q && t != t)) ++bad;
+        }
+    }
+    if (bad) atomicAdd(mismatches, bad);
 }
 
 // layout helpers: (3,E) interleaved <-> [3][E]

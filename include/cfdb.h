@@ -152,6 +152,10 @@ int cfdb_gcl_main(cfdb_ctx* ctx, double* M, const double* W_x, const double* W_y
                   const double* W_y_old, const double* area_old, const double* dNx, const double* dNy,
                   const double* area, const int32_t* inpoel, int32_t nelem, int32_t npoin, double dt);
 
+/* ---- device self-test of the exact-arithmetic helpers (cfd_b200/csrc/exact.cuh) against the plain IEEE operations:
+ * which = 0 shared-reciprocal division, 1 division by three, 2 zero-numerator division; n random operand pairs. */
+int cfdb_selftest(cfdb_ctx* ctx, int32_t which, int64_t n, uint64_t seed, int64_t* mismatches);
+
 /* ---- host-side integer artefacts (bit-exact vs the oracle) --------------------------------- */
 /* PointNeighbor::getEsup / getPsup, pointNeighbor.f90:5-91.  psup1 needs capacity >= returned count. */
 int cfdb_get_esup(const int32_t* inpoel, int32_t nelem, int32_t npoin, int32_t* esup1, int32_t* esup2);

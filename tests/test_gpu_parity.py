@@ -290,3 +290,17 @@ def test_config1_channel_1000_steps():
         assert_bit_equal(g.get(n), o.get(n), n)
     U, Uo = g.get("U").reshape(-1, 4), o.get("U").reshape(-1, 4)
     assert np.max(np.abs(U - Uo) / np.abs(Uo).max(0)) <= 1e-8   # the stated tolerance, met with margin (exactly 0)
+
+
+@pytest.mark.parametrize("which", [0, 1, 2])
+def test_exact_arithmetic_helpers_on_device(cases, which):
+    """exact.cuh: shared-reciprocal division, x/3 and zero-numerator division equal the IEEE '/' on 2e9 random operands."""
+    import ctypes as C
+
+    from cfd_b200 import capi
+    from cfd_b200.solver import NSComp2D
+
+    g = NSComp2D(cases["channel"])
+    bad = C.c_int64(-1)
+    capi.check(g.L.cfdb_selftest(g.h, which, 2_000_000_000, 1234567 + which, C.byref(bad)))
+    assert bad.value == 0
