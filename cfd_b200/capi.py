@@ -19,7 +19,7 @@ SYMBOLS = [
     "cfdb_rk_stage", "cfdb_geometry", "cfdb_fluid_structure", "cfdb_residual_norms", "cfdb_step_norms", "cfdb_get", "cfdb_set",
     "cfdb_field_size", "cfdb_get_scalar", "cfdb_set_scalar", "cfdb_stream", "cfdb_profile_enable", "cfdb_profile_get",
     "cfdb_launch_count", "cfdb_nccl_unique_id", "cfdb_comm_init", "cfdb_set_halo", "cfdb_halo_exchange", "cfdb_calcrhs", "cfdb_fuente", "cfdb_deltat", "cfdb_estab", "cfdb_deriv", "cfdb_masas",
-    "cfdb_normales", "cfdb_laplace", "cfdb_bicg", "cfdb_spmv", "cfdb_vecdot", "cfdb_gcl_main", "cfdb_selftest", "cfdb_get_esup",
+    "cfdb_normales", "cfdb_laplace", "cfdb_bicg", "cfdb_spmv", "cfdb_vecdot", "cfdb_gcl_main", "cfdb_smoothing", "cfdb_selftest", "cfdb_get_esup",
     "cfdb_get_psup",
 ]
 
@@ -97,6 +97,7 @@ def lib():
     L.cfdb_spmv.argtypes = [vp, _dp, _ip, _ip, _dp, _dp, i32, i32]
     L.cfdb_vecdot.argtypes = [vp, i32, _dp, _dp, C.POINTER(d)]
     L.cfdb_gcl_main.argtypes = [vp] + [_dp] * 9 + [_ip, i32, i32, d]
+    L.cfdb_smoothing.argtypes = [_dp, _dp, _ip, np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS"), i32, i32, C.POINTER(i32)]
     L.cfdb_selftest.argtypes = [vp, i32, i64, C.c_uint64, C.POINTER(i64)]
     L.cfdb_get_esup.argtypes = [_ip, i32, i32, _ip, _ip]
     L.cfdb_get_psup.argtypes = [_ip, i32, i32, _ip, i32, _ip, C.POINTER(i32)]
@@ -139,3 +140,10 @@ def get_psup(inpoel, npoin):
     p1, p2, cnt = np.zeros(cap, np.int32), np.zeros(npoin + 1, np.int32), C.c_int32()
     check(lib().cfdb_get_psup(inpoel, nelem, npoin, p1, cap, p2, C.byref(cnt)))
     return p1[: cnt.value].copy(), p2
+
+
+def smoothing(lc):
+    """smoothing_mod::smoothing on a LoadedCase (updates lc.X, lc.Y in place); returns the number of sweeps."""
+    n = C.c_int32()
+    check(lib().cfdb_smoothing(lc.X, lc.Y, lc.inpoel, lc.smooth_fix, lc.npoin, lc.nelem, C.byref(n)))
+    return n.value

@@ -2,6 +2,7 @@
 // Compiled for sm_100a only, with -fmad=false (see exact.cuh).  No CPU fallback anywhere.
 #include "../../include/cfdb.h"
 #include "host_topology.h"
+#include "../../host/mesh_smoothing.h"
 #include "kernels.cuh"
 
 #include <nccl.h>
@@ -222,6 +223,16 @@ extern "C" int cfdb_get_psup(const int32_t* inpoel, int32_t nelem, int32_t npoin
     std::copy(p2.begin(), p2.end(), psup2);
     if ((int)p1.size() > cap) return fail("cfdb_get_psup: capacity too small");
     std::copy(p1.begin(), p1.end(), psup1);
+    return 0;
+}
+
+extern "C" int cfdb_smoothing(double* X, double* Y, const int32_t* inpoel, const unsigned char* fixed, int32_t npoin,
+                              int32_t nelem, int32_t* sweeps) {
+    if (npoin < 1 || nelem < 1) return fail("cfdb_smoothing: empty mesh");
+    for (size_t k = 0; k < 3 * (size_t)nelem; ++k)
+        if (inpoel[k] < 1 || inpoel[k] > npoin) return fail("cfdb_smoothing: inpoel entry out of range");
+    host::MeshSmoother sm(X, Y, inpoel, npoin, nelem);
+    *sweeps = sm.run(fixed);
     return 0;
 }
 

@@ -26,9 +26,11 @@ def _vp(a):
 
 
 class NSComp2D:
-    def __init__(self, lc: LoadedCase, device: int = 0, use_gcl: int = 0, init: bool = True):
+    def __init__(self, lc: LoadedCase, device: int = 0, use_gcl: int = 0, init: bool = True, smooth: bool = False):
         self.L = capi.lib()
         self.lc = lc
+        if smooth:  # ns2DComp.ALE.f90:63-76: SMOOTH_FIX = I_M + IFM nodes, then the one-time mesh optimiser
+            self.smoothing_sweeps = capi.smoothing(lc)
         s = lc.sets
         self._keep = [np.ascontiguousarray(s[:, k]) for k in range(4)] if s.size else [np.zeros(0, np.int32)] * 4
         bc = capi.BC(

@@ -152,6 +152,12 @@ int cfdb_gcl_main(cfdb_ctx* ctx, double* M, const double* W_x, const double* W_y
                   const double* W_y_old, const double* area_old, const double* dNx, const double* dNy,
                   const double* area, const int32_t* inpoel, int32_t nelem, int32_t npoin, double dt);
 
+/* smoothing_mod::smoothing(X, Y, inpoel, fixed, npoin, nelem), smoothing.f90:21 — the init-time mesh optimiser the
+ * driver applies once before the time loop (ns2DComp.ALE.f90:76).  Host code (serial Gauss-Seidel by construction);
+ * X, Y are updated in place, *sweeps returns the number of outer sweeps (0: nothing to smooth). */
+int cfdb_smoothing(double* X, double* Y, const int32_t* inpoel, const unsigned char* fixed, int32_t npoin,
+                   int32_t nelem, int32_t* sweeps);
+
 /* ---- device self-test of the exact-arithmetic helpers (cfd_b200/csrc/exact.cuh) against the plain IEEE operations:
  * which = 0 shared-reciprocal division, 1 division by three, 2 zero-numerator division; n random operand pairs. */
 int cfdb_selftest(cfdb_ctx* ctx, int32_t which, int64_t n, uint64_t seed, int64_t* mismatches);

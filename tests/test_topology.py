@@ -43,3 +43,16 @@ def test_ragged_and_tiny_meshes():
         cnt = L.orc_get_psup(inpoel, len(inpoel), npoin, p1, 32, p2)
         assert np.array_equal(p1[:cnt], q1) and np.array_equal(p2, q2)
     assert q2[3] == q2[2]  # node 3 has no neighbours
+
+
+def test_product_smoothing_matches_oracle():
+    """cfdb_smoothing (host code inside libcfdb200.so, no GPU needed) is bit-exact against the oracle's restatement."""
+    from cfd_b200 import deck, meshgen
+
+    for seed, jit in ((5, 0.42), (8, 0.45)):
+        lc = deck.load(meshgen.channel(nx=31, ny=11, jitter=jit, seed=seed))
+        X, Y = lc.X.copy(), lc.Y.copy()
+        so = orclib.lib().orc_smoothing(X, Y, lc.inpoel, lc.smooth_fix, lc.npoin, lc.nelem)
+        sp = capi.smoothing(lc)
+        assert so == sp and so > 0
+        assert np.array_equal(lc.X.view(np.uint64), X.view(np.uint64)) and np.array_equal(lc.Y.view(np.uint64), Y.view(np.uint64))
