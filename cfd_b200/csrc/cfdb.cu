@@ -79,6 +79,7 @@ struct cfdb_ctx {
     cudaEvent_t ev_elem[4] = {nullptr, nullptr, nullptr, nullptr}, ev_node[4] = {nullptr, nullptr, nullptr, nullptr};
     double* ECcur = nullptr;  // staging buffers the element / node kernels use right now (double-buffered when
     double* FCcur = nullptr;  // node_update(k) overlaps calcrhs_elem(k+1))
+    const double* Usrc = nullptr;  // state calcRHS/FUENTE are evaluated at (U, or U1 for true_rk stages 2..4)
     cfdb_params par{};
     int npoin = 0, nelem = 0;
     // host copies of integer artefacts (API layout: 1-based)
@@ -114,6 +115,7 @@ struct cfdb_ctx {
     double DISN[2] = {0, 0};
     int bicg_iters[2] = {0, 0};
     bool theta_nonzero = false;
+    int use_cuarto = 0, true_rk = 0;  // "next" rows N1 / N2, default off (reference behaviour)
     bool u1_is_u = false;  // after U = U1 (ns2DComp.ALE.f90:277-281) the two arrays are one buffer
     // multi-GPU (one rank per context)
     ncclComm_t comm = nullptr;
@@ -713,7 +715,7 @@ static int run_calcrhs_elem(cfdb_ctx* c, const k::Gas& g, bool theta, bool ale, 
     if (e1 < 0) e1 = c->nelem;
     if (e1 <= e0) return 0;
     const int B = 128, G = grid_for(e1 - e0, B);
-#define ARGS e0, e1, c->nelem, c->inp.p, c->U.p, c->UN.p, c->T.p, c->W_X.p, c->W_Y.p, c->dNx.p, c->dNy.p, c->area.p, c->SHOC.p, \
+#define ARGS e0, e1, c->nelem, c->inp.p, (c->Usrc ? c->Usrc : c->U.p), c->UN.p, c->T.p, c->W_X.p, c->W_Y.p, c->dNx.p, c->dNy.p, c->area.p, c->SHOC.p, \
              dtl_arr, dtl_sc, c->TS1.p, c->TS2.p, c->TS3.p, g, (c->ECcur ? c->ECcur : c->EC.p), (c->FCcur ? c->FCcur : c->FC.p)
     // persistent cp.async-pipelined variant: whole-mesh launches on fixed meshes with theta = 0
     static const int pipe = getenv("CFDB_CALCRHS_PIPE") ? atoi(getenv("CFDB_CALCRHS_PIPE")) : 0;
@@ -729,7 +731,7 @@ static int run_calcrhs_elem(cfdb_ctx* c, const k::Gas& g, bool theta, bool ale, 
             int grid = std::min(ntiles, nsm * M);                                                                 \
             cudaEvent_t _a = nullptr, _b = nullptr;                                                               \
             TRY(prof_begin(c, c->st, K_CALCRHS, &_a, &_b));                                                       \
-            kp<<<grid, 128, smem, c->st>>>(c->nelem, c->inp.p, c->U.p, c->T.p, c->dNx.p, c->dNy.p, c->area.p,     \
+            kp<<<grid, 128, smem, c->st>>>(c->nelem, c->inp.p, (c->Usrc ? c->Usrc : c->U.p), c->T.p, c->dNx.p, c->dNy.p, c->area.p,     \
                                            c->SHOC.p, dtl_arr, dtl_sc, c->TS1.p, c->TS2.p, c->TS3.p, g,           \
                                            (c->ECcur ? c->ECcur : c->EC.p));                                      \
             CK(cudaGetLastError());                                                                               \
@@ -793,19 +795,28 @@ extern "C" int cfdb_rk_stage(cfdb_ctx* c, int32_t irk) {
     if (irk < 1 || irk > NRK) return fail("cfdb_rk_stage: irk must be 1..4");
     double RK_FACT = 1.0 / (NRK + 1 - irk);
     if (irk == 1) {
-        // cuarto_orden's projection is discarded by UN = 0.0 (subrutinas.f90:673-674)
-        if (c->theta_nonzero) {
+        // cuarto_orden's projection is discarded by UN = 0.0 (subrutinas.f90:673-674) unless use_cuarto
+        if (c->use_cuarto) {
+            const double* u1 = c->u1_is_u ? c->U.p : c->U1.p;  // cuarto_orden(U1, UN, ...): U1 == U at this point (:168-172)
+            LAUNCH(K_CALCRHS, k::cuarto_elem, grid_for(c->nelem, 128), 128, c->nelem, c->inp.p, u1, c->GAMM.p, c->dNx.p,
+                   c->dNy.p, c->area.p, c->EC.p);
+            LAUNCH(K_NODE, k::cuarto_node, grid_for(c->npoin, 256), 256, c->npoin, c->d_esup2.p, c->eslot.p, c->EC.p, c->M.p, c->UN.p);
+            TRY(halo_vec(c, c->UN.p, 4));
+            c->theta_nonzero = true;
+        } else if (c->theta_nonzero) {
             CK(cudaMemsetAsync(c->UN.p, 0, 4 * (size_t)c->npoin * sizeof(double), c->st));
             c->theta_nonzero = false;
         }
         TRY(run_estab(c, &c->sc->DTMIN));
     }
     c->u1_is_u = false;
+    c->Usrc = (c->true_rk && irk > 1) ? c->U1.p : nullptr;
+    struct UsrcReset { cfdb_ctx* c; ~UsrcReset() { c->Usrc = nullptr; } } usrc_reset{c};
     k::Gas g{p.FCv, p.FK, p.FMU, p.GAMA, p.T_inf, p.CTE};
     const double* dtl_arr = p.ITLOCAL != 0 ? c->DTL.p : nullptr;
     const int nch = (int)c->chunk_ev.size();
     if (nch <= 1) {
-        TRY(run_calcrhs_elem(c, g, false, c->ale, dtl_arr, &c->sc->DTMIN));
+        TRY(run_calcrhs_elem(c, g, c->use_cuarto != 0, c->ale, dtl_arr, &c->sc->DTMIN));
         TRY(run_node(c, c->st, c->ale, true, RK_FACT));
         TRY(halo_state(c));
         return 0;
@@ -845,7 +856,7 @@ static int run_rk(cfdb_ctx* c) {
     // the same SM residency — so it is opt-in (CFDB_STAGE_OVERLAP=1)
     static const bool no_ovl = getenv("CFDB_STAGE_OVERLAP") == nullptr;
     const bool visc = p.FMU > 2.2250738585072014e-308;
-    if (visc || no_ovl || c->chunk_ev.size() > 1) {
+    if (visc || no_ovl || c->chunk_ev.size() > 1 || c->use_cuarto || c->true_rk) {
         for (int irk = 1; irk <= 4; ++irk) TRY(cfdb_rk_stage(c, irk));
         return 0;
     }
@@ -1093,6 +1104,14 @@ extern "C" int cfdb_sync(cfdb_ctx* c) {
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->st));
     TRY(prof_resolve(c));
+    return 0;
+}
+extern "C" int cfdb_set_option(cfdb_ctx* c, const char* name, int32_t value) {
+    std::string n(name);
+    if (n == "use_cuarto") c->use_cuarto = value;
+    else if (n == "true_rk") c->true_rk = value;
+    else return fail("cfdb_set_option: unknown option " + n);
+    if (c->chunk_ev.size() > 1 && (c->use_cuarto || c->true_rk)) return fail("cfdb_set_option: not available with CFDB_CHUNK");
     return 0;
 }
 extern "C" void* cfdb_stream(cfdb_ctx* c) { return (void*)c->st; }

@@ -604,6 +604,79 @@ __global__ void __launch_bounds__(128, MINB) calcrhs_pipe(int nelem, const int* 
     cp_async_wait<0>();
 }
 
+// CUARTO_ORDEN (subrutinas.f90:243-327), "next" row N1: element part -> staging buffer, node part
+// U_n = -(ordered sum)/M.  Same ordered-gather scheme as calcRHS.
+__global__ void __launch_bounds__(128) cuarto_elem(int nelem, const int* __restrict__ inp, const double* __restrict__ U,
+                                                    const double* __restrict__ GAMM, const double* __restrict__ dNx,
+                                                    const double* __restrict__ dNy, const double* __restrict__ area,
+                                                    double* __restrict__ EC) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nelem) return;
+    const double sp[3][3] = {{.5, .5, 0.0}, {0.0, .5, .5}, {.5, 0.0, .5}};
+    int ip[3] = {inp[e], inp[nelem + e], inp[2 * (size_t)nelem + e]};
+    double Nx[3] = {dNx[e], dNx[nelem + e], dNx[2 * (size_t)nelem + e]};
+    double Ny[3] = {dNy[e], dNy[nelem + e], dNy[2 * (size_t)nelem + e]};
+    double Un[3][4];
+    ld4(U + 4 * (size_t)ip[0], Un[0]);
+    ld4(U + 4 * (size_t)ip[1], Un[1]);
+    ld4(U + 4 * (size_t)ip[2], Un[2]);
+    double gama = (GAMM[ip[0]] + GAMM[ip[1]] + GAMM[ip[2]]) / 3.0;
+    double Ux[4], Uy[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        Ux[i] = Un[0][i] * Nx[0] + Un[1][i] * Nx[1] + Un[2][i] * Nx[2];
+        Uy[i] = Un[0][i] * Ny[0] + Un[1][i] * Ny[1] + Un[2][i] * Ny[2];
+    }
+    double AR = area[e] / 3.0;
+    double Adv[3][4];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        double Ul[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) Ul[i] = sp[c][0] * Un[0][i] + sp[c][1] * Un[1][i] + sp[c][2] * Un[2][i];
+        double vx = Ul[1] / Ul[0], vy = Ul[2] / Ul[0], en = Ul[3] / Ul[0];
+        double V_sq = vx * vx + vy * vy;
+        double A1[3][4] = {{(gama - 1.0) / 2.0 * V_sq - vx * vx, (3.0 - gama) * vx, -(gama - 1.0) * vy, (gama - 1.0)},
+                           {-vx * vy, vy, vx, 0.0},
+                           {((gama - 1.0) * V_sq - gama * en) * vx, gama * en - (gama - 1.0) / 2.0 * V_sq - (gama - 1.0) * vx * vx,
+                            -(gama - 1.0) * vx * vy, gama * vx}};
+        double A2[3][4] = {{-vx * vy, vy, vx, 0.0},
+                           {(gama - 1.0) / 2.0 * V_sq - vy * vy, -(gama - 1.0) * vx, (3.0 - gama) * vy, (gama - 1.0)},
+                           {((gama - 1.0) * V_sq - gama * en) * vy, -(gama - 1.0) * vx * vy,
+                            gama * en - (gama - 1.0) / 2.0 * V_sq - (gama - 1.0) * vy * vy, gama * vy}};
+        Adv[c][0] = Ux[1] + Uy[2];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+            Adv[c][1 + r] = A1[r][0] * Ux[0] + A1[r][1] * Ux[1] + A1[r][2] * Ux[2] + A1[r][3] * Ux[3] + A2[r][0] * Uy[0] +
+                            A2[r][1] * Uy[1] + A2[r][2] * Uy[2] + A2[r][3] * Uy[3];
+    }
+    double* out = EC + 12 * (size_t)e;
+#pragma unroll
+    for (int n = 0; n < 3; ++n) {
+        double v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = Adv[0][i] * sp[0][n] * AR + Adv[1][i] * sp[1][n] * AR + Adv[2][i] * sp[2][n] * AR;
+        st4(out + 4 * n, v);
+    }
+}
+__global__ void __launch_bounds__(256) cuarto_node(int npoin, const int* __restrict__ esup2, const int* __restrict__ eslot,
+                                                    const double* __restrict__ EC, const double* __restrict__ M,
+                                                    double* __restrict__ UN) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= npoin) return;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k = esup2[n]; k < esup2[n + 1]; ++k) {
+        double c[4];
+        ld4(EC + 4 * (size_t)eslot[k], c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = acc[i] + c[i];
+    }
+    double m = M[n];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] = -acc[i] / m;
+    st4(UN + 4 * (size_t)n, acc);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Node kernel: ordered sum of the staged contributions (= RHS), then the whole nodal chain of RK
 // (subrutinas.f90:695-826): U1 = U - rk/M*RHS, primitives, fixvel -> normalvel -> FIX, conservative.

@@ -319,3 +319,36 @@ def read_deck(directory: str) -> RawCase:
         MOVING=MOVING, XREF1=XREF1, YREF1=YREF1, fixrho=fixrho, fixvi=fixvi, fixv=fixv, wall=wall, fixt=fixt,
         sets=sets, master=master, slave=slave, ifm=ifm, i_m=i_m,
     )
+
+
+# ---------------------------------------------------------------------------------------------
+# restart file <name>.RST — Fortran unformatted sequential (PRINTREST ns2DComp.ALE.f90:898-917, RESTART :423-431):
+# record 1 = (ITER int32, TIME real64); then one record per node = (U(1:4), T, GAMM) real64.  Each record is
+# framed by 4-byte length markers (gfortran / ifort default).
+
+def write_rst(path: str, it: int, time: float, U, T, GAMM) -> None:
+    import struct
+
+    U = np.asarray(U, F64).reshape(-1, 4)
+    n = U.shape[0]
+    rec = np.zeros(n, dtype=[("l0", "<i4"), ("u", "<f8", 4), ("t", "<f8"), ("g", "<f8"), ("l1", "<i4")])
+    rec["l0"] = rec["l1"] = 48
+    rec["u"], rec["t"], rec["g"] = U, np.asarray(T, F64), np.asarray(GAMM, F64)
+    with open(path, "wb") as f:
+        f.write(struct.pack("<iidi", 12, int(it), float(time), 12))
+        f.write(rec.tobytes())
+
+
+def read_rst(path: str, npoin: int):
+    """Returns (ITER, TIME, U(npoin,4), T, GAMM).  The reference reads ITER/TIME into locals and drops them, and does
+    not restore VEL_X/VEL_Y; callers decide what to do with them."""
+    import struct
+
+    with open(path, "rb") as f:
+        l0, it, time, l1 = struct.unpack("<iidi", f.read(20))
+        if l0 != 12 or l1 != 12:
+            raise ValueError("not a Fortran unformatted .RST file (bad first record)")
+        rec = np.frombuffer(f.read(npoin * 56), dtype=[("l0", "<i4"), ("u", "<f8", 4), ("t", "<f8"), ("g", "<f8"), ("l1", "<i4")])
+    if rec.size != npoin or (rec["l0"] != 48).any() or (rec["l1"] != 48).any():
+        raise ValueError("restart file does not hold npoin node records")
+    return it, time, np.ascontiguousarray(rec["u"]), np.ascontiguousarray(rec["t"]), np.ascontiguousarray(rec["g"])

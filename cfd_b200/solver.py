@@ -139,6 +139,30 @@ class NSComp2D:
     def set_scalar(self, name, v):
         capi.check(self.L.cfdb_set_scalar(self.h, name.encode(), float(v)))
 
+    # ---- restart files (PRINTREST / RESTART, ns2DComp.ALE.f90:898-917, :423-431) ---------------------------
+    def print_rest(self, path):
+        """PRINTREST: <name>.RST with (ITER, TIME) and, per node, (U(1:4), T, GAMM)."""
+        from .deck import write_rst
+
+        write_rst(path, int(self.scalar("ITER")), self.scalar("TIME"), self.get("U"), self.get("T"), self.get("GAMM"))
+
+    def restart(self, path):
+        """RESTART with IRESTART == 1: U, T, GAMM come from the file; ITER/TIME are read and dropped and VEL_X/VEL_Y are
+        not restored, exactly as the reference does (they are left at zero here, the value fresh ALLOCATE memory has)."""
+        from .deck import read_rst
+
+        _, _, U, T, G = read_rst(path, self.npoin)
+        self.set("U", U)
+        self.set("T", T)
+        self.set("GAMM", G)
+        z = np.zeros(self.npoin)
+        self.set("VEL_X", z)
+        self.set("VEL_Y", z)
+
+    def set_option(self, name, value):
+        """'use_cuarto' / 'true_rk' (SURVEY.md §8f N1, N2); default 0 = the reference's behaviour."""
+        capi.check(self.L.cfdb_set_option(self.h, name.encode(), int(value)))
+
     @property
     def stream(self):
         return self.L.cfdb_stream(self.h)

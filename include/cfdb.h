@@ -85,6 +85,10 @@ int cfdb_set(cfdb_ctx* ctx, const char* name, const void* host, int64_t count);
 int64_t cfdb_field_size(cfdb_ctx* ctx, const char* name);    /* elements; <0 if unknown */
 int cfdb_get_scalar(cfdb_ctx* ctx, const char* name, double* value); /* TIME DTMIN DTMIN1 HMIN ITER BANDERA n_m bicg_x bicg_y FX1 FY1 RM1 */
 int cfdb_set_scalar(cfdb_ctx* ctx, const char* name, double value);
+/* switches beyond the reference's behaviour ("next" rows of SURVEY.md §8f), all default 0:
+ *   "use_cuarto" 1: keep CUARTO_ORDEN's projection as theta instead of UN = 0.0 (subrutinas.f90:673-674, F7)
+ *   "true_rk"    1: RK stages 2..4 evaluate calcRHS/FUENTE at U1 instead of U (subrutinas.f90:685,697, F6) */
+int cfdb_set_option(cfdb_ctx* ctx, const char* name, int32_t value);
 /* CUDA stream the context launches on (cudaStream_t as void*), for event timing by the caller */
 void* cfdb_stream(cfdb_ctx* ctx);
 /* per-kernel timing: enable, run, then read accumulated device milliseconds and launch counts */

@@ -422,6 +422,56 @@ static void fuente(double* rhs, const double* U, const double* w_x, const double
     }
 }
 
+// subrutinas.f90:220-329  CUARTO_ORDEN — 4th-order projection theta = -(1/M) sum_e int N_i (A1 U_x + A2 U_y).
+// The reference computes it and discards it (UN = 0.0, :674); kept behind Solver::use_cuarto ("next" N1).
+static void cuarto_orden(const double* U, double* U_n, double FR, const double* GAMM, const double* dNx,
+                         const double* dNy, const double* area, const double* M, const int* inpoel, int nelem, int npoin) {
+    static const double sp[3][3] = {{.5, .5, 0.0}, {0.0, .5, .5}, {.5, 0.0, .5}};  // sp[c][r] = sp(r+1,c+1) :236-238
+    for (int i = 0; i < 4 * npoin; ++i) U_n[i] = 0.0;
+    for (int ie = 0; ie < nelem; ++ie) {
+        const int* ip = inpoel + 3 * ie;
+        const double* U1 = U + 4 * (ip[0] - 1);
+        const double* U2 = U + 4 * (ip[1] - 1);
+        const double* U3 = U + 4 * (ip[2] - 1);
+        double gama = (GAMM[ip[0] - 1] + GAMM[ip[1] - 1] + GAMM[ip[2] - 1]) / 3.0;
+        const double* Nx = dNx + 3 * ie;
+        const double* Ny = dNy + 3 * ie;
+        double Ux[4], Uy[4];
+        for (int i = 0; i < 4; ++i) {
+            Ux[i] = U1[i] * Nx[0] + U2[i] * Nx[1] + U3[i] * Nx[2];
+            Uy[i] = U1[i] * Ny[0] + U2[i] * Ny[1] + U3[i] * Ny[2];
+        }
+        double AR = area[ie] / 3.0;
+        double Adv[3][4];
+        for (int c = 0; c < 3; ++c) {
+            double Ul[4];
+            for (int i = 0; i < 4; ++i) Ul[i] = sp[c][0] * U1[i] + sp[c][1] * U2[i] + sp[c][2] * U3[i];
+            double vx = Ul[1] / Ul[0], vy = Ul[2] / Ul[0], e = Ul[3] / Ul[0];
+            double V_sq = vx * vx + vy * vy;
+            // temp, c (:267-268) are computed and never used
+            double A1[3][4] = {{(gama - 1.0) / 2.0 * V_sq - vx * vx, (3.0 - gama) * vx, -(gama - 1.0) * vy, (gama - 1.0)},
+                               {-vx * vy, vy, vx, 0.0},
+                               {((gama - 1.0) * V_sq - gama * e) * vx, gama * e - (gama - 1.0) / 2.0 * V_sq - (gama - 1.0) * vx * vx,
+                                -(gama - 1.0) * vx * vy, gama * vx}};
+            double A2[3][4] = {{-vx * vy, vy, vx, 0.0},
+                               {(gama - 1.0) / 2.0 * V_sq - vy * vy, -(gama - 1.0) * vx, (3.0 - gama) * vy, (gama - 1.0)},
+                               {((gama - 1.0) * V_sq - gama * e) * vy, -(gama - 1.0) * vx * vy,
+                                gama * e - (gama - 1.0) / 2.0 * V_sq - (gama - 1.0) * vy * vy, gama * vy}};
+            Adv[c][0] = Ux[1] + Uy[2];
+            for (int r = 0; r < 3; ++r)
+                Adv[c][1 + r] = A1[r][0] * Ux[0] + A1[r][1] * Ux[1] + A1[r][2] * Ux[2] + A1[r][3] * Ux[3] + A2[r][0] * Uy[0] +
+                                A2[r][1] * Uy[1] + A2[r][2] * Uy[2] + A2[r][3] * Uy[3];
+        }
+        for (int n = 0; n < 3; ++n)
+            for (int i = 0; i < 4; ++i) {
+                double t = Adv[0][i] * sp[0][n] * AR + Adv[1][i] * sp[1][n] * AR + Adv[2][i] * sp[2][n] * AR;  // :305-307
+                U_n[4 * (ip[n] - 1) + i] += t;                                                                // :309-318
+            }
+    }
+    for (int n = 0; n < npoin; ++n)
+        for (int i = 0; i < 4; ++i) U_n[4 * n + i] = -U_n[4 * n + i] / M[n];  // :325
+}
+
 // ------------------------------------------------------------------------------------------
 // mLaplace.f90:96-108  mu
 static inline double mu_metric(const double* X3, const double* Y3) {
@@ -588,6 +638,8 @@ struct Solver {
     // loop scalars (ns2DComp.ALE.f90:109-134)
     double TIME = 0, DTMIN = 0, DTMIN1 = 0, HMIN = 0;
     int ITER = 0, BANDERA = 1, ITERPRINT = 0, norms_every_step = 1;
+    int use_cuarto = 0;  // "next" N1: keep CUARTO_ORDEN's projection instead of UN = 0.0 (subrutinas.f90:674)
+    int true_rk = 0;     // "next" N2: stages 2..4 evaluate calcRHS/FUENTE at U1 instead of U
     int last_bicg_iters[2] = {0, 0};
     double ER[4], ERR[4];
 };
@@ -632,17 +684,22 @@ static void rk_stage(Solver& s, int IRK, int NRK) {
     const int npoin = s.npoin, nelem = s.nelem;
     double RK_FACT = 1.0 / (NRK + 1 - IRK);
     if (IRK == 1) {
-        // cuarto_orden result is discarded: UN = 0.0 (:673-674, F7)
-        std::fill(s.UN.begin(), s.UN.end(), 0.0);
+        // cuarto_orden result is discarded: UN = 0.0 (:673-674, F7) unless use_cuarto
+        if (s.use_cuarto)
+            cuarto_orden(s.U1.data(), s.UN.data(), p.FR, s.GAMM.data(), s.dNx.data(), s.dNy.data(), s.area.data(), s.M.data(),
+                         s.inpoel.data(), nelem, npoin);
+        else
+            std::fill(s.UN.begin(), s.UN.end(), 0.0);
         estab(nelem, s.inpoel.data(), s.U.data(), s.T.data(), s.VEL_X.data(), s.VEL_Y.data(), s.W_X.data(),
               s.W_Y.data(), s.GAMM.data(), s.dNx.data(), s.dNy.data(), p.FR, s.DTMIN, p.RHO_inf, p.T_inf,
               s.SHOC.data(), s.T_SUGN1.data(), s.T_SUGN2.data(), s.T_SUGN3.data());
     }
     std::fill(s.RHS.begin(), s.RHS.end(), 0.0);
     GasK g{p.FCv, p.FK, p.FMU, p.GAMA, p.T_inf, p.CTE};
-    calcrhs(g, s.RHS.data(), s.U.data(), s.UN.data(), s.T.data(), s.dNx.data(), s.dNy.data(), s.area.data(),
+    const double* Usrc = (s.true_rk && IRK > 1) ? s.U1.data() : s.U.data();
+    calcrhs(g, s.RHS.data(), Usrc, s.UN.data(), s.T.data(), s.dNx.data(), s.dNy.data(), s.area.data(),
             s.SHOC.data(), s.DTL.data(), s.T_SUGN1.data(), s.T_SUGN2.data(), s.T_SUGN3.data(), s.inpoel.data(), nelem);
-    fuente(s.RHS.data(), s.U.data(), s.W_X.data(), s.W_Y.data(), s.dNx.data(), s.dNy.data(), s.area.data(),
+    fuente(s.RHS.data(), Usrc, s.W_X.data(), s.W_Y.data(), s.dNx.data(), s.dNy.data(), s.area.data(),
            s.DTL.data(), s.inpoel.data(), nelem);
     OMP_FOR
     for (int ip = 0; ip < npoin; ++ip) {
@@ -1048,6 +1105,8 @@ void orc_set_scalar(void* h, const char* name, double v) {
     else if (n == "ITER") s.ITER = (int)v;
     else if (n == "BANDERA") s.BANDERA = (int)v;
     else if (n == "norms_every_step") s.norms_every_step = (int)v;
+    else if (n == "use_cuarto") s.use_cuarto = (int)v;
+    else if (n == "true_rk") s.true_rk = (int)v;
 }
 int orc_omp_threads() {
 #ifdef ORC_OMP

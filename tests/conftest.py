@@ -43,4 +43,16 @@ def cases():
     out["wedge"] = deck.load(meshgen.wedge(nx=49, ny=25, mach=2.5))
     out["ale"] = deck.load(meshgen.ale_body(nt=48, nr=14))
     out["square"] = deck.load(meshgen.square(n=33))
+    # viscous channel with a no-slip lower wall (fixv -> also fixed wall temperature, single-precision TWALL),
+    # a fixed-temperature patch, duplicated list entries (last entry wins) and a wall/no-slip overlap
+    raw = meshgen.channel(nx=37, ny=11, FMU=1.8e-5, FK=0.0257, mach=0.6)
+    nx = 37
+    lower = np.arange(2, nx, dtype=np.int32)                       # interior nodes of the lower wall
+    raw.wall = raw.wall[~np.isin(raw.wall, lower[5:]).any(1)]      # keep a few slip edges that overlap no-slip nodes
+    raw.fixv = np.concatenate([lower, lower[:3]]).astype(np.int32)  # duplicates
+    top = (10 * nx + np.arange(5, 15)).astype(np.int32)
+    raw.fixt = (np.concatenate([top, top[:2]]).astype(np.int32), np.concatenate([np.full(10, 1.1), np.full(2, 0.9)]))
+    raw.fixrho = (np.concatenate([raw.fixrho[0], raw.fixrho[0][:2]]).astype(np.int32),
+                  np.concatenate([raw.fixrho[1], np.array([-1.0, 1.05])]))
+    out["channel_noslip"] = deck.load(raw)
     return out

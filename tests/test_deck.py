@@ -47,3 +47,19 @@ def test_generated_meshes_are_valid():
         assert np.unique(inp).size == raw.npoin
     a, b = meshgen.square(n=12, seed=3), meshgen.square(n=12, seed=3)
     assert np.array_equal(a.X, b.X) and np.array_equal(a.inpoel, b.inpoel)      # seeded
+
+
+def test_restart_file_round_trip(tmp_path):
+    rng = np.random.default_rng(2)
+    n = 37
+    U, T, G = rng.standard_normal((n, 4)), rng.random(n) + 250, np.full(n, 1.4)
+    p = str(tmp_path / "case.RST")
+    deck.write_rst(p, 123, 0.5, U, T, G)
+    raw = open(p, "rb").read()
+    assert len(raw) == 20 + n * 56 and raw[:4] == (12).to_bytes(4, "little")      # Fortran record framing
+    it, time, U2, T2, G2 = deck.read_rst(p, n)
+    assert (it, time) == (123, 0.5) and np.array_equal(U, U2) and np.array_equal(T, T2) and np.array_equal(G, G2)
+    import pytest
+
+    with pytest.raises(ValueError):
+        deck.read_rst(p, n + 1)

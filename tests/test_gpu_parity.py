@@ -51,7 +51,7 @@ def test_init_geometry(cases, name):
     assert_bit_equal(g.get("n_y"), o.get("n_y")[:m], "n_y")
 
 
-@pytest.mark.parametrize("name", ["channel", "channel_visc", "wedge", "square", "channel_itlocal"])
+@pytest.mark.parametrize("name", ["channel", "channel_visc", "wedge", "square", "channel_itlocal", "channel_noslip"])
 def test_steps_bit_exact(cases, name):
     lc = cases[name]
     g, o = _pair(lc)
@@ -326,3 +326,62 @@ def test_config2_size_wedge_1m_triangles():
     g2 = NSComp2D(lc)
     g2.step(3)
     assert_bit_equal(g2.get("U"), g.get("U"), "second run")
+
+
+def test_no_bc_lists_and_isolated_node():
+    """cfdb_create with bc = NULL-equivalent empty lists and a node no element references."""
+    from cfd_b200 import deck, meshgen
+    from cfd_b200.solver import NSComp2D
+    from oracle.orclib import Oracle
+
+    raw = meshgen.square(n=9)
+    empty = np.zeros(0, np.int32)
+    raw.fixrho, raw.fixvi, raw.wall, raw.ifm = (empty, np.zeros(0)), (empty, np.zeros(0), np.zeros(0)), np.zeros((0, 2), np.int32), empty
+    raw.X, raw.Y = np.append(raw.X, 5.0), np.append(raw.Y, 5.0)     # isolated node 82
+    lc = deck.load(raw)
+    g, o = NSComp2D(lc), Oracle(lc)
+    for k, v in meshgen.density_bump(lc, x0=0.5, y0=0.5, sigma=0.2).items():
+        g.set(k, v)
+        o.set(k, v)
+    g.step(3)
+    o.step(3)
+    own = slice(0, 4 * 81)                                          # the isolated node has M = 0: 0/0 on both sides
+    assert_bit_equal(g.get("U")[own], o.get("U")[own], "U")
+    assert np.array_equal(np.isnan(g.get("U")), np.isnan(o.get("U")))
+
+
+@pytest.mark.parametrize("opts", [{"use_cuarto": 1}, {"true_rk": 1}, {"use_cuarto": 1, "true_rk": 1}])
+@pytest.mark.parametrize("name", ["channel_visc", "ale"])
+def test_next_rows_cuarto_orden_and_true_rk(cases, name, opts):
+    """SURVEY.md §8f N1/N2 behind switches (default off): CUARTO_ORDEN's projection kept as theta, and RK stages
+    evaluated at U1 — bit-exact against the oracle's restatement of subrutinas.f90:220-329 / the one-line RK change."""
+    lc = cases[name]
+    g, o = _pair(lc)
+    for k, v in opts.items():
+        g.set_option(k, v)
+        o.set_scalar(k, v)
+    if name != "ale":
+        _perturb(lc, g, o)
+    g.step(4)
+    o.step(4)
+    _compare(g, o, STATE + ["UN"], tag=f"{name} {opts}:")
+    if "use_cuarto" in opts:
+        assert np.abs(g.get("UN")).max() > 0
+
+
+def test_restart_file_resumes_state(cases, tmp_path):
+    from cfd_b200.solver import NSComp2D
+
+    lc = cases["channel_visc"]
+    g, o = _pair(lc)
+    _perturb(lc, g, o)
+    g.step(5)
+    p = str(tmp_path / "c.RST")
+    g.print_rest(p)
+    h = NSComp2D(lc)
+    h.restart(p)
+    assert_bit_equal(h.get("U"), g.get("U"), "U")
+    assert_bit_equal(h.get("T"), g.get("T"), "T")
+    assert not h.get("VEL_X").any()          # the reference does not restore velocities
+    h.step(1)
+    assert np.isfinite(h.get("U")).all()
