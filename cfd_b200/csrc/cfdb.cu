@@ -797,8 +797,9 @@ extern "C" int cfdb_rk_stage(cfdb_ctx* c, int32_t irk) {
     if (irk == 1) {
         // cuarto_orden's projection is discarded by UN = 0.0 (subrutinas.f90:673-674) unless use_cuarto
         if (c->use_cuarto) {
-            const double* u1 = c->u1_is_u ? c->U.p : c->U1.p;  // cuarto_orden(U1, UN, ...): U1 == U at this point (:168-172)
-            LAUNCH(K_CALCRHS, k::cuarto_elem, grid_for(c->nelem, 128), 128, c->nelem, c->inp.p, u1, c->GAMM.p, c->dNx.p,
+            // cuarto_orden(U1, UN, ...): the loop has just copied U1 = U (ns2DComp.ALE.f90:168-172; the copy itself is
+            // elided here because every stage rewrites U1), so the projection is evaluated at U
+            LAUNCH(K_CALCRHS, k::cuarto_elem, grid_for(c->nelem, 128), 128, c->nelem, c->inp.p, c->U.p, c->GAMM.p, c->dNx.p,
                    c->dNy.p, c->area.p, c->EC.p);
             LAUNCH(K_NODE, k::cuarto_node, grid_for(c->npoin, 256), 256, c->npoin, c->d_esup2.p, c->eslot.p, c->EC.p, c->M.p, c->UN.p);
             TRY(halo_vec(c, c->UN.p, 4));
