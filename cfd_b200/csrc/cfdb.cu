@@ -117,6 +117,13 @@ struct cfdb_ctx {
     bool theta_nonzero = false;
     int use_cuarto = 0, true_rk = 0;  // "next" rows N1 / N2, default off (reference behaviour)
     bool u1_is_u = false;  // after U = U1 (ns2DComp.ALE.f90:277-281) the two arrays are one buffer
+    // tile-fused RK stage (fixed meshes)
+    bool tile_ok = false;
+    int ntiles = 0, nbnodes = 0;
+    double tile_interior = 0.0;
+    DBuf<int> tile_elems, tnode_ptr, tnodes, bnodes;
+    DBuf<unsigned char> ebmask;
+    DBuf<unsigned short> tslot;
     // multi-GPU (one rank per context)
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
@@ -447,6 +454,26 @@ extern "C" int cfdb_create(cfdb_ctx** out, const cfdb_params* par, int32_t npoin
     B(upload(c, c->yref, c->par.YREF, 10));
     B(build_bc_tables(c, bc));
     if (c->ale) B(zero(c, c->FC, 12 * E));
+    if (!c->ale && getenv("CFDB_TILE") && atoi(getenv("CFDB_TILE")) != 0) {
+        // tiles for the fused stage (opt-in: measured slower than the two-kernel stage on B200 — 2.04 + 0.26 ms against
+        // 1.19 + 0.62 ms per stage on the 16 M-triangle mesh; the memory-bound node phase starves at the 12 warps/SM
+        // the register-heavy element phase allows.  Bit-identical, covered by the GPU tests under CFDB_TILE=1.)
+        topo::Tiling T;
+        topo::build_tiling(inpoel, nelem, npoin, X, Y, c->esup1, c->esup2, c->h_eslot, 512, T);
+        c->tile_interior = T.interior_fraction;
+        {
+            c->ntiles = T.ntiles;
+            c->nbnodes = (int)T.bnodes.size();
+            B(upload(c, c->tile_elems, T.tile_elems));
+            B(upload(c, c->ebmask, T.ebmask));
+            B(upload(c, c->tnode_ptr, T.tnode_ptr));
+            B(upload(c, c->tnodes, T.tnodes));
+            B(upload(c, c->tslot, T.tslot));
+            B(upload(c, c->bnodes, T.bnodes));
+            CK(cudaStreamSynchronize(c->st));
+            c->tile_ok = true;
+        }
+    }
     if (cudaMalloc(&c->sc, sizeof(k::Scal)) != cudaSuccess) return bail(fail("cudaMalloc Scal failed"));
     if (cudaMemsetAsync(c->sc, 0, sizeof(k::Scal), c->st) != cudaSuccess) return bail(fail("memset Scal failed"));
     if (cudaMallocHost(&c->h_sc, sizeof(k::Scal)) != cudaSuccess) return bail(fail("cudaMallocHost failed"));
@@ -474,6 +501,7 @@ extern "C" void cfdb_destroy(cfdb_ctx* c) {
         d->release();
     c->lpos.release();
     c->bcflag.release();
+    c->tile_elems.release(); c->tnode_ptr.release(); c->tnodes.release(); c->bnodes.release(); c->ebmask.release(); c->tslot.release();
     c->isfix.release();
     c->bp2.release();
     for (auto* d : {&c->X, &c->Y, &c->X1, &c->Y1, &c->area, &c->HH, &c->HHX, &c->HHY, &c->dNx, &c->dNy, &c->M, &c->U, &c->U1,
@@ -772,11 +800,12 @@ static int run_calcrhs_elem(cfdb_ctx* c, const k::Gas& g, bool theta, bool ale, 
     return 0;
 }
 
-static int run_node(cfdb_ctx* c, cudaStream_t st, bool ale, bool update, double rk_fact, int n0 = 0, int n1 = -1) {
+static int run_node(cfdb_ctx* c, cudaStream_t st, bool ale, bool update, double rk_fact, int n0 = 0, int n1 = -1,
+                    const int* nlist = nullptr) {
     if (n1 < 0) n1 = c->npoin;
     if (n1 <= n0) return 0;
     const int B = 256, G = grid_for(n1 - n0, B);
-#define ARGS n0, n1, c->d_esup2.p, c->eslot.p, (c->ECcur ? c->ECcur : c->EC.p), (c->FCcur ? c->FCcur : c->FC.p), c->U.p, c->M.p, c->GAMM.p, c->W_X.p, c->W_Y.p, \
+#define ARGS n0, n1, nlist, c->d_esup2.p, c->eslot.p, (c->ECcur ? c->ECcur : c->EC.p), (c->FCcur ? c->FCcur : c->FC.p), c->U.p, c->M.p, c->GAMM.p, c->W_X.p, c->W_Y.p, \
              c->bcflag.p, bctab(c), rk_fact, c->par.FR, c->U1.p, c->RHS.p, c->RHO.p, c->VEL_X.p, c->VEL_Y.p, c->E.p, \
              c->P.p, c->T.p, c->RMACH.p
     auto kern = k::node_update<false, true>;
@@ -785,6 +814,30 @@ static int run_node(cfdb_ctx* c, cudaStream_t st, bool ale, bool update, double 
     else if (!update) kern = k::node_update<false, false>;
     LAUNCH_ON(st, K_NODE, kern, G, B, ARGS);
 #undef ARGS
+    return 0;
+}
+
+// tile-fused stage: element contributions -> shared memory -> interior nodes updated in the same kernel; the
+// tile-boundary nodes (about a quarter) go through the staging buffer and node_update over a node list
+static int run_stage_tile(cfdb_ctx* c, const k::Gas& g, const double* dtl_arr, const double* dtl_sc, double rk_fact) {
+    const bool visc = g.mu_ref > 2.2250738585072014e-308;
+    const int smem = 12 * 512 * (int)sizeof(double);
+    auto kern = visc ? k::stage_tile<true, 3> : k::stage_tile<false, 3>;
+    static bool attr_done[2] = {false, false};
+    if (!attr_done[visc]) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_done[visc] = true;
+    }
+    cudaEvent_t _a = nullptr, _b = nullptr;
+    TRY(prof_begin(c, c->st, K_CALCRHS, &_a, &_b));
+    kern<<<c->ntiles, 128, smem, c->st>>>(c->ntiles, c->nelem, c->tile_elems.p, c->ebmask.p, c->tnode_ptr.p, c->tnodes.p,
+                                         c->d_esup2.p, c->tslot.p, c->inp.p, c->U.p, c->T.p, c->dNx.p, c->dNy.p, c->area.p,
+                                         c->SHOC.p, dtl_arr, dtl_sc, c->TS1.p, c->TS2.p, c->TS3.p, g, c->EC.p, c->U.p, c->M.p,
+                                         c->GAMM.p, c->W_X.p, c->W_Y.p, c->bcflag.p, bctab(c), rk_fact, c->par.FR, c->U1.p,
+                                         c->RHS.p, c->RHO.p, c->VEL_X.p, c->VEL_Y.p, c->E.p, c->P.p, c->T.p, c->RMACH.p);
+    CK(cudaGetLastError());
+    TRY(prof_end(c, c->st, K_CALCRHS, _a, _b));
+    TRY(run_node(c, c->st, false, true, rk_fact, 0, c->nbnodes, c->bnodes.p));
     return 0;
 }
 
@@ -816,6 +869,11 @@ extern "C" int cfdb_rk_stage(cfdb_ctx* c, int32_t irk) {
     k::Gas g{p.FCv, p.FK, p.FMU, p.GAMA, p.T_inf, p.CTE};
     const double* dtl_arr = p.ITLOCAL != 0 ? c->DTL.p : nullptr;
     const int nch = (int)c->chunk_ev.size();
+    if (c->tile_ok && !c->ale && !c->use_cuarto && !c->true_rk && nch <= 1) {
+        TRY(run_stage_tile(c, g, dtl_arr, &c->sc->DTMIN, RK_FACT));
+        TRY(halo_state(c));
+        return 0;
+    }
     if (nch <= 1) {
         TRY(run_calcrhs_elem(c, g, c->use_cuarto != 0, c->ale, dtl_arr, &c->sc->DTMIN));
         TRY(run_node(c, c->st, c->ale, true, RK_FACT));
@@ -1288,6 +1346,7 @@ extern "C" int cfdb_get_scalar(cfdb_ctx* c, const char* name, double* v) {
     else if (n == "FX1") *v = s.FX[0];
     else if (n == "FY1") *v = s.FY[0];
     else if (n == "RM1") *v = s.RM[0];
+    else if (n == "tile_interior") *v = c->tile_ok ? c->tile_interior : 0.0;
     else if (n == "n_m") {
         vector<int> wv(c->nwn);
         if (c->nwn) CK(cudaMemcpy(wv.data(), c->wn_valid.p, c->nwn * sizeof(int), cudaMemcpyDeviceToHost));

@@ -694,37 +694,15 @@ struct BcTab {
     const int* wn_valid;
 };
 
-template <bool ALE, bool UPDATE>
-__global__ void __launch_bounds__(256) node_update(int n0, int n1, const int* __restrict__ esup2, const int* __restrict__ eslot,
-                                                    const double* __restrict__ EC, const double* __restrict__ FC,
-                                                    const double* __restrict__ U, const double* __restrict__ M,
-                                                    const double* __restrict__ GAMM, const double* __restrict__ WXa,
-                                                    const double* __restrict__ WYa, const unsigned char* __restrict__ bcflag,
-                                                    BcTab bc, double rk_fact, double FR, double* __restrict__ U1,
-                                                    double* __restrict__ RHS, double* __restrict__ RHO,
-                                                    double* __restrict__ VELX, double* __restrict__ VELY,
-                                                    double* __restrict__ Ea, double* __restrict__ Pa,
-                                                    double* __restrict__ Ta, double* __restrict__ RMACH) {
-    int n = n0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= n1) return;
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    const int k0 = esup2[n], k1 = esup2[n + 1];
-    for (int k = k0; k < k1; ++k) {
-        double c[4];
-        ld4(EC + 4 * (size_t)eslot[k], c);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acc[i] = acc[i] + c[i];
-    }
-    if (ALE) {
-        for (int k = k0; k < k1; ++k) {
-            double c[4];
-            ld4(FC + 4 * (size_t)eslot[k], c);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i] = acc[i] + c[i];
-        }
-    }
-    st4(RHS + 4 * (size_t)n, acc);
-    if (!UPDATE) return;
+// The nodal chain of RK after the ordered sum (subrutinas.f90:695-826): U1 = U - rk/M*RHS, primitives, fixvel ->
+// normalvel -> FIX, conservative.  Shared by node_update and the tile-fused stage kernel.
+__device__ __forceinline__ void node_finish(int n, const double (&acc)[4], const double* __restrict__ U,
+                                            const double* __restrict__ M, const double* __restrict__ GAMM,
+                                            const double* __restrict__ WXa, const double* __restrict__ WYa,
+                                            const unsigned char* __restrict__ bcflag, const BcTab& bc, double rk_fact,
+                                            double FR, double* __restrict__ U1, double* __restrict__ RHO,
+                                            double* __restrict__ VELX, double* __restrict__ VELY, double* __restrict__ Ea,
+                                            double* __restrict__ Pa, double* __restrict__ Ta, double* __restrict__ RMACH) {
     double u[4];
     ld4(U + 4 * (size_t)n, u);
     double f = rk_fact / M[n];
@@ -769,6 +747,41 @@ __global__ void __launch_bounds__(256) node_update(int n0, int n1, const int* __
     RHO[n] = rho; VELX[n] = vx; VELY[n] = vy; Ea[n] = en; Pa[n] = p; Ta[n] = t; RMACH[n] = mach;
 }
 
+template <bool ALE, bool UPDATE>
+__global__ void __launch_bounds__(256) node_update(int n0, int n1, const int* __restrict__ nlist, const int* __restrict__ esup2, const int* __restrict__ eslot,
+                                                    const double* __restrict__ EC, const double* __restrict__ FC,
+                                                    const double* __restrict__ U, const double* __restrict__ M,
+                                                    const double* __restrict__ GAMM, const double* __restrict__ WXa,
+                                                    const double* __restrict__ WYa, const unsigned char* __restrict__ bcflag,
+                                                    BcTab bc, double rk_fact, double FR, double* __restrict__ U1,
+                                                    double* __restrict__ RHS, double* __restrict__ RHO,
+                                                    double* __restrict__ VELX, double* __restrict__ VELY,
+                                                    double* __restrict__ Ea, double* __restrict__ Pa,
+                                                    double* __restrict__ Ta, double* __restrict__ RMACH) {
+    int n = n0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n1) return;
+    if (nlist) n = nlist[n];  // [n0,n1) indexes a node list (the tile-boundary nodes of the fused stage)
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    const int k0 = esup2[n], k1 = esup2[n + 1];
+    for (int k = k0; k < k1; ++k) {
+        double c[4];
+        ld4(EC + 4 * (size_t)eslot[k], c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = acc[i] + c[i];
+    }
+    if (ALE) {
+        for (int k = k0; k < k1; ++k) {
+            double c[4];
+            ld4(FC + 4 * (size_t)eslot[k], c);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = acc[i] + c[i];
+        }
+    }
+    st4(RHS + 4 * (size_t)n, acc);
+    if (!UPDATE) return;
+    node_finish(n, acc, U, M, GAMM, WXa, WYa, bcflag, bc, rk_fact, FR, U1, RHO, VELX, VELY, Ea, Pa, Ta, RMACH);
+}
+
 // rhs_out = ((rhs_in + c1) + c2) + ... in ascending element order (call-site mode of calcRHS / FUENTE, whose
 // rhs argument is inout)
 __global__ void __launch_bounds__(256) node_accumulate(int npoin, const int* __restrict__ esup2, const int* __restrict__ eslot,
@@ -785,6 +798,91 @@ __global__ void __launch_bounds__(256) node_accumulate(int npoin, const int* __r
         for (int i = 0; i < 4; ++i) acc[i] = acc[i] + c[i];
     }
     st4(rhs_out + 4 * (size_t)n, acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tile-fused RK stage (fixed meshes): one CTA per tile of 512 elements (a spatially compact set chosen on the host).
+// Phase 1 computes the tile's element contributions into shared memory (48 KB, [12][512] so the stores are
+// conflict-free); contributions to nodes shared with other tiles also go to the global staging buffer.  Phase 2
+// sums, for every node all of whose elements lie in this tile (~3/4 of the nodes), its contributions from shared
+// memory in ascending ORIGINAL element order and runs the nodal chain.  Only the tile-boundary nodes take the
+// two-kernel route (node_update over a node list).  Same arithmetic, same summation order: same bits; what changes
+// is that ~3/4 of the staging traffic (96 B/element written + read) never reaches HBM.
+template <bool VISC, int MINB>
+__global__ void __launch_bounds__(128, MINB) stage_tile(int ntiles, int nelem, const int* __restrict__ tile_elems,
+                                                         const unsigned char* __restrict__ ebmask, const int* __restrict__ tnode_ptr,
+                                                         const int* __restrict__ tnodes, const int* __restrict__ esup2,
+                                                         const unsigned short* __restrict__ tslot, const int* __restrict__ inp,
+                                                         const double* __restrict__ Usrc, const double* __restrict__ T,
+                                                         const double* __restrict__ dNx, const double* __restrict__ dNy,
+                                                         const double* __restrict__ area, const double* __restrict__ shoc,
+                                                         const double* __restrict__ dtl_arr, const double* __restrict__ dtl_sc,
+                                                         const double* __restrict__ ts1, const double* __restrict__ ts2,
+                                                         const double* __restrict__ ts3, Gas g, double* __restrict__ EC,
+                                                         const double* __restrict__ U, const double* __restrict__ M,
+                                                         const double* __restrict__ GAMM, const double* __restrict__ WXa,
+                                                         const double* __restrict__ WYa, const unsigned char* __restrict__ bcflag,
+                                                         BcTab bc, double rk_fact, double FR, double* __restrict__ U1,
+                                                         double* __restrict__ RHS, double* __restrict__ RHO, double* __restrict__ VELX,
+                                                         double* __restrict__ VELY, double* __restrict__ Ea, double* __restrict__ Pa,
+                                                         double* __restrict__ Ta, double* __restrict__ RMACH) {
+    extern __shared__ double sm[];  // [12][512]
+    const int t = blockIdx.x;
+    if (t >= ntiles) return;
+    const size_t NE = (size_t)nelem;
+    const double dtl_uniform = dtl_arr ? 0.0 : *dtl_sc;
+    // element ids and connectivity of all four rounds up front: takes two levels out of every round's load chain
+    int ea[4], ipa[4][3];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) ea[r] = tile_elems[(size_t)t * 512 + r * 128 + threadIdx.x];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int e = ea[r] < 0 ? 0 : ea[r];
+        ipa[r][0] = inp[e]; ipa[r][1] = inp[NE + e]; ipa[r][2] = inp[2 * NE + e];
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int k = r * 128 + threadIdx.x;
+        const int e = ea[r];
+        if (e < 0) continue;
+        int ip[3] = {ipa[r][0], ipa[r][1], ipa[r][2]};
+        double Nx[3] = {dNx[e], dNx[NE + e], dNx[2 * NE + e]};
+        double Ny[3] = {dNy[e], dNy[NE + e], dNy[2 * NE + e]};
+        double Un[3][4], Th[3][4], Tn[3] = {0.0, 0.0, 0.0};
+        ld4(Usrc + 4 * (size_t)ip[0], Un[0]);
+        ld4(Usrc + 4 * (size_t)ip[1], Un[1]);
+        ld4(Usrc + 4 * (size_t)ip[2], Un[2]);
+        if (VISC) { Tn[0] = T[ip[0]]; Tn[1] = T[ip[1]]; Tn[2] = T[ip[2]]; }
+        const double tau[3] = {ts1[e], ts2[e], ts3[e]};
+        const double dtl = dtl_arr ? dtl_arr[e] : dtl_uniform;
+        const double ar = area[e];
+        double Ux[4], Uy[4], rt[3][4];
+        calcrhs_body<VISC, false>(g, Un, Th, Tn, Nx, Ny, tau, shoc[e], Ux, Uy, rt);
+        const unsigned mask = ebmask[(size_t)t * 512 + k];
+#pragma unroll
+        for (int n = 0; n < 3; ++n) {
+            double v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                v[i] = ex::div3(rt[n][i] * ar * dtl);
+                sm[(n * 4 + i) * 512 + k] = v[i];
+            }
+            if (mask & (1u << n)) st4(EC + 12 * (size_t)e + 4 * n, v);
+        }
+    }
+    __syncthreads();
+    for (int j = tnode_ptr[t] + threadIdx.x; j < tnode_ptr[t + 1]; j += 128) {
+        const int n = tnodes[j];
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int q = esup2[n]; q < esup2[n + 1]; ++q) {
+            const int slot = tslot[q];  // 3*position-in-tile + local node
+            const int lp = slot / 3, ln = slot - 3 * lp;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = acc[i] + sm[(ln * 4 + i) * 512 + lp];
+        }
+        st4(RHS + 4 * (size_t)n, acc);
+        node_finish(n, acc, U, M, GAMM, WXa, WYa, bcflag, bc, rk_fact, FR, U1, RHO, VELX, VELY, Ea, Pa, Ta, RMACH);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
