@@ -1042,8 +1042,10 @@ extern "C" int cfdb_fluid_structure(cfdb_ctx* c, double dtmin, double time) {
     CK(cudaSetDevice(c->device));
     const int P = c->npoin;
     (void)dtmin;  // W = XPOS/DTMIN uses the device-resident DTMIN (same value)
-    CK(cudaMemsetAsync(c->dxpos.p, 0, P * sizeof(double), c->st));
-    CK(cudaMemsetAsync(c->dypos.p, 0, P * sizeof(double), c->st));
+    if (c->nse) {  // DXPOS = DYPOS = 0 (meshMove.f90:51-52): without body sets nothing ever writes them (zeroed at create)
+        CK(cudaMemsetAsync(c->dxpos.p, 0, P * sizeof(double), c->st));
+        CK(cudaMemsetAsync(c->dypos.p, 0, P * sizeof(double), c->st));
+    }
     // XREF(2)=1.4, YREF(2)=0 are overwritten on every call (meshMove.f90:58): applied once in cfdb_create
     if (c->nset || c->nranks > 1) {  // every rank joins the all-reduce, with or without body edges of its own
         CK(cudaMemsetAsync(c->sc->FX, 0, 30 * sizeof(double), c->st));
@@ -1064,7 +1066,7 @@ extern "C" int cfdb_fluid_structure(cfdb_ctx* c, double dtmin, double time) {
         double* pos = dir ? c->ypos.p : c->xpos.p;
         if (c->nnmove)
             LAUNCH(K_MOVE, k::pos_aux_fill, grid_for(c->nnmove, 128), 128, c->nmove, c->nnmove, c->ilaux.p, dpos, c->pos_aux.p);
-        CK(cudaMemsetAsync(c->bb.p, 0, P * sizeof(double), c->st));
+        // B = 0 (meshMove.f90:91-95, :113-117): bb is zeroed at create and never written by anything else
         TRY(bicg_dev(c, c->lap_sparse.p, c->d_lap_idx.p, c->d_lap_rowptr.p, c->lap_diag.p, pos, c->bb.p, c->pos_aux.p,
                      c->ilaux.p, c->ilaux_last.p, P, c->nnmove, &c->bicg_iters[dir]));
         LAUNCH(K_MOVE, k::move_apply, grid_for(P, 256), 256, P, pos, &c->sc->DTMIN, dir ? c->Y.p : c->X.p,
@@ -1308,7 +1310,7 @@ extern "C" int cfdb_set(cfdb_ctx* c, const char* name, const void* host, int64_t
     Field f;
     std::string n(name);
     if (!find_field(c, n, f)) return fail("cfdb_set: unknown field " + n);
-    if (f.kind >= 2) return fail("cfdb_set: field " + n + " is read-only");
+    if (f.kind >= 2 || n == "dxpos" || n == "dypos") return fail("cfdb_set: field " + n + " is read-only");
     if (count != f.count) return fail("cfdb_set: wrong element count for " + n);
     if (f.kind == 0) {
         if (f.count) CK(cudaMemcpyAsync(f.dev, host, f.count * sizeof(double), cudaMemcpyHostToDevice, c->st));
