@@ -156,6 +156,7 @@ def main():
     ap.add_argument("--n", type=int, default=2829, help="lattice nodes per side per GPU (2829 -> 16.0 M triangles)")
     ap.add_argument("--ref-n", type=int, default=1415, help="lattice of the bounded CPU sample (1415 -> 4.0 M triangles)")
     ap.add_argument("--cpu-steps", type=int, default=20)
+    ap.add_argument("--strong", action="store_true", help="strong scaling (BASELINE configs[3]): one n x n domain cut into N strips")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -189,12 +190,20 @@ def main():
     from cfd_b200 import partition
     from cfd_b200.dist import make_rank_solver
 
-    win = partition.square_window(args.n, world, rank, IPRINT=10**9, MAXITER=10**9)
+    rows_per = None
+    if args.strong:
+        if (args.n - 1) % world:
+            raise SystemExit("--strong needs (n-1) divisible by the number of GPUs")
+        rows_per = (args.n - 1) // world
+    win = partition.square_window(args.n, world, rank, rows_per=rows_per, IPRINT=10**9, MAXITER=10**9)
     g, part = make_rank_solver(win, rank, world, local, dist if world > 1 else None)
     lc = part.lc
-    E = 2 * (args.n - 1) ** 2          # elements of this rank's own range (global elements / world)
+    E = 2 * (args.n - 1) * (rows_per if args.strong else args.n - 1)   # elements of this rank's own range
     P = part.n_owned
-    bump = meshgen.density_bump(lc, x0=0.5, y0=0.5, sigma=0.15, period_y=1.0)  # one bump per strip
+    if args.strong:
+        bump = meshgen.density_bump(lc, x0=0.5, y0=0.5, sigma=0.15)    # one bump in the middle of the fixed domain
+    else:
+        bump = meshgen.density_bump(lc, x0=0.5, y0=0.5, sigma=0.15, period_y=1.0)  # one bump per strip
     for k, v in bump.items():
         g.set(k, v)
     t_gen = time.perf_counter() - t_gen
@@ -307,7 +316,7 @@ def main():
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"square16M: {E}-triangle / {P}-node jittered-lattice Delaunay-diagonal strip per GPU "
                                    "(BASELINE configs[4]; the mesh north_star's target is stated on), Euler, fixed mesh, "

@@ -236,12 +236,15 @@ def _rows_lattice(nx, j0, j1, ny_total, jitter, seed):
     return x, y
 
 
-def square_rows(n, nranks, rank, mach=0.5, jitter=0.3, seed=12345, name="square", all_rows=False, **kw):
-    """Window (own quad rows +-1) of the `nranks`-strip square mesh; returns (RawCase, first global row)."""
+def square_rows(n, nranks, rank, mach=0.5, jitter=0.3, seed=12345, name="square", all_rows=False, rows_per=None, **kw):
+    """Window (own quad rows +-1) of the `nranks`-strip square mesh; returns (RawCase, first global row).
+    Each strip has n nodes per row and `rows_per` quad rows (default n-1: weak scaling, one n x n lattice per rank;
+    strong scaling passes rows_per = (n-1)/nranks so that the whole domain stays n x n)."""
     nx = n
-    ny_total = nranks * (n - 1) + 1
-    j0 = 0 if all_rows else max(0, rank * (n - 1) - 1)
-    j1 = ny_total - 1 if all_rows else min(ny_total - 1, (rank + 1) * (n - 1) + 1)
+    rows_per = (n - 1) if rows_per is None else rows_per
+    ny_total = nranks * rows_per + 1
+    j0 = 0 if all_rows else max(0, rank * rows_per - 1)
+    j1 = ny_total - 1 if all_rows else min(ny_total - 1, (rank + 1) * rows_per + 1)
     x, y = _rows_lattice(nx, j0, j1, ny_total, jitter, seed)
     nrows = j1 - j0 + 1
     inpoel = _triangulate(x, y, nx, nrows)
@@ -262,6 +265,6 @@ def square_rows(n, nranks, rank, mach=0.5, jitter=0.3, seed=12345, name="square"
     return raw, j0
 
 
-def square_global(n, nranks, **kw):
+def square_global(n, nranks, rows_per=None, **kw):
     """The whole `nranks`-strip square mesh in one piece (tests; small sizes)."""
-    return square_rows(n, nranks, 0, all_rows=True, **kw)[0]
+    return square_rows(n, nranks, 0, all_rows=True, rows_per=rows_per, **kw)[0]

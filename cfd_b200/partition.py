@@ -155,7 +155,7 @@ def build_local(lc: LoadedCase, nranks: int, rank: int, elem_rank: np.ndarray | 
                      n_owned=int(n_owned), elem_own=(elem_rank[loc_el] == rank), neighbors=neighbors, send=send, recv=recv)
 
 
-def square_window(n: int, nranks: int, rank: int, **kw):
+def square_window(n: int, nranks: int, rank: int, rows_per: int | None = None, **kw):
     """Weak-scaling bench mesh: rank's window of the global `nranks`-strip square mesh (each strip is the
     n x n lattice of meshgen.square, stacked in y), generated without building the global mesh.
 
@@ -165,11 +165,11 @@ def square_window(n: int, nranks: int, rank: int, **kw):
     """
     from . import deck, meshgen
 
-    raw, j0 = meshgen.square_rows(n, nranks, rank, **kw)
+    raw, j0 = meshgen.square_rows(n, nranks, rank, rows_per=rows_per, **kw)
     lc = deck.load(raw)
     nx = n
     nqx = nx - 1
-    rows_per = n - 1                                       # quad rows per rank
+    rows_per = (n - 1) if rows_per is None else rows_per  # quad rows per rank
     qrow = (np.arange(lc.nelem) // (2 * nqx)) + j0        # global quad row of each window element
     elem_rank = np.minimum(qrow // rows_per, nranks - 1)
     elem_gid = 2 * nqx * j0 + np.arange(lc.nelem, dtype=np.int64)
