@@ -7,7 +7,7 @@ Workload (N=1 and per GPU for N>1, weak scaling): BASELINE.json configs[4] — a
 jittered-lattice Delaunay-diagonal unit-square mesh per GPU, the mesh north_star's target is stated
 on (configs[1], the 1 M wedge, fits in L2 and is a parity-test case, see tests/).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--n LATTICE] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--lattice N] [--strong] [--impl reference]
 
 Prints ONE JSON line (rank 0).  Keys: value (device-resident throughput, CUDA events on the
 library's stream, max over ranks), e2e (same step through the C ABI with host buffers: pinned
@@ -153,7 +153,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--n", type=int, default=2829, help="lattice nodes per side per GPU (2829 -> 16.0 M triangles)")
+    ap.add_argument("--lattice", "--n", dest="n", type=int, default=2829, help="lattice nodes per side per GPU (2829 -> 16.0 M triangles)")
     ap.add_argument("--ref-n", type=int, default=1415, help="lattice of the bounded CPU sample (1415 -> 4.0 M triangles)")
     ap.add_argument("--cpu-steps", type=int, default=20)
     ap.add_argument("--strong", action="store_true", help="strong scaling (BASELINE configs[3]): one n x n domain cut into N strips")
