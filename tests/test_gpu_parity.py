@@ -385,3 +385,21 @@ def test_restart_file_resumes_state(cases, tmp_path):
     assert not h.get("VEL_X").any()          # the reference does not restore velocities
     h.step(1)
     assert np.isfinite(h.get("U")).all()
+
+
+@pytest.mark.parametrize("env", ["CFDB_STAGE_OVERLAP=1", "CFDB_CALCRHS_PIPE=3", "CFDB_CALCRHS_PIPE=4", "CFDB_TILE=1", "CFDB_CHUNK=100",
+                                 "CFDB_CHUNK=100,CFDB_CHUNK_SEQ=1", "CFDB_BICG_UNFUSED=1", "CFDB_CALCRHS_MINB=3",
+                                 "CFDB_CALCRHS_MINB=1", "CFDB_ESTAB_MINB=3"])
+def test_optional_paths_bit_exact(env):
+    """Every opt-in code path kept in the library (profiles/r1_experiments.md) produces the same bits as the default."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ)
+    for kv in env.split(","):
+        k, v = kv.split("=")
+        e[k] = v
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "opt_worker.py")], env=e, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "OPT_PATH_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
