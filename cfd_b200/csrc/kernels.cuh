@@ -223,10 +223,6 @@ __global__ void rhs_history(long n, const Scal* sc, const double* __restrict__ R
     double* dst = b == 2 ? R3 : b == 3 ? R2 : R1;
     dst[i] = RHS[i];
 }
-__global__ void fill(int n, double* __restrict__ a, const double* src) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) a[i] = *src;
-}
 __global__ void fill_const(long n, double* __restrict__ a, double v) {
     long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (i < n) a[i] = v;
@@ -964,8 +960,9 @@ __global__ void __launch_bounds__(256) spmv(int npoin, const double* __restrict_
 }
 enum { ALFA_CONST = 0, ALFA_POS = 1, ALFA_NEG = 2, BETA_POS = 3 };
 // z = alfa*x + y  with alfa taken from the device scalars (vecsum, :79)
-__global__ void __launch_bounds__(256) vecsum(int n, int mode, double aconst, const Scal* sc, const double* __restrict__ x,
-                                               const double* __restrict__ y, double* __restrict__ z) {
+// (no __restrict__: biCG calls it in place, z aliasing x or y; each thread touches only its own index)
+__global__ void __launch_bounds__(256) vecsum(int n, int mode, double aconst, const Scal* sc, const double* x, const double* y,
+                                               double* z) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double a = mode == ALFA_CONST ? aconst : mode == ALFA_POS ? sc->alfa : mode == ALFA_NEG ? -sc->alfa : sc->beta;

@@ -427,6 +427,7 @@ static void fuente(double* rhs, const double* U, const double* w_x, const double
 static void cuarto_orden(const double* U, double* U_n, double FR, const double* GAMM, const double* dNx,
                          const double* dNy, const double* area, const double* M, const int* inpoel, int nelem, int npoin) {
     static const double sp[3][3] = {{.5, .5, 0.0}, {0.0, .5, .5}, {.5, 0.0, .5}};  // sp[c][r] = sp(r+1,c+1) :236-238
+    (void)FR;  // only feeds temp/c (:267-268), which are computed and never used
     for (int i = 0; i < 4 * npoin; ++i) U_n[i] = 0.0;
     for (int ie = 0; ie < nelem; ++ie) {
         const int* ip = inpoel + 3 * ie;
