@@ -6,7 +6,8 @@
 //
 // PARITY UNPINNED: the reference ships no tests, golden vectors or input decks
 // and cannot be compiled here (no Fortran compiler in the image), so this
-// restatement is pinned only by (1) analytic invariants checked in tests/test_oracle_*.py and
+// restatement is pinned only by (0) an independent textbook evaluation of calcRHS/FUENTE/CUARTO_ORDEN
+// (tests/test_oracle_textbook.py), (1) analytic invariants checked in tests/test_oracle_*.py and
 // (2) golden vectors generated from this file itself (tests/golden/, guards refactors).
 //
 // Conventions kept from the Fortran: arrays are column-major, U(4,npoin) = 4 consecutive
