@@ -17,6 +17,19 @@
 
 using std::vector;
 
+namespace fastmode {  // fast.cu: the relaxed stage, compiled with FMA contraction
+int launch_calcrhs_scatter(bool visc, bool ale, cudaStream_t st, int nelem, const int* inp, const double* U, const double* T,
+                           const double* WX, const double* WY, const double* dNx, const double* dNy, const double* area,
+                           const double* shoc, const double* dtl_arr, const double* dtl_sc, const double* ts1, const double* ts2,
+                           const double* ts3, double Cv, double lambda_ref, double mu_ref, double gamma0, double T_inf, double cte,
+                           double* RHS);
+int launch_node_update_rhs(cudaStream_t st, int npoin, const double* RHS, const double* U, const double* M, const double* GAMM,
+                           const double* WX, const double* WY, const unsigned char* bcflag, int nb, const int* bnode,
+                           const int* bkind, const double* bvx, const double* bvy, const double* brho, const double* bT,
+                           const int* bwslot, const double* wnx, const double* wny, const int* wnvalid, double rk_fact, double FR,
+                           double* U1, double* RHO, double* VX, double* VY, double* E, double* P, double* T, double* RMACH);
+}  // namespace fastmode
+
 static thread_local std::string g_err;
 static int fail(const std::string& m) {
     g_err = m;
@@ -116,6 +129,7 @@ struct cfdb_ctx {
     int bicg_iters[2] = {0, 0};
     bool theta_nonzero = false;
     int use_cuarto = 0, true_rk = 0;  // "next" rows N1 / N2, default off (reference behaviour)
+    int fast = 0;                     // relaxed stage (FMA + atomic scatter), opt-in, NOT bit-exact
     bool u1_is_u = false;  // after U = U1 (ns2DComp.ALE.f90:277-281) the two arrays are one buffer
     // tile-fused RK stage (fixed meshes)
     bool tile_ok = false;
@@ -871,6 +885,28 @@ extern "C" int cfdb_rk_stage(cfdb_ctx* c, int32_t irk) {
     k::Gas g{p.FCv, p.FK, p.FMU, p.GAMA, p.T_inf, p.CTE};
     const double* dtl_arr = p.ITLOCAL != 0 ? c->DTL.p : nullptr;
     const int nch = (int)c->chunk_ev.size();
+    if (c->fast && !c->use_cuarto && !c->true_rk) {
+        // relaxed stage: RHS = 0, scatter-add with red.global.add.f64, nodal chain from RHS
+        const bool visc = g.mu_ref > 2.2250738585072014e-308;
+        CK(cudaMemsetAsync(c->RHS.p, 0, 4 * (size_t)c->npoin * sizeof(double), c->st));
+        cudaEvent_t _a = nullptr, _b = nullptr;
+        TRY(prof_begin(c, c->st, K_CALCRHS, &_a, &_b));
+        if (fastmode::launch_calcrhs_scatter(visc, c->ale, c->st, c->nelem, c->inp.p, c->U.p, c->T.p, c->W_X.p, c->W_Y.p, c->dNx.p,
+                                             c->dNy.p, c->area.p, c->SHOC.p, dtl_arr, &c->sc->DTMIN, c->TS1.p, c->TS2.p, c->TS3.p,
+                                             g.Cv, g.lambda_ref, g.mu_ref, g.gamma0, g.T_inf, g.cte, c->RHS.p))
+            return fail("calcrhs_scatter launch failed");
+        TRY(prof_end(c, c->st, K_CALCRHS, _a, _b));
+        TRY(prof_begin(c, c->st, K_NODE, &_a, &_b));
+        k::BcTab b = bctab(c);
+        if (fastmode::launch_node_update_rhs(c->st, c->npoin, c->RHS.p, c->U.p, c->M.p, c->GAMM.p, c->W_X.p, c->W_Y.p, c->bcflag.p,
+                                             b.nb, b.node, b.kind, b.vx, b.vy, b.rho, b.Tfix, b.wslot, b.wn_x, b.wn_y, b.wn_valid,
+                                             RK_FACT, c->par.FR, c->U1.p, c->RHO.p, c->VEL_X.p, c->VEL_Y.p, c->E.p, c->P.p, c->T.p,
+                                             c->RMACH.p))
+            return fail("node_update_rhs launch failed");
+        TRY(prof_end(c, c->st, K_NODE, _a, _b));
+        TRY(halo_state(c));
+        return 0;
+    }
     if (c->tile_ok && !c->ale && !c->use_cuarto && !c->true_rk && nch <= 1) {
         TRY(run_stage_tile(c, g, dtl_arr, &c->sc->DTMIN, RK_FACT));
         TRY(halo_state(c));
@@ -917,7 +953,7 @@ static int run_rk(cfdb_ctx* c) {
     // the same SM residency — so it is opt-in (CFDB_STAGE_OVERLAP=1)
     static const bool no_ovl = getenv("CFDB_STAGE_OVERLAP") == nullptr;
     const bool visc = p.FMU > 2.2250738585072014e-308;
-    if (visc || no_ovl || c->chunk_ev.size() > 1 || c->use_cuarto || c->true_rk) {
+    if (visc || no_ovl || c->chunk_ev.size() > 1 || c->use_cuarto || c->true_rk || c->fast) {
         for (int irk = 1; irk <= 4; ++irk) TRY(cfdb_rk_stage(c, irk));
         return 0;
     }
@@ -1171,7 +1207,8 @@ extern "C" int cfdb_sync(cfdb_ctx* c) {
 }
 extern "C" int cfdb_set_option(cfdb_ctx* c, const char* name, int32_t value) {
     std::string n(name);
-    if (n == "use_cuarto") c->use_cuarto = value;
+    if (n == "fast") c->fast = value;
+    else if (n == "use_cuarto") c->use_cuarto = value;
     else if (n == "true_rk") c->true_rk = value;
     else return fail("cfdb_set_option: unknown option " + n);
     if (c->chunk_ev.size() > 1 && (c->use_cuarto || c->true_rk)) return fail("cfdb_set_option: not available with CFDB_CHUNK");

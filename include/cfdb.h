@@ -87,7 +87,10 @@ int cfdb_get_scalar(cfdb_ctx* ctx, const char* name, double* value); /* TIME DTM
 int cfdb_set_scalar(cfdb_ctx* ctx, const char* name, double value);
 /* switches beyond the reference's behaviour ("next" rows of SURVEY.md §8f), all default 0:
  *   "use_cuarto" 1: keep CUARTO_ORDEN's projection as theta instead of UN = 0.0 (subrutinas.f90:673-674, F7)
- *   "true_rk"    1: RK stages 2..4 evaluate calcRHS/FUENTE at U1 instead of U (subrutinas.f90:685,697, F6) */
+ *   "true_rk"    1: RK stages 2..4 evaluate calcRHS/FUENTE at U1 instead of U (subrutinas.f90:685,697, F6)
+ *   "fast"       1: relaxed stage — FMA contraction and red.global.add.f64 scatter straight into RHS, no staging buffer,
+ *                   summation order undefined.  Agrees with the default to ~1e-15 per call (meets the 1e-11 per-step
+ *                   tolerance) but is NOT bit-exact, so long runs diverge from the reference. */
 int cfdb_set_option(cfdb_ctx* ctx, const char* name, int32_t value);
 /* CUDA stream the context launches on (cudaStream_t as void*), for event timing by the caller */
 void* cfdb_stream(cfdb_ctx* ctx);
