@@ -28,6 +28,10 @@ int launch_node_update_rhs(cudaStream_t st, int npoin, const double* RHS, const 
                            const int* bkind, const double* bvx, const double* bvy, const double* brho, const double* bT,
                            const int* bwslot, const double* wnx, const double* wny, const int* wnvalid, double rk_fact, double FR,
                            double* U1, double* RHO, double* VX, double* VY, double* E, double* P, double* T, double* RMACH);
+int launch_calcrhs_staged_fma(bool visc, cudaStream_t st, int nelem, const int* inp, const double* U, const double* T,
+                              const double* dNx, const double* dNy, const double* area, const double* shoc, const double* dtl_arr,
+                              const double* dtl_sc, const double* ts1, const double* ts2, const double* ts3, double Cv,
+                              double lambda_ref, double mu_ref, double gamma0, double T_inf, double cte, double* EC);
 }  // namespace fastmode
 
 static thread_local std::string g_err;
@@ -805,10 +809,11 @@ static int run_calcrhs_elem(cfdb_ctx* c, const k::Gas& g, bool theta, bool ale, 
     if (minb == 3) { PICK(3) } else if (minb == 4) { PICK(4) } else if (minb == 5) { PICK(5) } else if (minb == 6) { PICK(6) } else if (minb == 2) { PICK(2) } else { PICK(1) }
 #undef PICK
     // experiment: 64-thread CTAs, 7 per SM (<=146 registers, 14 warps/SM)
-    static const bool bs64 = getenv("CFDB_CALCRHS_BS64") != nullptr;
-    if (bs64 && sel == 0) {
-        kern = k::calcrhs_elem<false, false, false, 7, 64>;
-        LAUNCH(K_CALCRHS, kern, grid_for(e1 - e0, 64), 64, ARGS);
+    static const int bs = getenv("CFDB_CALCRHS_BS") ? atoi(getenv("CFDB_CALCRHS_BS")) : 128;
+    if (bs != 128 && sel == 0) {
+        if (bs == 64) { kern = k::calcrhs_elem<false, false, false, 8, 64>; LAUNCH(K_CALCRHS, kern, grid_for(e1 - e0, 64), 64, ARGS); }
+        else if (bs == 32) { kern = k::calcrhs_elem<false, false, false, 16, 32>; LAUNCH(K_CALCRHS, kern, grid_for(e1 - e0, 32), 32, ARGS); }
+        else { kern = k::calcrhs_elem<false, false, false, 2, 256>; LAUNCH(K_CALCRHS, kern, grid_for(e1 - e0, 256), 256, ARGS); }
         return 0;
     }
     LAUNCH(K_CALCRHS, kern, G, B, ARGS);
@@ -885,6 +890,20 @@ extern "C" int cfdb_rk_stage(cfdb_ctx* c, int32_t irk) {
     k::Gas g{p.FCv, p.FK, p.FMU, p.GAMA, p.T_inf, p.CTE};
     const double* dtl_arr = p.ITLOCAL != 0 ? c->DTL.p : nullptr;
     const int nch = (int)c->chunk_ev.size();
+    if (c->fast == 2 && !c->ale && !c->use_cuarto && !c->true_rk) {
+        // measurement only: the staged element kernel compiled with FMA contraction + the exact ordered node kernel
+        const bool visc = g.mu_ref > 2.2250738585072014e-308;
+        cudaEvent_t _a = nullptr, _b = nullptr;
+        TRY(prof_begin(c, c->st, K_CALCRHS, &_a, &_b));
+        if (fastmode::launch_calcrhs_staged_fma(visc, c->st, c->nelem, c->inp.p, c->U.p, c->T.p, c->dNx.p, c->dNy.p, c->area.p,
+                                                c->SHOC.p, dtl_arr, &c->sc->DTMIN, c->TS1.p, c->TS2.p, c->TS3.p, g.Cv, g.lambda_ref,
+                                                g.mu_ref, g.gamma0, g.T_inf, g.cte, c->EC.p))
+            return fail("calcrhs_staged_fma launch failed");
+        TRY(prof_end(c, c->st, K_CALCRHS, _a, _b));
+        TRY(run_node(c, c->st, false, true, RK_FACT));
+        TRY(halo_state(c));
+        return 0;
+    }
     if (c->fast && !c->use_cuarto && !c->true_rk) {
         // relaxed stage: RHS = 0, scatter-add with red.global.add.f64, nodal chain from RHS
         const bool visc = g.mu_ref > 2.2250738585072014e-308;

@@ -20,6 +20,18 @@ int launch_calcrhs_scatter(bool visc, bool ale, cudaStream_t st, int nelem, cons
     return (int)cudaGetLastError();
 }
 
+// the staged element kernel of the exact path, but compiled with FMA contraction (measurement of what -fmad=false costs)
+int launch_calcrhs_staged_fma(bool visc, cudaStream_t st, int nelem, const int* inp, const double* U, const double* T,
+                              const double* dNx, const double* dNy, const double* area, const double* shoc, const double* dtl_arr,
+                              const double* dtl_sc, const double* ts1, const double* ts2, const double* ts3, double Cv,
+                              double lambda_ref, double mu_ref, double gamma0, double T_inf, double cte, double* EC) {
+    kfast::Gas g{Cv, lambda_ref, mu_ref, gamma0, T_inf, cte};
+    const int B = 128, G = (nelem + B - 1) / B;
+    if (visc) kfast::calcrhs_elem<true, false, false, 4><<<G, B, 0, st>>>(0, nelem, nelem, inp, U, nullptr, T, nullptr, nullptr, dNx, dNy, area, shoc, dtl_arr, dtl_sc, ts1, ts2, ts3, g, EC, nullptr);
+    else kfast::calcrhs_elem<false, false, false, 4><<<G, B, 0, st>>>(0, nelem, nelem, inp, U, nullptr, T, nullptr, nullptr, dNx, dNy, area, shoc, dtl_arr, dtl_sc, ts1, ts2, ts3, g, EC, nullptr);
+    return (int)cudaGetLastError();
+}
+
 int launch_node_update_rhs(cudaStream_t st, int npoin, const double* RHS, const double* U, const double* M, const double* GAMM,
                            const double* WX, const double* WY, const unsigned char* bcflag, int nb, const int* bnode,
                            const int* bkind, const double* bvx, const double* bvy, const double* brho, const double* bT,

@@ -14,7 +14,7 @@ if len(sys.argv) > 2 and sys.argv[2] == "visc":
 lc = deck.load(meshgen.square(n=n, IPRINT=10**9, MAXITER=10**9, **kw))
 g = NSComp2D(lc)
 if os.environ.get("FAST"):
-    g.set_option("fast", 1)
+    g.set_option("fast", int(os.environ["FAST"]))
 for k, v in meshgen.density_bump(lc).items():
     g.set(k, v)
 g.step(3)
