@@ -1,0 +1,138 @@
+"""Generate tests/golden/ref_*.npz by EXECUTING THE REFERENCE'S OWN FORTRAN SOURCES (read from /root/reference at
+generation time, never copied) with oracle/f90ref -- a Fortran-subset translator written for this purpose, because no
+Fortran compiler exists in the image.  What runs is `PROGRAM NSComp2D` itself: readInputData and
+loadMeshData on a deck written by cfd_b200.deck.write_deck, RESTART (free stream), smoothing, NORMALES, DERIV, MASAS,
+laplace, then MAXITER passes of the time loop (DELTAT, the dt logic, RK with CUARTO_ORDEN/ESTAB/calcRHS/FUENTE/
+FIXVEL/NORMALVEL/FIX, fluidStructure with FORCES/TRANSF/biCG, the residual norms, the MOVING geometry refresh).
+
+These vectors are what pins the oracle (and through it the CUDA path) to the reference:
+    python tests/golden/make_golden_ref.py          # needs /root/reference; a few seconds per case
+
+Two things are injected, both stated in DESIGN.md section 3:
+  * an initial density bump, written into U/T right after RESTART returns (the reference starts from uniform free stream;
+    the bump makes every term of calcRHS non-trivial from step 1);
+  * for the moving-mesh case only, biCG's `vecdot` is evaluated in the build's canonical summation order: it is the one
+    place where the reference leaves the order to OpenMP (`reduction(+:res)`, biconjGrad.f90:162).  `ref_ale_seqdot.npz`
+    keeps the same run with the reference's own sequential loop, to show the difference is round-off.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+from cfd_b200 import deck, meshgen  # noqa: E402
+
+
+def _noslip():
+    """viscous channel with a no-slip lower wall (single-precision TWALL, F11), a fixed-T patch, duplicated list entries"""
+    nx, ny = 21, 9
+    raw = meshgen.channel(nx=nx, ny=ny, FMU=1.8e-5, FK=0.0257, mach=0.6)
+    lower = np.arange(2, nx, dtype=np.int32)
+    raw.wall = raw.wall[~np.isin(raw.wall, lower[4:]).any(1)]
+    raw.fixv = np.concatenate([lower, lower[:3]]).astype(np.int32)
+    top = ((ny - 1) * nx + np.arange(4, 10)).astype(np.int32)
+    raw.fixt = (np.concatenate([top, top[:2]]).astype(np.int32), np.concatenate([np.full(6, 1.1), np.full(2, 0.9)]))
+    raw.fixrho = (np.concatenate([raw.fixrho[0], raw.fixrho[0][:2]]).astype(np.int32),
+                  np.concatenate([raw.fixrho[1], np.array([-1.0, 1.05])]))
+    return raw
+
+
+# name -> (RawCase factory, steps, density bump?, canonical vecdot?)
+CASES = {
+    "ref_channel_visc": (lambda: meshgen.channel(nx=21, ny=9, FMU=1.8e-5, FK=0.0257), 6, True, False),
+    "ref_channel_euler_itlocal": (lambda: meshgen.channel(nx=17, ny=9, ITLOCAL=5), 8, True, False),
+    "ref_channel_noslip": (_noslip, 6, True, False),
+    "ref_wedge": (lambda: meshgen.wedge(nx=25, ny=13, mach=2.5), 6, True, False),
+    "ref_ale": (lambda: meshgen.ale_body(nt=32, nr=8), 5, False, True),
+    "ref_ale_seqdot": (lambda: meshgen.ale_body(nt=32, nr=8), 5, False, False),
+}
+NODE_FIELDS = ["T", "P", "RHO", "E", "RMACH", "VEL_X", "VEL_Y", "W_X", "W_Y", "X", "Y", "M"]
+ELEM_FIELDS = ["SHOC", "T_SUGN1", "T_SUGN2", "T_SUGN3", "area"]
+FIELDS = ["U", "RHS"] + NODE_FIELDS + ELEM_FIELDS + ["dNx", "dNy", "lap_sparse"]
+INT_FIELDS = ["esup1", "esup2", "psup1", "psup2", "lap_idx", "lap_rowptr"]
+
+
+def raw_case(name):
+    raw = CASES[name][0]()
+    raw.IPRINT = 1          # residual norms (and PRINTREST's arguments) every step
+    raw.MAXITER = CASES[name][1]
+    return raw
+
+
+def run_reference(name):
+    """-> dict of arrays in the repo's layouts (Fortran memory order: U as [npoin][4], dNx as [nelem][3])"""
+    from oracle import orclib
+    from oracle.f90ref.refrun import Reference
+
+    raw = raw_case(name)
+    _, steps, bump, canon = CASES[name]
+    lc0 = deck.load(raw)
+    st = meshgen.density_bump(lc0) if bump else None
+    trace = {"dtmin": [], "time": [], "bicg_calls": 0}
+
+    def hook(r):
+        ns = r.ns
+        restart = ns["p___restart"]
+
+        def restart_with_bump(gamm, *a):
+            out = restart(gamm)
+            if st is not None:
+                r.mod("mvariabgen").u[...] = st["U"].T
+                r.mod("mvariables").t[...] = st["T"]
+                r.mod("mvelocidades").vel_x[...] = st["VEL_X"]
+                r.mod("mvelocidades").vel_y[...] = st["VEL_Y"]
+            return out
+
+        ns["p___restart"] = restart_with_bump
+        fs = ns["p_meshmove__fluidstructure"]
+
+        def fs_traced(dtmin, time, *a):
+            trace["dtmin"].append(float(dtmin))
+            trace["time"].append(float(time))
+            return fs(dtmin, time, *a)
+
+        ns["p_meshmove__fluidstructure"] = fs_traced
+        if canon:
+            L = orclib.lib()
+            ns["p_biconjgrad__vecdot"] = lambda n, x, y, *a: np.float64(
+                L.orc_vecdot(int(n), np.ascontiguousarray(x), np.ascontiguousarray(y)))
+
+    ref = Reference()
+    cnv = ref.run_program(raw, hook=hook)
+    g, v, md = ref.mod("mvariabgen"), ref.mod("mvariables"), ref.mod("meshdata")
+    vel, est, lap, pn = ref.mod("mvelocidades"), ref.mod("mestabilizacion"), ref.mod("mlaplace"), ref.mod("pointneighbor")
+    nor = ref.mod("mnormales")
+    out = {
+        "U": g.u.T.ravel(), "RHS": g.rhs.T.ravel(),
+        "T": v.t, "P": v.p, "RHO": v.rho, "E": v.e, "RMACH": v.rmach,
+        "VEL_X": vel.vel_x, "VEL_Y": vel.vel_y, "W_X": vel.w_x, "W_Y": vel.w_y,
+        "X": md.x, "Y": md.y, "M": md.m, "area": md.area, "dNx": md.dnx.ravel(order="F"), "dNy": md.dny.ravel(order="F"),
+        "SHOC": est.shoc, "T_SUGN1": est.t_sugn1, "T_SUGN2": est.t_sugn2, "T_SUGN3": est.t_sugn3,
+        "lap_sparse": lap.lap_sparse, "lap_idx": lap.lap_idx, "lap_rowptr": lap.lap_rowptr,
+        "esup1": pn.esup1, "esup2": pn.esup2, "psup1": pn.psup1, "psup2": pn.psup2,
+        "n_m": np.array([nor.m]), "n_ipoin": nor.n_ipoin[:nor.m], "n_x": nor.n_x[:nor.m], "n_y": nor.n_y[:nor.m],
+        "cnv": np.array([[float(x) for x in rec] for rec in cnv]),
+        "dtmin": np.array(trace["dtmin"]), "time": np.array(trace["time"]),
+        # what readInputData / loadMeshData left in the modules (the deck-reader boundary)
+        "in_ifixv_node": md.ifixv_node, "in_rfixv_valuex": md.rfixv_valuex, "in_rfixv_valuey": md.rfixv_valuey,
+        "in_ifixrho_node": md.ifixrho_node, "in_rfixrho_value": md.rfixrho_value,
+        "in_ifixt_node": md.ifixt_node, "in_rfixt_value": md.rfixt_value, "in_ilaux": md.ilaux if md.ilaux is not None else np.zeros(0, np.int32),
+    }
+    return {k: np.array(a) for k, a in out.items()}
+
+
+def main():
+    from oracle.f90ref import runtime as rt
+    for name in CASES:
+        out = run_reference(name)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print(name, "npoin", out["X"].size, "nelem", out["area"].size, "steps", len(out["dtmin"]), "cnv[-1]", out["cnv"][-1])
+    print("x**1.5/.5/-.5 evaluations:", rt.pow_stats, "(glibc pow differs from the correctly rounded value in that many)")
+
+
+if __name__ == "__main__":
+    main()
