@@ -816,6 +816,19 @@ static int run_calcrhs_elem(cfdb_ctx* c, const k::Gas& g, bool theta, bool ale, 
         else { kern = k::calcrhs_elem<false, false, false, 2, 256>; LAUNCH(K_CALCRHS, kern, grid_for(e1 - e0, 256), 256, ARGS); }
         return 0;
     }
+    // experiment (CFDB_CALCRHS_PAD_KB): unused dynamic shared memory caps the CTAs per SM below what the registers allow,
+    // leaving register-file room for node_update CTAs of the previous stage to be co-resident (CFDB_STAGE_OVERLAP)
+    static const int pad_kb = getenv("CFDB_CALCRHS_PAD_KB") ? atoi(getenv("CFDB_CALCRHS_PAD_KB")) : 0;
+    if (pad_kb > 0) {
+        const int smem = pad_kb * 1024;
+        CK(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        cudaEvent_t _a = nullptr, _b = nullptr;
+        TRY(prof_begin(c, c->st, K_CALCRHS, &_a, &_b));
+        kern<<<G, B, smem, c->st>>>(ARGS);
+        CK(cudaGetLastError());
+        TRY(prof_end(c, c->st, K_CALCRHS, _a, _b));
+        return 0;
+    }
     LAUNCH(K_CALCRHS, kern, G, B, ARGS);
 #undef ARGS
     return 0;

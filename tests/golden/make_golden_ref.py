@@ -49,7 +49,10 @@ CASES = {
     "ref_wedge": (lambda: meshgen.wedge(nx=25, ny=13, mach=2.5), 6, True, False),
     "ref_ale": (lambda: meshgen.ale_body(nt=32, nr=8), 5, False, True),
     "ref_ale_seqdot": (lambda: meshgen.ale_body(nt=32, nr=8), 5, False, False),
+    # 1000 passes of the reference's time loop (about five minutes of interpretation): north_star's long-run tolerance
+    "ref_channel_1000": (lambda: meshgen.channel(nx=17, ny=9, FMU=1.8e-5, FK=0.0257), 1000, True, False),
 }
+IPRINT = {"ref_channel_1000": 100}
 NODE_FIELDS = ["T", "P", "RHO", "E", "RMACH", "VEL_X", "VEL_Y", "W_X", "W_Y", "X", "Y", "M"]
 ELEM_FIELDS = ["SHOC", "T_SUGN1", "T_SUGN2", "T_SUGN3", "area"]
 FIELDS = ["U", "RHS"] + NODE_FIELDS + ELEM_FIELDS + ["dNx", "dNy", "lap_sparse"]
@@ -58,7 +61,7 @@ INT_FIELDS = ["esup1", "esup2", "psup1", "psup2", "lap_idx", "lap_rowptr"]
 
 def raw_case(name):
     raw = CASES[name][0]()
-    raw.IPRINT = 1          # residual norms (and PRINTREST's arguments) every step
+    raw.IPRINT = IPRINT.get(name, 1)          # residual norms every IPRINT steps
     raw.MAXITER = CASES[name][1]
     return raw
 
@@ -127,7 +130,7 @@ def run_reference(name):
 
 def main():
     from oracle.f90ref import runtime as rt
-    for name in CASES:
+    for name in (sys.argv[1:] or CASES):
         out = run_reference(name)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
         print(name, "npoin", out["X"].size, "nelem", out["area"].size, "steps", len(out["dtmin"]), "cnv[-1]", out["cnv"][-1])

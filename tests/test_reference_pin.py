@@ -65,12 +65,14 @@ def run_and_check(make_solver, name, smoother):
         for k, v in st.items():
             s.set(k, v)
     g = gold(name)
-    for it in range(steps):
-        s.step(1)
+    every = mg.IPRINT.get(name, 1)
+    for it in range(0, steps, every):
+        s.step(every)
         # the program's .cnv line: sqrt(ER/ERR) summed sequentially by the reference, canonically here -> round-off
         er, err = s.step_norms() if hasattr(s, "step_norms") else s.norms_last()
-        np.testing.assert_allclose(np.sqrt(er / err), g["cnv"][it, 2:], rtol=1e-12, err_msg=f"{name}: residuals of step {it + 1}")
-        assert s.scalar("DTMIN") == g["dtmin"][it], f"{name}: DTMIN of step {it + 1}"
+        np.testing.assert_allclose(np.sqrt(er / err), g["cnv"][it // every, 2:], rtol=1e-12,
+                                   err_msg=f"{name}: residuals of step {it + every}")
+        assert s.scalar("DTMIN") == g["dtmin"][it + every - 1], f"{name}: DTMIN of step {it + every}"
     check_state(s, g, name)
 
 
