@@ -118,7 +118,9 @@ struct cfdb_ctx {
     DBuf<unsigned char> isfix;
     DBuf<double> bp2;
     DBuf<double> lap_sparse, lap_diag, by, bp, br, bz, bb, xpos, ypos, dxpos, dypos, pos_aux, xref, yref;
-    DBuf<int> ilaux, ilaux_last, se_node, se_set, set_ptr, set_n1, set_n2;
+    DBuf<int> ilaux, ilaux_last, se_node, se_set, set_ptr, set_n1, set_n2, set_el;
+    DBuf<double> fvisc, skin;   // FORCE_VISC: F_VX(10) F_VY(10); SKIN.DAT columns [3][nedges]
+    int nedges = 0;
     // gcl
     DBuf<double> W_x_old, W_y_old, area_old;
     // reductions / scalars
@@ -349,11 +351,13 @@ static int build_bc_tables(cfdb_ctx* c, const cfdb_bc* bc) {
         nset = std::max(nset, bc->iset_id[i]);
     }
     c->nset = nset;
-    vector<int32_t> sptr((size_t)nset + 1, 0), n1, n2, se_node, se_set;
+    vector<int32_t> sptr((size_t)nset + 1, 0), n1, n2, el, se_node, se_set;
     for (int s = 1; s <= nset; ++s) {
         for (int i = 0; i < bc->nsets; ++i)
             if (bc->iset_id[i] == s) {
                 n1.push_back(bc->iset_n1[i] - 1); n2.push_back(bc->iset_n2[i] - 1);
+                if (bc->iset_elem[i] < 0 || bc->iset_elem[i] > c->nelem) return fail("ISET element out of range");
+                el.push_back(bc->iset_elem[i] - 1);   // 0 in a rank-local deck = element not held by this rank -> -1
                 se_node.push_back(bc->iset_n1[i] - 1); se_set.push_back(s - 1);
                 se_node.push_back(bc->iset_n2[i] - 1); se_set.push_back(s - 1);
             }
@@ -361,7 +365,11 @@ static int build_bc_tables(cfdb_ctx* c, const cfdb_bc* bc) {
     }
     c->nse = (int)se_node.size();
     c->ale = c->nse > 0;
-    TRY(upload(c, c->set_ptr, sptr)); TRY(upload(c, c->set_n1, n1)); TRY(upload(c, c->set_n2, n2));
+    TRY(upload(c, c->set_ptr, sptr)); TRY(upload(c, c->set_n1, n1)); TRY(upload(c, c->set_n2, n2)); TRY(upload(c, c->set_el, el));
+    c->nedges = (int)n1.size();
+    TRY(c->fvisc.alloc(20)); TRY(c->skin.alloc(3 * (size_t)std::max(c->nedges, 1)));
+    CK(cudaMemsetAsync(c->fvisc.p, 0, 20 * sizeof(double), c->st));
+    CK(cudaMemsetAsync(c->skin.p, 0, 3 * (size_t)std::max(c->nedges, 1) * sizeof(double), c->st));
     TRY(upload(c, c->se_node, se_node)); TRY(upload(c, c->se_set, se_set));
     return 0;
 }
@@ -515,7 +523,7 @@ extern "C" void cfdb_destroy(cfdb_ctx* c) {
     if (c->st2) cudaStreamDestroy(c->st2);
     for (auto* d : {&c->inp, &c->d_esup2, &c->eslot, &c->d_lap_idx, &c->d_lap_rowptr, &c->wall, &c->wn_node, &c->wn_ptr,
                     &c->wn_edge, &c->wn_valid, &c->bc_node, &c->bc_kind, &c->bc_wslot, &c->ilaux, &c->ilaux_last, &c->se_node,
-                    &c->se_set, &c->set_ptr, &c->set_n1, &c->set_n2, &c->flags})
+                    &c->se_set, &c->set_ptr, &c->set_n1, &c->set_n2, &c->set_el, &c->flags})
         d->release();
     c->lpos.release();
     c->bcflag.release();
@@ -1173,6 +1181,19 @@ extern "C" int cfdb_selftest(cfdb_ctx* c, int32_t which, int64_t n, uint64_t see
     return 0;
 }
 
+// FORCE_VISC (ns2DComp.ALE.f90:819-893) on the current device state; results in the fields F_VX, F_VY, skin, skin_x, skin_p
+extern "C" int cfdb_force_visc(cfdb_ctx* c) {
+    CK(cudaSetDevice(c->device));
+    const cfdb_params& p = c->par;
+    CK(cudaMemsetAsync(c->fvisc.p, 0, 20 * sizeof(double), c->st));  // F_VX = 0; F_VY = 0 (:832)
+    if (c->nset)
+        LAUNCH(K_FORCES, k::force_visc, 1, 32, c->nset, c->n_owned, c->set_ptr.p, c->set_n1.p, c->set_n2.p, c->set_el.p, c->nelem,
+               c->inp.p, c->X.p, c->Y.p, c->P.p, c->T.p, c->VEL_X.p, c->VEL_Y.p, c->dNx.p, c->dNy.p, p.U_inf, p.V_inf, p.RHO_inf,
+               p.T_inf, c->fvisc.p, c->skin.p, c->nedges);
+    if (c->nranks > 1) TRY(allreduce(c, c->fvisc.p, 20, ncclSum));
+    return 0;
+}
+
 extern "C" int cfdb_step_norms(cfdb_ctx* c, double er[4], double err[4]) {
     CK(cudaSetDevice(c->device));
     TRY(read_scal(c));
@@ -1215,6 +1236,7 @@ static int step_once(cfdb_ctx* c) {
     c->iterprint += 1;
     if (c->iterprint == p.IPRINT || c->h_iter == p.MAXITER) {  // :186-197
         TRY(run_norms(c));
+        if (p.FMU != 0.0) TRY(cfdb_force_visc(c));  // :228-233
         c->iterprint = 0;
     }
     LAUNCH(K_SCALAR, k::bandera_inc, 1, 1, c->sc);
@@ -1297,6 +1319,14 @@ static bool find_field(cfdb_ctx* c, const std::string& n, Field& f) {
 #undef FD
 #undef FS
 #undef FH
+    if (n == "FX") { f.dev = c->sc->FX; f.count = 10; f.kind = 0; return true; }
+    if (n == "FY") { f.dev = c->sc->FY; f.count = 10; f.kind = 0; return true; }
+    if (n == "RM") { f.dev = c->sc->RM; f.count = 10; f.kind = 0; return true; }
+    if (n == "F_VX") { f.dev = c->fvisc.p; f.count = 10; f.kind = 0; return true; }
+    if (n == "F_VY") { f.dev = c->fvisc.p + 10; f.count = 10; f.kind = 0; return true; }
+    if (n == "skin") { f.dev = c->skin.p; f.count = c->nedges; f.kind = 0; return true; }
+    if (n == "skin_x") { f.dev = c->skin.p + c->nedges; f.count = c->nedges; f.kind = 0; return true; }
+    if (n == "skin_p") { f.dev = c->skin.p + 2 * (size_t)c->nedges; f.count = c->nedges; f.kind = 0; return true; }
     if (n == "DTL") { f.count = E; f.kind = 3; return true; }
     if (n == "n_ipoin" || n == "n_x" || n == "n_y") { f.count = c->nwn; f.kind = 3; return true; }
     return false;

@@ -1196,6 +1196,57 @@ __global__ void forces(int nset, int n_owned, const int* __restrict__ sptr, cons
     sc->FX[s] = fx; sc->FY[s] = fy; sc->RM[s] = rm;
 }
 
+// FORCE_VISC (ns2DComp.ALE.f90:819-893): traction of the element behind each body-set edge (pressure + viscous stress),
+// summed per set in list order by one thread per set, like FORCES; skin[3][ne] = the three columns of SKIN.DAT.
+__global__ void force_visc(int nset, int n_owned, const int* __restrict__ sptr, const int* __restrict__ n1a, const int* __restrict__ n2a,
+                           const int* __restrict__ ela, int nelem, const int* __restrict__ inp, const double* __restrict__ X,
+                           const double* __restrict__ Y, const double* __restrict__ P, const double* __restrict__ T,
+                           const double* __restrict__ VX, const double* __restrict__ VY, const double* __restrict__ dNx,
+                           const double* __restrict__ dNy, double U_inf, double V_inf, double RHO_inf, double T_inf,
+                           double* __restrict__ fv, double* __restrict__ skin, int ne) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nset) return;
+    double fx = 0.0, fy = 0.0;
+    for (int k = sptr[s]; k < sptr[s + 1]; ++k) {
+        int NN1 = n1a[k], NN2 = n2a[k], IELEM = ela[k];
+        if (NN1 >= n_owned || IELEM < 0) continue;  // multi-rank: an edge belongs to the rank owning its first node
+        double TEMP = (T[NN1] + T[NN2]) / 2.0;
+        double smu = 110.0;
+        double fmu = 0.017 * ex::pow15(TEMP / T_inf) * (T_inf + smu) / (TEMP + smu);
+        double RLY = -(X[NN2] - X[NN1]);
+        double RLX = Y[NN2] - Y[NN1];
+        double RMOD = sqrt(RLX * RLX + RLY * RLY);
+        RLX = RLX / RMOD;
+        RLY = RLY / RMOD;
+        double DUX = 0.0, DUY = 0.0, DVX = 0.0, DVY = 0.0, PRESS = 0.0;
+#pragma unroll
+        for (int JJ = 0; JJ < 3; ++JJ) {
+            int NN = inp[(size_t)JJ * nelem + IELEM];
+            double nx = dNx[(size_t)JJ * nelem + IELEM], ny = dNy[(size_t)JJ * nelem + IELEM];
+            DUX = DUX + nx * VX[NN];
+            DUY = DUY + ny * VX[NN];
+            DVX = DVX + nx * VY[NN];
+            DVY = DVY + ny * VY[NN];
+            PRESS = PRESS + P[NN];
+        }
+        PRESS = PRESS / 3.0;
+        double TXX = -PRESS - fmu * (2.0 / 3.0 * (DUX + DVY) - 2.0 * DUX);
+        double TXY = fmu * (DUY + DVX);
+        double TYX = TXY;
+        double TYY = -PRESS - fmu * (2.0 / 3.0 * (DUX + DVY) - 2.0 * DVY);
+        double TTX = TXX * RLX + TXY * RLY;
+        double TTY = TYX * RLX + TYY * RLY;
+        double TMOD = -TTX * RLY + TTY * RLX;
+        double UU = U_inf * U_inf + V_inf * V_inf;
+        fx = fx + TTX * RMOD;
+        fy = fy + TTY * RMOD;
+        skin[k] = TMOD / (.5 * RHO_inf * UU);
+        skin[ne + k] = (X[NN2] + X[NN1]) / 2.0;
+        skin[2 * ne + k] = PRESS / 82713.27;
+    }
+    fv[s] = fx; fv[10 + s] = fy;
+}
+
 // gcl_mod::main (gcl.f90:29-45) as an ordered node gather; W_x appears twice as written (:38-41)
 __global__ void __launch_bounds__(256) gcl(int npoin, int nelem, const int* __restrict__ esup2, const int* __restrict__ eslot,
                                             const int* __restrict__ inp, const double* __restrict__ dNx,

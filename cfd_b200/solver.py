@@ -102,6 +102,11 @@ class NSComp2D:
         capi.check(self.L.cfdb_residual_norms(self.h, er, err))
         return er, err
 
+    def force_visc(self):
+        """FORCE_VISC (ns2DComp.ALE.f90:819-893) now -> (F_VX(10), F_VY(10), skin, edge mid x, press/82713.27)."""
+        capi.check(self.L.cfdb_force_visc(self.h))
+        return tuple(self.get(n) for n in ("F_VX", "F_VY", "skin", "skin_x", "skin_p"))
+
     def step_norms(self):
         """ER, ERR as evaluated inside the last print step of cfdb_step (before U = U1)."""
         er, err = np.zeros(4), np.zeros(4)

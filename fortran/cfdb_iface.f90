@@ -41,6 +41,9 @@ module cfdb_iface
      function cfdb_step(ctx, nsteps) bind(C, name="cfdb_step") result(rc)
        import; type(c_ptr), value :: ctx; integer(c_int32_t), value :: nsteps; integer(c_int) :: rc
      end function
+     function cfdb_force_visc(ctx) bind(C, name="cfdb_force_visc") result(rc)   ! FORCE_VISC, ns2DComp.ALE.f90:819-893
+       import; type(c_ptr), value :: ctx; integer(c_int) :: rc
+     end function
      function cfdb_get(ctx, name, host, count) bind(C, name="cfdb_get") result(rc)
        import; type(c_ptr), value :: ctx, host; character(kind=c_char) :: name(*)
        integer(c_int64_t), value :: count; integer(c_int) :: rc

@@ -76,6 +76,11 @@ int cfdb_rk_stage(cfdb_ctx* ctx, int32_t irk);               /* body of RK's IRK
 int cfdb_geometry(cfdb_ctx* ctx, int32_t moving_step);       /* NORMALES, DERIV, MASAS[, gcl], laplace */
 int cfdb_fluid_structure(cfdb_ctx* ctx, double dtmin, double time); /* meshMove.f90:28-142 */
 int cfdb_residual_norms(cfdb_ctx* ctx, double er[4], double err[4]); /* ns2DComp.ALE.f90:191-197, evaluated now */
+/* FORCE_VISC (ns2DComp.ALE.f90:819-893; called by the time loop on print steps when FMU /= 0, :228-233): pressure + viscous
+ * traction on the ISET body edges from the resident P, T, VEL_X, VEL_Y, X, Y, dNx, dNy.  Results are the fields
+ * "F_VX"(10), "F_VY"(10) and the SKIN.DAT columns "skin", "skin_x", "skin_p" (one entry per ISET edge, set by set);
+ * FORCES' "FX", "FY", "RM" (10 each, meshMove.f90:153-194) are fields too.  cfdb_step calls it at the same place. */
+int cfdb_force_visc(cfdb_ctx* ctx);
 /* the norms cfdb_step evaluated on its last print step (ITERPRINT==IPRINT or ITER==MAXITER, :186), i.e. before U=U1 */
 int cfdb_step_norms(cfdb_ctx* ctx, double er[4], double err[4]);
 /* field transfer by Fortran variable name ("U","U1","RHS","T","VEL_X","X","inpoel","esup1","lap_idx",...);

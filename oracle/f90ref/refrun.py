@@ -5,7 +5,7 @@
                                            # normales/deriv/masas/laplace, then the time loop, on a deck written to a tmp dir
     ref.mod("mvariabgen").u                # module variables afterwards (Fortran shapes, e.g. U is (4, npoin))
 
-Only the file-output routines PRINTFLAVIA / PRINTREST / FORCE_VISC are replaced by no-ops (their results feed nothing).
+Only the file-output routines PRINTFLAVIA / PRINTREST are replaced by no-ops (their results feed nothing).
 """
 from __future__ import annotations
 
@@ -54,7 +54,7 @@ class Reference:
         self.ns.update(self._orig)      # drop the overrides of an earlier run
         self.ns["IO"].__init__()
         self.ns["_reset"]()
-        for name in ("printflavia", "printrest", "force_visc"):
+        for name in ("printflavia", "printrest"):
             self.ns["p___" + name] = lambda *a, **k: None
 
     def mod(self, name):

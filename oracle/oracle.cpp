@@ -635,6 +635,8 @@ struct Solver {
     vector<double> b, pos_aux, dxpos, dypos, xpos, ypos, by, bp, br, bz;
     double DISN[2] = {0, 0};
     double FX[10], FY[10], RM[10];
+    double F_VX[10] = {0}, F_VY[10] = {0};      // FORCE_VISC
+    vector<double> skin, skin_x, skin_p;       // the three columns of SKIN.DAT, set by set, edge by edge
     // gcl
     vector<double> W_x_old, W_y_old, area_old;
     // loop scalars (ns2DComp.ALE.f90:109-134)
@@ -763,6 +765,59 @@ static void forces(Solver& s) {
     }
 }
 
+// ns2DComp.ALE.f90:819-893  FORCE_VISC: traction (pressure + viscous stress of the adjacent element) on the body-set
+// edges, summed per set in list order; SKIN.DAT columns per edge: skin friction, edge mid x, press/82713.27
+static void force_visc(int nset_numb, const vector<int>* set_n1, const vector<int>* set_n2, const vector<int>* set_el,
+                       const int* inpoel, const double* X, const double* Y, const double* P, const double* T,
+                       const double* VEL_X, const double* VEL_Y, const double* DNX, const double* DNY, double U_inf,
+                       double V_inf, double RHO_inf, double T_inf, double* F_VX, double* F_VY, vector<double>& skin,
+                       vector<double>& skin_x, vector<double>& skin_p) {
+    for (int i = 0; i < 10; ++i) F_VX[i] = F_VY[i] = 0.0;  // :832
+    skin.clear(); skin_x.clear(); skin_p.clear();
+    for (int is = 0; is < nset_numb; ++is)
+        for (size_t ii = 0; ii < set_n1[is].size(); ++ii) {
+            int NN1 = set_n1[is][ii] - 1, NN2 = set_n2[is][ii] - 1, IELEM = set_el[is][ii] - 1;
+            double TEMP = (T[NN1] + T[NN2]) / 2.0;
+            double smu = 110.0;
+            double fmu = 0.017 * pow15(TEMP / T_inf) * (T_inf + smu) / (TEMP + smu);
+            double RLY = -(X[NN2] - X[NN1]);
+            double RLX = Y[NN2] - Y[NN1];
+            double RMOD = std::sqrt(RLX * RLX + RLY * RLY);
+            RLX = RLX / RMOD;
+            RLY = RLY / RMOD;
+            double DUX = 0.0, DUY = 0.0, DVX = 0.0, DVY = 0.0, PRESS = 0.0;
+            for (int JJ = 0; JJ < 3; ++JJ) {
+                int NN = inpoel[3 * IELEM + JJ] - 1;
+                DUX = DUX + DNX[3 * IELEM + JJ] * VEL_X[NN];
+                DUY = DUY + DNY[3 * IELEM + JJ] * VEL_X[NN];
+                DVX = DVX + DNX[3 * IELEM + JJ] * VEL_Y[NN];
+                DVY = DVY + DNY[3 * IELEM + JJ] * VEL_Y[NN];
+                PRESS = PRESS + P[NN];
+            }
+            PRESS = PRESS / 3.0;
+            double TXX = -PRESS - fmu * (2.0 / 3.0 * (DUX + DVY) - 2.0 * DUX);
+            double TXY = fmu * (DUY + DVX);
+            double TYX = TXY;
+            double TYY = -PRESS - fmu * (2.0 / 3.0 * (DUX + DVY) - 2.0 * DVY);
+            double TTX = TXX * RLX + TXY * RLY;
+            double TTY = TYX * RLX + TYY * RLY;
+            double TMOD = -TTX * RLY + TTY * RLX;
+            double UU = U_inf * U_inf + V_inf * V_inf;
+            double SKIN = TMOD / (.5 * RHO_inf * UU);
+            F_VX[is] = F_VX[is] + TTX * RMOD;
+            F_VY[is] = F_VY[is] + TTY * RMOD;
+            skin.push_back(SKIN);
+            skin_x.push_back((X[NN2] + X[NN1]) / 2.0);
+            skin_p.push_back(PRESS / 82713.27);
+        }
+}
+static void force_visc(Solver& s) {
+    const Params& p = s.par;
+    force_visc(s.nset_numb, s.set_n1, s.set_n2, s.set_el, s.inpoel.data(), s.X.data(), s.Y.data(), s.P.data(), s.T.data(),
+               s.VEL_X.data(), s.VEL_Y.data(), s.dNx.data(), s.dNy.data(), p.U_inf, p.V_inf, p.RHO_inf, p.T_inf, s.F_VX,
+               s.F_VY, s.skin, s.skin_x, s.skin_p);
+}
+
 // meshMove.f90:369-392  TRANSF
 static void transf(Solver& s, double ALPHA, double YPOSR) {
     for (int is = 0; is < s.nset_numb; ++is)
@@ -861,7 +916,10 @@ static void step_part3(Solver& s) {
     s.ITERPRINT += 1;
     if (s.ITERPRINT == p.IPRINT || s.ITER == p.MAXITER || s.norms_every_step) {  // :186-197
         residual_norms(s);
-        if (s.ITERPRINT == p.IPRINT || s.ITER == p.MAXITER) s.ITERPRINT = 0;
+        if (s.ITERPRINT == p.IPRINT || s.ITER == p.MAXITER) {
+            if (p.FMU != 0.0) force_visc(s);  // :228-233, print steps only
+            s.ITERPRINT = 0;
+        }
     }
     s.BANDERA += 1;
     if (p.MOVING == 1) geometry(s, true);
@@ -1058,6 +1116,7 @@ void orc_step_part3(void* h) { step_part3(*(Solver*)h); }
 void orc_rk_stage(void* h, int irk) { rk_stage(*(Solver*)h, irk, 4); }
 void orc_geometry(void* h, int moving_step) { geometry(*(Solver*)h, moving_step != 0); }
 void orc_fluid_structure(void* h, double dtmin, double time) { fluid_structure(*(Solver*)h, dtmin, time); }
+void orc_force_visc(void* h) { force_visc(*(Solver*)h); }
 void orc_residual_norms(void* h, double* er, double* err) {
     Solver& s = *(Solver*)h;
     residual_norms(s);
@@ -1074,7 +1133,12 @@ int orc_field(void* h, const char* name, void** ptr, long* len) {
     DF(VEL_X) DF(VEL_Y) DF(W_X) DF(W_Y) DF(U) DF(U1) DF(RHS) DF(RHS1) DF(RHS2) DF(RHS3) DF(UN)
     DF(P) DF(T) DF(RHO) DF(E) DF(RMACH) DF(SHOC) DF(T_SUGN1) DF(T_SUGN2) DF(T_SUGN3) DF(GAMM) DF(DTL) DF(DT)
     DF(X1) DF(Y1) DF(lap_sparse) DF(lap_diag) DF(n_x) DF(n_y) DF(xpos) DF(ypos) DF(dxpos) DF(dypos)
-    DF(W_x_old) DF(W_y_old) DF(area_old)
+    DF(W_x_old) DF(W_y_old) DF(area_old) DF(skin) DF(skin_x) DF(skin_p)
+    if (n == "FX") { *ptr = s.FX; *len = 10; return 0; }
+    if (n == "FY") { *ptr = s.FY; *len = 10; return 0; }
+    if (n == "RM") { *ptr = s.RM; *len = 10; return 0; }
+    if (n == "F_VX") { *ptr = s.F_VX; *len = 10; return 0; }
+    if (n == "F_VY") { *ptr = s.F_VY; *len = 10; return 0; }
     IF(inpoel) IF(esup1) IF(esup2) IF(psup1) IF(psup2) IF(lap_idx) IF(lap_rowptr) IF(n_ipoin) IF(ilaux)
 #undef DF
 #undef IF

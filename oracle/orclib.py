@@ -64,6 +64,7 @@ def lib(omp=False):
     L.orc_step_part3.argtypes = [C.c_void_p]
     L.orc_geometry.argtypes = [C.c_void_p, C.c_int]
     L.orc_fluid_structure.argtypes = [C.c_void_p, C.c_double, C.c_double]
+    L.orc_force_visc.argtypes = [C.c_void_p]
     L.orc_residual_norms.argtypes = [C.c_void_p, _dp, _dp]
     L.orc_field.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_long)]
     L.orc_scalar.argtypes = [C.c_void_p, C.c_char_p]
@@ -183,3 +184,8 @@ class Oracle:
         er, err = np.zeros(4), np.zeros(4)
         self.L.orc_residual_norms(self.h, er, err)
         return er, err
+
+    def force_visc(self):
+        """FORCE_VISC on the current state -> (F_VX(10), F_VY(10), skin, edge mid x, press/82713.27)"""
+        self.L.orc_force_visc(self.h)
+        return tuple(self.get(n) for n in ("F_VX", "F_VY", "skin", "skin_x", "skin_p"))

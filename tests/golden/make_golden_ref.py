@@ -49,6 +49,8 @@ CASES = {
     "ref_wedge": (lambda: meshgen.wedge(nx=25, ny=13, mach=2.5), 6, True, False),
     "ref_ale": (lambda: meshgen.ale_body(nt=32, nr=8), 5, False, True),
     "ref_ale_seqdot": (lambda: meshgen.ale_body(nt=32, nr=8), 5, False, False),
+    # viscous moving mesh: FUENTE with W /= 0 next to the viscous terms, FORCES and FORCE_VISC on the body set
+    "ref_ale_visc": (lambda: meshgen.ale_body(nt=32, nr=8, FMU=1.8e-5, FK=0.0257), 4, False, True),
     # 1000 passes of the reference's time loop (about five minutes of interpretation): north_star's long-run tolerance
     "ref_channel_1000": (lambda: meshgen.channel(nx=17, ny=9, FMU=1.8e-5, FK=0.0257), 1000, True, False),
 }
@@ -108,7 +110,8 @@ def run_reference(name):
     cnv = ref.run_program(raw, hook=hook)
     g, v, md = ref.mod("mvariabgen"), ref.mod("mvariables"), ref.mod("meshdata")
     vel, est, lap, pn = ref.mod("mvelocidades"), ref.mod("mestabilizacion"), ref.mod("mlaplace"), ref.mod("pointneighbor")
-    nor = ref.mod("mnormales")
+    nor, mm = ref.mod("mnormales"), ref.mod("meshmove")
+    nedges = int(md.nsets) if float(ref.mod("inputdata").fmu) != 0.0 else 0
     out = {
         "U": g.u.T.ravel(), "RHS": g.rhs.T.ravel(),
         "T": v.t, "P": v.p, "RHO": v.rho, "E": v.e, "RMACH": v.rmach,
@@ -119,6 +122,8 @@ def run_reference(name):
         "esup1": pn.esup1, "esup2": pn.esup2, "psup1": pn.psup1, "psup2": pn.psup2,
         "n_m": np.array([nor.m]), "n_ipoin": nor.n_ipoin[:nor.m], "n_x": nor.n_x[:nor.m], "n_y": nor.n_y[:nor.m],
         "cnv": np.array([[float(x) for x in rec] for rec in cnv]),
+        "FX": mm.fx, "FY": mm.fy, "RM": mm.rm, "F_VX": mm.f_vx, "F_VY": mm.f_vy,
+        "skin": np.array([[float(x) for x in rec] for rec in ref.io.written.get("SKIN.DAT", [])[-nedges:]]).reshape(-1, 3),
         "dtmin": np.array(trace["dtmin"]), "time": np.array(trace["time"]),
         # what readInputData / loadMeshData left in the modules (the deck-reader boundary)
         "in_ifixv_node": md.ifixv_node, "in_rfixv_valuex": md.rfixv_valuex, "in_rfixv_valuey": md.rfixv_valuey,

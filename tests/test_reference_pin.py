@@ -56,6 +56,14 @@ def check_state(solver, g, name, skip=()):
         assert_bit_equal(solver.get("n_x")[:m], g["n_x"], "n_x")
         assert_bit_equal(solver.get("n_y")[:m], g["n_y"], "n_y")
     assert solver.scalar("DTMIN") == g["dtmin"][-1] and solver.scalar("TIME") == g["time"][-1], "DTMIN/TIME"
+    if "FX" in g.files:   # FORCES (meshMove.f90:153-194) and, on viscous print steps, FORCE_VISC (ns2DComp.ALE.f90:819-893)
+        for f in ("FX", "FY", "RM"):
+            assert_bit_equal(solver.get(f), g[f], f"{name}:{f}")
+        if g["skin"].size:
+            for f in ("F_VX", "F_VY"):
+                assert_bit_equal(solver.get(f), g[f], f"{name}:{f}")
+            for k, f in enumerate(("skin", "skin_x", "skin_p")):
+                assert_bit_equal(solver.get(f), g["skin"][:, k], f"{name}:SKIN.DAT column {k + 1}")
 
 
 def run_and_check(make_solver, name, smoother):
