@@ -7,6 +7,7 @@
 
 #include <nccl.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -33,6 +34,11 @@ int launch_calcrhs_staged_fma(bool visc, cudaStream_t st, int nelem, const int* 
                               const double* dtl_sc, const double* ts1, const double* ts2, const double* ts3, double Cv,
                               double lambda_ref, double mu_ref, double gamma0, double T_inf, double cte, double* EC);
 }  // namespace fastmode
+
+namespace topogpu {
+int build(cudaStream_t st, const int* inp, int nelem, int npoin, int* esup2, int* eslot, int* psup2, int** psup1_out,
+          int* npsup_out, int* rowptr, int** idx0_out, unsigned char* lpos, int* maxrow_out);
+}
 
 static thread_local std::string g_err;
 static int fail(const std::string& m) {
@@ -100,7 +106,9 @@ struct cfdb_ctx {
     cfdb_params par{};
     int npoin = 0, nelem = 0;
     // host copies of integer artefacts (API layout: 1-based)
-    vector<int32_t> h_inpoel, esup1, esup2, psup1, psup2, lap_idx, lap_rowptr, h_eslot;
+    vector<int32_t> h_inpoel, esup1, esup2, psup1, psup2, lap_idx, lap_rowptr, h_eslot;   // host mirrors: see ensure_host_topology
+    bool host_topo_valid = true;
+    int npsup = 0;
     vector<int32_t> h_wall, h_wn_node, h_ilaux, h_fixidx_last;
     int nnz = 0, maxrow = 0, nwn = 0, nb = 0, nmove = 0, nnmove = 0, nset = 0, nse = 0;
     bool ale = false;  // mesh can move (body sets present or W set by the caller)
@@ -118,7 +126,7 @@ struct cfdb_ctx {
     DBuf<unsigned char> isfix;
     DBuf<double> bp2;
     DBuf<double> lap_sparse, lap_diag, by, bp, br, bz, bb, xpos, ypos, dxpos, dypos, pos_aux, xref, yref;
-    DBuf<int> ilaux, ilaux_last, se_node, se_set, set_ptr, set_n1, set_n2, set_el;
+    DBuf<int> ilaux, ilaux_last, se_node, se_set, set_ptr, set_n1, set_n2, set_el, d_psup1, d_psup2;
     DBuf<double> fvisc, skin;   // FORCE_VISC: F_VX(10) F_VY(10); SKIN.DAT columns [3][nedges]
     int nedges = 0;
     // gcl
@@ -374,10 +382,39 @@ static int build_bc_tables(cfdb_ctx* c, const cfdb_bc* bc) {
     return 0;
 }
 
+// The device-built topology (topo_gpu.cu) is mirrored into the host vectors only when something asks for it: cfdb_get of
+// esup1/esup2/psup1/psup2/lap_idx/lap_rowptr, the CFDB_CHUNK planner, the CFDB_TILE tiler.
+static int ensure_host_topology(cfdb_ctx* c) {
+    if (c->host_topo_valid) return 0;
+    const size_t P = c->npoin, E = c->nelem;
+    c->esup2.resize(P + 1); c->h_eslot.resize(3 * E); c->psup2.resize(P + 1); c->psup1.resize(c->npsup);
+    c->lap_rowptr.resize(P + 1); c->lap_idx.resize(c->nnz);
+    CK(cudaMemcpyAsync(c->esup2.data(), c->d_esup2.p, (P + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(c->h_eslot.data(), c->eslot.p, 3 * E * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(c->psup2.data(), c->d_psup2.p, (P + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    if (c->npsup) CK(cudaMemcpyAsync(c->psup1.data(), c->d_psup1.p, (size_t)c->npsup * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(c->lap_rowptr.data(), c->d_lap_rowptr.p, (P + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(c->lap_idx.data(), c->d_lap_idx.p, (size_t)c->nnz * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    c->esup1.resize(3 * E);
+    for (size_t k = 0; k < 3 * E; ++k) c->esup1[k] = c->h_eslot[k] / 3 + 1;
+    for (auto& v : c->lap_idx) v += 1;   // host copy is 1-based like the reference's lap_idx
+    c->host_topo_valid = true;
+    return 0;
+}
+
 extern "C" int cfdb_create(cfdb_ctx** out, const cfdb_params* par, int32_t npoin, int32_t nelem, const double* X,
                            const double* Y, const int32_t* inpoel, const cfdb_bc* bc, int device) {
     *out = nullptr;
     int ndev = 0;
+    const bool verbose = getenv("CFDB_VERBOSE") != nullptr;   // phase times of the set-up to stderr
+    auto t_prev = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!verbose) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[cfdb_create] %-28s %8.3f s\n", what, std::chrono::duration<double>(now - t_prev).count());
+        t_prev = now;
+    };
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail("cfdb_create: no CUDA device available (libcfdb200 has no CPU path)");
     if (device < 0 || device >= ndev) return fail("cfdb_create: bad device index");
@@ -387,7 +424,10 @@ extern "C" int cfdb_create(cfdb_ctx** out, const cfdb_params* par, int32_t npoin
     if (npoin < 1 || nelem < 1) return fail("cfdb_create: empty mesh");
     for (size_t k = 0; k < 3 * (size_t)nelem; ++k)
         if (inpoel[k] < 1 || inpoel[k] > npoin) return fail("cfdb_create: inpoel entry out of range");
+    lap("validate inpoel");
     CK(cudaSetDevice(device));
+    CK(cudaFree(nullptr));
+    lap("CUDA context");
     cfdb_ctx* c = new cfdb_ctx();
     c->device = device;
     c->par = *par;
@@ -407,12 +447,54 @@ extern "C" int cfdb_create(cfdb_ctx** out, const cfdb_params* par, int32_t npoin
                 return bail(fail("event create failed"));
     }
     const size_t P = npoin, E = nelem;
+#define B(x)                    \
+    do {                        \
+        int _r = (x);           \
+        if (_r) return bail(_r); \
+    } while (0)
     c->h_inpoel.assign(inpoel, inpoel + 3 * E);
-    // topology
-    topo::build_esup(inpoel, nelem, npoin, c->esup1, c->esup2, &c->h_eslot);
-    topo::build_psup(inpoel, npoin, c->esup1, c->esup2, c->psup1, c->psup2);
-    topo::build_lap_pattern(npoin, c->psup1, c->psup2, c->lap_idx, c->lap_rowptr);
-    c->nnz = c->lap_rowptr[npoin];
+    vector<int32_t> inp_soa(3 * E);
+    for (size_t e = 0; e < E; ++e)
+        for (int i = 0; i < 3; ++i) inp_soa[i * E + e] = inpoel[3 * e + i] - 1;
+    B(upload(c, c->inp, inp_soa));
+    if (verbose) cudaStreamSynchronize(c->st);
+    lap("connectivity SoA + upload");
+    // topology: getEsup/getPsup, the Laplacian pattern and the row positions -- built on the device (topo_gpu.cu,
+    // SURVEY.md 8f N4) and mirrored to the host vectors; CFDB_HOST_TOPO=1 keeps the serial host code (bit-identical,
+    // tests/test_topology.py compares the two)
+    vector<uint8_t> lpos;
+    const bool host_topo = getenv("CFDB_HOST_TOPO") != nullptr || E == 0 || P == 0;
+    if (host_topo) {
+        topo::build_esup(inpoel, nelem, npoin, c->esup1, c->esup2, &c->h_eslot);
+        topo::build_psup(inpoel, npoin, c->esup1, c->esup2, c->psup1, c->psup2);
+        topo::build_lap_pattern(npoin, c->psup1, c->psup2, c->lap_idx, c->lap_rowptr);
+        topo::build_lap_pos(inpoel, npoin, c->esup1, c->esup2, c->lap_idx, c->lap_rowptr, lpos, c->maxrow);
+    } else {
+        DBuf<int> d_psup2;
+        B(c->d_esup2.alloc(P + 1));
+        B(c->eslot.alloc(3 * E));
+        B(d_psup2.alloc(P + 1));
+        B(c->d_lap_rowptr.alloc(P + 1));
+        B(c->lpos.alloc(9 * E));
+        int *d_psup1 = nullptr, *d_idx0 = nullptr, npsup = 0;
+        int rc = topogpu::build(c->st, c->inp.p, nelem, npoin, c->d_esup2.p, c->eslot.p, d_psup2.p, &d_psup1, &npsup,
+                                c->d_lap_rowptr.p, &d_idx0, c->lpos.p, &c->maxrow);
+        if (rc) { d_psup2.release(); return bail(fail(std::string("device topology build failed: ") + cudaGetErrorString((cudaError_t)rc))); }
+        if (c->maxrow > 32) { d_psup2.release(); return bail(fail("node valence above 31 is not supported")); }
+        lap("device topology");
+        c->nnz = npsup + npoin;
+        c->d_lap_idx.p = d_idx0;     // ownership of the two late-sized arrays passes to the context
+        c->d_lap_idx.n = (size_t)c->nnz + 1;
+        // host mirrors (fields esup1/esup2/psup1/psup2/lap_idx/lap_rowptr, the chunk/tile planners) are downloaded on
+        // first use: ensure_host_topology
+        c->npsup = npsup;
+        c->d_psup1.p = d_psup1; c->d_psup1.n = (size_t)npsup + 1;
+        c->d_psup2.p = d_psup2.p; c->d_psup2.n = d_psup2.n;
+        d_psup2.p = nullptr; d_psup2.n = 0;
+        c->host_topo_valid = false;
+    }
+    if (host_topo) c->nnz = c->lap_rowptr[npoin];
+    if (host_topo) lap("host topology");
     {
         // stage pipeline: element chunk k is followed by the nodes all of whose elements lie in chunks <= k
         // (measured on B200, 16 M triangles: the pipeline does not pay — 10.2 ms/step against 9.5 ms for whole-mesh
@@ -420,11 +502,12 @@ extern "C" int cfdb_create(cfdb_ctx** out, const cfdb_params* par, int32_t npoin
         long chunk = getenv("CFDB_CHUNK") ? atol(getenv("CFDB_CHUNK")) : nelem;
         if (chunk < 64) chunk = nelem;
         int nch = (int)((nelem + chunk - 1) / chunk);
+        if (nch > 1) B(ensure_host_topology(c));
         c->chunk_e.assign(nch + 1, 0);
         c->chunk_n.assign(nch + 1, 0);
         for (int k = 1; k <= nch; ++k) c->chunk_e[k] = (int)std::min<long>(nelem, k * chunk);
         int n = 0, pm = -1;
-        for (int k = 1; k <= nch; ++k) {
+        for (int k = 1; k <= nch && nch > 1; ++k) {
             while (n < npoin) {
                 int emax = c->esup2[n + 1] > c->esup2[n] ? c->esup1[c->esup2[n + 1] - 1] - 1 : -1;
                 int pm2 = std::max(pm, emax);
@@ -439,24 +522,16 @@ extern "C" int cfdb_create(cfdb_ctx** out, const cfdb_params* par, int32_t npoin
         for (auto& e : c->chunk_ev)
             if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail(fail("event create failed"));
     }
-    vector<uint8_t> lpos;
-    topo::build_lap_pos(inpoel, npoin, c->esup1, c->esup2, c->lap_idx, c->lap_rowptr, lpos, c->maxrow);
     if (c->maxrow > 32) return bail(fail("node valence above 31 is not supported"));
-    vector<int32_t> inp_soa(3 * E), idx0(c->lap_idx);
-    for (size_t e = 0; e < E; ++e)
-        for (int i = 0; i < 3; ++i) inp_soa[i * E + e] = inpoel[3 * e + i] - 1;
-    for (auto& v : idx0) v -= 1;
-#define B(x)                    \
-    do {                        \
-        int _r = (x);           \
-        if (_r) return bail(_r); \
-    } while (0)
-    B(upload(c, c->inp, inp_soa));
-    B(upload(c, c->d_esup2, c->esup2));
-    B(upload(c, c->eslot, c->h_eslot));
-    B(upload(c, c->d_lap_idx, idx0));
-    B(upload(c, c->d_lap_rowptr, c->lap_rowptr));
-    B(upload(c, c->lpos, lpos));
+    if (host_topo) {
+        vector<int32_t> idx0(c->lap_idx);
+        for (auto& v : idx0) v -= 1;
+        B(upload(c, c->d_esup2, c->esup2));
+        B(upload(c, c->eslot, c->h_eslot));
+        B(upload(c, c->d_lap_idx, idx0));
+        B(upload(c, c->d_lap_rowptr, c->lap_rowptr));
+        B(upload(c, c->lpos, lpos));
+    }
     B(upload(c, c->X, X, P));
     B(upload(c, c->Y, Y, P));
     for (auto* d : {&c->X1, &c->Y1, &c->M, &c->VEL_X, &c->VEL_Y, &c->W_X, &c->W_Y, &c->P, &c->T, &c->RHO, &c->E, &c->RMACH,
@@ -478,13 +553,18 @@ extern "C" int cfdb_create(cfdb_ctx** out, const cfdb_params* par, int32_t npoin
     c->par.YREF[1] = 0.0;
     B(upload(c, c->xref, c->par.XREF, 10));
     B(upload(c, c->yref, c->par.YREF, 10));
+    if (verbose) cudaStreamSynchronize(c->st);
+    lap("allocate + zero + upload");
     B(build_bc_tables(c, bc));
+    if (verbose) cudaStreamSynchronize(c->st);
+    lap("BC tables");
     if (c->ale) B(zero(c, c->FC, 12 * E));
     if (!c->ale && getenv("CFDB_TILE") && atoi(getenv("CFDB_TILE")) != 0) {
         // tiles for the fused stage (opt-in: measured slower than the two-kernel stage on B200 — 2.04 + 0.26 ms against
         // 1.19 + 0.62 ms per stage on the 16 M-triangle mesh; the memory-bound node phase starves at the 12 warps/SM
         // the register-heavy element phase allows.  Bit-identical, covered by the GPU tests under CFDB_TILE=1.)
         topo::Tiling T;
+        B(ensure_host_topology(c));
         topo::build_tiling(inpoel, nelem, npoin, X, Y, c->esup1, c->esup2, c->h_eslot, 512, T);
         c->tile_interior = T.interior_fraction;
         {
@@ -504,6 +584,7 @@ extern "C" int cfdb_create(cfdb_ctx** out, const cfdb_params* par, int32_t npoin
     if (cudaMemsetAsync(c->sc, 0, sizeof(k::Scal), c->st) != cudaSuccess) return bail(fail("memset Scal failed"));
     if (cudaMallocHost(&c->h_sc, sizeof(k::Scal)) != cudaSuccess) return bail(fail("cudaMallocHost failed"));
     if (cudaStreamSynchronize(c->st) != cudaSuccess) return bail(fail("sync after create failed"));
+    lap("tail");
 #undef B
     *out = c;
     return 0;
@@ -523,7 +604,7 @@ extern "C" void cfdb_destroy(cfdb_ctx* c) {
     if (c->st2) cudaStreamDestroy(c->st2);
     for (auto* d : {&c->inp, &c->d_esup2, &c->eslot, &c->d_lap_idx, &c->d_lap_rowptr, &c->wall, &c->wn_node, &c->wn_ptr,
                     &c->wn_edge, &c->wn_valid, &c->bc_node, &c->bc_kind, &c->bc_wslot, &c->ilaux, &c->ilaux_last, &c->se_node,
-                    &c->se_set, &c->set_ptr, &c->set_n1, &c->set_n2, &c->set_el, &c->flags})
+                    &c->se_set, &c->set_ptr, &c->set_n1, &c->set_n2, &c->set_el, &c->d_psup1, &c->d_psup2, &c->flags})
         d->release();
     c->lpos.release();
     c->bcflag.release();
@@ -1314,6 +1395,8 @@ static bool find_field(cfdb_ctx* c, const std::string& n, Field& f) {
     FD("lap_sparse", lap_sparse, c->nnz) FD("lap_diag", lap_diag, P) FD("xpos", xpos, P) FD("ypos", ypos, P)
     FD("dxpos", dxpos, P) FD("dypos", dypos, P) FD("W_x_old", W_x_old, P) FD("W_y_old", W_y_old, P)
     FD("area_old", area_old, E) FD("EC", EC, 12 * E)
+    if (n == "esup1" || n == "esup2" || n == "psup1" || n == "psup2" || n == "lap_idx" || n == "lap_rowptr")
+        if (ensure_host_topology(c)) return false;
     FH("inpoel", h_inpoel) FH("esup1", esup1) FH("esup2", esup2) FH("psup1", psup1) FH("psup2", psup2)
     FH("lap_idx", lap_idx) FH("lap_rowptr", lap_rowptr) FH("ilaux", h_ilaux)
 #undef FD

@@ -389,7 +389,8 @@ def test_restart_file_resumes_state(cases, tmp_path):
 
 @pytest.mark.parametrize("env", ["CFDB_STAGE_OVERLAP=1", "CFDB_CALCRHS_PIPE=3", "CFDB_CALCRHS_PIPE=4", "CFDB_TILE=1", "CFDB_CHUNK=100",
                                  "CFDB_CHUNK=100,CFDB_CHUNK_SEQ=1", "CFDB_BICG_UNFUSED=1", "CFDB_CALCRHS_MINB=3",
-                                 "CFDB_CALCRHS_MINB=1", "CFDB_ESTAB_MINB=3"])
+                                 "CFDB_CALCRHS_MINB=1", "CFDB_ESTAB_MINB=3", "CFDB_HOST_TOPO=1",
+                                 "CFDB_STAGE_OVERLAP=1,CFDB_CALCRHS_PAD_KB=60"])
 def test_optional_paths_bit_exact(env):
     """Every opt-in code path kept in the library (profiles/r1_experiments.md) produces the same bits as the default."""
     import os
@@ -426,3 +427,51 @@ def test_fast_mode_meets_the_per_step_tolerance_only(cases, name):
         assert rel <= 1e-11, (f, rel)
     assert not np.array_equal(g.get("RHS").view(np.uint64), o.get("RHS").view(np.uint64))   # and it is not bit-exact
     g.set_option("fast", 0)
+
+
+@pytest.mark.parametrize("kind", ["square", "wedge", "ale", "fan_isolated", "single", "delaunay"])
+def test_device_built_topology_matches_oracle(kind):
+    """getEsup/getPsup, the Laplacian pattern and esup2 built on the device (topo_gpu.cu: stable radix sort + per-node
+    first-encounter walk) are bit-identical to the oracle's restatement of pointNeighbor.f90 /
+    mLaplace.f90:60-94 -- including nodes no element references and a 30 k-node scipy Delaunay mesh with ragged valence."""
+    from cfd_b200 import deck, meshgen
+    from cfd_b200.solver import NSComp2D
+    from oracle import orclib
+
+    if kind in ("square", "wedge", "ale"):
+        raw = {"square": lambda: meshgen.square(n=97), "wedge": lambda: meshgen.wedge(nx=49, ny=25),
+               "ale": lambda: meshgen.ale_body(nt=48, nr=14)}[kind]()
+    else:
+        if kind == "single":
+            X, Y, tri = np.array([0.0, 1.0, 0.0]), np.array([0.0, 0.0, 1.0]), np.array([[1, 2, 3]], np.int32)
+        elif kind == "fan_isolated":   # node 3 is referenced by no element
+            X = np.array([0.0, 1.0, 5.0, 0.0, 1.0, 2.0])
+            Y = np.array([0.0, 0.0, 5.0, 1.0, 1.0, 1.0])
+            tri = np.array([[1, 2, 5], [1, 5, 4], [2, 6, 5]], np.int32)
+        else:
+            from scipy.spatial import Delaunay
+            rng = np.random.default_rng(11)
+            pts = rng.random((30000, 2))
+            tri = Delaunay(pts).simplices.astype(np.int32)
+            a = pts[tri]
+            d1, d2 = a[:, 1] - a[:, 0], a[:, 2] - a[:, 0]
+            cw = d1[:, 0] * d2[:, 1] - d1[:, 1] * d2[:, 0] < 0
+            tri[cw] = tri[cw][:, ::-1]
+            X, Y, tri = pts[:, 0].copy(), pts[:, 1].copy(), np.ascontiguousarray(tri + 1)
+        raw = deck.RawCase(name=kind, X=X, Y=Y, inpoel=tri, U_inf=100.0)
+    lc = deck.load(raw)
+    g = NSComp2D(lc, init=False)
+    L = orclib.lib()
+    e1, e2 = np.zeros(3 * lc.nelem, np.int32), np.zeros(lc.npoin + 1, np.int32)
+    L.orc_get_esup(lc.inpoel, lc.nelem, lc.npoin, e1, e2)
+    p1, p2 = np.zeros(8 * lc.nelem + 8, np.int32), np.zeros(lc.npoin + 1, np.int32)
+    cnt = L.orc_get_psup(lc.inpoel, lc.nelem, lc.npoin, p1, p1.size, p2)
+    assert np.array_equal(g.get("esup1"), e1) and np.array_equal(g.get("esup2"), e2)
+    assert np.array_equal(g.get("psup1"), p1[:cnt]) and np.array_equal(g.get("psup2"), p2)
+    rowptr = p2 + np.arange(lc.npoin + 1, dtype=np.int32)
+    assert np.array_equal(g.get("lap_rowptr"), rowptr)
+    idx = g.get("lap_idx")
+    assert np.array_equal(idx[rowptr[:-1]], np.arange(1, lc.npoin + 1))           # diagonal first
+    mask = np.ones(idx.size, bool)
+    mask[rowptr[:-1]] = False
+    assert np.array_equal(idx[mask], p1[:cnt])                                     # then psup in order
