@@ -16,7 +16,7 @@ _ip = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
 # every symbol include/cfdb.h declares (tests/test_abi.py checks the library exports each one)
 SYMBOLS = [
     "cfdb_last_error", "cfdb_device_count", "cfdb_create", "cfdb_destroy", "cfdb_init", "cfdb_step", "cfdb_sync",
-    "cfdb_rk_stage", "cfdb_geometry", "cfdb_fluid_structure", "cfdb_residual_norms", "cfdb_step_norms", "cfdb_force_visc", "cfdb_get", "cfdb_set",
+    "cfdb_rk_stage", "cfdb_geometry", "cfdb_fluid_structure", "cfdb_residual_norms", "cfdb_step_norms", "cfdb_force_visc", "cfdb_printflavia", "cfdb_format_cnv", "cfdb_format_real", "cfdb_get", "cfdb_set",
     "cfdb_field_size", "cfdb_get_scalar", "cfdb_set_scalar", "cfdb_set_option", "cfdb_stream", "cfdb_profile_enable", "cfdb_profile_get",
     "cfdb_launch_count", "cfdb_nccl_unique_id", "cfdb_comm_init", "cfdb_set_halo", "cfdb_halo_exchange", "cfdb_calcrhs", "cfdb_fuente", "cfdb_deltat", "cfdb_estab", "cfdb_deriv", "cfdb_masas",
     "cfdb_normales", "cfdb_laplace", "cfdb_bicg", "cfdb_spmv", "cfdb_vecdot", "cfdb_gcl_main", "cfdb_smoothing", "cfdb_selftest", "cfdb_get_esup",
@@ -70,6 +70,9 @@ def lib():
     L.cfdb_residual_norms.argtypes = [vp, _dp, _dp]
     L.cfdb_step_norms.argtypes = [vp, _dp, _dp]
     L.cfdb_force_visc.argtypes = [vp]
+    L.cfdb_printflavia.argtypes = [vp, cp, i32, _ip, i32]
+    L.cfdb_format_cnv.argtypes = [i32, d, _dp, cp, i32]
+    L.cfdb_format_real.argtypes = [i32, d, i32, i32, cp, i32]
     L.cfdb_get.argtypes = [vp, cp, vp, i64]
     L.cfdb_set.argtypes = [vp, cp, vp, i64]
     L.cfdb_field_size.argtypes = [vp, cp]

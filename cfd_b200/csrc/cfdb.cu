@@ -3,6 +3,7 @@
 #include "../../include/cfdb.h"
 #include "host_topology.h"
 #include "../../host/mesh_smoothing.h"
+#include "../../host/fortran_format.h"
 #include "kernels.cuh"
 
 #include <nccl.h>
@@ -1272,6 +1273,74 @@ extern "C" int cfdb_force_visc(cfdb_ctx* c) {
                c->inp.p, c->X.p, c->Y.p, c->P.p, c->T.p, c->VEL_X.p, c->VEL_Y.p, c->dNx.p, c->dNy.p, p.U_inf, p.V_inf, p.RHO_inf,
                p.T_inf, c->fvisc.p, c->skin.p, c->nedges);
     if (c->nranks > 1) TRY(allreduce(c, c->fvisc.p, 20, ncclSum));
+    return 0;
+}
+
+// one real in Fortran Ew.d ('E') or Fw.d ('F') layout (host/fortran_format.h), for tests of the output formats
+extern "C" int cfdb_format_real(int32_t kind, double v, int32_t w, int32_t d, char* buf, int32_t buflen) {
+    std::string s = kind == 'F' ? ffmt::F(v, w, d) : ffmt::E(v, w, d);
+    if ((int)s.size() + 1 > buflen) return fail("cfdb_format_real: buffer too small");
+    memcpy(buf, s.c_str(), s.size() + 1);
+    return 0;
+}
+extern "C" int cfdb_format_cnv(int32_t iter, double time, const double r[4], char* buf, int32_t buflen) {
+    std::string s = ffmt::cnv_record(iter, time, r);
+    if ((int)s.size() + 1 > buflen) return fail("cfdb_format_cnv: buffer too small");
+    memcpy(buf, s.c_str(), s.size() + 1);
+    return 0;
+}
+
+// PRINTFLAVIA (ns2DComp.ALE.f90:701-817) with the arguments of its call site (:225-226): velocities relative to the mesh,
+// X1/Y1 as positions.  flags: RHO, VEL2, MACH, PRES, TEMP, ENER, POS ('.si.' in <name>-1.dat).
+extern "C" int cfdb_printflavia(cfdb_ctx* c, const char* path, int32_t iter, const int32_t flags[7], int32_t append) {
+    CK(cudaSetDevice(c->device));
+    const size_t P = c->npoin;
+    vector<double> rho(P), vx(P), vy(P), wx(P), wy(P), pr(P), tt(P), en(P), gm(P), x1(P), y1(P);
+    struct { double* h; const double* d; } cp[] = {{rho.data(), c->RHO.p}, {vx.data(), c->VEL_X.p}, {vy.data(), c->VEL_Y.p},
+        {wx.data(), c->W_X.p}, {wy.data(), c->W_Y.p}, {pr.data(), c->P.p}, {tt.data(), c->T.p}, {en.data(), c->E.p},
+        {gm.data(), c->GAMM.p}, {x1.data(), c->X1.p}, {y1.data(), c->Y1.p}};
+    for (auto& q : cp) CK(cudaMemcpyAsync(q.h, q.d, P * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    for (size_t i = 0; i < P; ++i) { vx[i] = vx[i] - wx[i]; vy[i] = vy[i] - wy[i]; }   // VEL_X - W_X, VEL_Y - W_Y (:225)
+    std::FILE* f = std::fopen(path, append ? "a" : "w");
+    if (!f) return fail(std::string("cfdb_printflavia: cannot open ") + path);
+    auto header = [&](const char* name, int ncomp) {
+        std::string h = ffmt::A(name, 15);
+        const int v[5] = {2, iter, ncomp, 1, 1};
+        for (int k = 0; k < 5; ++k) h += ffmt::I(v[k], 8) + "  ";
+        std::fprintf(f, "%s\n", h.c_str());
+    };
+    if (flags[1]) {
+        header("VELOCITY", 2);
+        std::fprintf(f, "VEL_X\nVEL_Y\n");
+        for (size_t i = 0; i < P; ++i)
+            std::fprintf(f, "%s%s%s\n", ffmt::I((long)i + 1, 8).c_str(), ffmt::E(vx[i], 13, 4).c_str(), ffmt::E(vy[i], 13, 4).c_str());
+    }
+    if (flags[6]) {
+        header("POSITION", 2);
+        std::fprintf(f, "X\nY\n");
+        for (size_t i = 0; i < P; ++i)
+            std::fprintf(f, "%s%s%s\n", ffmt::I((long)i + 1, 8).c_str(), ffmt::E(x1[i], 16, 6).c_str(), ffmt::E(y1[i], 16, 6).c_str());
+    }
+    auto scalar = [&](const char* name, const vector<double>& a, int w, int d) {
+        header(name, 1);
+        std::fprintf(f, "%s\n", name);
+        for (size_t i = 0; i < P; ++i) std::fprintf(f, "%s%s\n", ffmt::I((long)i + 1, 8).c_str(), ffmt::E(a[i], w, d).c_str());
+    };
+    if (flags[0]) scalar("DENSITY", rho, 13, 4);
+    if (flags[3]) scalar("PRESSURE", pr, 16, 3);
+    if (flags[4]) scalar("TEMPERATURE", tt, 13, 3);
+    if (flags[2]) {
+        header("Mach_Number", 1);
+        std::fprintf(f, "Mach_Number\n");
+        for (size_t i = 0; i < P; ++i) {
+            double VEL = std::sqrt(vx[i] * vx[i] + vy[i] * vy[i]);
+            double VC = std::sqrt(gm[i] * c->par.FR * tt[i]);
+            std::fprintf(f, "%s%s\n", ffmt::I((long)i + 1, 8).c_str(), ffmt::F(VEL / VC, 11, 2).c_str());
+        }
+    }
+    if (flags[5]) scalar("Internal_Energy", en, 16, 8);
+    std::fclose(f);
     return 0;
 }
 

@@ -107,6 +107,17 @@ class NSComp2D:
         capi.check(self.L.cfdb_force_visc(self.h))
         return tuple(self.get(n) for n in ("F_VX", "F_VY", "skin", "skin_x", "skin_p"))
 
+    def printflavia(self, path, it, flags=(1, 1, 1, 1, 1, 1, 1), append=False):
+        """PRINTFLAVIA (ns2DComp.ALE.f90:701-817): GiD result blocks; flags = RHO, VEL2, MACH, PRES, TEMP, ENER, POS."""
+        capi.check(self.L.cfdb_printflavia(self.h, str(path).encode(), int(it), np.asarray(flags, np.int32), int(append)))
+
+    @staticmethod
+    def cnv_record(it, time, r):
+        """one line of <name>.cnv ('(I7, 5E14.6)')"""
+        buf = C.create_string_buffer(128)
+        capi.check(capi.lib().cfdb_format_cnv(int(it), float(time), np.ascontiguousarray(r, np.float64), buf, 128))
+        return buf.value.decode()
+
     def step_norms(self):
         """ER, ERR as evaluated inside the last print step of cfdb_step (before U = U1)."""
         er, err = np.zeros(4), np.zeros(4)

@@ -24,6 +24,7 @@ struct Deck {
     std::vector<int32_t> ifixrho_node, ifixv_node, ifixt_node, wall, iset_n1, iset_n2, iset_elem, iset_id, ifm, i_m, master, slave;
     std::vector<double> rfixrho_value, rfixv_valuex, rfixv_valuey, rfixt_value;
     std::vector<unsigned char> smooth_fix;  // ns2DComp.ALE.f90:63-73
+    int32_t print_flags[7] = {0, 0, 0, 0, 0, 0, 0};  // RHO VEL2 MACH PRES TEMP ENER POS
     cfdb_bc bc() const {
         cfdb_bc b{};
         b.nfixrho = (int)ifixrho_node.size(); b.ifixrho_node = ifixrho_node.data(); b.rfixrho_value = rfixrho_value.data();
@@ -84,6 +85,9 @@ inline Deck read_deck(const std::string& dir) {
         p.CTE = num(v.at(0));
         L.skip(2); v = L.read();
         p.MOVING = std::stoi(v.at(0)); p.XREF[0] = num(v.at(1)); p.YREF[0] = num(v.at(2));
+        // RHOCHAR VEL2CHAR MACHCHAR PRESCHAR TEMPCHAR ENERCHAR POSCHAR (dataLoader.f90:46-48): '.si.' switches a block on
+        L.skip(2); v = L.read();
+        for (int k = 0; k < 7 && k < (int)v.size(); ++k) d.print_flags[k] = v[k].find(".si.") != std::string::npos;
     }
     // dataLoader.f90:58-64
     p.CTE = 1.0 / p.CTE;

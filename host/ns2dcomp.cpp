@@ -19,6 +19,7 @@
 #include "../include/cfdb.h"
 #include "deck_reader.h"
 #include "mesh_smoothing.h"
+#include "fortran_format.h"
 
 static void die(const char* who) {
     std::fprintf(stderr, "%s: %s\n", who, cfdb_last_error());
@@ -77,6 +78,7 @@ int main(int argc, char** argv) {
     std::printf("****-------> RUNGE-KUTTA DE  4  ORDEN <-------****\n\n");
     std::FILE* cnv = std::fopen((dir + "/" + d.name + ".cnv").c_str(), "w");
     int iter = 0, iterprint = 0;
+    bool flavia_written = false;
     const int MAXITER = d.par.MAXITER, IPRINT = d.par.IPRINT;
     while (iter < MAXITER) {  // ns2DComp.ALE.f90:138
         iter += 1;
@@ -89,7 +91,7 @@ int main(int argc, char** argv) {
             cfdb_get_scalar(ctx, "DTMIN", &dtmin);
             double r[4], fus = 0;
             for (int i = 0; i < 4; ++i) { r[i] = std::sqrt(er[i] / err[i]); if (r[i] > fus) fus = r[i]; }
-            std::fprintf(cnv, "%7d%14.6E%14.6E%14.6E%14.6E%14.6E\n", iter, time, r[0], r[1], r[2], r[3]);
+            std::fprintf(cnv, "%s\n", ffmt::cnv_record(iter, time, r).c_str());
             std::fflush(cnv);
             if (fus > 1.e2) {  // FUSIBLE, :202-210
                 std::printf("      ERROR CONVERGENCIA\n    *****  OVERFLOW  *****\n");
@@ -98,6 +100,11 @@ int main(int argc, char** argv) {
             std::printf("CCCC  ----> INFORMACION DE LA CORRIDA <----  CCCC\nPASOS EJECUTADOS:%6d\nTIEMPO ACUMULADO:%12.4E\nPASO DE TIEMPO:%12.4E\n",
                         iter, time, dtmin);
             std::printf("Continuidad %12.4E\nMomento u   %12.4E\nMomento v   %12.4E\nEnergia     %12.4E\n\n", r[0], r[1], r[2], r[3]);
+            // PRINTFLAVIA (:225-226): with MOVIE=0 the file is reopened and rewritten at every print step (:709-711)
+            if (cfdb_printflavia(ctx, (dir + "/" + d.name + ".flavia.res").c_str(), iter, d.print_flags,
+                                 d.par.MOVIE == 1 && flavia_written))
+                die("cfdb_printflavia");
+            flavia_written = true;
             iterprint = 0;
         }
     }

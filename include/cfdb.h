@@ -81,6 +81,14 @@ int cfdb_residual_norms(cfdb_ctx* ctx, double er[4], double err[4]); /* ns2DComp
  * "F_VX"(10), "F_VY"(10) and the SKIN.DAT columns "skin", "skin_x", "skin_p" (one entry per ISET edge, set by set);
  * FORCES' "FX", "FY", "RM" (10 each, meshMove.f90:153-194) are fields too.  cfdb_step calls it at the same place. */
 int cfdb_force_visc(cfdb_ctx* ctx);
+/* PRINTFLAVIA (ns2DComp.ALE.f90:701-817, call site :225-226): write the GiD result blocks of the resident state
+ * (velocities relative to the mesh, X1/Y1 as positions) with the reference's FORMATs.  flags[7] = RHO, VEL2, MACH, PRES,
+ * TEMP, ENER, POS (1 where <name>-1.dat says '.si.'); append = 1 for MOVIE runs (one file, a block per print step). */
+int cfdb_printflavia(cfdb_ctx* ctx, const char* path, int32_t iter, const int32_t flags[7], int32_t append);
+/* one record of <name>.cnv as '(I7, 5E14.6)' (the reference's '(I7, 4E14.6)' is one slot short) */
+int cfdb_format_cnv(int32_t iter, double time, const double r[4], char* buf, int32_t buflen);
+/* one real laid out as Fortran Ew.d (kind 'E') or Fw.d (kind 'F') */
+int cfdb_format_real(int32_t kind, double v, int32_t w, int32_t d, char* buf, int32_t buflen);
 /* the norms cfdb_step evaluated on its last print step (ITERPRINT==IPRINT or ITER==MAXITER, :186), i.e. before U=U1 */
 int cfdb_step_norms(cfdb_ctx* ctx, double er[4], double err[4]);
 /* field transfer by Fortran variable name ("U","U1","RHS","T","VEL_X","X","inpoel","esup1","lap_idx",...);

@@ -5,7 +5,8 @@
                                            # normales/deriv/masas/laplace, then the time loop, on a deck written to a tmp dir
     ref.mod("mvariabgen").u                # module variables afterwards (Fortran shapes, e.g. U is (4, npoin))
 
-Only the file-output routines PRINTFLAVIA / PRINTREST are replaced by no-ops (their results feed nothing).
+Only PRINTREST (unformatted restart dump) is replaced by a no-op; formatted output (PRINTFLAVIA's GiD file, FORCES, ...)
+is kept as text records in Reference.io.text.
 """
 from __future__ import annotations
 
@@ -54,7 +55,7 @@ class Reference:
         self.ns.update(self._orig)      # drop the overrides of an earlier run
         self.ns["IO"].__init__()
         self.ns["_reset"]()
-        for name in ("printflavia", "printrest"):
+        for name in ("printrest",):      # unformatted (binary) WRITE: not interpreted
             self.ns["p___" + name] = lambda *a, **k: None
 
     def mod(self, name):

@@ -344,6 +344,7 @@ class IO:
     def __init__(self):
         self.units = {}
         self.written = {}
+        self.text = {}
 
     def open(self, unit, file=None, status=None, **kw):
         unit = int(unit)
@@ -354,6 +355,7 @@ class IO:
         else:
             self.units[unit] = {"lines": None, "name": file}
             self.written.setdefault(file, [])
+            self.text[file] = []          # a re-opened file is rewritten from its first record
 
     def close(self, unit, **kw):
         self.units.pop(int(unit), None)
@@ -364,6 +366,11 @@ class IO:
         u = self.units.get(int(unit))
         if u is not None and u["lines"] is None:
             self.written[u["name"]].append(items)
+            if fmt is not None:      # formatted: also keep the text records (list-directed layout is compiler-specific)
+                try:
+                    self.text.setdefault(u["name"], []).extend(format_records(fmt, items))
+                except FormatError as ex:
+                    self.text.setdefault(u["name"], []).append(f"<run-time error: {ex}>")
 
     def read_list(self, unit, n):
         """next record(s) -> n list-directed tokens (n == 0 skips one record)"""
@@ -397,3 +404,163 @@ def conv_token(tok, like):
     if type(like) is f4 or (type(like) is np.ndarray and like.dtype == np.float32):
         return f4(t)
     return f8(t)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# formatted WRITE: the edit descriptors the reference uses (A, Aw, Iw, Ew.d, Fw.d, nX, /, repeat counts, groups,
+# format reversion), laid out the way gfortran does (leading "0." when the field has room, two-digit exponent)
+# ----------------------------------------------------------------------------------------------------------------
+class FormatError(Exception):
+    pass
+
+
+def _fmt_E(v, w, d):
+    v = float(v)
+    if v != v:
+        s = "NaN"
+    elif v in (math.inf, -math.inf):
+        s = ("-" if v < 0 else "") + ("Infinity" if w >= 8 + (v < 0) else "Inf")
+    else:
+        neg = math.copysign(1.0, v) < 0
+        if v == 0.0:
+            digits, ex = "0" * d, 0
+        else:
+            m, e = ("%.*e" % (d - 1, abs(v))).split("e")      # d significant digits, correctly rounded
+            digits, ex = m.replace(".", ""), int(e) + 1       # 0.ddddE+ex
+        es = ("E%+03d" % ex) if abs(ex) <= 99 else ("%+04d" % ex)
+        body = "." + digits + es
+        s = ("-" if neg else "") + "0" + body
+        if len(s) > w:
+            s = ("-" if neg else "") + body
+    return s.rjust(w) if len(s) <= w else "*" * w
+
+
+def _fmt_F(v, w, d):
+    v = float(v)
+    if v != v:
+        s = "NaN"
+    elif v in (math.inf, -math.inf):
+        s = ("-" if v < 0 else "") + ("Infinity" if w >= 8 + (v < 0) else "Inf")
+    else:
+        s = "%.*f" % (d, v)
+        if len(s) > w and (s.startswith("0.") or s.startswith("-0.")):
+            s = s.replace("0.", ".", 1)
+    return s.rjust(w) if len(s) <= w else "*" * w
+
+
+def _parse_format(f):
+    """'(I7, 4E14.6)' -> nested list of items: ('I',w) ('E',w,d) ('F',w,d) ('A',w|None) ('X',n) ('/',) ('S',text) (n,[group])"""
+    f = f.strip()
+    if not (f.startswith("(") and f.endswith(")")):
+        raise FormatError(f)
+    pos = 1
+
+    def group():
+        nonlocal pos
+        items = []
+        while True:
+            while pos < len(f) and f[pos] in " ,":
+                pos += 1
+            ch = f[pos]
+            if ch == ")":
+                pos += 1
+                return items
+            if ch == "/":
+                items.append(("/",))
+                pos += 1
+                continue
+            if ch in "'\"":
+                q, end = ch, f.index(ch, pos + 1)
+                items.append(("S", f[pos + 1:end]))
+                pos = end + 1
+                continue
+            n = 0
+            has_n = False
+            while f[pos].isdigit():
+                n, has_n, pos = n * 10 + int(f[pos]), True, pos + 1
+            rep = n if has_n else 1
+            ch = f[pos].upper()
+            if ch == "(":
+                pos += 1
+                items.append((rep, group()))
+                continue
+            pos += 1
+            if ch == "X":
+                items.append(("X", rep))
+                continue
+            num = ""
+            while pos < len(f) and (f[pos].isdigit() or f[pos] == "."):
+                num += f[pos]
+                pos += 1
+            if ch == "A":
+                it = ("A", int(num) if num else None)
+            elif ch == "I":
+                it = ("I", int(num.split(".")[0]))
+            elif ch in "EFDG":
+                w, d = num.split(".")
+                it = ("F" if ch == "F" else "E", int(w), int(d))
+            else:
+                raise FormatError(f"edit descriptor {ch} in {f}")
+            items.extend([it] * rep)
+
+    return group()
+
+
+def format_records(fmt, values):
+    """-> list of text records produced by WRITE(u, fmt) values"""
+    items = _parse_format(fmt)
+    vals = list(values)
+    recs, cur = [], []
+    vi = 0
+
+    class Done(Exception):
+        pass
+
+    def emit(it):
+        nonlocal vi, cur
+        k = it[0]
+        if k == "/":
+            recs.append("".join(cur))
+            cur = []
+        elif k == "X":
+            cur.append(" " * it[1])
+        elif k == "S":
+            cur.append(it[1])
+        else:
+            if vi >= len(vals):
+                raise Done
+            v = vals[vi]
+            vi += 1
+            if k == "A":
+                if not isinstance(v, str):
+                    raise FormatError("A edit descriptor with a non-character item")
+                cur.append(v if it[1] is None else (v[:it[1]] if len(v) >= it[1] else v.rjust(it[1])))
+            elif k == "I":
+                if type(v) not in _INT:
+                    raise FormatError("I edit descriptor with a non-integer item (gfortran: run-time error)")
+                s = str(int(v))
+                cur.append(s.rjust(it[1]) if len(s) <= it[1] else "*" * it[1])
+            else:
+                if type(v) in _INT or isinstance(v, str):
+                    raise FormatError(f"{k} edit descriptor with a non-real item")
+                cur.append(_fmt_E(v, it[1], it[2]) if k == "E" else _fmt_F(v, it[1], it[2]))
+
+    def run(lst):
+        for it in lst:
+            if isinstance(it[0], int):
+                for _ in range(it[0]):
+                    run(it[1])
+            else:
+                emit(it)
+
+    try:
+        run(items)
+        while vi < len(vals):   # format reversion: new record, restart at the last top-level group (or the whole format)
+            recs.append("".join(cur))
+            cur = []
+            last = [it for it in items if isinstance(it[0], int)]
+            run([last[-1]] if last else items)
+    except Done:
+        pass
+    recs.append("".join(cur))
+    return recs

@@ -992,7 +992,10 @@ class Program:
                 items = [self.ex(unit, parse_expr(a.strip())) for a in _split_top(s[j + 1:], ",") if a.strip()]
             except SyntaxError:
                 raise rt.Unsupported("write with implied-do")
-            return [f"{pad}IO.write({unit_code}, None, [{', '.join(items)}])"]
+            fmt_code = "None"
+            if len(ctl) > 1 and ctl[1].strip()[:1] in ("'", '"'):
+                fmt_code = self.ex(unit, parse_expr(ctl[1].strip()))
+            return [f"{pad}IO.write({unit_code}, {fmt_code}, [{', '.join(items)}])"]
         if lead == "read":
             return self.read(unit, ind, s)
         # assignment

@@ -130,6 +130,9 @@ def run_reference(name):
         "in_ifixrho_node": md.ifixrho_node, "in_rfixrho_value": md.rfixrho_value,
         "in_ifixt_node": md.ifixt_node, "in_rfixt_value": md.rfixt_value, "in_ilaux": md.ilaux if md.ilaux is not None else np.zeros(0, np.int32),
     }
+    if name == "ref_ale_visc":   # PRINTFLAVIA's GiD file of the last print step (MOVIE = 0: rewritten every time), byte for byte
+        with open(os.path.join(HERE, name + ".flavia.res"), "w") as f:
+            f.write("\n".join(ref.io.text[raw.name + ".flavia.res"]) + "\n")
     return {k: np.array(a) for k, a in out.items()}
 
 
