@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcfdb200.so")
+LIB_PATH = os.environ.get("CFDB_LIB_PATH") or os.path.join(_HERE, "libcfdb200.so")   # override: A/B builds (csrc/Makefile: hints)
 
 _dp = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
 _ip = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
