@@ -157,7 +157,10 @@ class NSComp2D:
 
     # ---- restart files (PRINTREST / RESTART, ns2DComp.ALE.f90:898-917, :423-431) ---------------------------
     def print_rest(self, path):
-        """PRINTREST: <name>.RST with (ITER, TIME) and, per node, (U(1:4), T, GAMM)."""
+        """PRINTREST: <name>.RST with (ITER, TIME) and, per node, (U(1:4), T, GAMM) -- unformatted sequential records,
+        byte-identical to the reference's (tests/test_reference_callsites.py).  The reference calls PRINTREST before its
+        U = U1 (ns2DComp.ALE.f90:254 vs :277), so its file pairs the state the step started from with the temperature it
+        ended with; this method writes the consistent pair (U and T of the same step)."""
         from .deck import write_rst
 
         write_rst(path, int(self.scalar("ITER")), self.scalar("TIME"), self.get("U"), self.get("T"), self.get("GAMM"))

@@ -5,8 +5,8 @@
                                            # normales/deriv/masas/laplace, then the time loop, on a deck written to a tmp dir
     ref.mod("mvariabgen").u                # module variables afterwards (Fortran shapes, e.g. U is (4, npoin))
 
-Only PRINTREST (unformatted restart dump) is replaced by a no-op; formatted output (PRINTFLAVIA's GiD file, FORCES, ...)
-is kept as text records in Reference.io.text.
+Nothing is stubbed: formatted output (PRINTFLAVIA's GiD file, FORCES, ...) is kept as text records in
+Reference.io.text, PRINTREST's unformatted restart dump as bytes in Reference.io.binary.
 """
 from __future__ import annotations
 
@@ -55,8 +55,6 @@ class Reference:
         self.ns.update(self._orig)      # drop the overrides of an earlier run
         self.ns["IO"].__init__()
         self.ns["_reset"]()
-        for name in ("printrest",):      # unformatted (binary) WRITE: not interpreted
-            self.ns["p___" + name] = lambda *a, **k: None
 
     def mod(self, name):
         return _ModView(self.ns["M_" + name.lower()])
@@ -68,8 +66,8 @@ class Reference:
     def io(self):
         return self.ns["IO"]
 
-    def run_program(self, raw, maxiter=None, hook=None):
-        """write the deck, run PROGRAM NSComp2D; returns the records written to <name>.cnv"""
+    def run_program(self, raw, maxiter=None, hook=None, files=None):
+        """write the deck (+ extra files: {name: bytes}), run PROGRAM NSComp2D; returns the records written to <name>.cnv"""
         from cfd_b200 import deck
         import copy
 
@@ -82,6 +80,9 @@ class Reference:
         cwd = os.getcwd()
         with tempfile.TemporaryDirectory() as d, np.errstate(all="ignore"):
             deck.write_deck(raw, d)
+            for fname, data in (files or {}).items():
+                with open(os.path.join(d, fname), "wb") as f:
+                    f.write(data)
             os.chdir(d)
             try:
                 self.ns["p___nscomp2d"]()

@@ -338,6 +338,22 @@ def idx(e, lb):
     return e - lb
 
 
+class _Record:
+    """one unformatted record being consumed by a READ list"""
+
+    def __init__(self, data):
+        self.data, self.pos = data, 0
+
+    def take(self, ftype):
+        import struct
+        fmt, n = {"i": ("<i", 4), "r4": ("<f", 4), "r8": ("<d", 8)}[ftype]
+        if self.pos + n > len(self.data):
+            raise IOError("READ list longer than the record")
+        (v,) = struct.unpack_from(fmt, self.data, self.pos)
+        self.pos += n
+        return v
+
+
 class IO:
     """list-directed READ from text files, WRITE/PRINT recorded (never formatted): enough for dataLoader and the .cnv values"""
 
@@ -345,10 +361,20 @@ class IO:
         self.units = {}
         self.written = {}
         self.text = {}
+        self.binary = {}
 
-    def open(self, unit, file=None, status=None, **kw):
+    def open(self, unit, file=None, status=None, form=None, **kw):
         unit = int(unit)
         file = str(file).strip()
+        if form is not None and str(form).strip().lower() == "unformatted":
+            # sequential unformatted file: 4-byte little-endian record markers around every record (gfortran's default)
+            data = b""
+            import os as _os
+            if _os.path.exists(file):
+                with open(file, "rb") as f:
+                    data = f.read()
+            self.units[unit] = {"lines": None, "name": file, "unf": True, "data": data, "pos": 0, "out": bytearray()}
+            return
         if status is not None and str(status).strip().lower() == "old":
             with open(file) as f:
                 self.units[unit] = {"lines": f.read().split("\n"), "pos": 0, "name": file}
@@ -358,7 +384,37 @@ class IO:
             self.text[file] = []          # a re-opened file is rewritten from its first record
 
     def close(self, unit, **kw):
-        self.units.pop(int(unit), None)
+        u = self.units.pop(int(unit), None)
+        if u is not None and u.get("unf") and u["out"]:
+            self.binary[u["name"]] = bytes(u["out"])
+            with open(u["name"], "wb") as f:
+                f.write(u["out"])
+
+    def write_unf(self, unit, items):
+        import struct
+        payload = bytearray()
+        for v in items:
+            if type(v) in _INT:
+                payload += struct.pack("<i", int(v))
+            elif type(v) is f4:
+                payload += struct.pack("<f", float(v))
+            elif type(v) is np.ndarray:
+                payload += np.ascontiguousarray(v.ravel(order="F")).tobytes()
+            else:
+                payload += struct.pack("<d", float(v))
+        u = self.units[int(unit)]
+        u["out"] += struct.pack("<i", len(payload)) + payload + struct.pack("<i", len(payload))
+
+    def read_unf(self, unit):
+        import struct
+        u = self.units[int(unit)]
+        (n,) = struct.unpack_from("<i", u["data"], u["pos"])
+        rec = _Record(u["data"][u["pos"] + 4:u["pos"] + 4 + n])
+        (n2,) = struct.unpack_from("<i", u["data"], u["pos"] + 4 + n)
+        if n2 != n:
+            raise IOError("corrupt unformatted record")
+        u["pos"] += n + 8
+        return rec
 
     def write(self, unit, fmt, items):
         if unit == "*":

@@ -988,6 +988,8 @@ class Program:
             j = _match_paren(s, s.index("("))
             ctl = _split_top(s[s.index("(") + 1:j], ",")
             unit_code = "'*'" if ctl[0].strip() == "*" else self.ex(unit, parse_expr(ctl[0].strip()))
+            if len(ctl) == 1:   # unformatted: one record of raw bytes
+                return [f"{pad}IO.write_unf({unit_code}, [{', '.join(self._unf_write_items(unit, self._io_items(s[j + 1:])))}])"]
             try:
                 items = [self.ex(unit, parse_expr(a.strip())) for a in _split_top(s[j + 1:], ",") if a.strip()]
             except SyntaxError:
@@ -1005,14 +1007,60 @@ class Program:
             return [pad + self.assign(unit, tgt, self.ex(unit, parse_expr(parts[1].strip())))]
         raise rt.Unsupported("statement")
 
+
+    # ---------------------------------------------------------------- unformatted (binary) I/O lists
+    def _io_items(self, text):
+        """split an I/O list at top-level commas; '(a(j), j=1,4)' stays one item"""
+        return [a.strip() for a in _split_top(text, ",") if a.strip()]
+
+    def _implied_do(self, item):
+        """'(u(j, inod), j=1, 4)' -> (['u(j, inod)'], 'j', ['1', '4']) or None"""
+        if not (item.startswith("(") and _match_paren(item, 0) == len(item) - 1):
+            return None
+        parts = _split_top(item[1:-1], ",")
+        for k, part in enumerate(parts):
+            m = re.match(r"^\s*(\w+)\s*=\s*(.*)$", part)
+            if m and _split_top_assign(part):
+                return [x.strip() for x in parts[:k]], m.group(1), [m.group(2).strip()] + [x.strip() for x in parts[k + 1:]]
+        return None
+
+    def _unf_write_items(self, unit, items):
+        out = []
+        for it in items:
+            d = self._implied_do(it)
+            if d:
+                inner, var, rng = d
+                v, _ = self.varcode(unit, var)
+                body = ", ".join(self._unf_write_items(unit, inner))
+                out.append(f"*[x for {v} in rt.dorange({', '.join(self.ex(unit, parse_expr(r)) for r in rng)}) for x in ({body},)]")
+            else:
+                out.append(self.ex(unit, parse_expr(it)))
+        return out
+
+    def _unf_read_stmts(self, unit, pad, items):
+        out = []
+        for it in items:
+            d = self._implied_do(it)
+            if d:
+                inner, var, rng = d
+                v, _ = self.varcode(unit, var)
+                out.append(f"{pad}for {v} in rt.dorange({', '.join(self.ex(unit, parse_expr(r)) for r in rng)}):")
+                out.extend(self._unf_read_stmts(unit, pad + "    ", inner))
+            else:
+                e = parse_expr(it)
+                name = e[1]
+                _, var = self.varcode(unit, name)
+                out.append(pad + self.assign(unit, e, f"_rec.take({var.ftype!r})"))
+        return out
+
     def read(self, unit, ind, s):
         pad = "    " * ind
         j = _match_paren(s, s.index("("))
         ctl = [c.strip() for c in _split_top(s[s.index("(") + 1:j], ",")]
         u = self.ex(unit, parse_expr(ctl[0]))
         items = [a.strip() for a in _split_top(s[j + 1:], ",") if a.strip()]
-        if len(ctl) == 1:
-            raise rt.Unsupported("unformatted read")
+        if len(ctl) == 1:   # unformatted: one record
+            return [f"{pad}_rec = IO.read_unf({u})"] + self._unf_read_stmts(unit, pad, self._io_items(s[j + 1:]))
         if len(ctl) > 1 and ctl[1] != "*":
             if ctl[1].replace(" ", "").lower() in ("'(a)'", '"(a)"') and len(items) == 1:
                 return [pad + self.assign(unit, parse_expr(items[0]), f"IO.read_fmt_a({u})")]

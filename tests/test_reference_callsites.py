@@ -151,3 +151,58 @@ def test_bicg_spmv_laplace(ctx):
     assert its > 3
     assert_bit_equal(x_o, x_ref, "biCG solution")
     np.testing.assert_allclose(x_o[fix - 1], xf, rtol=1e-12)     # penalty rows hold the prescribed values
+
+
+def test_restart_files_both_directions(tmp_path):
+    """<name>.RST: the reference's PRINTREST output (unformatted sequential records, ns2DComp.ALE.f90:898-917) is byte-identical
+    to cfd_b200.deck.write_rst, and its RESTART (IRESTART = 1, :421-432) reads a file deck.write_rst wrote -- U, T and GAMM
+    restored, ITER/TIME read and dropped, velocities left as allocated (zero)."""
+    from cfd_b200 import deck, meshgen
+    from oracle import orclib
+    from oracle.f90ref.refrun import Reference
+    from oracle.orclib import Oracle
+
+    raw = meshgen.channel(nx=11, ny=5, FMU=1.8e-5, FK=0.0257)
+    raw.IPRINT = 2
+    ref = Reference()
+    ref.run_program(raw, maxiter=4)
+    g, v = ref.mod("mvariabgen"), ref.mod("mvariables")
+    P = int(ref.mod("meshdata").npoin)
+    rst = ref.io.binary[raw.name + ".RST"]
+    # the program's locals are gone; TIME is the second item of the first record
+    it, time = np.frombuffer(rst[4:8], "<i4")[0], np.frombuffer(rst[8:16], "<f8")[0]
+    assert it == 4 and time > 0
+    # PRINTREST is called before the loop's U = U1 (ns2DComp.ALE.f90:254 vs :277): the file holds the state the step STARTED
+    # from next to the temperature it ENDED with -- a quirk of the reference, reproduced here by feeding write_rst the same
+    T4 = v.t.copy()
+    ref.run_program(raw, maxiter=3)
+    U3 = ref.mod("mvariabgen").u.T.ravel().copy()
+    mine = tmp_path / "mine.RST"
+    deck.write_rst(str(mine), int(it), float(time), U3, T4, np.full(P, 1.4))
+    assert open(mine, "rb").read() == rst
+    it2, time2, U2, T2, G2 = deck.read_rst(str(mine), P)
+    assert (it2, time2) == (it, time) and np.array_equal(U2.ravel(), U3) and np.array_equal(T2, T4)
+    # restart from a perturbed file: one step of the reference program == one step of the oracle from the same state
+    rng = np.random.default_rng(2)
+    Ur = U2 * (1 + 1e-3 * rng.normal(size=U2.shape))
+    Tr = T2 * (1 + 1e-3 * rng.normal(size=P))
+    deck.write_rst(str(mine), 77, 0.25, Ur, Tr, G2)
+    raw2 = meshgen.channel(nx=11, ny=5, FMU=1.8e-5, FK=0.0257)
+    raw2.IPRINT, raw2.IRESTART = 1, 1
+    ref.run_program(raw2, maxiter=1, files={raw2.name + ".RST": open(mine, "rb").read()})
+    lc = deck.load(raw2)
+    orclib.lib().orc_smoothing(lc.X, lc.Y, lc.inpoel, lc.smooth_fix, lc.npoin, lc.nelem)
+    o = Oracle(lc)
+    o.set("U", Ur)
+    o.set("T", Tr)
+    o.set("VEL_X", np.zeros(P))           # RESTART does not restore the velocities (fresh ALLOCATE memory)
+    o.set("VEL_Y", np.zeros(P))
+    o.step(1)
+    # with the velocities unset the reference's first step after a restart produces NaNs around the bump (both sides, same
+    # entries); the sign bit of a NaN depends on the instruction that made it, so NaNs are compared by position
+    for name, a, b in (("U", o.get("U"), ref.mod("mvariabgen").u.T.ravel()), ("T", o.get("T"), ref.mod("mvariables").t)):
+        a, b = np.asarray(a), np.asarray(b)
+        assert np.array_equal(np.isnan(a), np.isnan(b)), name
+        ok = ~np.isnan(a)
+        assert ok.sum() > a.size // 2
+        assert_bit_equal(a[ok], b[ok], f"{name} one step after RESTART")
