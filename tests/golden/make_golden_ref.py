@@ -81,18 +81,6 @@ def run_reference(name):
 
     def hook(r):
         ns = r.ns
-        restart = ns["p___restart"]
-
-        def restart_with_bump(gamm, *a):
-            out = restart(gamm)
-            if st is not None:
-                r.mod("mvariabgen").u[...] = st["U"].T
-                r.mod("mvariables").t[...] = st["T"]
-                r.mod("mvelocidades").vel_x[...] = st["VEL_X"]
-                r.mod("mvelocidades").vel_y[...] = st["VEL_Y"]
-            return out
-
-        ns["p___restart"] = restart_with_bump
         fs = ns["p_meshmove__fluidstructure"]
 
         def fs_traced(dtmin, time, *a):
@@ -101,13 +89,9 @@ def run_reference(name):
             return fs(dtmin, time, *a)
 
         ns["p_meshmove__fluidstructure"] = fs_traced
-        if canon:
-            L = orclib.lib()
-            ns["p_biconjgrad__vecdot"] = lambda n, x, y, *a: np.float64(
-                L.orc_vecdot(int(n), np.ascontiguousarray(x), np.ascontiguousarray(y)))
 
     ref = Reference()
-    cnv = ref.run_program(raw, hook=hook)
+    cnv = ref.run_program(raw, hook=hook, initial_state=st, canonical_vecdot=canon)
     g, v, md = ref.mod("mvariabgen"), ref.mod("mvariables"), ref.mod("meshdata")
     vel, est, lap, pn = ref.mod("mvelocidades"), ref.mod("mestabilizacion"), ref.mod("mlaplace"), ref.mod("pointneighbor")
     nor, mm = ref.mod("mnormales"), ref.mod("meshmove")

@@ -12,8 +12,9 @@ import pytest
 
 from conftest import assert_bit_equal
 
-HAVE_REF = os.path.exists(os.path.join(os.environ.get("CFD_REFERENCE_DIR", "/root/reference"), "calcRHS.f90"))
-pytestmark = pytest.mark.skipif(not HAVE_REF, reason="the reference sources are not on this machine")
+from oracle.f90ref import refrun  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not refrun.available(), reason="neither the reference sources nor oracle/_ref/refprog.py are here")
 
 
 @pytest.fixture(scope="module")

@@ -25,8 +25,10 @@ spec.loader.exec_module(mg)
 
 from cfd_b200 import deck, meshgen  # noqa: E402
 
-HAVE_REF = os.path.exists(os.path.join(os.environ.get("CFD_REFERENCE_DIR", "/root/reference"), "calcRHS.f90"))
-needs_ref = pytest.mark.skipif(not HAVE_REF, reason="the reference sources are not on this machine")
+from oracle.f90ref import refrun  # noqa: E402
+
+HAVE_REF = refrun.available()       # /root/reference, or its translation oracle/_ref/refprog.py made by build()
+needs_ref = pytest.mark.skipif(not HAVE_REF, reason="neither the reference sources nor oracle/_ref/refprog.py are on this machine")
 BITEXACT_CASES = [n for n in mg.CASES if n != "ref_ale_seqdot"]
 
 
@@ -241,3 +243,37 @@ def test_gpu_matches_reference_program(name):
     from cfd_b200 import capi
     from cfd_b200.solver import NSComp2D
     run_and_check(lambda lc: NSComp2D(lc), name, lambda lc: capi.smoothing(lc))
+
+
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("kind", ["channel_visc", "ale_visc"])
+def test_gpu_against_the_reference_program_run_live(kind):
+    """PROGRAM NSComp2D interpreted on this machine (from /root/reference, or from the translation __graft_entry__.build()
+    left in oracle/_ref/, which travels to the GPU box) next to libcfdb200.so on the same deck: every array bit-identical."""
+    from cfd_b200 import capi
+    from cfd_b200.solver import NSComp2D
+
+    if kind == "channel_visc":
+        raw, bump, steps = meshgen.channel(nx=15, ny=7, FMU=1.8e-5, FK=0.0257, seed=77, jitter=0.3), True, 4
+    else:
+        raw, bump, steps = meshgen.ale_body(nt=24, nr=6, FMU=1.8e-5, FK=0.0257, seed=5), False, 3
+    raw.IPRINT, raw.MAXITER = 1, steps
+    st = meshgen.density_bump(deck.load(raw)) if bump else None
+    ref = refrun.Reference()
+    cnv = ref.run_program(raw, initial_state=st, canonical_vecdot=True)
+    lc = deck.load(raw)
+    capi.smoothing(lc)
+    g = NSComp2D(lc)
+    if st is not None:
+        for k, v in st.items():
+            g.set(k, v)
+    g.step(steps)
+    gen, var, md, vel, est, lap = (ref.mod(m) for m in ("mvariabgen", "mvariables", "meshdata", "mvelocidades", "mestabilizacion", "mlaplace"))
+    for name, a in (("U", gen.u.T.ravel()), ("RHS", gen.rhs.T.ravel()), ("T", var.t), ("P", var.p), ("RMACH", var.rmach),
+                    ("VEL_X", vel.vel_x), ("VEL_Y", vel.vel_y), ("W_X", vel.w_x), ("X", md.x), ("Y", md.y), ("M", md.m),
+                    ("SHOC", est.shoc), ("T_SUGN2", est.t_sugn2), ("T_SUGN3", est.t_sugn3), ("lap_sparse", lap.lap_sparse),
+                    ("F_VX", ref.mod("meshmove").f_vx), ("FX", ref.mod("meshmove").fx)):
+        assert_bit_equal(g.get(name), a, f"{kind}:{name}")
+    er, err = g.step_norms()
+    np.testing.assert_allclose(np.sqrt(er / err), [float(x) for x in cnv[-1][2:]], rtol=1e-12)
