@@ -53,8 +53,13 @@ CASES = {
     "ref_ale_visc": (lambda: meshgen.ale_body(nt=32, nr=8, FMU=1.8e-5, FK=0.0257), 4, False, True),
     # 1000 passes of the reference's time loop (about five minutes of interpretation): north_star's long-run tolerance
     "ref_channel_1000": (lambda: meshgen.channel(nx=17, ny=9, FMU=1.8e-5, FK=0.0257), 1000, True, False),
+    # BASELINE configs[0]'s mesh itself: 10 251 nodes / 20 000 triangles, smoothing included, three passes of the loop
+    # (a minute of interpretation per pass); only the arrays in SUBSET are kept, to bound the file size
+    "ref_channel_10k": (lambda: meshgen.channel(nx=201, ny=51, FMU=1.8e-5, FK=0.0257), 3, True, False),
 }
 IPRINT = {"ref_channel_1000": 100}
+SUBSET = {"ref_channel_10k": ["U", "RHS", "T", "X", "Y", "M", "SHOC", "T_SUGN2", "esup2", "psup2", "lap_rowptr", "n_m", "n_ipoin",
+                              "n_x", "n_y", "cnv", "dtmin", "time"]}
 NODE_FIELDS = ["T", "P", "RHO", "E", "RMACH", "VEL_X", "VEL_Y", "W_X", "W_Y", "X", "Y", "M"]
 ELEM_FIELDS = ["SHOC", "T_SUGN1", "T_SUGN2", "T_SUGN3", "area"]
 FIELDS = ["U", "RHS"] + NODE_FIELDS + ELEM_FIELDS + ["dNx", "dNy", "lap_sparse"]
@@ -117,6 +122,8 @@ def run_reference(name):
     if name == "ref_ale_visc":   # PRINTFLAVIA's GiD file of the last print step (MOVIE = 0: rewritten every time), byte for byte
         with open(os.path.join(HERE, name + ".flavia.res"), "w") as f:
             f.write("\n".join(ref.io.text[raw.name + ".flavia.res"]) + "\n")
+    if name in SUBSET:
+        out = {k: out[k] for k in SUBSET[name]}
     return {k: np.array(a) for k, a in out.items()}
 
 
@@ -125,7 +132,7 @@ def main():
     for name in (sys.argv[1:] or CASES):
         out = run_reference(name)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
-        print(name, "npoin", out["X"].size, "nelem", out["area"].size, "steps", len(out["dtmin"]), "cnv[-1]", out["cnv"][-1])
+        print(name, "npoin", out["X"].size, "nelem", out["SHOC"].size, "steps", len(out["dtmin"]), "cnv[-1]", out["cnv"][-1])
     print("x**1.5/.5/-.5 evaluations:", rt.pow_stats, "(glibc pow differs from the correctly rounded value in that many)")
 
 

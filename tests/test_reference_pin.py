@@ -47,10 +47,11 @@ def prepare(name, smoother):
 
 def check_state(solver, g, name, skip=()):
     for f in mg.FIELDS:
-        if f not in skip:
+        if f not in skip and f in g.files:          # the large case keeps a subset of the arrays (make_golden_ref.SUBSET)
             assert_bit_equal(solver.get(f), g[f], f"{name}:{f}")
     for f in mg.INT_FIELDS:
-        assert np.array_equal(solver.get(f), g[f]), f"{name}:{f}"
+        if f in g.files:
+            assert np.array_equal(solver.get(f), g[f]), f"{name}:{f}"
     m = int(g["n_m"][0])
     assert int(solver.scalar("n_m")) == m
     if m:
