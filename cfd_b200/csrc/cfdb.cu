@@ -561,8 +561,8 @@ extern "C" int cfdb_create(cfdb_ctx** out, const cfdb_params* par, int32_t npoin
     lap("BC tables");
     if (c->ale) B(zero(c, c->FC, 12 * E));
     if (!c->ale && getenv("CFDB_TILE") && atoi(getenv("CFDB_TILE")) != 0) {
-        // tiles for the fused stage (opt-in: measured slower than the two-kernel stage on B200 — 2.04 + 0.26 ms against
-        // 1.19 + 0.62 ms per stage on the 16 M-triangle mesh; the memory-bound node phase starves at the 12 warps/SM
+        // tiles for the fused stage (opt-in: measured slower than the two-kernel stage on B200 — 1.70 + 0.27 ms against
+        // 1.10 + 0.62 ms per stage on the 16 M-triangle mesh; the memory-bound node phase starves at the 12 warps/SM
         // the register-heavy element phase allows.  Bit-identical, covered by the GPU tests under CFDB_TILE=1.)
         topo::Tiling T;
         B(ensure_host_topology(c));
@@ -946,7 +946,7 @@ static int run_node(cfdb_ctx* c, cudaStream_t st, bool ale, bool update, double 
 static int run_stage_tile(cfdb_ctx* c, const k::Gas& g, const double* dtl_arr, const double* dtl_sc, double rk_fact) {
     const bool visc = g.mu_ref > 2.2250738585072014e-308;
     const int smem = 12 * 512 * (int)sizeof(double);
-    auto kern = visc ? k::stage_tile<true, 3> : k::stage_tile<false, 3>;
+    auto kern = visc ? k::stage_tile<true, 3> : k::stage_tile<false, 4>;   // Euler: 128 registers, four CTAs (4 x 48 KB) per SM
     static bool attr_done[2] = {false, false};
     if (!attr_done[visc]) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
