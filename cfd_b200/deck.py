@@ -180,9 +180,56 @@ def _r(x):
     return repr(float(x))
 
 
-def write_deck(raw: RawCase, directory: str) -> None:
-    """Write EULER.DAT, <name>-1.dat, <name>.dat in the layout dataLoader.f90 reads."""
+MESH_MAGIC = b"CFDBMSH1"
+
+
+def write_mesh_binary(raw: RawCase, path: str) -> None:
+    """<name>.cfdbmesh: the content of <name>.dat as little-endian raw arrays, in the order the text file lists them
+    (a text deck of a 16 M-triangle mesh is > 1 GB and takes minutes to parse).  Layout: magic, 12 int32
+    counts (npoin nelem nfixrho nfixvi nfixv nwall nfixt nsets nmaster nslave nfix_move nmove), X, Y (f64), inpoel (i32,
+    3 per element), then per list: node ids (i32) followed by its value columns (f64)."""
+    cnt = np.array([raw.npoin, raw.nelem, len(raw.fixrho[0]), len(raw.fixvi[0]), len(raw.fixv), len(raw.wall), len(raw.fixt[0]),
+                    len(raw.sets), len(raw.master), len(raw.slave), len(raw.ifm), len(raw.i_m)], I32)
+    with open(path, "wb") as f:
+        f.write(MESH_MAGIC)
+        f.write(cnt.tobytes())
+        for a, t in ((raw.X, F64), (raw.Y, F64), (raw.inpoel, I32), (raw.fixrho[0], I32), (raw.fixrho[1], F64),
+                     (raw.fixvi[0], I32), (raw.fixvi[1], F64), (raw.fixvi[2], F64), (raw.fixv, I32), (raw.wall, I32),
+                     (raw.fixt[0], I32), (raw.fixt[1], F64), (raw.sets, I32), (raw.master, I32), (raw.slave, I32),
+                     (raw.ifm, I32), (raw.i_m, I32)):
+            f.write(np.ascontiguousarray(np.asarray(a, t)).tobytes())
+
+
+def read_mesh_binary(path: str) -> dict:
+    with open(path, "rb") as f:
+        if f.read(8) != MESH_MAGIC:
+            raise ValueError(f"{path}: not a cfdb binary mesh")
+        cnt = np.frombuffer(f.read(48), I32)
+        npoin, nelem, nfixrho, nfixvi, nfixv, nwall, nfixt, nsets, nmaster, nslave, nfix_move, nmove = (int(c) for c in cnt)
+
+        def rd(n, t, shape=None):
+            a = np.frombuffer(f.read(n * np.dtype(t).itemsize), t).copy()
+            if a.size != n:
+                raise ValueError(f"{path}: truncated")
+            return a.reshape(shape) if shape else a
+
+        out = dict(X=rd(npoin, F64), Y=rd(npoin, F64), inpoel=rd(3 * nelem, I32, (nelem, 3)))
+        out["fixrho"] = (rd(nfixrho, I32), rd(nfixrho, F64))
+        out["fixvi"] = (rd(nfixvi, I32), rd(nfixvi, F64), rd(nfixvi, F64))
+        out["fixv"] = rd(nfixv, I32)
+        out["wall"] = rd(2 * nwall, I32, (nwall, 2))
+        out["fixt"] = (rd(nfixt, I32), rd(nfixt, F64))
+        out["sets"] = rd(4 * nsets, I32, (nsets, 4))
+        out["master"], out["slave"], out["ifm"], out["i_m"] = rd(nmaster, I32), rd(nslave, I32), rd(nfix_move, I32), rd(nmove, I32)
+    return out
+
+
+def write_deck(raw: RawCase, directory: str, binary_mesh: bool = False) -> None:
+    """Write EULER.DAT, <name>-1.dat, <name>.dat in the layout dataLoader.f90 reads (binary_mesh: <name>.cfdbmesh instead of
+    the text mesh file; read_deck and host/deck_reader.h prefer it when present)."""
     os.makedirs(directory, exist_ok=True)
+    if binary_mesh:
+        write_mesh_binary(raw, os.path.join(directory, raw.name + ".cfdbmesh"))
     with open(os.path.join(directory, "EULER.DAT"), "w") as f:
         f.write(raw.name + "\n")
     with open(os.path.join(directory, raw.name + "-1.dat"), "w") as f:
@@ -203,6 +250,8 @@ def write_deck(raw: RawCase, directory: str) -> None:
         w(" ".join(["'.si.'"] * 7) + "\n")
         w("--\n--\n--\nETA_REFIN HHMAX_REFIN HHMIN_REFIN\n")
         w("0.0 0.0 0.0\n")
+    if binary_mesh:
+        return
     with open(os.path.join(directory, raw.name + ".dat"), "w") as f:
         w = f.write
         w("NPOIN NELEM\n")
@@ -284,6 +333,13 @@ def read_deck(directory: str) -> RawCase:
     L.skip(); v = L.vals(); FK, FR, FCv, GAMA = (_fnum(x) for x in v[:4]); NGAS = int(v[4])
     L.skip(); CTE = _fnum(L.vals()[0])
     L.skip(2); v = L.vals(); MOVING = int(v[0]); XREF1, YREF1 = _fnum(v[1]), _fnum(v[2])
+    common = dict(name=name, IRESTART=IRESTART, MAXITER=MAXITER, IPRINT=IPRINT, MOVIE=MOVIE,
+                  ITLOCAL=ITLOCAL, FSAFE=FSAFE, U_inf=U_inf, V_inf=V_inf, MACH_inf=MACH_inf, T_inf=T_inf, RHO_inf=RHO_inf,
+                  P_inf=P_inf, FMU=FMU, FGX=FGX, FGY=FGY, QH=QH, FK=FK, FR=FR, FCv=FCv, GAMA=GAMA, NGAS=NGAS, CTE=CTE,
+                  MOVING=MOVING, XREF1=XREF1, YREF1=YREF1)
+    bin_path = os.path.join(directory, name + ".cfdbmesh")
+    if os.path.exists(bin_path):
+        return RawCase(**common, **read_mesh_binary(bin_path))
     M = _Lines(os.path.join(directory, name + ".dat"))
     M.skip(); npoin, nelem = (int(x) for x in M.vals()[:2])
     M.skip(); cnt = [int(x) for x in M.vals()[:10]]

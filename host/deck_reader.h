@@ -97,68 +97,104 @@ inline Deck read_deck(const std::string& dir) {
     p.C_inf = std::sqrt(p.GAMA * p.FR * p.T_inf);
     if (std::sqrt(p.U_inf * p.U_inf + p.V_inf * p.V_inf) == 0.0) p.U_inf = p.C_inf * p.MACH_inf;
 
-    Lines M(dir + "/" + d.name + ".dat");
-    M.skip(); auto v = M.read();
-    d.npoin = std::stoi(v.at(0)); d.nelem = std::stoi(v.at(1));
-    M.skip(); v = M.read();
-    int nfixrho = std::stoi(v.at(0)), nfixvi = std::stoi(v.at(1)), nfixv = std::stoi(v.at(2)), nwall = std::stoi(v.at(3)), nfixt = std::stoi(v.at(4)),
-        nsets = std::stoi(v.at(5)), nmaster = std::stoi(v.at(6)), nslave = std::stoi(v.at(7)), nfix_move = std::stoi(v.at(8)), nmove = std::stoi(v.at(9));
-    M.skip(4);
-    d.X.assign(d.npoin, 0.0); d.Y.assign(d.npoin, 0.0); d.inpoel.assign(3 * (size_t)d.nelem, 0);
-    for (int k = 0; k < d.npoin; ++k) {
-        v = M.read();
-        int i = std::stoi(v.at(0));
-        if (i < 1 || i > d.npoin) throw std::runtime_error("ERROR EN LA LECTURA DE NODOS");
-        d.X[i - 1] = num(v.at(1)); d.Y[i - 1] = num(v.at(2));
+    // raw lists of <name>.dat: from the binary side-car <name>.cfdbmesh when present (same content, little-endian arrays:
+    // cfd_b200/deck.py write_mesh_binary), else from the text file in dataLoader.f90's read order (:98-255)
+    std::vector<int32_t> r_fixrho_n, r_fixvi_n, r_fixv_n, r_fixt_n;
+    std::vector<double> r_fixrho_v, r_fixvi_x, r_fixvi_y, r_fixt_v;
+    int nmaster = 0, nslave = 0;
+    std::ifstream bin(dir + "/" + d.name + ".cfdbmesh", std::ios::binary);
+    if (bin) {
+        char magic[8];
+        int32_t cnt[12];
+        bin.read(magic, 8);
+        bin.read(reinterpret_cast<char*>(cnt), sizeof cnt);
+        if (!bin || std::string(magic, 8) != "CFDBMSH1") throw std::runtime_error("not a cfdb binary mesh: " + d.name + ".cfdbmesh");
+        d.npoin = cnt[0]; d.nelem = cnt[1];
+        nmaster = cnt[8]; nslave = cnt[9];
+        auto rd_i = [&](std::vector<int32_t>& v, size_t n) { v.resize(n); bin.read(reinterpret_cast<char*>(v.data()), n * sizeof(int32_t)); };
+        auto rd_d = [&](std::vector<double>& v, size_t n) { v.resize(n); bin.read(reinterpret_cast<char*>(v.data()), n * sizeof(double)); };
+        rd_d(d.X, d.npoin); rd_d(d.Y, d.npoin); rd_i(d.inpoel, 3 * (size_t)d.nelem);
+        rd_i(r_fixrho_n, cnt[2]); rd_d(r_fixrho_v, cnt[2]);
+        rd_i(r_fixvi_n, cnt[3]); rd_d(r_fixvi_x, cnt[3]); rd_d(r_fixvi_y, cnt[3]);
+        rd_i(r_fixv_n, cnt[4]);
+        rd_i(d.wall, 2 * (size_t)cnt[5]);
+        rd_i(r_fixt_n, cnt[6]); rd_d(r_fixt_v, cnt[6]);
+        std::vector<int32_t> sets;
+        rd_i(sets, 4 * (size_t)cnt[7]);
+        for (int k = 0; k < cnt[7]; ++k) {
+            d.iset_elem.push_back(sets[4 * k]); d.iset_n1.push_back(sets[4 * k + 1]); d.iset_n2.push_back(sets[4 * k + 2]); d.iset_id.push_back(sets[4 * k + 3]);
+        }
+        rd_i(d.master, cnt[8]); rd_i(d.slave, cnt[9]); rd_i(d.ifm, cnt[10]); rd_i(d.i_m, cnt[11]);
+        if (!bin) throw std::runtime_error("truncated binary mesh: " + d.name + ".cfdbmesh");
+    } else {
+        Lines M(dir + "/" + d.name + ".dat");
+        M.skip(); auto v = M.read();
+        d.npoin = std::stoi(v.at(0)); d.nelem = std::stoi(v.at(1));
+        M.skip(); v = M.read();
+        int nfixrho = std::stoi(v.at(0)), nfixvi = std::stoi(v.at(1)), nfixv = std::stoi(v.at(2)), nwall = std::stoi(v.at(3)), nfixt = std::stoi(v.at(4)),
+            nsets = std::stoi(v.at(5)), nfix_move = std::stoi(v.at(8)), nmove = std::stoi(v.at(9));
+        nmaster = std::stoi(v.at(6)); nslave = std::stoi(v.at(7));
+        M.skip(4);
+        d.X.assign(d.npoin, 0.0); d.Y.assign(d.npoin, 0.0); d.inpoel.assign(3 * (size_t)d.nelem, 0);
+        for (int k = 0; k < d.npoin; ++k) {
+            v = M.read();
+            int i = std::stoi(v.at(0));
+            if (i < 1 || i > d.npoin) throw std::runtime_error("ERROR EN LA LECTURA DE NODOS");
+            d.X[i - 1] = num(v.at(1)); d.Y[i - 1] = num(v.at(2));
+        }
+        M.skip();
+        for (int k = 0; k < d.nelem; ++k) {
+            v = M.read();
+            int i = std::stoi(v.at(0));
+            if (i < 1 || i > d.nelem) throw std::runtime_error("ERROR EN LA LECTURA DE ELEMENTOS");
+            for (int j = 0; j < 3; ++j) d.inpoel[3 * (size_t)(i - 1) + j] = std::stoi(v.at(1 + j));
+        }
+        M.skip();
+        for (int k = 0; k < nfixrho; ++k) { v = M.read(); r_fixrho_n.push_back(std::stoi(v.at(0))); r_fixrho_v.push_back(num(v.at(1))); }
+        M.skip();
+        for (int k = 0; k < nfixvi; ++k) { v = M.read(); r_fixvi_n.push_back(std::stoi(v.at(0))); r_fixvi_x.push_back(num(v.at(1))); r_fixvi_y.push_back(num(v.at(2))); }
+        M.skip();
+        for (int k = 0; k < nfixv; ++k) { v = M.read(); r_fixv_n.push_back(std::stoi(v.at(0))); }
+        M.skip();
+        for (int k = 0; k < nwall; ++k) { v = M.read(); d.wall.push_back(std::stoi(v.at(0))); d.wall.push_back(std::stoi(v.at(1))); }
+        M.skip();
+        for (int k = 0; k < nfixt; ++k) { v = M.read(); r_fixt_n.push_back(std::stoi(v.at(0))); r_fixt_v.push_back(num(v.at(1))); }
+        M.skip();
+        for (int k = 0; k < nsets; ++k) {
+            v = M.read();
+            d.iset_elem.push_back(std::stoi(v.at(0))); d.iset_n1.push_back(std::stoi(v.at(1))); d.iset_n2.push_back(std::stoi(v.at(2))); d.iset_id.push_back(std::stoi(v.at(3)));
+        }
+        if (nmaster != nslave) throw std::runtime_error("ERROR NODOS MASTER DISTINTO NODOS SLAVE");  // :223-226
+        M.skip();
+        for (int k = 0; k < nmaster; ++k) d.master.push_back(std::stoi(M.read().at(0)));
+        M.skip();
+        for (int k = 0; k < nmaster; ++k) d.slave.push_back(std::stoi(M.read().at(0)));
+        M.skip();
+        for (int k = 0; k < nfix_move; ++k) d.ifm.push_back(std::stoi(M.read().at(0)));
+        M.skip();
+        for (int k = 0; k < nmove; ++k) d.i_m.push_back(std::stoi(M.read().at(0)));
     }
-    M.skip();
-    for (int k = 0; k < d.nelem; ++k) {
-        v = M.read();
-        int i = std::stoi(v.at(0));
-        if (i < 1 || i > d.nelem) throw std::runtime_error("ERROR EN LA LECTURA DE ELEMENTOS");
-        for (int j = 0; j < 3; ++j) d.inpoel[3 * (size_t)(i - 1) + j] = std::stoi(v.at(1 + j));
+    if (nmaster != nslave) throw std::runtime_error("ERROR NODOS MASTER DISTINTO NODOS SLAVE");  // :223-226
+    // post-processing of the lists, dataLoader.f90:121-198
+    for (size_t k = 0; k < r_fixrho_n.size(); ++k) {  // :121-130
+        d.ifixrho_node.push_back(r_fixrho_n[k]);
+        d.rfixrho_value.push_back(r_fixrho_v[k] < 0 ? 1.225 : r_fixrho_v[k] * p.RHO_inf);
     }
-    M.skip();
-    for (int k = 0; k < nfixrho; ++k) {  // :121-130
-        v = M.read();
-        double val = num(v.at(1));
-        d.ifixrho_node.push_back(std::stoi(v.at(0)));
-        d.rfixrho_value.push_back(val < 0 ? 1.225 : val * p.RHO_inf);
-    }
-    M.skip();
-    for (int k = 0; k < nfixvi; ++k) {  // :136-143
-        v = M.read();
-        d.ifixv_node.push_back(std::stoi(v.at(0)));
-        d.rfixv_valuex.push_back(num(v.at(1)) * p.U_inf);
-        d.rfixv_valuey.push_back(num(v.at(2)) * p.V_inf);
+    for (size_t k = 0; k < r_fixvi_n.size(); ++k) {  // :136-143
+        d.ifixv_node.push_back(r_fixvi_n[k]);
+        d.rfixv_valuex.push_back(r_fixvi_x[k] * p.U_inf);
+        d.rfixv_valuey.push_back(r_fixvi_y[k] * p.V_inf);
     }
     // TWALL is implicitly typed single precision (dataLoader.f90:147)
     float TWALL = (float)(p.T_inf * (1.0 + (p.GAMA - 1) / 2.0 * p.MACH_inf * p.MACH_inf));
-    M.skip();
-    for (int k = 0; k < nfixv; ++k) {  // :152-161
-        v = M.read();
-        int n = std::stoi(v.at(0));
+    for (int n : r_fixv_n) {  // :152-161: no-slip nodes, then they also join the fixed-temperature list
         d.ifixv_node.push_back(n); d.rfixv_valuex.push_back(0.0); d.rfixv_valuey.push_back(0.0);
-        d.ifixt_node.push_back(n); d.rfixt_value.push_back((double)TWALL);
     }
-    M.skip();
-    for (int k = 0; k < nwall; ++k) { v = M.read(); d.wall.push_back(std::stoi(v.at(0))); d.wall.push_back(std::stoi(v.at(1))); }
-    M.skip();
-    for (int k = 0; k < nfixt; ++k) { v = M.read(); d.ifixt_node.push_back(std::stoi(v.at(0))); d.rfixt_value.push_back(num(v.at(1)) * p.T_inf); }
-    M.skip();
-    for (int k = 0; k < nsets; ++k) {
-        v = M.read();
-        d.iset_elem.push_back(std::stoi(v.at(0))); d.iset_n1.push_back(std::stoi(v.at(1))); d.iset_n2.push_back(std::stoi(v.at(2))); d.iset_id.push_back(std::stoi(v.at(3)));
-    }
-    if (nmaster != nslave) throw std::runtime_error("ERROR NODOS MASTER DISTINTO NODOS SLAVE");  // :223-226
-    M.skip();
-    for (int k = 0; k < nmaster; ++k) d.master.push_back(std::stoi(M.read().at(0)));
-    M.skip();
-    for (int k = 0; k < nmaster; ++k) d.slave.push_back(std::stoi(M.read().at(0)));
-    M.skip();
-    for (int k = 0; k < nfix_move; ++k) d.ifm.push_back(std::stoi(M.read().at(0)));
-    M.skip();
-    for (int k = 0; k < nmove; ++k) d.i_m.push_back(std::stoi(M.read().at(0)));
+    std::vector<int32_t> t_nodes;
+    std::vector<double> t_vals;
+    for (int n : r_fixv_n) { t_nodes.push_back(n); t_vals.push_back((double)TWALL); }
+    for (size_t k = 0; k < r_fixt_n.size(); ++k) { t_nodes.push_back(r_fixt_n[k]); t_vals.push_back(r_fixt_v[k] * p.T_inf); }
+    d.ifixt_node = t_nodes; d.rfixt_value = t_vals;
     d.smooth_fix.assign(d.npoin, 0);
     for (int n : d.i_m) d.smooth_fix.at(n - 1) = 1;
     for (int n : d.ifm) d.smooth_fix.at(n - 1) = 1;

@@ -36,6 +36,35 @@ def test_deck_reader_and_smoothing_match_oracle(tmp_path):
     assert_bit_equal(np.fromfile(fy), Y, "smoothed Y")
 
 
+def test_binary_mesh_sidecar_reads_like_the_text_deck(tmp_path):
+    """<name>.cfdbmesh (binary side-car for meshes whose text deck would be gigabytes): the C++ reader and the
+    Python reader give exactly what they give for the text file -- same post-processed lists, same smoothing result."""
+    _build()
+    raw = meshgen.ale_body(nt=24, nr=6, FMU=1.8e-5, FK=0.0257)
+    raw.fixv = np.array([30, 31], np.int32)
+    raw.fixt = (np.array([40, 41], np.int32), np.array([1.1, 0.9]))
+    a, b = tmp_path / "text", tmp_path / "bin"
+    deck.write_deck(raw, str(a))
+    deck.write_deck(raw, str(b), binary_mesh=True)
+    assert not (b / (raw.name + ".dat")).exists() and (b / (raw.name + ".cfdbmesh")).exists()
+    ra, rb = deck.read_deck(str(a)), deck.read_deck(str(b))
+    la, lb = deck.load(ra), deck.load(rb)
+    for f in ("X", "Y", "inpoel", "ifixrho_node", "rfixrho_value", "ifixv_node", "rfixv_valuex", "rfixv_valuey", "wall", "ifixt_node",
+              "rfixt_value", "sets", "ifm", "i_m", "ilaux", "smooth_fix"):
+        assert np.array_equal(getattr(la, f), getattr(lb, f)), f
+    outs = []
+    for d in (a, b):
+        fx = str(d / "x.bin")
+        r = subprocess.run([EXE, str(d), "--check-deck", "--dump", "X:" + fx], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        outs.append((r.stdout, np.fromfile(fx)))
+    assert outs[0][0] == outs[1][0] and "sweeps:" in outs[0][0]
+    assert_bit_equal(outs[0][1], outs[1][1], "smoothed X")
+    (b / (raw.name + ".cfdbmesh")).write_bytes(b"garbage!" + bytes(100))
+    r = subprocess.run([EXE, str(b), "--check-deck"], capture_output=True, text=True)
+    assert r.returncode != 0 and "binary mesh" in r.stderr
+
+
 def test_bad_deck_stops(tmp_path):
     _build()
     r = subprocess.run([EXE, str(tmp_path), "--check-deck"], capture_output=True, text=True)
