@@ -94,13 +94,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_oracle_throughput(n_lattice, steps, warmup=1):
-    """Element updates/s of the oracle's OpenMP build (C++ restatement of the reference) on the host cores."""
+def cpu_oracle_throughput(n_lattice, steps, warmup=1, omp=True):
+    """Element updates/s of the oracle (C++ restatement of the reference) on the host: the OpenMP build on all cores, or the
+    sequential build (the order the parity tests use) on one."""
     from cfd_b200 import deck, meshgen
     from oracle.orclib import Oracle
 
     lc = deck.load(meshgen.square(n=n_lattice, IPRINT=10**9, MAXITER=10**9))
-    o = Oracle(lc, omp=True)
+    o = Oracle(lc, omp=omp)
     o.set_scalar("norms_every_step", 0)
     st = meshgen.density_bump(lc)
     for k, v in st.items():
@@ -109,7 +110,7 @@ def cpu_oracle_throughput(n_lattice, steps, warmup=1):
     t0 = time.perf_counter()
     o.step(steps)
     dt = time.perf_counter() - t0
-    return lc.nelem * steps / dt, o.L.orc_omp_threads(), lc.nelem, dt
+    return lc.nelem * steps / dt, (o.L.orc_omp_threads() if omp else 1), lc.nelem, dt
 
 
 def run_reference(args, rank, out):
@@ -309,9 +310,12 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         v, cores, ne, dt = cpu_oracle_throughput(args.ref_n, args.cpu_steps)
+        v1, _, ne1, dt1 = cpu_oracle_throughput(709, 3, omp=False)     # threads = 1 next to all cores
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{ne}-triangle square mesh, {args.cpu_steps} steps ({dt:.1f} s), oracle OpenMP build "
-                         "(C++ restatement; the Fortran reference cannot be built here)"}
+                         "(C++ restatement; the Fortran reference cannot be built here)",
+               "single_thread": {"value": v1, "cores": 1, "sample": f"{ne1}-triangle square mesh, 3 steps ({dt1:.1f} s), "
+                                 "sequential build (the summation order of the parity tests)"}}
 
     if rank == 0:
         print(json.dumps({
