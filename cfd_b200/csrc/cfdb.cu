@@ -928,7 +928,7 @@ static int run_node(cfdb_ctx* c, cudaStream_t st, bool ale, bool update, double 
                     const int* nlist = nullptr) {
     if (n1 < 0) n1 = c->npoin;
     if (n1 <= n0) return 0;
-    const int B = 256, G = grid_for(n1 - n0, B);
+    const int B = CFDB_NODE_BS, G = grid_for(n1 - n0, B);
 #define ARGS n0, n1, nlist, c->d_esup2.p, c->eslot.p, (c->ECcur ? c->ECcur : c->EC.p), (c->FCcur ? c->FCcur : c->FC.p), c->U.p, c->M.p, c->GAMM.p, c->W_X.p, c->W_Y.p, \
              c->bcflag.p, bctab(c), rk_fact, c->par.FR, c->U1.p, c->RHS.p, c->RHO.p, c->VEL_X.p, c->VEL_Y.p, c->E.p, \
              c->P.p, c->T.p, c->RMACH.p

@@ -758,13 +758,17 @@ __device__ __forceinline__ void node_finish(int n, const double (&acc)[4], const
     RHO[n] = rho; VELX[n] = vx; VELY[n] = vy; Ea[n] = en; Pa[n] = p; Ta[n] = t; RMACH[n] = mach;
 }
 
-// 5 CTAs of 256 threads per SM (48 registers, 40 warps): measured 0.575 ms per launch on the 16 M-triangle mesh against
-// 0.617 at the compiler's own choice (56 registers, 32 warps), 0.579 at 6 CTAs, 0.65 at 8 (profiles/r1_experiments.md)
+// 40 warps per SM at 48 registers, in CTAs of 128 threads: measured 0.557 ms per launch on the 16 M-triangle mesh against
+// 0.617 at the compiler's own choice (256 threads, 56 registers, 32 warps); 256 x 5: 0.569, 256 x 6: 0.579, 256 x 8: 0.65,
+// 128 x 8 (64 registers): 0.592, 64 x 20: 0.550, 512 x 2: 0.63 (profiles/r1_experiments.md)
 #ifndef CFDB_NODE_MINB
-#define CFDB_NODE_MINB 5
+#define CFDB_NODE_MINB 10
+#endif
+#ifndef CFDB_NODE_BS
+#define CFDB_NODE_BS 128
 #endif
 template <bool ALE, bool UPDATE>
-__global__ void __launch_bounds__(256, CFDB_NODE_MINB) node_update(int n0, int n1, const int* __restrict__ nlist, const int* __restrict__ esup2, const int* __restrict__ eslot,
+__global__ void __launch_bounds__(CFDB_NODE_BS, CFDB_NODE_MINB) node_update(int n0, int n1, const int* __restrict__ nlist, const int* __restrict__ esup2, const int* __restrict__ eslot,
                                                     const double* __restrict__ EC, const double* __restrict__ FC,
                                                     const double* __restrict__ U, const double* __restrict__ M,
                                                     const double* __restrict__ GAMM, const double* __restrict__ WXa,
