@@ -832,12 +832,21 @@ static k::BcTab bctab(cfdb_ctx* c) {
 
 static int run_estab(cfdb_ctx* c, const double* dtmin_dev) {
     const cfdb_params& p = c->par;
-    static int minb = getenv("CFDB_ESTAB_MINB") ? atoi(getenv("CFDB_ESTAB_MINB")) : 5;  // 48 regs, 40 warps/SM: 1.01 ms vs 1.29
-    auto kern = k::estab<3>;
-    if (minb == 4) kern = k::estab<4>;
-    else if (minb == 5) kern = k::estab<5>;
-    else if (minb == 6) kern = k::estab<6>;
-    else if (minb == 2) kern = k::estab<2>;
+    // branch-free estab_fast: 64 regs without spills (MINB 4) 0.617 ms, 48 regs (5) 0.676, 40 regs (6) 0.809; the plain form was 1.06
+    static int minb = getenv("CFDB_ESTAB_MINB") ? atoi(getenv("CFDB_ESTAB_MINB")) : 4;
+    auto kern = k::estab<3, true>;
+    if (c->ale) {
+        if (minb == 4) kern = k::estab<4, true>;
+        else if (minb == 5) kern = k::estab<5, true>;
+        else if (minb == 6) kern = k::estab<6, true>;
+        else if (minb == 2) kern = k::estab<2, true>;
+    } else {  // fixed mesh: W_X = W_Y = +0 (cfdb_set of either turns c->ale on)
+        if (minb == 4) kern = k::estab<4, false>;
+        else if (minb == 5) kern = k::estab<5, false>;
+        else if (minb == 6) kern = k::estab<6, false>;
+        else if (minb == 2) kern = k::estab<2, false>;
+        else kern = k::estab<3, false>;
+    }
     LAUNCH(K_ESTAB, kern, grid_for(c->nelem, 256), 256, c->nelem, c->inp.p, c->U.p, c->T.p, c->VEL_X.p, c->VEL_Y.p,
            c->W_X.p, c->W_Y.p, c->GAMM.p, c->dNx.p, c->dNy.p, p.FR, dtmin_dev, p.RHO_inf, p.T_inf, c->SHOC.p, c->TS1.p,
            c->TS2.p, c->TS3.p);
@@ -879,33 +888,44 @@ static int run_calcrhs_elem(cfdb_ctx* c, const k::Gas& g, bool theta, bool ale, 
         return 0;
     }
     int sel = (visc ? 4 : 0) | (theta ? 2 : 0) | (ale ? 1 : 0);
+    // defaults from the A/B runs in profiles/r1_experiments.md
+#ifndef CFDB_NB_DEFAULT
+#define CFDB_NB_DEFAULT(visc) (visc)
+#endif
+#ifndef CFDB_MINB_DEFAULT
+#define CFDB_MINB_DEFAULT(visc, nb) (((visc) && (nb)) ? 3 : 4)
+#endif
     // 4 CTAs/SM (128 registers, 16 warps/SM) is the measured optimum once the nine Gauss-point divisions are issued
     // up front: 1.11 ms per launch against 1.23 (3 CTAs), 1.33 (5), 1.88 (6) on the 16 M-triangle mesh
-    static int minb = getenv("CFDB_CALCRHS_MINB") ? atoi(getenv("CFDB_CALCRHS_MINB")) : 4;
-#define PICK(M)                                                                 \
-    switch (sel) {                                                              \
-        case 0: kern = k::calcrhs_elem<false, false, false, M>; break;          \
-        case 1: kern = k::calcrhs_elem<false, false, true, M>; break;           \
-        case 2: kern = k::calcrhs_elem<false, true, false, M>; break;           \
-        case 3: kern = k::calcrhs_elem<false, true, true, M>; break;            \
-        case 4: kern = k::calcrhs_elem<true, false, false, M>; break;           \
-        case 5: kern = k::calcrhs_elem<true, false, true, M>; break;            \
-        case 6: kern = k::calcrhs_elem<true, true, false, M>; break;            \
-        default: kern = k::calcrhs_elem<true, true, true, M>; break;            \
+    static const int minb_env = getenv("CFDB_CALCRHS_MINB") ? atoi(getenv("CFDB_CALCRHS_MINB")) : 0;
+    // branch-free division forms (kernels.cuh: calcrhs_one<.., NB>): CFDB_CALCRHS_NB=0/1 forces them off/on
+    static const int nb_env = getenv("CFDB_CALCRHS_NB") ? atoi(getenv("CFDB_CALCRHS_NB")) : -1;
+    const bool nb = nb_env >= 0 ? nb_env != 0 : CFDB_NB_DEFAULT(visc);
+    const int minb = minb_env ? minb_env : CFDB_MINB_DEFAULT(visc, nb);
+#define PICK(M)                                                                                                   \
+    switch (sel | (nb ? 8 : 0)) {                                                                                 \
+        case 0: kern = k::calcrhs_elem<false, false, false, M>; break;                                            \
+        case 1: kern = k::calcrhs_elem<false, false, true, M>; break;                                             \
+        case 2: kern = k::calcrhs_elem<false, true, false, M>; break;                                             \
+        case 3: kern = k::calcrhs_elem<false, true, true, M>; break;                                              \
+        case 4: kern = k::calcrhs_elem<true, false, false, M>; break;                                             \
+        case 5: kern = k::calcrhs_elem<true, false, true, M>; break;                                              \
+        case 6: kern = k::calcrhs_elem<true, true, false, M>; break;                                              \
+        case 7: kern = k::calcrhs_elem<true, true, true, M>; break;                                               \
+        case 8: kern = k::calcrhs_elem<false, false, false, M, 128, true>; break;                                 \
+        case 9: kern = k::calcrhs_elem<false, false, true, M, 128, true>; break;                                  \
+        case 10: kern = k::calcrhs_elem<false, true, false, M, 128, true>; break;                                 \
+        case 11: kern = k::calcrhs_elem<false, true, true, M, 128, true>; break;                                  \
+        case 12: kern = k::calcrhs_elem<true, false, false, M, 128, true>; break;                                 \
+        case 13: kern = k::calcrhs_elem<true, false, true, M, 128, true>; break;                                  \
+        case 14: kern = k::calcrhs_elem<true, true, false, M, 128, true>; break;                                  \
+        default: kern = k::calcrhs_elem<true, true, true, M, 128, true>; break;                                   \
     }
     void (*kern)(int, int, int, const int*, const double*, const double*, const double*, const double*, const double*, const double*,
                  const double*, const double*, const double*, const double*, const double*, const double*, const double*,
                  const double*, k::Gas, double*, double*) = nullptr;
-    if (minb == 3) { PICK(3) } else if (minb == 4) { PICK(4) } else if (minb == 5) { PICK(5) } else if (minb == 6) { PICK(6) } else if (minb == 2) { PICK(2) } else { PICK(1) }
+    if (minb == 3) { PICK(3) } else if (minb == 5) { PICK(5) } else { PICK(4) }
 #undef PICK
-    // experiment: 64-thread CTAs, 7 per SM (<=146 registers, 14 warps/SM)
-    static const int bs = getenv("CFDB_CALCRHS_BS") ? atoi(getenv("CFDB_CALCRHS_BS")) : 128;
-    if (bs != 128 && sel == 0) {
-        if (bs == 64) { kern = k::calcrhs_elem<false, false, false, 8, 64>; LAUNCH(K_CALCRHS, kern, grid_for(e1 - e0, 64), 64, ARGS); }
-        else if (bs == 32) { kern = k::calcrhs_elem<false, false, false, 16, 32>; LAUNCH(K_CALCRHS, kern, grid_for(e1 - e0, 32), 32, ARGS); }
-        else { kern = k::calcrhs_elem<false, false, false, 2, 256>; LAUNCH(K_CALCRHS, kern, grid_for(e1 - e0, 256), 256, ARGS); }
-        return 0;
-    }
     // experiment (CFDB_CALCRHS_PAD_KB): unused dynamic shared memory caps the CTAs per SM below what the registers allow,
     // leaving register-file room for node_update CTAs of the previous stage to be co-resident (CFDB_STAGE_OVERLAP)
     static const int pad_kb = getenv("CFDB_CALCRHS_PAD_KB") ? atoi(getenv("CFDB_CALCRHS_PAD_KB")) : 0;
@@ -1358,12 +1378,12 @@ static int step_once(cfdb_ctx* c) {
     const size_t P = c->npoin;
     c->h_iter += 1;
     LAUNCH(K_DTLOGIC, k::step_begin, 1, 1, c->sc);
-    if (p.ITLOCAL != 0)
-        LAUNCH(K_DELTAT, k::deltat<true>, grid_for(E, 256), 256, E, c->inp.p, c->area.p, c->T.p, c->VEL_X.p, c->VEL_Y.p,
+    {
+        auto kdt = p.ITLOCAL != 0 ? (c->ale ? k::deltat<true, true> : k::deltat<true, false>)
+                                  : (c->ale ? k::deltat<false, true> : k::deltat<false, false>);
+        LAUNCH(K_DELTAT, kdt, grid_for(E, 256), 256, E, c->inp.p, c->area.p, c->T.p, c->VEL_X.p, c->VEL_Y.p,
                c->W_X.p, c->W_Y.p, p.FSAFE, p.T_inf, c->DT.p, c->sc);
-    else
-        LAUNCH(K_DELTAT, k::deltat<false>, grid_for(E, 256), 256, E, c->inp.p, c->area.p, c->T.p, c->VEL_X.p, c->VEL_Y.p,
-               c->W_X.p, c->W_Y.p, p.FSAFE, p.T_inf, c->DT.p, c->sc);
+    }
     TRY(allreduce(c, &c->sc->dtmin_acc, 1, ncclMin));
     LAUNCH(K_DTLOGIC, k::dt_logic, 1, 1, c->sc);
     if (p.ITLOCAL != 0) {

@@ -18,6 +18,9 @@
 #ifndef CFDB_KNS
 #define CFDB_KNS k
 #endif
+#ifndef CFDB_BATCH_DIV
+#define CFDB_BATCH_DIV 1
+#endif
 namespace CFDB_KNS {
 
 // device-resident loop scalars (ns2DComp.ALE.f90:109-166) and reduction results
@@ -135,7 +138,66 @@ __global__ void normales(int nwn, const int* __restrict__ wn_node, const int* __
 
 // ---------------------------------------------------------------------------------------------
 // deltat (subrutinas.f90:172-210) : one thread per element + exact global min
-template <bool WRITE_DT>
+// Gathers first, MOVING as in estab; the kernel runs the branch-free forms (NB) and falls back per element like estab.
+template <bool MOVING, bool NB>
+__device__ __forceinline__ double deltat_elem(int e, int nelem, const int* __restrict__ inp, const double* __restrict__ area,
+                                              const double* __restrict__ T, const double* __restrict__ VX,
+                                              const double* __restrict__ VY, const double* __restrict__ WX,
+                                              const double* __restrict__ WY, double FSAFE, double T_inf, unsigned& bad) {
+    int n[3] = {inp[e], inp[nelem + e], inp[2 * (size_t)nelem + e]};
+    const double tsum = T[n[0]] + T[n[1]] + T[n[2]];
+    double vu[3], vv[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        vu[i] = VX[n[i]];
+        vv[i] = VY[n[i]];
+        if (MOVING) {
+            vu[i] = vu[i] - WX[n[i]];
+            vv[i] = vv[i] - WY[n[i]];
+        }
+    }
+    const double ar = area[e];
+    double T_iel = NB ? ex::div3_nb(tsum, bad) : ex::div3(tsum);
+    double VUMAX = 0.0, VVMAX = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        double VU = fabs(vu[i]);
+        double VV = fabs(vv[i]);
+        if (VU > VUMAX) VUMAX = VU;
+        if (VV > VVMAX) VVMAX = VV;
+    }
+    double smu = 110.0;
+    if (NB) {
+        double HH = ex::sqrt_nb(2.0 * ar, bad);
+        double VEL = ex::sqrt_nb(VUMAX * VUMAX + VVMAX * VVMAX, bad);  // = pow05: a sum of squares is never -0
+        double ET = ex::Recip(T_iel + smu).div(0.017 * ex::pow15_nb(ex::Recip(T_inf).div(T_iel, bad), bad) * (T_inf + smu), bad);
+        double Pe = ex::Recip(2.0 * ET).div(VEL * HH, bad);
+        double ALPHA = ex::fmin2(ex::div3_nb(Pe, bad), 1.0);
+        const double a4 = ex::Recip(HH * HH).div(4.0 * ET, bad);
+        const double av = ex::Recip(HH).div(ALPHA * VEL, bad);
+        double DELTATU = ex::Recip(a4 + av).div(1.0, bad);
+        double DELTATC = ex::Recip(a4).div(1.0, bad);
+        return ex::Recip(ex::Recip(DELTATC).div(1.0, bad) + ex::Recip(DELTATU).div(1.0, bad)).div(FSAFE, bad);
+    }
+    double HH = sqrt(2.0 * ar);
+    double VEL = ex::pow05(VUMAX * VUMAX + VVMAX * VVMAX);
+    double fmu = 0.017 * ex::pow15(T_iel / T_inf) * (T_inf + smu) / (T_iel + smu);
+    double ET = fmu;
+    double Pe = (VEL * HH) / (2.0 * ET);
+    double ALPHA = ex::fmin2(ex::div3(Pe), 1.0);
+    double DELTATU = 1.0 / (4.0 * ET / (HH * HH) + ALPHA * VEL / HH);
+    double DELTATC = 1.0 / (4.0 * ET / (HH * HH));
+    return FSAFE / (1.0 / DELTATC + 1.0 / DELTATU);
+}
+template <bool MOVING>
+__device__ __noinline__ double deltat_plain(int e, int nelem, const int* __restrict__ inp, const double* __restrict__ area,
+                                            const double* __restrict__ T, const double* __restrict__ VX,
+                                            const double* __restrict__ VY, const double* __restrict__ WX,
+                                            const double* __restrict__ WY, double FSAFE, double T_inf) {
+    unsigned bad = 0;
+    return deltat_elem<MOVING, false>(e, nelem, inp, area, T, VX, VY, WX, WY, FSAFE, T_inf, bad);
+}
+template <bool WRITE_DT, bool MOVING = true>
 __global__ void __launch_bounds__(256) deltat(int nelem, const int* __restrict__ inp, const double* __restrict__ area,
                                                const double* __restrict__ T, const double* __restrict__ VX,
                                                const double* __restrict__ VY, const double* __restrict__ WX,
@@ -144,26 +206,13 @@ __global__ void __launch_bounds__(256) deltat(int nelem, const int* __restrict__
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     double dte = 1.e20;
     if (e < nelem) {
-        int n[3] = {inp[e], inp[nelem + e], inp[2 * (size_t)nelem + e]};
-        double T_iel = ex::div3(T[n[0]] + T[n[1]] + T[n[2]]);
-        double VUMAX = 0.0, VVMAX = 0.0;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            double VU = fabs(VX[n[i]] - WX[n[i]]);
-            double VV = fabs(VY[n[i]] - WY[n[i]]);
-            if (VU > VUMAX) VUMAX = VU;
-            if (VV > VVMAX) VVMAX = VV;
-        }
-        double HH = sqrt(2.0 * area[e]);
-        double VEL = ex::pow05(VUMAX * VUMAX + VVMAX * VVMAX);
-        double smu = 110.0;
-        double fmu = 0.017 * ex::pow15(T_iel / T_inf) * (T_inf + smu) / (T_iel + smu);
-        double ET = fmu;
-        double Pe = (VEL * HH) / (2.0 * ET);
-        double ALPHA = ex::fmin2(ex::div3(Pe), 1.0);
-        double DELTATU = 1.0 / (4.0 * ET / (HH * HH) + ALPHA * VEL / HH);
-        double DELTATC = 1.0 / (4.0 * ET / (HH * HH));
-        double DTELEM = FSAFE / (1.0 / DELTATC + 1.0 / DELTATU);
+        unsigned bad = 0;
+#if CFDB_BATCH_DIV
+        double DTELEM = deltat_elem<MOVING, true>(e, nelem, inp, area, T, VX, VY, WX, WY, FSAFE, T_inf, bad);
+        if (bad) DTELEM = deltat_plain<MOVING>(e, nelem, inp, area, T, VX, VY, WX, WY, FSAFE, T_inf);
+#else
+        double DTELEM = deltat_elem<MOVING, false>(e, nelem, inp, area, T, VX, VY, WX, WY, FSAFE, T_inf, bad);
+#endif
         if (WRITE_DT) DT[e] = DTELEM;
         if (DTELEM < dte) dte = DTELEM;
     }
@@ -235,8 +284,15 @@ __global__ void fill_const(long n, double* __restrict__ a, double v) {
 
 // ---------------------------------------------------------------------------------------------
 // ESTAB (subrutinas.f90:349-443) : one thread per element
-template <int MINB>
-__global__ void __launch_bounds__(256, MINB) estab(int nelem, const int* __restrict__ inp, const double* __restrict__ U,
+// Every gather is issued before the first x/3: ex::div3 (and every division and square root after it) carries a
+// range-check branch, and the compiler does not move loads across those, so interleaving "load three, divide" as the
+// source does serialises seven round trips to memory.  MOVING = false (fixed mesh: W_X = W_Y = +0 everywhere, the
+// same condition under which FUENTE is skipped) drops the mesh-velocity gathers: x - (+0) = x for every x.
+// The kernel runs estab_fast — the same operations through the branch-free forms of exact.cuh, ~35 quotients and roots
+// as straight-line code, the source's x/0 = Inf, Inf > 10 and 1/Inf = 0 cases as selects — and hands the element to the
+// plain form (estab_plain, not inlined) when an operand left their fast path.  CFDB_BATCH_DIV=0: plain form only.
+template <bool MOVING>
+__device__ __forceinline__ void estab_one(int e, int nelem, const int* __restrict__ inp, const double* __restrict__ U,
                                               const double* __restrict__ T, const double* __restrict__ VXa,
                                               const double* __restrict__ VYa, const double* __restrict__ WXa,
                                               const double* __restrict__ WYa, const double* __restrict__ GAMM,
@@ -244,26 +300,34 @@ __global__ void __launch_bounds__(256, MINB) estab(int nelem, const int* __restr
                                               double FR, const double* __restrict__ dtmin_p, double RHOINF,
                                               double TINF, double* __restrict__ SHOC, double* __restrict__ TS1,
                                               double* __restrict__ TS2, double* __restrict__ TS3) {
-    int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= nelem) return;
-    const double DTMIN = *dtmin_p;
     int N1 = inp[e], N2 = inp[nelem + e], N3 = inp[2 * (size_t)nelem + e];
+    const double r1 = U[4 * (size_t)N1], r2 = U[4 * (size_t)N2], r3 = U[4 * (size_t)N3];
+    const double t1 = T[N1], t2 = T[N2], t3 = T[N3];
+    const double gsum = GAMM[N1] + GAMM[N2] + GAMM[N3];
+    const double vxsum = VXa[N1] + VXa[N2] + VXa[N3];
+    const double vysum = VYa[N1] + VYa[N2] + VYa[N3];
+    double wxsum = 0.0, wysum = 0.0;
+    if (MOVING) {
+        wxsum = WXa[N1] + WXa[N2] + WXa[N3];
+        wysum = WYa[N1] + WYa[N2] + WYa[N3];
+    }
     double nx[3] = {dNx[e], dNx[nelem + e], dNx[2 * (size_t)nelem + e]};
     double ny[3] = {dNy[e], dNy[nelem + e], dNy[2 * (size_t)nelem + e]};
-    double GM = ex::div3(GAMM[N1] + GAMM[N2] + GAMM[N3]);
+    const double DTMIN = *dtmin_p;
+    double GM = ex::div3(gsum);
     double TAU = 0.0, H_RGNE = 0.0, H_RGN = 0.0, H_JGN = 0.0;
-    double r1 = U[4 * (size_t)N1], r2 = U[4 * (size_t)N2], r3 = U[4 * (size_t)N3];
     double RHO_ELEM = ex::div3(r1 + r2 + r3);
-    double VX = ex::div3(VXa[N1] + VXa[N2] + VXa[N3]);
-    double VY = ex::div3(VYa[N1] + VYa[N2] + VYa[N3]);
-    double WX = ex::div3(WXa[N1] + WXa[N2] + WXa[N3]);
-    double WY = ex::div3(WYa[N1] + WYa[N2] + WYa[N3]);
-    VX = VX - WX; VY = VY - WY;
+    double VX = ex::div3(vxsum);
+    double VY = ex::div3(vysum);
+    if (MOVING) {
+        double WX = ex::div3(wxsum);
+        double WY = ex::div3(wysum);
+        VX = VX - WX; VY = VY - WY;
+    }
     double VEL2 = sqrt(VX * VX + VY * VY);
     double DRX = r1 * nx[0] + r2 * nx[1] + r3 * nx[2];
     double DRY = r1 * ny[0] + r2 * ny[1] + r3 * ny[2];
     double DR2 = sqrt(DRX * DRX + DRY * DRY) + 1.e-20;
-    double t1 = T[N1], t2 = T[N2], t3 = T[N3];
     double DTX = t1 * nx[0] + t2 * nx[1] + t3 * nx[2];
     double DTY = t1 * ny[0] + t2 * ny[1] + t3 * ny[2];
     double DT2 = sqrt(DTX * DTX + DTY * DTY) + 1.e-20;
@@ -316,16 +380,160 @@ __global__ void __launch_bounds__(256, MINB) estab(int nelem, const int* __restr
     TS1[e] = RRR; TS2[e] = s2; TS3[e] = s3;
 }
 
+template <bool MOVING>
+__device__ __noinline__ void estab_plain(int e, int nelem, const int* __restrict__ inp, const double* __restrict__ U,
+                                              const double* __restrict__ T, const double* __restrict__ VXa,
+                                              const double* __restrict__ VYa, const double* __restrict__ WXa,
+                                              const double* __restrict__ WYa, const double* __restrict__ GAMM,
+                                              const double* __restrict__ dNx, const double* __restrict__ dNy,
+                                              double FR, const double* __restrict__ dtmin_p, double RHOINF,
+                                              double TINF, double* __restrict__ SHOC, double* __restrict__ TS1,
+                                              double* __restrict__ TS2, double* __restrict__ TS3) {
+    estab_one<MOVING>(e, nelem, inp, U, T, VXa, VYa, WXa, WYa, GAMM, dNx, dNy, FR, dtmin_p, RHOINF, TINF, SHOC, TS1, TS2, TS3);
+}
+__device__ __forceinline__ bool is_zero(double x) {
+    return ((static_cast<unsigned>(__double2hiint(x)) << 1) | static_cast<unsigned>(__double2loint(x))) == 0u;
+}
+__device__ __forceinline__ bool is_pinf(double x) {
+    return static_cast<unsigned>(__double2hiint(x)) == 0x7ff00000u && __double2loint(x) == 0;
+}
+// returns the fast-path flag; stores only when it is 0
+template <bool MOVING>
+__device__ __forceinline__ unsigned estab_fast(int e, int nelem, const int* __restrict__ inp, const double* __restrict__ U,
+                                              const double* __restrict__ T, const double* __restrict__ VXa,
+                                              const double* __restrict__ VYa, const double* __restrict__ WXa,
+                                              const double* __restrict__ WYa, const double* __restrict__ GAMM,
+                                              const double* __restrict__ dNx, const double* __restrict__ dNy,
+                                              double FR, const double* __restrict__ dtmin_p, double RHOINF,
+                                              double TINF, double* __restrict__ SHOC, double* __restrict__ TS1,
+                                              double* __restrict__ TS2, double* __restrict__ TS3) {
+    unsigned bad = 0;
+    int N1 = inp[e], N2 = inp[nelem + e], N3 = inp[2 * (size_t)nelem + e];
+    const double r1 = U[4 * (size_t)N1], r2 = U[4 * (size_t)N2], r3 = U[4 * (size_t)N3];
+    const double t1 = T[N1], t2 = T[N2], t3 = T[N3];
+    const double gsum = GAMM[N1] + GAMM[N2] + GAMM[N3];
+    const double vxsum = VXa[N1] + VXa[N2] + VXa[N3];
+    const double vysum = VYa[N1] + VYa[N2] + VYa[N3];
+    double wxsum = 0.0, wysum = 0.0;
+    if (MOVING) {
+        wxsum = WXa[N1] + WXa[N2] + WXa[N3];
+        wysum = WYa[N1] + WYa[N2] + WYa[N3];
+    }
+    double nx[3] = {dNx[e], dNx[nelem + e], dNx[2 * (size_t)nelem + e]};
+    double ny[3] = {dNy[e], dNy[nelem + e], dNy[2 * (size_t)nelem + e]};
+    const double DTMIN = *dtmin_p;
+    double GM = ex::div3_nb(gsum, bad);
+    double TAU = 0.0, H_RGNE = 0.0, H_RGN = 0.0, H_JGN = 0.0;
+    double RHO_ELEM = ex::div3_nb(r1 + r2 + r3, bad);
+    double VX = ex::div3_nb(vxsum, bad);
+    double VY = ex::div3_nb(vysum, bad);
+    if (MOVING) {
+        double WX = ex::div3_nb(wxsum, bad);
+        double WY = ex::div3_nb(wysum, bad);
+        VX = VX - WX; VY = VY - WY;
+    }
+    double VEL2 = ex::sqrt_nb(VX * VX + VY * VY, bad);
+    double DRX = r1 * nx[0] + r2 * nx[1] + r3 * nx[2];
+    double DRY = r1 * ny[0] + r2 * ny[1] + r3 * ny[2];
+    double DR2 = ex::sqrt_nb(DRX * DRX + DRY * DRY, bad) + 1.e-20;
+    double DTX = t1 * nx[0] + t2 * nx[1] + t3 * nx[2];
+    double DTY = t1 * ny[0] + t2 * ny[1] + t3 * ny[2];
+    double DT2 = ex::sqrt_nb(DTX * DTX + DTY * DTY, bad) + 1.e-20;
+    double DUX = VEL2 * nx[0] + VEL2 * nx[1] + VEL2 * nx[2];
+    double DUY = VEL2 * ny[0] + VEL2 * ny[1] + VEL2 * ny[2];
+    double DU2 = ex::sqrt_nb(DUX * DUX + DUY * DUY, bad) + 1.e-20;
+    const ex::Recip dT(DT2), dR(DR2), dU(DU2);
+    double RTX = dT.div(DTX, bad), RTY = dT.div(DTY, bad);
+    double RJX = dR.div(DRX, bad), RJY = dR.div(DRY, bad);
+    double RUX = dU.div(DUX, bad), RUY = dU.div(DUY, bad);
+    double TEMP = ex::div3_nb(t1 + t2 + t3, bad);
+    double C = ex::sqrt_nb(GM * FR * TEMP, bad);
+    double smu = 110.0;
+    double fmu = ex::Recip(TEMP + smu).div(0.017 * ex::pow15_nb(ex::Recip(TINF).div(TEMP, bad), bad) * (TINF + smu), bad);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        double TERM_1 = fabs(VX * nx[i] + VY * ny[i]);
+        double TERM_2 = fabs(RJX * nx[i] + RJY * ny[i]);
+        double H_RGN1 = fabs(RTX * nx[i] + RTY * ny[i]);
+        double H_RGN2 = fabs(RUX * nx[i] + RUY * ny[i]);
+        TAU = TAU + TERM_1 + TERM_2 * C;
+        H_RGNE = H_RGNE + H_RGN1;
+        H_RGN = H_RGN + H_RGN2;
+        H_JGN = H_JGN + TERM_2;
+    }
+    // c/x for a sum x >= +0: x = 0 gives +Inf (select); the divisor handed to the fast path is then a harmless 1
+    auto over = [&](double c, double x) {
+        bool z = is_zero(x);
+        double q = ex::Recip(z ? 1.0 : x).div(c, bad);
+        return z ? CUDART_INF : q;
+    };
+    TAU = over(1.0, TAU);
+    H_RGNE = over(2.0, H_RGNE);
+    H_RGN = over(2.0, H_RGN);
+    if (H_RGN > 1.e1) H_RGN = 0.0;
+    H_JGN = over(2.0, H_JGN);
+    if (H_JGN > 1.e1) H_JGN = 0.0;
+    double TR1 = ex::Recip(RHO_ELEM).div(DR2 * H_JGN, bad);
+    double ZZZ = ex::Recip(2.0 * C).div(H_JGN, bad);
+    const double shoc_e = (TR1 + TR1 * TR1) * .5 * (C * C) * ZZZ;
+    double tt = TAU * TAU;
+    const bool ttinf = is_pinf(tt);
+    const double itt = ex::Recip(ttinf ? 1.0 : tt).div(1.0, bad);
+    const double twodt = ex::Recip(DTMIN).div(2.0, bad);
+    double RESUMEN = (ttinf ? 0.0 : itt) + twodt * twodt;
+    double RRR = ex::powm05_nb(RESUMEN, bad);
+    bad |= (fmu != 0.0) ? 0u : 1u;  // the plain form's fmu == 0 branch
+    double den = ex::Recip(RHOINF).div(4.0 * fmu, bad);
+    const ex::Recip dden(den);
+    double TAU_SUNG3 = dden.div(H_RGN * H_RGN, bad);
+    double TAU_SUNG3_E = dden.div(H_RGNE * H_RGNE, bad);
+    double q2 = TAU_SUNG3 * TAU_SUNG3, q3 = TAU_SUNG3_E * TAU_SUNG3_E;
+    // 1/q for a square q: 1/(+0) = +Inf, 1/(+Inf) = +0; then (RESUMEN + that)**(-.5), which is 0 at +Inf
+    auto tail = [&](double q) {
+        bool z = is_zero(q), inf = is_pinf(q);
+        double iq = ex::Recip((z || inf) ? 1.0 : q).div(1.0, bad);
+        double arg = RESUMEN + iq;
+        bool ainf = z || is_pinf(arg);
+        double r = ex::powm05_nb(ainf ? 1.0 : (inf ? RESUMEN : arg), bad);
+        return ainf ? 0.0 : r;
+    };
+    double s2 = tail(q2), s3 = tail(q3);
+    if (bad) return bad;
+    SHOC[e] = shoc_e;
+    TS1[e] = RRR; TS2[e] = s2; TS3[e] = s3;
+    return 0;
+}
+template <int MINB, bool MOVING = true>
+__global__ void __launch_bounds__(256, MINB) estab(int nelem, const int* __restrict__ inp, const double* __restrict__ U,
+                                              const double* __restrict__ T, const double* __restrict__ VXa,
+                                              const double* __restrict__ VYa, const double* __restrict__ WXa,
+                                              const double* __restrict__ WYa, const double* __restrict__ GAMM,
+                                              const double* __restrict__ dNx, const double* __restrict__ dNy,
+                                              double FR, const double* __restrict__ dtmin_p, double RHOINF,
+                                              double TINF, double* __restrict__ SHOC, double* __restrict__ TS1,
+                                              double* __restrict__ TS2, double* __restrict__ TS3) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nelem) return;
+#if CFDB_BATCH_DIV
+    if (estab_fast<MOVING>(e, nelem, inp, U, T, VXa, VYa, WXa, WYa, GAMM, dNx, dNy, FR, dtmin_p, RHOINF, TINF, SHOC, TS1, TS2, TS3)) estab_plain<MOVING>(e, nelem, inp, U, T, VXa, VYa, WXa, WYa, GAMM, dNx, dNy, FR, dtmin_p, RHOINF, TINF, SHOC, TS1, TS2, TS3);
+#else
+    estab_one<MOVING>(e, nelem, inp, U, T, VXa, VYa, WXa, WYa, GAMM, dNx, dNy, FR, dtmin_p, RHOINF, TINF, SHOC, TS1, TS2, TS3);
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------
 // calcRHS (calcRHS.f90:36-141): the arithmetic of one element, shared by the direct and the cp.async-pipelined
 // kernels.  Inputs are the gathered nodal values and the element's stream data; rt(3 nodes, 4 eqns) is the
 // contribution before the scatter.  Evaluation order is the source's (see exact.cuh).
-template <bool VISC, bool THETA>
+// NB = true: the divisions are the branch-free forms of exact.cuh (same values); *bad is raised when an operand falls
+// outside their fast path, and the caller then recomputes the element with NB = false.
+template <bool VISC, bool THETA, bool NB = false>
 __device__ __forceinline__ void calcrhs_body(const Gas& g, const double (&Un)[3][4], const double (&Th)[3][4],
                                              const double (&Tn)[3], const double (&Nx)[3], const double (&Ny)[3],
                                              const double (&tau)[3], double shoc_e, double (&Ux)[4], double (&Uy)[4],
-                                             double (&rt)[3][4]) {
+                                             double (&rt)[3][4], unsigned* bad_out = nullptr) {
     const double gamma0 = g.gamma0;
+    unsigned bad = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         Ux[i] = Un[0][i] * Nx[0] + Un[1][i] * Nx[1] + Un[2][i] * Nx[2];
@@ -334,10 +542,17 @@ __device__ __forceinline__ void calcrhs_body(const Gas& g, const double (&Un)[3]
     const double nu = shoc_e * g.cte;
     double mu = 0.0, lambda = 0.0;
     if (VISC) {
-        double T_avg = ex::div3(Tn[0] + Tn[1] + Tn[2]);
-        double p15 = ex::pow15(T_avg / g.T_inf);
-        mu = g.mu_ref * p15 * (g.T_inf + 110) / (T_avg + 110);
-        lambda = g.lambda_ref * p15 * (g.T_inf + 194) / (T_avg + 194);
+        if (NB) {
+            double T_avg = ex::div3_nb(Tn[0] + Tn[1] + Tn[2], bad);
+            double p15 = ex::pow15_nb(ex::Recip(g.T_inf).div(T_avg, bad), bad);
+            mu = ex::Recip(T_avg + 110).div(g.mu_ref * p15 * (g.T_inf + 110), bad);
+            lambda = ex::Recip(T_avg + 194).div(g.lambda_ref * p15 * (g.T_inf + 194), bad);
+        } else {
+            double T_avg = ex::div3(Tn[0] + Tn[1] + Tn[2]);
+            double p15 = ex::pow15(T_avg / g.T_inf);
+            mu = g.mu_ref * p15 * (g.T_inf + 110) / (T_avg + 110);
+            lambda = g.lambda_ref * p15 * (g.T_inf + 194) / (T_avg + 194);
+        }
     }
 #pragma unroll
     for (int n = 0; n < 3; ++n)
@@ -355,16 +570,26 @@ __device__ __forceinline__ void calcrhs_body(const Gas& g, const double (&Un)[3]
     // (ex::DivBy — one reciprocal refinement shared by the three quotients — is exact but measured slower here:
     // 1.275 ms against 1.186 ms per launch; its fallback branches cost more than the 13 fp64 instructions saved)
     double rho_k[3], v1_k[3], v2_k[3], en_k[3];
+    double ry_k[3] = {0.0, 0.0, 0.0};          // NB: refined 1/rho of each Gauss point, reused by the viscous quotients
+    bool rp_k[3] = {false, false, false};
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const double Nk[3] = {k == 0 ? 0.0 : .5, k == 1 ? 0.0 : .5, k == 2 ? 0.0 : .5};
         double U_k[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) U_k[i] = Nk[0] * Un[0][i] + Nk[1] * Un[1][i] + Nk[2] * Un[2][i];
+        for (int i = 0; i < 4; ++i) U_k[i] = ex::lin3(Nk[0], Un[0][i], Nk[1], Un[1][i], Nk[2], Un[2][i]);
         rho_k[k] = U_k[0];
-        v1_k[k] = ex::divz(U_k[1], U_k[0]);
-        v2_k[k] = ex::divz(U_k[2], U_k[0]);
-        en_k[k] = U_k[3] / U_k[0];
+        if (NB) {
+            ex::Recip d(U_k[0]);
+            v1_k[k] = d.div(U_k[1], bad);
+            v2_k[k] = d.div(U_k[2], bad);
+            en_k[k] = d.div(U_k[3], bad);
+            ry_k[k] = d.y; rp_k[k] = d.bpos;
+        } else {
+            v1_k[k] = ex::divz(U_k[1], U_k[0]);
+            v2_k[k] = ex::divz(U_k[2], U_k[0]);
+            en_k[k] = U_k[3] / U_k[0];
+        }
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -372,87 +597,120 @@ __device__ __forceinline__ void calcrhs_body(const Gas& g, const double (&Un)[3]
         const double Nk[3] = {k == 0 ? 0.0 : .5, k == 1 ? 0.0 : .5, k == 2 ? 0.0 : .5};
         double th_k[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) th_k[i] = THETA ? (Nk[0] * Th[0][i] + Nk[1] * Th[1][i] + Nk[2] * Th[2][i]) : 0.0;
+        for (int i = 0; i < 4; ++i) th_k[i] = THETA ? ex::lin3(Nk[0], Th[0][i], Nk[1], Th[1][i], Nk[2], Th[2][i]) : 0.0;
         const double rho = rho_k[k], v1 = v1_k[k], v2 = v2_k[k], en = en_k[k];
         double V_sq = v1 * v1 + v2 * v2;
+        // Sub-expressions the source scales by 2 or 1/2 (exact.cuh, "exact scalings"): with Vg = V_sq*(gamma0-1),
+        // eg = en*gamma0, c1 = v1*v1*(gamma0-1), c2 = v2*v2*(gamma0-1) as the source forms them,
+        //   V_sq*(gamma0-1) - 2*(v1*v1)                               == pfma(-2, v1*v1, Vg)
+        //   V_sq*(gamma0-1) - 2*en*gamma0 + 2*(v1*v1)*(gamma0-1)      == pfma(2, c1, pfma(-2, eg, Vg))
+        //   (1.0/2.0)*V_sq*(gamma0-1) - v1*v1                         == pfma(.5, Vg, -(v1*v1))
+        //   -1.0/2.0*V_sq*(gamma0-1) + en*gamma0 - v1*v1*(gamma0-1)   == pfma(-.5, Vg, eg) - c1
+        // bit for bit, in one fp64 instruction per line instead of three.
+        const double gm1 = gamma0 - 1;
+        const double Vg = V_sq * gm1, eg = en * gamma0;
+        const double v11 = v1 * v1, v22 = v2 * v2;
+        const double c1 = v11 * gm1, c2 = v22 * gm1;
+        const double Vg_2eg = ex::pfma(-2.0, eg, Vg);
+        const double hVg_eg = ex::pfma(-.5, Vg, eg);
         double A[4];
         A[0] = Ux[1] + Uy[2];
-        A[1] = (1.0 / 2.0) * Ux[0] * (V_sq * (gamma0 - 1) - 2 * (v1 * v1)) - Ux[1] * v1 * (gamma0 - 3) -
-               Ux[2] * v2 * (gamma0 - 1) + Ux[3] * (gamma0 - 1) - Uy[0] * v1 * v2 + Uy[1] * v2 + Uy[2] * v1;
+        A[1] = (1.0 / 2.0) * Ux[0] * ex::pfma(-2.0, v11, Vg) - Ux[1] * v1 * (gamma0 - 3) -
+               Ux[2] * v2 * gm1 + Ux[3] * gm1 - Uy[0] * v1 * v2 + Uy[1] * v2 + Uy[2] * v1;
         A[2] = -Ux[0] * v1 * v2 + Ux[1] * v2 + Ux[2] * v1 +
-               (1.0 / 2.0) * Uy[0] * (V_sq * (gamma0 - 1) - 2 * (v2 * v2)) - Uy[1] * v1 * (gamma0 - 1) -
-               Uy[2] * v2 * (gamma0 - 3) + Uy[3] * (gamma0 - 1);
-        A[3] = Ux[0] * v1 * (V_sq * (gamma0 - 1) - en * gamma0) -
-               1.0 / 2.0 * Ux[1] * (V_sq * (gamma0 - 1) - 2 * en * gamma0 + 2 * (v1 * v1) * (gamma0 - 1)) -
-               Ux[2] * v1 * v2 * (gamma0 - 1) + Ux[3] * gamma0 * v1 +
-               Uy[0] * v2 * (V_sq * (gamma0 - 1) - en * gamma0) - Uy[1] * v1 * v2 * (gamma0 - 1) -
-               1.0 / 2.0 * Uy[2] * (V_sq * (gamma0 - 1) - 2 * en * gamma0 + 2 * (v2 * v2) * (gamma0 - 1)) +
+               (1.0 / 2.0) * Uy[0] * ex::pfma(-2.0, v22, Vg) - Uy[1] * v1 * gm1 -
+               Uy[2] * v2 * (gamma0 - 3) + Uy[3] * gm1;
+        A[3] = Ux[0] * v1 * (Vg - eg) -
+               1.0 / 2.0 * Ux[1] * ex::pfma(2.0, c1, Vg_2eg) -
+               Ux[2] * v1 * v2 * gm1 + Ux[3] * gamma0 * v1 +
+               Uy[0] * v2 * (Vg - eg) - Uy[1] * v1 * v2 * gm1 -
+               1.0 / 2.0 * Uy[2] * ex::pfma(2.0, c2, Vg_2eg) +
                Uy[3] * gamma0 * v2;
         double At[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) At[i] = th_k[i] + A[i];
         double A1[4], A2[4];
         A1[0] = At[1];
-        A1[1] = v1 * (-gamma0 + 3) * At[1] - v2 * (gamma0 - 1) * At[2] + (gamma0 - 1) * At[3] +
-                ((1.0 / 2.0) * V_sq * (gamma0 - 1) - v1 * v1) * At[0];
+        A1[1] = v1 * (-gamma0 + 3) * At[1] - v2 * gm1 * At[2] + gm1 * At[3] +
+                ex::pfma(.5, Vg, -v11) * At[0];
         A1[2] = -v1 * v2 * At[0] + v1 * At[2] + v2 * At[1];
-        A1[3] = gamma0 * v1 * At[3] - v1 * v2 * (gamma0 - 1) * At[2] +
-                v1 * (V_sq * (gamma0 - 1) - en * gamma0) * At[0] +
-                (-1.0 / 2.0 * V_sq * (gamma0 - 1) + en * gamma0 - v1 * v1 * (gamma0 - 1)) * At[1];
+        A1[3] = gamma0 * v1 * At[3] - v1 * v2 * gm1 * At[2] +
+                v1 * (Vg - eg) * At[0] +
+                (hVg_eg - c1) * At[1];
         A2[0] = At[2];
         A2[1] = -v1 * v2 * At[0] + v1 * At[2] + v2 * At[1];
-        A2[2] = -v1 * (gamma0 - 1) * At[1] + v2 * (-gamma0 + 3) * At[2] + (gamma0 - 1) * At[3] +
-                ((1.0 / 2.0) * V_sq * (gamma0 - 1) - v2 * v2) * At[0];
-        A2[3] = gamma0 * v2 * At[3] - v1 * v2 * (gamma0 - 1) * At[1] +
-                v2 * (V_sq * (gamma0 - 1) - en * gamma0) * At[0] +
-                (-1.0 / 2.0 * V_sq * (gamma0 - 1) + en * gamma0 - v2 * v2 * (gamma0 - 1)) * At[2];
+        A2[2] = -v1 * gm1 * At[1] + v2 * (-gamma0 + 3) * At[2] + gm1 * At[3] +
+                ex::pfma(.5, Vg, -v22) * At[0];
+        A2[3] = gamma0 * v2 * At[3] - v1 * v2 * gm1 * At[1] +
+                v2 * (Vg - eg) * At[0] +
+                (hVg_eg - c2) * At[2];
 #pragma unroll
         for (int n = 0; n < 3; ++n)
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                rt[n][i] = rt[n][i] + Nk[n] * A[i] + tau[n] * (Nx[n] * A1[i] + Ny[n] * A2[i]) + sh[n][i];
+                rt[n][i] = ex::pfma(Nk[n], A[i], rt[n][i]) + tau[n] * (Nx[n] * A1[i] + Ny[n] * A2[i]) + sh[n][i];
         if (VISC) {
             const double Cv = g.Cv;
             double K1[4], K2[4];
-            K1[1] = (2.0 / 3.0) * mu * (-2 * Ux[0] * v1 + 2 * Ux[1] + Uy[0] * v2 - Uy[2]) / rho;
-            K1[2] = mu * (-Ux[0] * v2 + Ux[2] - Uy[0] * v1 + Uy[1]) / rho;
-            K1[3] = (1.0 / 3.0) *
+            // numerators as the source writes them; the quotients by rho and by Cv*rho follow
+            const double k11 = (2.0 / 3.0) * mu * (-2 * Ux[0] * v1 + 2 * Ux[1] + Uy[0] * v2 - Uy[2]);
+            const double k12 = mu * (-Ux[0] * v2 + Ux[2] - Uy[0] * v1 + Uy[1]);
+            const double k13 = (1.0 / 3.0) *
                     (Cv * mu * (-Uy[0] * v1 * v2 + 3 * Uy[1] * v2 - 2 * Uy[2] * v1) -
                      Ux[0] * (Cv * mu * (3 * V_sq + v1 * v1) - 3 * lambda * (V_sq - en)) +
                      Ux[1] * v1 * (4 * Cv * mu - 3 * lambda) + 3 * Ux[2] * v2 * (Cv * mu - lambda) +
-                     3 * Ux[3] * lambda) /
-                    (Cv * rho);
-            K2[1] = mu * (-Ux[0] * v2 + Ux[2] - Uy[0] * v1 + Uy[1]) / rho;
-            K2[2] = (2.0 / 3.0) * mu * (Ux[0] * v1 - Ux[1] - 2 * Uy[0] * v2 + 2 * Uy[2]) / rho;
-            K2[3] = (1.0 / 3.0) *
+                     3 * Ux[3] * lambda);
+            const double k22 = (2.0 / 3.0) * mu * (Ux[0] * v1 - Ux[1] - 2 * Uy[0] * v2 + 2 * Uy[2]);
+            const double k23 = (1.0 / 3.0) *
                     (Cv * mu * (-Ux[0] * v1 * v2 - 2 * Ux[1] * v2 + 3 * Ux[2] * v1) -
                      Uy[0] * (Cv * mu * (3 * V_sq + v2 * v2) - 3 * lambda * (V_sq - en)) +
                      3 * Uy[1] * v1 * (Cv * mu - lambda) + Uy[2] * v2 * (4 * Cv * mu - 3 * lambda) +
-                     3 * Uy[3] * lambda) /
-                    (Cv * rho);
+                     3 * Uy[3] * lambda);
+            if (NB) {
+                const ex::Recip dr(rho, ry_k[k], rp_k[k]), dc(Cv * rho);
+                K1[1] = dr.div(k11, bad);
+                K1[2] = dr.div(k12, bad);
+                K1[3] = dc.div(k13, bad);
+                K2[1] = K1[2];  // the source writes the same expression twice
+                K2[2] = dr.div(k22, bad);
+                K2[3] = dc.div(k23, bad);
+            } else {
+                K1[1] = k11 / rho;
+                K1[2] = k12 / rho;
+                K1[3] = k13 / (Cv * rho);
+                K2[1] = k12 / rho;
+                K2[2] = k22 / rho;
+                K2[3] = k23 / (Cv * rho);
+            }
 #pragma unroll
             for (int n = 0; n < 3; ++n)
 #pragma unroll
                 for (int i = 1; i < 4; ++i) rt[n][i] = rt[n][i] + (Nx[n] * K1[i] + Ny[n] * K2[i]);
         }
     }
+    if (NB) *bad_out = bad;
 }
 
 // calcRHS [+ FUENTE, subrutinas.f90:1060-1078] : one thread per element, direct loads.
 // Shape-function gradients and the 12+12 contributions stay in registers; the results go to the
 // staging buffers EC/FC, not to RHS: the node kernel sums them in the reference's order.
-template <bool VISC, bool THETA, bool ALE, int MINB, int BS = 128>
-__global__ void __launch_bounds__(BS, MINB) calcrhs_elem(int e0, int e1, int nelem, const int* __restrict__ inp, const double* __restrict__ U,
-                                                     const double* __restrict__ TH, const double* __restrict__ T,
-                                                     const double* __restrict__ WXa, const double* __restrict__ WYa,
-                                                     const double* __restrict__ dNx, const double* __restrict__ dNy,
-                                                     const double* __restrict__ area, const double* __restrict__ shoc,
-                                                     const double* __restrict__ dtl_arr, const double* __restrict__ dtl_sc,
-                                                     const double* __restrict__ ts1, const double* __restrict__ ts2,
-                                                     const double* __restrict__ ts3, Gas g, double* __restrict__ EC,
-                                                     double* __restrict__ FC) {
-    int e = e0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= e1) return;
+//
+// The kernel runs the element through the branch-free division forms (NB = true: the nine Gauss-point quotients, the
+// viscous quotients and the twelve x/3 of the tail are straight-line code the scheduler interleaves instead of ~21-45
+// serial chains behind range-check branches) and, if any operand left their fast path, recomputes it with the plain
+// operations in a separate, non-inlined copy (calcrhs_one_plain).  CFDB_BATCH_DIV=0 compiles the plain form only.
+#define CFDB_CALC_PARAMS                                                                                             \
+    int nelem, const int* __restrict__ inp, const double* __restrict__ U, const double* __restrict__ TH,            \
+        const double* __restrict__ T, const double* __restrict__ WXa, const double* __restrict__ WYa,               \
+        const double* __restrict__ dNx, const double* __restrict__ dNy, const double* __restrict__ area,            \
+        const double* __restrict__ shoc, const double* __restrict__ dtl_arr, const double* __restrict__ dtl_sc,     \
+        const double* __restrict__ ts1, const double* __restrict__ ts2, const double* __restrict__ ts3, const Gas& g, \
+        double* __restrict__ EC, double* __restrict__ FC
+#define CFDB_CALC_ARGS nelem, inp, U, TH, T, WXa, WYa, dNx, dNy, area, shoc, dtl_arr, dtl_sc, ts1, ts2, ts3, g, EC, FC
+
+// one element, loads to stores; returns the fast-path flag (always 0 for NB = false)
+template <bool VISC, bool THETA, bool ALE, bool NB>
+__device__ __forceinline__ unsigned calcrhs_one(int e, CFDB_CALC_PARAMS) {
     int ip[3] = {inp[e], inp[nelem + e], inp[2 * (size_t)nelem + e]};
     double Nx[3] = {dNx[e], dNx[nelem + e], dNx[2 * (size_t)nelem + e]};
     double Ny[3] = {dNy[e], dNy[nelem + e], dNy[2 * (size_t)nelem + e]};
@@ -466,46 +724,76 @@ __global__ void __launch_bounds__(BS, MINB) calcrhs_elem(int e0, int e1, int nel
         ld4(TH + 4 * (size_t)ip[1], Th[1]);
         ld4(TH + 4 * (size_t)ip[2], Th[2]);
     }
+    double wxn[3] = {0.0, 0.0, 0.0}, wyn[3] = {0.0, 0.0, 0.0};
+    if (ALE) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { wxn[r] = WXa[ip[r]]; wyn[r] = WYa[ip[r]]; }
+    }
     const double tau[3] = {ts1[e], ts2[e], ts3[e]};
     const double dtl = dtl_arr ? dtl_arr[e] : *dtl_sc;
     const double ar = area[e];
     double Ux[4], Uy[4], rt[3][4];
-    calcrhs_body<VISC, THETA>(g, Un, Th, Tn, Nx, Ny, tau, shoc[e], Ux, Uy, rt);
+    unsigned bad = 0;
+    calcrhs_body<VISC, THETA, NB>(g, Un, Th, Tn, Nx, Ny, tau, shoc[e], Ux, Uy, rt, &bad);
+    // the staged values are stored as they become ready, whatever the flag says: if it is raised the caller runs the plain
+    // form afterwards, whose stores (same thread, same addresses, program order) replace these
     double* out = EC + 12 * (size_t)e;
 #pragma unroll
     for (int n = 0; n < 3; ++n) {
         double v[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = ex::div3(rt[n][i] * ar * dtl);
+        for (int i = 0; i < 4; ++i) v[i] = NB ? ex::div3_nb(rt[n][i] * ar * dtl, bad) : ex::div3(rt[n][i] * ar * dtl);
         st4(out + 4 * n, v);
     }
     if (ALE) {
         // FUENTE: sp(:,1)=(.5,.5,0) sp(:,2)=(0,.5,.5) sp(:,3)=(.5,0,.5); sp[c][r] = sp(r+1,c+1)
         const double sp[3][3] = {{.5, .5, 0.0}, {0.0, .5, .5}, {.5, 0.0, .5}};
-        double AR = ex::div3(ar * dtl);
+        double AR = NB ? ex::div3_nb(ar * dtl, bad) : ex::div3(ar * dtl);
         double wx[3], wy[3];
-        double wxn[3] = {WXa[ip[0]], WXa[ip[1]], WXa[ip[2]]};
-        double wyn[3] = {WYa[ip[0]], WYa[ip[1]], WYa[ip[2]]};
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             double sx = 0.0, sy = 0.0;
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                sx = sx + sp[c][r] * wxn[r];
-                sy = sy + sp[c][r] * wyn[r];
+                sx = ex::pfma(sp[c][r], wxn[r], sx);
+                sy = ex::pfma(sp[c][r], wyn[r], sy);
             }
             wx[c] = sx; wy[c] = sy;
         }
         double* fo = FC + 12 * (size_t)e;
 #pragma unroll
         for (int n = 0; n < 3; ++n) {
-            double v[4];
+            double f[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                v[i] = -AR * (sp[0][n] * (Ux[i] * wx[0] + Uy[i] * wy[0]) + sp[1][n] * (Ux[i] * wx[1] + Uy[i] * wy[1]) +
-                              sp[2][n] * (Ux[i] * wx[2] + Uy[i] * wy[2]));
-            st4(fo + 4 * n, v);
+                f[i] = -AR * ex::lin3(sp[0][n], Ux[i] * wx[0] + Uy[i] * wy[0], sp[1][n], Ux[i] * wx[1] + Uy[i] * wy[1],
+                                      sp[2][n], Ux[i] * wx[2] + Uy[i] * wy[2]);
+            st4(fo + 4 * n, f);
         }
+    }
+    return bad;
+}
+template <bool VISC, bool THETA, bool ALE>
+__device__ __noinline__ void calcrhs_one_plain(int e, CFDB_CALC_PARAMS) {
+    calcrhs_one<VISC, THETA, ALE, false>(e, CFDB_CALC_ARGS);
+}
+
+template <bool VISC, bool THETA, bool ALE, int MINB, int BS = 128, bool NB = false>
+__global__ void __launch_bounds__(BS, MINB) calcrhs_elem(int e0, int e1, int nelem, const int* __restrict__ inp, const double* __restrict__ U,
+                                                     const double* __restrict__ TH, const double* __restrict__ T,
+                                                     const double* __restrict__ WXa, const double* __restrict__ WYa,
+                                                     const double* __restrict__ dNx, const double* __restrict__ dNy,
+                                                     const double* __restrict__ area, const double* __restrict__ shoc,
+                                                     const double* __restrict__ dtl_arr, const double* __restrict__ dtl_sc,
+                                                     const double* __restrict__ ts1, const double* __restrict__ ts2,
+                                                     const double* __restrict__ ts3, Gas g, double* __restrict__ EC,
+                                                     double* __restrict__ FC) {
+    int e = e0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= e1) return;
+    if (NB) {
+        if (calcrhs_one<VISC, THETA, ALE, true>(e, CFDB_CALC_ARGS)) calcrhs_one_plain<VISC, THETA, ALE>(e, CFDB_CALC_ARGS);
+    } else {
+        calcrhs_one<VISC, THETA, ALE, false>(e, CFDB_CALC_ARGS);
     }
 }
 
@@ -767,6 +1055,7 @@ __device__ __forceinline__ void node_finish(int n, const double (&acc)[4], const
 #ifndef CFDB_NODE_BS
 #define CFDB_NODE_BS 128
 #endif
+
 template <bool ALE, bool UPDATE>
 __global__ void __launch_bounds__(CFDB_NODE_BS, CFDB_NODE_MINB) node_update(int n0, int n1, const int* __restrict__ nlist, const int* __restrict__ esup2, const int* __restrict__ eslot,
                                                     const double* __restrict__ EC, const double* __restrict__ FC,
@@ -1332,9 +1621,50 @@ __global__ void selftest(int which, long n, unsigned long long seed, unsigned lo
         } else if (which == 1) {
             double q = ex::div3(a), t = a / 3.0;
             if (__double_as_longlong(q) != __double_as_longlong(t) && !(q != q && t != t)) ++bad;
-        } else {
+        } else if (which == 2) {
+            // one numerator in eight is a signed zero: the case the shortcut exists for
+            if ((next() & 7ull) == 0) a = __longlong_as_double((long long)(__double_as_longlong(a) & 0x8000000000000000ull));
             double q = ex::divz(a, b), t = a / b;
             if (__double_as_longlong(q) != __double_as_longlong(t) && !(q != q && t != t)) ++bad;
+        } else if (which >= 4 && which <= 6) {
+            // branch-free forms: where the flag is clear the value is the plain operation's; in the central exponent
+            // range the flag must be clear (the test is not vacuous)
+            if ((next() & 7ull) == 0) a = __longlong_as_double((long long)(__double_as_longlong(a) & 0x8000000000000000ull));
+            unsigned ea = (static_cast<unsigned>(__double2hiint(a)) >> 20) & 0x7ffu, eb = (static_cast<unsigned>(__double2hiint(b)) >> 20) & 0x7ffu;
+            bool central = ea - 723u < 600u && eb - 723u < 600u;
+            unsigned f = 0;
+            auto same = [](double q, double t) { return __double_as_longlong(q) == __double_as_longlong(t) || (q != q && t != t); };
+            if (which == 4) {
+                double q = ex::Recip(b).div(a, f), t = a / b;
+                if (f ? (central && b > 0.0) : !same(q, t)) ++bad;
+            } else if (which == 5) {
+                double x = fabs(b);
+                double q = ex::sqrt_nb(x, f), t = sqrt(x);
+                if (f ? central : !same(q, t)) ++bad;
+                f = 0; q = ex::pow15_nb(x, f); t = ex::pow15(x);
+                if (f ? (eb - 900u < 250u) : !same(q, t)) ++bad;
+                f = 0; q = ex::powm05_nb(x, f); t = ex::powm05(x);
+                if (f ? (eb - 900u < 250u) : !same(q, t)) ++bad;
+            } else {
+                double q = ex::div3_nb(a, f), t = a / 3.0;
+                if (f ? central : !same(q, t)) ++bad;
+            }
+        } else {
+            // exact scalings (exact.cuh): fma(c,x,t) == c*x + t and (c*a)*b == c*(a*b) for c in {0, +-1/2, +-2},
+            // outside the subnormal/overflow ends of the exponent range
+            const double cs[5] = {0.0, .5, -.5, 2.0, -2.0};
+            double c = cs[next() % 5];
+            unsigned ea = (static_cast<unsigned>(__double2hiint(a)) >> 20) & 0x7ffu;
+            if (ea >= 2 && ea <= 2045) {
+                double q = __fma_rn(c, a, b), t = __dadd_rn(__dmul_rn(c, a), b);
+                if (__double_as_longlong(q) != __double_as_longlong(t) && !(q != q && t != t)) ++bad;
+            }
+            double p = __dmul_rn(a, b);
+            unsigned ep = (static_cast<unsigned>(__double2hiint(p)) >> 20) & 0x7ffu;
+            if (ea >= 2 && ea <= 2045 && ep >= 2 && ep <= 2045) {
+                double q = __dmul_rn(__dmul_rn(c, a), b), t = __dmul_rn(c, p);
+                if (__double_as_longlong(q) != __double_as_longlong(t) && !(q != q && t != t)) ++bad;
+            }
         }
     }
     if (bad) atomicAdd(mismatches, bad);

@@ -179,7 +179,9 @@ int cfdb_smoothing(double* X, double* Y, const int32_t* inpoel, const unsigned c
                    int32_t nelem, int32_t* sweeps);
 
 /* ---- device self-test of the exact-arithmetic helpers (cfd_b200/csrc/exact.cuh) against the plain IEEE operations:
- * which = 0 shared-reciprocal division, 1 division by three, 2 zero-numerator division; n random operand pairs. */
+ * which = 0 shared-reciprocal division, 1 division by three, 2 zero-numerator division, 3 exact scalings by 0, 1/2, 2
+ * folded into one fma, 4/5/6 the branch-free division, square root (and the two powers built on it) and x/3 with their
+ * fast-path flag; n random operand pairs. */
 int cfdb_selftest(cfdb_ctx* ctx, int32_t which, int64_t n, uint64_t seed, int64_t* mismatches);
 
 /* ---- host-side integer artefacts (bit-exact vs the oracle) --------------------------------- */

@@ -292,9 +292,12 @@ def test_config1_channel_1000_steps():
     assert np.max(np.abs(U - Uo) / np.abs(Uo).max(0)) <= 1e-8   # the stated tolerance, met with margin (exactly 0)
 
 
-@pytest.mark.parametrize("which", [0, 1, 2])
+@pytest.mark.parametrize("which", [0, 1, 2, 3, 4, 5, 6])
 def test_exact_arithmetic_helpers_on_device(cases, which):
-    """exact.cuh: shared-reciprocal division, x/3 and zero-numerator division equal the IEEE '/' on 2e9 random operands."""
+    """exact.cuh: shared-reciprocal division, x/3 and zero-numerator division equal the IEEE '/', and c*x + t == fma(c, x, t),
+    (c*a)*b == c*(a*b) for c in {0, +-1/2, +-2}; the branch-free division / sqrt / x**1.5 / x**-.5 / x/3 equal the plain
+    operations wherever their fast-path flag is clear, and the flag is clear in the central exponent range; 2e9 random
+    operands each."""
     import ctypes as C
 
     from cfd_b200 import capi

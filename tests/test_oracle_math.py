@@ -66,3 +66,30 @@ def test_canonical_reduction_order():
         assert abs(got - math.fsum(v)) <= 1e-9 * (np.abs(v).sum() + 1e-300)
     x, y = rng.standard_normal(9000), rng.standard_normal(9000)
     assert L.orc_vecdot(9000, x, y) == _canon_py(x * y)
+
+
+def test_power_of_two_scalings_fold_into_one_fma_exactly():
+    """exact.cuh "exact scalings": for c in {0, +-1/2, +-2} the two IEEE operations of the source, c*x + t, give the
+    correctly rounded value of the exact c*x + t (what one fused multiply-add returns), and (c*a)*b == c*(a*b).
+    Exact rational arithmetic is the referee; float(Fraction) rounds to nearest-even."""
+    from fractions import Fraction
+
+    rng = np.random.default_rng(20261017)
+    n = 20000
+    mant = rng.random((3, n)) + 1.0
+    # exponents near each other so that the additions round, signs mixed so that they cancel
+    expo = rng.integers(-6, 7, size=(3, n))
+    sign = rng.choice([-1.0, 1.0], size=(3, n))
+    xs, ts, bs = (sign * np.ldexp(mant, expo)).tolist()
+    for c in (0.0, 0.5, -0.5, 2.0, -2.0):
+        fc = Fraction(c)
+        for x, t, b in zip(xs, ts, bs):
+            two_ops = c * x + t
+            fused = float(fc * Fraction(x) + Fraction(t))
+            assert two_ops == fused and math.copysign(1.0, two_ops) == math.copysign(1.0, fused)
+            assert (c * x) * b == c * (x * b)
+    # signed zeros: 0*x + t keeps IEEE's zero-sum rules on both sides (-0 only from (-0) + (-0))
+    for x, t in ((3.0, -0.0), (-3.0, -0.0), (3.0, 0.0), (-3.0, 0.0)):
+        r = 0.0 * x + t
+        want_negative = (math.copysign(1.0, 0.0 * x) < 0) and (math.copysign(1.0, t) < 0)
+        assert r == 0.0 and (math.copysign(1.0, r) < 0) == want_negative
