@@ -591,14 +591,23 @@ __device__ __forceinline__ void calcrhs_body(const Gas& g, const double (&Un)[3]
             en_k[k] = U_k[3] / U_k[0];
         }
     }
+    // CFDB_ROLL_K=1 (experiment): the Gauss-point loop left rolled — one copy of its ~350 instructions instead of three
+#ifndef CFDB_ROLL_K
+#define CFDB_ROLL_K 0
+#endif
+#define CFDB_SEL3(a) (k == 0 ? a[0] : (k == 1 ? a[1] : a[2]))
+#if CFDB_ROLL_K
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
     for (int k = 0; k < 3; ++k) {
         // N(:,k): zero at local node k, one half elsewhere (calcRHS.f90:18-23)
         const double Nk[3] = {k == 0 ? 0.0 : .5, k == 1 ? 0.0 : .5, k == 2 ? 0.0 : .5};
         double th_k[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) th_k[i] = THETA ? ex::lin3(Nk[0], Th[0][i], Nk[1], Th[1][i], Nk[2], Th[2][i]) : 0.0;
-        const double rho = rho_k[k], v1 = v1_k[k], v2 = v2_k[k], en = en_k[k];
+        const double rho = CFDB_SEL3(rho_k), v1 = CFDB_SEL3(v1_k), v2 = CFDB_SEL3(v2_k), en = CFDB_SEL3(en_k);
         double V_sq = v1 * v1 + v2 * v2;
         // Sub-expressions the source scales by 2 or 1/2 (exact.cuh, "exact scalings"): with Vg = V_sq*(gamma0-1),
         // eg = en*gamma0, c1 = v1*v1*(gamma0-1), c2 = v2*v2*(gamma0-1) as the source forms them,
@@ -667,7 +676,7 @@ __device__ __forceinline__ void calcrhs_body(const Gas& g, const double (&Un)[3]
                      3 * Uy[1] * v1 * (Cv * mu - lambda) + Uy[2] * v2 * (4 * Cv * mu - 3 * lambda) +
                      3 * Uy[3] * lambda);
             if (NB) {
-                const ex::Recip dr(rho, ry_k[k], rp_k[k]), dc(Cv * rho);
+                const ex::Recip dr(rho, CFDB_SEL3(ry_k), CFDB_SEL3(rp_k)), dc(Cv * rho);
                 K1[1] = dr.div(k11, bad);
                 K1[2] = dr.div(k12, bad);
                 K1[3] = dc.div(k13, bad);

@@ -32,4 +32,8 @@ for name, (mk, bump) in CASES.items():
         if not np.array_equal(a.view(np.uint64), b.view(np.uint64)):
             raise SystemExit(f"{name}: {f} differs ({int((a.view(np.uint64) != b.view(np.uint64)).sum())} entries)")
     assert g.scalar("bicg_y") == o.scalar("bicg_y") and g.scalar("DTMIN") == o.scalar("DTMIN")
+import pathological  # noqa: E402  (tests/ is sys.path[0] for this script)
+
+lc = deck.load(meshgen.channel(nx=41, ny=13, FMU=1.8e-5, FK=0.0257))
+pathological.check(lc, NSComp2D(lc), Oracle(lc))
 print("OPT_PATH_OK")

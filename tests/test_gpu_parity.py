@@ -390,9 +390,20 @@ def test_restart_file_resumes_state(cases, tmp_path):
     assert np.isfinite(h.get("U")).all()
 
 
+def test_operands_outside_the_fast_paths_take_the_plain_form(cases):
+    """Subnormal, zero, infinite, negative and overflowing operands in 16 elements: calcRHS (Euler and viscous), deltat and
+    ESTAB through the call-site entries equal the oracle (tests/pathological.py)."""
+    import pathological
+
+    lc = cases["channel_visc"]
+    g, o = _pair(lc)
+    assert pathological.check(lc, g, o) == 16
+
+
 @pytest.mark.parametrize("env", ["CFDB_STAGE_OVERLAP=1", "CFDB_CALCRHS_PIPE=3", "CFDB_CALCRHS_PIPE=4", "CFDB_TILE=1", "CFDB_CHUNK=100",
                                  "CFDB_CHUNK=100,CFDB_CHUNK_SEQ=1", "CFDB_BICG_UNFUSED=1", "CFDB_CALCRHS_MINB=3",
-                                 "CFDB_CALCRHS_MINB=1", "CFDB_ESTAB_MINB=3", "CFDB_HOST_TOPO=1",
+                                 "CFDB_CALCRHS_MINB=5", "CFDB_ESTAB_MINB=3", "CFDB_ESTAB_MINB=5", "CFDB_HOST_TOPO=1",
+                                 "CFDB_CALCRHS_NB=1", "CFDB_CALCRHS_NB=0", "CFDB_CALCRHS_NB=1,CFDB_CALCRHS_MINB=3",
                                  "CFDB_STAGE_OVERLAP=1,CFDB_CALCRHS_PAD_KB=60"])
 def test_optional_paths_bit_exact(env):
     """Every opt-in code path kept in the library (profiles/r1_experiments.md) produces the same bits as the default."""
