@@ -591,16 +591,11 @@ __device__ __forceinline__ void calcrhs_body(const Gas& g, const double (&Un)[3]
             en_k[k] = U_k[3] / U_k[0];
         }
     }
-    // CFDB_ROLL_K=1 (experiment): the Gauss-point loop left rolled — one copy of its ~350 instructions instead of three
-#ifndef CFDB_ROLL_K
-#define CFDB_ROLL_K 0
-#endif
+    // The viscous branch-free form keeps the Gauss-point loop rolled (one copy of its ~600 instructions instead of three:
+    // 1.79 -> 1.69 ms per launch); everywhere else unrolling wins (Euler: 1.10 unrolled, 1.28 rolled).
+    constexpr int kUnroll = (VISC && NB) ? 1 : 3;
 #define CFDB_SEL3(a) (k == 0 ? a[0] : (k == 1 ? a[1] : a[2]))
-#if CFDB_ROLL_K
-#pragma unroll 1
-#else
-#pragma unroll
-#endif
+#pragma unroll kUnroll
     for (int k = 0; k < 3; ++k) {
         // N(:,k): zero at local node k, one half elsewhere (calcRHS.f90:18-23)
         const double Nk[3] = {k == 0 ? 0.0 : .5, k == 1 ? 0.0 : .5, k == 2 ? 0.0 : .5};
@@ -720,7 +715,7 @@ __device__ __forceinline__ void calcrhs_body(const Gas& g, const double (&Un)[3]
 // one element, loads to stores; returns the fast-path flag (always 0 for NB = false)
 template <bool VISC, bool THETA, bool ALE, bool NB>
 __device__ __forceinline__ unsigned calcrhs_one(int e, CFDB_CALC_PARAMS) {
-    int ip[3] = {inp[e], inp[nelem + e], inp[2 * (size_t)nelem + e]};
+    const int ip[3] = {inp[e], inp[nelem + e], inp[2 * (size_t)nelem + e]};
     double Nx[3] = {dNx[e], dNx[nelem + e], dNx[2 * (size_t)nelem + e]};
     double Ny[3] = {dNy[e], dNy[nelem + e], dNy[2 * (size_t)nelem + e]};
     double Un[3][4], Th[3][4], Tn[3] = {0.0, 0.0, 0.0};
