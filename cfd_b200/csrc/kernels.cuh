@@ -1258,6 +1258,22 @@ __global__ void __launch_bounds__(256) spmv(int npoin, const double* __restrict_
     for (int j = rowptr[i]; j < rowptr[i + 1]; ++j) dot = dot + A[j] * v[idx[j]];
     y[i] = dot;
 }
+// two products with one matrix (the first SpMV of fluidStructure's x- and y-solve): each row's two sums in the same order
+__global__ void __launch_bounds__(256) spmv2(int npoin, const double* __restrict__ A, const int* __restrict__ idx,
+                                              const int* __restrict__ rowptr, const double* __restrict__ v1,
+                                              const double* __restrict__ v2, double* __restrict__ y1, double* __restrict__ y2) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npoin) return;
+    double d1 = 0.0, d2 = 0.0;
+    for (int j = rowptr[i]; j < rowptr[i + 1]; ++j) {
+        const double a = A[j];
+        const int cidx = idx[j];
+        d1 = d1 + a * v1[cidx];
+        d2 = d2 + a * v2[cidx];
+    }
+    y1[i] = d1;
+    y2[i] = d2;
+}
 enum { ALFA_CONST = 0, ALFA_POS = 1, ALFA_NEG = 2, BETA_POS = 3 };
 // z = alfa*x + y  with alfa taken from the device scalars (vecsum, :79)
 // (no __restrict__: biCG calls it in place, z aliasing x or y; each thread touches only its own index)

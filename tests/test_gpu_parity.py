@@ -331,6 +331,28 @@ def test_config2_size_wedge_1m_triangles():
     assert_bit_equal(g2.get("U"), g.get("U"), "second run")
 
 
+def test_config3_size_ale_4m_triangles():
+    """BASELINE config 3 at full size: 4.0 M-triangle O-mesh around a pitching ellipse, MOVING=1 (FORCES, TRANSF, two biCG
+    mesh solves, NORMALES/DERIV/MASAS/laplace refreshed every step), two steps bit-exact against the oracle."""
+    from cfd_b200 import deck, meshgen
+    from cfd_b200.solver import NSComp2D
+    from oracle.orclib import Oracle
+
+    lc = deck.load(meshgen.ale_body(nt=2000, nr=1000))
+    assert lc.nelem == 3_996_000
+    g, o = NSComp2D(lc), Oracle(lc)
+    o.set_scalar("norms_every_step", 0)
+    x0 = g.get("X").copy()
+    g.step(2)
+    o.step(2)
+    for n in ("U", "T", "X", "Y", "W_X", "W_Y", "M", "area", "dNx", "dNy", "lap_sparse", "SHOC", "T_SUGN2", "RHS"):
+        assert_bit_equal(g.get(n), o.get(n), n)
+    assert g.scalar("DTMIN") == o.scalar("DTMIN") and g.scalar("bicg_y") == o.scalar("bicg_y")
+    # size-independent properties: the body moved, the mesh stayed valid, the lumped mass is the area
+    assert np.abs(g.get("X") - x0).max() > 0 and g.get("area").min() > 0
+    assert abs(g.get("M").sum() - g.get("area").sum()) <= 1e-12 * g.get("area").sum()
+
+
 def test_no_bc_lists_and_isolated_node():
     """cfdb_create with bc = NULL-equivalent empty lists and a node no element references."""
     from cfd_b200 import deck, meshgen
@@ -403,7 +425,7 @@ def test_operands_outside_the_fast_paths_take_the_plain_form(cases):
 @pytest.mark.parametrize("env", ["CFDB_STAGE_OVERLAP=1", "CFDB_CALCRHS_PIPE=3", "CFDB_CALCRHS_PIPE=4", "CFDB_TILE=1", "CFDB_CHUNK=100",
                                  "CFDB_CHUNK=100,CFDB_CHUNK_SEQ=1", "CFDB_BICG_UNFUSED=1", "CFDB_CALCRHS_MINB=3",
                                  "CFDB_CALCRHS_MINB=5", "CFDB_ESTAB_MINB=3", "CFDB_ESTAB_MINB=5", "CFDB_HOST_TOPO=1",
-                                 "CFDB_CALCRHS_NB=1", "CFDB_CALCRHS_NB=0", "CFDB_CALCRHS_NB=1,CFDB_CALCRHS_MINB=3",
+                                 "CFDB_CALCRHS_NB=1", "CFDB_CALCRHS_NB=0", "CFDB_CALCRHS_NB=1,CFDB_CALCRHS_MINB=3", "CFDB_BICG_NOPRE=1",
                                  "CFDB_STAGE_OVERLAP=1,CFDB_CALCRHS_PAD_KB=60"])
 def test_optional_paths_bit_exact(env):
     """Every opt-in code path kept in the library (profiles/r1_experiments.md) produces the same bits as the default."""
