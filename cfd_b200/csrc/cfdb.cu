@@ -1419,7 +1419,8 @@ static int step_once(cfdb_ctx* c) {
     TRY(run_rk(c));
     // RHS history copies for BANDERA 2..4 (subrutinas.f90:830-848); BANDERA lives on the device, the kernel
     // exits at once for any other value
-    LAUNCH(K_FILL, k::rhs_history, grid_for(4 * (long)P, 256), 256, 4 * (long)P, c->sc, c->RHS.p, c->RHS1.p, c->RHS2.p, c->RHS3.p);
+    LAUNCH(K_FILL, k::rhs_history, (int)std::min<long>(grid_for(4 * (long)P, 256), 148 * 8), 256, 4 * (long)P, c->sc, c->RHS.p, c->RHS1.p,
+           c->RHS2.p, c->RHS3.p);
     double dtmin = 0.0, time = 0.0;
     if (c->nse) {  // pitching law needs TIME on the host (meshMove.f90:70)
         TRY(read_scal(c));

@@ -272,10 +272,10 @@ __global__ void rhs_history(long n, const Scal* sc, const double* __restrict__ R
                             double* __restrict__ R2, double* __restrict__ R3) {
     int b = sc->BANDERA;
     if (b < 2 || b > 4) return;
-    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-    if (i >= n) return;
     double* dst = b == 2 ? R3 : b == 3 ? R2 : R1;
-    dst[i] = RHS[i];
+    // grid-stride: the launch is a fixed small grid, so the steps on which nothing is copied (all but three) cost a
+    // few hundred CTAs that exit at once instead of one per 256 entries
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) dst[i] = RHS[i];
 }
 __global__ void fill_const(long n, double* __restrict__ a, double v) {
     long i = blockIdx.x * (long)blockDim.x + threadIdx.x;

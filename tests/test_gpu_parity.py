@@ -60,6 +60,7 @@ def test_steps_bit_exact(cases, name):
         g.step(chunk)
         o.step(chunk)
         _compare(g, o, tag=f"{name}@{int(o.scalar('ITER'))}:")
+        _compare(g, o, names=["RHS1", "RHS2", "RHS3"], tag=f"{name}@{int(o.scalar('ITER'))}:")  # subrutinas.f90:830-848
         for s in ("DTMIN", "DTMIN1", "TIME", "ITER", "BANDERA"):
             assert g.scalar(s) == o.scalar(s), s
     er_g, err_g = g.norms()
