@@ -889,20 +889,15 @@ static int run_calcrhs_elem(cfdb_ctx* c, const k::Gas& g, bool theta, bool ale, 
         return 0;
     }
     int sel = (visc ? 4 : 0) | (theta ? 2 : 0) | (ale ? 1 : 0);
-    // defaults from the A/B runs in profiles/r1_experiments.md
-#ifndef CFDB_NB_DEFAULT
-#define CFDB_NB_DEFAULT(visc) (visc)
-#endif
-#ifndef CFDB_MINB_DEFAULT
-#define CFDB_MINB_DEFAULT(visc, nb) (((visc) && (nb)) ? 3 : 4)
-#endif
     // 4 CTAs/SM (128 registers, 16 warps/SM) is the measured optimum once the nine Gauss-point divisions are issued
     // up front: 1.11 ms per launch against 1.23 (3 CTAs), 1.33 (5), 1.88 (6) on the 16 M-triangle mesh
     static const int minb_env = getenv("CFDB_CALCRHS_MINB") ? atoi(getenv("CFDB_CALCRHS_MINB")) : 0;
     // branch-free division forms (kernels.cuh: calcrhs_one<.., NB>): CFDB_CALCRHS_NB=0/1 forces them off/on
     static const int nb_env = getenv("CFDB_CALCRHS_NB") ? atoi(getenv("CFDB_CALCRHS_NB")) : -1;
-    const bool nb = nb_env >= 0 ? nb_env != 0 : CFDB_NB_DEFAULT(visc);
-    const int minb = minb_env ? minb_env : CFDB_MINB_DEFAULT(visc, nb);
+    // defaults from the A/B runs in profiles/r1_experiments.md: branch-free forms for viscous flow only (1.96 -> 1.67 ms at
+    // 3 CTAs/SM with the Gauss loop rolled), the plain form at 4 CTAs/SM for Euler flow (1.10 against 1.14)
+    const bool nb = nb_env >= 0 ? nb_env != 0 : visc;
+    const int minb = minb_env ? minb_env : ((visc && nb) ? 3 : 4);
 #define PICK(M)                                                                                                   \
     switch (sel | (nb ? 8 : 0)) {                                                                                 \
         case 0: kern = k::calcrhs_elem<false, false, false, M>; break;                                            \
