@@ -836,7 +836,7 @@ static int run_estab(cfdb_ctx* c, const double* dtmin_dev) {
     // branch-free estab_fast: 64 regs without spills (MINB 4) 0.617 ms, 48 regs (5) 0.676, 40 regs (6) 0.809; the plain form was 1.06
     static int minb = getenv("CFDB_ESTAB_MINB") ? atoi(getenv("CFDB_ESTAB_MINB")) : 4;
     auto kern = k::estab<3, true>;
-    if (c->ale) {
+    if (c->ale || c->nranks > 1) {  // a rank of a multi-GPU run never assumes W = 0 from its own lists alone
         if (minb == 4) kern = k::estab<4, true>;
         else if (minb == 5) kern = k::estab<5, true>;
         else if (minb == 6) kern = k::estab<6, true>;
@@ -1398,8 +1398,9 @@ static int step_once(cfdb_ctx* c) {
     c->h_iter += 1;
     LAUNCH(K_DTLOGIC, k::step_begin, 1, 1, c->sc);
     {
-        auto kdt = p.ITLOCAL != 0 ? (c->ale ? k::deltat<true, true> : k::deltat<true, false>)
-                                  : (c->ale ? k::deltat<false, true> : k::deltat<false, false>);
+        const bool moving = c->ale || c->nranks > 1;  // as in run_estab
+        auto kdt = p.ITLOCAL != 0 ? (moving ? k::deltat<true, true> : k::deltat<true, false>)
+                                  : (moving ? k::deltat<false, true> : k::deltat<false, false>);
         LAUNCH(K_DELTAT, kdt, grid_for(E, 256), 256, E, c->inp.p, c->area.p, c->T.p, c->VEL_X.p, c->VEL_Y.p,
                c->W_X.p, c->W_Y.p, p.FSAFE, p.T_inf, c->DT.p, c->sc);
     }
@@ -1454,6 +1455,11 @@ extern "C" int cfdb_set_option(cfdb_ctx* c, const char* name, int32_t value) {
     if (n == "fast") c->fast = value;
     else if (n == "use_cuarto") c->use_cuarto = value;
     else if (n == "true_rk") c->true_rk = value;
+    else if (n == "ale") {
+        // The mesh moves although this context holds no body set of its own: a rank of a multi-GPU run whose sub-domain
+        // does not touch the body still receives W_X, W_Y from the global mesh solve (cfd_b200/partition.py sets this).
+        if (value && !c->ale) { c->ale = true; TRY(zero(c, c->FC, 12 * (size_t)c->nelem)); }
+    }
     else return fail("cfdb_set_option: unknown option " + n);
     if (c->chunk_ev.size() > 1 && (c->use_cuarto || c->true_rk)) return fail("cfdb_set_option: not available with CFDB_CHUNK");
     return 0;

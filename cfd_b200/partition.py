@@ -38,6 +38,8 @@ class LocalPart:
     neighbors: list = field(default_factory=list)
     send: dict = field(default_factory=dict)   # rank -> local ids of owned nodes that rank needs (by gid)
     recv: dict = field(default_factory=dict)   # rank -> local ids of ghost nodes that rank owns (by gid)
+    moving: bool = False        # the GLOBAL case has body sets (fluidStructure moves the mesh on every rank, also on
+                                # ranks whose local deck holds none of the set edges)
 
     def halo_arrays(self):
         """Flattened CSR form for cfdb_set_halo: ranks, send_ptr, send_idx, recv_ptr, recv_idx (0-based)."""
@@ -152,7 +154,8 @@ def build_local(lc: LoadedCase, nranks: int, rank: int, elem_rank: np.ndarray | 
         sets=sets, ifm=ifm, i_m=i_m, ilaux=np.concatenate([i_m, ifm]).astype(I32), smooth_fix=fix,
     )
     return LocalPart(rank=rank, nranks=nranks, lc=local, node_gid=node_gid[order], elem_gid=elem_gid[loc_el],
-                     n_owned=int(n_owned), elem_own=(elem_rank[loc_el] == rank), neighbors=neighbors, send=send, recv=recv)
+                     n_owned=int(n_owned), elem_own=(elem_rank[loc_el] == rank), neighbors=neighbors, send=send, recv=recv,
+                     moving=bool(lc.sets.size))
 
 
 def square_window(n: int, nranks: int, rank: int, rows_per: int | None = None, **kw):

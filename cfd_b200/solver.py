@@ -66,6 +66,8 @@ class NSComp2D:
         ranks, sp, si, rp, ri = part.halo_arrays()
         self._halo_keep = (ranks, sp, si, rp, ri)
         capi.check(self.L.cfdb_set_halo(self.h, part.n_owned, ranks.size, ranks, sp, si, rp, ri))
+        if getattr(part, "moving", False):
+            self.set_option("ale", 1)   # FUENTE and the mesh-velocity terms also on ranks without body edges of their own
         self.part = part
 
     def comm_init(self, uid: bytes, rank: int, nranks: int):
@@ -179,7 +181,8 @@ class NSComp2D:
         self.set("VEL_Y", z)
 
     def set_option(self, name, value):
-        """'use_cuarto' / 'true_rk' (SURVEY.md §8f N1, N2); default 0 = the reference's behaviour."""
+        """'use_cuarto' / 'true_rk' (SURVEY.md §8f N1, N2); default 0 = the reference's behaviour.  'ale' = 1: the mesh moves
+        although this context's own deck has no body sets (ranks of a multi-GPU run, set by attach_partition)."""
         capi.check(self.L.cfdb_set_option(self.h, name.encode(), int(value)))
 
     @property

@@ -82,6 +82,20 @@ def test_strip_window_equals_global(nranks):
             assert np.array_equal(getattr(a.lc, f), getattr(b.lc, f)), f
 
 
+def test_every_rank_of_a_moving_mesh_case_is_flagged_moving():
+    """The body sets of the ALE case end up on one rank only, but fluidStructure moves the mesh everywhere: LocalPart.moving
+    (-> cfdb_set_option "ale": FUENTE and the mesh-velocity terms of ESTAB/deltat) must be set on every rank; fixed-mesh
+    cases are not flagged."""
+    from cfd_b200 import deck, meshgen, partition
+
+    glc = deck.load(meshgen.ale_body(nt=48, nr=14))
+    parts = [partition.build_local(glc, 2, r) for r in range(2)]
+    assert any(p.lc.sets.size == 0 for p in parts) and any(p.lc.sets.size > 0 for p in parts)
+    assert all(p.moving for p in parts)
+    flc = deck.load(meshgen.channel(nx=21, ny=9))
+    assert not any(partition.build_local(flc, 2, r).moving for r in range(2))
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
