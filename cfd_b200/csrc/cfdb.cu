@@ -1617,7 +1617,9 @@ extern "C" int cfdb_set(cfdb_ctx* c, const char* name, const void* host, int64_t
             CK(cudaMemcpyAsync(c->U1.p, c->U.p, f.count * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
             CK(cudaStreamSynchronize(c->st));
         }
-        if (n == "W_X" || n == "W_Y") {
+        // anything that can make the mesh velocity non-zero on a context without body sets: from here on the context
+        // computes FUENTE and the mesh-velocity terms of ESTAB/deltat
+        if (n == "W_X" || n == "W_Y" || n == "xpos" || n == "ypos" || n == "dxpos" || n == "dypos") {
             if (!c->ale) { c->ale = true; TRY(zero(c, c->FC, 12 * (size_t)c->nelem)); }
         }
         return 0;
