@@ -18,7 +18,7 @@ SYMBOLS = [
     "cfdb_last_error", "cfdb_device_count", "cfdb_create", "cfdb_destroy", "cfdb_init", "cfdb_step", "cfdb_sync",
     "cfdb_rk_stage", "cfdb_geometry", "cfdb_fluid_structure", "cfdb_residual_norms", "cfdb_step_norms", "cfdb_force_visc", "cfdb_printflavia", "cfdb_format_cnv", "cfdb_format_real", "cfdb_get", "cfdb_set",
     "cfdb_field_size", "cfdb_get_scalar", "cfdb_set_scalar", "cfdb_set_option", "cfdb_stream", "cfdb_profile_enable", "cfdb_profile_get",
-    "cfdb_launch_count", "cfdb_nccl_unique_id", "cfdb_comm_init", "cfdb_set_halo", "cfdb_halo_exchange", "cfdb_calcrhs", "cfdb_fuente", "cfdb_deltat", "cfdb_estab", "cfdb_deriv", "cfdb_masas",
+    "cfdb_launch_count", "cfdb_nccl_unique_id", "cfdb_comm_init", "cfdb_set_halo", "cfdb_halo_exchange", "cfdb_set_reduction_layout", "cfdb_calcrhs", "cfdb_fuente", "cfdb_deltat", "cfdb_estab", "cfdb_deriv", "cfdb_masas",
     "cfdb_normales", "cfdb_laplace", "cfdb_bicg", "cfdb_spmv", "cfdb_vecdot", "cfdb_gcl_main", "cfdb_smoothing", "cfdb_selftest", "cfdb_get_esup",
     "cfdb_get_psup",
 ]
@@ -90,6 +90,7 @@ def lib():
     L.cfdb_comm_init.argtypes = [vp, vp, i32, i32]
     L.cfdb_set_halo.argtypes = [vp, i32, i32, _ip, _ip, _ip, _ip, _ip]
     L.cfdb_halo_exchange.argtypes = [vp, cp]
+    L.cfdb_set_reduction_layout.argtypes = [vp, i64, i64]
     L.cfdb_calcrhs.argtypes = [vp] + [_dp] * 12 + [_ip, i32, i32] + [d] * 6
     L.cfdb_fuente.argtypes = [vp] + [_dp] * 8 + [_ip, i32, i32]
     L.cfdb_deltat.argtypes = [vp, _dp, _dp, _ip] + [_dp] * 6 + [i32, i32] + [d] * 4

@@ -96,13 +96,6 @@ static const char* kKernelNames[K_COUNT] = {"deriv", "masas", "normales", "delta
 struct cfdb_ctx {
     int device = 0;
     cudaStream_t st = nullptr;
-    cudaStream_t st2 = nullptr;            // node kernels of a stage run here, overlapping the element kernels on st
-    vector<int> chunk_e, chunk_n;          // element / node range boundaries of the stage pipeline (nchunk+1 each)
-    vector<cudaEvent_t> chunk_ev;
-    cudaEvent_t ev_join = nullptr;
-    cudaEvent_t ev_elem[4] = {nullptr, nullptr, nullptr, nullptr}, ev_node[4] = {nullptr, nullptr, nullptr, nullptr};
-    double* ECcur = nullptr;  // staging buffers the element / node kernels use right now (double-buffered when
-    double* FCcur = nullptr;  // node_update(k) overlaps calcrhs_elem(k+1))
     const double* Usrc = nullptr;  // state calcRHS/FUENTE are evaluated at (U, or U1 for true_rk stages 2..4)
     cfdb_params par{};
     int npoin = 0, nelem = 0;
@@ -112,14 +105,20 @@ struct cfdb_ctx {
     int npsup = 0;
     vector<int32_t> h_wall, h_wn_node, h_ilaux, h_fixidx_last;
     int nnz = 0, maxrow = 0, nwn = 0, nb = 0, nmove = 0, nnmove = 0, nset = 0, nse = 0;
-    bool ale = false;  // mesh can move (body sets present or W set by the caller)
+    bool ale = false;  // mesh can move (body sets present or W set by the caller; multi-rank: on ANY rank, see agree_on_ale)
+    bool ale_agreed = false;
+    // CUDA graphs of the fixed-mesh step, one per parity of the U/U1 buffer swap (step_graph)
+    cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+    uint64_t epoch = 0, gepoch[2] = {0, 0};
+    const double* gU[2] = {nullptr, nullptr};
+    int64_t glaunches[2] = {0, 0}, graph_replays = 0;
     // device: mesh
     DBuf<int> inp, d_esup2, eslot, d_lap_idx, d_lap_rowptr, wall, wn_node, wn_ptr, wn_edge, wn_valid;
     DBuf<unsigned char> lpos, bcflag;
     DBuf<double> X, Y, X1, Y1, area, HH, HHX, HHY, dNx, dNy, M;
     // device: state
     DBuf<double> U, U1, RHS, RHS1, RHS2, RHS3, UN, VEL_X, VEL_Y, W_X, W_Y, P, T, RHO, E, RMACH, GAMM;
-    DBuf<double> SHOC, TS1, TS2, TS3, DT, DTL, EC, FC, EC2, FC2;
+    DBuf<double> SHOC, TS1, TS2, TS3, DT, DTL, EC, FC;
     // device: BC tables
     DBuf<int> bc_node, bc_kind, bc_wslot;
     DBuf<double> bc_vx, bc_vy, bc_rho, bc_T, wn_x, wn_y;
@@ -147,17 +146,15 @@ struct cfdb_ctx {
     int use_cuarto = 0, true_rk = 0;  // "next" rows N1 / N2, default off (reference behaviour)
     int fast = 0;                     // relaxed stage (FMA + atomic scatter), opt-in, NOT bit-exact
     bool u1_is_u = false;  // after U = U1 (ns2DComp.ALE.f90:277-281) the two arrays are one buffer
-    // tile-fused RK stage (fixed meshes)
-    bool tile_ok = false;
-    int ntiles = 0, nbnodes = 0;
-    double tile_interior = 0.0;
-    DBuf<int> tile_elems, tnode_ptr, tnodes, bnodes;
-    DBuf<unsigned char> ebmask;
-    DBuf<unsigned short> tslot;
     // multi-GPU (one rank per context)
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
     int n_owned = 0;           // reductions run over local nodes [0,n_owned)
+    // chunk-aligned ownership (cfdb_set_reduction_layout): the owned nodes are the global range [red_gid0, red_gid0+n_owned),
+    // red_gid0 % 4096 == 0, so this rank's first-level chunk sums ARE chunk sums of the global canonical order
+    bool red_aligned = false;
+    long red_chunk0 = 0, red_nchunk_global = 0;
+    DBuf<double> redG;
     vector<int> nb_rank, send_ptr, recv_ptr;
     DBuf<int> send_idx, recv_idx;
     DBuf<double> sendbuf, recvbuf;
@@ -199,7 +196,6 @@ static int prof_end(cfdb_ctx* c, cudaStream_t st, int id, cudaEvent_t a, cudaEve
 static int prof_resolve(cfdb_ctx* c) {
     if (c->pending.empty()) return 0;
     CK(cudaStreamSynchronize(c->st));
-    if (c->st2) CK(cudaStreamSynchronize(c->st2));
     for (auto& p : c->pending) {
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, p.a, p.b));
@@ -385,7 +381,7 @@ static int build_bc_tables(cfdb_ctx* c, const cfdb_bc* bc) {
 }
 
 // The device-built topology (topo_gpu.cu) is mirrored into the host vectors only when something asks for it: cfdb_get of
-// esup1/esup2/psup1/psup2/lap_idx/lap_rowptr, the CFDB_CHUNK planner, the CFDB_TILE tiler.
+// esup1/esup2/psup1/psup2/lap_idx/lap_rowptr, the stage tiler.
 static int ensure_host_topology(cfdb_ctx* c) {
     if (c->host_topo_valid) return 0;
     const size_t P = c->npoin, E = c->nelem;
@@ -424,6 +420,9 @@ extern "C" int cfdb_create(cfdb_ctx** out, const cfdb_params* par, int32_t npoin
     CK(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return fail("cfdb_create: device is not sm_100 (this library is built for sm_100a only)");
     if (npoin < 1 || nelem < 1) return fail("cfdb_create: empty mesh");
+    // NGAS /= 0 selects the equilibrium-air TGAS branch of the reference (subrutinas.f90:706-741, ns2DComp.ALE.f90:78,456),
+    // which this library does not implement: refuse the deck instead of silently running ideal gas
+    if (par->NGAS != 0) return fail("cfdb_create: NGAS /= 0 (equilibrium-air TGAS) is not implemented; only the ideal-gas path NGAS = 0");
     for (size_t k = 0; k < 3 * (size_t)nelem; ++k)
         if (inpoel[k] < 1 || inpoel[k] > npoin) return fail("cfdb_create: inpoel entry out of range");
     lap("validate inpoel");
@@ -437,17 +436,7 @@ extern "C" int cfdb_create(cfdb_ctx** out, const cfdb_params* par, int32_t npoin
     c->nelem = nelem;
     c->n_owned = npoin;
     auto bail = [&](int r) { cfdb_destroy(c); return r; };
-    {
-        int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = greatest priority (numerically lowest)
-        if (cudaStreamCreateWithPriority(&c->st, cudaStreamNonBlocking, lo) != cudaSuccess) return bail(fail("stream create failed"));
-        if (cudaStreamCreateWithPriority(&c->st2, cudaStreamNonBlocking, hi) != cudaSuccess) return bail(fail("stream create failed"));
-        if (cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) return bail(fail("event create failed"));
-        for (int i = 0; i < 4; ++i)
-            if (cudaEventCreateWithFlags(&c->ev_elem[i], cudaEventDisableTiming) != cudaSuccess ||
-                cudaEventCreateWithFlags(&c->ev_node[i], cudaEventDisableTiming) != cudaSuccess)
-                return bail(fail("event create failed"));
-    }
+    if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) return bail(fail("stream create failed"));
     const size_t P = npoin, E = nelem;
 #define B(x)                    \
     do {                        \
@@ -497,33 +486,6 @@ extern "C" int cfdb_create(cfdb_ctx** out, const cfdb_params* par, int32_t npoin
     }
     if (host_topo) c->nnz = c->lap_rowptr[npoin];
     if (host_topo) lap("host topology");
-    {
-        // stage pipeline: element chunk k is followed by the nodes all of whose elements lie in chunks <= k
-        // (measured on B200, 16 M triangles: the pipeline does not pay — 10.2 ms/step against 9.5 ms for whole-mesh
-        // launches — so it is off unless CFDB_CHUNK is set; kept because it is bit-identical and tested)
-        long chunk = getenv("CFDB_CHUNK") ? atol(getenv("CFDB_CHUNK")) : nelem;
-        if (chunk < 64) chunk = nelem;
-        int nch = (int)((nelem + chunk - 1) / chunk);
-        if (nch > 1) B(ensure_host_topology(c));
-        c->chunk_e.assign(nch + 1, 0);
-        c->chunk_n.assign(nch + 1, 0);
-        for (int k = 1; k <= nch; ++k) c->chunk_e[k] = (int)std::min<long>(nelem, k * chunk);
-        int n = 0, pm = -1;
-        for (int k = 1; k <= nch && nch > 1; ++k) {
-            while (n < npoin) {
-                int emax = c->esup2[n + 1] > c->esup2[n] ? c->esup1[c->esup2[n + 1] - 1] - 1 : -1;
-                int pm2 = std::max(pm, emax);
-                if (pm2 >= c->chunk_e[k]) break;
-                pm = pm2;
-                ++n;
-            }
-            c->chunk_n[k] = n;
-        }
-        c->chunk_n[nch] = npoin;
-        c->chunk_ev.resize(nch);
-        for (auto& e : c->chunk_ev)
-            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail(fail("event create failed"));
-    }
     if (c->maxrow > 32) return bail(fail("node valence above 31 is not supported"));
     if (host_topo) {
         vector<int32_t> idx0(c->lap_idx);
@@ -549,7 +511,7 @@ extern "C" int cfdb_create(cfdb_ctx** out, const cfdb_params* par, int32_t npoin
     B(zero(c, c->lap_sparse, (size_t)c->nnz));
     size_t nchunk = (std::max(P, E) + 4095) / 4096;
     B(zero(c, c->redA, 8 * nchunk + 8));
-    B(zero(c, c->redB, 8 * ((nchunk + 4095) / 4096) + 8));
+    B(zero(c, c->redB, 64 * 8 * ((nchunk + 4095) / 4096) + 8));   // x64: room for the global chunk count of a multi-rank tree
     B(zero(c, c->flags, 4));
     c->par.XREF[1] = 1.4;  // meshMove.f90:58 overwrites set 2's reference point before its first use
     c->par.YREF[1] = 0.0;
@@ -561,27 +523,6 @@ extern "C" int cfdb_create(cfdb_ctx** out, const cfdb_params* par, int32_t npoin
     if (verbose) cudaStreamSynchronize(c->st);
     lap("BC tables");
     if (c->ale) B(zero(c, c->FC, 12 * E));
-    if (!c->ale && getenv("CFDB_TILE") && atoi(getenv("CFDB_TILE")) != 0) {
-        // tiles for the fused stage (opt-in: measured slower than the two-kernel stage on B200 — 1.70 + 0.27 ms against
-        // 1.10 + 0.62 ms per stage on the 16 M-triangle mesh; the memory-bound node phase starves at the 12 warps/SM
-        // the register-heavy element phase allows.  Bit-identical, covered by the GPU tests under CFDB_TILE=1.)
-        topo::Tiling T;
-        B(ensure_host_topology(c));
-        topo::build_tiling(inpoel, nelem, npoin, X, Y, c->esup1, c->esup2, c->h_eslot, 512, T);
-        c->tile_interior = T.interior_fraction;
-        {
-            c->ntiles = T.ntiles;
-            c->nbnodes = (int)T.bnodes.size();
-            B(upload(c, c->tile_elems, T.tile_elems));
-            B(upload(c, c->ebmask, T.ebmask));
-            B(upload(c, c->tnode_ptr, T.tnode_ptr));
-            B(upload(c, c->tnodes, T.tnodes));
-            B(upload(c, c->tslot, T.tslot));
-            B(upload(c, c->bnodes, T.bnodes));
-            CK(cudaStreamSynchronize(c->st));
-            c->tile_ok = true;
-        }
-    }
     if (cudaMalloc(&c->sc, sizeof(k::Scal)) != cudaSuccess) return bail(fail("cudaMalloc Scal failed"));
     if (cudaMemsetAsync(c->sc, 0, sizeof(k::Scal), c->st) != cudaSuccess) return bail(fail("memset Scal failed"));
     if (cudaMallocHost(&c->h_sc, sizeof(k::Scal)) != cudaSuccess) return bail(fail("cudaMallocHost failed"));
@@ -596,21 +537,15 @@ extern "C" void cfdb_destroy(cfdb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->st) cudaStreamSynchronize(c->st);
-    if (c->st2) cudaStreamSynchronize(c->st2);
+    for (int i = 0; i < 2; ++i) if (c->gexec[i]) cudaGraphExecDestroy(c->gexec[i]);
     if (c->comm) ncclCommDestroy(c->comm);
-    c->send_idx.release(); c->recv_idx.release(); c->sendbuf.release(); c->recvbuf.release();
-    for (auto e : c->chunk_ev) cudaEventDestroy(e);
-    if (c->ev_join) cudaEventDestroy(c->ev_join);
-    for (int i = 0; i < 4; ++i) { if (c->ev_elem[i]) cudaEventDestroy(c->ev_elem[i]); if (c->ev_node[i]) cudaEventDestroy(c->ev_node[i]); }
-    c->EC2.release(); c->FC2.release();
-    if (c->st2) cudaStreamDestroy(c->st2);
+    c->send_idx.release(); c->recv_idx.release(); c->sendbuf.release(); c->recvbuf.release(); c->redG.release();
     for (auto* d : {&c->inp, &c->d_esup2, &c->eslot, &c->d_lap_idx, &c->d_lap_rowptr, &c->wall, &c->wn_node, &c->wn_ptr,
                     &c->wn_edge, &c->wn_valid, &c->bc_node, &c->bc_kind, &c->bc_wslot, &c->ilaux, &c->ilaux_last, &c->se_node,
                     &c->se_set, &c->set_ptr, &c->set_n1, &c->set_n2, &c->set_el, &c->d_psup1, &c->d_psup2, &c->flags})
         d->release();
     c->lpos.release();
     c->bcflag.release();
-    c->tile_elems.release(); c->tnode_ptr.release(); c->tnodes.release(); c->bnodes.release(); c->ebmask.release(); c->tslot.release();
     c->isfix.release();
     c->bp2.release(); c->by2.release(); c->pos_aux2.release();
     for (auto* d : {&c->X, &c->Y, &c->X1, &c->Y1, &c->area, &c->HH, &c->HHX, &c->HHY, &c->dNx, &c->dNy, &c->M, &c->U, &c->U1,
@@ -645,6 +580,7 @@ extern "C" int cfdb_comm_init(cfdb_ctx* c, const void* uid128, int32_t rank, int
     NK(ncclCommInitRank(&c->comm, nranks, id, rank));
     c->rank = rank;
     c->nranks = nranks;
+    c->epoch++;
     return 0;
 }
 extern "C" int cfdb_set_halo(cfdb_ctx* c, int32_t n_owned, int32_t nneigh, const int32_t* neigh_rank,
@@ -662,8 +598,27 @@ extern "C" int cfdb_set_halo(cfdb_ctx* c, int32_t n_owned, int32_t nneigh, const
         if (recv_idx[i] < n_owned || recv_idx[i] >= c->npoin) return fail("cfdb_set_halo: receive list must name ghost nodes");
     TRY(upload(c, c->send_idx, send_idx, (size_t)c->send_ptr[nneigh]));
     TRY(upload(c, c->recv_idx, recv_idx, (size_t)c->recv_ptr[nneigh]));
-    TRY(c->sendbuf.alloc(7 * (size_t)c->send_ptr[nneigh] + 8));
-    TRY(c->recvbuf.alloc(7 * (size_t)c->recv_ptr[nneigh] + 8));
+    TRY(c->sendbuf.alloc(k::HALO_W * (size_t)c->send_ptr[nneigh] + 8));
+    TRY(c->recvbuf.alloc(k::HALO_W * (size_t)c->recv_ptr[nneigh] + 8));
+    CK(cudaStreamSynchronize(c->st));
+    c->epoch++;
+    return 0;
+}
+// chunk-aligned ownership: this rank's owned nodes are the global nodes [gid0, gid0 + n_owned)
+extern "C" int cfdb_set_reduction_layout(cfdb_ctx* c, int64_t gid0, int64_t npoin_global) {
+    CK(cudaSetDevice(c->device));
+    if (gid0 < 0 || gid0 % 4096 != 0) return fail("cfdb_set_reduction_layout: gid0 must be a non-negative multiple of 4096");
+    if (gid0 + c->n_owned > npoin_global) return fail("cfdb_set_reduction_layout: owned range exceeds the global node count");
+    if (c->n_owned % 4096 != 0 && gid0 + c->n_owned != npoin_global)
+        return fail("cfdb_set_reduction_layout: only the last rank may own a partial chunk");
+    c->red_chunk0 = gid0 / 4096;
+    c->red_nchunk_global = (npoin_global + 4095) / 4096;
+    TRY(c->redG.alloc(8 * (size_t)c->red_nchunk_global + 8));
+    // the upper tree levels run over the global chunk count: redA/redB must hold 8 vectors of ceil(M/4096) sums
+    const size_t need = 8 * (((size_t)c->red_nchunk_global + 4095) / 4096) + 8;
+    if (c->redA.n < need || c->redB.n < need) return fail("cfdb_set_reduction_layout: reduction scratch too small for the global chunk count");
+    c->red_aligned = true;
+    c->epoch++;
     CK(cudaStreamSynchronize(c->st));
     return 0;
 }
@@ -691,15 +646,16 @@ static int halo_vec(cfdb_ctx* c, double* v, int w) {
     if (mr) LAUNCH(K_HALO, k::halo_unpack, grid_for((long)mr * w, 128), 128, mr, w, c->recv_idx.p, c->recvbuf.p, v);
     return 0;
 }
-// ghosts of U1, T, VEL_X, VEL_Y in one message per neighbour (after every RK stage)
+// ghosts of U1, T, VEL_X, VEL_Y, RHO, E, P, RMACH in one message per neighbour (after every RK stage)
 static int halo_state(cfdb_ctx* c, cudaStream_t st = nullptr) {
     const int nn = (int)c->nb_rank.size();
     if (!nn) return 0;
     if (!st) st = c->st;
     int ms = c->send_ptr[nn], mr = c->recv_ptr[nn];
-    if (ms) LAUNCH_ON(st, K_HALO, k::halo_pack_state, grid_for(ms, 128), 128, ms, c->send_idx.p, c->U1.p, c->T.p, c->VEL_X.p, c->VEL_Y.p, c->sendbuf.p);
-    TRY(halo_sendrecv(c, 7, st));
-    if (mr) LAUNCH_ON(st, K_HALO, k::halo_unpack_state, grid_for(mr, 128), 128, mr, c->recv_idx.p, c->recvbuf.p, c->U1.p, c->T.p, c->VEL_X.p, c->VEL_Y.p);
+    if (ms) LAUNCH_ON(st, K_HALO, k::halo_pack_state, grid_for(ms, 128), 128, ms, c->send_idx.p, c->U1.p, c->T.p, c->VEL_X.p, c->VEL_Y.p, c->E.p, c->P.p, c->RMACH.p, c->sendbuf.p);
+    TRY(halo_sendrecv(c, k::HALO_W, st));
+    if (mr) LAUNCH_ON(st, K_HALO, k::halo_unpack_state, grid_for(mr, 128), 128, mr, c->recv_idx.p, c->recvbuf.p, c->U1.p, c->T.p, c->VEL_X.p, c->VEL_Y.p,
+                      c->RHO.p, c->E.p, c->P.p, c->RMACH.p);
     return 0;
 }
 static int allreduce(cfdb_ctx* c, double* dev, int count, ncclRedOp_t op) {
@@ -711,18 +667,37 @@ static int allreduce(cfdb_ctx* c, double* dev, int count, ncclRedOp_t op) {
 
 // ---------------------------------------------------------------------------------------------
 // canonical reduction of nv vectors whose first-level chunk sums are in redA laid out [v][m]
+// Multi-rank: with chunk-aligned ownership (cfd_b200/partition.py) every rank places its chunk sums at their global chunk
+// positions in a zero-filled array, one ncclAllReduce(sum) assembles it (exactly one rank contributes a non-zero value per
+// entry, and x + 0 + ... + 0 = x bit for bit: chunk sums start from +0.0, so they are never -0), and every rank runs the
+// upper levels of the tree on the same numbers: the result has the bits of the single-GPU reduction.  Without the alignment
+// (owned sets not contiguous in the global numbering) the per-rank canonical sums are added by ncclAllReduce: round-off level.
 static int reduce_levels(cfdb_ctx* c, int nv, long m, int slot) {
     double* in = c->redA.p;
-    double* outb = c->redB.p;
+    double *out = c->redB.p, *spare = c->redA.p;   // outputs alternate; the level-1 sums in redA are dead once level 2 is done
+    const bool global_tree = c->nranks > 1 && c->red_aligned;
+    if (global_tree) {
+        const long M = c->red_nchunk_global;
+        CK(cudaMemsetAsync(c->redG.p, 0, (size_t)nv * M * sizeof(double), c->st));
+        for (int v = 0; v < nv; ++v)
+            CK(cudaMemcpyAsync(c->redG.p + v * M + c->red_chunk0, in + v * m, (size_t)m * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
+        NK(ncclAllReduce(c->redG.p, c->redG.p, (size_t)nv * M, ncclDouble, ncclSum, c->comm, c->st));
+        c->launches += 1;
+        in = c->redG.p;
+        out = c->redA.p;
+        spare = c->redB.p;
+        m = M;
+    }
     while (m > 1) {
         long m2 = (m + 4095) / 4096;
         for (int v = 0; v < nv; ++v)
-            LAUNCH(K_DOT, k::dot_chunks, (int)std::min<long>(m2, 1024), 256, m, in + v * m, (const double*)nullptr, outb + v * m2);
-        std::swap(in, outb);
+            LAUNCH(K_DOT, k::dot_chunks, (int)std::min<long>(m2, 1024), 256, m, in + v * m, (const double*)nullptr, out + v * m2);
+        in = out;
+        std::swap(out, spare);
         m = m2;
     }
     CK(cudaMemcpyAsync(&c->sc->red[slot], in, nv * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
-    TRY(allreduce(c, &c->sc->red[slot], nv, ncclSum));  // multi-rank: sum of the per-rank canonical sums
+    if (!global_tree) TRY(allreduce(c, &c->sc->red[slot], nv, ncclSum));  // multi-rank, not aligned: sum of the per-rank canonical sums
     return 0;
 }
 static int dev_dot(cfdb_ctx* c, long n, const double* x, const double* y, int slot) {
@@ -836,7 +811,7 @@ static int run_estab(cfdb_ctx* c, const double* dtmin_dev) {
     // branch-free estab_fast: 64 regs without spills (MINB 4) 0.617 ms, 48 regs (5) 0.676, 40 regs (6) 0.809; the plain form was 1.06
     static int minb = getenv("CFDB_ESTAB_MINB") ? atoi(getenv("CFDB_ESTAB_MINB")) : 4;
     auto kern = k::estab<3, true>;
-    if (c->ale || c->nranks > 1) {  // a rank of a multi-GPU run never assumes W = 0 from its own lists alone
+    if (c->ale || (c->nranks > 1 && !c->ale_agreed)) {  // multi-rank: once the ranks have agreed on the flag (agree_on_ale); before that no rank assumes W = 0 from its own lists alone
         if (minb == 4) kern = k::estab<4, true>;
         else if (minb == 5) kern = k::estab<5, true>;
         else if (minb == 6) kern = k::estab<6, true>;
@@ -855,88 +830,28 @@ static int run_estab(cfdb_ctx* c, const double* dtmin_dev) {
 }
 
 // calcRHS (+FUENTE when `ale`) into the staging buffers
-static int run_calcrhs_elem(cfdb_ctx* c, const k::Gas& g, bool theta, bool ale, const double* dtl_arr, const double* dtl_sc,
-                            int e0 = 0, int e1 = -1) {
+// Launch shapes from the A/B runs of round 1 (profiles/r1_experiments.md): Euler flow runs the plain divisions at 4 CTAs/SM
+// (128 registers, 16 warps/SM: 1.10 ms per launch on the 16 M-triangle mesh against 1.23 at 3 and 1.33 at 5 CTAs), viscous
+// flow the branch-free forms with the Gauss loop rolled at 3 CTAs/SM (1.96 -> 1.67 ms).
+static int run_calcrhs_elem(cfdb_ctx* c, const k::Gas& g, bool theta, bool ale, const double* dtl_arr, const double* dtl_sc) {
     const bool visc = g.mu_ref > 2.2250738585072014e-308;  // tiny(0d0), calcRHS.f90:119
-    if (e1 < 0) e1 = c->nelem;
-    if (e1 <= e0) return 0;
+    const int e0 = 0, e1 = c->nelem;
     const int B = 128, G = grid_for(e1 - e0, B);
-#define ARGS e0, e1, c->nelem, c->inp.p, (c->Usrc ? c->Usrc : c->U.p), c->UN.p, c->T.p, c->W_X.p, c->W_Y.p, c->dNx.p, c->dNy.p, c->area.p, c->SHOC.p, \
-             dtl_arr, dtl_sc, c->TS1.p, c->TS2.p, c->TS3.p, g, (c->ECcur ? c->ECcur : c->EC.p), (c->FCcur ? c->FCcur : c->FC.p)
-    // persistent cp.async-pipelined variant: whole-mesh launches on fixed meshes with theta = 0
-    static const int pipe = getenv("CFDB_CALCRHS_PIPE") ? atoi(getenv("CFDB_CALCRHS_PIPE")) : 0;
-    if (pipe && !theta && !ale && e0 == 0 && e1 == c->nelem) {
-        int nsm = 148;
-        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device);
-        const int ntiles = (c->nelem + 127) / 128;
-#define PIPE_LAUNCH(V, M)                                                                                         \
-        {                                                                                                         \
-            auto kp = k::calcrhs_pipe<V, M>;                                                                      \
-            const int smem = 2 * k::PipeLayout<V>::kStageBytes;                                                   \
-            CK(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                      \
-            int grid = std::min(ntiles, nsm * M);                                                                 \
-            cudaEvent_t _a = nullptr, _b = nullptr;                                                               \
-            TRY(prof_begin(c, c->st, K_CALCRHS, &_a, &_b));                                                       \
-            kp<<<grid, 128, smem, c->st>>>(c->nelem, c->inp.p, (c->Usrc ? c->Usrc : c->U.p), c->T.p, c->dNx.p, c->dNy.p, c->area.p,     \
-                                           c->SHOC.p, dtl_arr, dtl_sc, c->TS1.p, c->TS2.p, c->TS3.p, g,           \
-                                           (c->ECcur ? c->ECcur : c->EC.p));                                      \
-            CK(cudaGetLastError());                                                                               \
-            TRY(prof_end(c, c->st, K_CALCRHS, _a, _b));                                                           \
-        }
-        if (visc) { if (pipe == 4) PIPE_LAUNCH(true, 4) else PIPE_LAUNCH(true, 3) }
-        else { if (pipe == 4) PIPE_LAUNCH(false, 4) else PIPE_LAUNCH(false, 3) }
-#undef PIPE_LAUNCH
-        return 0;
-    }
-    int sel = (visc ? 4 : 0) | (theta ? 2 : 0) | (ale ? 1 : 0);
-    // 4 CTAs/SM (128 registers, 16 warps/SM) is the measured optimum once the nine Gauss-point divisions are issued
-    // up front: 1.11 ms per launch against 1.23 (3 CTAs), 1.33 (5), 1.88 (6) on the 16 M-triangle mesh
-    static const int minb_env = getenv("CFDB_CALCRHS_MINB") ? atoi(getenv("CFDB_CALCRHS_MINB")) : 0;
-    // branch-free division forms (kernels.cuh: calcrhs_one<.., NB>): CFDB_CALCRHS_NB=0/1 forces them off/on
-    static const int nb_env = getenv("CFDB_CALCRHS_NB") ? atoi(getenv("CFDB_CALCRHS_NB")) : -1;
-    // defaults from the A/B runs in profiles/r1_experiments.md: branch-free forms for viscous flow only (1.96 -> 1.67 ms at
-    // 3 CTAs/SM with the Gauss loop rolled), the plain form at 4 CTAs/SM for Euler flow (1.10 against 1.14)
-    const bool nb = nb_env >= 0 ? nb_env != 0 : visc;
-    const int minb = minb_env ? minb_env : ((visc && nb) ? 3 : 4);
-#define PICK(M)                                                                                                   \
-    switch (sel | (nb ? 8 : 0)) {                                                                                 \
-        case 0: kern = k::calcrhs_elem<false, false, false, M>; break;                                            \
-        case 1: kern = k::calcrhs_elem<false, false, true, M>; break;                                             \
-        case 2: kern = k::calcrhs_elem<false, true, false, M>; break;                                             \
-        case 3: kern = k::calcrhs_elem<false, true, true, M>; break;                                              \
-        case 4: kern = k::calcrhs_elem<true, false, false, M>; break;                                             \
-        case 5: kern = k::calcrhs_elem<true, false, true, M>; break;                                              \
-        case 6: kern = k::calcrhs_elem<true, true, false, M>; break;                                              \
-        case 7: kern = k::calcrhs_elem<true, true, true, M>; break;                                               \
-        case 8: kern = k::calcrhs_elem<false, false, false, M, 128, true>; break;                                 \
-        case 9: kern = k::calcrhs_elem<false, false, true, M, 128, true>; break;                                  \
-        case 10: kern = k::calcrhs_elem<false, true, false, M, 128, true>; break;                                 \
-        case 11: kern = k::calcrhs_elem<false, true, true, M, 128, true>; break;                                  \
-        case 12: kern = k::calcrhs_elem<true, false, false, M, 128, true>; break;                                 \
-        case 13: kern = k::calcrhs_elem<true, false, true, M, 128, true>; break;                                  \
-        case 14: kern = k::calcrhs_elem<true, true, false, M, 128, true>; break;                                  \
-        default: kern = k::calcrhs_elem<true, true, true, M, 128, true>; break;                                   \
-    }
     void (*kern)(int, int, int, const int*, const double*, const double*, const double*, const double*, const double*, const double*,
                  const double*, const double*, const double*, const double*, const double*, const double*, const double*,
                  const double*, k::Gas, double*, double*) = nullptr;
-    if (minb == 3) { PICK(3) } else if (minb == 5) { PICK(5) } else { PICK(4) }
-#undef PICK
-    // experiment (CFDB_CALCRHS_PAD_KB): unused dynamic shared memory caps the CTAs per SM below what the registers allow,
-    // leaving register-file room for node_update CTAs of the previous stage to be co-resident (CFDB_STAGE_OVERLAP)
-    static const int pad_kb = getenv("CFDB_CALCRHS_PAD_KB") ? atoi(getenv("CFDB_CALCRHS_PAD_KB")) : 0;
-    if (pad_kb > 0) {
-        const int smem = pad_kb * 1024;
-        CK(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        cudaEvent_t _a = nullptr, _b = nullptr;
-        TRY(prof_begin(c, c->st, K_CALCRHS, &_a, &_b));
-        kern<<<G, B, smem, c->st>>>(ARGS);
-        CK(cudaGetLastError());
-        TRY(prof_end(c, c->st, K_CALCRHS, _a, _b));
-        return 0;
+    switch ((visc ? 4 : 0) | (theta ? 2 : 0) | (ale ? 1 : 0)) {
+        case 0: kern = k::calcrhs_elem<false, false, false, 4>; break;
+        case 1: kern = k::calcrhs_elem<false, false, true, 4>; break;
+        case 2: kern = k::calcrhs_elem<false, true, false, 4>; break;
+        case 3: kern = k::calcrhs_elem<false, true, true, 4>; break;
+        case 4: kern = k::calcrhs_elem<true, false, false, 3, 128, true>; break;
+        case 5: kern = k::calcrhs_elem<true, false, true, 3, 128, true>; break;
+        case 6: kern = k::calcrhs_elem<true, true, false, 3, 128, true>; break;
+        default: kern = k::calcrhs_elem<true, true, true, 3, 128, true>; break;
     }
-    LAUNCH(K_CALCRHS, kern, G, B, ARGS);
-#undef ARGS
+    LAUNCH(K_CALCRHS, kern, G, B, e0, e1, c->nelem, c->inp.p, (c->Usrc ? c->Usrc : c->U.p), c->UN.p, c->T.p, c->W_X.p, c->W_Y.p,
+           c->dNx.p, c->dNy.p, c->area.p, c->SHOC.p, dtl_arr, dtl_sc, c->TS1.p, c->TS2.p, c->TS3.p, g, c->EC.p, c->FC.p);
     return 0;
 }
 
@@ -945,7 +860,7 @@ static int run_node(cfdb_ctx* c, cudaStream_t st, bool ale, bool update, double 
     if (n1 < 0) n1 = c->npoin;
     if (n1 <= n0) return 0;
     const int B = CFDB_NODE_BS, G = grid_for(n1 - n0, B);
-#define ARGS n0, n1, nlist, c->d_esup2.p, c->eslot.p, (c->ECcur ? c->ECcur : c->EC.p), (c->FCcur ? c->FCcur : c->FC.p), c->U.p, c->M.p, c->GAMM.p, c->W_X.p, c->W_Y.p, \
+#define ARGS n0, n1, nlist, c->d_esup2.p, c->eslot.p, c->EC.p, c->FC.p, c->U.p, c->M.p, c->GAMM.p, c->W_X.p, c->W_Y.p, \
              c->bcflag.p, bctab(c), rk_fact, c->par.FR, c->U1.p, c->RHS.p, c->RHO.p, c->VEL_X.p, c->VEL_Y.p, c->E.p, \
              c->P.p, c->T.p, c->RMACH.p
     auto kern = k::node_update<false, true>;
@@ -954,30 +869,6 @@ static int run_node(cfdb_ctx* c, cudaStream_t st, bool ale, bool update, double 
     else if (!update) kern = k::node_update<false, false>;
     LAUNCH_ON(st, K_NODE, kern, G, B, ARGS);
 #undef ARGS
-    return 0;
-}
-
-// tile-fused stage: element contributions -> shared memory -> interior nodes updated in the same kernel; the
-// tile-boundary nodes (about a quarter) go through the staging buffer and node_update over a node list
-static int run_stage_tile(cfdb_ctx* c, const k::Gas& g, const double* dtl_arr, const double* dtl_sc, double rk_fact) {
-    const bool visc = g.mu_ref > 2.2250738585072014e-308;
-    const int smem = 12 * 512 * (int)sizeof(double);
-    auto kern = visc ? k::stage_tile<true, 3> : k::stage_tile<false, 4>;   // Euler: 128 registers, four CTAs (4 x 48 KB) per SM
-    static bool attr_done[2] = {false, false};
-    if (!attr_done[visc]) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_done[visc] = true;
-    }
-    cudaEvent_t _a = nullptr, _b = nullptr;
-    TRY(prof_begin(c, c->st, K_CALCRHS, &_a, &_b));
-    kern<<<c->ntiles, 128, smem, c->st>>>(c->ntiles, c->nelem, c->tile_elems.p, c->ebmask.p, c->tnode_ptr.p, c->tnodes.p,
-                                         c->d_esup2.p, c->tslot.p, c->inp.p, c->U.p, c->T.p, c->dNx.p, c->dNy.p, c->area.p,
-                                         c->SHOC.p, dtl_arr, dtl_sc, c->TS1.p, c->TS2.p, c->TS3.p, g, c->EC.p, c->U.p, c->M.p,
-                                         c->GAMM.p, c->W_X.p, c->W_Y.p, c->bcflag.p, bctab(c), rk_fact, c->par.FR, c->U1.p,
-                                         c->RHS.p, c->RHO.p, c->VEL_X.p, c->VEL_Y.p, c->E.p, c->P.p, c->T.p, c->RMACH.p);
-    CK(cudaGetLastError());
-    TRY(prof_end(c, c->st, K_CALCRHS, _a, _b));
-    TRY(run_node(c, c->st, false, true, rk_fact, 0, c->nbnodes, c->bnodes.p));
     return 0;
 }
 
@@ -1008,7 +899,6 @@ extern "C" int cfdb_rk_stage(cfdb_ctx* c, int32_t irk) {
     struct UsrcReset { cfdb_ctx* c; ~UsrcReset() { c->Usrc = nullptr; } } usrc_reset{c};
     k::Gas g{p.FCv, p.FK, p.FMU, p.GAMA, p.T_inf, p.CTE};
     const double* dtl_arr = p.ITLOCAL != 0 ? c->DTL.p : nullptr;
-    const int nch = (int)c->chunk_ev.size();
     if (c->fast == 2 && !c->ale && !c->use_cuarto && !c->true_rk) {
         // measurement only: the staged element kernel compiled with FMA contraction + the exact ordered node kernel
         const bool visc = g.mu_ref > 2.2250738585072014e-308;
@@ -1045,95 +935,30 @@ extern "C" int cfdb_rk_stage(cfdb_ctx* c, int32_t irk) {
         TRY(halo_state(c));
         return 0;
     }
-    if (c->tile_ok && !c->ale && !c->use_cuarto && !c->true_rk && nch <= 1) {
-        TRY(run_stage_tile(c, g, dtl_arr, &c->sc->DTMIN, RK_FACT));
-        TRY(halo_state(c));
-        return 0;
-    }
-    if (nch <= 1) {
-        TRY(run_calcrhs_elem(c, g, c->use_cuarto != 0, c->ale, dtl_arr, &c->sc->DTMIN));
-        TRY(run_node(c, c->st, c->ale, true, RK_FACT));
-        TRY(halo_state(c));
-        return 0;
-    }
-    // software pipeline: the (memory-bound) node kernel of chunk k runs on st2 while the (fp64-bound) element
-    // kernel of chunk k+1 runs on st; st2 joins st at the end of the stage
-    static const bool seq = getenv("CFDB_CHUNK_SEQ") != nullptr;  // same stream: L2-blocking only, no overlap
-    if (seq) {
-        for (int kc = 0; kc < nch; ++kc) {
-            TRY(run_calcrhs_elem(c, g, false, c->ale, dtl_arr, &c->sc->DTMIN, c->chunk_e[kc], c->chunk_e[kc + 1]));
-            TRY(run_node(c, c->st, c->ale, true, RK_FACT, c->chunk_n[kc], c->chunk_n[kc + 1]));
-        }
-        TRY(halo_state(c));
-        return 0;
-    }
-    for (int kc = 0; kc < nch; ++kc) {
-        TRY(run_calcrhs_elem(c, g, false, c->ale, dtl_arr, &c->sc->DTMIN, c->chunk_e[kc], c->chunk_e[kc + 1]));
-        if (c->chunk_n[kc + 1] > c->chunk_n[kc]) {
-            CK(cudaEventRecord(c->chunk_ev[kc], c->st));
-            CK(cudaStreamWaitEvent(c->st2, c->chunk_ev[kc], 0));
-            TRY(run_node(c, c->st2, c->ale, true, RK_FACT, c->chunk_n[kc], c->chunk_n[kc + 1]));
-        }
-    }
-    CK(cudaEventRecord(c->ev_join, c->st2));
-    CK(cudaStreamWaitEvent(c->st, c->ev_join, 0));
+    TRY(run_calcrhs_elem(c, g, c->use_cuarto != 0, c->ale, dtl_arr, &c->sc->DTMIN));
+    TRY(run_node(c, c->st, c->ale, true, RK_FACT));
     TRY(halo_state(c));
     return 0;
 }
 
-// RK (subrutinas.f90:645-849) inside the time loop.  When calcRHS does not read anything the nodal chain writes
-// (Euler: mu_ref <= tiny, so T is not read; U, dtl, SHOC, T_SUGN are step constants), node_update(k) on st2
-// overlaps calcrhs_elem(k+1) on st: the memory-bound node kernel hides behind the fp64-bound element kernel.
-// Needs the staging buffers double-buffered.  Same kernels, same order of arithmetic: results are unchanged.
+// RK (subrutinas.f90:645-849) inside the time loop
 static int run_rk(cfdb_ctx* c) {
-    const cfdb_params& p = c->par;
-    // measured on B200 (16 M triangles): 9.30 ms/step with the overlap, 9.32 without — the two kernels compete for
-    // the same SM residency — so it is opt-in (CFDB_STAGE_OVERLAP=1)
-    static const bool no_ovl = getenv("CFDB_STAGE_OVERLAP") == nullptr;
-    const bool visc = p.FMU > 2.2250738585072014e-308;
-    if (visc || no_ovl || c->chunk_ev.size() > 1 || c->use_cuarto || c->true_rk || c->fast) {
-        for (int irk = 1; irk <= 4; ++irk) TRY(cfdb_rk_stage(c, irk));
-        return 0;
-    }
-    const size_t E = c->nelem;
-    TRY(c->EC2.alloc(12 * E));
-    if (c->ale) TRY(c->FC2.alloc(12 * E));
-    if (c->theta_nonzero) {
-        CK(cudaMemsetAsync(c->UN.p, 0, 4 * (size_t)c->npoin * sizeof(double), c->st));
-        c->theta_nonzero = false;
-    }
-    TRY(run_estab(c, &c->sc->DTMIN));
-    c->u1_is_u = false;
-    k::Gas g{p.FCv, p.FK, p.FMU, p.GAMA, p.T_inf, p.CTE};
-    const double* dtl_arr = p.ITLOCAL != 0 ? c->DTL.p : nullptr;
-    int rc = 0;
-    for (int irk = 1; irk <= 4 && !rc; ++irk) {
-        const int b = (irk - 1) & 1;
-        c->ECcur = b ? c->EC2.p : c->EC.p;
-        c->FCcur = c->ale ? (b ? c->FC2.p : c->FC.p) : nullptr;
-        if (irk >= 3) CK(cudaStreamWaitEvent(c->st, c->ev_node[irk - 3], 0));  // node(irk-2) has consumed this buffer
-        rc = run_calcrhs_elem(c, g, false, c->ale, dtl_arr, &c->sc->DTMIN);
-        if (rc) break;
-        CK(cudaEventRecord(c->ev_elem[irk - 1], c->st));
-        CK(cudaStreamWaitEvent(c->st2, c->ev_elem[irk - 1], 0));
-        rc = run_node(c, c->st2, c->ale, true, 1.0 / (4 + 1 - irk));
-        if (!rc) rc = halo_state(c, c->st2);
-        CK(cudaEventRecord(c->ev_node[irk - 1], c->st2));
-    }
-    c->ECcur = nullptr;
-    c->FCcur = nullptr;
-    if (rc) return rc;
-    CK(cudaStreamWaitEvent(c->st, c->ev_node[3], 0));
+    for (int irk = 1; irk <= 4; ++irk) TRY(cfdb_rk_stage(c, irk));
     return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
-// biCG on device arrays (biconjGrad.f90:8-62); host loop control reads err back once per iteration
+// biCG on device arrays (biconjGrad.f90:8-62).  The early return (:35), the loop condition (:47) and every scalar of the
+// algorithm live on the device; the host only enqueues.  The prologue (:37-45) is enqueued unconditionally -- if r.r < tol
+// its results are work-array garbage that nothing applies -- and the iterations follow in batches of 1, 2, 4, 8, 16, 16, ...
+// each closed by a flush of the pending x update and ONE read-back of the loop state (most mesh solves need a handful of
+// iterations because the tolerance is absolute).  static_zero: the caller knows that x, x_fix and b are all zero (a fixed
+// mesh: r.r = 0 < tol, the reference returns at :35 after its SpMV and inner product): nothing after r.r is enqueued and
+// nothing is read back.
 static int bicg_dev(cfdb_ctx* c, const double* A, const int* idx, const int* rowptr, const double* diag, double* x,
                     const double* b, const double* x_fix, const int* fixIdx, const int* fixLast, int npoin, int nfix,
-                    int* iters, double* y_pre = nullptr) {
+                    int* iters, double* y_pre = nullptr, bool static_zero = false) {
     const int B = 256, G = grid_for(npoin, B), GF = grid_for(std::max(nfix, 1), 128);
-    const double tol = 1.e-10;
     // y_pre: x already carries its Dirichlet values and y_pre = A*x (fluid_structure computes both solves' first
     // products in one pass over the matrix); it then serves as this solve's y work array
     double *y = y_pre ? y_pre : c->by.p, *p = c->bp.p, *r = c->br.p, *z = c->bz.p;
@@ -1148,8 +973,7 @@ static int bicg_dev(cfdb_ctx* c, const double* A, const int* idx, const int* row
     if (nfix) LAUNCH(K_FIXROWS, k::assign2, GF, 128, nfix, fixIdx, 0.0, r);
     TRY(dev_dot(c, nred, r, r, 0));
     LAUNCH(K_SCALAR, k::bicg_scalar, 1, 1, c->sc, (int)k::SC_RR, 0);
-    TRY(read_scal(c));
-    if (c->h_sc->rr < tol) { *iters = -1; return halo_vec(c, x, 1); }
+    if (static_zero) { *iters = -1; return 0; }   // :35 is known to return; the ghosts of x (all zero) need no refresh
     LAUNCH(K_VEC, k::vecdiv, G, B, npoin, r, diag, p);
     TRY(dev_dot(c, nred, r, p, 0));
     LAUNCH(K_SCALAR, k::bicg_scalar, 1, 1, c->sc, (int)k::SC_ERRNEW, 0);
@@ -1158,60 +982,33 @@ static int bicg_dev(cfdb_ctx* c, const double* A, const int* idx, const int* row
     if (nfix) LAUNCH(K_FIXROWS, k::copy2, GF, 128, nfix, fixIdx, 1.e30, p, y);
     TRY(dev_dot(c, nred, p, y, 1));
     LAUNCH(K_SCALAR, k::bicg_scalar, 1, 1, c->sc, (int)k::SC_PY_ALFA, 1);
-    LAUNCH(K_VEC, k::vecsum, G, B, npoin, (int)k::ALFA_POS, 0.0, c->sc, p, x, x);
-    // while loop (:47-61): fused iterations, enqueued in batches; the loop condition lives on the device
-    static const bool unfused = getenv("CFDB_BICG_UNFUSED") != nullptr;
-    int kk = 0;
-    if (!unfused) {
-        TRY(c->isfix.alloc((size_t)c->npoin > (size_t)npoin ? c->npoin : npoin));
-        CK(cudaMemsetAsync(c->isfix.p, 0, npoin, c->st));
-        if (nfix) LAUNCH(K_FIXROWS, k::mark_fixed, GF, 128, nfix, fixIdx, c->isfix.p);
-        LAUNCH(K_SCALAR, k::bicg_fused_scalar, 1, 1, c->sc, (int)k::SCF_START, 0);
-        const long nch = ((long)npoin + 4095) / 4096, mred = ((long)nred + 4095) / 4096;
-        const int GB = (int)std::min<long>(nch, 148 * 8);
-        double* pa = p;         // current p
-        double* pb = c->bp2.p;  // next p
-        int batch = 1;  // 1, 2, 4, 8, 16, 16, ...: most mesh solves need a handful of iterations (absolute tolerance)
-        for (int done = 0; done < 1000; batch = std::min(2 * batch, 16)) {
-            for (int it = 0; it < batch; ++it, ++done) {
-                LAUNCH(K_VEC, k::bicg_k1, GB, 256, npoin, nred, c->sc, y, diag, pa, x, r, z, c->redA.p);
-                TRY(reduce_levels(c, 1, mred, 0));
-                LAUNCH(K_SCALAR, k::bicg_fused_scalar, 1, 1, c->sc, (int)k::SCF_BETA, 0);
-                TRY(halo_vec(c, z, 1));
-                LAUNCH(K_SPMV, k::bicg_k2, GB, 256, npoin, nred, c->sc, A, idx, rowptr, c->isfix.p, pa, z, pb, y, c->redA.p);
-                TRY(reduce_levels(c, 1, mred, 1));
-                LAUNCH(K_SCALAR, k::bicg_fused_scalar, 1, 1, c->sc, (int)k::SCF_ALFA, 1);
-                std::swap(pa, pb);
-            }
-            TRY(read_scal(c));
-            if (!c->h_sc->bicg_state) break;
+    // while loop (:47-61): fused iterations; x = alfa*p + x (:44, :59) is applied by the next bicg_k1 or by bicg_flush
+    TRY(c->isfix.alloc((size_t)c->npoin > (size_t)npoin ? c->npoin : npoin));
+    CK(cudaMemsetAsync(c->isfix.p, 0, npoin, c->st));
+    if (nfix) LAUNCH(K_FIXROWS, k::mark_fixed, GF, 128, nfix, fixIdx, c->isfix.p);
+    LAUNCH(K_SCALAR, k::bicg_fused_scalar, 1, 1, c->sc, (int)k::SCF_START, 0);
+    const long nch = ((long)npoin + 4095) / 4096, mred = ((long)nred + 4095) / 4096;
+    const int GB = (int)std::min<long>(nch, 148 * 8);
+    double* pa = p;         // current p
+    double* pb = c->bp2.p;  // next p
+    // the first read-back follows the prologue alone: most steps of a slowly moving mesh end there
+    for (int done = 0, batch = 0; done <= 1000; batch = batch ? std::min(2 * batch, 16) : 1) {
+        for (int it = 0; it < batch; ++it, ++done) {
+            LAUNCH(K_VEC, k::bicg_k1, GB, 256, npoin, nred, c->sc, y, diag, pa, x, r, z, c->redA.p);
+            TRY(reduce_levels(c, 1, mred, 0));
+            LAUNCH(K_SCALAR, k::bicg_fused_scalar, 1, 1, c->sc, (int)k::SCF_BETA, 0);
+            TRY(halo_vec(c, z, 1));
+            LAUNCH(K_SPMV, k::bicg_k2, GB, 256, npoin, nred, c->sc, A, idx, rowptr, c->isfix.p, pa, z, pb, y, c->redA.p);
+            TRY(reduce_levels(c, 1, mred, 1));
+            LAUNCH(K_SCALAR, k::bicg_fused_scalar, 1, 1, c->sc, (int)k::SCF_ALFA, 1);
+            std::swap(pa, pb);
         }
-        // the last x = alfa*p + x may still be pending: one more k1 applies it (no-op otherwise)
-        LAUNCH(K_VEC, k::bicg_k1, GB, 256, npoin, nred, c->sc, y, diag, pa, x, r, z, c->redA.p);
-        LAUNCH(K_SCALAR, k::bicg_fused_scalar, 1, 1, c->sc, (int)k::SCF_FLUSHED, 0);
+        LAUNCH(K_VEC, k::bicg_flush, GB, 256, npoin, c->sc, pa, x);
+        LAUNCH(K_SCALAR, k::bicg_flushed, 1, 1, c->sc);
         TRY(read_scal(c));
-        kk = c->h_sc->bicg_k;
-    } else {
-    TRY(read_scal(c));
-    double err_old = c->h_sc->err_old;
-    while (std::fabs(err_old) > tol && kk < 1000) {
-        kk++;
-        LAUNCH(K_VEC, k::vecsum, G, B, npoin, (int)k::ALFA_NEG, 0.0, c->sc, y, r, r);
-        LAUNCH(K_VEC, k::vecdiv, G, B, npoin, r, diag, z);
-        TRY(dev_dot(c, nred, r, z, 0));
-        LAUNCH(K_SCALAR, k::bicg_scalar, 1, 1, c->sc, (int)k::SC_BETA, 0);
-        LAUNCH(K_VEC, k::vecsum, G, B, npoin, (int)k::BETA_POS, 0.0, c->sc, p, z, p);
-        TRY(halo_vec(c, p, 1));
-        LAUNCH(K_SPMV, k::spmv, G, B, npoin, A, idx, rowptr, p, y);
-        if (nfix) LAUNCH(K_FIXROWS, k::copy2, GF, 128, nfix, fixIdx, 1.e30, p, y);
-        TRY(dev_dot(c, nred, p, y, 1));
-        LAUNCH(K_SCALAR, k::bicg_scalar, 1, 1, c->sc, (int)k::SC_PY_ALFA, 1);
-        LAUNCH(K_VEC, k::vecsum, G, B, npoin, (int)k::ALFA_POS, 0.0, c->sc, p, x, x);
-        TRY(read_scal(c));
-        err_old = c->h_sc->err_old;
+        if (!c->h_sc->bicg_state) break;
     }
-    }
-    *iters = kk;
+    *iters = c->h_sc->rr < 1.e-10 ? -1 : c->h_sc->bicg_k;
     TRY(halo_vec(c, x, 1));  // ghosts of the solution (the caller moves ghost nodes with it)
     return 0;
 }
@@ -1225,7 +1022,7 @@ extern "C" int cfdb_fluid_structure(cfdb_ctx* c, double dtmin, double time) {
         CK(cudaMemsetAsync(c->dypos.p, 0, P * sizeof(double), c->st));
     }
     // XREF(2)=1.4, YREF(2)=0 are overwritten on every call (meshMove.f90:58): applied once in cfdb_create
-    if (c->nset || c->nranks > 1) {  // every rank joins the all-reduce, with or without body edges of its own
+    if (c->nset || (c->nranks > 1 && c->ale)) {  // every rank of a moving-mesh run joins the all-reduce, with or without body edges of its own
         CK(cudaMemsetAsync(c->sc->FX, 0, 30 * sizeof(double), c->st));
         if (c->nset) LAUNCH(K_FORCES, k::forces, 1, 32, c->nset, c->n_owned, c->set_ptr.p, c->set_n1.p, c->set_n2.p, c->X.p, c->Y.p, c->P.p,
                c->xref.p, c->yref.p, c->sc);
@@ -1241,31 +1038,30 @@ extern "C" int cfdb_fluid_structure(cfdb_ctx* c, double dtmin, double time) {
                std::sin(ALPHA), YPOSR, c->xref.p, c->yref.p, c->X.p, c->Y.p, c->dxpos.p, c->dypos.p);
     // The two solves (meshMove.f90:97, :119) are independent until their results are applied: the y-solve's Dirichlet
     // values, warm start and first product A*ypos do not depend on the x-solve.  Both first products are therefore taken
-    // in ONE pass over the matrix (k::spmv2: same row-sequential sums, 12 B/nnz read once instead of twice);
-    // CFDB_BICG_NOPRE=1 keeps the two separate passes.
-    static const bool nopre = getenv("CFDB_BICG_NOPRE") != nullptr;
-    if (!nopre) {
-        const int GF = grid_for(std::max(c->nnmove, 1), 128);
-        if (c->nnmove) {
-            LAUNCH(K_MOVE, k::pos_aux_fill, GF, 128, c->nmove, c->nnmove, c->ilaux.p, c->dxpos.p, c->pos_aux.p);
-            LAUNCH(K_MOVE, k::pos_aux_fill, GF, 128, c->nmove, c->nnmove, c->ilaux.p, c->dypos.p, c->pos_aux2.p);
-            LAUNCH(K_FIXROWS, k::copy1, GF, 128, c->nnmove, c->ilaux.p, c->ilaux_last.p, 1.0, c->pos_aux.p, c->xpos.p);
-            LAUNCH(K_FIXROWS, k::copy1, GF, 128, c->nnmove, c->ilaux.p, c->ilaux_last.p, 1.0, c->pos_aux2.p, c->ypos.p);
-        }
+    // in ONE pass over the matrix (k::spmv2: same row-sequential sums, 12 B/nnz read once instead of twice).
+    // Fixed mesh (no body sets on any rank, xpos/ypos/W never set by the caller): DXPOS = 0, the warm start is 0, so both
+    // solves return at biconjGrad.f90:35 -- the host knows it and neither enqueues the rest of biCG nor reads anything back;
+    // what the reference executes on that path (Dirichlet rows, SpMV, residual, r.r, the move with XPOS = 0) still runs.
+    const bool static_zero = !c->ale;
+    const int GF = grid_for(std::max(c->nnmove, 1), 128);
+    if (c->nnmove) {
+        LAUNCH(K_MOVE, k::pos_aux_fill, GF, 128, c->nmove, c->nnmove, c->ilaux.p, c->dxpos.p, c->pos_aux.p);
+        LAUNCH(K_MOVE, k::pos_aux_fill, GF, 128, c->nmove, c->nnmove, c->ilaux.p, c->dypos.p, c->pos_aux2.p);
+        LAUNCH(K_FIXROWS, k::copy1, GF, 128, c->nnmove, c->ilaux.p, c->ilaux_last.p, 1.0, c->pos_aux.p, c->xpos.p);
+        LAUNCH(K_FIXROWS, k::copy1, GF, 128, c->nnmove, c->ilaux.p, c->ilaux_last.p, 1.0, c->pos_aux2.p, c->ypos.p);
+    }
+    if (!static_zero) {
         TRY(halo_vec(c, c->xpos.p, 1));
         TRY(halo_vec(c, c->ypos.p, 1));
-        LAUNCH(K_SPMV, k::spmv2, grid_for(P, 256), 256, P, c->lap_sparse.p, c->d_lap_idx.p, c->d_lap_rowptr.p, c->xpos.p, c->ypos.p,
-               c->by.p, c->by2.p);
     }
+    LAUNCH(K_SPMV, k::spmv2, grid_for(P, 256), 256, P, c->lap_sparse.p, c->d_lap_idx.p, c->d_lap_rowptr.p, c->xpos.p, c->ypos.p,
+           c->by.p, c->by2.p);
     for (int dir = 0; dir < 2; ++dir) {
-        double* dpos = dir ? c->dypos.p : c->dxpos.p;
         double* pos = dir ? c->ypos.p : c->xpos.p;
-        double* paux = (!nopre && dir) ? c->pos_aux2.p : c->pos_aux.p;
-        if (nopre && c->nnmove)
-            LAUNCH(K_MOVE, k::pos_aux_fill, grid_for(c->nnmove, 128), 128, c->nmove, c->nnmove, c->ilaux.p, dpos, c->pos_aux.p);
+        double* paux = dir ? c->pos_aux2.p : c->pos_aux.p;
         // B = 0 (meshMove.f90:91-95, :113-117): bb is zeroed at create and never written by anything else
         TRY(bicg_dev(c, c->lap_sparse.p, c->d_lap_idx.p, c->d_lap_rowptr.p, c->lap_diag.p, pos, c->bb.p, paux,
-                     c->ilaux.p, c->ilaux_last.p, P, c->nnmove, &c->bicg_iters[dir], nopre ? nullptr : (dir ? c->by2.p : c->by.p)));
+                     c->ilaux.p, c->ilaux_last.p, P, c->nnmove, &c->bicg_iters[dir], dir ? c->by2.p : c->by.p, static_zero));
         LAUNCH(K_MOVE, k::move_apply, grid_for(P, 256), 256, P, pos, &c->sc->DTMIN, dir ? c->Y.p : c->X.p,
                dir ? c->Y1.p : c->X1.p, dir ? c->W_Y.p : c->W_X.p);
     }
@@ -1390,15 +1186,28 @@ extern "C" int cfdb_step_norms(cfdb_ctx* c, double er[4], double err[4]) {
     return 0;
 }
 
-// one pass of ns2DComp.ALE.f90:138-282
-static int step_once(cfdb_ctx* c) {
+// Multi-rank: whether the mesh can move is a GLOBAL fact (the body sets usually sit on one rank, the mesh solve moves every
+// rank's nodes).  The ranks agree on it once, before the first step: after that `ale` is the same everywhere, and a
+// fixed-mesh multi-GPU run uses the same W = 0 kernels as a single-GPU one.
+static int agree_on_ale(cfdb_ctx* c) {
+    if (c->nranks <= 1 || c->ale_agreed) return 0;
+    LAUNCH(K_SCALAR, k::set_double, 1, 1, &c->sc->red[14], c->ale ? 1.0 : 0.0);
+    TRY(allreduce(c, &c->sc->red[14], 1, ncclMax));
+    TRY(read_scal(c));
+    if (c->h_sc->red[14] != 0.0 && !c->ale) { c->ale = true; TRY(zero(c, c->FC, 12 * (size_t)c->nelem)); }
+    c->ale_agreed = true;
+    c->epoch++;
+    return 0;
+}
+
+// everything one pass of ns2DComp.ALE.f90:138-282 enqueues, except the print-step work and the U = U1 pointer swap
+static int step_body(cfdb_ctx* c) {
     const cfdb_params& p = c->par;
     const int E = c->nelem;
     const size_t P = c->npoin;
-    c->h_iter += 1;
     LAUNCH(K_DTLOGIC, k::step_begin, 1, 1, c->sc);
     {
-        const bool moving = c->ale || c->nranks > 1;  // as in run_estab
+        const bool moving = c->ale;  // as in run_estab
         auto kdt = p.ITLOCAL != 0 ? (moving ? k::deltat<true, true> : k::deltat<true, false>)
                                   : (moving ? k::deltat<false, true> : k::deltat<false, false>);
         LAUNCH(K_DELTAT, kdt, grid_for(E, 256), 256, E, c->inp.p, c->area.p, c->T.p, c->VEL_X.p, c->VEL_Y.p,
@@ -1424,6 +1233,54 @@ static int step_once(cfdb_ctx* c) {
         time = c->h_sc->TIME;
     }
     TRY(cfdb_fluid_structure(c, dtmin, time));
+    return 0;
+}
+
+// A fixed-mesh step enqueues ~35 small-to-large launches and never needs the host (no body sets: no TIME read-back, the
+// mesh solve is known to return early; uniform time step: no host-computed blend factor).  It is captured ONCE per state
+// buffer parity (U and U1 swap roles every step) into a CUDA graph and replayed: one launch per step instead of ~35, which
+// removes the launch gaps between the kernels (0.5 ms of an 8.2 ms step in round 1).  NCCL's ghost refresh and all-reduces
+// are captured with it.  CFDB_NO_GRAPH=1 keeps stream launches (tests compare the two).
+static bool graph_eligible(const cfdb_ctx* c) {
+    static const bool off = getenv("CFDB_NO_GRAPH") != nullptr;
+    const cfdb_params& p = c->par;
+    return !off && !c->prof && !c->ale && c->nse == 0 && p.ITLOCAL == 0 && p.MOVING != 1 && !c->theta_nonzero && !c->use_cuarto;
+}
+static int step_graph(cfdb_ctx* c) {
+    int par = -1;
+    for (int i = 0; i < 2; ++i)
+        if (c->gexec[i] && c->gepoch[i] == c->epoch && c->gU[i] == c->U.p) par = i;
+    if (par < 0) {
+        par = (c->gexec[0] && c->gepoch[0] == c->epoch) ? 1 : 0;
+        if (c->gexec[par]) { cudaGraphExecDestroy(c->gexec[par]); c->gexec[par] = nullptr; }
+        const int64_t l0 = c->launches;
+        CK(cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal));
+        int rc = step_body(c);
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamEndCapture(c->st, &g);
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        if (e != cudaSuccess) return fail(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&c->gexec[par], g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return fail(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+        c->glaunches[par] = c->launches - l0;
+        c->launches = l0;
+        c->gepoch[par] = c->epoch;
+        c->gU[par] = c->U.p;
+    }
+    CK(cudaGraphLaunch(c->gexec[par], c->st));
+    c->launches += c->glaunches[par];
+    c->graph_replays++;
+    return 0;
+}
+
+// one pass of ns2DComp.ALE.f90:138-282
+static int step_once(cfdb_ctx* c) {
+    const cfdb_params& p = c->par;
+    TRY(agree_on_ale(c));
+    c->h_iter += 1;
+    if (graph_eligible(c)) TRY(step_graph(c));
+    else TRY(step_body(c));
     c->iterprint += 1;
     if (c->iterprint == p.IPRINT || c->h_iter == p.MAXITER) {  // :186-197
         TRY(run_norms(c));
@@ -1435,7 +1292,6 @@ static int step_once(cfdb_ctx* c) {
     // U = U1 (:277-281): swap the buffers instead of copying
     std::swap(c->U.p, c->U1.p);
     c->u1_is_u = true;
-    (void)P;
     return 0;
 }
 
@@ -1461,13 +1317,14 @@ extern "C" int cfdb_set_option(cfdb_ctx* c, const char* name, int32_t value) {
         if (value && !c->ale) { c->ale = true; TRY(zero(c, c->FC, 12 * (size_t)c->nelem)); }
     }
     else return fail("cfdb_set_option: unknown option " + n);
-    if (c->chunk_ev.size() > 1 && (c->use_cuarto || c->true_rk)) return fail("cfdb_set_option: not available with CFDB_CHUNK");
+    c->epoch++;
     return 0;
 }
 extern "C" void* cfdb_stream(cfdb_ctx* c) { return (void*)c->st; }
 extern "C" int cfdb_profile_enable(cfdb_ctx* c, int32_t on) {
     TRY(prof_resolve(c));
     c->prof = on != 0;
+    c->epoch++;
     if (on) {
         for (int i = 0; i < K_COUNT; ++i) { c->prof_ms[i] = 0; c->prof_n[i] = 0; }
     }
@@ -1612,15 +1469,15 @@ extern "C" int cfdb_set(cfdb_ctx* c, const char* name, const void* host, int64_t
     if (f.kind == 0) {
         if (f.count) CK(cudaMemcpyAsync(f.dev, host, f.count * sizeof(double), cudaMemcpyHostToDevice, c->st));
         CK(cudaStreamSynchronize(c->st));
-        if (n == "UN") c->theta_nonzero = true;
+        if (n == "UN") { c->theta_nonzero = true; c->epoch++; }
         if (n == "U" && c->u1_is_u) {  // keep U1 == U as in the reference
             CK(cudaMemcpyAsync(c->U1.p, c->U.p, f.count * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
             CK(cudaStreamSynchronize(c->st));
         }
         // anything that can make the mesh velocity non-zero on a context without body sets: from here on the context
         // computes FUENTE and the mesh-velocity terms of ESTAB/deltat
-        if (n == "W_X" || n == "W_Y" || n == "xpos" || n == "ypos" || n == "dxpos" || n == "dypos") {
-            if (!c->ale) { c->ale = true; TRY(zero(c, c->FC, 12 * (size_t)c->nelem)); }
+        if (n == "W_X" || n == "W_Y" || n == "xpos" || n == "ypos") {
+            if (!c->ale) { c->ale = true; c->epoch++; TRY(zero(c, c->FC, 12 * (size_t)c->nelem)); }
         }
         return 0;
     }
@@ -1649,7 +1506,6 @@ extern "C" int cfdb_get_scalar(cfdb_ctx* c, const char* name, double* v) {
     else if (n == "FX1") *v = s.FX[0];
     else if (n == "FY1") *v = s.FY[0];
     else if (n == "RM1") *v = s.RM[0];
-    else if (n == "tile_interior") *v = c->tile_ok ? c->tile_interior : 0.0;
     else if (n == "n_m") {
         vector<int> wv(c->nwn);
         if (c->nwn) CK(cudaMemcpy(wv.data(), c->wn_valid.p, c->nwn * sizeof(int), cudaMemcpyDeviceToHost));
@@ -1727,6 +1583,7 @@ extern "C" int cfdb_calcrhs(cfdb_ctx* c, double* rhs, const double* U, const dou
     TRY(up_plain(c, c->TS2.p, ts2, E));
     TRY(up_plain(c, c->TS3.p, ts3, E));
     c->theta_nonzero = true;
+    c->epoch++;
     k::Gas g{Cv, lambda_ref, mu_ref, gamma0, T_inf, cte};
     TRY(run_calcrhs_elem(c, g, true, false, c->DTL.p, nullptr));
     // rhs is inout: the reference adds onto the caller's array in element order, (((rhs+a1)+a2)+...)
@@ -1745,6 +1602,8 @@ extern "C" int cfdb_fuente(cfdb_ctx* c, double* rhs, const double* U, const doub
     (void)inpoel;
     const size_t P = npoin, E = nelem;
     TRY(c->FC.alloc(12 * E));
+    c->ale = true;   // the caller's W replaces the resident one: a later cfdb_step must not assume W = 0
+    c->epoch++;
     TRY(up_soa3(c, c->dNx.p, dNx));
     TRY(up_soa3(c, c->dNy.p, dNy));
     TRY(up_plain(c, c->U.p, U, 4 * P));
@@ -1776,6 +1635,7 @@ extern "C" int cfdb_deltat(cfdb_ctx* c, double* dtmin, double* dt, const int32_t
     TRY(up_plain(c, c->VEL_Y.p, vel_y, P));
     TRY(up_plain(c, c->W_X.p, w_x, P));
     TRY(up_plain(c, c->W_Y.p, w_y, P));
+    if (!c->ale) { c->ale = true; c->epoch++; TRY(zero(c, c->FC, 12 * E)); }   // caller's W is resident now (see cfdb_fuente)
     LAUNCH(K_SCALAR, k::set_double, 1, 1, &c->sc->dtmin_acc, 1.e20);
     LAUNCH(K_DELTAT, k::deltat<true>, grid_for(nelem, 256), 256, nelem, c->inp.p, c->area.p, c->T.p, c->VEL_X.p,
            c->VEL_Y.p, c->W_X.p, c->W_Y.p, FSAFE, T_inf, c->DT.p, c->sc);
@@ -1803,6 +1663,7 @@ extern "C" int cfdb_estab(cfdb_ctx* c, const double* U, const double* T, const d
     TRY(up_plain(c, c->W_X.p, w_x, P));
     TRY(up_plain(c, c->W_Y.p, w_y, P));
     TRY(up_plain(c, c->GAMM.p, GAMM, P));
+    if (!c->ale) { c->ale = true; c->epoch++; TRY(zero(c, c->FC, 12 * E)); }   // caller's W is resident now (see cfdb_fuente)
     LAUNCH(K_SCALAR, k::set_double, 1, 1, &c->sc->red[15], DTMIN);
     LAUNCH(K_ESTAB, k::estab<3>, grid_for(nelem, 256), 256, nelem, c->inp.p, c->U.p, c->T.p, c->VEL_X.p, c->VEL_Y.p, c->W_X.p,
            c->W_Y.p, c->GAMM.p, c->dNx.p, c->dNy.p, FR, &c->sc->red[15], RHOINF, TINF, c->SHOC.p, c->TS1.p, c->TS2.p,

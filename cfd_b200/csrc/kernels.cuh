@@ -50,6 +50,38 @@ __device__ __forceinline__ void st4(double* p, const double v[4]) {
     q[1] = make_double2(v[2], v[3]);
 }
 
+// exact global minimum of one value per thread (NaN never wins a '<'): warp shuffles, one shared-memory slot per warp,
+// one compare-and-swap per CTA and only when the CTA's minimum beats the current one.  min is order-independent, so this
+// is bit-identical to any other reduction order (the reference's minval / sequential loop).
+template <int BS>
+__device__ __forceinline__ void block_min_to_global(double v, double* target) {
+    __shared__ double wmin[BS / 32];
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        double o = __shfl_down_sync(0xffffffffu, v, s);
+        if (o < v) v = o;
+    }
+    if ((threadIdx.x & 31) == 0) wmin[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = threadIdx.x < BS / 32 ? wmin[threadIdx.x] : CUDART_INF;
+#pragma unroll
+        for (int s = BS / 64; s >= 1; s >>= 1) {
+            double o = __shfl_down_sync(0xffffffffu, v, s);
+            if (o < v) v = o;
+        }
+        if (threadIdx.x == 0) {
+            unsigned long long* addr = reinterpret_cast<unsigned long long*>(target);
+            unsigned long long old = *addr;
+            while (v < __longlong_as_double((long long)old)) {
+                unsigned long long assumed = old;
+                old = atomicCAS(addr, assumed, (unsigned long long)__double_as_longlong(v));
+                if (old == assumed) break;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // deriv  (subrutinas.f90:99-122) : one thread per element
 __global__ void __launch_bounds__(256) deriv(int nelem, const int* __restrict__ inp, const double* __restrict__ X,
@@ -77,26 +109,7 @@ __global__ void __launch_bounds__(256) deriv(int nelem, const int* __restrict__ 
         HHY[e] = fabs(ex::fmin2(ex::fmin2(y3 - y2, y1 - y3), y2 - y1));
     }
     // hmin = minval(HH) (:124) — exact whatever the order; NaN never wins a '<'
-    __shared__ double sm[256];
-    sm[threadIdx.x] = hh;
-    __syncthreads();
-    for (int s = 128; s >= 1; s >>= 1) {
-        if (threadIdx.x < s) {
-            double o = sm[threadIdx.x + s];
-            if (o < sm[threadIdx.x]) sm[threadIdx.x] = o;
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        double v = sm[0];
-        unsigned long long* addr = reinterpret_cast<unsigned long long*>(&sc->HMIN);
-        unsigned long long old = *addr;
-        while (v < __longlong_as_double((long long)old)) {
-            unsigned long long assumed = old;
-            old = atomicCAS(addr, assumed, (unsigned long long)__double_as_longlong(v));
-            if (old == assumed) break;
-        }
-    }
+    block_min_to_global<256>(hh, &sc->HMIN);
 }
 
 // MASAS (subrutinas.f90:137-152) as an ordered node gather over esup
@@ -216,26 +229,7 @@ __global__ void __launch_bounds__(256) deltat(int nelem, const int* __restrict__
         if (WRITE_DT) DT[e] = DTELEM;
         if (DTELEM < dte) dte = DTELEM;
     }
-    __shared__ double sm[256];
-    sm[threadIdx.x] = dte;
-    __syncthreads();
-    for (int s = 128; s >= 1; s >>= 1) {
-        if (threadIdx.x < s) {
-            double o = sm[threadIdx.x + s];
-            if (o < sm[threadIdx.x]) sm[threadIdx.x] = o;
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        double v = sm[0];
-        unsigned long long* addr = reinterpret_cast<unsigned long long*>(&sc->dtmin_acc);
-        unsigned long long old = *addr;
-        while (v < __longlong_as_double((long long)old)) {
-            unsigned long long assumed = old;
-            old = atomicCAS(addr, assumed, (unsigned long long)__double_as_longlong(v));
-            if (old == assumed) break;
-        }
-    }
+    block_min_to_global<256>(dte, &sc->dtmin_acc);
 }
 
 // start of a pass of the time loop: ITER++ (ns2DComp.ALE.f90:140), reset the running min
@@ -522,8 +516,7 @@ __global__ void __launch_bounds__(256, MINB) estab(int nelem, const int* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
-// calcRHS (calcRHS.f90:36-141): the arithmetic of one element, shared by the direct and the cp.async-pipelined
-// kernels.  Inputs are the gathered nodal values and the element's stream data; rt(3 nodes, 4 eqns) is the
+// calcRHS (calcRHS.f90:36-141): the arithmetic of one element, shared by the two-kernel stage and the fused tile stage.  Inputs are the gathered nodal values and the element's stream data; rt(3 nodes, 4 eqns) is the
 // contribution before the scatter.  Evaluation order is the source's (see exact.cuh).
 // NB = true: the divisions are the branch-free forms of exact.cuh (same values); *bad is raised when an operand falls
 // outside their fast path, and the caller then recomputes the element with NB = false.
@@ -802,112 +795,6 @@ __global__ void __launch_bounds__(BS, MINB) calcrhs_elem(int e0, int e1, int nel
     }
 }
 
-// calcRHS, persistent + software-pipelined variant (fixed meshes, theta = 0).  The grid is a multiple of the SM
-// count; every CTA walks tiles of 128 elements.  While a thread computes element e of tile t, the inputs of its
-// element of tile t+1 are already in flight to shared memory (cp.async: the element stream coalesced, the nodal
-// gathers by index) and the connectivity of tile t+2 is in flight to registers, so the fp64 pipe is not left idle
-// while a warp waits for HBM at the top of the kernel.  A thread only ever reads the shared-memory slots it
-// filled itself, so there is no block-level barrier.  Arithmetic: calcrhs_body, unchanged.
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
-    unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-template <bool VISC>
-struct PipeLayout {
-    // per stage, per thread: 6 x 16 B (U of 3 nodes) + 12 (Nx,Ny,area,shoc,ts1-3,dtl) + 3 (T) doubles
-    static constexpr int kD2 = 6;
-    static constexpr int kD1 = 12 + (VISC ? 3 : 0);
-    static constexpr int kStageBytes = 128 * (kD2 * 16 + kD1 * 8);
-};
-
-template <bool VISC, int MINB>
-__global__ void __launch_bounds__(128, MINB) calcrhs_pipe(int nelem, const int* __restrict__ inp, const double* __restrict__ U,
-                                                           const double* __restrict__ T, const double* __restrict__ dNx,
-                                                           const double* __restrict__ dNy, const double* __restrict__ area,
-                                                           const double* __restrict__ shoc, const double* __restrict__ dtl_arr,
-                                                           const double* __restrict__ dtl_sc, const double* __restrict__ ts1,
-                                                           const double* __restrict__ ts2, const double* __restrict__ ts3, Gas g,
-                                                           double* __restrict__ EC) {
-    using L = PipeLayout<VISC>;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x;
-    const int ntiles = (nelem + 127) / 128;
-    const size_t NE = (size_t)nelem;
-    auto d2 = [&](int stage, int slot) { return reinterpret_cast<double2*>(smem_raw + (size_t)stage * L::kStageBytes) + slot * 128 + tid; };
-    auto d1 = [&](int stage, int slot) {
-        return reinterpret_cast<double*>(smem_raw + (size_t)stage * L::kStageBytes + 128 * L::kD2 * 16) + slot * 128 + tid;
-    };
-    auto load_idx = [&](int tile, int (&ip)[3]) {
-        int e = tile * 128 + tid;
-        if (tile < ntiles && e < nelem) { ip[0] = inp[e]; ip[1] = inp[NE + e]; ip[2] = inp[2 * NE + e]; }
-    };
-    auto issue = [&](int tile, int stage, const int (&ip)[3]) {
-        int e = tile * 128 + tid;
-        if (tile < ntiles && e < nelem) {
-#pragma unroll
-            for (int n = 0; n < 3; ++n) {
-                const double* u = U + 4 * (size_t)ip[n];
-                cp_async16(d2(stage, 2 * n), u);
-                cp_async16(d2(stage, 2 * n + 1), u + 2);
-                cp_async8(d1(stage, n), dNx + n * NE + e);
-                cp_async8(d1(stage, 3 + n), dNy + n * NE + e);
-                if (VISC) cp_async8(d1(stage, 12 + n), T + ip[n]);
-            }
-            cp_async8(d1(stage, 6), area + e);
-            cp_async8(d1(stage, 7), shoc + e);
-            cp_async8(d1(stage, 8), ts1 + e);
-            cp_async8(d1(stage, 9), ts2 + e);
-            cp_async8(d1(stage, 10), ts3 + e);
-            if (dtl_arr) cp_async8(d1(stage, 11), dtl_arr + e);
-        }
-        cp_async_commit();
-    };
-    int t = blockIdx.x, tn = t + gridDim.x, stage = 0;
-    int ipC[3] = {0, 0, 0}, ipN[3] = {0, 0, 0};
-    load_idx(t, ipC);
-    issue(t, 0, ipC);
-    load_idx(tn, ipN);
-    const double dtl_uniform = dtl_arr ? 0.0 : *dtl_sc;
-    for (; t < ntiles; t = tn, tn += gridDim.x, stage ^= 1) {
-        issue(tn, stage ^ 1, ipN);
-        load_idx(tn + gridDim.x, ipN);  // consumed by the issue of the next iteration
-        cp_async_wait<1>();
-        int e = t * 128 + tid;
-        if (e >= nelem) continue;
-        double Un[3][4], Th[3][4], Tn[3] = {0.0, 0.0, 0.0}, Nx[3], Ny[3], tau[3];
-#pragma unroll
-        for (int n = 0; n < 3; ++n) {
-            double2 a = *d2(stage, 2 * n), b = *d2(stage, 2 * n + 1);
-            Un[n][0] = a.x; Un[n][1] = a.y; Un[n][2] = b.x; Un[n][3] = b.y;
-            Nx[n] = *d1(stage, n);
-            Ny[n] = *d1(stage, 3 + n);
-            tau[n] = *d1(stage, 8 + n);
-            if (VISC) Tn[n] = *d1(stage, 12 + n);
-        }
-        const double ar = *d1(stage, 6), sh_e = *d1(stage, 7);
-        const double dtl = dtl_arr ? *d1(stage, 11) : dtl_uniform;
-        double Ux[4], Uy[4], rt[3][4];
-        calcrhs_body<VISC, false>(g, Un, Th, Tn, Nx, Ny, tau, sh_e, Ux, Uy, rt);
-        double* out = EC + 12 * (size_t)e;
-#pragma unroll
-        for (int n = 0; n < 3; ++n) {
-            double v[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] = ex::div3(rt[n][i] * ar * dtl);
-            st4(out + 4 * n, v);
-        }
-    }
-    cp_async_wait<0>();
-}
-
 // CUARTO_ORDEN (subrutinas.f90:243-327), "next" row N1: element part -> staging buffer, node part
 // U_n = -(ordered sum)/M.  Same ordered-gather scheme as calcRHS.
 __global__ void __launch_bounds__(128) cuarto_elem(int nelem, const int* __restrict__ inp, const double* __restrict__ U,
@@ -1115,94 +1002,26 @@ __global__ void __launch_bounds__(256) node_accumulate(int npoin, const int* __r
 }
 
 // ---------------------------------------------------------------------------------------------
-// Tile-fused RK stage (fixed meshes): one CTA per tile of 512 elements (a spatially compact set chosen on the host).
-// Phase 1 computes the tile's element contributions into shared memory (48 KB, [12][512] so the stores are
-// conflict-free); contributions to nodes shared with other tiles also go to the global staging buffer.  Phase 2
-// sums, for every node all of whose elements lie in this tile (~3/4 of the nodes), its contributions from shared
-// memory in ascending ORIGINAL element order and runs the nodal chain.  Only the tile-boundary nodes take the
-// two-kernel route (node_update over a node list).  Same arithmetic, same summation order: same bits; what changes
-// is that ~3/4 of the staging traffic (96 B/element written + read) never reaches HBM.
-template <bool VISC, int MINB>
-__global__ void __launch_bounds__(128, MINB) stage_tile(int ntiles, int nelem, const int* __restrict__ tile_elems,
-                                                         const unsigned char* __restrict__ ebmask, const int* __restrict__ tnode_ptr,
-                                                         const int* __restrict__ tnodes, const int* __restrict__ esup2,
-                                                         const unsigned short* __restrict__ tslot, const int* __restrict__ inp,
-                                                         const double* __restrict__ Usrc, const double* __restrict__ T,
-                                                         const double* __restrict__ dNx, const double* __restrict__ dNy,
-                                                         const double* __restrict__ area, const double* __restrict__ shoc,
-                                                         const double* __restrict__ dtl_arr, const double* __restrict__ dtl_sc,
-                                                         const double* __restrict__ ts1, const double* __restrict__ ts2,
-                                                         const double* __restrict__ ts3, Gas g, double* __restrict__ EC,
-                                                         const double* __restrict__ U, const double* __restrict__ M,
-                                                         const double* __restrict__ GAMM, const double* __restrict__ WXa,
-                                                         const double* __restrict__ WYa, const unsigned char* __restrict__ bcflag,
-                                                         BcTab bc, double rk_fact, double FR, double* __restrict__ U1,
-                                                         double* __restrict__ RHS, double* __restrict__ RHO, double* __restrict__ VELX,
-                                                         double* __restrict__ VELY, double* __restrict__ Ea, double* __restrict__ Pa,
-                                                         double* __restrict__ Ta, double* __restrict__ RMACH) {
-    extern __shared__ double sm[];  // [12][512]
-    const int t = blockIdx.x;
-    if (t >= ntiles) return;
-    const size_t NE = (size_t)nelem;
-    const double dtl_uniform = dtl_arr ? 0.0 : *dtl_sc;
-    // four rounds of 128 elements, NOT unrolled: one copy of the ~1500-instruction element arithmetic in the instruction
-    // stream instead of four (measured 1.96 -> 1.70 ms per launch, profiles/r1_experiments.md)
-#pragma unroll 1
-    for (int r = 0; r < 4; ++r) {
-        const int k = r * 128 + threadIdx.x;
-        const int e = tile_elems[(size_t)t * 512 + k];
-        if (e < 0) continue;
-        int ip[3] = {inp[e], inp[NE + e], inp[2 * NE + e]};
-        double Nx[3] = {dNx[e], dNx[NE + e], dNx[2 * NE + e]};
-        double Ny[3] = {dNy[e], dNy[NE + e], dNy[2 * NE + e]};
-        double Un[3][4], Th[3][4], Tn[3] = {0.0, 0.0, 0.0};
-        ld4(Usrc + 4 * (size_t)ip[0], Un[0]);
-        ld4(Usrc + 4 * (size_t)ip[1], Un[1]);
-        ld4(Usrc + 4 * (size_t)ip[2], Un[2]);
-        if (VISC) { Tn[0] = T[ip[0]]; Tn[1] = T[ip[1]]; Tn[2] = T[ip[2]]; }
-        const double tau[3] = {ts1[e], ts2[e], ts3[e]};
-        const double dtl = dtl_arr ? dtl_arr[e] : dtl_uniform;
-        const double ar = area[e];
-        double Ux[4], Uy[4], rt[3][4];
-        calcrhs_body<VISC, false>(g, Un, Th, Tn, Nx, Ny, tau, shoc[e], Ux, Uy, rt);
-        const unsigned mask = ebmask[(size_t)t * 512 + k];
-#pragma unroll
-        for (int n = 0; n < 3; ++n) {
-            double v[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                v[i] = ex::div3(rt[n][i] * ar * dtl);
-                sm[(n * 4 + i) * 512 + k] = v[i];
-            }
-            if (mask & (1u << n)) st4(EC + 12 * (size_t)e + 4 * n, v);
-        }
-    }
-    __syncthreads();
-    for (int j = tnode_ptr[t] + threadIdx.x; j < tnode_ptr[t + 1]; j += 128) {
-        const int n = tnodes[j];
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int q = esup2[n]; q < esup2[n + 1]; ++q) {
-            const int slot = tslot[q];  // 3*position-in-tile + local node
-            const int lp = slot / 3, ln = slot - 3 * lp;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[i] = acc[i] + sm[(ln * 4 + i) * 512 + lp];
-        }
-        st4(RHS + 4 * (size_t)n, acc);
-        node_finish(n, acc, U, M, GAMM, WXa, WYa, bcflag, bc, rk_fact, FR, U1, RHO, VELX, VELY, Ea, Pa, Ta, RMACH);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
 // Canonical reductions (oracle/orc_math.h canon_sum): 4096-entry chunks, 256 lanes stride 256
 // ascending, binary tree 128..1, recursive over chunk sums.  One CTA of 256 threads per chunk.
 __device__ __forceinline__ double tree256(double v, double* sm) {
-    sm[threadIdx.x] = v;
+    // sm[t] += sm[t+s], s = 128, 64, ..., 1: the first two levels through shared memory, the last six inside warp 0
+    // (level 32 read from shared memory, levels 16..1 by __shfl_down_sync, which pairs lane t with lane t+s: the same
+    // operands in the same order, so the same bits as the shared-memory tree of oracle/orc_math.h canon_sum)
+    const int t = threadIdx.x;
+    sm[t] = v;
     __syncthreads();
+    if (t < 128) sm[t] = sm[t] + sm[t + 128];
+    __syncthreads();
+    if (t < 64) sm[t] = sm[t] + sm[t + 64];
+    __syncthreads();
+    if (t < 32) {
+        double r = sm[t] + sm[t + 32];
 #pragma unroll
-    for (int s = 128; s >= 1; s >>= 1) {
-        if (threadIdx.x < s) sm[threadIdx.x] = sm[threadIdx.x] + sm[threadIdx.x + s];
-        __syncthreads();
+        for (int s = 16; s >= 1; s >>= 1) r = r + __shfl_down_sync(0xffffffffu, r, s);
+        if (t == 0) sm[0] = r;
     }
+    __syncthreads();
     double r = sm[0];
     __syncthreads();
     return r;
@@ -1382,10 +1201,13 @@ __global__ void __launch_bounds__(256) bicg_k2(int n, int nred, const Scal* sc, 
 }
 enum { SCF_BETA = 0, SCF_ALFA = 1, SCF_START = 2, SCF_FLUSHED = 3 };
 __global__ void bicg_fused_scalar(Scal* sc, int what, int slot) {
-    if (what == SCF_START) {  // after the prologue (:37-45): enter the while loop or not
+    if (what == SCF_START) {  // after the prologue (:37-45): the early return (:35), else enter the while loop or not
+        // the prologue's own x = alfa*p + x (:44) is left pending like the loop's (:59): the next bicg_k1 / bicg_flush
+        // applies it -- unless r.r < tol, in which case the reference has returned before computing any of it
+        const bool ret = sc->rr < 1.e-10;
         sc->bicg_k = 0;
-        sc->bicg_xpend = 0;
-        sc->bicg_state = fabs(sc->err_old) > 1.e-10 ? 1 : 0;
+        sc->bicg_xpend = ret ? 0 : 1;
+        sc->bicg_state = (!ret && fabs(sc->err_old) > 1.e-10) ? 1 : 0;
         return;
     }
     if (what == SCF_FLUSHED) { sc->bicg_xpend = 0; return; }
@@ -1402,6 +1224,15 @@ __global__ void bicg_fused_scalar(Scal* sc, int what, int slot) {
         sc->bicg_xpend = 1;                   // :59, applied by the next bicg_k1
         sc->bicg_state = (fabs(sc->err_old) > 1.e-10 && sc->bicg_k < 1000) ? 1 : 0;  // :47
     }
+}
+// end of a batch of enqueued iterations: if the loop has ended on the device, apply the pending x = alfa*p + x (:59 / :44)
+__global__ void __launch_bounds__(256) bicg_flush(int n, const Scal* sc, const double* __restrict__ p, double* __restrict__ x) {
+    if (sc->bicg_state || !sc->bicg_xpend) return;
+    const double alfa = sc->alfa;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) x[i] = alfa * p[i] + x[i];
+}
+__global__ void bicg_flushed(Scal* sc) {
+    if (!sc->bicg_state) sc->bicg_xpend = 0;
 }
 __global__ void mark_fixed(int m, const int* __restrict__ idx, unsigned char* __restrict__ flag) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1586,26 +1417,34 @@ __global__ void __launch_bounds__(256) gcl(int npoin, int nelem, const int* __re
 }
 
 // ---------------------------------------------------------------------------------------------
-// ghost exchange packing: 7 doubles per node (U1(4), T, VEL_X, VEL_Y) or one double
+// ghost exchange packing: 10 doubles per node -- U1(4), T, VEL_X, VEL_Y, E, P, RMACH (RHO is U1(1) exactly) -- so that every
+// nodal array the reference's RK leaves behind is valid at ghost nodes too (FORCES / FORCE_VISC read P at both ends of a body
+// edge and at the three nodes of the element behind it, either of which can be a ghost); or one double
+constexpr int HALO_W = 10;
 __global__ void halo_pack_state(int m, const int* __restrict__ idx, const double* __restrict__ U1, const double* __restrict__ T,
-                                const double* __restrict__ VX, const double* __restrict__ VY, double* __restrict__ buf) {
+                                const double* __restrict__ VX, const double* __restrict__ VY, const double* __restrict__ Ea,
+                                const double* __restrict__ Pa, const double* __restrict__ RMACH, double* __restrict__ buf) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     int n = idx[i];
     double u[4];
     ld4(U1 + 4 * (size_t)n, u);
-    double* b = buf + 7 * (size_t)i;
+    double* b = buf + HALO_W * (size_t)i;
     b[0] = u[0]; b[1] = u[1]; b[2] = u[2]; b[3] = u[3]; b[4] = T[n]; b[5] = VX[n]; b[6] = VY[n];
+    b[7] = Ea[n]; b[8] = Pa[n]; b[9] = RMACH[n];
 }
 __global__ void halo_unpack_state(int m, const int* __restrict__ idx, const double* __restrict__ buf, double* __restrict__ U1,
-                                  double* __restrict__ T, double* __restrict__ VX, double* __restrict__ VY) {
+                                  double* __restrict__ T, double* __restrict__ VX, double* __restrict__ VY,
+                                  double* __restrict__ RHO, double* __restrict__ Ea, double* __restrict__ Pa,
+                                  double* __restrict__ RMACH) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     int n = idx[i];
-    const double* b = buf + 7 * (size_t)i;
+    const double* b = buf + HALO_W * (size_t)i;
     double u[4] = {b[0], b[1], b[2], b[3]};
     st4(U1 + 4 * (size_t)n, u);
     T[n] = b[4]; VX[n] = b[5]; VY[n] = b[6];
+    RHO[n] = b[0]; Ea[n] = b[7]; Pa[n] = b[8]; RMACH[n] = b[9];
 }
 __global__ void halo_pack(int m, int w, const int* __restrict__ idx, const double* __restrict__ v, double* __restrict__ buf) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;

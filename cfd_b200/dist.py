@@ -18,7 +18,8 @@ def make_rank_solver(lc_or_window, rank, nranks, device, dist=None, use_gcl=0):
         part = partition.build_local(lc_or_window[0], nranks, rank, *lc_or_window[1:])
     else:
         part = partition.build_local(lc_or_window, nranks, rank)
-    g = NSComp2D(part.lc, device=device, use_gcl=use_gcl)
+    # the communicator comes before cfdb_init: DERIV's HMIN is a global minimum (subrutinas.f90:124)
+    g = NSComp2D(part.lc, device=device, use_gcl=use_gcl, init=False)
     g.attach_partition(part)
     if nranks > 1:
         if dist is None:
@@ -26,6 +27,7 @@ def make_rank_solver(lc_or_window, rank, nranks, device, dist=None, use_gcl=0):
         box = [NSComp2D.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         g.comm_init(box[0], rank, nranks)
+    g.init()
     return g, part
 
 

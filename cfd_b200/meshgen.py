@@ -236,7 +236,7 @@ def _rows_lattice(nx, j0, j1, ny_total, jitter, seed):
     return x, y
 
 
-def square_rows(n, nranks, rank, mach=0.5, jitter=0.3, seed=12345, name="square", all_rows=False, rows_per=None, **kw):
+def square_rows(n, nranks, rank, mach=0.5, jitter=0.3, seed=12345, name="square", all_rows=False, rows_per=None, jrange=None, **kw):
     """Window (own quad rows +-1) of the `nranks`-strip square mesh; returns (RawCase, first global row).
     Each strip has n nodes per row and `rows_per` quad rows (default n-1: weak scaling, one n x n lattice per rank;
     strong scaling passes rows_per = (n-1)/nranks so that the whole domain stays n x n)."""
@@ -245,6 +245,8 @@ def square_rows(n, nranks, rank, mach=0.5, jitter=0.3, seed=12345, name="square"
     ny_total = nranks * rows_per + 1
     j0 = 0 if all_rows else max(0, rank * rows_per - 1)
     j1 = ny_total - 1 if all_rows else min(ny_total - 1, (rank + 1) * rows_per + 1)
+    if jrange is not None:   # node rows chosen by the caller (partition.square_window: chunk-aligned ownership)
+        j0, j1 = jrange
     x, y = _rows_lattice(nx, j0, j1, ny_total, jitter, seed)
     nrows = j1 - j0 + 1
     inpoel = _triangulate(x, y, nx, nrows)

@@ -11,6 +11,18 @@ Definition, deterministic and bit-exact against tests' br
     RK stage (one packed message per neighbour).
 Local numbering: owned nodes first (ascending global id), then ghosts (ascending global id); local
 elements in ascending global id.  Exchange lists are sorted by global node id on both sides.
+
+Reduction alignment (round 2).  Inner products (biCG) and the residual norms use one fixed "canonical" order over
+the GLOBAL node index: chunks of RED_CHUNK = 4096 consecutive nodes, then a recursive tree over the chunk sums
+(oracle/orc_math.h canon_sum).  To make an N-rank run reproduce the single-GPU bits, every chunk must be summed by
+ONE rank.  When the owned sets of the "lowest rank touching" rule are contiguous ranges of the global numbering (strip
+partitions of meshes numbered along the element order -- every mesh of this repository), the range boundaries are
+therefore moved to the NEAREST multiple of RED_CHUNK (`align_owner`): rank r owns [B_r, B_{r+1}), B_r % 4096 == 0.
+Everything else follows from the ownership as before (a rank computes every element touching a node it owns, a few
+thousand elements more or less than with the natural boundary).  The ranks then exchange chunk sums, never partial
+sums of a chunk, and run the upper tree levels redundantly: bit-identical to one GPU.  Meshes whose owned sets are
+not contiguous (or ranks with fewer than two chunks) keep the natural ownership; their multi-rank inner products
+then agree with the single-GPU ones to round-off only (`LocalPart.red_aligned` says which).
 """
 from __future__ import annotations
 
@@ -19,6 +31,9 @@ from dataclasses import dataclass, field, replace
 import numpy as np
 
 from .deck import I32, LoadedCase
+
+
+RED_CHUNK = 4096   # first-level chunk of the canonical reduction order (oracle/orc_math.h, kernels.cuh: dot_chunks)
 
 
 def element_ranges(nelem: int, nranks: int) -> np.ndarray:
@@ -40,6 +55,10 @@ class LocalPart:
     recv: dict = field(default_factory=dict)   # rank -> local ids of ghost nodes that rank owns (by gid)
     moving: bool = False        # the GLOBAL case has body sets (fluidStructure moves the mesh on every rank, also on
                                 # ranks whose local deck holds none of the set edges)
+    red_aligned: bool = False   # owned nodes = the global range [gid0, gid0 + n_owned) with gid0 % RED_CHUNK == 0
+    gid0: int = 0               # global id of the first owned node (meaningful when red_aligned)
+    npoin_global: int = 0
+    set_gidx: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int64))  # local ISET row -> global ISET row
 
     def halo_arrays(self):
         """Flattened CSR form for cfdb_set_halo: ranks, send_ptr, send_idx, recv_ptr, recv_idx (0-based)."""
@@ -63,6 +82,34 @@ def node_owner(inpoel0: np.ndarray, elem_rank: np.ndarray, npoin: int) -> np.nda
     return owner
 
 
+def aligned_boundaries(first_owned: np.ndarray, npoin_global: int, chunk: int = RED_CHUNK):
+    """first_owned[r] = global id of the first node rank r owns under the natural rule (first_owned[0] == 0), ranges
+    contiguous and ascending.  Returns B (nranks+1,) with B[r] the nearest multiple of `chunk`, or None when a rank would be
+    left with fewer than two chunks (tiny meshes keep the natural ownership)."""
+    g = np.asarray(first_owned, np.int64)
+    B = np.concatenate([((g + chunk // 2) // chunk) * chunk, [npoin_global]]).astype(np.int64)
+    B[0] = 0
+    if (np.diff(B) < 2 * chunk).any():
+        return None
+    return B
+
+
+def align_owner(owner: np.ndarray, node_gid: np.ndarray, nranks: int, npoin_global: int):
+    """Natural owner (global mesh) -> chunk-aligned owner, or (owner, None) when the natural owned sets are not contiguous
+    ascending ranges of the global numbering."""
+    order = np.argsort(node_gid, kind="stable")
+    o = owner[order]
+    if nranks < 2 or (o < 0).any() or (np.diff(o) < 0).any() or node_gid.size != npoin_global:
+        return owner, None
+    first = np.searchsorted(o, np.arange(nranks), side="left")          # position == global id (all nodes present)
+    if (np.diff(np.concatenate([first, [npoin_global]])) <= 0).any():
+        return owner, None
+    B = aligned_boundaries(node_gid[order][first], npoin_global)
+    if B is None:
+        return owner, None
+    return (np.searchsorted(B, node_gid, side="right") - 1).astype(np.int64), B
+
+
 def _need_pairs(inpoel0, owner):
     """Unique (node, rank) pairs: `rank` needs the state of `node`, which it does not own."""
     on = owner[inpoel0]                                 # (E,3) owner of each local node
@@ -80,9 +127,11 @@ def _need_pairs(inpoel0, owner):
 
 
 def build_local(lc: LoadedCase, nranks: int, rank: int, elem_rank: np.ndarray | None = None,
-                node_gid: np.ndarray | None = None, elem_gid: np.ndarray | None = None) -> LocalPart:
+                node_gid: np.ndarray | None = None, elem_gid: np.ndarray | None = None,
+                bounds: np.ndarray | None = None, npoin_global: int | None = None, align: bool = True) -> LocalPart:
     """Local part of `rank`.  `lc` is the global mesh, or a window of it that contains every element
-    touching a node of the rank's local elements (then pass the window's elem_rank / node_gid / elem_gid)."""
+    touching a node of the rank's local elements (then pass the window's elem_rank / node_gid / elem_gid, and the
+    chunk-aligned ownership boundaries `bounds` the window's generator knows analytically, or None for the natural rule)."""
     E, P = lc.nelem, lc.npoin
     inp0 = lc.inpoel.astype(np.int64) - 1
     if elem_rank is None:
@@ -91,7 +140,17 @@ def build_local(lc: LoadedCase, nranks: int, rank: int, elem_rank: np.ndarray | 
     elem_rank = np.asarray(elem_rank, np.int64)
     node_gid = np.arange(P, dtype=np.int64) if node_gid is None else np.asarray(node_gid, np.int64)
     elem_gid = np.arange(E, dtype=np.int64) if elem_gid is None else np.asarray(elem_gid, np.int64)
+    window = npoin_global is not None and int(npoin_global) != P
+    npoin_global = P if npoin_global is None else int(npoin_global)
     owner = node_owner(inp0, elem_rank, P)
+    B = None
+    if align and nranks > 1:
+        if window:
+            if bounds is not None:
+                B = np.asarray(bounds, np.int64)
+                owner = (np.searchsorted(B, node_gid, side="right") - 1).astype(np.int64)
+        else:
+            owner, B = align_owner(owner, node_gid, nranks, npoin_global)
     emask = (owner[inp0] == rank).any(1)
     loc_el = np.flatnonzero(emask)                       # ascending window id == ascending global id
     nodes = np.unique(inp0[loc_el])
@@ -137,8 +196,10 @@ def build_local(lc: LoadedCase, nranks: int, rank: int, elem_rank: np.ndarray | 
         e_l = np.searchsorted(loc_el, s[:, 0].astype(np.int64) - 1)
         e_l = np.where((e_l < loc_el.size) & (loc_el[np.minimum(e_l, loc_el.size - 1)] == s[:, 0] - 1), e_l + 1, 0)
         sets = np.stack([e_l.astype(I32), ren(s[:, 1]), ren(s[:, 2]), s[:, 3]], 1).astype(I32)
+        set_gidx = np.flatnonzero(m_s).astype(np.int64)
     else:
         sets = np.zeros((0, 4), I32)
+        set_gidx = np.zeros(0, np.int64)
     i_m, ifm = ren(lc.i_m[m_im]), ren(lc.ifm[m_ifm])
     fix = np.zeros(order.size, np.uint8)
     fix[i_m - 1] = 1
@@ -155,26 +216,43 @@ def build_local(lc: LoadedCase, nranks: int, rank: int, elem_rank: np.ndarray | 
     )
     return LocalPart(rank=rank, nranks=nranks, lc=local, node_gid=node_gid[order], elem_gid=elem_gid[loc_el],
                      n_owned=int(n_owned), elem_own=(elem_rank[loc_el] == rank), neighbors=neighbors, send=send, recv=recv,
-                     moving=bool(lc.sets.size))
+                     moving=bool(lc.sets.size), red_aligned=B is not None, gid0=int(B[rank]) if B is not None else 0,
+                     npoin_global=npoin_global, set_gidx=set_gidx)
 
 
-def square_window(n: int, nranks: int, rank: int, rows_per: int | None = None, **kw):
+def square_window(n: int, nranks: int, rank: int, rows_per: int | None = None, align: bool = True, **kw):
     """Weak-scaling bench mesh: rank's window of the global `nranks`-strip square mesh (each strip is the
     n x n lattice of meshgen.square, stacked in y), generated without building the global mesh.
 
-    Returns (window LoadedCase, elem_rank, node_gid, elem_gid) ready for build_local().  The window holds the
-    rank's own quad rows plus one quad row on either side, which is enough to know the owner of every node
-    of the rank's local elements.  meshgen.square_global(n, nranks) builds the same mesh in one piece.
+    Returns (window LoadedCase, elem_rank, node_gid, elem_gid, bounds, npoin_global) ready for build_local().  The window
+    holds every node row that carries a node this rank owns plus one row on either side, which is enough to know the owner
+    of every node of the rank's local elements; the ownership boundaries are the chunk-aligned ones (module docstring),
+    known analytically here: the natural first owned node of rank r >= 1 is the first node of row r*rows_per + 1.
+    meshgen.square_global(n, nranks) builds the same mesh in one piece.
     """
     from . import deck, meshgen
 
-    raw, j0 = meshgen.square_rows(n, nranks, rank, rows_per=rows_per, **kw)
-    lc = deck.load(raw)
     nx = n
     nqx = nx - 1
     rows_per = (n - 1) if rows_per is None else rows_per  # quad rows per rank
+    ny_total = nranks * rows_per + 1
+    npoin_global = nx * ny_total
+    B = None
+    if align and nranks > 1:
+        first = np.array([0] + [(r * rows_per + 1) * nx for r in range(1, nranks)], np.int64)
+        B = aligned_boundaries(first, npoin_global)
+    jrange = None
+    if B is not None:
+        j0 = max(0, int(B[rank] // nx) - 1)
+        j1 = min(ny_total - 1, int((B[rank + 1] - 1) // nx) + 1)
+        # the natural window (own quad rows +-1) is kept inside: elem_rank of the window's elements stays meaningful
+        j0 = min(j0, max(0, rank * rows_per - 1))
+        j1 = max(j1, min(ny_total - 1, (rank + 1) * rows_per + 1))
+        jrange = (j0, j1)
+    raw, j0 = meshgen.square_rows(n, nranks, rank, rows_per=rows_per, jrange=jrange, **kw)
+    lc = deck.load(raw)
     qrow = (np.arange(lc.nelem) // (2 * nqx)) + j0        # global quad row of each window element
     elem_rank = np.minimum(qrow // rows_per, nranks - 1)
     elem_gid = 2 * nqx * j0 + np.arange(lc.nelem, dtype=np.int64)
     node_gid = nx * j0 + np.arange(lc.npoin, dtype=np.int64)
-    return lc, elem_rank, node_gid, elem_gid
+    return lc, elem_rank, node_gid, elem_gid, B, npoin_global

@@ -49,6 +49,10 @@ class NSComp2D:
         if init:
             capi.check(self.L.cfdb_init(self.h))
 
+    def init(self):
+        """ns2DComp.ALE.f90:59-136 on the device (cfdb_init); the constructor calls it unless init=False."""
+        capi.check(self.L.cfdb_init(self.h))
+
     def close(self):
         if getattr(self, "h", None) is not None and self.h.value:
             self.L.cfdb_destroy(self.h)
@@ -66,6 +70,8 @@ class NSComp2D:
         ranks, sp, si, rp, ri = part.halo_arrays()
         self._halo_keep = (ranks, sp, si, rp, ri)
         capi.check(self.L.cfdb_set_halo(self.h, part.n_owned, ranks.size, ranks, sp, si, rp, ri))
+        if getattr(part, "red_aligned", False):   # chunk-aligned ownership: global canonical reductions, bit-identical to one GPU
+            capi.check(self.L.cfdb_set_reduction_layout(self.h, int(part.gid0), int(part.npoin_global)))
         if getattr(part, "moving", False):
             self.set_option("ale", 1)   # FUENTE and the mesh-velocity terms also on ranks without body edges of their own
         self.part = part

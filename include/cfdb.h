@@ -116,14 +116,20 @@ int64_t cfdb_launch_count(cfdb_ctx* ctx);                    /* kernels launched
  * (new: the reference is single-process.)  Rank r computes every element touching a node it owns, so
  * owned-node sums are complete and bit-identical to the single-GPU run; ghost nodes are refreshed from their
  * owners after every RK stage (ncclSend/ncclRecv, one packed message per neighbour); DTMIN is an
- * ncclAllReduce(min); biCG inner products and the residual norms are ncclAllReduce(sum) of per-rank
- * canonical sums over owned nodes.  Local numbering: owned nodes first. */
+ * ncclAllReduce(min); biCG inner products and the residual norms are canonical sums over the GLOBAL node index when the
+ * ownership is chunk-aligned (cfdb_set_reduction_layout: bit-identical to one GPU), else ncclAllReduce(sum) of per-rank
+ * canonical sums over owned nodes (round-off level).  Local numbering: owned nodes first. */
 int cfdb_nccl_unique_id(void* out128);                       /* ncclGetUniqueId on one rank; broadcast it yourself */
 int cfdb_comm_init(cfdb_ctx* ctx, const void* uid128, int32_t rank, int32_t nranks);
 int cfdb_set_halo(cfdb_ctx* ctx, int32_t n_owned, int32_t nneigh, const int32_t* neigh_rank,
                   const int32_t* send_ptr, const int32_t* send_idx, const int32_t* recv_ptr,
                   const int32_t* recv_idx);                  /* 0-based local node ids, CSR per neighbour */
 int cfdb_halo_exchange(cfdb_ctx* ctx, const char* field);    /* refresh the ghosts of one nodal field ("T", "U", ...) */
+/* Chunk-aligned ownership (cfd_b200/partition.py): this rank's owned nodes are the global nodes [gid0, gid0 + n_owned) with
+ * gid0 a multiple of 4096, the first-level chunk of the canonical reduction order.  The ranks then exchange chunk sums
+ * (one ncclAllReduce over a zero-filled global array: exact) and every rank runs the upper tree levels itself, so biCG's
+ * inner products and the residual norms carry the bits of the single-GPU run.  Call after cfdb_set_halo. */
+int cfdb_set_reduction_layout(cfdb_ctx* ctx, int64_t gid0, int64_t npoin_global);
 
 /* ---- (i) call-site mode: one entry point per reference subroutine, host pointers ------------ */
 /* calcRHS_mod::calcRHS, calcRHS.f90:4 (module inputs FCV,FK,FMU,gama,T_inf,cte and T(:) made explicit) */

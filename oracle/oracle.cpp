@@ -1135,6 +1135,8 @@ int orc_field(void* h, const char* name, void** ptr, long* len) {
     DF(X1) DF(Y1) DF(lap_sparse) DF(lap_diag) DF(n_x) DF(n_y) DF(xpos) DF(ypos) DF(dxpos) DF(dypos)
     DF(W_x_old) DF(W_y_old) DF(area_old) DF(skin) DF(skin_x) DF(skin_p)
     if (n == "FX") { *ptr = s.FX; *len = 10; return 0; }
+    if (n == "ER") { *ptr = s.ER; *len = 4; return 0; }    // as the time loop left them (ns2DComp.ALE.f90:191-197)
+    if (n == "ERR") { *ptr = s.ERR; *len = 4; return 0; }
     if (n == "FY") { *ptr = s.FY; *len = 10; return 0; }
     if (n == "RM") { *ptr = s.RM; *len = 10; return 0; }
     if (n == "F_VX") { *ptr = s.F_VX; *len = 10; return 0; }

@@ -185,6 +185,10 @@ class Oracle:
         self.L.orc_residual_norms(self.h, er, err)
         return er, err
 
+    def step_norms(self):
+        """ER, ERR as the time loop evaluated them on its last print step (before U = U1)."""
+        return self.get("ER"), self.get("ERR")
+
     def force_visc(self):
         """FORCE_VISC on the current state -> (F_VX(10), F_VY(10), skin, edge mid x, press/82713.27)"""
         self.L.orc_force_visc(self.h)

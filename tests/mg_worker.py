@@ -24,12 +24,18 @@ def main():
     elif case == "channel_itlocal":
         glc = deck.load(meshgen.channel(nx=41, ny=13, ITLOCAL=50))
     elif case == "ale":
-        glc = deck.load(meshgen.ale_body(nt=48, nr=14))
+        glc = deck.load(meshgen.ale_body(nt=48, nr=14))            # too small for chunk-aligned ownership: round-off agreement
+    elif case == "ale_aligned":
+        glc = deck.load(meshgen.ale_body(nt=192, nr=96))           # 18 432 nodes: every rank owns >= 2 reduction chunks
+    elif case == "ale_visc_aligned":
+        glc = deck.load(meshgen.ale_body(nt=192, nr=96, FMU=1.8e-5, FK=0.0257, IPRINT=3))
+    elif case == "square_aligned":
+        glc = deck.load(meshgen.square_global(129, world, IPRINT=2))
     else:
         raise SystemExit("unknown case")
     g, part = make_rank_solver(glc, rank, world, local, dist)
     st = None
-    if case != "ale":
+    if not case.startswith("ale"):
         st = meshgen.density_bump(glc)
         g.set("U", st["U"][part.node_gid])
         for k in ("T", "VEL_X", "VEL_Y"):
@@ -39,8 +45,15 @@ def main():
     U = gather_owned(g, part, "U", 4, dist, glc.npoin)
     T = gather_owned(g, part, "T", 1, dist, glc.npoin)[:, 0]
     X = gather_owned(g, part, "X", 1, dist, glc.npoin)[:, 0]
+    P_ = gather_owned(g, part, "P", 1, dist, glc.npoin)[:, 0]
+    W_ = gather_owned(g, part, "W_X", 1, dist, glc.npoin)[:, 0]
     er, err = g.norms()
+    ser, serr = g.step_norms()
+    fx = np.concatenate([g.get("FX"), g.get("FY"), g.get("RM")])
+    fv = np.concatenate(g.force_visc()[:2]) if case == "ale_visc_aligned" else None
     dtmin, time = g.scalar("DTMIN"), g.scalar("TIME")
+    if case.endswith("aligned"):
+        assert part.red_aligned, "this case is sized for chunk-aligned ownership"
     if rank == 0:
         ref = Oracle(glc)
         if st:
@@ -49,7 +62,26 @@ def main():
                 ref.set(k, st[k])
         ref.step(steps)
         Ur, Tr, Xr = ref.get("U").reshape(-1, 4), ref.get("T"), ref.get("X")
-        if case == "ale":
+        if case.endswith("aligned"):
+            # chunk-aligned ownership: the inner products of biCG and the residual norms are the global canonical sums, so the
+            # moving-mesh run is bit-identical to the undivided one, mesh solve included
+            print(case, "diag: bicg", g.scalar("bicg_x"), ref.scalar("bicg_x"), g.scalar("bicg_y"), ref.scalar("bicg_y"), flush=True)
+            assert g.scalar("bicg_x") == ref.scalar("bicg_x") and g.scalar("bicg_y") == ref.scalar("bicg_y")
+            assert dtmin == ref.scalar("DTMIN") and time == ref.scalar("TIME")
+            for nm, a, b in (("U", U, Ur), ("T", T, Tr), ("X", X, Xr), ("P", P_, ref.get("P")), ("W_X", W_, ref.get("W_X"))):
+                assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), f"{nm} differs, max {np.max(np.abs(a - b))}"
+            ero, erro = ref.norms()
+            assert np.array_equal(err.view(np.uint64), erro.view(np.uint64)) and np.array_equal(er.view(np.uint64), ero.view(np.uint64))
+            if case == "square_aligned":   # norms of the last print step (before U = U1): the 8 canonical sums of run_norms
+                sero, serro = ref.step_norms()
+                assert np.array_equal(ser.view(np.uint64), sero.view(np.uint64)) and np.array_equal(serr.view(np.uint64), serro.view(np.uint64))
+            # body forces are per-rank sequential sums added across ranks (edge order within a rank kept): round-off
+            fxo = np.concatenate([ref.get("FX"), ref.get("FY"), ref.get("RM")])
+            assert np.allclose(fx, fxo, rtol=1e-12, atol=1e-12 * np.abs(fxo).max()), (fx, fxo)
+            if fv is not None:
+                fvo = np.concatenate(ref.force_visc()[:2])
+                assert np.allclose(fv, fvo, rtol=1e-12, atol=1e-12 * np.abs(fvo).max()), (fv, fvo)
+        elif case == "ale":
             # inner products are reduced per rank then summed: round-off level differences in the mesh solve
             print("ale diag: bicg", g.scalar("bicg_x"), ref.scalar("bicg_x"), g.scalar("bicg_y"), ref.scalar("bicg_y"),
                   "dX", np.max(np.abs(X - Xr)), "dU", np.max(np.abs(U - Ur) / np.abs(Ur).max(0)), "dt", dtmin, ref.scalar("DTMIN"), flush=True)

@@ -82,6 +82,59 @@ def test_strip_window_equals_global(nranks):
             assert np.array_equal(getattr(a.lc, f), getattr(b.lc, f)), f
 
 
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_chunk_aligned_ownership(nranks):
+    """Round 2: when every rank owns at least two reduction chunks, the ownership boundaries sit on multiples of 4096 in the
+    global node numbering (partition module docstring), the window generator and the global partitioner agree, every other
+    invariant of the partition still holds, and the rank-wise protocol of the canonical reduction -- chunk sums placed at
+    their global positions, summed with zeros, upper tree levels on every rank -- reproduces the undivided canonical sum
+    bit for bit."""
+    from oracle.orclib import lib as orclib
+
+    n = 129
+    glc = deck.load(meshgen.square_global(n, nranks))
+    inp0 = glc.inpoel.astype(np.int64) - 1
+    parts = [partition.build_local(glc, nranks, r) for r in range(nranks)]
+    B = [p.gid0 for p in parts] + [glc.npoin]
+    assert all(p.red_aligned for p in parts) and B[0] == 0 and all(b % partition.RED_CHUNK == 0 for b in B[:-1])
+    nat = partition.node_owner(inp0, np.searchsorted(partition.element_ranges(glc.nelem, nranks), np.arange(glc.nelem), side="right") - 1, glc.npoin)
+    rng = np.random.default_rng(7)
+    x, y = rng.standard_normal(glc.npoin), rng.standard_normal(glc.npoin)
+    L = orclib()
+    nchunk = (glc.npoin + 4095) // 4096
+    G = np.zeros(nchunk)
+    for r, p in enumerate(parts):
+        gid = p.node_gid
+        assert np.array_equal(gid[: p.n_owned], np.arange(B[r], B[r + 1]))          # contiguous, aligned
+        first_nat = np.flatnonzero(nat == r)[0]
+        assert abs(B[r] - first_nat) <= partition.RED_CHUNK // 2 or r == 0            # nearest multiple of the chunk
+        owner = np.searchsorted(np.array(B), np.arange(glc.npoin), side="right") - 1
+        need = np.flatnonzero((owner[inp0] == r).any(1))
+        assert np.array_equal(need, p.elem_gid)                                       # every element touching an owned node
+        assert np.array_equal(np.sort(np.concatenate([v for v in p.recv.values()])), np.arange(p.n_owned, p.lc.npoin))
+        w = partition.square_window(n, nranks, r)
+        b = partition.build_local(w[0], nranks, r, *w[1:])
+        assert b.red_aligned and b.gid0 == p.gid0 and b.npoin_global == glc.npoin
+        assert np.array_equal(p.node_gid, b.node_gid) and np.array_equal(p.elem_gid, b.elem_gid) and p.n_owned == b.n_owned
+        assert np.array_equal(p.lc.inpoel, b.lc.inpoel) and np.array_equal(p.lc.X.view(np.uint64), b.lc.X.view(np.uint64))
+        for s_ in p.neighbors:
+            assert np.array_equal(p.send.get(s_, []), b.send.get(s_, [])) and np.array_equal(p.recv.get(s_, []), b.recv.get(s_, []))
+        # this rank's first-level chunk sums over its owned prefix, at their global chunk positions
+        xl, yl = x[gid[: p.n_owned]], y[gid[: p.n_owned]]
+        for cidx in range((p.n_owned + 4095) // 4096):
+            lo, hi = 4096 * cidx, min(4096 * (cidx + 1), p.n_owned)
+            G[B[r] // 4096 + cidx] += L.orc_vecdot(hi - lo, np.ascontiguousarray(xl[lo:hi]), np.ascontiguousarray(yl[lo:hi]))
+    want = L.orc_vecdot(glc.npoin, x, y)
+    got = L.orc_canon_sum(nchunk, G)   # nchunk <= 4096: one more level of the same tree
+    assert np.float64(got).view(np.uint64) == np.float64(want).view(np.uint64)
+
+
+def test_small_meshes_keep_the_natural_ownership():
+    glc = deck.load(meshgen.square_global(9, 2))
+    assert not any(partition.build_local(glc, 2, r).red_aligned for r in range(2))
+    assert partition.square_window(9, 2, 0)[4] is None
+
+
 def test_every_rank_of_a_moving_mesh_case_is_flagged_moving():
     """The body sets of the ALE case end up on one rank only, but fluidStructure moves the mesh everywhere: LocalPart.moving
     (-> cfdb_set_option "ale": FUENTE and the mesh-velocity terms of ESTAB/deltat) must be set on every rank; fixed-mesh
