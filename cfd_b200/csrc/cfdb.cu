@@ -41,6 +41,20 @@ int build(cudaStream_t st, const int* inp, int nelem, int npoin, int* esup2, int
           int* npsup_out, int* rowptr, int** idx0_out, unsigned char* lpos, int* maxrow_out);
 }
 
+namespace {
+// eslot entries 3*e+local: file-order element ids -> internal positions
+__global__ void remap_slots(long n, const int* __restrict__ e2i, int* __restrict__ eslot) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int s = eslot[i], e = s / 3;
+    eslot[i] = 3 * e2i[e] + (s - 3 * e);
+}
+__global__ void remap_ids(int n, const int* __restrict__ e2i, int* __restrict__ ids) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && ids[i] >= 0) ids[i] = e2i[ids[i]];
+}
+}  // namespace
+
 static thread_local std::string g_err;
 static int fail(const std::string& m) {
     g_err = m;
@@ -87,11 +101,11 @@ struct DBuf {
 
 enum KernelId {
     K_DERIV, K_MASAS, K_NORMALES, K_DELTAT, K_DTLOGIC, K_DTL, K_ESTAB, K_CALCRHS, K_NODE, K_DOT, K_NORMS, K_SPMV,
-    K_VEC, K_FIXROWS, K_SCALAR, K_LAPLACE, K_TRANSF, K_MOVE, K_FORCES, K_GCL, K_LAYOUT, K_FILL, K_HALO, K_COUNT
+    K_VEC, K_FIXROWS, K_SCALAR, K_LAPLACE, K_TRANSF, K_MOVE, K_FORCES, K_GCL, K_LAYOUT, K_FILL, K_HALO, K_STAGE, K_COUNT
 };
 static const char* kKernelNames[K_COUNT] = {"deriv", "masas", "normales", "deltat", "dt_logic", "dtl", "estab",
                                             "calcrhs_elem", "node_update", "dot", "norms", "spmv", "vec", "fixrows",
-                                            "scalar", "laplace", "transf", "move_apply", "forces", "gcl", "layout", "fill", "halo"};
+                                            "scalar", "laplace", "transf", "move_apply", "forces", "gcl", "layout", "fill", "halo", "stage_fused"};
 
 struct cfdb_ctx {
     int device = 0;
@@ -104,6 +118,7 @@ struct cfdb_ctx {
     bool host_topo_valid = true;
     int npsup = 0;
     vector<int32_t> h_wall, h_wn_node, h_ilaux, h_fixidx_last;
+    vector<unsigned char> h_bcflag;
     int nnz = 0, maxrow = 0, nwn = 0, nb = 0, nmove = 0, nnmove = 0, nset = 0, nse = 0;
     bool ale = false;  // mesh can move (body sets present or W set by the caller; multi-rank: on ANY rank, see agree_on_ale)
     bool ale_agreed = false;
@@ -146,6 +161,18 @@ struct cfdb_ctx {
     int use_cuarto = 0, true_rk = 0;  // "next" rows N1 / N2, default off (reference behaviour)
     int fast = 0;                     // relaxed stage (FMA + atomic scatter), opt-in, NOT bit-exact
     bool u1_is_u = false;  // after U = U1 (ns2DComp.ALE.f90:277-281) the two arrays are one buffer
+    // fused RK stage (kernels: stage_fused.cuh; tiling: host_topology.h build_tiling).  The element arrays of the context
+    // are kept in INTERNAL (tile) order: i2e[p] = file-order element at internal position p, e2i its inverse (null: identity)
+    bool tiles_ok = false, perm_on = false, geo_dirty = true;
+    int ntiles = 0, nbnodes = 0, tile_ncw = 0;
+    double tile_interior = 0.0;
+    long Epad = 0;
+    k::TileGeom tgeom{};
+    size_t stage_smem = 0;
+    vector<int32_t> h_i2e;
+    DBuf<int> i2e, e2i, bnodes;
+    DBuf<unsigned char> TB;
+    DBuf<double> geo;
     // multi-GPU (one rank per context)
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
@@ -336,6 +363,7 @@ static int build_bc_tables(cfdb_ctx* c, const cfdb_bc* bc) {
             bvx.push_back(vx[n]); bvy.push_back(vy[n]); brho.push_back(rho[n]); bT.push_back(tf[n]);
         }
     c->nb = (int)bnode.size();
+    c->h_bcflag = flag;
     TRY(upload(c, c->bcflag, flag));
     TRY(upload(c, c->bc_node, bnode)); TRY(upload(c, c->bc_kind, bkind)); TRY(upload(c, c->bc_wslot, bw));
     TRY(upload(c, c->bc_vx, bvx)); TRY(upload(c, c->bc_vy, bvy)); TRY(upload(c, c->bc_rho, brho)); TRY(upload(c, c->bc_T, bT));
@@ -395,9 +423,87 @@ static int ensure_host_topology(cfdb_ctx* c) {
     CK(cudaMemcpyAsync(c->lap_idx.data(), c->d_lap_idx.p, (size_t)c->nnz * sizeof(int), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
     c->esup1.resize(3 * E);
+    if (c->perm_on)   // the device list holds internal element positions: back to the file's numbering
+        for (size_t k = 0; k < 3 * E; ++k) c->h_eslot[k] = 3 * c->h_i2e[c->h_eslot[k] / 3] + c->h_eslot[k] % 3;
     for (size_t k = 0; k < 3 * E; ++k) c->esup1[k] = c->h_eslot[k] / 3 + 1;
     for (auto& v : c->lap_idx) v += 1;   // host copy is 1-based like the reference's lap_idx
     c->host_topo_valid = true;
+    return 0;
+}
+
+// Tiles of the fused RK stage and the internal element order (host_topology.h: build_tiling).  Called at the end of
+// cfdb_create: the device topology has been built from the file-order connectivity (so every per-node list is in ascending
+// FILE-order element id, the reference's summation order); from here on the element arrays live in tile order.
+//   CFDB_NO_PERM=1   keep the file's element order (tiles = runs of consecutive elements)
+//   CFDB_TILE_TE=384 tile size (512 default; must be a multiple of 128, <= 512)
+static int build_stage_tiles(cfdb_ctx* c, const int32_t* inpoel, const double* X, const double* Y) {
+    const size_t E = c->nelem, P = c->npoin;
+    int TE = getenv("CFDB_TILE_TE") ? atoi(getenv("CFDB_TILE_TE")) : 512;
+    if (TE != 384 && TE != 512) return fail("CFDB_TILE_TE must be 384 or 512");
+    const bool permute = getenv("CFDB_NO_PERM") == nullptr;
+    // host copies of esup2 / eslot (file order)
+    vector<int32_t> esup2(P + 1), eslot(3 * E), esup1(3 * E);
+    if (c->host_topo_valid) {
+        esup2 = c->esup2; eslot = c->h_eslot; esup1 = c->esup1;
+    } else {
+        CK(cudaMemcpyAsync(esup2.data(), c->d_esup2.p, (P + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaMemcpyAsync(eslot.data(), c->eslot.p, 3 * E * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        for (size_t k = 0; k < 3 * E; ++k) esup1[k] = eslot[k] / 3 + 1;
+    }
+    topo::Tiling T;
+    topo::build_tiling(inpoel, c->nelem, c->npoin, X, Y, esup1, esup2, eslot, c->h_bcflag, TE, permute, T);
+    if (T.L.nint_max > 65535 || 12 * TE > 65535) return fail("tile too large for 16-bit slots");
+    c->ntiles = T.ntiles;
+    c->tile_ncw = TE / 32;
+    c->tile_interior = T.interior_fraction;
+    c->nbnodes = (int)T.bnodes.size();
+    c->Epad = (long)T.ntiles * TE;
+    TRY(upload(c, c->TB, T.blocks));
+    TRY(upload(c, c->bnodes, T.bnodes));
+    TRY(zero(c, c->geo, 7 * (size_t)c->Epad));
+    if (permute) {
+        c->h_i2e = T.i2e;
+        TRY(upload(c, c->i2e, T.i2e));
+        TRY(upload(c, c->e2i, T.e2i));
+        // connectivity into tile order; per-node element lists keep their (file-order ascending) sequence but name internal positions
+        DBuf<int> tmp;
+        TRY(tmp.alloc(3 * E));
+        for (int cpt = 0; cpt < 3; ++cpt)
+            LAUNCH(K_LAYOUT, k::perm_rows<int>, grid_for((long)E, 256), 256, (long)E, 1, c->i2e.p, c->inp.p + cpt * E, tmp.p + cpt * E);
+        CK(cudaMemcpyAsync(c->inp.p, tmp.p, 3 * E * sizeof(int), cudaMemcpyDeviceToDevice, c->st));
+        LAUNCH(K_LAYOUT, remap_slots, grid_for(3 * (long)E, 256), 256, 3 * (long)E, c->e2i.p, c->eslot.p);
+        if (c->nedges) LAUNCH(K_LAYOUT, remap_ids, grid_for(c->nedges, 128), 128, c->nedges, c->e2i.p, c->set_el.p);
+        CK(cudaStreamSynchronize(c->st));
+        tmp.release();
+        c->perm_on = true;
+    }
+    // ring-stage layout in shared memory
+    const topo::TileLayout& L = T.L;
+    k::TileGeom& G = c->tgeom;
+    auto up16 = [](int v) { return (v + 15) & ~15; };
+    auto up128 = [](int v) { return (v + 127) & ~127; };
+    G.TE = TE; G.ntn_max = L.ntn_max; G.nint_max = L.nint_max; G.nslot_max = L.nslot_max;
+    G.off_lnode = L.off_lnode; G.off_tnode = L.off_tnode; G.off_nptr = L.off_nptr; G.off_slots = L.off_slots; G.off_bcf = L.off_bcf;
+    G.tb_bytes = L.tb_bytes;
+    G.nfields = c->par.ITLOCAL != 0 ? 12 : 11;
+    G.st_static = 0;
+    G.st_stream = up128(L.tb_bytes);
+    G.st_u = G.st_stream + G.nfields * TE * 8;
+    G.st_t = G.st_u + L.ntn_max * 32;
+    G.st_m = G.st_t + up16(L.ntn_max * 8);
+    G.st_g = G.st_m + up16(L.nint_max * 8);
+    G.stage_bytes = up128(G.st_g + up16(L.nint_max * 8));
+    G.off_c = 128;
+    G.off_stage0 = up128(G.off_c + 12 * TE * 8);
+    c->stage_smem = (size_t)G.off_stage0 + 2 * (size_t)G.stage_bytes;
+    int smem_max = 0;
+    CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+    c->tiles_ok = c->stage_smem <= (size_t)smem_max;   // else: the two-kernel stage (very high valence / odd meshes)
+    c->geo_dirty = true;
+    if (getenv("CFDB_VERBOSE"))
+        fprintf(stderr, "[cfdb_create] tiles: TE %d, %d tiles, interior nodes %.3f, nodes/tile <= %d (interior <= %d), block %d B, smem %zu B%s\n",
+                TE, c->ntiles, c->tile_interior, L.ntn_max, L.nint_max, L.tb_bytes, c->stage_smem, c->tiles_ok ? "" : " (too large: fused stage off)");
     return 0;
 }
 
@@ -503,8 +609,9 @@ extern "C" int cfdb_create(cfdb_ctx** out, const cfdb_params* par, int32_t npoin
                     &c->dypos, &c->pos_aux, &c->W_x_old, &c->W_y_old, &c->tmpA, &c->tmpB, &c->tmpC, &c->by2, &c->pos_aux2})
         B(zero(c, *d, P));
     for (auto* d : {&c->U, &c->U1, &c->RHS, &c->RHS1, &c->RHS2, &c->RHS3, &c->UN}) B(zero(c, *d, 4 * P));
+    // +1024: the fused stage streams whole tiles (<= 512 elements) of SHOC, T_SUGN1-3 and DTL with bulk copies
     for (auto* d : {&c->area, &c->HH, &c->HHX, &c->HHY, &c->SHOC, &c->TS1, &c->TS2, &c->TS3, &c->DT, &c->DTL, &c->area_old})
-        B(zero(c, *d, E));
+        B(zero(c, *d, E + 1024));
     B(zero(c, c->dNx, 3 * E));
     B(zero(c, c->dNy, 3 * E));
     B(zero(c, c->EC, 12 * E));
@@ -523,6 +630,9 @@ extern "C" int cfdb_create(cfdb_ctx** out, const cfdb_params* par, int32_t npoin
     if (verbose) cudaStreamSynchronize(c->st);
     lap("BC tables");
     if (c->ale) B(zero(c, c->FC, 12 * E));
+    B(build_stage_tiles(c, inpoel, X, Y));
+    if (verbose) cudaStreamSynchronize(c->st);
+    lap("stage tiles + element order");
     if (cudaMalloc(&c->sc, sizeof(k::Scal)) != cudaSuccess) return bail(fail("cudaMalloc Scal failed"));
     if (cudaMemsetAsync(c->sc, 0, sizeof(k::Scal), c->st) != cudaSuccess) return bail(fail("memset Scal failed"));
     if (cudaMallocHost(&c->h_sc, sizeof(k::Scal)) != cudaSuccess) return bail(fail("cudaMallocHost failed"));
@@ -546,6 +656,7 @@ extern "C" void cfdb_destroy(cfdb_ctx* c) {
         d->release();
     c->lpos.release();
     c->bcflag.release();
+    c->i2e.release(); c->e2i.release(); c->bnodes.release(); c->TB.release(); c->geo.release();
     c->isfix.release();
     c->bp2.release(); c->by2.release(); c->pos_aux2.release();
     for (auto* d : {&c->X, &c->Y, &c->X1, &c->Y1, &c->area, &c->HH, &c->HHX, &c->HHY, &c->dNx, &c->dNy, &c->M, &c->U, &c->U1,
@@ -754,6 +865,7 @@ extern "C" int cfdb_geometry(cfdb_ctx* c, int32_t moving_step) {
     if (gcl) CK(cudaMemcpyAsync(c->area_old.p, c->area.p, E * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
     TRY(run_normales(c));
     TRY(run_deriv(c));
+    c->geo_dirty = true;
     TRY(run_masas(c));
     if (gcl) {
         TRY(run_gcl(c, &c->sc->DTMIN, 0.0));
@@ -872,6 +984,51 @@ static int run_node(cfdb_ctx* c, cudaStream_t st, bool ale, bool update, double 
     return 0;
 }
 
+// geo[7][Epad] (the fused stage's copy of dNx, dNy, area with a tile-aligned component stride) follows the geometry
+static int refresh_geo(cfdb_ctx* c) {
+    if (!c->tiles_ok || !c->geo_dirty) return 0;
+    LAUNCH(K_LAYOUT, k::pack_geo, grid_for(c->nelem, 256), 256, (long)c->nelem, c->Epad, c->dNx.p, c->dNy.p, c->area.p, c->geo.p);
+    c->geo_dirty = false;
+    return 0;
+}
+
+// fused tile stage (stage_fused.cuh) + node_update over the tile-boundary nodes
+static bool fused_eligible(const cfdb_ctx* c) {
+    static const bool off = getenv("CFDB_NO_FUSED") != nullptr;
+    return !off && c->tiles_ok && !c->ale && !c->use_cuarto && !c->fast && !c->theta_nonzero;
+}
+static int run_stage_fused(cfdb_ctx* c, const k::Gas& g, const double* dtl_arr, const double* dtl_sc, double rk_fact) {
+    const bool visc = g.mu_ref > 2.2250738585072014e-308;
+    k::StageArgs A{};
+    A.ntiles = c->ntiles; A.TB = c->TB.p; A.geo = c->geo.p; A.Epad = c->Epad;
+    A.shoc = c->SHOC.p; A.ts1 = c->TS1.p; A.ts2 = c->TS2.p; A.ts3 = c->TS3.p; A.dtl_arr = dtl_arr; A.dtl_sc = dtl_sc;
+    A.Usrc = c->Usrc ? c->Usrc : c->U.p; A.U = c->U.p; A.T = c->T.p; A.M = c->M.p; A.GAMM = c->GAMM.p; A.WXa = c->W_X.p; A.WYa = c->W_Y.p;
+    A.bc = bctab(c); A.rk_fact = rk_fact; A.FR = c->par.FR; A.g = g;
+    A.EC = c->EC.p; A.U1 = c->U1.p; A.RHS = c->RHS.p; A.RHO = c->RHO.p; A.VELX = c->VEL_X.p; A.VELY = c->VEL_Y.p; A.Ea = c->E.p;
+    A.Pa = c->P.p; A.Ta = c->T.p; A.RMACH = c->RMACH.p;
+    k::TileGeom G = c->tgeom;
+    G.nfields = dtl_arr ? 12 : 11;
+    if (G.nfields > c->tgeom.nfields) return fail("run_stage_fused: stage layout was sized without a local time step array");
+    void (*kern)(const k::TileGeom, const k::StageArgs) = nullptr;
+    if (c->tile_ncw == 16) kern = visc ? k::stage_fused<true, 16, 120, 24> : k::stage_fused<false, 16, 120, 24>;
+    else kern = visc ? k::stage_fused<true, 12, 152, 56> : k::stage_fused<false, 12, 152, 56>;
+    static std::map<const void*, bool> attr_done;
+    if (!attr_done[(const void*)kern]) {
+        CK(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->stage_smem));
+        attr_done[(const void*)kern] = true;
+    }
+    static int nsm = 0;
+    if (!nsm) CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device));
+    const int grid = std::min(c->ntiles, nsm), block = (c->tile_ncw + 4) * 32;
+    cudaEvent_t _a = nullptr, _b = nullptr;
+    TRY(prof_begin(c, c->st, K_STAGE, &_a, &_b));
+    kern<<<grid, block, c->stage_smem, c->st>>>(G, A);
+    CK(cudaGetLastError());
+    TRY(prof_end(c, c->st, K_STAGE, _a, _b));
+    TRY(run_node(c, c->st, false, true, rk_fact, 0, c->nbnodes, c->bnodes.p));
+    return 0;
+}
+
 extern "C" int cfdb_rk_stage(cfdb_ctx* c, int32_t irk) {
     CK(cudaSetDevice(c->device));
     const cfdb_params& p = c->par;
@@ -932,6 +1089,12 @@ extern "C" int cfdb_rk_stage(cfdb_ctx* c, int32_t irk) {
                                              c->RMACH.p))
             return fail("node_update_rhs launch failed");
         TRY(prof_end(c, c->st, K_NODE, _a, _b));
+        TRY(halo_state(c));
+        return 0;
+    }
+    if (fused_eligible(c)) {
+        TRY(refresh_geo(c));
+        TRY(run_stage_fused(c, g, dtl_arr, &c->sc->DTMIN, RK_FACT));
         TRY(halo_state(c));
         return 0;
     }
@@ -1278,9 +1441,11 @@ static int step_graph(cfdb_ctx* c) {
 static int step_once(cfdb_ctx* c) {
     const cfdb_params& p = c->par;
     TRY(agree_on_ale(c));
+    if (fused_eligible(c)) TRY(refresh_geo(c));   // outside the captured step
     c->h_iter += 1;
     if (graph_eligible(c)) TRY(step_graph(c));
     else TRY(step_body(c));
+    c->u1_is_u = false;   // the RK stages have rewritten U1 (a replayed graph does not run cfdb_rk_stage's host code)
     c->iterprint += 1;
     if (c->iterprint == p.IPRINT || c->h_iter == p.MAXITER) {  // :186-197
         TRY(run_norms(c));
@@ -1343,6 +1508,61 @@ extern "C" int cfdb_profile_get(cfdb_ctx* c, const char* kernel, double* total_m
 extern "C" int64_t cfdb_launch_count(cfdb_ctx* c) { return c->launches; }
 
 // ---------------------------------------------------------------------------------------------
+// host <-> device transfers of nodal and element arrays
+static int up_plain(cfdb_ctx* c, double* dev, const double* h, size_t n) {
+    if (n) CK(cudaMemcpyAsync(dev, h, n * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    return 0;
+}
+static int down_plain(cfdb_ctx* c, const double* dev, double* h, size_t n) {
+    if (n) CK(cudaMemcpyAsync(h, dev, n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    return 0;
+}
+// Element arrays cross the ABI in the file's element order and live on the device in the internal (tile) order.
+// scratch: EC is free between calls (12 doubles per element); an array that IS EC goes through a temporary.
+static int up_elem(cfdb_ctx* c, double* dev, const double* h, int w = 1) {   // dev[p][q] = h[i2e[p]][q]
+    const long E = c->nelem;
+    if (!c->perm_on) return up_plain(c, dev, h, (size_t)w * E);
+    double* stage = c->EC.p;
+    DBuf<double> tmp;
+    if (dev == c->EC.p || w > 12) { TRY(tmp.alloc((size_t)w * E)); stage = tmp.p; }
+    CK(cudaMemcpyAsync(stage, h, (size_t)w * E * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    LAUNCH(K_LAYOUT, k::perm_rows<double>, grid_for(w * E, 256), 256, E, w, c->i2e.p, stage, dev);
+    if (tmp.p) { CK(cudaStreamSynchronize(c->st)); tmp.release(); }
+    return 0;
+}
+static int down_elem(cfdb_ctx* c, const double* dev, double* h, int w = 1) {   // h[e][q] = dev[e2i[e]][q]
+    const long E = c->nelem;
+    if (!c->perm_on) return down_plain(c, dev, h, (size_t)w * E);
+    double* stage = c->EC.p;
+    DBuf<double> tmp;
+    if (dev == c->EC.p || w > 12) { TRY(tmp.alloc((size_t)w * E)); stage = tmp.p; }
+    LAUNCH(K_LAYOUT, k::perm_rows<double>, grid_for(w * E, 256), 256, E, w, c->e2i.p, dev, stage);
+    CK(cudaMemcpyAsync(h, stage, (size_t)w * E * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));   // the scratch buffer is reused by the next transfer
+    if (tmp.p) tmp.release();
+    return 0;
+}
+static int up_soa3(cfdb_ctx* c, double* dev, const double* h) {  // (3,E) host, file order -> [3][E] device, internal order
+    const long E = c->nelem;
+    TRY(c->EC.alloc(12 * (size_t)E));
+    double* stage = c->EC.p;
+    CK(cudaMemcpyAsync(stage, h, 3 * E * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    if (c->perm_on) LAUNCH(K_LAYOUT, k::aos3_to_soa_perm, grid_for(3 * E, 256), 256, E, c->i2e.p, stage, dev);
+    else LAUNCH(K_LAYOUT, k::aos3_to_soa, grid_for(3 * E, 256), 256, E, stage, dev);
+    c->geo_dirty = true;   // dNx / dNy are the only (3,E) arrays
+    return 0;
+}
+static int down_soa3(cfdb_ctx* c, const double* dev, double* h) {
+    const long E = c->nelem;
+    double* stage = c->EC.p;
+    if (c->perm_on) LAUNCH(K_LAYOUT, k::soa_to_aos3_perm, grid_for(3 * E, 256), 256, E, c->i2e.p, dev, stage);
+    else LAUNCH(K_LAYOUT, k::soa_to_aos3, grid_for(3 * E, 256), 256, E, dev, stage);
+    CK(cudaMemcpyAsync(h, stage, 3 * E * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // field access
 struct Field;
 static bool find_field(cfdb_ctx* c, const std::string& n, Field& f);
@@ -1351,27 +1571,30 @@ struct Field {
     const void* host = nullptr;   // or host-resident integer artefact
     int64_t count = 0;
     int kind = 0;                 // 0 f64 plain, 1 f64 (3,E) stored [3][E], 2 int32 host (read-only), 3 computed
+    int ew = 0;                   // > 0: element-indexed, ew doubles per element, stored in the internal element order
 };
 static bool find_field(cfdb_ctx* c, const std::string& n, Field& f) {
     const int64_t P = c->npoin, E = c->nelem;
 #define FD(name, buf, cnt) if (n == name) { f.dev = c->buf.p; f.count = (cnt); f.kind = 0; return true; }
+#define FE(name, buf, w) if (n == name) { f.dev = c->buf.p; f.count = (w) * E; f.kind = 0; f.ew = (w); return true; }
 #define FS(name, buf) if (n == name) { f.dev = c->buf.p; f.count = 3 * E; f.kind = 1; return true; }
 #define FH(name, vec) if (n == name) { f.host = c->vec.data(); f.count = (int64_t)c->vec.size(); f.kind = 2; return true; }
-    FD("X", X, P) FD("Y", Y, P) FD("X1", X1, P) FD("Y1", Y1, P) FD("M", M, P) FD("area", area, E) FD("HH", HH, E)
-    FD("HHX", HHX, E) FD("HHY", HHY, E) FS("dNx", dNx) FS("dNy", dNy)
+    FD("X", X, P) FD("Y", Y, P) FD("X1", X1, P) FD("Y1", Y1, P) FD("M", M, P) FE("area", area, 1) FE("HH", HH, 1)
+    FE("HHX", HHX, 1) FE("HHY", HHY, 1) FS("dNx", dNx) FS("dNy", dNy)
     FD("U", U, 4 * P) FD("U1", U1, 4 * P) FD("RHS", RHS, 4 * P) FD("UN", UN, 4 * P)
     FD("RHS1", RHS1, 4 * P) FD("RHS2", RHS2, 4 * P) FD("RHS3", RHS3, 4 * P)
     FD("VEL_X", VEL_X, P) FD("VEL_Y", VEL_Y, P) FD("W_X", W_X, P) FD("W_Y", W_Y, P) FD("P", P, P) FD("T", T, P)
     FD("RHO", RHO, P) FD("E", E, P) FD("RMACH", RMACH, P) FD("GAMM", GAMM, P)
-    FD("SHOC", SHOC, E) FD("T_SUGN1", TS1, E) FD("T_SUGN2", TS2, E) FD("T_SUGN3", TS3, E) FD("DT", DT, E)
+    FE("SHOC", SHOC, 1) FE("T_SUGN1", TS1, 1) FE("T_SUGN2", TS2, 1) FE("T_SUGN3", TS3, 1) FE("DT", DT, 1)
     FD("lap_sparse", lap_sparse, c->nnz) FD("lap_diag", lap_diag, P) FD("xpos", xpos, P) FD("ypos", ypos, P)
     FD("dxpos", dxpos, P) FD("dypos", dypos, P) FD("W_x_old", W_x_old, P) FD("W_y_old", W_y_old, P)
-    FD("area_old", area_old, E) FD("EC", EC, 12 * E)
+    FE("area_old", area_old, 1) FE("EC", EC, 12)
     if (n == "esup1" || n == "esup2" || n == "psup1" || n == "psup2" || n == "lap_idx" || n == "lap_rowptr")
         if (ensure_host_topology(c)) return false;
     FH("inpoel", h_inpoel) FH("esup1", esup1) FH("esup2", esup2) FH("psup1", psup1) FH("psup2", psup2)
     FH("lap_idx", lap_idx) FH("lap_rowptr", lap_rowptr) FH("ilaux", h_ilaux)
 #undef FD
+#undef FE
 #undef FS
 #undef FH
     if (n == "FX") { f.dev = c->sc->FX; f.count = 10; f.kind = 0; return true; }
@@ -1413,25 +1636,21 @@ extern "C" int cfdb_get(cfdb_ctx* c, const char* name, void* host, int64_t count
         memcpy(host, f.host, f.count * sizeof(int32_t));
         return 0;
     }
+    if (f.kind == 0 && f.ew > 0) {
+        TRY(down_elem(c, (const double*)f.dev, (double*)host, f.ew));
+        CK(cudaStreamSynchronize(c->st));
+        return 0;
+    }
     if (f.kind == 0) {
         if (f.count) CK(cudaMemcpyAsync(host, f.dev, f.count * sizeof(double), cudaMemcpyDeviceToHost, c->st));
         CK(cudaStreamSynchronize(c->st));
         return 0;
     }
-    if (f.kind == 1) {
-        const int64_t E = c->nelem;
-        vector<double> tmp(3 * E);
-        CK(cudaMemcpyAsync(tmp.data(), f.dev, 3 * E * sizeof(double), cudaMemcpyDeviceToHost, c->st));
-        CK(cudaStreamSynchronize(c->st));
-        double* o = (double*)host;
-        for (int64_t e = 0; e < E; ++e)
-            for (int i = 0; i < 3; ++i) o[3 * e + i] = tmp[i * E + e];
-        return 0;
-    }
+    if (f.kind == 1) return down_soa3(c, (const double*)f.dev, (double*)host);
     if (n == "DTL") {  // ns2DComp.ALE.f90:159-164
         if (count < c->nelem) return fail("cfdb_get: host buffer too small for DTL");
         if (c->par.ITLOCAL != 0) {
-            CK(cudaMemcpyAsync(host, c->DTL.p, c->nelem * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+            TRY(down_elem(c, c->DTL.p, (double*)host));
             CK(cudaStreamSynchronize(c->st));
         } else {
             TRY(read_scal(c));
@@ -1466,6 +1685,12 @@ extern "C" int cfdb_set(cfdb_ctx* c, const char* name, const void* host, int64_t
     if (!find_field(c, n, f)) return fail("cfdb_set: unknown field " + n);
     if (f.kind >= 2 || n == "dxpos" || n == "dypos") return fail("cfdb_set: field " + n + " is read-only");
     if (count != f.count) return fail("cfdb_set: wrong element count for " + n);
+    if (f.kind == 0 && f.ew > 0) {
+        TRY(up_elem(c, (double*)f.dev, (const double*)host, f.ew));
+        CK(cudaStreamSynchronize(c->st));
+        if (n == "area") c->geo_dirty = true;
+        return 0;
+    }
     if (f.kind == 0) {
         if (f.count) CK(cudaMemcpyAsync(f.dev, host, f.count * sizeof(double), cudaMemcpyHostToDevice, c->st));
         CK(cudaStreamSynchronize(c->st));
@@ -1481,12 +1706,7 @@ extern "C" int cfdb_set(cfdb_ctx* c, const char* name, const void* host, int64_t
         }
         return 0;
     }
-    const int64_t E = c->nelem;
-    vector<double> tmp(3 * E);
-    const double* in = (const double*)host;
-    for (int64_t e = 0; e < E; ++e)
-        for (int i = 0; i < 3; ++i) tmp[i * E + e] = in[3 * e + i];
-    CK(cudaMemcpyAsync(f.dev, tmp.data(), 3 * E * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    TRY(up_soa3(c, (double*)f.dev, (const double*)host));
     CK(cudaStreamSynchronize(c->st));
     return 0;
 }
@@ -1506,6 +1726,8 @@ extern "C" int cfdb_get_scalar(cfdb_ctx* c, const char* name, double* v) {
     else if (n == "FX1") *v = s.FX[0];
     else if (n == "FY1") *v = s.FY[0];
     else if (n == "RM1") *v = s.RM[0];
+    else if (n == "tile_interior") *v = c->tiles_ok ? c->tile_interior : 0.0;
+    else if (n == "graph_replays") *v = (double)c->graph_replays;
     else if (n == "n_m") {
         vector<int> wv(c->nwn);
         if (c->nwn) CK(cudaMemcpy(wv.data(), c->wn_valid.p, c->nwn * sizeof(int), cudaMemcpyDeviceToHost));
@@ -1538,30 +1760,6 @@ static int check_mesh(cfdb_ctx* c, int32_t nelem, int32_t npoin, const char* who
         return fail(std::string(who) + ": nelem/npoin differ from the connectivity this context was created with");
     return 0;
 }
-static int up_plain(cfdb_ctx* c, double* dev, const double* h, size_t n) {
-    if (n) CK(cudaMemcpyAsync(dev, h, n * sizeof(double), cudaMemcpyHostToDevice, c->st));
-    return 0;
-}
-static int up_soa3(cfdb_ctx* c, double* dev, const double* h) {  // (3,E) host -> [3][E] device, via tmp staging
-    const long E = c->nelem;
-    TRY(c->EC.alloc(12 * (size_t)E));
-    double* stage = c->EC.p;  // EC is free between calls
-    CK(cudaMemcpyAsync(stage, h, 3 * E * sizeof(double), cudaMemcpyHostToDevice, c->st));
-    LAUNCH(K_LAYOUT, k::aos3_to_soa, grid_for(3 * E, 256), 256, E, stage, dev);
-    return 0;
-}
-static int down_soa3(cfdb_ctx* c, const double* dev, double* h) {
-    const long E = c->nelem;
-    double* stage = c->EC.p;
-    LAUNCH(K_LAYOUT, k::soa_to_aos3, grid_for(3 * E, 256), 256, E, dev, stage);
-    CK(cudaMemcpyAsync(h, stage, 3 * E * sizeof(double), cudaMemcpyDeviceToHost, c->st));
-    return 0;
-}
-static int down_plain(cfdb_ctx* c, const double* dev, double* h, size_t n) {
-    if (n) CK(cudaMemcpyAsync(h, dev, n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
-    return 0;
-}
-
 extern "C" int cfdb_calcrhs(cfdb_ctx* c, double* rhs, const double* U, const double* theta, const double* T,
                             const double* dNx, const double* dNy, const double* area, const double* shoc,
                             const double* dtl, const double* ts1, const double* ts2, const double* ts3,
@@ -1576,12 +1774,12 @@ extern "C" int cfdb_calcrhs(cfdb_ctx* c, double* rhs, const double* U, const dou
     TRY(up_plain(c, c->U.p, U, 4 * P));
     TRY(up_plain(c, c->UN.p, theta, 4 * P));
     TRY(up_plain(c, c->T.p, T, P));
-    TRY(up_plain(c, c->area.p, area, E));
-    TRY(up_plain(c, c->SHOC.p, shoc, E));
-    TRY(up_plain(c, c->DTL.p, dtl, E));
-    TRY(up_plain(c, c->TS1.p, ts1, E));
-    TRY(up_plain(c, c->TS2.p, ts2, E));
-    TRY(up_plain(c, c->TS3.p, ts3, E));
+    TRY(up_elem(c, c->area.p, area)); c->geo_dirty = true;
+    TRY(up_elem(c, c->SHOC.p, shoc));
+    TRY(up_elem(c, c->DTL.p, dtl));
+    TRY(up_elem(c, c->TS1.p, ts1));
+    TRY(up_elem(c, c->TS2.p, ts2));
+    TRY(up_elem(c, c->TS3.p, ts3));
     c->theta_nonzero = true;
     c->epoch++;
     k::Gas g{Cv, lambda_ref, mu_ref, gamma0, T_inf, cte};
@@ -1609,8 +1807,8 @@ extern "C" int cfdb_fuente(cfdb_ctx* c, double* rhs, const double* U, const doub
     TRY(up_plain(c, c->U.p, U, 4 * P));
     TRY(up_plain(c, c->W_X.p, w_x, P));
     TRY(up_plain(c, c->W_Y.p, w_y, P));
-    TRY(up_plain(c, c->area.p, area, E));
-    TRY(up_plain(c, c->DTL.p, dtl, E));
+    TRY(up_elem(c, c->area.p, area)); c->geo_dirty = true;
+    TRY(up_elem(c, c->DTL.p, dtl));
     k::Gas g{1.0, 0.0, 0.0, 1.4, 1.0, 1.0};
     // the ALE instantiation writes FC (FUENTE) next to EC (calcRHS, ignored here)
     TRY(run_calcrhs_elem(c, g, false, true, c->DTL.p, nullptr));
@@ -1629,7 +1827,7 @@ extern "C" int cfdb_deltat(cfdb_ctx* c, double* dtmin, double* dt, const int32_t
     TRY(check_mesh(c, nelem, npoin, "cfdb_deltat"));
     (void)inpoel; (void)FR; (void)GAMA;  // VC = sqrt(GAMA*FR*T) is dead in the reference (subrutinas.f90:179)
     const size_t P = npoin, E = nelem;
-    TRY(up_plain(c, c->area.p, area, E));
+    TRY(up_elem(c, c->area.p, area)); c->geo_dirty = true;
     TRY(up_plain(c, c->T.p, T, P));
     TRY(up_plain(c, c->VEL_X.p, vel_x, P));
     TRY(up_plain(c, c->VEL_Y.p, vel_y, P));
@@ -1640,7 +1838,7 @@ extern "C" int cfdb_deltat(cfdb_ctx* c, double* dtmin, double* dt, const int32_t
     LAUNCH(K_DELTAT, k::deltat<true>, grid_for(nelem, 256), 256, nelem, c->inp.p, c->area.p, c->T.p, c->VEL_X.p,
            c->VEL_Y.p, c->W_X.p, c->W_Y.p, FSAFE, T_inf, c->DT.p, c->sc);
     LAUNCH(K_DTL, k::dtl_blend, grid_for(nelem, 256), 256, nelem, c->DT.p, c->DTL.p, c->sc, 0);
-    TRY(down_plain(c, c->DT.p, dt, E));
+    TRY(down_elem(c, c->DT.p, dt));
     TRY(read_scal(c));
     *dtmin = c->h_sc->dtmin_acc;
     return 0;
@@ -1668,10 +1866,10 @@ extern "C" int cfdb_estab(cfdb_ctx* c, const double* U, const double* T, const d
     LAUNCH(K_ESTAB, k::estab<3>, grid_for(nelem, 256), 256, nelem, c->inp.p, c->U.p, c->T.p, c->VEL_X.p, c->VEL_Y.p, c->W_X.p,
            c->W_Y.p, c->GAMM.p, c->dNx.p, c->dNy.p, FR, &c->sc->red[15], RHOINF, TINF, c->SHOC.p, c->TS1.p, c->TS2.p,
            c->TS3.p);
-    TRY(down_plain(c, c->SHOC.p, shoc, E));
-    TRY(down_plain(c, c->TS1.p, ts1, E));
-    TRY(down_plain(c, c->TS2.p, ts2, E));
-    TRY(down_plain(c, c->TS3.p, ts3, E));
+    TRY(down_elem(c, c->SHOC.p, shoc));
+    TRY(down_elem(c, c->TS1.p, ts1));
+    TRY(down_elem(c, c->TS2.p, ts2));
+    TRY(down_elem(c, c->TS3.p, ts3));
     CK(cudaStreamSynchronize(c->st));
     return 0;
 }
@@ -1686,10 +1884,10 @@ extern "C" int cfdb_deriv(cfdb_ctx* c, const double* X, const double* Y, const i
     TRY(up_plain(c, c->X.p, X, P));
     TRY(up_plain(c, c->Y.p, Y, P));
     TRY(run_deriv(c));
-    TRY(down_plain(c, c->area.p, area, E));
-    TRY(down_plain(c, c->HH.p, HH, E));
-    TRY(down_plain(c, c->HHX.p, HHX, E));
-    TRY(down_plain(c, c->HHY.p, HHY, E));
+    TRY(down_elem(c, c->area.p, area));
+    TRY(down_elem(c, c->HH.p, HH));
+    TRY(down_elem(c, c->HHX.p, HHX));
+    TRY(down_elem(c, c->HHY.p, HHY));
     TRY(down_soa3(c, c->dNx.p, dNx));
     CK(cudaStreamSynchronize(c->st));
     TRY(down_soa3(c, c->dNy.p, dNy));
@@ -1702,7 +1900,7 @@ extern "C" int cfdb_masas(cfdb_ctx* c, const double* area, const int32_t* inpoel
     CK(cudaSetDevice(c->device));
     TRY(check_mesh(c, nelem, npoin, "cfdb_masas"));
     (void)inpoel;
-    TRY(up_plain(c, c->area.p, area, nelem));
+    TRY(up_elem(c, c->area.p, area)); c->geo_dirty = true;
     TRY(run_masas(c));
     TRY(down_plain(c, c->M.p, M, npoin));
     CK(cudaStreamSynchronize(c->st));
@@ -1839,8 +2037,8 @@ extern "C" int cfdb_gcl_main(cfdb_ctx* c, double* M, const double* W_x, const do
     TRY(up_plain(c, c->M.p, M, npoin));
     TRY(up_plain(c, c->W_X.p, W_x, npoin));
     TRY(up_plain(c, c->W_x_old.p, W_x_old, npoin));
-    TRY(up_plain(c, c->area.p, area, nelem));
-    TRY(up_plain(c, c->area_old.p, area_old, nelem));
+    TRY(up_elem(c, c->area.p, area)); c->geo_dirty = true;
+    TRY(up_elem(c, c->area_old.p, area_old));
     TRY(run_gcl(c, nullptr, dt));
     TRY(down_plain(c, c->M.p, M, npoin));
     CK(cudaStreamSynchronize(c->st));

@@ -86,17 +86,38 @@ inline void build_lap_pos(const int32_t* inpoel, int npoin, const vector<int32_t
     }
 }
 
-// Tiling for the fused RK stage: elements are grouped into spatially compact tiles of `tile` elements (Morton order
-// of the centroids, cut every `tile` elements; ids ascending inside a tile so a warp reads runs of consecutive
-// elements).  A node is INTERIOR to a tile when every element touching it belongs to that tile; all other nodes
-// (and nodes without elements) are tile-boundary nodes.
+// ---------------------------------------------------------------------------------------------------------------------
+// Tiling for the fused RK stage (kernels.cuh: stage_fused).
+//
+// Element order.  The library keeps its element arrays in an INTERNAL order: the elements sorted by the Morton code of
+// their centroids (ties by original id), cut into tiles of TE consecutive elements.  A tile is then a compact patch of the
+// mesh whatever numbering the mesh file uses, and everything the stage kernel streams per tile (connectivity, geometry,
+// stabilisation parameters) is one contiguous run per array -- a handful of bulk copies.  i2e[pos] = original element at
+// internal position pos, e2i = inverse.  The C ABI keeps speaking the file's numbering (cfdb.cu permutes at get/set).
+//
+// Nodes keep their numbering.  A node is INTERIOR to tile t when every element touching it lies in t (~80 % of the nodes at
+// TE = 512): its ordered sum and its nodal update are finished inside the tile's CTA from shared memory.  All other nodes
+// (shared by two or more tiles, or touched by no element) are tile-BOUNDARY nodes: their contributions go through the
+// staging buffer EC and node_update runs over the list `bnodes`.
+//
+// Per tile one static block of tb_bytes (TileLayout gives the offsets; every section starts on a 16-byte boundary):
+//   header  int32[4]           ne (elements in the tile), ntn (nodes touched), nint (interior nodes), 0
+//   lnode   uint16[3][TE]      tile-local index of each element vertex
+//   tnode   int32[ntn_max]     node id of each tile-local index: the nint interior nodes first (ascending), then the others
+//   nptr    uint16[nint_max+1] CSR over `slots` for the interior nodes
+//   slots   uint16[nslot_max]  contributions of each interior node in ascending ORIGINAL element order (the reference's
+//                              1-thread summation order); value = (4*local_vertex)*TE + position in tile, i.e. the index
+//                              of equation 0 of that contribution in the shared-memory array C[12][TE]
+//   bcf     uint8[nint_max]    bcflag of the interior nodes
+struct TileLayout {
+    int TE = 0, ntn_max = 0, nint_max = 0, nslot_max = 0;
+    int off_lnode = 0, off_tnode = 0, off_nptr = 0, off_slots = 0, off_bcf = 0, tb_bytes = 0;
+};
 struct Tiling {
+    TileLayout L;
     int ntiles = 0;
-    vector<int32_t> tile_elems;    // ntiles*tile, 0-based element ids, -1 padding
-    vector<uint8_t> ebmask;        // per tile position: bit n set when local node n is a tile-boundary node
-    vector<int32_t> tnode_ptr;     // ntiles+1
-    vector<int32_t> tnodes;        // interior nodes of each tile, ascending
-    vector<uint16_t> tslot;        // per esup entry (original order): 3*position-in-tile + local node
+    vector<int32_t> i2e, e2i;      // 0-based
+    vector<uint8_t> blocks;        // ntiles * L.tb_bytes
     vector<int32_t> bnodes;        // tile-boundary nodes, ascending
     double interior_fraction = 0;
 };
@@ -111,91 +132,126 @@ inline uint32_t morton16(uint32_t x, uint32_t y) {
     };
     return spread(x) | (spread(y) << 1);
 }
+// inpoel: (3,nelem) 1-based, original order; esup1 (1-based original element ids) / esup2 / eslot (3*(e-1)+local) in the
+// reference's order (ascending element id per node); bcflag[npoin]
 inline void build_tiling(const int32_t* inpoel, int nelem, int npoin, const double* X, const double* Y,
-                         const vector<int32_t>& esup1, const vector<int32_t>& esup2, const vector<int32_t>& eslot, int tile,
-                         Tiling& T) {
-    double x0 = X[0], x1 = X[0], y0 = Y[0], y1 = Y[0];
-    for (int n = 1; n < npoin; ++n) {
-        x0 = std::min(x0, X[n]); x1 = std::max(x1, X[n]);
-        y0 = std::min(y0, Y[n]); y1 = std::max(y1, Y[n]);
-    }
-    (void)x0; (void)x1; (void)y0; (void)y1;
-    // k-d bisection of the element centroids (longer side of the bounding box, median split) down to <= tile elements:
-    // compact, balanced tiles for any mesh density
-    vector<double> cx((size_t)nelem), cy((size_t)nelem);
-    for (int e = 0; e < nelem; ++e) {
-        const int32_t* t = inpoel + 3 * (size_t)e;
-        cx[e] = (X[t[0] - 1] + X[t[1] - 1] + X[t[2] - 1]) / 3.0;
-        cy[e] = (Y[t[0] - 1] + Y[t[1] - 1] + Y[t[2] - 1]) / 3.0;
-    }
-    vector<int32_t> ids((size_t)nelem);
-    for (int e = 0; e < nelem; ++e) ids[e] = e;
-    vector<std::pair<size_t, size_t>> leaves, stack;
-    stack.push_back({0, (size_t)nelem});
-    while (!stack.empty()) {
-        auto [lo, hi] = stack.back();
-        stack.pop_back();
-        if (hi - lo <= (size_t)tile) { leaves.push_back({lo, hi}); continue; }
-        double ax0 = cx[ids[lo]], ax1 = ax0, ay0 = cy[ids[lo]], ay1 = ay0;
-        for (size_t k = lo + 1; k < hi; ++k) {
-            double a = cx[ids[k]], b = cy[ids[k]];
-            ax0 = std::min(ax0, a); ax1 = std::max(ax1, a); ay0 = std::min(ay0, b); ay1 = std::max(ay1, b);
+                         const vector<int32_t>& esup1, const vector<int32_t>& esup2, const vector<int32_t>& eslot,
+                         const vector<uint8_t>& bcflag, int TE, bool permute, Tiling& T) {
+    const size_t E = nelem;
+    T.i2e.resize(E);
+    T.e2i.resize(E);
+    if (permute) {
+        double x0 = X[0], x1 = X[0], y0 = Y[0], y1 = Y[0];
+        for (int n = 1; n < npoin; ++n) {
+            x0 = std::min(x0, X[n]); x1 = std::max(x1, X[n]);
+            y0 = std::min(y0, Y[n]); y1 = std::max(y1, Y[n]);
         }
-        const bool by_x = (ax1 - ax0) >= (ay1 - ay0);
-        // left part = half of the leaves this range needs, so leaves come out as full as possible
-        size_t nleaf = (hi - lo + tile - 1) / tile;
-        size_t mid = lo + (hi - lo) * (nleaf / 2) / nleaf;
-        const vector<double>& c = by_x ? cx : cy;
-        std::nth_element(ids.begin() + lo, ids.begin() + mid, ids.begin() + hi, [&](int32_t a, int32_t b) {
-            return c[a] < c[b] || (c[a] == c[b] && a < b);
-        });
-        stack.push_back({mid, hi});
-        stack.push_back({lo, mid});
-    }
-    std::sort(leaves.begin(), leaves.end());
-    T.ntiles = (int)leaves.size();
-    T.tile_elems.assign((size_t)T.ntiles * tile, -1);
-    vector<int32_t> etile((size_t)nelem), epos((size_t)nelem);
-    for (int t = 0; t < T.ntiles; ++t) {
-        auto [lo, hi] = leaves[t];
-        std::sort(ids.begin() + lo, ids.begin() + hi);
-        for (size_t k = lo; k < hi; ++k) {
-            T.tile_elems[(size_t)t * tile + (k - lo)] = ids[k];
-            etile[ids[k]] = t;
-            epos[ids[k]] = (int32_t)(k - lo);
+        const double span = std::max(x1 - x0, y1 - y0);
+        const double q = span > 0 ? 65535.0 / span : 0.0;   // one scale for both axes: square cells
+        vector<uint64_t> key(E);
+        for (size_t e = 0; e < E; ++e) {
+            const int32_t* t = inpoel + 3 * e;
+            double cx = (X[t[0] - 1] + X[t[1] - 1] + X[t[2] - 1]) / 3.0, cy = (Y[t[0] - 1] + Y[t[1] - 1] + Y[t[2] - 1]) / 3.0;
+            uint32_t ix = (uint32_t)std::min(65535.0, std::max(0.0, (cx - x0) * q)), iy = (uint32_t)std::min(65535.0, std::max(0.0, (cy - y0) * q));
+            key[e] = ((uint64_t)morton16(ix, iy) << 32) | (uint64_t)e;
         }
+        std::sort(key.begin(), key.end());
+        for (size_t p = 0; p < E; ++p) T.i2e[p] = (int32_t)(key[p] & 0xffffffffu);
+    } else {
+        for (size_t p = 0; p < E; ++p) T.i2e[p] = (int32_t)p;
     }
-    vector<int32_t> owner((size_t)npoin, -1);  // tile of an interior node, -1 for boundary nodes
-    vector<int32_t> count((size_t)T.ntiles + 1, 0);
+    for (size_t p = 0; p < E; ++p) T.e2i[T.i2e[p]] = (int32_t)p;
+    const int nt = (int)((E + TE - 1) / TE);
+    T.ntiles = nt;
+    // interior tile of every node (-1: boundary)
+    vector<int32_t> owner((size_t)npoin, -1);
+    size_t ninterior = 0;
     for (int n = 0; n < npoin; ++n) {
         int k0 = esup2[n], k1 = esup2[n + 1];
         if (k0 == k1) continue;
-        int t0 = etile[esup1[k0] - 1];
+        int t0 = T.e2i[esup1[k0] - 1] / TE;
         bool same = true;
-        for (int k = k0 + 1; k < k1 && same; ++k) same = etile[esup1[k] - 1] == t0;
-        if (same) { owner[n] = t0; count[t0 + 1]++; }
+        for (int k = k0 + 1; k < k1 && same; ++k) same = T.e2i[esup1[k] - 1] / TE == t0;
+        if (same) { owner[n] = t0; ++ninterior; }
     }
-    for (int t = 0; t < T.ntiles; ++t) count[t + 1] += count[t];
-    T.tnode_ptr = count;
-    T.tnodes.assign(count[T.ntiles], 0);
-    vector<int32_t> cur(count.begin(), count.end() - 1);
     T.bnodes.clear();
-    for (int n = 0; n < npoin; ++n) {
-        if (owner[n] >= 0) T.tnodes[cur[owner[n]]++] = n;
-        else T.bnodes.push_back(n);
+    for (int n = 0; n < npoin; ++n)
+        if (owner[n] < 0) T.bnodes.push_back(n);
+    T.interior_fraction = npoin ? (double)ninterior / npoin : 0.0;
+    // pass 1: per-tile node lists (interior ascending, then the rest ascending) and the section sizes
+    vector<int32_t> stamp((size_t)npoin, -1), lidx((size_t)npoin, 0);
+    vector<int32_t> tn_ptr((size_t)nt + 1, 0), tn_nint((size_t)nt, 0), tn_nslot((size_t)nt, 0);
+    vector<int32_t> tn_nodes;
+    tn_nodes.reserve((size_t)(0.7 * E) + 1024);
+    vector<int32_t> a, b;
+    int ntn_max = 0, nint_max = 0, nslot_max = 0;
+    for (int t = 0; t < nt; ++t) {
+        size_t p0 = (size_t)t * TE, p1 = std::min(E, p0 + TE);
+        a.clear(); b.clear();
+        for (size_t p = p0; p < p1; ++p) {
+            const int32_t* el = inpoel + 3 * (size_t)T.i2e[p];
+            for (int i = 0; i < 3; ++i) {
+                int n = el[i] - 1;
+                if (stamp[n] != t) { stamp[n] = t; (owner[n] == t ? a : b).push_back(n); }
+            }
+        }
+        std::sort(a.begin(), a.end());
+        std::sort(b.begin(), b.end());
+        int ns = 0;
+        for (int n : a) ns += esup2[n + 1] - esup2[n];
+        tn_nint[t] = (int)a.size();
+        tn_nslot[t] = ns;
+        tn_nodes.insert(tn_nodes.end(), a.begin(), a.end());
+        tn_nodes.insert(tn_nodes.end(), b.begin(), b.end());
+        tn_ptr[t + 1] = (int32_t)tn_nodes.size();
+        ntn_max = std::max(ntn_max, (int)(a.size() + b.size()));
+        nint_max = std::max(nint_max, (int)a.size());
+        nslot_max = std::max(nslot_max, ns);
     }
-    T.tslot.assign(esup1.size(), 0);
-    for (size_t k = 0; k < esup1.size(); ++k) T.tslot[k] = (uint16_t)(epos[esup1[k] - 1] * 3 + eslot[k] % 3);
-    T.ebmask.assign(T.tile_elems.size(), 0);
-    for (size_t k = 0; k < T.tile_elems.size(); ++k) {
-        int e = T.tile_elems[k];
-        if (e < 0) continue;
-        uint8_t m = 0;
-        for (int i = 0; i < 3; ++i)
-            if (owner[inpoel[3 * (size_t)e + i] - 1] < 0) m |= (uint8_t)(1u << i);
-        T.ebmask[k] = m;
+    auto up16 = [](int v) { return (v + 15) & ~15; };
+    TileLayout& L = T.L;
+    L.TE = TE;
+    L.ntn_max = ntn_max; L.nint_max = nint_max; L.nslot_max = nslot_max;
+    L.off_lnode = 16;
+    L.off_tnode = up16(L.off_lnode + 3 * TE * 2);
+    L.off_nptr = up16(L.off_tnode + ntn_max * 4);
+    L.off_slots = up16(L.off_nptr + (nint_max + 1) * 2);
+    L.off_bcf = up16(L.off_slots + nslot_max * 2);
+    L.tb_bytes = up16(L.off_bcf + nint_max);
+    // pass 2: fill the blocks
+    T.blocks.assign((size_t)nt * L.tb_bytes, 0);
+    for (int t = 0; t < nt; ++t) {
+        uint8_t* blk = T.blocks.data() + (size_t)t * L.tb_bytes;
+        int32_t* hdr = reinterpret_cast<int32_t*>(blk);
+        uint16_t* lnode = reinterpret_cast<uint16_t*>(blk + L.off_lnode);
+        int32_t* tnode = reinterpret_cast<int32_t*>(blk + L.off_tnode);
+        uint16_t* nptr = reinterpret_cast<uint16_t*>(blk + L.off_nptr);
+        uint16_t* slots = reinterpret_cast<uint16_t*>(blk + L.off_slots);
+        uint8_t* bcf = blk + L.off_bcf;
+        size_t p0 = (size_t)t * TE, p1 = std::min(E, p0 + TE);
+        const int ntn = tn_ptr[t + 1] - tn_ptr[t], nint = tn_nint[t];
+        hdr[0] = (int32_t)(p1 - p0); hdr[1] = ntn; hdr[2] = nint; hdr[3] = 0;
+        for (int j = 0; j < ntn; ++j) {
+            int n = tn_nodes[(size_t)tn_ptr[t] + j];
+            tnode[j] = n;
+            lidx[n] = j;
+        }
+        for (size_t p = p0; p < p1; ++p) {
+            const int32_t* el = inpoel + 3 * (size_t)T.i2e[p];
+            for (int i = 0; i < 3; ++i) lnode[(size_t)i * TE + (p - p0)] = (uint16_t)lidx[el[i] - 1];
+        }
+        int q = 0;
+        for (int j = 0; j < nint; ++j) {
+            int n = tnode[j];
+            nptr[j] = (uint16_t)q;
+            for (int k = esup2[n]; k < esup2[n + 1]; ++k) {
+                int pos = T.e2i[esup1[k] - 1] - (int)p0, ln = eslot[k] % 3;
+                slots[q++] = (uint16_t)(4 * ln * TE + pos);
+            }
+            bcf[j] = bcflag[n];
+        }
+        nptr[nint] = (uint16_t)q;
     }
-    T.interior_fraction = npoin ? (double)T.tnodes.size() / npoin : 0.0;
 }
 
 // last[i] = index of the last entry of list[] naming the same node as entry i ("last entry wins",

@@ -887,27 +887,22 @@ struct BcTab {
 
 // The nodal chain of RK after the ordered sum (subrutinas.f90:695-826): U1 = U - rk/M*RHS, primitives, fixvel ->
 // normalvel -> FIX, conservative.  Shared by node_update and the tile-fused stage kernel.
-__device__ __forceinline__ void node_finish(int n, const double (&acc)[4], const double* __restrict__ U,
-                                            const double* __restrict__ M, const double* __restrict__ GAMM,
-                                            const double* __restrict__ WXa, const double* __restrict__ WYa,
-                                            const unsigned char* __restrict__ bcflag, const BcTab& bc, double rk_fact,
-                                            double FR, double* __restrict__ U1, double* __restrict__ RHO,
-                                            double* __restrict__ VELX, double* __restrict__ VELY, double* __restrict__ Ea,
-                                            double* __restrict__ Pa, double* __restrict__ Ta, double* __restrict__ RMACH) {
-    double u[4];
-    ld4(U + 4 * (size_t)n, u);
-    double f = rk_fact / M[n];
+__device__ __forceinline__ void node_finish_v(int n, const double (&acc)[4], const double (&u)[4], double m, double gam,
+                                              unsigned fl, const double* __restrict__ WXa, const double* __restrict__ WYa,
+                                              const BcTab& bc, double rk_fact, double FR, double* __restrict__ U1,
+                                              double* __restrict__ RHO, double* __restrict__ VELX, double* __restrict__ VELY,
+                                              double* __restrict__ Ea, double* __restrict__ Pa, double* __restrict__ Ta,
+                                              double* __restrict__ RMACH) {
+    double f = rk_fact / m;
     double u1[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) u1[i] = u[i] - f * acc[i];
-    double gam = GAMM[n];
     double rho = u1[0];
     double vx = u1[1] / rho, vy = u1[2] / rho, en = u1[3] / rho;
     double VEL2 = (vx * vx + vy * vy);
     double p = rho * (gam - 1.0) * (en - .5 * VEL2);
     double t = p / (rho * FR);
     double mach = sqrt(VEL2 / (t * gam * FR));
-    unsigned char fl = bcflag[n];
     if (fl) {
         int lo = 0, hi = bc.nb - 1;
         while (lo < hi) {
@@ -936,6 +931,17 @@ __device__ __forceinline__ void node_finish(int n, const double (&acc)[4], const
     double o[4] = {rho, vx * rho, vy * rho, en * rho};
     st4(U1 + 4 * (size_t)n, o);
     RHO[n] = rho; VELX[n] = vx; VELY[n] = vy; Ea[n] = en; Pa[n] = p; Ta[n] = t; RMACH[n] = mach;
+}
+__device__ __forceinline__ void node_finish(int n, const double (&acc)[4], const double* __restrict__ U,
+                                            const double* __restrict__ M, const double* __restrict__ GAMM,
+                                            const double* __restrict__ WXa, const double* __restrict__ WYa,
+                                            const unsigned char* __restrict__ bcflag, const BcTab& bc, double rk_fact,
+                                            double FR, double* __restrict__ U1, double* __restrict__ RHO,
+                                            double* __restrict__ VELX, double* __restrict__ VELY, double* __restrict__ Ea,
+                                            double* __restrict__ Pa, double* __restrict__ Ta, double* __restrict__ RMACH) {
+    double u[4];
+    ld4(U + 4 * (size_t)n, u);
+    node_finish_v(n, acc, u, M[n], GAMM[n], bcflag[n], WXa, WYa, bc, rk_fact, FR, U1, RHO, VELX, VELY, Ea, Pa, Ta, RMACH);
 }
 
 // 40 warps per SM at 48 registers, in CTAs of 128 threads: measured 0.557 ms per launch on the 16 M-triangle mesh against
@@ -1609,5 +1615,7 @@ __global__ void __launch_bounds__(256) node_update_rhs(int npoin, const double* 
     ld4(RHS + 4 * (size_t)n, acc);
     node_finish(n, acc, U, M, GAMM, WXa, WYa, bcflag, bc, rk_fact, FR, U1, RHO, VELX, VELY, Ea, Pa, Ta, RMACH);
 }
+
+#include "stage_fused.cuh"
 
 }  // namespace CFDB_KNS

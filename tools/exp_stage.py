@@ -27,8 +27,9 @@ g.profile(True)
 g.step(3)
 g.sync()
 out = [f"E={lc.nelem} ms/step={dt*1e3:.3f}"]
-for kn in ("calcrhs_elem", "node_update", "estab", "deltat", "spmv", "dot", "vec", "fixrows", "scalar", "fill", "dt_logic"):
+for kn in ("stage_fused", "calcrhs_elem", "node_update", "estab", "deltat", "spmv", "dot", "vec", "fixrows", "scalar", "fill", "dt_logic"):
     ms, cnt = g.profile_get(kn)
     if cnt:
         out.append(f"{kn}={ms/cnt:.4f}ms x{cnt/3:.0f}")
-print(os.environ.get("CFDB_CALCRHS_MINB", "-"), " ".join(out), flush=True)
+tag = " ".join(f"{k}={v}" for k, v in os.environ.items() if k.startswith("CFDB_"))
+print(tag or "default", "|", " ".join(out), f"interior={g.scalar('tile_interior'):.3f}", flush=True)
