@@ -9,15 +9,22 @@ on (configs[1], the 1 M wedge, fits in L2 and is a parity-test case, see tests/)
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--lattice N] [--strong] [--impl reference]
 
-Prints ONE JSON line (rank 0).  Keys: value (device-resident throughput, CUDA events on the
-library's stream, max over ranks), e2e (same step through the C ABI with host buffers: pinned
-H2D of the state every step + D2H of the result), roofline (dominant kernel, algorithmic bytes /
-measured per-launch time vs MEASURED_PEAKS.json), cpu_baseline (the oracle's OpenMP build on the
-host cores, bounded sample), clocks, gpu_launches.
-`--impl reference` times the CPU restatement of the reference (oracle/, OpenMP build) — the
+Prints ONE JSON line (rank 0).  Keys:
+  value         device-resident throughput (CUDA events on the library's stream, max over ranks)
+  roofline      the RK stage (fused tile kernel + tile-boundary pass; north_star's unit): algorithmic bytes / measured time
+                vs MEASURED_PEAKS.json, per-kernel launch durations measured live with event pairs
+  e2e           the same step through the C ABI with HOST buffers (cfdb_step_streamed: pinned H2D of the state and D2H of the
+                result every step, pipelined on copy streams); e2e.callsite = the literal per-subroutine drop-in
+  config.secondary   short timings of the other BASELINE configs: viscous 16 M, ALE 4 M (+ biCG-iteration roofline) at N=1,
+                strong-scaling 64 M at N>1
+  multi_gpu_parity   N>1: a small moving-mesh case and a small viscous case run on the N ranks and, on rank 0, on one GPU
+                with the same library; owned state compared byte for byte before anything is timed
+  cpu_baseline  the oracle's OpenMP build on all host cores (bounded sample), clocks, gpu_launches.
+`--impl reference` times the CPU restatement of the reference (oracle/, OpenMP build, all host cores) — the
 reference itself is Fortran and cannot be built in this image.
 """
 import argparse
+import glob
 import json
 import os
 import subprocess
@@ -35,7 +42,9 @@ UNIT = "elements/s"
 # SURVEY.md §8(d) / BASELINE.md §3: algorithmic bytes per element (r = npoin/nelem = 0.5)
 BYTES_STAGE_CALCRHS = 100 + 20 + 16      # element stream + gathers(U,T) + RHS write   (per element-stage)
 BYTES_STAGE_UPDATE = 16 + 68             # RHS read + nodal update                     (per element-stage)
+BYTES_STAGE = BYTES_STAGE_CALCRHS + BYTES_STAGE_UPDATE
 BYTES_STEP = 1136                        # whole fixed-mesh step
+BYTES_BICG_ITER_PER_NODE = 192           # 12*nnz + 108*P, nnz ~ 7P
 
 
 def peaks():
@@ -46,8 +55,17 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def host_threads():
+    """threads the CPU arms use: every core this process may run on (not what a launcher exported as OMP_NUM_THREADS:
+    torch.distributed.run sets that to 1)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 50 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 20 ms during the timed region."""
 
     def __init__(self, index):
         self.index = index
@@ -60,7 +78,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -79,19 +97,42 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
+                pw.append(float(r[2]))
                 for n, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def bind_to_gpu_numa_node(local):
+    """first-touch the pinned host arrays on the NUMA node the GPU hangs off (e2e copies then stay on one socket)"""
+    try:
+        bus = subprocess.run(["nvidia-smi", f"--id={local}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        bus = bus[-12:] if len(bus) > 12 else bus              # 00000000:1B:00.0 -> 0000:1b:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
 
 
 def cpu_oracle_throughput(n_lattice, steps, warmup=1, omp=True):
@@ -102,6 +143,7 @@ def cpu_oracle_throughput(n_lattice, steps, warmup=1, omp=True):
 
     lc = deck.load(meshgen.square(n=n_lattice, IPRINT=10**9, MAXITER=10**9))
     o = Oracle(lc, omp=omp)
+    threads = o.L.orc_set_omp_threads(host_threads()) if omp else 1
     o.set_scalar("norms_every_step", 0)
     st = meshgen.density_bump(lc)
     for k, v in st.items():
@@ -110,7 +152,7 @@ def cpu_oracle_throughput(n_lattice, steps, warmup=1, omp=True):
     t0 = time.perf_counter()
     o.step(steps)
     dt = time.perf_counter() - t0
-    return lc.nelem * steps / dt, (o.L.orc_omp_threads() if omp else 1), lc.nelem, dt
+    return lc.nelem * steps / dt, threads, lc.nelem, dt
 
 
 def run_reference(args, rank, out):
@@ -124,6 +166,7 @@ def run_reference(args, rank, out):
     n = args.ref_n
     lc = deck.load(meshgen.square(n=n, IPRINT=10**9, MAXITER=10**9))
     o = Oracle(lc, omp=True)
+    cores = o.L.orc_set_omp_threads(host_threads())     # explicit: never the launcher's OMP_NUM_THREADS
     o.set_scalar("norms_every_step", 0)
     for k, v in meshgen.density_bump(lc).items():
         o.set(k, v)
@@ -132,17 +175,88 @@ def run_reference(args, rank, out):
     o.step(args.steps)
     dt = time.perf_counter() - t0
     val = lc.nelem * args.steps / dt
-    cores = o.L.orc_omp_threads()
-    sample = f"{lc.nelem}-triangle square mesh (lattice {n}), {args.steps} steps in {dt:.1f} s, oracle OpenMP build, {cores} threads"
+    sample = (f"{lc.nelem}-triangle square mesh (lattice {n}; the GPU arm's generator and flow on a smaller mesh -- a per-element "
+              f"rate), {args.steps} steps in {dt:.1f} s, oracle OpenMP build, {cores} threads")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"bounded CPU sample of the GPU arm's workload (same generator, same flow): {sample}"},
+        "config": {"workload": f"bounded CPU sample of the GPU arm's workload: {sample}"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "C++ restatement of chanshing/cfd (oracle/), not the Fortran binary: no Fortran compiler in the image",
     }), file=out, flush=True)
+
+
+PROF_KERNELS = ("stage_fused", "calcrhs_elem", "node_update", "estab", "deltat", "spmv", "dot", "vec", "scalar", "fixrows",
+                "move_apply", "halo", "laplace", "deriv", "masas", "gcl", "fill", "layout")
+
+
+def kernel_profile(g, steps=3):
+    g.profile(True)
+    g.step(steps)
+    g.sync()
+    prof = {}
+    for kname in PROF_KERNELS:
+        t_ms, n = g.profile_get(kname)
+        if n:
+            prof[kname] = {"avg_ms": t_ms / n, "launches_per_step": n / float(steps)}
+    g.profile(False)
+    return prof
+
+
+def timed_steps(g, torch, stream, steps, barrier):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    g.step(steps)
+    e1.record(stream)
+    barrier()
+    return e0.elapsed_time(e1)
+
+
+def parity_selfcheck(torch, dist, rank, world, local):
+    """Correctness carried by the scaling record: a small moving-mesh case (biCG, global canonical reductions) and a small
+    viscous fixed-mesh case on the N ranks, against the same library on ONE GPU (rank 0), owned state compared byte for byte."""
+    from cfd_b200 import deck, meshgen
+    from cfd_b200.dist import make_rank_solver
+    from cfd_b200.solver import NSComp2D
+
+    cases = {"ale": (lambda: meshgen.ale_body(nt=512, nr=160), False, 4),
+             "viscous": (lambda: meshgen.square_global(129, world, FMU=1.8e-5, FK=0.0257), True, 4)}
+    verdict = []
+    for name, (mk, bump, steps) in cases.items():
+        glc = deck.load(mk())
+        g, part = make_rank_solver(glc, rank, world, local, dist)
+        st = meshgen.density_bump(glc) if bump else None
+        if st:
+            g.set("U", st["U"][part.node_gid])
+            for k in ("T", "VEL_X", "VEL_Y"):
+                g.set(k, st[k][part.node_gid])
+        g.step(steps)
+        g.sync()
+        own = slice(0, part.n_owned)
+        mine = {f: g.get(f).reshape(part.lc.npoin, -1)[own] for f in ("U", "T", "X", "P")}
+        box = [None] * world
+        dist.all_gather_object(box, (part.node_gid[own], mine, part.red_aligned))
+        g.close()
+        if rank == 0:
+            ref = NSComp2D(glc, device=local)
+            if st:
+                for k, v in st.items():
+                    ref.set(k, v)
+            ref.step(steps)
+            ok = all(b[2] for b in box) or name != "ale"
+            for f in ("U", "T", "X", "P"):
+                want = ref.get(f).reshape(glc.npoin, -1)
+                for gid, vals, _ in box:
+                    ok = ok and np.array_equal(vals[f].view(np.uint64), want[gid].view(np.uint64))
+            ref.close()
+            verdict.append((name, ok))
+    if rank == 0:
+        bad = [n for n, ok in verdict if not ok]
+        return "bit-exact" if not bad else "FAILED: " + ",".join(bad)
+    return None
 
 
 def main():
@@ -160,6 +274,8 @@ def main():
     ap.add_argument("--strong", action="store_true", help="strong scaling (BASELINE configs[3]): one n x n domain cut into N strips")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -179,35 +295,43 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — cfd_b200 has no CPU path")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    parity = None
+    if world > 1 and not args.no_parity:
+        parity = parity_selfcheck(torch, dist, rank, world, local)
 
     # ---- workload: this rank's sub-domain (weak scaling: fixed work per GPU) --------------------
     # The global mesh is `world` 16 M-triangle strips stacked in y; each rank builds only its window of it
     # (cfd_b200/partition.py), computes its own range plus a one-element ghost layer, and refreshes ghost nodes
     # over NCCL after every RK stage.
-    t_gen = time.perf_counter()
     from cfd_b200 import partition
     from cfd_b200.dist import make_rank_solver
 
-    rows_per = None
-    if args.strong:
-        if (args.n - 1) % world:
-            raise SystemExit("--strong needs (n-1) divisible by the number of GPUs")
-        rows_per = (args.n - 1) // world
-    win = partition.square_window(args.n, world, rank, rows_per=rows_per, IPRINT=10**9, MAXITER=10**9)
-    g, part = make_rank_solver(win, rank, world, local, dist if world > 1 else None)
+    def build(n, strong, **kw):
+        t0 = time.perf_counter()
+        rows_per = None
+        if strong:
+            if (n - 1) % world:
+                raise SystemExit("--strong needs (n-1) divisible by the number of GPUs")
+            rows_per = (n - 1) // world
+        win = partition.square_window(n, world, rank, rows_per=rows_per, IPRINT=10**9, MAXITER=10**9, **kw)
+        g, part = make_rank_solver(win, rank, world, local, dist if world > 1 else None)
+        E = 2 * (n - 1) * (rows_per if strong else n - 1)   # elements of this rank's own range
+        if strong:
+            bump = meshgen.density_bump(part.lc, x0=0.5, y0=0.5, sigma=0.15)    # one bump in the middle of the fixed domain
+        else:
+            bump = meshgen.density_bump(part.lc, x0=0.5, y0=0.5, sigma=0.15, period_y=1.0)  # one bump per strip
+        for k, v in bump.items():
+            g.set(k, v)
+        return g, part, E, time.perf_counter() - t0
+
+    g, part, E, t_gen = build(args.n, args.strong)
     lc = part.lc
-    E = 2 * (args.n - 1) * (rows_per if args.strong else args.n - 1)   # elements of this rank's own range
     P = part.n_owned
-    if args.strong:
-        bump = meshgen.density_bump(lc, x0=0.5, y0=0.5, sigma=0.15)    # one bump in the middle of the fixed domain
-    else:
-        bump = meshgen.density_bump(lc, x0=0.5, y0=0.5, sigma=0.15, period_y=1.0)  # one bump per strip
-    for k, v in bump.items():
-        g.set(k, v)
-    t_gen = time.perf_counter() - t_gen
     stream = torch.cuda.ExternalStream(g.stream, device=torch.device("cuda", local))
 
     def barrier():
@@ -216,54 +340,55 @@ def main():
         if world > 1:
             dist.barrier()
 
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
     # ---- device-resident timing -------------------------------------------------------------------
     g.step(args.warmup)
     barrier()
     l0 = g.launch_count()
     sampler = ClockSampler(local)
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    g.step(args.steps)
-    e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms = timed_steps(g, torch, stream, args.steps, barrier)
     clocks = sampler.stop()
     launches = g.launch_count() - l0
-    if world > 1:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = max_over_ranks(ms)
     value = world * E * args.steps / (ms * 1e-3)
 
-    # ---- per-kernel launch durations (events on the launching stream; separate pass) ---------------
-    g.profile(True)
-    g.step(3)
-    g.sync()
-    prof = {}
-    for kname in ("calcrhs_elem", "node_update", "estab", "deltat", "spmv", "dot", "vec"):
-        t_ms, n = g.profile_get(kname)
-        if n:
-            prof[kname] = {"avg_ms": t_ms / n, "launches_per_step": n / 3.0}
-    g.profile(False)
+    # ---- per-kernel launch durations (event pairs on the launching stream; separate pass, stream launches) ---------------
+    prof = kernel_profile(g)
     peak, peak_src = peaks()
-    stage_ms = prof["calcrhs_elem"]["avg_ms"] + prof["node_update"]["avg_ms"]
-    dom = "calcrhs_elem" if prof["calcrhs_elem"]["avg_ms"] >= prof["node_update"]["avg_ms"] else "node_update"
-    dom_bytes = BYTES_STAGE_CALCRHS if dom == "calcrhs_elem" else BYTES_STAGE_UPDATE
-    achieved = dom_bytes * E / (prof[dom]["avg_ms"] * 1e-3) / 1e9
-    stage_achieved = (BYTES_STAGE_CALCRHS + BYTES_STAGE_UPDATE) * E / (stage_ms * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")   # dram__bytes_read+write per launch from the committed ncu capture
-    if os.path.exists(tp):
-        with open(tp) as f:
-            traffic = json.load(f).get(dom)
+    fused = "stage_fused" in prof
+    if fused:   # the RK stage = fused tile kernel + node_update over the tile-boundary nodes
+        stage_ms = prof["stage_fused"]["avg_ms"] + prof["node_update"]["avg_ms"]
+        stage_kernels = "stage_fused+node_update(tile-boundary nodes)"
+        dom = "stage_fused"
+    else:
+        stage_ms = prof["calcrhs_elem"]["avg_ms"] + prof["node_update"]["avg_ms"]
+        stage_kernels = "calcrhs_elem+node_update"
+        dom = "calcrhs_elem" if prof["calcrhs_elem"]["avg_ms"] >= prof["node_update"]["avg_ms"] else "node_update"
+    El = lc.nelem    # elements this rank computes (own range + ghost layer); the stage's algorithmic bytes follow the work done
+    stage_achieved = BYTES_STAGE * El / (stage_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    cands = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))
+    if cands:   # dram__bytes_read+write per launch from the newest committed ncu capture (NOT measured in this run)
+        with open(cands[-1]) as f:
+            tj = json.load(f)
+        traffic = sum(tj.get(k, 0) for k in (("stage_fused", "node_update") if fused else ("calcrhs_elem", "node_update")) if k in tj) or None
+        traffic_src = f"profiles/{os.path.basename(cands[-1])} (committed ncu --set full capture, bytes per stage; not measured in this run)"
     roofline = {
-        "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": traffic, "peak_source": peak_src,
-        "algorithmic_bytes_per_element": dom_bytes,
-        "stage": {"kernels": "calcrhs_elem+node_update", "bytes_per_element_stage": BYTES_STAGE_CALCRHS + BYTES_STAGE_UPDATE,
-                  "ms": stage_ms, "achieved": stage_achieved, "frac": stage_achieved / peak,
-                  "element_stage_per_s": E / (stage_ms * 1e-3)},
+        "bound": "hbm", "kernel": stage_kernels, "achieved": stage_achieved, "peak": peak, "unit": "GB/s", "frac": stage_achieved / peak,
+        "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+        "algorithmic_bytes_per_element": BYTES_STAGE, "launch_ms": stage_ms,
+        "what": "the RK stage (calcRHS + ordered sum + nodal update + BCs), north_star's unit: 220 algorithmic B per element-stage "
+                "x elements per launch / event-timed duration of the stage's launches",
+        "dominant_kernel": {"name": dom, "avg_ms": prof[dom]["avg_ms"]},
+        "stage": {"kernels": stage_kernels, "bytes_per_element_stage": BYTES_STAGE, "ms": stage_ms, "achieved": stage_achieved,
+                  "frac": stage_achieved / peak, "element_stage_per_s": El / (stage_ms * 1e-3)},
         "step": {"bytes_per_element_step": BYTES_STEP, "achieved": BYTES_STEP * E * args.steps / (ms * 1e-3) / 1e9,
                  "frac": BYTES_STEP * E * args.steps / (ms * 1e-3) / 1e9 / peak},
         "kernels": prof,
@@ -273,52 +398,162 @@ def main():
     e2e = None
     if not args.no_e2e:
         names = ["U", "T", "VEL_X", "VEL_Y"]
-        host = {nme: torch.empty(g.L.cfdb_field_size(g.h, nme.encode()), dtype=torch.float64, pin_memory=True) for nme in names}
-        for nme in names:
-            host[nme].numpy()[:] = g.get(nme)
-        h2d = sum(8 * h.numel() for h in host.values())
+        sizes = {nme: g.L.cfdb_field_size(g.h, nme.encode()) for nme in names}
+        # two sets of pinned host arrays on each side (the host program double-buffers its state): call k reads set k%2 and
+        # delivers into set k%2 of the outputs; uploads, steps and downloads of consecutive calls overlap (cfdb_step_streamed)
+        hin = [{nme: torch.empty(sizes[nme], dtype=torch.float64, pin_memory=True) for nme in names} for _ in range(2)]
+        hout = [{nme: torch.empty(sizes[nme], dtype=torch.float64, pin_memory=True) for nme in names} for _ in range(2)]
+        hnorm = [torch.empty(8, dtype=torch.float64, pin_memory=True) for _ in range(2)]
+        for s in range(2):
+            for nme in names:
+                hin[s][nme].numpy()[:] = g.get(nme)
+        h2d = sum(8 * sizes[nme] for nme in names)
         d2h = h2d + 64
         ksteps = max(3, min(args.steps, 10))
 
-        hv = {nme: host[nme].numpy() for nme in names}
+        def one(kk):
+            s = kk & 1
+            g.step_streamed({nme: hin[s][nme].numpy() for nme in names}, {nme: hout[s][nme].numpy() for nme in names}, hnorm[s].numpy())
 
-        def one():
-            for nme in names:
-                g.set_from(nme, hv[nme])   # pinned host -> HBM
-            g.step(1)
-            # HBM -> pinned host, straight into the host program's own arrays: U = U1 (ns2DComp.ALE.f90:277-281) and the
-            # primitives the next DELTAT/ESTAB read, so the host copy of the state stays consistent step after step
-            for nme in names:
-                g.get_into(nme, hv[nme])
-            g.norms()
-
-        one()
+        one(0)
+        one(1)
+        g.streamed_wait()
         barrier()
         t0 = time.perf_counter()
-        for _ in range(ksteps):
-            one()
+        for kk in range(ksteps):
+            one(kk)
+        g.streamed_wait()
         barrier()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        dt = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": world * E * ksteps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "steps": ksteps, "what": "state U,T,VEL_X,VEL_Y uploaded from pinned host memory, cfdb_step(1), "
-               "the same four arrays and the residual norms downloaded into the host program's arrays, every step"}
+               "steps": ksteps, "ms_per_step": 1e3 * dt / ksteps, "numa_node": numa,
+               "what": "cfdb_step_streamed: every step takes its state U,T,VEL_X,VEL_Y from pinned host arrays and delivers the new "
+                       "state and the residual norms into pinned host arrays (double-buffered on the host side); upload of call "
+                       "k+1, step k and download of call k-1 run concurrently on three streams (wall clock, max over ranks)"}
+        del hin, hout
+        # the literal per-subroutine drop-in (pageable host arrays in the Fortran layouts through the call-site entries): deltat,
+        # RK and fluidStructure of one pass of the loop, every array of every call crossing PCIe both ways
+        if world == 1:
+            Pn, En = lc.npoin, lc.nelem
+            arr = {k: g.get(k) for k in ("U", "T", "VEL_X", "VEL_Y", "W_X", "W_Y", "GAMM", "area", "X", "Y", "X1", "Y1", "P", "xpos", "ypos")}
+            outs = {k: np.zeros(4 * Pn) for k in ("U1", "RHS", "RHS1", "RHS2", "RHS3")}
+            outs.update({k: np.zeros(Pn) for k in ("RHO", "E", "RMACH")})
+            outs.update({k: np.zeros(En) for k in ("SHOC", "T_SUGN1", "T_SUGN2", "T_SUGN3")})
+            par = lc.par
+            kcs = 2
+
+            def callsite_step():
+                dtmin, dt_e = g.deltat(arr["area"], arr["T"], arr["VEL_X"], arr["VEL_Y"], arr["W_X"], arr["W_Y"], par["FSAFE"], par["FR"],
+                                       par["GAMA"], par["T_inf"])
+                dtl = np.full(En, dtmin)
+                g.rk_callsite(dtmin, 4, 5, arr["GAMM"], dtl, arr["U"], outs["U1"], outs["RHS"], outs["RHS1"], outs["RHS2"], outs["RHS3"],
+                              arr["T"], arr["P"], outs["RHO"], outs["E"], outs["RMACH"], arr["VEL_X"], arr["VEL_Y"], arr["W_X"], arr["W_Y"],
+                              outs["SHOC"], outs["T_SUGN1"], outs["T_SUGN2"], outs["T_SUGN3"])
+                g.mesh_move(dtmin, 0.0, arr["X"], arr["Y"], arr["X1"], arr["Y1"], arr["W_X"], arr["W_Y"], arr["P"], arr["xpos"], arr["ypos"])
+                arr["U"][:] = outs["U1"]
+
+            callsite_step()
+            t0 = time.perf_counter()
+            for _ in range(kcs):
+                callsite_step()
+            dtc = time.perf_counter() - t0
+            e2e["callsite"] = {"value": E * kcs / dtc, "unit": UNIT, "steps": kcs, "ms_per_step": 1e3 * dtc / kcs,
+                               "what": "one pass of the loop as three call-site calls with pageable host arrays (cfdb_deltat, cfdb_rk, "
+                                       "cfdb_mesh_move): ~1.6 GB up and ~2.4 GB down per step; the context is a moving-mesh one afterwards"}
+            del arr, outs
+
+    # ---- the other BASELINE configs, short (config.secondary) ----------------------------------------------------------
+    secondary = {}
+    if not args.no_secondary and not args.strong:
+        g.close()
+        del g
+        if world == 1:
+            # viscous 16 M (calcRHS.f90:119-137 path)
+            gv, pv, Ev, _ = build(args.n, False, FMU=1.8e-5, FK=0.0257)
+            sv = torch.cuda.ExternalStream(gv.stream, device=torch.device("cuda", local))
+            gv.step(3)
+            msv = timed_steps(gv, torch, sv, 10, lambda: (gv.sync(), torch.cuda.synchronize()))
+            pk = kernel_profile(gv, 2)
+            st_ms = pk.get("stage_fused", pk.get("calcrhs_elem"))["avg_ms"] + pk["node_update"]["avg_ms"]
+            secondary["viscous16M"] = {"workload": f"{Ev}-triangle strip, FMU=1.8e-5, FK=0.0257 (viscous terms of calcRHS.f90:119-137), fixed mesh",
+                                       "ms_per_step": msv / 10, "value": Ev * 10 / (msv * 1e-3), "unit": UNIT, "stage_ms": st_ms,
+                                       "stage_frac": (BYTES_STAGE + 4) * pv.lc.nelem / (st_ms * 1e-3) / 1e9 / peak,
+                                       "kernels": {k: round(v["avg_ms"], 4) for k, v in pk.items()}}
+            gv.close()
+            del gv
+            # ALE 4 M (BASELINE configs[2]): pitching body, meshMove Laplace biCG + geometry refresh + GCL every step
+            lca = deck.load(meshgen.ale_body(nt=2000, nr=1000, IPRINT=10**9, MAXITER=10**9))
+            ga = NSComp2D(lca, device=local, use_gcl=1)
+            sa = torch.cuda.ExternalStream(ga.stream, device=torch.device("cuda", local))
+            ga.step(2)
+            its = []
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ga.sync()
+            ea.record(sa)
+            for _ in range(8):
+                ga.step(1)
+                its.append((int(ga.scalar("bicg_x")), int(ga.scalar("bicg_y"))))
+            eb.record(sa)
+            ga.sync()
+            torch.cuda.synchronize()
+            msa = ea.elapsed_time(eb) / 8
+            # biCG-iteration roofline: the reference's tolerance is absolute (1e-10 on r.z), so a physical step needs 0-1
+            # iterations; perturb the warm start so that one solve runs many iterations and time its kernels
+            rng = np.random.default_rng(1)
+            ga.set("xpos", 1e-3 * rng.standard_normal(lca.npoin))
+            ga.profile(True)
+            ga.step(1)
+            ga.sync()
+            nit = max(1, int(ga.scalar("bicg_x")) + max(0, int(ga.scalar("bicg_y"))))
+            tb = 0.0
+            per = {}
+            for kname in ("vec", "spmv", "dot", "scalar"):
+                t_ms, nk = ga.profile_get(kname)
+                per[kname] = t_ms
+                tb += t_ms
+            ga.profile(False)
+            it_ms = tb / nit
+            bicg = {"iterations": nit, "ms_per_iteration": it_ms, "bytes_per_node": BYTES_BICG_ITER_PER_NODE,
+                    "achieved": BYTES_BICG_ITER_PER_NODE * lca.npoin / (it_ms * 1e-3) / 1e9,
+                    "frac": BYTES_BICG_ITER_PER_NODE * lca.npoin / (it_ms * 1e-3) / 1e9 / peak,
+                    "kernel_ms": {k: round(v, 4) for k, v in per.items()},
+                    "what": "one biCG solve with a perturbed warm start (forces iterations; the physical steps above need 0-1): "
+                            "all vec/spmv/dot/scalar kernel time of that step / iterations, against 192 B per node"}
+            secondary["ale4M"] = {"workload": f"{lca.nelem}-triangle / {lca.npoin}-node O-mesh around a pitching ellipse, MOVING=1, gcl on",
+                                  "ms_per_step": msa, "value": lca.nelem / (msa * 1e-3), "unit": UNIT,
+                                  "bicg_iters_per_step": its, "bicg_iteration": bicg}
+            ga.close()
+            del ga
+        else:
+            n64 = 5657
+            if (n64 - 1) % world == 0:
+                gs, ps, Es, _ = build(n64, True)
+                ss = torch.cuda.ExternalStream(gs.stream, device=torch.device("cuda", local))
+
+                def bar2():
+                    gs.sync()
+                    torch.cuda.synchronize()
+                    dist.barrier()
+
+                gs.step(3)
+                mss = max_over_ranks(timed_steps(gs, torch, ss, 10, bar2))
+                secondary["strong64M"] = {"workload": f"one {world * Es}-triangle domain (lattice {n64}) cut into {world} strips (BASELINE configs[3])",
+                                          "ms_per_step": mss / 10, "value": world * Es * 10 / (mss * 1e-3), "unit": UNIT, "scaling": "strong"}
+                gs.close()
+                del gs
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         v, cores, ne, dt = cpu_oracle_throughput(args.ref_n, args.cpu_steps)
         v1, _, ne1, dt1 = cpu_oracle_throughput(709, 3, omp=False)     # threads = 1 next to all cores
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{ne}-triangle square mesh, {args.cpu_steps} steps ({dt:.1f} s), oracle OpenMP build "
-                         "(C++ restatement; the Fortran reference cannot be built here)",
+               "sample": f"{ne}-triangle square mesh (same generator and flow as the GPU arm, smaller mesh: a per-element rate), "
+                         f"{args.cpu_steps} steps ({dt:.1f} s), oracle OpenMP build (C++ restatement; the Fortran reference cannot be built here)",
                "single_thread": {"value": v1, "cores": 1, "sample": f"{ne1}-triangle square mesh, 3 steps ({dt1:.1f} s), "
                                  "sequential build (the summation order of the parity tests)"}}
 
     if rank == 0:
-        print(json.dumps({
+        line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
@@ -327,9 +562,13 @@ def main():
                                    "density-bump initial state", "l2": "inputs larger than L2 (no flush needed)",
                        "elements_per_gpu": E, "local_elements_incl_ghost_layer": lc.nelem,
                        "parallelism": f"{world} contiguous strips, owner-computes + NCCL ghost refresh per RK stage",
-                       "element_stage_updates_per_s": 4 * value, "setup_s": t_gen},
+                       "stage": "fused tile kernel (stage_fused) + tile-boundary pass" if fused else "two kernels",
+                       "element_stage_updates_per_s": 4 * value, "setup_s": t_gen, "secondary": secondary},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "gpu_launches": launches,
-        }), file=real_stdout, flush=True)
+        }
+        if world > 1:
+            line["multi_gpu_parity"] = parity
+        print(json.dumps(line), file=real_stdout, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -159,12 +159,14 @@ struct cfdb_ctx {
     int bicg_iters[2] = {0, 0};
     bool theta_nonzero = false;
     int use_cuarto = 0, true_rk = 0;  // "next" rows N1 / N2, default off (reference behaviour)
+    bool dtl_force = false;           // call-site RK: the local time step array is the caller's dtl whatever ITLOCAL says
     int fast = 0;                     // relaxed stage (FMA + atomic scatter), opt-in, NOT bit-exact
     bool u1_is_u = false;  // after U = U1 (ns2DComp.ALE.f90:277-281) the two arrays are one buffer
     // fused RK stage (kernels: stage_fused.cuh; tiling: host_topology.h build_tiling).  The element arrays of the context
     // are kept in INTERNAL (tile) order: i2e[p] = file-order element at internal position p, e2i its inverse (null: identity)
     bool tiles_ok = false, perm_on = false, geo_dirty = true;
-    int ntiles = 0, nbnodes = 0, tile_ncw = 0;
+    int ntiles = 0, nbnodes = 0, tile_ncw = 0, tile_na = 3;
+    unsigned long long* stage_stats = nullptr;   // CFDB_STAGE_STATS=1: cycle counters of stage_fused, printed by cfdb_sync
     double tile_interior = 0.0;
     long Epad = 0;
     k::TileGeom tgeom{};
@@ -173,6 +175,11 @@ struct cfdb_ctx {
     DBuf<int> i2e, e2i, bnodes;
     DBuf<unsigned char> TB;
     DBuf<double> geo;
+    // cfdb_step_streamed: copy streams, device-side staging on both sides, and the events that order them
+    cudaStream_t st_in = nullptr, st_out = nullptr;
+    cudaEvent_t ev_in_done = nullptr, ev_in_used = nullptr, ev_step_done = nullptr, ev_out_done = nullptr;
+    bool streamed_any = false;
+    DBuf<double> sin_U, sin_T, sin_VX, sin_VY, sout_U, sout_T, sout_VX, sout_VY, sout_N;
     // multi-GPU (one rank per context)
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
@@ -435,11 +442,14 @@ static int ensure_host_topology(cfdb_ctx* c) {
 // cfdb_create: the device topology has been built from the file-order connectivity (so every per-node list is in ascending
 // FILE-order element id, the reference's summation order); from here on the element arrays live in tile order.
 //   CFDB_NO_PERM=1   keep the file's element order (tiles = runs of consecutive elements)
-//   CFDB_TILE_TE=384 tile size (512 default; must be a multiple of 128, <= 512)
+//   CFDB_TILE_TE=352|384|416 tile size (352 default)
 static int build_stage_tiles(cfdb_ctx* c, const int32_t* inpoel, const double* X, const double* Y) {
     const size_t E = c->nelem, P = c->npoin;
-    int TE = getenv("CFDB_TILE_TE") ? atoi(getenv("CFDB_TILE_TE")) : 512;
-    if (TE != 384 && TE != 512) return fail("CFDB_TILE_TE must be 384 or 512");
+    // TE = 32 x compute warps.  The register file is split over the four SM sub-partitions, so the per-thread budget follows
+    // from the warps ONE sub-partition holds: 12 warps per CTA (11 compute + the loader) leave 168 registers per thread,
+    // 13 or 14 warps leave 128.  Shared memory (two C buffers, the A and B rings) caps TE at 416.
+    int TE = getenv("CFDB_TILE_TE") ? atoi(getenv("CFDB_TILE_TE")) : 352;
+    if (TE != 352 && TE != 384 && TE != 416) return fail("CFDB_TILE_TE must be 352, 384 or 416");
     const bool permute = getenv("CFDB_NO_PERM") == nullptr;
     // host copies of esup2 / eslot (file order)
     vector<int32_t> esup2(P + 1), eslot(3 * E), esup1(3 * E);
@@ -478,7 +488,8 @@ static int build_stage_tiles(cfdb_ctx* c, const int32_t* inpoel, const double* X
         tmp.release();
         c->perm_on = true;
     }
-    // ring-stage layout in shared memory
+    // shared-memory layout of the stage kernel: barriers + counters, C[2][12][TE], the A ring (static block + gathered
+    // nodal data of a tile), the B ring (its element stream)
     const topo::TileLayout& L = T.L;
     k::TileGeom& G = c->tgeom;
     auto up16 = [](int v) { return (v + 15) & ~15; };
@@ -487,16 +498,18 @@ static int build_stage_tiles(cfdb_ctx* c, const int32_t* inpoel, const double* X
     G.off_lnode = L.off_lnode; G.off_tnode = L.off_tnode; G.off_nptr = L.off_nptr; G.off_slots = L.off_slots; G.off_bcf = L.off_bcf;
     G.tb_bytes = L.tb_bytes;
     G.nfields = c->par.ITLOCAL != 0 ? 12 : 11;
-    G.st_static = 0;
-    G.st_stream = up128(L.tb_bytes);
-    G.st_u = G.st_stream + G.nfields * TE * 8;
-    G.st_t = G.st_u + L.ntn_max * 32;
-    G.st_m = G.st_t + up16(L.ntn_max * 8);
-    G.st_g = G.st_m + up16(L.nint_max * 8);
-    G.stage_bytes = up128(G.st_g + up16(L.nint_max * 8));
-    G.off_c = 128;
-    G.off_stage0 = up128(G.off_c + 12 * TE * 8);
-    c->stage_smem = (size_t)G.off_stage0 + 2 * (size_t)G.stage_bytes;
+    G.a_static = 0;
+    G.a_u = up128(L.tb_bytes);
+    G.a_t = G.a_u + L.ntn_max * 32;
+    G.a_m = G.a_t + up16(L.ntn_max * 8);
+    G.a_g = G.a_m + up16(L.nint_max * 8);
+    G.a_bytes = up128(G.a_g + up16(L.nint_max * 8));
+    G.b_bytes = up128(G.nfields * TE * 8);
+    G.off_c = 256;
+    G.off_a = up128(G.off_c + 2 * 12 * TE * 8);
+    c->tile_na = TE == 352 ? 4 : 3;
+    G.off_b = G.off_a + c->tile_na * G.a_bytes;
+    c->stage_smem = (size_t)G.off_b + 2 * (size_t)G.b_bytes;
     int smem_max = 0;
     CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
     c->tiles_ok = c->stage_smem <= (size_t)smem_max;   // else: the two-kernel stage (very high valence / odd meshes)
@@ -648,6 +661,10 @@ extern "C" void cfdb_destroy(cfdb_ctx* c) {
     cudaSetDevice(c->device);
     if (c->st) cudaStreamSynchronize(c->st);
     for (int i = 0; i < 2; ++i) if (c->gexec[i]) cudaGraphExecDestroy(c->gexec[i]);
+    if (c->st_in) { cudaStreamSynchronize(c->st_in); cudaStreamDestroy(c->st_in); }
+    if (c->st_out) { cudaStreamSynchronize(c->st_out); cudaStreamDestroy(c->st_out); }
+    for (auto e : {c->ev_in_done, c->ev_in_used, c->ev_step_done, c->ev_out_done}) if (e) cudaEventDestroy(e);
+    for (auto* d : {&c->sin_U, &c->sin_T, &c->sin_VX, &c->sin_VY, &c->sout_U, &c->sout_T, &c->sout_VX, &c->sout_VY, &c->sout_N}) d->release();
     if (c->comm) ncclCommDestroy(c->comm);
     c->send_idx.release(); c->recv_idx.release(); c->sendbuf.release(); c->recvbuf.release(); c->redG.release();
     for (auto* d : {&c->inp, &c->d_esup2, &c->eslot, &c->d_lap_idx, &c->d_lap_rowptr, &c->wall, &c->wn_node, &c->wn_ptr,
@@ -995,7 +1012,7 @@ static int refresh_geo(cfdb_ctx* c) {
 // fused tile stage (stage_fused.cuh) + node_update over the tile-boundary nodes
 static bool fused_eligible(const cfdb_ctx* c) {
     static const bool off = getenv("CFDB_NO_FUSED") != nullptr;
-    return !off && c->tiles_ok && !c->ale && !c->use_cuarto && !c->fast && !c->theta_nonzero;
+    return !off && c->tiles_ok && !c->ale && !c->use_cuarto && !c->fast && !c->theta_nonzero && !c->dtl_force;
 }
 static int run_stage_fused(cfdb_ctx* c, const k::Gas& g, const double* dtl_arr, const double* dtl_sc, double rk_fact) {
     const bool visc = g.mu_ref > 2.2250738585072014e-308;
@@ -1010,8 +1027,15 @@ static int run_stage_fused(cfdb_ctx* c, const k::Gas& g, const double* dtl_arr, 
     G.nfields = dtl_arr ? 12 : 11;
     if (G.nfields > c->tgeom.nfields) return fail("run_stage_fused: stage layout was sized without a local time step array");
     void (*kern)(const k::TileGeom, const k::StageArgs) = nullptr;
-    if (c->tile_ncw == 16) kern = visc ? k::stage_fused<true, 16, 120, 24> : k::stage_fused<false, 16, 120, 24>;
-    else kern = visc ? k::stage_fused<true, 12, 152, 56> : k::stage_fused<false, 12, 152, 56>;
+    if (c->tile_ncw == 11) kern = visc ? k::stage_fused<true, 11, 4, 2> : k::stage_fused<false, 11, 4, 2>;
+    else if (c->tile_ncw == 13) kern = visc ? k::stage_fused<true, 13, 3, 2> : k::stage_fused<false, 13, 3, 2>;
+    else kern = visc ? k::stage_fused<true, 12, 3, 2> : k::stage_fused<false, 12, 3, 2>;
+    static const bool want_stats = getenv("CFDB_STAGE_STATS") != nullptr;
+    if (want_stats && !c->stage_stats) {
+        CK(cudaMalloc(&c->stage_stats, k::ST_COUNT * sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(c->stage_stats, 0, k::ST_COUNT * sizeof(unsigned long long), c->st));
+    }
+    A.stats = c->stage_stats;
     static std::map<const void*, bool> attr_done;
     if (!attr_done[(const void*)kern]) {
         CK(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->stage_smem));
@@ -1019,7 +1043,7 @@ static int run_stage_fused(cfdb_ctx* c, const k::Gas& g, const double* dtl_arr, 
     }
     static int nsm = 0;
     if (!nsm) CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device));
-    const int grid = std::min(c->ntiles, nsm), block = (c->tile_ncw + 4) * 32;
+    const int grid = std::min(c->ntiles, nsm), block = (c->tile_ncw + 1) * 32;
     cudaEvent_t _a = nullptr, _b = nullptr;
     TRY(prof_begin(c, c->st, K_STAGE, &_a, &_b));
     kern<<<grid, block, c->stage_smem, c->st>>>(G, A);
@@ -1055,7 +1079,7 @@ extern "C" int cfdb_rk_stage(cfdb_ctx* c, int32_t irk) {
     c->Usrc = (c->true_rk && irk > 1) ? c->U1.p : nullptr;
     struct UsrcReset { cfdb_ctx* c; ~UsrcReset() { c->Usrc = nullptr; } } usrc_reset{c};
     k::Gas g{p.FCv, p.FK, p.FMU, p.GAMA, p.T_inf, p.CTE};
-    const double* dtl_arr = p.ITLOCAL != 0 ? c->DTL.p : nullptr;
+    const double* dtl_arr = (p.ITLOCAL != 0 || c->dtl_force) ? c->DTL.p : nullptr;
     if (c->fast == 2 && !c->ale && !c->use_cuarto && !c->true_rk) {
         // measurement only: the staged element kernel compiled with FMA contraction + the exact ordered node kernel
         const bool visc = g.mu_ref > 2.2250738585072014e-308;
@@ -1460,6 +1484,75 @@ static int step_once(cfdb_ctx* c) {
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Streamed stepping: the state of every step comes from host arrays and its results go back to host arrays, as a literal
+// "the host program owns the arrays" integration needs, but pipelined.  Three streams: st_in uploads the inputs of call
+// k+1 into device staging while the compute stream runs step k; st_out downloads the results of step k from a second
+// staging area while step k+1 runs.  Events order the hand-overs; one staging area per direction is enough because the
+// copy out of (into) staging is a device-to-device copy at the very start (end) of the step.  PCIe carries both
+// directions at once, so a step costs max(upload, step, download) instead of their sum.
+static int streamed_setup(cfdb_ctx* c) {
+    if (c->st_in) return 0;
+    const size_t P = c->npoin;
+    CK(cudaStreamCreateWithFlags(&c->st_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->st_out, cudaStreamNonBlocking));
+    for (auto* e : {&c->ev_in_done, &c->ev_in_used, &c->ev_step_done, &c->ev_out_done}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    for (auto* d : {&c->sin_U, &c->sout_U}) TRY(d->alloc(4 * P));
+    for (auto* d : {&c->sin_T, &c->sin_VX, &c->sin_VY, &c->sout_T, &c->sout_VX, &c->sout_VY}) TRY(d->alloc(P));
+    TRY(c->sout_N.alloc(8));
+    return 0;
+}
+extern "C" int cfdb_step_streamed(cfdb_ctx* c, const double* in_U, const double* in_T, const double* in_VEL_X, const double* in_VEL_Y,
+                                  double* out_U, double* out_T, double* out_VEL_X, double* out_VEL_Y, double* out_norms) {
+    CK(cudaSetDevice(c->device));
+    TRY(streamed_setup(c));
+    const size_t P = c->npoin, B = sizeof(double);
+    // 1. upload into staging (waits until the previous call's staging has been consumed)
+    if (c->streamed_any) CK(cudaStreamWaitEvent(c->st_in, c->ev_in_used, 0));
+    if (in_U) CK(cudaMemcpyAsync(c->sin_U.p, in_U, 4 * P * B, cudaMemcpyHostToDevice, c->st_in));
+    if (in_T) CK(cudaMemcpyAsync(c->sin_T.p, in_T, P * B, cudaMemcpyHostToDevice, c->st_in));
+    if (in_VEL_X) CK(cudaMemcpyAsync(c->sin_VX.p, in_VEL_X, P * B, cudaMemcpyHostToDevice, c->st_in));
+    if (in_VEL_Y) CK(cudaMemcpyAsync(c->sin_VY.p, in_VEL_Y, P * B, cudaMemcpyHostToDevice, c->st_in));
+    CK(cudaEventRecord(c->ev_in_done, c->st_in));
+    // 2. compute stream: staging -> state, the step, state -> staging
+    CK(cudaStreamWaitEvent(c->st, c->ev_in_done, 0));
+    if (in_U) CK(cudaMemcpyAsync(c->U.p, c->sin_U.p, 4 * P * B, cudaMemcpyDeviceToDevice, c->st));
+    if (in_T) CK(cudaMemcpyAsync(c->T.p, c->sin_T.p, P * B, cudaMemcpyDeviceToDevice, c->st));
+    if (in_VEL_X) CK(cudaMemcpyAsync(c->VEL_X.p, c->sin_VX.p, P * B, cudaMemcpyDeviceToDevice, c->st));
+    if (in_VEL_Y) CK(cudaMemcpyAsync(c->VEL_Y.p, c->sin_VY.p, P * B, cudaMemcpyDeviceToDevice, c->st));
+    CK(cudaEventRecord(c->ev_in_used, c->st));
+    TRY(step_once(c));
+    if (c->streamed_any) CK(cudaStreamWaitEvent(c->st, c->ev_out_done, 0));   // the previous download has left the staging
+    if (out_norms) {   // ER, ERR of this step (ns2DComp.ALE.f90:191-197): after the swap U1.p holds the state the step started from
+        long m = ((long)c->n_owned + 4095) / 4096;
+        LAUNCH(K_NORMS, k::norm_chunks, (int)std::min<long>(m, 148 * 8), 256, (long)c->n_owned, c->U1.p, c->U.p, c->redA.p);
+        TRY(reduce_levels(c, 8, m, 0));
+        CK(cudaMemcpyAsync(c->sout_N.p, c->sc->red, 8 * B, cudaMemcpyDeviceToDevice, c->st));
+    }
+    if (out_U) CK(cudaMemcpyAsync(c->sout_U.p, c->U.p, 4 * P * B, cudaMemcpyDeviceToDevice, c->st));
+    if (out_T) CK(cudaMemcpyAsync(c->sout_T.p, c->T.p, P * B, cudaMemcpyDeviceToDevice, c->st));
+    if (out_VEL_X) CK(cudaMemcpyAsync(c->sout_VX.p, c->VEL_X.p, P * B, cudaMemcpyDeviceToDevice, c->st));
+    if (out_VEL_Y) CK(cudaMemcpyAsync(c->sout_VY.p, c->VEL_Y.p, P * B, cudaMemcpyDeviceToDevice, c->st));
+    CK(cudaEventRecord(c->ev_step_done, c->st));
+    // 3. download
+    CK(cudaStreamWaitEvent(c->st_out, c->ev_step_done, 0));
+    if (out_U) CK(cudaMemcpyAsync(out_U, c->sout_U.p, 4 * P * B, cudaMemcpyDeviceToHost, c->st_out));
+    if (out_T) CK(cudaMemcpyAsync(out_T, c->sout_T.p, P * B, cudaMemcpyDeviceToHost, c->st_out));
+    if (out_VEL_X) CK(cudaMemcpyAsync(out_VEL_X, c->sout_VX.p, P * B, cudaMemcpyDeviceToHost, c->st_out));
+    if (out_VEL_Y) CK(cudaMemcpyAsync(out_VEL_Y, c->sout_VY.p, P * B, cudaMemcpyDeviceToHost, c->st_out));
+    if (out_norms) CK(cudaMemcpyAsync(out_norms, c->sout_N.p, 8 * B, cudaMemcpyDeviceToHost, c->st_out));
+    CK(cudaEventRecord(c->ev_out_done, c->st_out));
+    c->streamed_any = true;
+    return 0;
+}
+extern "C" int cfdb_streamed_wait(cfdb_ctx* c) {
+    CK(cudaSetDevice(c->device));
+    if (c->st_in) CK(cudaStreamSynchronize(c->st_in));
+    CK(cudaStreamSynchronize(c->st));
+    if (c->st_out) CK(cudaStreamSynchronize(c->st_out));
+    return 0;
+}
+
 extern "C" int cfdb_step(cfdb_ctx* c, int32_t nsteps) {
     CK(cudaSetDevice(c->device));
     for (int i = 0; i < nsteps; ++i) TRY(step_once(c));
@@ -1469,6 +1562,16 @@ extern "C" int cfdb_sync(cfdb_ctx* c) {
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->st));
     TRY(prof_resolve(c));
+    if (c->stage_stats) {   // CFDB_STAGE_STATS: where the cycles of the fused stage went (sums over the 148 CTAs)
+        unsigned long long h[k::ST_COUNT];
+        CK(cudaMemcpy(h, c->stage_stats, sizeof h, cudaMemcpyDeviceToHost));
+        CK(cudaMemset(c->stage_stats, 0, sizeof h));
+        const double tl = h[k::ST_TILES] ? (double)h[k::ST_TILES] : 1.0;
+        fprintf(stderr, "[stage_fused] cycles per tile (compute warp 0): element %.0f  node %.0f  wait inputs %.0f  wait C free %.0f  wait C full %.0f"
+                        " | loader waits: stream slot %.0f  static landed %.0f  A slot %.0f  (tiles %.0f)\n",
+                h[k::ST_E] / tl, h[k::ST_N] / tl, h[k::ST_WAIT_IN] / tl, h[k::ST_WAIT_CE] / tl, h[k::ST_WAIT_CF] / tl, h[k::ST_LD_WB] / tl,
+                h[k::ST_LD_WS] / tl, h[k::ST_LD_WA] / tl, tl);
+    }
     return 0;
 }
 extern "C" int cfdb_set_option(cfdb_ctx* c, const char* name, int32_t value) {
@@ -1939,6 +2042,298 @@ extern "C" int cfdb_laplace(cfdb_ctx* c, const int32_t* inpoel, const double* ar
     TRY(down_plain(c, c->lap_sparse.p, lap_sparse, c->nnz));
     TRY(down_plain(c, c->lap_diag.p, lap_diag, npoin));
     CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// call-site entries for the list-driven boundary conditions and for RK / fluidStructure as whole routines
+namespace {
+__global__ void k_fixvel(int m, const int* __restrict__ idx, const int* __restrict__ last, const double* __restrict__ vx,
+                         const double* __restrict__ vy, double* __restrict__ VX, double* __restrict__ VY) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    VX[idx[i]] = vx[last[i]];   // duplicates: every copy writes the value of the LAST list entry
+    VY[idx[i]] = vy[last[i]];
+}
+__global__ void k_normalvel(int m, const int* __restrict__ ip, const double* __restrict__ nx, const double* __restrict__ ny,
+                            double* __restrict__ VX, double* __restrict__ VY, const double* __restrict__ WX,
+                            const double* __restrict__ WY) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    int n = ip[i];
+    double vx = VX[n], vy = VY[n], wx = WX[n], wy = WY[n];
+    double p = -ny[i] * (vx - wx) + nx[i] * (vy - wy);   // subrutinas.f90:78-80
+    VX[n] = -ny[i] * p + wx;
+    VY[n] = nx[i] * p + wy;
+}
+__global__ void k_fix_rho(int m, const int* __restrict__ idx, const int* __restrict__ last, const double* __restrict__ val,
+                          double* __restrict__ RHO) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) RHO[idx[i]] = val[last[i]];
+}
+__global__ void k_fix_T(int m, const int* __restrict__ idx, const int* __restrict__ last, const double* __restrict__ val, double FR,
+                        const double* __restrict__ GAMM, const double* __restrict__ VX, const double* __restrict__ VY,
+                        double* __restrict__ T, double* __restrict__ E) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    int j = idx[i];
+    double GM = GAMM[j] - 1.0;
+    double t = val[last[i]];
+    T[j] = t;
+    E[j] = t * FR / GM + .5 * (VX[j] * VX[j] + VY[j] * VY[j]);   // subrutinas.f90:636-638
+}
+}  // namespace
+
+// 1-based node list -> device (0-based) + the last-wins table
+static int up_list(cfdb_ctx* c, const int32_t* list, int m, int npoin, DBuf<int>& d_idx, DBuf<int>& d_last, const char* who) {
+    vector<int32_t> i0(list, list + m), last;
+    for (int v : i0)
+        if (v < 1 || v > npoin) return fail(std::string(who) + ": node id out of range");
+    topo::last_wins(list, m, npoin, last);
+    for (auto& v : i0) v -= 1;
+    TRY(upload(c, d_idx, i0));
+    TRY(upload(c, d_last, last));
+    CK(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+extern "C" int cfdb_fixvel(cfdb_ctx* c, int32_t nfixv, const int32_t* ifixv_node, const double* rfixv_valuex,
+                           const double* rfixv_valuey, double* vel_x, double* vel_y, int32_t npoin) {
+    CK(cudaSetDevice(c->device));
+    if (npoin != c->npoin) return fail("cfdb_fixvel: npoin differs from the context");
+    DBuf<int> idx, last;
+    DBuf<double> vx, vy;
+    auto body = [&]() -> int {
+        TRY(up_list(c, ifixv_node, nfixv, npoin, idx, last, "cfdb_fixvel"));
+        TRY(upload(c, vx, rfixv_valuex, (size_t)nfixv));
+        TRY(upload(c, vy, rfixv_valuey, (size_t)nfixv));
+        TRY(up_plain(c, c->tmpA.p, vel_x, npoin));
+        TRY(up_plain(c, c->tmpB.p, vel_y, npoin));
+        if (nfixv) LAUNCH(K_FIXROWS, k_fixvel, grid_for(nfixv, 128), 128, nfixv, idx.p, last.p, vx.p, vy.p, c->tmpA.p, c->tmpB.p);
+        TRY(down_plain(c, c->tmpA.p, vel_x, npoin));
+        TRY(down_plain(c, c->tmpB.p, vel_y, npoin));
+        CK(cudaStreamSynchronize(c->st));
+        return 0;
+    };
+    int r = body();
+    idx.release(); last.release(); vx.release(); vy.release();
+    return r;
+}
+
+extern "C" int cfdb_normalvel(cfdb_ctx* c, int32_t m, const int32_t* n_ipoin, const double* n_x, const double* n_y, double* vel_x,
+                              double* vel_y, const double* w_x, const double* w_y, int32_t npoin) {
+    CK(cudaSetDevice(c->device));
+    if (npoin != c->npoin) return fail("cfdb_normalvel: npoin differs from the context");
+    DBuf<int> idx;
+    DBuf<double> nx, ny;
+    auto body = [&]() -> int {
+        vector<int32_t> i0(n_ipoin, n_ipoin + m);
+        for (auto& v : i0) {
+            if (v < 1 || v > npoin) return fail("cfdb_normalvel: n_ipoin out of range");
+            v -= 1;
+        }
+        TRY(upload(c, idx, i0));
+        TRY(upload(c, nx, n_x, (size_t)m));
+        TRY(upload(c, ny, n_y, (size_t)m));
+        TRY(up_plain(c, c->tmpA.p, vel_x, npoin));
+        TRY(up_plain(c, c->tmpB.p, vel_y, npoin));
+        TRY(up_plain(c, c->tmpC.p, w_x, npoin));
+        TRY(up_plain(c, c->by.p, w_y, npoin));
+        if (m) LAUNCH(K_FIXROWS, k_normalvel, grid_for(m, 128), 128, m, idx.p, nx.p, ny.p, c->tmpA.p, c->tmpB.p, c->tmpC.p, c->by.p);
+        TRY(down_plain(c, c->tmpA.p, vel_x, npoin));
+        TRY(down_plain(c, c->tmpB.p, vel_y, npoin));
+        CK(cudaStreamSynchronize(c->st));
+        return 0;
+    };
+    int r = body();
+    idx.release(); nx.release(); ny.release();
+    return r;
+}
+
+extern "C" int cfdb_fix(cfdb_ctx* c, double FR, const double* GAMM, int32_t nfixrho, const int32_t* ifixrho_node,
+                        const double* rfixrho_value, int32_t nfixt, const int32_t* ifixt_node, const double* rfixt_value,
+                        const double* vel_x, const double* vel_y, double* rho, double* T, double* E, int32_t npoin) {
+    CK(cudaSetDevice(c->device));
+    if (npoin != c->npoin) return fail("cfdb_fix: npoin differs from the context");
+    DBuf<int> ri, rl, ti, tl;
+    DBuf<double> rv, tv, drho, dT, dE;
+    auto body = [&]() -> int {
+        TRY(up_list(c, ifixrho_node, nfixrho, npoin, ri, rl, "cfdb_fix"));
+        TRY(up_list(c, ifixt_node, nfixt, npoin, ti, tl, "cfdb_fix"));
+        TRY(upload(c, rv, rfixrho_value, (size_t)nfixrho));
+        TRY(upload(c, tv, rfixt_value, (size_t)nfixt));
+        TRY(upload(c, drho, rho, (size_t)npoin));
+        TRY(upload(c, dT, T, (size_t)npoin));
+        TRY(upload(c, dE, E, (size_t)npoin));
+        TRY(up_plain(c, c->tmpA.p, vel_x, npoin));
+        TRY(up_plain(c, c->tmpB.p, vel_y, npoin));
+        TRY(up_plain(c, c->tmpC.p, GAMM, npoin));
+        if (nfixrho) LAUNCH(K_FIXROWS, k_fix_rho, grid_for(nfixrho, 128), 128, nfixrho, ri.p, rl.p, rv.p, drho.p);
+        if (nfixt) LAUNCH(K_FIXROWS, k_fix_T, grid_for(nfixt, 128), 128, nfixt, ti.p, tl.p, tv.p, FR, c->tmpC.p, c->tmpA.p, c->tmpB.p, dT.p, dE.p);
+        TRY(down_plain(c, drho.p, rho, npoin));
+        TRY(down_plain(c, dT.p, T, npoin));
+        TRY(down_plain(c, dE.p, E, npoin));
+        CK(cudaStreamSynchronize(c->st));
+        return 0;
+    };
+    int r = body();
+    for (auto* d : {&ri, &rl, &ti, &tl}) d->release();
+    for (auto* d : {&rv, &tv, &drho, &dT, &dE}) d->release();
+    return r;
+}
+
+// RK as a whole routine with host arrays (subrutinas.f90:645-849): the module arrays it reads (U, T, VEL_X, VEL_Y, W, GAMM,
+// the RHS history) come from the caller, those it writes go back.  Geometry, M and the BC lists are the context's.
+extern "C" int cfdb_rk(cfdb_ctx* c, double DTMIN, int32_t NRK, int32_t BANDERA, const double* GAMM, const double* dtl, const double* U,
+                       double* U1, double* RHS, double* RHS1, double* RHS2, double* RHS3, double* T, double* P, double* RHO, double* E,
+                       double* RMACH, double* VEL_X, double* VEL_Y, const double* W_X, const double* W_Y, double* SHOC, double* T_SUGN1,
+                       double* T_SUGN2, double* T_SUGN3, int32_t nelem, int32_t npoin) {
+    CK(cudaSetDevice(c->device));
+    TRY(check_mesh(c, nelem, npoin, "cfdb_rk"));
+    if (NRK != 4) return fail("cfdb_rk: NRK must be 4 (ns2DComp.ALE.f90:111)");
+    const size_t P_ = npoin;
+    TRY(up_plain(c, c->U.p, U, 4 * P_));
+    TRY(up_plain(c, c->GAMM.p, GAMM, P_));
+    TRY(up_plain(c, c->T.p, T, P_));
+    TRY(up_plain(c, c->VEL_X.p, VEL_X, P_));
+    TRY(up_plain(c, c->VEL_Y.p, VEL_Y, P_));
+    TRY(up_plain(c, c->W_X.p, W_X, P_));
+    TRY(up_plain(c, c->W_Y.p, W_Y, P_));
+    TRY(up_plain(c, c->RHS1.p, RHS1, 4 * P_));
+    TRY(up_plain(c, c->RHS2.p, RHS2, 4 * P_));
+    TRY(up_plain(c, c->RHS3.p, RHS3, 4 * P_));
+    TRY(up_elem(c, c->DTL.p, dtl));
+    if (!c->ale) { c->ale = true; TRY(zero(c, c->FC, 12 * (size_t)nelem)); }   // the caller's W is resident now
+    c->epoch++;
+    c->u1_is_u = false;
+    TRY(read_scal(c));
+    c->h_sc->DTMIN = DTMIN;
+    c->h_sc->BANDERA = BANDERA;
+    CK(cudaMemcpyAsync(c->sc, c->h_sc, sizeof(k::Scal), cudaMemcpyHostToDevice, c->st));
+    c->dtl_force = true;
+    int rc = 0;
+    for (int irk = 1; irk <= 4 && !rc; ++irk) rc = cfdb_rk_stage(c, irk);
+    c->dtl_force = false;
+    if (rc) return rc;
+    LAUNCH(K_FILL, k::rhs_history, (int)std::min<long>(grid_for(4 * (long)P_, 256), 148 * 8), 256, 4 * (long)P_, c->sc, c->RHS.p, c->RHS1.p,
+           c->RHS2.p, c->RHS3.p);
+    TRY(down_plain(c, c->U1.p, U1, 4 * P_));
+    TRY(down_plain(c, c->RHS.p, RHS, 4 * P_));
+    TRY(down_plain(c, c->RHS1.p, RHS1, 4 * P_));
+    TRY(down_plain(c, c->RHS2.p, RHS2, 4 * P_));
+    TRY(down_plain(c, c->RHS3.p, RHS3, 4 * P_));
+    struct { double* h; const double* d; } outs[] = {{T, c->T.p}, {P, c->P.p}, {RHO, c->RHO.p}, {E, c->E.p}, {RMACH, c->RMACH.p},
+                                                     {VEL_X, c->VEL_X.p}, {VEL_Y, c->VEL_Y.p}};
+    for (auto& o : outs) TRY(down_plain(c, o.d, o.h, P_));
+    CK(cudaStreamSynchronize(c->st));
+    TRY(down_elem(c, c->SHOC.p, SHOC));
+    TRY(down_elem(c, c->TS1.p, T_SUGN1));
+    TRY(down_elem(c, c->TS2.p, T_SUGN2));
+    TRY(down_elem(c, c->TS3.p, T_SUGN3));
+    return 0;
+}
+
+// fluidStructure as a whole routine with host arrays (meshMove.f90:28-142)
+extern "C" int cfdb_mesh_move(cfdb_ctx* c, double dtmin, double time, double* X, double* Y, double* X1, double* Y1, double* W_X,
+                              double* W_Y, const double* P, double* xpos, double* ypos, double fx[10], double fy[10], double rm[10],
+                              int32_t npoin) {
+    CK(cudaSetDevice(c->device));
+    if (npoin != c->npoin) return fail("cfdb_mesh_move: npoin differs from the context");
+    const size_t P_ = npoin;
+    TRY(up_plain(c, c->X.p, X, P_));
+    TRY(up_plain(c, c->Y.p, Y, P_));
+    TRY(up_plain(c, c->X1.p, X1, P_));
+    TRY(up_plain(c, c->Y1.p, Y1, P_));
+    TRY(up_plain(c, c->P.p, P, P_));
+    TRY(up_plain(c, c->xpos.p, xpos, P_));
+    TRY(up_plain(c, c->ypos.p, ypos, P_));
+    if (!c->ale) { c->ale = true; TRY(zero(c, c->FC, 12 * (size_t)c->nelem)); }
+    c->epoch++;
+    TRY(read_scal(c));
+    c->h_sc->DTMIN = dtmin;
+    CK(cudaMemcpyAsync(c->sc, c->h_sc, sizeof(k::Scal), cudaMemcpyHostToDevice, c->st));
+    TRY(cfdb_fluid_structure(c, dtmin, time));
+    struct { double* h; const double* d; } outs[] = {{X, c->X.p}, {Y, c->Y.p}, {X1, c->X1.p}, {Y1, c->Y1.p}, {W_X, c->W_X.p},
+                                                     {W_Y, c->W_Y.p}, {xpos, c->xpos.p}, {ypos, c->ypos.p}};
+    for (auto& o : outs) TRY(down_plain(c, o.d, o.h, P_));
+    TRY(read_scal(c));
+    for (int i = 0; i < 10; ++i) { fx[i] = c->h_sc->FX[i]; fy[i] = c->h_sc->FY[i]; rm[i] = c->h_sc->RM[i]; }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the print step's text files besides the GiD post file
+static int get_forces(cfdb_ctx* c, double fx[10], double fy[10], double rm[10], double fvx[10], double fvy[10]) {
+    TRY(read_scal(c));
+    for (int i = 0; i < 10; ++i) { fx[i] = c->h_sc->FX[i]; fy[i] = c->h_sc->FY[i]; rm[i] = c->h_sc->RM[i]; }
+    double fv[20];
+    CK(cudaMemcpyAsync(fv, c->fvisc.p, sizeof fv, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    for (int i = 0; i < 10; ++i) { fvx[i] = fv[i]; fvy[i] = fv[10 + i]; }
+    return 0;
+}
+extern "C" int cfdb_write_forces(cfdb_ctx* c, const char* path) {   // ns2DComp.ALE.f90:238-250
+    CK(cudaSetDevice(c->device));
+    double fx[10], fy[10], rm[10], fvx[10], fvy[10];
+    TRY(get_forces(c, fx, fy, rm, fvx, fvy));
+    std::FILE* f = std::fopen(path, "w");
+    if (!f) return fail(std::string("cfdb_write_forces: cannot open ") + path);
+    for (int s = 0; s < c->nset; ++s) {   // NSET_NUMB sets
+        std::fprintf(f, "SET NUMERO%s\n", ffmt::I(s + 1, 2).c_str());
+        std::fprintf(f, "FUERZA EN X:%s\n", ffmt::E(fx[s], 14, 5).c_str());
+        std::fprintf(f, "FUERZA EN Y:%s\n\n", ffmt::E(fy[s], 14, 5).c_str());
+        std::fprintf(f, "FUERZA VISCOSA EN X:%s\n", ffmt::E(fvx[s], 14, 5).c_str());
+        std::fprintf(f, "FUERZA VISCOSA EN Y:%s\n\n", ffmt::E(fvy[s], 14, 5).c_str());
+        std::fprintf(f, "FUERZA TOTAL EN X:%s\n", ffmt::E(fx[s] + fvx[s], 14, 5).c_str());
+        std::fprintf(f, "FUERZA TOTAL EN Y:%s\n\n", ffmt::E(fy[s] + fvy[s], 14, 5).c_str());
+    }
+    std::fclose(f);
+    return 0;
+}
+extern "C" int cfdb_write_desplazamiento(cfdb_ctx* c, const char* path, double time, int32_t append) {   // :237 '(7E13.5)'
+    CK(cudaSetDevice(c->device));
+    double fx[10], fy[10], rm[10], fvx[10], fvy[10];
+    TRY(get_forces(c, fx, fy, rm, fvx, fvy));
+    std::FILE* f = std::fopen(path, append ? "a" : "w");
+    if (!f) return fail(std::string("cfdb_write_desplazamiento: cannot open ") + path);
+    const double v[7] = {time, fvx[0], fvy[0], rm[0], fvx[1], fvy[1], rm[1]};
+    std::string s;
+    for (double x : v) s += ffmt::E(x, 13, 5);
+    std::fprintf(f, "%s\n", s.c_str());
+    std::fclose(f);
+    return 0;
+}
+extern "C" int cfdb_write_skin(cfdb_ctx* c, const char* path) {   // :833, :888  write(1, *) SKIN, xmid, press/82713.27
+    CK(cudaSetDevice(c->device));
+    const int ne = c->nedges;
+    vector<double> sk(3 * (size_t)std::max(ne, 1));
+    CK(cudaMemcpyAsync(sk.data(), c->skin.p, 3 * (size_t)std::max(ne, 1) * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    std::FILE* f = std::fopen(path, "w");
+    if (!f) return fail(std::string("cfdb_write_skin: cannot open ") + path);
+    for (int k = 0; k < ne; ++k)
+        std::fprintf(f, " %s%s%s\n", ffmt::list_r8(sk[k]).c_str(), ffmt::list_r8(sk[ne + k]).c_str(), ffmt::list_r8(sk[2 * (size_t)ne + k]).c_str());
+    std::fclose(f);
+    return 0;
+}
+
+// greedy first-fit colouring of the element list, host code: ascending element order, a 64-bit forbidden
+// mask per node, colour = lowest bit clear in the union of the three masks
+extern "C" int cfdb_color_elements(const int32_t* inpoel, int32_t nelem, int32_t npoin, int32_t* color, int32_t* ncolors) {
+    vector<uint64_t> mask((size_t)npoin, 0);
+    int nc = 0;
+    for (int e = 0; e < nelem; ++e) {
+        const int32_t* t = inpoel + 3 * (size_t)e;
+        for (int i = 0; i < 3; ++i)
+            if (t[i] < 1 || t[i] > npoin) return fail("cfdb_color_elements: inpoel entry out of range");
+        uint64_t m = mask[t[0] - 1] | mask[t[1] - 1] | mask[t[2] - 1];
+        if (~m == 0) return fail("cfdb_color_elements: more than 64 colours needed (node valence above 63)");
+        int col = __builtin_ctzll(~m);
+        color[e] = col;
+        for (int i = 0; i < 3; ++i) mask[t[i] - 1] |= 1ull << col;
+        nc = std::max(nc, col + 1);
+    }
+    *ncolors = nc;
     return 0;
 }
 

@@ -14,11 +14,10 @@
 //     nodal state of the tile's nodes by cp.async gathers (one 32-byte sector per node) tracked by the same mbarrier.
 //     Compute warps therefore never wait for HBM: their inputs are in shared memory when full[stage] completes;
 //   * compute warps: thread = element; gradients and the 12 contributions in registers (calcrhs_body, unchanged
-//     arithmetic), results to the shared-memory array C[12][TE]; contributions to tile-boundary nodes ALSO go to the global
-//     staging buffer EC.  After a CTA barrier the same threads become node threads: interior node j sums its
-//     contributions from C in ascending ORIGINAL element order (the `slots` list of the static block) and runs the nodal
-//     chain (node_finish_v) -- same operations, same order, same bits as node_update;
-//   * setmaxnreg moves registers from the loader's warpgroup to the compute warpgroups.
+//     arithmetic), results to the shared-memory array C[12][TE] (double-buffered); contributions to tile-boundary nodes
+//     ALSO go to the global staging buffer EC.  Each warp then takes its share of the PREVIOUS tile's interior nodes:
+//     node j sums its contributions from C in ascending ORIGINAL element order (the `slots` list of the static block) and
+//     runs the nodal chain (node_finish_v) -- same operations, same order, same bits as node_update;
 // Tile-boundary nodes (~20 %) are finished by node_update over the list `bnodes` right after this kernel.
 //
 // Roofline: HBM traffic per element-stage falls from 404 B (220 algorithmic + 192 staging, measured 6.46 GB per stage on the
@@ -70,19 +69,18 @@ __device__ __forceinline__ void fence_barrier_init() {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
-template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 }  // namespace ptx
 
-// offsets of the static tile block (mirror of topo::TileLayout) and of one ring stage
+// offsets of the static tile block (mirror of topo::TileLayout) and of the two shared-memory rings
 struct TileGeom {
     int TE, ntn_max, nint_max, nslot_max;
     int off_lnode, off_tnode, off_nptr, off_slots, off_bcf, tb_bytes;
-    // one stage of the ring, in bytes from the stage base
-    int st_static, st_stream, st_u, st_t, st_m, st_g, stage_bytes;
+    // A ring slot (static block + gathered nodal data), bytes from the slot base
+    int a_static, a_u, a_t, a_m, a_g, a_bytes;
+    int b_bytes;       // B ring slot: the element stream, nfields x TE doubles
     int nfields;       // doubles per element in the stream: 11, or 12 with a local time step array
-    int off_c;         // C[12][TE] from the shared-memory base (after the barriers)
-    int off_stage0;
+    int off_c;         // C[2][12][TE] from the shared-memory base (after the barriers)
+    int off_a, off_b;  // ring bases
 };
 struct StageArgs {
     int ntiles;
@@ -99,16 +97,19 @@ struct StageArgs {
     double rk_fact, FR;
     Gas g;
     double *EC, *U1, *RHS, *RHO, *VELX, *VELY, *Ea, *Pa, *Ta, *RMACH;
+    unsigned long long* stats;                     // optional (CFDB_STAGE_STATS): cycle counters, see stage_fused
 };
+enum { ST_E = 0, ST_N, ST_WAIT_IN, ST_WAIT_CE, ST_WAIT_CF, ST_LD_WB, ST_LD_WS, ST_LD_WA, ST_TILES, ST_COUNT };
 
-// everything a compute thread reads for its element comes from the ring stage `sb` (shared memory)
+// The arithmetic of one element from shared memory: `sa` is the tile's A slot (connectivity + nodal state), `sbm` its B slot
+// (element stream).  v = the twelve contributions, ln = tile-local node of each vertex.
 template <bool VISC, bool NB>
-__device__ __forceinline__ unsigned fused_elem(const TileGeom& G, const StageArgs& A, const unsigned char* sb, double* C,
-                                               int k, int nint, long e_glob, double dtl_uniform) {
+__device__ __forceinline__ unsigned fused_elem_math(const TileGeom& G, const StageArgs& A, const unsigned char* sa, const unsigned char* sbm,
+                                                    int k, double dtl_uniform, double (&v)[3][4], int (&ln)[3]) {
     const int TE = G.TE;
-    const unsigned short* lnode = reinterpret_cast<const unsigned short*>(sb + G.st_static + G.off_lnode);
-    const int ln[3] = {lnode[k], lnode[TE + k], lnode[2 * TE + k]};
-    const double* ut = reinterpret_cast<const double*>(sb + G.st_u);
+    const unsigned short* lnode = reinterpret_cast<const unsigned short*>(sa + G.a_static + G.off_lnode);
+    ln[0] = lnode[k]; ln[1] = lnode[TE + k]; ln[2] = lnode[2 * TE + k];
+    const double* ut = reinterpret_cast<const double*>(sa + G.a_u);
     double Un[3][4], Th[3][4], Tn[3] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
@@ -117,10 +118,10 @@ __device__ __forceinline__ unsigned fused_elem(const TileGeom& G, const StageArg
         Un[j][0] = a.x; Un[j][1] = a.y; Un[j][2] = b.x; Un[j][3] = b.y;
     }
     if (VISC) {
-        const double* tt = reinterpret_cast<const double*>(sb + G.st_t);
+        const double* tt = reinterpret_cast<const double*>(sa + G.a_t);
         Tn[0] = tt[ln[0]]; Tn[1] = tt[ln[1]]; Tn[2] = tt[ln[2]];
     }
-    const double* sd = reinterpret_cast<const double*>(sb + G.st_stream);
+    const double* sd = reinterpret_cast<const double*>(sbm);
     double Nx[3] = {sd[k], sd[TE + k], sd[2 * TE + k]};
     double Ny[3] = {sd[3 * TE + k], sd[4 * TE + k], sd[5 * TE + k]};
     const double ar = sd[6 * TE + k];
@@ -131,118 +132,150 @@ __device__ __forceinline__ unsigned fused_elem(const TileGeom& G, const StageArg
     unsigned bad = 0;
     calcrhs_body<VISC, false, NB>(A.g, Un, Th, Tn, Nx, Ny, tau, shoc_e, Ux, Uy, rt, &bad);
 #pragma unroll
-    for (int n = 0; n < 3; ++n) {
-        double v[4];
+    for (int n = 0; n < 3; ++n)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            v[i] = NB ? ex::div3_nb(rt[n][i] * ar * dtl, bad) : ex::div3(rt[n][i] * ar * dtl);
-            C[(4 * n + i) * TE + k] = v[i];
-        }
-        if (ln[n] >= nint) st4(A.EC + 12 * e_glob + 4 * n, v);   // tile-boundary node: finished by node_update afterwards
-    }
+        for (int i = 0; i < 4; ++i) v[n][i] = NB ? ex::div3_nb(rt[n][i] * ar * dtl, bad) : ex::div3(rt[n][i] * ar * dtl);
     return bad;
 }
 template <bool VISC>
-__device__ __noinline__ void fused_elem_plain(const TileGeom& G, const StageArgs& A, const unsigned char* sb, double* C, int k,
-                                              int nint, long e_glob, double dtl_uniform) {
-    fused_elem<VISC, false>(G, A, sb, C, k, nint, e_glob, dtl_uniform);
+__device__ __noinline__ void fused_elem_plain(const TileGeom& G, const StageArgs& A, const unsigned char* sa, const unsigned char* sbm, int k,
+                                              double dtl_uniform, double (&v)[3][4], int (&ln)[3]) {
+    fused_elem_math<VISC, false>(G, A, sa, sbm, k, dtl_uniform, v, ln);
 }
 
-// NCW compute warps (a multiple of 4) + one auxiliary warpgroup whose warp 0 is the loader; TE = 32*NCW elements per tile
-template <bool VISC, int NCW, int RC, int RA>
-__global__ void __launch_bounds__((NCW + 4) * 32, 1) stage_fused(const __grid_constant__ TileGeom G, const __grid_constant__ StageArgs A) {
+// NCW compute warps + ONE loader warp; TE = 32*NCW elements per tile.  One CTA per SM.  The register file is split over the
+// four SM sub-partitions (16384 registers each, warps dealt round-robin), so the per-thread budget is set by the fullest
+// sub-partition: 16 warps (NCW = 15) -> 128 registers, 12 warps (NCW = 11) -> 168; 13/14 warps (NCW = 12/13) -> 128.
+//
+// Pipeline (all hand-overs are mbarriers; no CTA-wide barrier in the steady state, warps drift freely):
+//   loader      : stream(i) -> B ring [NBR slots]; gathers(i) (U, T, M, GAMM of the tile's nodes, addresses from the static
+//                 block that landed earlier) -> A ring [NA slots]; static block of tile i+1 -> A ring, one tile ahead of its
+//                 gathers so that the two dependent round trips to HBM never sit on a compute warp's path;
+//   compute warp: E(i): its 32 elements of tile i from A(i), B(i) -> registers; wait until C[i&1] is free (node phase i-2
+//                 done everywhere: long ago); C[i&1] <- contributions; release B(i).
+//                 N(i-1): its share of the interior nodes of the PREVIOUS tile from C[(i-1)&1] and A(i-1) -- every warp
+//                 finished E(i-1) a whole element ago, so this wait is free too; release C[(i-1)&1] and A(i-1).
+//   The node phase (gather chains, 4 divisions + a square root per node, scattered stores) therefore runs in the shadow
+//   of other warps' element arithmetic instead of idling the fp64 pipe between two barriers.
+template <bool VISC, int NCW, int NA, int NBR>
+__global__ void __launch_bounds__((NCW + 1) * 32, 1) stage_fused(const __grid_constant__ TileGeom G, const __grid_constant__ StageArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
-    constexpr int NSTAGE = 2;
     constexpr int NCT = NCW * 32;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // barriers: full[s] (33 arrivals: the loader's expect_tx + one cp.async arrival per loader lane, plus the bulk bytes),
-    // fstat[s] (static block landed; 1 arrival + bytes), empty[s] (NCW arrivals: one per compute warp)
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem);
-    const unsigned full0 = ptx::smem_u32(bars), fstat0 = full0 + 8 * NSTAGE, empty0 = fstat0 + 8 * NSTAGE;
+    // barriers (8 bytes each): astat[NA] static block landed (1 arrival + bytes); afull[NA] gathers landed (32 cp.async
+    // arrivals); aempty[NA] (NCW arrivals, after the node phase); bfull[NBR] (1 + bytes); bempty[NBR] (NCW, after the element
+    // phase); cfull[2], cempty[2] (NCW each)
+    const unsigned bar0 = ptx::smem_u32(smem);
+    const unsigned astat0 = bar0, afull0 = astat0 + 8 * NA, aempty0 = afull0 + 8 * NA, bfull0 = aempty0 + 8 * NA,
+                   bempty0 = bfull0 + 8 * NBR, cfull0 = bempty0 + 8 * NBR, cempty0 = cfull0 + 16;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGE; ++s) {
-            ptx::mbar_init(full0 + 8 * s, 33);
-            ptx::mbar_init(fstat0 + 8 * s, 1);
-            ptx::mbar_init(empty0 + 8 * s, NCW);
+        for (int s = 0; s < NA; ++s) {
+            ptx::mbar_init(astat0 + 8 * s, 1);
+            ptx::mbar_init(afull0 + 8 * s, 32);
+            ptx::mbar_init(aempty0 + 8 * s, NCW);
+        }
+        for (int s = 0; s < NBR; ++s) {
+            ptx::mbar_init(bfull0 + 8 * s, 1);
+            ptx::mbar_init(bempty0 + 8 * s, NCW);
+        }
+        for (int s = 0; s < 2; ++s) {
+            ptx::mbar_init(cfull0 + 8 * s, NCW);
+            ptx::mbar_init(cempty0 + 8 * s, NCW);
         }
         ptx::fence_barrier_init();
     }
     __syncthreads();
-    double* C = reinterpret_cast<double*>(smem + G.off_c);
     const int TE = G.TE;
-    if (warp >= NCW) {
-        // ---------------- auxiliary warpgroup: give registers away; warp NCW is the loader -----------------------
-        ptx::reg_dec<RA>();
-        if (warp != NCW) return;
-        const unsigned stream_bytes = (unsigned)(G.nfields * TE * 8);
-        int it = 0;
-        for (int t = blockIdx.x; t < A.ntiles; t += gridDim.x, ++it) {
-            const int s = it & 1;
-            const unsigned ph = (it >> 1) & 1;
-            unsigned char* sb = smem + G.off_stage0 + (size_t)s * G.stage_bytes;
-            const unsigned sbu = ptx::smem_u32(sb);
-            ptx::mbar_wait(empty0 + 8 * s, ph ^ 1);
+    // optional cycle counters (CFDB_STAGE_STATS): warp 0 reports the compute side, the loader its own waits; kept in shared
+    // memory so that they cost no registers
+    unsigned long long* st = reinterpret_cast<unsigned long long*>(smem + 176);   // barriers end at byte 160 (NA = 4), C starts at 256
+    if (threadIdx.x < ST_COUNT) st[threadIdx.x] = 0;
+    __syncthreads();
+    const bool stat = A.stats != nullptr && lane == 0 && (warp == 0 || warp == NCW);
+    auto waitc = [&](unsigned bar, unsigned par, int slot) {   // wait, with the cycles charged to st[slot] on the reporting lanes
+        if (ptx::mbar_try_wait(bar, par)) return;
+        const long long t0 = clock64();
+        ptx::mbar_wait(bar, par);
+        if (stat) st[slot] += (unsigned long long)(clock64() - t0);
+    };
+    if (warp == NCW) {
+        // ---------------- loader warp ----------------------------------------------------------------------------
+        const unsigned stream_bytes = (unsigned)G.b_bytes;
+        auto issue_static = [&](int it2, int t2) {
+            const int sa = it2 % NA;
+            waitc(aempty0 + 8 * sa, ((it2 / NA) & 1) ^ 1, ST_LD_WA);
             if (lane == 0) {
-                ptx::mbar_arrive_expect_tx(fstat0 + 8 * s, (unsigned)G.tb_bytes);
-                ptx::bulk_g2s(sbu + G.st_static, A.TB + (size_t)t * G.tb_bytes, (unsigned)G.tb_bytes, fstat0 + 8 * s);
-                ptx::mbar_arrive_expect_tx(full0 + 8 * s, stream_bytes);
-                const size_t e0 = (size_t)t * TE;
-                const unsigned fb = (unsigned)(TE * 8), dst = sbu + G.st_stream;
-#pragma unroll 1
-                for (int f = 0; f < 7; ++f) ptx::bulk_g2s(dst + f * fb, A.geo + (size_t)f * A.Epad + e0, fb, full0 + 8 * s);
-                ptx::bulk_g2s(dst + 7 * fb, A.shoc + e0, fb, full0 + 8 * s);
-                ptx::bulk_g2s(dst + 8 * fb, A.ts1 + e0, fb, full0 + 8 * s);
-                ptx::bulk_g2s(dst + 9 * fb, A.ts2 + e0, fb, full0 + 8 * s);
-                ptx::bulk_g2s(dst + 10 * fb, A.ts3 + e0, fb, full0 + 8 * s);
-                if (G.nfields == 12) ptx::bulk_g2s(dst + 11 * fb, A.dtl_arr + e0, fb, full0 + 8 * s);
+                ptx::mbar_arrive_expect_tx(astat0 + 8 * sa, (unsigned)G.tb_bytes);
+                ptx::bulk_g2s(ptx::smem_u32(smem + G.off_a + (size_t)sa * G.a_bytes + G.a_static), A.TB + (size_t)t2 * G.tb_bytes,
+                              (unsigned)G.tb_bytes, astat0 + 8 * sa);
             }
-            ptx::mbar_wait(fstat0 + 8 * s, ph);
-            const int* hdr = reinterpret_cast<const int*>(sb + G.st_static);
+        };
+        int it = 0, t = blockIdx.x;
+        if (t < A.ntiles) issue_static(0, t);
+        for (; t < A.ntiles; t += gridDim.x, ++it) {
+            // element stream of tile it
+            const int sb = it % NBR;
+            waitc(bempty0 + 8 * sb, ((it / NBR) & 1) ^ 1, ST_LD_WB);
+            if (lane == 0) {
+                ptx::mbar_arrive_expect_tx(bfull0 + 8 * sb, stream_bytes);
+                const size_t e0 = (size_t)t * TE;
+                const unsigned fb = (unsigned)(TE * 8), dst = ptx::smem_u32(smem + G.off_b + (size_t)sb * G.b_bytes), bar = bfull0 + 8 * sb;
+#pragma unroll 1
+                for (int f = 0; f < 7; ++f) ptx::bulk_g2s(dst + f * fb, A.geo + (size_t)f * A.Epad + e0, fb, bar);
+                ptx::bulk_g2s(dst + 7 * fb, A.shoc + e0, fb, bar);
+                ptx::bulk_g2s(dst + 8 * fb, A.ts1 + e0, fb, bar);
+                ptx::bulk_g2s(dst + 9 * fb, A.ts2 + e0, fb, bar);
+                ptx::bulk_g2s(dst + 10 * fb, A.ts3 + e0, fb, bar);
+                if (G.nfields == 12) ptx::bulk_g2s(dst + 11 * fb, A.dtl_arr + e0, fb, bar);
+            }
+            // nodal state of tile it (its static block was requested one tile ago)
+            const int sa = it % NA;
+            unsigned char* ab = smem + G.off_a + (size_t)sa * G.a_bytes;
+            const unsigned abu = ptx::smem_u32(ab);
+            waitc(astat0 + 8 * sa, (it / NA) & 1, ST_LD_WS);
+            const int* hdr = reinterpret_cast<const int*>(ab + G.a_static);
             const int ntn = hdr[1], nint = hdr[2];
-            const int* tnode = reinterpret_cast<const int*>(sb + G.st_static + G.off_tnode);
+            const int* tnode = reinterpret_cast<const int*>(ab + G.a_static + G.off_tnode);
             for (int j = lane; j < ntn; j += 32) {
                 const int n = tnode[j];
                 const double* u = A.Usrc + 4 * (size_t)n;
-                ptx::cp_async16(sbu + G.st_u + 32 * j, u);
-                ptx::cp_async16(sbu + G.st_u + 32 * j + 16, u + 2);
-                if (VISC) ptx::cp_async8(sbu + G.st_t + 8 * j, A.T + n);
+                ptx::cp_async16(abu + G.a_u + 32 * j, u);
+                ptx::cp_async16(abu + G.a_u + 32 * j + 16, u + 2);
+                if (VISC) ptx::cp_async8(abu + G.a_t + 8 * j, A.T + n);
             }
             for (int j = lane; j < nint; j += 32) {
                 const int n = tnode[j];
-                ptx::cp_async8(sbu + G.st_m + 8 * j, A.M + n);
-                ptx::cp_async8(sbu + G.st_g + 8 * j, A.GAMM + n);
+                ptx::cp_async8(abu + G.a_m + 8 * j, A.M + n);
+                ptx::cp_async8(abu + G.a_g + 8 * j, A.GAMM + n);
             }
-            ptx::cp_async_arrive_noinc(full0 + 8 * s);
+            ptx::cp_async_arrive_noinc(afull0 + 8 * sa);
+            // static block of the next tile
+            if (t + (int)gridDim.x < A.ntiles) issue_static(it + 1, t + gridDim.x);
+        }
+        if (stat) {
+            atomicAdd(A.stats + ST_LD_WB, st[ST_LD_WB]);
+            atomicAdd(A.stats + ST_LD_WS, st[ST_LD_WS]);
+            atomicAdd(A.stats + ST_LD_WA, st[ST_LD_WA]);
         }
         return;
     }
-    // ---------------- compute warpgroups --------------------------------------------------------------------------
-    ptx::reg_inc<RC>();
+    // ---------------- compute warps -------------------------------------------------------------------------------
     const double dtl_uniform = G.nfields == 12 ? 0.0 : *A.dtl_sc;
-    const int k = threadIdx.x;   // element position in the tile, then interior-node index
-    int it = 0;
-    for (int t = blockIdx.x; t < A.ntiles; t += gridDim.x, ++it) {
-        const int s = it & 1;
-        const unsigned ph = (it >> 1) & 1;
-        const unsigned char* sb = smem + G.off_stage0 + (size_t)s * G.stage_bytes;
-        ptx::mbar_wait(fstat0 + 8 * s, ph);
-        ptx::mbar_wait(full0 + 8 * s, ph);
-        const int* hdr = reinterpret_cast<const int*>(sb + G.st_static);
-        const int ne = hdr[0], nint = hdr[2];
-        if (k < ne) {
-            const long e_glob = (long)t * TE + k;
-            if (VISC) {
-                if (fused_elem<VISC, true>(G, A, sb, C, k, nint, e_glob, dtl_uniform))
-                    fused_elem_plain<VISC>(G, A, sb, C, k, nint, e_glob, dtl_uniform);
-            } else {
-                fused_elem<VISC, false>(G, A, sb, C, k, nint, e_glob, dtl_uniform);
-            }
-        }
-        ptx::named_bar_sync(1, NCT);   // C complete
-        for (int j = k; j < nint; j += NCT) {
-            const int* tnode = reinterpret_cast<const int*>(sb + G.st_static + G.off_tnode);
-            const unsigned short* nptr = reinterpret_cast<const unsigned short*>(sb + G.st_static + G.off_nptr);
-            const unsigned short* slots = reinterpret_cast<const unsigned short*>(sb + G.st_static + G.off_slots);
+    const int k = threadIdx.x;   // element position in the tile
+    double* const Cbase = reinterpret_cast<double*>(smem + G.off_c);
+    auto node_phase = [&](int j_it) {
+        const int cj = j_it & 1, sa = j_it % NA;
+        const unsigned char* ab = smem + G.off_a + (size_t)sa * G.a_bytes;
+        const double* C = Cbase + (size_t)cj * 12 * TE;
+        waitc(cfull0 + 8 * cj, (j_it >> 1) & 1, ST_WAIT_CF);
+        const long long t0 = stat ? clock64() : 0;
+        const int* hdr = reinterpret_cast<const int*>(ab + G.a_static);
+        const int nint = hdr[2];
+        const int* tnode = reinterpret_cast<const int*>(ab + G.a_static + G.off_tnode);
+        const unsigned short* nptr = reinterpret_cast<const unsigned short*>(ab + G.a_static + G.off_nptr);
+        const unsigned short* slots = reinterpret_cast<const unsigned short*>(ab + G.a_static + G.off_slots);
+        // interior node j -> warp j % NCW, lane (j / NCW) % 32: every warp gets the same share, whatever nint is
+        for (int j = lane * NCW + warp; j < nint; j += NCT) {
             const int n = tnode[j];
             double acc[4] = {0.0, 0.0, 0.0, 0.0};
             const int q1 = nptr[j + 1];
@@ -254,20 +287,71 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1) stage_fused(const __grid_co
             st4(A.RHS + 4 * (size_t)n, acc);
             double u[4];
             if (A.U == A.Usrc) {   // the tile's copy of the state is the state the update starts from
-                const double2* q = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(sb + G.st_u) + 4 * j);
+                const double2* q = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(ab + G.a_u) + 4 * j);
                 double2 a = q[0], b = q[1];
                 u[0] = a.x; u[1] = a.y; u[2] = b.x; u[3] = b.y;
             } else {
                 ld4(A.U + 4 * (size_t)n, u);
             }
-            const double m = reinterpret_cast<const double*>(sb + G.st_m)[j];
-            const double gam = reinterpret_cast<const double*>(sb + G.st_g)[j];
-            const unsigned fl = (sb + G.st_static + G.off_bcf)[j];
+            const double m = reinterpret_cast<const double*>(ab + G.a_m)[j];
+            const double gam = reinterpret_cast<const double*>(ab + G.a_g)[j];
+            const unsigned fl = (ab + G.a_static + G.off_bcf)[j];
             node_finish_v(n, acc, u, m, gam, fl, A.WXa, A.WYa, A.bc, A.rk_fact, A.FR, A.U1, A.RHO, A.VELX, A.VELY, A.Ea, A.Pa,
                           A.Ta, A.RMACH);
         }
-        ptx::named_bar_sync(1, NCT);   // C and the stage may be overwritten
-        if (lane == 0) ptx::mbar_arrive(empty0 + 8 * s);
+        __syncwarp();
+        if (lane == 0) {
+            ptx::mbar_arrive(cempty0 + 8 * cj);
+            ptx::mbar_arrive(aempty0 + 8 * sa);
+        }
+        if (stat) st[ST_N] += (unsigned long long)(clock64() - t0);
+    };
+    int it = 0;
+    for (int t = blockIdx.x; t < A.ntiles; t += gridDim.x, ++it) {
+        const int sa = it % NA, sb = it % NBR, c = it & 1;
+        const unsigned char* ab = smem + G.off_a + (size_t)sa * G.a_bytes;
+        const unsigned char* bb = smem + G.off_b + (size_t)sb * G.b_bytes;
+        waitc(afull0 + 8 * sa, (it / NA) & 1, ST_WAIT_IN);
+        waitc(bfull0 + 8 * sb, (it / NBR) & 1, ST_WAIT_IN);
+        const long long t0 = stat ? clock64() : 0;
+        const int* hdr = reinterpret_cast<const int*>(ab + G.a_static);
+        const int ne = hdr[0], nint = hdr[2];
+        double v[3][4];
+        int ln[3] = {0, 0, 0};
+        if (k < ne) {
+            if (VISC) {
+                if (fused_elem_math<VISC, true>(G, A, ab, bb, k, dtl_uniform, v, ln)) fused_elem_plain<VISC>(G, A, ab, bb, k, dtl_uniform, v, ln);
+            } else {
+                fused_elem_math<VISC, false>(G, A, ab, bb, k, dtl_uniform, v, ln);
+            }
+        }
+        if (stat) st[ST_E] += (unsigned long long)(clock64() - t0);
+        waitc(cempty0 + 8 * c, ((it >> 1) & 1) ^ 1, ST_WAIT_CE);   // node phase it-2 is done everywhere: C[c] is free
+        if (k < ne) {
+            double* C = Cbase + (size_t)c * 12 * TE;
+            const long e_glob = (long)t * TE + k;
+#pragma unroll
+            for (int n = 0; n < 3; ++n) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) C[(4 * n + i) * TE + k] = v[n][i];
+                if (ln[n] >= nint) st4(A.EC + 12 * e_glob + 4 * n, v[n]);   // tile-boundary node: finished by node_update afterwards
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            ptx::mbar_arrive(cfull0 + 8 * c);
+            ptx::mbar_arrive(bempty0 + 8 * sb);
+        }
+        if (it > 0) node_phase(it - 1);
+    }
+    if (it > 0) node_phase(it - 1);
+    if (stat) {
+        atomicAdd(A.stats + ST_E, st[ST_E]);
+        atomicAdd(A.stats + ST_N, st[ST_N]);
+        atomicAdd(A.stats + ST_WAIT_IN, st[ST_WAIT_IN]);
+        atomicAdd(A.stats + ST_WAIT_CE, st[ST_WAIT_CE]);
+        atomicAdd(A.stats + ST_WAIT_CF, st[ST_WAIT_CF]);
+        atomicAdd(A.stats + ST_TILES, (unsigned long long)it);
     }
 }
 

@@ -96,6 +96,19 @@ class NSComp2D:
     def sync(self):
         capi.check(self.L.cfdb_sync(self.h))
 
+    def step_streamed(self, ins, outs, norms=None):
+        """cfdb_step_streamed: one step whose state comes from / goes back to host arrays (dicts keyed U, T, VEL_X, VEL_Y of
+        contiguous float64 numpy arrays, ideally pinned; missing keys are not transferred), pipelined: returns at once."""
+        def p(d, k):
+            a = d.get(k) if d else None
+            return a.ctypes.data_as(C.c_void_p) if a is not None else None
+        n = norms.ctypes.data_as(C.c_void_p) if norms is not None else None
+        capi.check(self.L.cfdb_step_streamed(self.h, p(ins, "U"), p(ins, "T"), p(ins, "VEL_X"), p(ins, "VEL_Y"), p(outs, "U"), p(outs, "T"),
+                                             p(outs, "VEL_X"), p(outs, "VEL_Y"), n))
+
+    def streamed_wait(self):
+        capi.check(self.L.cfdb_streamed_wait(self.h))
+
     def rk_stage(self, irk):
         capi.check(self.L.cfdb_rk_stage(self.h, irk))
 
@@ -272,6 +285,37 @@ class NSComp2D:
         r = C.c_double()
         capi.check(self.L.cfdb_vecdot(self.h, x.size, x, y, C.byref(r)))
         return r.value
+
+    def fixvel(self, ifixv_node, rfixv_valuex, rfixv_valuey, vel_x, vel_y):
+        capi.check(self.L.cfdb_fixvel(self.h, ifixv_node.size, ifixv_node, rfixv_valuex, rfixv_valuey, vel_x, vel_y, self.npoin))
+
+    def normalvel(self, n_ipoin, n_x, n_y, vel_x, vel_y, w_x, w_y):
+        capi.check(self.L.cfdb_normalvel(self.h, n_ipoin.size, n_ipoin, n_x, n_y, vel_x, vel_y, w_x, w_y, self.npoin))
+
+    def fix(self, FR, GAMM, ifixrho_node, rfixrho_value, ifixt_node, rfixt_value, vel_x, vel_y, rho, T, E):
+        capi.check(self.L.cfdb_fix(self.h, FR, GAMM, ifixrho_node.size, ifixrho_node, rfixrho_value, ifixt_node.size, ifixt_node,
+                                   rfixt_value, vel_x, vel_y, rho, T, E, self.npoin))
+
+    def rk_callsite(self, DTMIN, NRK, BANDERA, GAMM, dtl, U, U1, RHS, RHS1, RHS2, RHS3, T, P, RHO, E, RMACH, VEL_X, VEL_Y, W_X, W_Y,
+                    SHOC, T_SUGN1, T_SUGN2, T_SUGN3):
+        """RK(DTMIN, NRK, BANDERA, GAMM, dtl) (subrutinas.f90:645) with the module arrays it touches as host arrays"""
+        capi.check(self.L.cfdb_rk(self.h, DTMIN, NRK, BANDERA, GAMM, dtl, U, U1, RHS, RHS1, RHS2, RHS3, T, P, RHO, E, RMACH, VEL_X, VEL_Y,
+                                  W_X, W_Y, SHOC, T_SUGN1, T_SUGN2, T_SUGN3, self.nelem, self.npoin))
+
+    def mesh_move(self, dtmin, time, X, Y, X1, Y1, W_X, W_Y, P, xpos, ypos):
+        """fluidStructure(dtmin, time, SMOOTH_FIX, x1, y1) (meshMove.f90:28) with host arrays -> (FX, FY, RM)"""
+        fx, fy, rm = np.zeros(10), np.zeros(10), np.zeros(10)
+        capi.check(self.L.cfdb_mesh_move(self.h, dtmin, time, X, Y, X1, Y1, W_X, W_Y, P, xpos, ypos, fx, fy, rm, self.npoin))
+        return fx, fy, rm
+
+    def write_forces(self, path):
+        capi.check(self.L.cfdb_write_forces(self.h, str(path).encode()))
+
+    def write_desplazamiento(self, path, time, append=False):
+        capi.check(self.L.cfdb_write_desplazamiento(self.h, str(path).encode(), float(time), int(append)))
+
+    def write_skin(self, path):
+        capi.check(self.L.cfdb_write_skin(self.h, str(path).encode()))
 
     def gcl_main(self, M, W_x, W_y, W_x_old, W_y_old, area_old, dNx, dNy, area, dt):
         capi.check(self.L.cfdb_gcl_main(self.h, M, W_x, W_y, W_x_old, W_y_old, area_old, dNx, dNy, area, self.lc.inpoel,

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 
 namespace ffmt {
@@ -70,6 +71,40 @@ inline std::string cnv_record(int iter, double time, const double r[4]) {
     std::string s = I(iter, 7) + E(time, 14, 6);
     for (int i = 0; i < 4; ++i) s += E(r[i], 14, 6);
     return s;
+}
+
+// One REAL(8) item of a list-directed WRITE as gfortran lays it out: the G25.17E3 editing with a scale factor of 1 that
+// libgfortran applies to kind-8 reals -- 17 significant digits in a field of 25: F editing with five trailing blanks when
+// 0.1 <= |x| < 1e17 (and for zero), otherwise d.ddddddddddddddddE+ddd.  List-directed output is processor-dependent
+// (F2008 10.10.4); this is the layout of the build line the oracle assumes (fortran/README.md), e.g.
+//   3.14d0 -> "   3.1400000000000001     "    1.d-3 -> "   1.0000000000000000E-003"    0.d0 -> "   0.0000000000000000     "
+inline std::string list_r8(double v) {
+    const int w = 25, d = 17;
+    std::string s;
+    if (std::isnan(v)) return rjust("NaN", w);
+    if (std::isinf(v)) return rjust(v < 0 ? "-Infinity" : "Infinity", w);
+    const double a = std::fabs(v);
+    char buf[128];
+    if (a == 0.0) {
+        std::snprintf(buf, sizeof buf, "%.*f", d - 1, 0.0);
+        s = std::string(std::signbit(v) ? "-" : "") + buf + "     ";
+        return rjust(s, w);
+    }
+    // decimal exponent after rounding to d significant digits
+    std::snprintf(buf, sizeof buf, "%.*e", d - 1, a);
+    const int ex = std::atoi(std::strchr(buf, 'e') + 1);   // a = m x 10^ex, 1 <= m < 10
+    if (ex >= -1 && ex < d) {
+        // F editing: d significant digits in all (a leading "0." digit does not count)
+        const int decimals = ex >= 0 ? d - 1 - ex : d;
+        std::snprintf(buf, sizeof buf, "%.*f", decimals, a);
+        s = std::string(v < 0 ? "-" : "") + buf + (decimals == 0 ? "." : "") + "     ";   // Fw.0 keeps its decimal point
+    } else {
+        std::string m(buf, std::strchr(buf, 'e') - buf);
+        char eb[16];
+        std::snprintf(eb, sizeof eb, "E%+04d", ex);
+        s = std::string(v < 0 ? "-" : "") + m + eb;
+    }
+    return rjust(s, w);
 }
 
 }  // namespace ffmt

@@ -1176,6 +1176,17 @@ void orc_set_scalar(void* h, const char* name, double v) {
     else if (n == "use_cuarto") s.use_cuarto = (int)v;
     else if (n == "true_rk") s.true_rk = (int)v;
 }
+// threads of the OpenMP build: n > 0 sets the team size (bench.py: all host cores, whatever OMP_NUM_THREADS the launcher
+// exported -- torch.distributed.run sets it to 1); returns the size in effect
+int orc_set_omp_threads(int n) {
+#ifdef ORC_OMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
 int orc_omp_threads() {
 #ifdef ORC_OMP
     return omp_get_max_threads();

@@ -94,6 +94,8 @@ def lib(omp=False):
     L.orc_gcl_main.argtypes = [_dp] * 9 + [_ip, C.c_int, C.c_int, C.c_double]
     L.orc_smoothing.argtypes = [_dp, _dp, _ip, np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS"), C.c_int, C.c_int]
     L.orc_omp_threads.restype = C.c_int
+    L.orc_set_omp_threads.argtypes = [C.c_int]
+    L.orc_set_omp_threads.restype = C.c_int
     _libs[key] = L
     return L
 
