@@ -442,14 +442,13 @@ static int ensure_host_topology(cfdb_ctx* c) {
 // cfdb_create: the device topology has been built from the file-order connectivity (so every per-node list is in ascending
 // FILE-order element id, the reference's summation order); from here on the element arrays live in tile order.
 //   CFDB_NO_PERM=1   keep the file's element order (tiles = runs of consecutive elements)
-//   CFDB_TILE_TE=352|384|416 tile size (352 default)
+//   CFDB_TILE_TE=384|512 tile size (384 default)
 static int build_stage_tiles(cfdb_ctx* c, const int32_t* inpoel, const double* X, const double* Y) {
     const size_t E = c->nelem, P = c->npoin;
-    // TE = 32 x compute warps.  The register file is split over the four SM sub-partitions, so the per-thread budget follows
-    // from the warps ONE sub-partition holds: 12 warps per CTA (11 compute + the loader) leave 168 registers per thread,
-    // 13 or 14 warps leave 128.  Shared memory (two C buffers, the A and B rings) caps TE at 416.
-    int TE = getenv("CFDB_TILE_TE") ? atoi(getenv("CFDB_TILE_TE")) : 352;
-    if (TE != 352 && TE != 384 && TE != 416) return fail("CFDB_TILE_TE must be 352, 384 or 416");
+    // TE = 32 x element warps (stage_fused.cuh): 12 element warps at 152 registers + 4 auxiliary warps at 56; 16 + 4 at
+    // 112 / 32 is kept for experiments but needs more shared memory than an SM has once the mesh is large
+    int TE = getenv("CFDB_TILE_TE") ? atoi(getenv("CFDB_TILE_TE")) : 384;
+    if (TE != 384 && TE != 512) return fail("CFDB_TILE_TE must be 384 or 512");
     const bool permute = getenv("CFDB_NO_PERM") == nullptr;
     // host copies of esup2 / eslot (file order)
     vector<int32_t> esup2(P + 1), eslot(3 * E), esup1(3 * E);
@@ -507,13 +506,17 @@ static int build_stage_tiles(cfdb_ctx* c, const int32_t* inpoel, const double* X
     G.b_bytes = up128(G.nfields * TE * 8);
     G.off_c = 256;
     G.off_a = up128(G.off_c + 2 * 12 * TE * 8);
-    c->tile_na = TE == 352 ? 4 : 3;
+    c->tile_na = 3;
     G.off_b = G.off_a + c->tile_na * G.a_bytes;
     c->stage_smem = (size_t)G.off_b + 2 * (size_t)G.b_bytes;
     int smem_max = 0;
     CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
     c->tiles_ok = c->stage_smem <= (size_t)smem_max;   // else: the two-kernel stage (very high valence / odd meshes)
     c->geo_dirty = true;
+    if (getenv("CFDB_STAGE_STATS") && !c->stage_stats) {
+        CK(cudaMalloc(&c->stage_stats, k::ST_COUNT * sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(c->stage_stats, 0, k::ST_COUNT * sizeof(unsigned long long), c->st));
+    }
     if (getenv("CFDB_VERBOSE"))
         fprintf(stderr, "[cfdb_create] tiles: TE %d, %d tiles, interior nodes %.3f, nodes/tile <= %d (interior <= %d), block %d B, smem %zu B%s\n",
                 TE, c->ntiles, c->tile_interior, L.ntn_max, L.nint_max, L.tb_bytes, c->stage_smem, c->tiles_ok ? "" : " (too large: fused stage off)");
@@ -674,6 +677,7 @@ extern "C" void cfdb_destroy(cfdb_ctx* c) {
     c->lpos.release();
     c->bcflag.release();
     c->i2e.release(); c->e2i.release(); c->bnodes.release(); c->TB.release(); c->geo.release();
+    if (c->stage_stats) cudaFree(c->stage_stats);
     c->isfix.release();
     c->bp2.release(); c->by2.release(); c->pos_aux2.release();
     for (auto* d : {&c->X, &c->Y, &c->X1, &c->Y1, &c->area, &c->HH, &c->HHX, &c->HHY, &c->dNx, &c->dNy, &c->M, &c->U, &c->U1,
@@ -1027,23 +1031,17 @@ static int run_stage_fused(cfdb_ctx* c, const k::Gas& g, const double* dtl_arr, 
     G.nfields = dtl_arr ? 12 : 11;
     if (G.nfields > c->tgeom.nfields) return fail("run_stage_fused: stage layout was sized without a local time step array");
     void (*kern)(const k::TileGeom, const k::StageArgs) = nullptr;
-    if (c->tile_ncw == 11) kern = visc ? k::stage_fused<true, 11, 4, 2> : k::stage_fused<false, 11, 4, 2>;
-    else if (c->tile_ncw == 13) kern = visc ? k::stage_fused<true, 13, 3, 2> : k::stage_fused<false, 13, 3, 2>;
+    if (c->tile_ncw == 16) kern = visc ? k::stage_fused<true, 16, 3, 2> : k::stage_fused<false, 16, 3, 2>;
     else kern = visc ? k::stage_fused<true, 12, 3, 2> : k::stage_fused<false, 12, 3, 2>;
-    static const bool want_stats = getenv("CFDB_STAGE_STATS") != nullptr;
-    if (want_stats && !c->stage_stats) {
-        CK(cudaMalloc(&c->stage_stats, k::ST_COUNT * sizeof(unsigned long long)));
-        CK(cudaMemsetAsync(c->stage_stats, 0, k::ST_COUNT * sizeof(unsigned long long), c->st));
-    }
     A.stats = c->stage_stats;
-    static std::map<const void*, bool> attr_done;
-    if (!attr_done[(const void*)kern]) {
+    static std::map<const void*, size_t> attr_done;   // per kernel: the largest dynamic shared-memory size opted into so far
+    if (attr_done[(const void*)kern] < c->stage_smem) {
         CK(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->stage_smem));
-        attr_done[(const void*)kern] = true;
+        attr_done[(const void*)kern] = c->stage_smem;
     }
     static int nsm = 0;
     if (!nsm) CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->device));
-    const int grid = std::min(c->ntiles, nsm), block = (c->tile_ncw + 1) * 32;
+    const int grid = std::min(c->ntiles, nsm), block = (c->tile_ncw + 4) * 32;
     cudaEvent_t _a = nullptr, _b = nullptr;
     TRY(prof_begin(c, c->st, K_STAGE, &_a, &_b));
     kern<<<grid, block, c->stage_smem, c->st>>>(G, A);

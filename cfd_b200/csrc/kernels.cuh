@@ -887,22 +887,12 @@ struct BcTab {
 
 // The nodal chain of RK after the ordered sum (subrutinas.f90:695-826): U1 = U - rk/M*RHS, primitives, fixvel ->
 // normalvel -> FIX, conservative.  Shared by node_update and the tile-fused stage kernel.
-__device__ __forceinline__ void node_finish_v(int n, const double (&acc)[4], const double (&u)[4], double m, double gam,
-                                              unsigned fl, const double* __restrict__ WXa, const double* __restrict__ WYa,
-                                              const BcTab& bc, double rk_fact, double FR, double* __restrict__ U1,
-                                              double* __restrict__ RHO, double* __restrict__ VELX, double* __restrict__ VELY,
-                                              double* __restrict__ Ea, double* __restrict__ Pa, double* __restrict__ Ta,
-                                              double* __restrict__ RMACH) {
-    double f = rk_fact / m;
-    double u1[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) u1[i] = u[i] - f * acc[i];
-    double rho = u1[0];
-    double vx = u1[1] / rho, vy = u1[2] / rho, en = u1[3] / rho;
-    double VEL2 = (vx * vx + vy * vy);
-    double p = rho * (gam - 1.0) * (en - .5 * VEL2);
-    double t = p / (rho * FR);
-    double mach = sqrt(VEL2 / (t * gam * FR));
+// boundary conditions (fixvel -> normalvel -> FIX) and the conservative state, from the primitives of one node
+__device__ __forceinline__ void node_bc_store(int n, double rho, double vx, double vy, double en, double p, double t, double mach,
+                                              double gam, unsigned fl, const double* __restrict__ WXa, const double* __restrict__ WYa,
+                                              const BcTab& bc, double FR, double* __restrict__ U1, double* __restrict__ RHO,
+                                              double* __restrict__ VELX, double* __restrict__ VELY, double* __restrict__ Ea,
+                                              double* __restrict__ Pa, double* __restrict__ Ta, double* __restrict__ RMACH) {
     if (fl) {
         int lo = 0, hi = bc.nb - 1;
         while (lo < hi) {
@@ -931,6 +921,57 @@ __device__ __forceinline__ void node_finish_v(int n, const double (&acc)[4], con
     double o[4] = {rho, vx * rho, vy * rho, en * rho};
     st4(U1 + 4 * (size_t)n, o);
     RHO[n] = rho; VELX[n] = vx; VELY[n] = vy; Ea[n] = en; Pa[n] = p; Ta[n] = t; RMACH[n] = mach;
+}
+__device__ __forceinline__ void node_finish_v(int n, const double (&acc)[4], const double (&u)[4], double m, double gam,
+                                              unsigned fl, const double* __restrict__ WXa, const double* __restrict__ WYa,
+                                              const BcTab& bc, double rk_fact, double FR, double* __restrict__ U1,
+                                              double* __restrict__ RHO, double* __restrict__ VELX, double* __restrict__ VELY,
+                                              double* __restrict__ Ea, double* __restrict__ Pa, double* __restrict__ Ta,
+                                              double* __restrict__ RMACH) {
+    double f = rk_fact / m;
+    double u1[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) u1[i] = u[i] - f * acc[i];
+    double rho = u1[0];
+    double vx = u1[1] / rho, vy = u1[2] / rho, en = u1[3] / rho;
+    double VEL2 = (vx * vx + vy * vy);
+    double p = rho * (gam - 1.0) * (en - .5 * VEL2);
+    double t = p / (rho * FR);
+    double mach = sqrt(VEL2 / (t * gam * FR));
+    node_bc_store(n, rho, vx, vy, en, p, t, mach, gam, fl, WXa, WYa, bc, FR, U1, RHO, VELX, VELY, Ea, Pa, Ta, RMACH);
+}
+// The same chain with the branch-free divisions and square root of exact.cuh (same operations on the same values; the five
+// quotients and the root are straight-line code whose reciprocal refinements the scheduler overlaps): returns the fast-path
+// flag and stores nothing when it is raised -- the caller then runs node_finish_v.
+__device__ __forceinline__ unsigned node_finish_nb(int n, const double (&acc)[4], const double (&u)[4], double m, double gam,
+                                                   unsigned fl, const double* __restrict__ WXa, const double* __restrict__ WYa,
+                                                   const BcTab& bc, double rk_fact, double FR, double* __restrict__ U1,
+                                                   double* __restrict__ RHO, double* __restrict__ VELX, double* __restrict__ VELY,
+                                                   double* __restrict__ Ea, double* __restrict__ Pa, double* __restrict__ Ta,
+                                                   double* __restrict__ RMACH) {
+    unsigned bad = 0;
+    double f = ex::Recip(m).div(rk_fact, bad);
+    double u1[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) u1[i] = u[i] - f * acc[i];
+    double rho = u1[0];
+    const ex::Recip dr(rho);
+    double vx = dr.div(u1[1], bad), vy = dr.div(u1[2], bad), en = dr.div(u1[3], bad);
+    double VEL2 = (vx * vx + vy * vy);
+    double p = rho * (gam - 1.0) * (en - .5 * VEL2);
+    double t = ex::Recip(rho * FR).div(p, bad);
+    double mach = ex::sqrt_nb(ex::Recip(t * gam * FR).div(VEL2, bad), bad);
+    if (bad) return bad;
+    node_bc_store(n, rho, vx, vy, en, p, t, mach, gam, fl, WXa, WYa, bc, FR, U1, RHO, VELX, VELY, Ea, Pa, Ta, RMACH);
+    return 0;
+}
+__device__ __noinline__ void node_finish_plain(int n, const double (&acc)[4], const double (&u)[4], double m, double gam,
+                                               unsigned fl, const double* __restrict__ WXa, const double* __restrict__ WYa,
+                                               const BcTab& bc, double rk_fact, double FR, double* __restrict__ U1,
+                                               double* __restrict__ RHO, double* __restrict__ VELX, double* __restrict__ VELY,
+                                               double* __restrict__ Ea, double* __restrict__ Pa, double* __restrict__ Ta,
+                                               double* __restrict__ RMACH) {
+    node_finish_v(n, acc, u, m, gam, fl, WXa, WYa, bc, rk_fact, FR, U1, RHO, VELX, VELY, Ea, Pa, Ta, RMACH);
 }
 __device__ __forceinline__ void node_finish(int n, const double (&acc)[4], const double* __restrict__ U,
                                             const double* __restrict__ M, const double* __restrict__ GAMM,

@@ -69,6 +69,8 @@ __device__ __forceinline__ void fence_barrier_init() {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
 }  // namespace ptx
 
 // offsets of the static tile block (mirror of topo::TileLayout) and of the two shared-memory rings
@@ -143,28 +145,37 @@ __device__ __noinline__ void fused_elem_plain(const TileGeom& G, const StageArgs
     fused_elem_math<VISC, false>(G, A, sa, sbm, k, dtl_uniform, v, ln);
 }
 
-// NCW compute warps + ONE loader warp; TE = 32*NCW elements per tile.  One CTA per SM.  The register file is split over the
-// four SM sub-partitions (16384 registers each, warps dealt round-robin), so the per-thread budget is set by the fullest
-// sub-partition: 16 warps (NCW = 15) -> 128 registers, 12 warps (NCW = 11) -> 168; 13/14 warps (NCW = 12/13) -> 128.
+// Warp roles.  NCW element warps (a multiple of 4) + one auxiliary warpgroup: warp NCW is the loader, warps NCW+1..NCW+3 are
+// node warps; TE = 32*NCW elements per tile; one CTA per SM.
 //
-// Pipeline (all hand-overs are mbarriers; no CTA-wide barrier in the steady state, warps drift freely):
-//   loader      : stream(i) -> B ring [NBR slots]; gathers(i) (U, T, M, GAMM of the tile's nodes, addresses from the static
-//                 block that landed earlier) -> A ring [NA slots]; static block of tile i+1 -> A ring, one tile ahead of its
-//                 gathers so that the two dependent round trips to HBM never sit on a compute warp's path;
-//   compute warp: E(i): its 32 elements of tile i from A(i), B(i) -> registers; wait until C[i&1] is free (node phase i-2
-//                 done everywhere: long ago); C[i&1] <- contributions; release B(i).
-//                 N(i-1): its share of the interior nodes of the PREVIOUS tile from C[(i-1)&1] and A(i-1) -- every warp
-//                 finished E(i-1) a whole element ago, so this wait is free too; release C[(i-1)&1] and A(i-1).
-//   The node phase (gather chains, 4 divisions + a square root per node, scattered stores) therefore runs in the shadow
-//   of other warps' element arithmetic instead of idling the fp64 pipe between two barriers.
+// Registers.  The register file is split over the four SM sub-partitions (16384 registers each, warps dealt round-robin), so
+// with 16 warps per CTA every sub-partition holds three element warps and one auxiliary warp, launched at 128 registers per
+// thread.  setmaxnreg then moves registers from the auxiliary warpgroup (56 each: the nodal chain needs ~48) to the element
+// warpgroups (152 each: the branch-free form of the element arithmetic runs without spills and its single-warp schedule is
+// within 40 % of the fp64 issue time, tools/sass_stalls.py).  3 x 152 + 56 = 4 x 128: what the element warps claim is exactly
+// what the auxiliary warpgroup released (the registers a warpgroup may claim come from its own CTA's pool).
+//
+// Pipeline (all hand-overs are mbarriers; no CTA-wide barrier in the steady state):
+//   loader       : stream(i) -> B ring [NBR slots]; gathers(i) (U, T, M, GAMM of the tile's nodes, addresses from the static
+//                  block that landed earlier) -> A ring [NA slots]; static block of tile i+1 -> A ring, one tile ahead of its
+//                  gathers so that the two dependent round trips to HBM never sit on an element warp's path;
+//   element warps: E(i): 32 elements each from A(i), B(i) -> registers; wait until C[i&1] is free (node phase i-2 done: long
+//                  ago); C[i&1] <- contributions (+ EC for tile-boundary nodes); release B(i), their share of A(i).  They do
+//                  nothing else: with three of them per sub-partition the fp64 pipe sees a pure arithmetic stream;
+//   node warps   : N(i): wait C[i&1] full; interior node j sums its contributions from C in ascending ORIGINAL element order
+//                  and runs the nodal chain; release C[i&1] and A(i).  Gather chains, four divisions and a square root per
+//                  node, scattered stores: latency-bound work that now runs beside the element arithmetic instead of
+//                  interrupting it.
 template <bool VISC, int NCW, int NA, int NBR>
-__global__ void __launch_bounds__((NCW + 1) * 32, 1) stage_fused(const __grid_constant__ TileGeom G, const __grid_constant__ StageArgs A) {
+__global__ void __launch_bounds__((NCW + 4) * 32, 1) stage_fused(const __grid_constant__ TileGeom G, const __grid_constant__ StageArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
-    constexpr int NCT = NCW * 32;
+    constexpr int NNW = 3;                       // node warps
+    constexpr int NNT = NNW * 32;
+    constexpr int RE = (NCW == 12) ? 152 : 112;  // registers per thread of an element warp after the hand-over
+    constexpr int RAUX = (NCW == 12) ? 56 : 32;  //                  ... of an auxiliary warp      (NCW*RE + 4*RAUX == (NCW+4) * launch registers)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // barriers (8 bytes each): astat[NA] static block landed (1 arrival + bytes); afull[NA] gathers landed (32 cp.async
-    // arrivals); aempty[NA] (NCW arrivals, after the node phase); bfull[NBR] (1 + bytes); bempty[NBR] (NCW, after the element
-    // phase); cfull[2], cempty[2] (NCW each)
+    // arrivals); aempty[NA] (NCW + NNW arrivals); bfull[NBR] (1 + bytes); bempty[NBR] (NCW); cfull[2] (NCW); cempty[2] (NNW)
     const unsigned bar0 = ptx::smem_u32(smem);
     const unsigned astat0 = bar0, afull0 = astat0 + 8 * NA, aempty0 = afull0 + 8 * NA, bfull0 = aempty0 + 8 * NA,
                    bempty0 = bfull0 + 8 * NBR, cfull0 = bempty0 + 8 * NBR, cempty0 = cfull0 + 16;
@@ -172,7 +183,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) stage_fused(const __grid_co
         for (int s = 0; s < NA; ++s) {
             ptx::mbar_init(astat0 + 8 * s, 1);
             ptx::mbar_init(afull0 + 8 * s, 32);
-            ptx::mbar_init(aempty0 + 8 * s, NCW);
+            ptx::mbar_init(aempty0 + 8 * s, NCW + NNW);
         }
         for (int s = 0; s < NBR; ++s) {
             ptx::mbar_init(bfull0 + 8 * s, 1);
@@ -180,134 +191,149 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) stage_fused(const __grid_co
         }
         for (int s = 0; s < 2; ++s) {
             ptx::mbar_init(cfull0 + 8 * s, NCW);
-            ptx::mbar_init(cempty0 + 8 * s, NCW);
+            ptx::mbar_init(cempty0 + 8 * s, NNW);
         }
         ptx::fence_barrier_init();
     }
-    __syncthreads();
     const int TE = G.TE;
-    // optional cycle counters (CFDB_STAGE_STATS): warp 0 reports the compute side, the loader its own waits; kept in shared
-    // memory so that they cost no registers
+    // optional cycle counters (CFDB_STAGE_STATS): element warp 0, node warp 0 and the loader report; kept in shared memory so
+    // that they cost no registers
     unsigned long long* st = reinterpret_cast<unsigned long long*>(smem + 176);   // barriers end at byte 160 (NA = 4), C starts at 256
     if (threadIdx.x < ST_COUNT) st[threadIdx.x] = 0;
     __syncthreads();
-    const bool stat = A.stats != nullptr && lane == 0 && (warp == 0 || warp == NCW);
+    const bool stat = A.stats != nullptr && lane == 0 && (warp == 0 || warp == NCW || warp == NCW + 1);
     auto waitc = [&](unsigned bar, unsigned par, int slot) {   // wait, with the cycles charged to st[slot] on the reporting lanes
         if (ptx::mbar_try_wait(bar, par)) return;
         const long long t0 = clock64();
         ptx::mbar_wait(bar, par);
         if (stat) st[slot] += (unsigned long long)(clock64() - t0);
     };
-    if (warp == NCW) {
-        // ---------------- loader warp ----------------------------------------------------------------------------
-        const unsigned stream_bytes = (unsigned)G.b_bytes;
-        auto issue_static = [&](int it2, int t2) {
-            const int sa = it2 % NA;
-            waitc(aempty0 + 8 * sa, ((it2 / NA) & 1) ^ 1, ST_LD_WA);
-            if (lane == 0) {
-                ptx::mbar_arrive_expect_tx(astat0 + 8 * sa, (unsigned)G.tb_bytes);
-                ptx::bulk_g2s(ptx::smem_u32(smem + G.off_a + (size_t)sa * G.a_bytes + G.a_static), A.TB + (size_t)t2 * G.tb_bytes,
-                              (unsigned)G.tb_bytes, astat0 + 8 * sa);
-            }
-        };
-        int it = 0, t = blockIdx.x;
-        if (t < A.ntiles) issue_static(0, t);
-        for (; t < A.ntiles; t += gridDim.x, ++it) {
-            // element stream of tile it
-            const int sb = it % NBR;
-            waitc(bempty0 + 8 * sb, ((it / NBR) & 1) ^ 1, ST_LD_WB);
-            if (lane == 0) {
-                ptx::mbar_arrive_expect_tx(bfull0 + 8 * sb, stream_bytes);
-                const size_t e0 = (size_t)t * TE;
-                const unsigned fb = (unsigned)(TE * 8), dst = ptx::smem_u32(smem + G.off_b + (size_t)sb * G.b_bytes), bar = bfull0 + 8 * sb;
+    const int my_tiles = A.ntiles > (int)blockIdx.x ? (A.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    double* const Cbase = reinterpret_cast<double*>(smem + G.off_c);
+    if (warp >= NCW) {
+        ptx::reg_dec<RAUX>();
+        if (warp == NCW) {
+            // ---------------- loader warp ------------------------------------------------------------------------
+            const unsigned stream_bytes = (unsigned)G.b_bytes;
+            auto issue_static = [&](int it2, int t2) {
+                const int sa = it2 % NA;
+                waitc(aempty0 + 8 * sa, ((it2 / NA) & 1) ^ 1, ST_LD_WA);
+                if (lane == 0) {
+                    ptx::mbar_arrive_expect_tx(astat0 + 8 * sa, (unsigned)G.tb_bytes);
+                    ptx::bulk_g2s(ptx::smem_u32(smem + G.off_a + (size_t)sa * G.a_bytes + G.a_static), A.TB + (size_t)t2 * G.tb_bytes,
+                                  (unsigned)G.tb_bytes, astat0 + 8 * sa);
+                }
+            };
+            int it = 0, t = blockIdx.x;
+            if (t < A.ntiles) issue_static(0, t);
+            for (; t < A.ntiles; t += gridDim.x, ++it) {
+                // element stream of tile it
+                const int sb = it % NBR;
+                waitc(bempty0 + 8 * sb, ((it / NBR) & 1) ^ 1, ST_LD_WB);
+                if (lane == 0) {
+                    ptx::mbar_arrive_expect_tx(bfull0 + 8 * sb, stream_bytes);
+                    const size_t e0 = (size_t)t * TE;
+                    const unsigned fb = (unsigned)(TE * 8), dst = ptx::smem_u32(smem + G.off_b + (size_t)sb * G.b_bytes), bar = bfull0 + 8 * sb;
 #pragma unroll 1
-                for (int f = 0; f < 7; ++f) ptx::bulk_g2s(dst + f * fb, A.geo + (size_t)f * A.Epad + e0, fb, bar);
-                ptx::bulk_g2s(dst + 7 * fb, A.shoc + e0, fb, bar);
-                ptx::bulk_g2s(dst + 8 * fb, A.ts1 + e0, fb, bar);
-                ptx::bulk_g2s(dst + 9 * fb, A.ts2 + e0, fb, bar);
-                ptx::bulk_g2s(dst + 10 * fb, A.ts3 + e0, fb, bar);
-                if (G.nfields == 12) ptx::bulk_g2s(dst + 11 * fb, A.dtl_arr + e0, fb, bar);
+                    for (int f = 0; f < 7; ++f) ptx::bulk_g2s(dst + f * fb, A.geo + (size_t)f * A.Epad + e0, fb, bar);
+                    ptx::bulk_g2s(dst + 7 * fb, A.shoc + e0, fb, bar);
+                    ptx::bulk_g2s(dst + 8 * fb, A.ts1 + e0, fb, bar);
+                    ptx::bulk_g2s(dst + 9 * fb, A.ts2 + e0, fb, bar);
+                    ptx::bulk_g2s(dst + 10 * fb, A.ts3 + e0, fb, bar);
+                    if (G.nfields == 12) ptx::bulk_g2s(dst + 11 * fb, A.dtl_arr + e0, fb, bar);
+                }
+                // nodal state of tile it (its static block was requested one tile ago)
+                const int sa = it % NA;
+                unsigned char* ab = smem + G.off_a + (size_t)sa * G.a_bytes;
+                const unsigned abu = ptx::smem_u32(ab);
+                waitc(astat0 + 8 * sa, (it / NA) & 1, ST_LD_WS);
+                const int* hdr = reinterpret_cast<const int*>(ab + G.a_static);
+                const int ntn = hdr[1], nint = hdr[2];
+                const int* tnode = reinterpret_cast<const int*>(ab + G.a_static + G.off_tnode);
+#pragma unroll 1
+                for (int j = lane; j < ntn; j += 32) {
+                    const int n = tnode[j];
+                    const double* u = A.Usrc + 4 * (size_t)n;
+                    ptx::cp_async16(abu + G.a_u + 32 * j, u);
+                    ptx::cp_async16(abu + G.a_u + 32 * j + 16, u + 2);
+                    if (VISC) ptx::cp_async8(abu + G.a_t + 8 * j, A.T + n);
+                }
+#pragma unroll 1
+                for (int j = lane; j < nint; j += 32) {
+                    const int n = tnode[j];
+                    ptx::cp_async8(abu + G.a_m + 8 * j, A.M + n);
+                    ptx::cp_async8(abu + G.a_g + 8 * j, A.GAMM + n);
+                }
+                ptx::cp_async_arrive_noinc(afull0 + 8 * sa);
+                // static block of the next tile
+                if (t + (int)gridDim.x < A.ntiles) issue_static(it + 1, t + gridDim.x);
             }
-            // nodal state of tile it (its static block was requested one tile ago)
-            const int sa = it % NA;
-            unsigned char* ab = smem + G.off_a + (size_t)sa * G.a_bytes;
-            const unsigned abu = ptx::smem_u32(ab);
-            waitc(astat0 + 8 * sa, (it / NA) & 1, ST_LD_WS);
+            if (stat) {
+                atomicAdd(A.stats + ST_LD_WB, st[ST_LD_WB]);
+                atomicAdd(A.stats + ST_LD_WS, st[ST_LD_WS]);
+                atomicAdd(A.stats + ST_LD_WA, st[ST_LD_WA]);
+            }
+            return;
+        }
+        // ---------------- node warps -----------------------------------------------------------------------------
+        const int nt = (warp - NCW - 1) * 32 + lane;   // 0 .. NNT-1
+        for (int it = 0; it < my_tiles; ++it) {
+            const int cj = it & 1, sa = it % NA;
+            const unsigned char* ab = smem + G.off_a + (size_t)sa * G.a_bytes;
+            const double* C = Cbase + (size_t)cj * 12 * TE;
+            waitc(cfull0 + 8 * cj, (it >> 1) & 1, ST_WAIT_CF);
+            const long long t0 = stat ? clock64() : 0;
             const int* hdr = reinterpret_cast<const int*>(ab + G.a_static);
-            const int ntn = hdr[1], nint = hdr[2];
+            const int nint = hdr[2];
             const int* tnode = reinterpret_cast<const int*>(ab + G.a_static + G.off_tnode);
-            for (int j = lane; j < ntn; j += 32) {
+            const unsigned short* nptr = reinterpret_cast<const unsigned short*>(ab + G.a_static + G.off_nptr);
+            const unsigned short* slots = reinterpret_cast<const unsigned short*>(ab + G.a_static + G.off_slots);
+#pragma unroll 1
+            for (int j = nt; j < nint; j += NNT) {
                 const int n = tnode[j];
-                const double* u = A.Usrc + 4 * (size_t)n;
-                ptx::cp_async16(abu + G.a_u + 32 * j, u);
-                ptx::cp_async16(abu + G.a_u + 32 * j + 16, u + 2);
-                if (VISC) ptx::cp_async8(abu + G.a_t + 8 * j, A.T + n);
+                double acc[4] = {0.0, 0.0, 0.0, 0.0};
+                const int q1 = nptr[j + 1];
+                for (int q = nptr[j]; q < q1; ++q) {
+                    const int sl = slots[q];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[i] = acc[i] + C[sl + i * TE];
+                }
+                st4(A.RHS + 4 * (size_t)n, acc);
+                double u[4];
+                if (A.U == A.Usrc) {   // the tile's copy of the state is the state the update starts from
+                    const double2* q = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(ab + G.a_u) + 4 * j);
+                    double2 a = q[0], b = q[1];
+                    u[0] = a.x; u[1] = a.y; u[2] = b.x; u[3] = b.y;
+                } else {
+                    ld4(A.U + 4 * (size_t)n, u);
+                }
+                const double m = reinterpret_cast<const double*>(ab + G.a_m)[j];
+                const double gam = reinterpret_cast<const double*>(ab + G.a_g)[j];
+                const unsigned fl = (ab + G.a_static + G.off_bcf)[j];
+                if (node_finish_nb(n, acc, u, m, gam, fl, A.WXa, A.WYa, A.bc, A.rk_fact, A.FR, A.U1, A.RHO, A.VELX, A.VELY, A.Ea, A.Pa,
+                                   A.Ta, A.RMACH))
+                    node_finish_plain(n, acc, u, m, gam, fl, A.WXa, A.WYa, A.bc, A.rk_fact, A.FR, A.U1, A.RHO, A.VELX, A.VELY, A.Ea,
+                                      A.Pa, A.Ta, A.RMACH);
             }
-            for (int j = lane; j < nint; j += 32) {
-                const int n = tnode[j];
-                ptx::cp_async8(abu + G.a_m + 8 * j, A.M + n);
-                ptx::cp_async8(abu + G.a_g + 8 * j, A.GAMM + n);
+            __syncwarp();
+            if (lane == 0) {
+                ptx::mbar_arrive(cempty0 + 8 * cj);
+                ptx::mbar_arrive(aempty0 + 8 * sa);
             }
-            ptx::cp_async_arrive_noinc(afull0 + 8 * sa);
-            // static block of the next tile
-            if (t + (int)gridDim.x < A.ntiles) issue_static(it + 1, t + gridDim.x);
+            if (stat) st[ST_N] += (unsigned long long)(clock64() - t0);
         }
         if (stat) {
-            atomicAdd(A.stats + ST_LD_WB, st[ST_LD_WB]);
-            atomicAdd(A.stats + ST_LD_WS, st[ST_LD_WS]);
-            atomicAdd(A.stats + ST_LD_WA, st[ST_LD_WA]);
+            atomicAdd(A.stats + ST_N, st[ST_N]);
+            atomicAdd(A.stats + ST_WAIT_CF, st[ST_WAIT_CF]);
         }
         return;
     }
-    // ---------------- compute warps -------------------------------------------------------------------------------
+    // ---------------- element warps -------------------------------------------------------------------------------
+    ptx::reg_inc<RE>();
     const double dtl_uniform = G.nfields == 12 ? 0.0 : *A.dtl_sc;
     const int k = threadIdx.x;   // element position in the tile
-    double* const Cbase = reinterpret_cast<double*>(smem + G.off_c);
-    auto node_phase = [&](int j_it) {
-        const int cj = j_it & 1, sa = j_it % NA;
-        const unsigned char* ab = smem + G.off_a + (size_t)sa * G.a_bytes;
-        const double* C = Cbase + (size_t)cj * 12 * TE;
-        waitc(cfull0 + 8 * cj, (j_it >> 1) & 1, ST_WAIT_CF);
-        const long long t0 = stat ? clock64() : 0;
-        const int* hdr = reinterpret_cast<const int*>(ab + G.a_static);
-        const int nint = hdr[2];
-        const int* tnode = reinterpret_cast<const int*>(ab + G.a_static + G.off_tnode);
-        const unsigned short* nptr = reinterpret_cast<const unsigned short*>(ab + G.a_static + G.off_nptr);
-        const unsigned short* slots = reinterpret_cast<const unsigned short*>(ab + G.a_static + G.off_slots);
-        // interior node j -> warp j % NCW, lane (j / NCW) % 32: every warp gets the same share, whatever nint is
-        for (int j = lane * NCW + warp; j < nint; j += NCT) {
-            const int n = tnode[j];
-            double acc[4] = {0.0, 0.0, 0.0, 0.0};
-            const int q1 = nptr[j + 1];
-            for (int q = nptr[j]; q < q1; ++q) {
-                const int sl = slots[q];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc[i] = acc[i] + C[sl + i * TE];
-            }
-            st4(A.RHS + 4 * (size_t)n, acc);
-            double u[4];
-            if (A.U == A.Usrc) {   // the tile's copy of the state is the state the update starts from
-                const double2* q = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(ab + G.a_u) + 4 * j);
-                double2 a = q[0], b = q[1];
-                u[0] = a.x; u[1] = a.y; u[2] = b.x; u[3] = b.y;
-            } else {
-                ld4(A.U + 4 * (size_t)n, u);
-            }
-            const double m = reinterpret_cast<const double*>(ab + G.a_m)[j];
-            const double gam = reinterpret_cast<const double*>(ab + G.a_g)[j];
-            const unsigned fl = (ab + G.a_static + G.off_bcf)[j];
-            node_finish_v(n, acc, u, m, gam, fl, A.WXa, A.WYa, A.bc, A.rk_fact, A.FR, A.U1, A.RHO, A.VELX, A.VELY, A.Ea, A.Pa,
-                          A.Ta, A.RMACH);
-        }
-        __syncwarp();
-        if (lane == 0) {
-            ptx::mbar_arrive(cempty0 + 8 * cj);
-            ptx::mbar_arrive(aempty0 + 8 * sa);
-        }
-        if (stat) st[ST_N] += (unsigned long long)(clock64() - t0);
-    };
-    int it = 0;
-    for (int t = blockIdx.x; t < A.ntiles; t += gridDim.x, ++it) {
+    int t = blockIdx.x;
+    for (int it = 0; it < my_tiles; ++it, t += gridDim.x) {
         const int sa = it % NA, sb = it % NBR, c = it & 1;
         const unsigned char* ab = smem + G.off_a + (size_t)sa * G.a_bytes;
         const unsigned char* bb = smem + G.off_b + (size_t)sb * G.b_bytes;
@@ -319,14 +345,11 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) stage_fused(const __grid_co
         double v[3][4];
         int ln[3] = {0, 0, 0};
         if (k < ne) {
-            if (VISC) {
-                if (fused_elem_math<VISC, true>(G, A, ab, bb, k, dtl_uniform, v, ln)) fused_elem_plain<VISC>(G, A, ab, bb, k, dtl_uniform, v, ln);
-            } else {
-                fused_elem_math<VISC, false>(G, A, ab, bb, k, dtl_uniform, v, ln);
-            }
+            // branch-free divisions (exact.cuh) first; the plain form only if an operand left their range
+            if (fused_elem_math<VISC, true>(G, A, ab, bb, k, dtl_uniform, v, ln)) fused_elem_plain<VISC>(G, A, ab, bb, k, dtl_uniform, v, ln);
         }
         if (stat) st[ST_E] += (unsigned long long)(clock64() - t0);
-        waitc(cempty0 + 8 * c, ((it >> 1) & 1) ^ 1, ST_WAIT_CE);   // node phase it-2 is done everywhere: C[c] is free
+        waitc(cempty0 + 8 * c, ((it >> 1) & 1) ^ 1, ST_WAIT_CE);   // node phase it-2 is done: C[c] is free
         if (k < ne) {
             double* C = Cbase + (size_t)c * 12 * TE;
             const long e_glob = (long)t * TE + k;
@@ -341,17 +364,14 @@ __global__ void __launch_bounds__((NCW + 1) * 32, 1) stage_fused(const __grid_co
         if (lane == 0) {
             ptx::mbar_arrive(cfull0 + 8 * c);
             ptx::mbar_arrive(bempty0 + 8 * sb);
+            ptx::mbar_arrive(aempty0 + 8 * sa);
         }
-        if (it > 0) node_phase(it - 1);
     }
-    if (it > 0) node_phase(it - 1);
     if (stat) {
         atomicAdd(A.stats + ST_E, st[ST_E]);
-        atomicAdd(A.stats + ST_N, st[ST_N]);
         atomicAdd(A.stats + ST_WAIT_IN, st[ST_WAIT_IN]);
         atomicAdd(A.stats + ST_WAIT_CE, st[ST_WAIT_CE]);
-        atomicAdd(A.stats + ST_WAIT_CF, st[ST_WAIT_CF]);
-        atomicAdd(A.stats + ST_TILES, (unsigned long long)it);
+        atomicAdd(A.stats + ST_TILES, (unsigned long long)my_tiles);
     }
 }
 

@@ -26,7 +26,8 @@ def _vp(a):
 
 
 class NSComp2D:
-    def __init__(self, lc: LoadedCase, device: int = 0, use_gcl: int = 0, init: bool = True, smooth: bool = False):
+    def __init__(self, lc: LoadedCase, device: int = 0, use_gcl: int = 0, init: bool = True, smooth: bool = False,
+                 restart_path: str | None = None):
         self.L = capi.lib()
         self.lc = lc
         if smooth:  # ns2DComp.ALE.f90:63-76: SMOOTH_FIX = I_M + IFM nodes, then the one-time mesh optimiser
@@ -46,12 +47,19 @@ class NSComp2D:
         capi.check(self.L.cfdb_create(C.byref(self.h), C.byref(self.par), lc.npoin, lc.nelem, lc.X, lc.Y, lc.inpoel,
                                       C.byref(bc), device))
         self.npoin, self.nelem = lc.npoin, lc.nelem
+        # IRESTART == 1 (ns2DComp.ALE.f90:423-431): the state comes from <name>.RST -- never silently a free-stream start
+        self._restart_path = restart_path
+        if int(lc.par.get("IRESTART", 0)) == 1 and restart_path is None:
+            self.close()
+            raise capi.CfdbError("the deck says IRESTART = 1: pass restart_path=<name>.RST (ns2DComp.ALE.f90:423-431)")
         if init:
-            capi.check(self.L.cfdb_init(self.h))
+            self.init()
 
     def init(self):
         """ns2DComp.ALE.f90:59-136 on the device (cfdb_init); the constructor calls it unless init=False."""
         capi.check(self.L.cfdb_init(self.h))
+        if int(self.lc.par.get("IRESTART", 0)) == 1:
+            self.restart(self._restart_path)
 
     def close(self):
         if getattr(self, "h", None) is not None and self.h.value:

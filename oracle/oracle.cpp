@@ -644,6 +644,8 @@ struct Solver {
     int ITER = 0, BANDERA = 1, ITERPRINT = 0, norms_every_step = 1;
     int use_cuarto = 0;  // "next" N1: keep CUARTO_ORDEN's projection instead of UN = 0.0 (subrutinas.f90:674)
     int true_rk = 0;     // "next" N2: stages 2..4 evaluate calcRHS/FUENTE at U1 instead of U
+    int adamsb = 0;      // "next" N2: ADAMSB replaces RK when BANDERA > 4, the call commented out at ns2DComp.ALE.f90:174-178
+    int NESTAB = 1;      // ns2DComp.ALE.f90:134
     int last_bicg_iters[2] = {0, 0};
     double ER[4], ERR[4];
 };
@@ -746,6 +748,68 @@ static void rk_stage(Solver& s, int IRK, int NRK) {
     }
 }
 
+// ADAMSB(DTMIN, NESTAB, GAMM, dtl), subrutinas.f90:851-1034: fourth-order Adams-Bashforth step on the RHS history that RK
+// fills while BANDERA runs 2..4 (:830-848).  Unlike RK it keeps CUARTO_ORDEN's projection as theta (no UN = 0.0 here),
+// refreshes it and the stabilisation parameters on every third call only (NESTAB), and has one calcRHS per step.
+static void adamsb(Solver& s) {
+    const Params& p = s.par;
+    const int npoin = s.npoin, nelem = s.nelem;
+    if (s.NESTAB == 4) s.NESTAB = 1;                                                   // :870
+    if (s.NESTAB == 2) {                                                               // :871-876
+        cuarto_orden(s.U1.data(), s.UN.data(), p.FR, s.GAMM.data(), s.dNx.data(), s.dNy.data(), s.area.data(), s.M.data(),
+                     s.inpoel.data(), nelem, npoin);
+        estab(nelem, s.inpoel.data(), s.U.data(), s.T.data(), s.VEL_X.data(), s.VEL_Y.data(), s.W_X.data(),
+              s.W_Y.data(), s.GAMM.data(), s.dNx.data(), s.dNy.data(), p.FR, s.DTMIN, p.RHO_inf, p.T_inf,
+              s.SHOC.data(), s.T_SUGN1.data(), s.T_SUGN2.data(), s.T_SUGN3.data());
+    }
+    s.NESTAB = s.NESTAB + 1;                                                           // :877
+    std::fill(s.RHS.begin(), s.RHS.end(), 0.0);                                        // :879-883
+    GasK g{p.FCv, p.FK, p.FMU, p.GAMA, p.T_inf, p.CTE};
+    calcrhs(g, s.RHS.data(), s.U.data(), s.UN.data(), s.T.data(), s.dNx.data(), s.dNy.data(), s.area.data(),
+            s.SHOC.data(), s.DTL.data(), s.T_SUGN1.data(), s.T_SUGN2.data(), s.T_SUGN3.data(), s.inpoel.data(), nelem);   // :885
+    fuente(s.RHS.data(), s.U.data(), s.W_X.data(), s.W_Y.data(), s.dNx.data(), s.dNy.data(), s.area.data(),
+           s.DTL.data(), s.inpoel.data(), nelem);                                     // :890
+    for (int ip = 0; ip < npoin; ++ip) {                                               // :894-899
+        double RL = 24.0 * s.M[ip];
+        for (int i = 0; i < 4; ++i) {
+            size_t q = 4 * (size_t)ip + i;
+            s.U1[q] = s.U[q] - (55.0 * s.RHS[q] - 59.0 * s.RHS1[q] + 37.0 * s.RHS2[q] - 9.0 * s.RHS3[q]) / RL;
+        }
+    }
+    s.RHS3 = s.RHS2;                                                                   // :901-907
+    s.RHS2 = s.RHS1;
+    s.RHS1 = s.RHS;
+    for (int ip = 0; ip < npoin; ++ip) {                                               // :914-925 (NGAS == 0)
+        s.RHO[ip] = s.U1[4 * ip];
+        s.VEL_X[ip] = s.U1[4 * ip + 1] / s.RHO[ip];
+        s.VEL_Y[ip] = s.U1[4 * ip + 2] / s.RHO[ip];
+        s.E[ip] = s.U1[4 * ip + 3] / s.RHO[ip];
+        double VEL2 = (s.VEL_X[ip] * s.VEL_X[ip] + s.VEL_Y[ip] * s.VEL_Y[ip]);
+        s.P[ip] = s.RHO[ip] * (s.GAMM[ip] - 1.0) * (s.E[ip] - .5 * VEL2);
+        s.T[ip] = s.P[ip] / (s.RHO[ip] * p.FR);
+        s.RMACH[ip] = std::sqrt(VEL2 / (s.T[ip] * s.GAMM[ip] * p.FR));
+    }
+    for (size_t i = 0; i < s.ifixv_node.size(); ++i) {                                 // FIXVEL :1014
+        int j = s.ifixv_node[i] - 1;
+        s.VEL_X[j] = s.rfixv_valuex[i];
+        s.VEL_Y[j] = s.rfixv_valuey[i];
+    }
+    normalvel(s.n_m, s.n_ipoin.data(), s.n_x.data(), s.n_y.data(), s.VEL_X.data(), s.VEL_Y.data(), s.W_X.data(),
+              s.W_Y.data());                                                           // :1018
+    for (size_t i = 0; i < s.ifixrho_node.size(); ++i) s.RHO[s.ifixrho_node[i] - 1] = s.rfixrho_value[i];   // FIX :1022
+    for (size_t i = 0; i < s.ifixt_node.size(); ++i) {
+        int j = s.ifixt_node[i] - 1;
+        double GM = s.GAMM[j] - 1.0;
+        s.T[j] = s.rfixt_value[i];
+        s.E[j] = s.T[j] * p.FR / GM + .5 * (s.VEL_X[j] * s.VEL_X[j] + s.VEL_Y[j] * s.VEL_Y[j]);
+    }
+    for (int ip = 0; ip < npoin; ++ip) {                                               // :1024-1031
+        s.U1[4 * ip] = s.RHO[ip];
+        s.U1[4 * ip + 1] = s.VEL_X[ip] * s.RHO[ip];
+        s.U1[4 * ip + 2] = s.VEL_Y[ip] * s.RHO[ip];
+        s.U1[4 * ip + 3] = s.E[ip] * s.RHO[ip];
+    }
+}
 
 // meshMove.f90:153-194  FORCES
 static void forces(Solver& s) {
@@ -907,11 +971,13 @@ static void step_part2(Solver& s, double dtmin_global) {
     s.TIME = s.TIME + s.DTMIN;
     s.U1 = s.U;
 }
-static void step_part3(Solver& s) {
+static void step_part3(Solver& s, bool after_rk = true) {
     const Params& p = s.par;
-    if (s.BANDERA == 2) s.RHS3 = s.RHS;       // subrutinas.f90:830-848 (end of RK)
-    else if (s.BANDERA == 3) s.RHS2 = s.RHS;
-    else if (s.BANDERA == 4) s.RHS1 = s.RHS;
+    if (after_rk) {
+        if (s.BANDERA == 2) s.RHS3 = s.RHS;       // subrutinas.f90:830-848 (end of RK)
+        else if (s.BANDERA == 3) s.RHS2 = s.RHS;
+        else if (s.BANDERA == 4) s.RHS1 = s.RHS;
+    }
     fluid_structure(s, s.DTMIN, s.TIME);
     s.ITERPRINT += 1;
     if (s.ITERPRINT == p.IPRINT || s.ITER == p.MAXITER || s.norms_every_step) {  // :186-197
@@ -928,8 +994,13 @@ static void step_part3(Solver& s) {
 static void step(Solver& s) {
     double d = step_part1(s);
     step_part2(s, d);
-    for (int IRK = 1; IRK <= 4; ++IRK) rk_stage(s, IRK, 4);
-    step_part3(s);
+    if (s.adamsb && s.BANDERA > 4) {      // ns2DComp.ALE.f90:174-178 as its comments intend: `if (BANDERA.LE.4) RK else ADAMSB`
+        adamsb(s);
+        step_part3(s, false);
+    } else {
+        for (int IRK = 1; IRK <= 4; ++IRK) rk_stage(s, IRK, 4);
+        step_part3(s);
+    }
 }
 
 }  // namespace orc
@@ -1117,6 +1188,7 @@ void orc_rk_stage(void* h, int irk) { rk_stage(*(Solver*)h, irk, 4); }
 void orc_geometry(void* h, int moving_step) { geometry(*(Solver*)h, moving_step != 0); }
 void orc_fluid_structure(void* h, double dtmin, double time) { fluid_structure(*(Solver*)h, dtmin, time); }
 void orc_force_visc(void* h) { force_visc(*(Solver*)h); }
+void orc_adamsb(void* h) { adamsb(*(Solver*)h); }   // one call of ADAMSB on the current state (tests: pin against the reference's routine)
 void orc_residual_norms(void* h, double* er, double* err) {
     Solver& s = *(Solver*)h;
     residual_norms(s);
@@ -1175,6 +1247,8 @@ void orc_set_scalar(void* h, const char* name, double v) {
     else if (n == "norms_every_step") s.norms_every_step = (int)v;
     else if (n == "use_cuarto") s.use_cuarto = (int)v;
     else if (n == "true_rk") s.true_rk = (int)v;
+    else if (n == "adamsb") s.adamsb = (int)v;
+    else if (n == "NESTAB") s.NESTAB = (int)v;
 }
 // threads of the OpenMP build: n > 0 sets the team size (bench.py: all host cores, whatever OMP_NUM_THREADS the launcher
 // exported -- torch.distributed.run sets it to 1); returns the size in effect
