@@ -159,6 +159,10 @@ struct cfdb_ctx {
     int bicg_iters[2] = {0, 0};
     bool theta_nonzero = false;
     int use_cuarto = 0, true_rk = 0;  // "next" rows N1 / N2, default off (reference behaviour)
+    int adamsb = 0, nestab = 1;       // "next" row N2: ADAMSB replaces RK when BANDERA > 4 (ns2DComp.ALE.f90:134,174-178)
+    int colored = 0;                  // relaxed stage with the deterministic coloured scatter (opt-in, NOT bit-exact vs the reference)
+    vector<int> color_ptr;            // per colour: range of color_list
+    DBuf<int> color_list;             // internal element positions, colour by colour, ascending original id inside a colour
     bool dtl_force = false;           // call-site RK: the local time step array is the caller's dtl whatever ITLOCAL says
     int fast = 0;                     // relaxed stage (FMA + atomic scatter), opt-in, NOT bit-exact
     bool u1_is_u = false;  // after U = U1 (ns2DComp.ALE.f90:277-281) the two arrays are one buffer
@@ -171,8 +175,9 @@ struct cfdb_ctx {
     long Epad = 0;
     k::TileGeom tgeom{};
     size_t stage_smem = 0;
-    vector<int32_t> h_i2e;
-    DBuf<int> i2e, e2i, bnodes;
+    vector<int32_t> h_i2e, h_e2i;
+    DBuf<int> i2e, e2i, bnodes, orphans, bcnt;
+    int norphans = 0;
     DBuf<unsigned char> TB;
     DBuf<double> geo;
     // cfdb_step_streamed: copy streams, device-side staging on both sides, and the events that order them
@@ -470,9 +475,13 @@ static int build_stage_tiles(cfdb_ctx* c, const int32_t* inpoel, const double* X
     c->Epad = (long)T.ntiles * TE;
     TRY(upload(c, c->TB, T.blocks));
     TRY(upload(c, c->bnodes, T.bnodes));
+    c->norphans = (int)T.orphans.size();
+    TRY(upload(c, c->orphans, T.orphans));
+    TRY(zero(c, c->bcnt, P));
     TRY(zero(c, c->geo, 7 * (size_t)c->Epad));
     if (permute) {
         c->h_i2e = T.i2e;
+        c->h_e2i = T.e2i;
         TRY(upload(c, c->i2e, T.i2e));
         TRY(upload(c, c->e2i, T.e2i));
         // connectivity into tile order; per-node element lists keep their (file-order ascending) sequence but name internal positions
@@ -495,6 +504,7 @@ static int build_stage_tiles(cfdb_ctx* c, const int32_t* inpoel, const double* X
     auto up128 = [](int v) { return (v + 127) & ~127; };
     G.TE = TE; G.ntn_max = L.ntn_max; G.nint_max = L.nint_max; G.nslot_max = L.nslot_max;
     G.off_lnode = L.off_lnode; G.off_tnode = L.off_tnode; G.off_nptr = L.off_nptr; G.off_slots = L.off_slots; G.off_bcf = L.off_bcf;
+    G.off_tch = L.off_tch; G.off_bptr = L.off_bptr; G.off_bidx = L.off_bidx;
     G.tb_bytes = L.tb_bytes;
     G.nfields = c->par.ITLOCAL != 0 ? 12 : 11;
     G.a_static = 0;
@@ -676,7 +686,8 @@ extern "C" void cfdb_destroy(cfdb_ctx* c) {
         d->release();
     c->lpos.release();
     c->bcflag.release();
-    c->i2e.release(); c->e2i.release(); c->bnodes.release(); c->TB.release(); c->geo.release();
+    c->color_list.release();
+    c->i2e.release(); c->e2i.release(); c->bnodes.release(); c->orphans.release(); c->bcnt.release(); c->TB.release(); c->geo.release();
     if (c->stage_stats) cudaFree(c->stage_stats);
     c->isfix.release();
     c->bp2.release(); c->by2.release(); c->pos_aux2.release();
@@ -923,6 +934,8 @@ extern "C" int cfdb_init(cfdb_ctx* c) {
     CK(cudaMemcpyAsync(c->W_y_old.p, c->W_Y.p, P * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
     CK(cudaMemcpyAsync(c->area_old.p, c->area.p, c->nelem * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
     c->h_iter = 0;
+    c->nestab = 1;   // ns2DComp.ALE.f90:134
+    if (c->bcnt.p) CK(cudaMemsetAsync(c->bcnt.p, 0, (size_t)c->npoin * sizeof(int), c->st));
     c->iterprint = 0;
     c->DISN[0] = c->DISN[1] = 0.0;
     c->theta_nonzero = false;
@@ -1016,7 +1029,7 @@ static int refresh_geo(cfdb_ctx* c) {
 // fused tile stage (stage_fused.cuh) + node_update over the tile-boundary nodes
 static bool fused_eligible(const cfdb_ctx* c) {
     static const bool off = getenv("CFDB_NO_FUSED") != nullptr;
-    return !off && c->tiles_ok && !c->ale && !c->use_cuarto && !c->fast && !c->theta_nonzero && !c->dtl_force;
+    return !off && c->tiles_ok && !c->ale && !c->use_cuarto && !c->fast && !c->colored && !c->theta_nonzero && !c->dtl_force;
 }
 static int run_stage_fused(cfdb_ctx* c, const k::Gas& g, const double* dtl_arr, const double* dtl_sc, double rk_fact) {
     const bool visc = g.mu_ref > 2.2250738585072014e-308;
@@ -1033,6 +1046,18 @@ static int run_stage_fused(cfdb_ctx* c, const k::Gas& g, const double* dtl_arr, 
     void (*kern)(const k::TileGeom, const k::StageArgs) = nullptr;
     if (c->tile_ncw == 16) kern = visc ? k::stage_fused<true, 16, 3, 2> : k::stage_fused<false, 16, 3, 2>;
     else kern = visc ? k::stage_fused<true, 12, 3, 2> : k::stage_fused<false, 12, 3, 2>;
+    // tile-boundary nodes: finished inside the stage kernel by the last tile to contribute (default), or by node_update over
+    // the list bnodes after it (CFDB_BOUNDARY_PASS=1)
+    // The in-kernel completion writes T, U1, ... of a tile-boundary node while other tiles of the same launch may still
+    // gather that node's state: safe when nothing the kernel gathers is written by it -- Euler flow (T is not read) with
+    // calcRHS evaluated at U (U1 is written, U is read).  Viscous flow and true_rk keep the separate pass.
+    // Measured on B200 (16 M triangles): the in-kernel completion costs the node warps ~10 000 cycles per tile (fence + atomic
+    // round trips + L2 gather chains they cannot hide) against ~5 300 for the interior nodes alone: stage_fused 3.08 ms against
+    // 1.16 ms + 0.35 ms for the separate pass -- so the separate pass is the default and CFDB_BOUNDARY_INKERNEL=1 selects this.
+    static const bool inkernel_env = getenv("CFDB_BOUNDARY_INKERNEL") != nullptr;
+    const bool boundary_pass = !inkernel_env || visc || A.Usrc != A.U;
+    A.cnt = boundary_pass ? nullptr : c->bcnt.p;
+    A.bcflag = c->bcflag.p;
     A.stats = c->stage_stats;
     static std::map<const void*, size_t> attr_done;   // per kernel: the largest dynamic shared-memory size opted into so far
     if (attr_done[(const void*)kern] < c->stage_smem) {
@@ -1047,7 +1072,8 @@ static int run_stage_fused(cfdb_ctx* c, const k::Gas& g, const double* dtl_arr, 
     kern<<<grid, block, c->stage_smem, c->st>>>(G, A);
     CK(cudaGetLastError());
     TRY(prof_end(c, c->st, K_STAGE, _a, _b));
-    TRY(run_node(c, c->st, false, true, rk_fact, 0, c->nbnodes, c->bnodes.p));
+    if (boundary_pass) TRY(run_node(c, c->st, false, true, rk_fact, 0, c->nbnodes, c->bnodes.p));
+    else if (c->norphans) TRY(run_node(c, c->st, false, true, rk_fact, 0, c->norphans, c->orphans.p));   // nodes no element touches
     return 0;
 }
 
@@ -1092,6 +1118,24 @@ extern "C" int cfdb_rk_stage(cfdb_ctx* c, int32_t irk) {
         TRY(halo_state(c));
         return 0;
     }
+    if (c->colored && !c->use_cuarto && !c->true_rk) {
+        // coloured deterministic scatter: RHS = 0, one launch per colour (no two elements of a colour share a node), nodal chain
+        // from RHS; exact arithmetic, fixed summation order (by colour) -- reproducible, not the reference's order
+        const bool visc = g.mu_ref > 2.2250738585072014e-308;
+        CK(cudaMemsetAsync(c->RHS.p, 0, 4 * (size_t)c->npoin * sizeof(double), c->st));
+        auto kc = visc ? (c->ale ? k::calcrhs_colored<true, true> : k::calcrhs_colored<true, false>)
+                       : (c->ale ? k::calcrhs_colored<false, true> : k::calcrhs_colored<false, false>);
+        for (size_t col = 0; col + 1 < c->color_ptr.size(); ++col) {
+            const int n0 = c->color_ptr[col], nc = c->color_ptr[col + 1] - n0;
+            if (nc)
+                LAUNCH(K_CALCRHS, kc, grid_for(nc, 128), 128, nc, c->color_list.p + n0, c->nelem, c->inp.p, c->U.p, c->T.p, c->W_X.p, c->W_Y.p,
+                       c->dNx.p, c->dNy.p, c->area.p, c->SHOC.p, dtl_arr, &c->sc->DTMIN, c->TS1.p, c->TS2.p, c->TS3.p, g, c->RHS.p);
+        }
+        LAUNCH(K_NODE, k::node_update_rhs, grid_for(c->npoin, 256), 256, c->npoin, c->RHS.p, c->U.p, c->M.p, c->GAMM.p, c->W_X.p, c->W_Y.p,
+               c->bcflag.p, bctab(c), RK_FACT, c->par.FR, c->U1.p, c->RHO.p, c->VEL_X.p, c->VEL_Y.p, c->E.p, c->P.p, c->T.p, c->RMACH.p);
+        TRY(halo_state(c));
+        return 0;
+    }
     if (c->fast && !c->use_cuarto && !c->true_rk) {
         // relaxed stage: RHS = 0, scatter-add with red.global.add.f64, nodal chain from RHS
         const bool visc = g.mu_ref > 2.2250738585072014e-308;
@@ -1123,6 +1167,34 @@ extern "C" int cfdb_rk_stage(cfdb_ctx* c, int32_t irk) {
     TRY(run_calcrhs_elem(c, g, c->use_cuarto != 0, c->ale, dtl_arr, &c->sc->DTMIN));
     TRY(run_node(c, c->st, c->ale, true, RK_FACT));
     TRY(halo_state(c));
+    return 0;
+}
+
+// ADAMSB(DTMIN, NESTAB, GAMM, dtl), subrutinas.f90:851-1034, on the resident state (option "adamsb"): CUARTO_ORDEN's projection
+// and ESTAB on every third call (NESTAB), ONE calcRHS + FUENTE with theta = UN, the Adams-Bashforth update from the RHS history.
+static int run_adamsb(cfdb_ctx* c) {
+    const cfdb_params& p = c->par;
+    if (c->nestab == 4) c->nestab = 1;
+    if (c->nestab == 2) {
+        // cuarto_orden(U1, UN, ...) with U1 = U (ns2DComp.ALE.f90:168-172); no UN = 0.0 afterwards in this routine
+        LAUNCH(K_CALCRHS, k::cuarto_elem, grid_for(c->nelem, 128), 128, c->nelem, c->inp.p, c->U.p, c->GAMM.p, c->dNx.p, c->dNy.p,
+               c->area.p, c->EC.p);
+        LAUNCH(K_NODE, k::cuarto_node, grid_for(c->npoin, 256), 256, c->npoin, c->d_esup2.p, c->eslot.p, c->EC.p, c->M.p, c->UN.p);
+        TRY(halo_vec(c, c->UN.p, 4));
+        c->theta_nonzero = true;
+        TRY(run_estab(c, &c->sc->DTMIN));
+    }
+    c->nestab += 1;
+    c->u1_is_u = false;
+    k::Gas g{p.FCv, p.FK, p.FMU, p.GAMA, p.T_inf, p.CTE};
+    const double* dtl_arr = p.ITLOCAL != 0 ? c->DTL.p : nullptr;
+    TRY(run_calcrhs_elem(c, g, true, c->ale, dtl_arr, &c->sc->DTMIN));
+    auto kern = c->ale ? k::node_update_adamsb<true> : k::node_update_adamsb<false>;
+    LAUNCH(K_NODE, kern, grid_for(c->npoin, 128), 128, c->npoin, c->d_esup2.p, c->eslot.p, c->EC.p, c->FC.p, c->U.p, c->M.p, c->GAMM.p,
+           c->W_X.p, c->W_Y.p, c->bcflag.p, bctab(c), p.FR, c->U1.p, c->RHS.p, c->RHS1.p, c->RHS2.p, c->RHS3.p, c->RHO.p, c->VEL_X.p,
+           c->VEL_Y.p, c->E.p, c->P.p, c->T.p, c->RMACH.p);
+    TRY(halo_state(c));
+    // RHS1-3 at ghost nodes are never read (the history enters the update of owned nodes only)
     return 0;
 }
 
@@ -1298,7 +1370,7 @@ extern "C" int cfdb_force_visc(cfdb_ctx* c) {
 
 // one real in Fortran Ew.d ('E') or Fw.d ('F') layout (host/fortran_format.h), for tests of the output formats
 extern "C" int cfdb_format_real(int32_t kind, double v, int32_t w, int32_t d, char* buf, int32_t buflen) {
-    std::string s = kind == 'F' ? ffmt::F(v, w, d) : ffmt::E(v, w, d);
+    std::string s = kind == 'L' ? ffmt::list_r8(v) : kind == 'F' ? ffmt::F(v, w, d) : ffmt::E(v, w, d);   // 'L': list-directed REAL(8)
     if ((int)s.size() + 1 > buflen) return fail("cfdb_format_real: buffer too small");
     memcpy(buf, s.c_str(), s.size() + 1);
     return 0;
@@ -1406,11 +1478,20 @@ static int step_body(cfdb_ctx* c) {
         LAUNCH(K_DTL, k::dtl_blend, grid_for(E, 256), 256, E, c->DT.p, c->DTL.p, c->sc, 1);
     }
     // U1 = U (:168-172) is dead: every RK stage overwrites U1 from U (subrutinas.f90:697)
-    TRY(run_rk(c));
-    // RHS history copies for BANDERA 2..4 (subrutinas.f90:830-848); BANDERA lives on the device, the kernel
-    // exits at once for any other value
-    LAUNCH(K_FILL, k::rhs_history, (int)std::min<long>(grid_for(4 * (long)P, 256), 148 * 8), 256, 4 * (long)P, c->sc, c->RHS.p, c->RHS1.p,
-           c->RHS2.p, c->RHS3.p);
+    bool adams = false;
+    if (c->adamsb) {   // `if (BANDERA.LE.4) RK else ADAMSB` (:174-178 as its comments intend); BANDERA lives on the device
+        TRY(read_scal(c));
+        adams = c->h_sc->BANDERA > 4;
+    }
+    if (adams) {
+        TRY(run_adamsb(c));
+    } else {
+        TRY(run_rk(c));
+        // RHS history copies for BANDERA 2..4 (subrutinas.f90:830-848); BANDERA lives on the device, the kernel
+        // exits at once for any other value
+        LAUNCH(K_FILL, k::rhs_history, (int)std::min<long>(grid_for(4 * (long)P, 256), 148 * 8), 256, 4 * (long)P, c->sc, c->RHS.p, c->RHS1.p,
+               c->RHS2.p, c->RHS3.p);
+    }
     double dtmin = 0.0, time = 0.0;
     if (c->nse) {  // pitching law needs TIME on the host (meshMove.f90:70)
         TRY(read_scal(c));
@@ -1429,7 +1510,7 @@ static int step_body(cfdb_ctx* c) {
 static bool graph_eligible(const cfdb_ctx* c) {
     static const bool off = getenv("CFDB_NO_GRAPH") != nullptr;
     const cfdb_params& p = c->par;
-    return !off && !c->prof && !c->ale && c->nse == 0 && p.ITLOCAL == 0 && p.MOVING != 1 && !c->theta_nonzero && !c->use_cuarto;
+    return !off && !c->prof && !c->ale && c->nse == 0 && p.ITLOCAL == 0 && p.MOVING != 1 && !c->theta_nonzero && !c->use_cuarto && !c->adamsb;
 }
 static int step_graph(cfdb_ctx* c) {
     int par = -1;
@@ -1577,6 +1658,23 @@ extern "C" int cfdb_set_option(cfdb_ctx* c, const char* name, int32_t value) {
     if (n == "fast") c->fast = value;
     else if (n == "use_cuarto") c->use_cuarto = value;
     else if (n == "true_rk") c->true_rk = value;
+    else if (n == "adamsb") c->adamsb = value;
+    else if (n == "colored") {
+        if (value && c->color_ptr.empty()) {
+            // greedy first-fit colours of the element list in the file's order (cfdb_color_elements)
+            vector<int32_t> col((size_t)c->nelem);
+            int32_t nc = 0;
+            TRY(cfdb_color_elements(c->h_inpoel.data(), c->nelem, c->npoin, col.data(), &nc));
+            c->color_ptr.assign((size_t)nc + 1, 0);
+            for (int e = 0; e < c->nelem; ++e) c->color_ptr[col[e] + 1]++;
+            for (int k = 0; k < nc; ++k) c->color_ptr[k + 1] += c->color_ptr[k];
+            vector<int> cur(c->color_ptr.begin(), c->color_ptr.end() - 1), list((size_t)c->nelem);
+            for (int e = 0; e < c->nelem; ++e) list[cur[col[e]]++] = c->perm_on ? c->h_e2i[e] : e;
+            TRY(upload(c, c->color_list, list));
+            CK(cudaStreamSynchronize(c->st));
+        }
+        c->colored = value;
+    }
     else if (n == "ale") {
         // The mesh moves although this context holds no body set of its own: a rank of a multi-GPU run whose sub-domain
         // does not touch the body still receives W_X, W_Y from the global mesh solve (cfd_b200/partition.py sets this).

@@ -6,6 +6,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <vector>
 
 namespace topo {
@@ -109,9 +110,14 @@ inline void build_lap_pos(const int32_t* inpoel, int npoin, const vector<int32_t
 //                              1-thread summation order); value = (4*local_vertex)*TE + position in tile, i.e. the index
 //                              of equation 0 of that contribution in the shared-memory array C[12][TE]
 //   bcf     uint8[nint_max]    bcflag of the interior nodes
+//   tch     uint8[nbd_max]     for each tile-boundary node of the tile (local index nint + jb): the number of tiles touching it
+//   bptr    uint16[nbd_max+1]  CSR over `bidx`
+//   bidx    uint32[nbidx_max]  ALL contributions of that node, tile by tile, in ascending ORIGINAL element order: index of
+//                              the 32-byte record in the global staging buffer EC (3*internal element + local vertex).  The
+//                              tile whose contributions arrive last finishes the node inside the stage kernel.
 struct TileLayout {
-    int TE = 0, ntn_max = 0, nint_max = 0, nslot_max = 0;
-    int off_lnode = 0, off_tnode = 0, off_nptr = 0, off_slots = 0, off_bcf = 0, tb_bytes = 0;
+    int TE = 0, ntn_max = 0, nint_max = 0, nslot_max = 0, nbd_max = 0, nbidx_max = 0;
+    int off_lnode = 0, off_tnode = 0, off_nptr = 0, off_slots = 0, off_bcf = 0, off_tch = 0, off_bptr = 0, off_bidx = 0, tb_bytes = 0;
 };
 struct Tiling {
     TileLayout L;
@@ -119,6 +125,7 @@ struct Tiling {
     vector<int32_t> i2e, e2i;      // 0-based
     vector<uint8_t> blocks;        // ntiles * L.tb_bytes
     vector<int32_t> bnodes;        // tile-boundary nodes, ascending
+    vector<int32_t> orphans;       // nodes touched by no element (never reached by the stage kernel), ascending
     double interior_fraction = 0;
 };
 inline uint32_t morton16(uint32_t x, uint32_t y) {
@@ -175,8 +182,22 @@ inline void build_tiling(const int32_t* inpoel, int nelem, int npoin, const doub
         if (same) { owner[n] = t0; ++ninterior; }
     }
     T.bnodes.clear();
+    T.orphans.clear();
+    vector<uint8_t> ntouch((size_t)npoin, 0);   // number of distinct tiles among the elements of a tile-boundary node
     for (int n = 0; n < npoin; ++n)
-        if (owner[n] < 0) T.bnodes.push_back(n);
+        if (owner[n] < 0) {
+            T.bnodes.push_back(n);
+            int k0 = esup2[n], k1 = esup2[n + 1];
+            if (k0 == k1) { T.orphans.push_back(n); continue; }
+            int seen[64], ns = 0;
+            for (int k = k0; k < k1; ++k) {
+                int tt = T.e2i[esup1[k] - 1] / TE;
+                bool f = false;
+                for (int q = 0; q < ns; ++q) f = f || seen[q] == tt;
+                if (!f && ns < 64) seen[ns++] = tt;
+            }
+            ntouch[n] = (uint8_t)ns;
+        }
     T.interior_fraction = npoin ? (double)ninterior / npoin : 0.0;
     // pass 1: per-tile node lists (interior ascending, then the rest ascending) and the section sizes
     vector<int32_t> stamp((size_t)npoin, -1), lidx((size_t)npoin, 0);
@@ -184,7 +205,7 @@ inline void build_tiling(const int32_t* inpoel, int nelem, int npoin, const doub
     vector<int32_t> tn_nodes;
     tn_nodes.reserve((size_t)(0.7 * E) + 1024);
     vector<int32_t> a, b;
-    int ntn_max = 0, nint_max = 0, nslot_max = 0;
+    int ntn_max = 0, nint_max = 0, nslot_max = 0, nbd_max = 0, nbidx_max = 0;
     for (int t = 0; t < nt; ++t) {
         size_t p0 = (size_t)t * TE, p1 = std::min(E, p0 + TE);
         a.clear(); b.clear();
@@ -207,17 +228,24 @@ inline void build_tiling(const int32_t* inpoel, int nelem, int npoin, const doub
         ntn_max = std::max(ntn_max, (int)(a.size() + b.size()));
         nint_max = std::max(nint_max, (int)a.size());
         nslot_max = std::max(nslot_max, ns);
+        int nbi = 0;
+        for (int n : b) nbi += esup2[n + 1] - esup2[n];
+        nbd_max = std::max(nbd_max, (int)b.size());
+        nbidx_max = std::max(nbidx_max, nbi);
     }
     auto up16 = [](int v) { return (v + 15) & ~15; };
     TileLayout& L = T.L;
     L.TE = TE;
-    L.ntn_max = ntn_max; L.nint_max = nint_max; L.nslot_max = nslot_max;
+    L.ntn_max = ntn_max; L.nint_max = nint_max; L.nslot_max = nslot_max; L.nbd_max = nbd_max; L.nbidx_max = nbidx_max;
     L.off_lnode = 16;
     L.off_tnode = up16(L.off_lnode + 3 * TE * 2);
     L.off_nptr = up16(L.off_tnode + ntn_max * 4);
     L.off_slots = up16(L.off_nptr + (nint_max + 1) * 2);
     L.off_bcf = up16(L.off_slots + nslot_max * 2);
-    L.tb_bytes = up16(L.off_bcf + nint_max);
+    L.off_tch = up16(L.off_bcf + nint_max);
+    L.off_bptr = up16(L.off_tch + nbd_max);
+    L.off_bidx = up16(L.off_bptr + (nbd_max + 1) * 2);
+    L.tb_bytes = up16(L.off_bidx + nbidx_max * 4);
     // pass 2: fill the blocks
     T.blocks.assign((size_t)nt * L.tb_bytes, 0);
     for (int t = 0; t < nt; ++t) {
@@ -231,6 +259,9 @@ inline void build_tiling(const int32_t* inpoel, int nelem, int npoin, const doub
         size_t p0 = (size_t)t * TE, p1 = std::min(E, p0 + TE);
         const int ntn = tn_ptr[t + 1] - tn_ptr[t], nint = tn_nint[t];
         hdr[0] = (int32_t)(p1 - p0); hdr[1] = ntn; hdr[2] = nint; hdr[3] = 0;
+        uint8_t* tch = blk + L.off_tch;
+        uint16_t* bptr = reinterpret_cast<uint16_t*>(blk + L.off_bptr);
+        uint32_t* bidx = reinterpret_cast<uint32_t*>(blk + L.off_bidx);
         for (int j = 0; j < ntn; ++j) {
             int n = tn_nodes[(size_t)tn_ptr[t] + j];
             tnode[j] = n;
@@ -251,6 +282,14 @@ inline void build_tiling(const int32_t* inpoel, int nelem, int npoin, const doub
             bcf[j] = bcflag[n];
         }
         nptr[nint] = (uint16_t)q;
+        int qb = 0;
+        for (int jb = 0; jb < ntn - nint; ++jb) {
+            int n = tnode[nint + jb];
+            tch[jb] = ntouch[n];
+            bptr[jb] = (uint16_t)qb;
+            for (int k = esup2[n]; k < esup2[n + 1]; ++k) bidx[qb++] = (uint32_t)(3 * T.e2i[esup1[k] - 1] + eslot[k] % 3);
+        }
+        bptr[ntn - nint] = (uint16_t)qb;
     }
 }
 

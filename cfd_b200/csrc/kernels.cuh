@@ -922,6 +922,20 @@ __device__ __forceinline__ void node_bc_store(int n, double rho, double vx, doub
     st4(U1 + 4 * (size_t)n, o);
     RHO[n] = rho; VELX[n] = vx; VELY[n] = vy; Ea[n] = en; Pa[n] = p; Ta[n] = t; RMACH[n] = mach;
 }
+// primitives (subrutinas.f90:708-717), boundary conditions, conservative state from the updated conserved vector u1
+__device__ __forceinline__ void node_from_u1(int n, const double (&u1)[4], double gam, unsigned fl, const double* __restrict__ WXa,
+                                             const double* __restrict__ WYa, const BcTab& bc, double FR, double* __restrict__ U1,
+                                             double* __restrict__ RHO, double* __restrict__ VELX, double* __restrict__ VELY,
+                                             double* __restrict__ Ea, double* __restrict__ Pa, double* __restrict__ Ta,
+                                             double* __restrict__ RMACH) {
+    double rho = u1[0];
+    double vx = u1[1] / rho, vy = u1[2] / rho, en = u1[3] / rho;
+    double VEL2 = (vx * vx + vy * vy);
+    double p = rho * (gam - 1.0) * (en - .5 * VEL2);
+    double t = p / (rho * FR);
+    double mach = sqrt(VEL2 / (t * gam * FR));
+    node_bc_store(n, rho, vx, vy, en, p, t, mach, gam, fl, WXa, WYa, bc, FR, U1, RHO, VELX, VELY, Ea, Pa, Ta, RMACH);
+}
 __device__ __forceinline__ void node_finish_v(int n, const double (&acc)[4], const double (&u)[4], double m, double gam,
                                               unsigned fl, const double* __restrict__ WXa, const double* __restrict__ WYa,
                                               const BcTab& bc, double rk_fact, double FR, double* __restrict__ U1,
@@ -932,37 +946,37 @@ __device__ __forceinline__ void node_finish_v(int n, const double (&acc)[4], con
     double u1[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) u1[i] = u[i] - f * acc[i];
-    double rho = u1[0];
-    double vx = u1[1] / rho, vy = u1[2] / rho, en = u1[3] / rho;
-    double VEL2 = (vx * vx + vy * vy);
-    double p = rho * (gam - 1.0) * (en - .5 * VEL2);
-    double t = p / (rho * FR);
-    double mach = sqrt(VEL2 / (t * gam * FR));
-    node_bc_store(n, rho, vx, vy, en, p, t, mach, gam, fl, WXa, WYa, bc, FR, U1, RHO, VELX, VELY, Ea, Pa, Ta, RMACH);
+    node_from_u1(n, u1, gam, fl, WXa, WYa, bc, FR, U1, RHO, VELX, VELY, Ea, Pa, Ta, RMACH);
 }
 // The same chain with the branch-free divisions and square root of exact.cuh (same operations on the same values; the five
 // quotients and the root are straight-line code whose reciprocal refinements the scheduler overlaps): returns the fast-path
 // flag and stores nothing when it is raised -- the caller then runs node_finish_v.
+struct NodePrims { double rho, vx, vy, en, p, t, mach; };
+__device__ __forceinline__ unsigned node_prims_nb(const double (&acc)[4], const double (&u)[4], double m, double gam, double rk_fact,
+                                                  double FR, NodePrims& o) {
+    unsigned bad = 0;
+    double f = ex::Recip(m).div(rk_fact, bad);
+    double u1[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) u1[i] = u[i] - f * acc[i];
+    o.rho = u1[0];
+    const ex::Recip dr(o.rho);
+    o.vx = dr.div(u1[1], bad); o.vy = dr.div(u1[2], bad); o.en = dr.div(u1[3], bad);
+    double VEL2 = (o.vx * o.vx + o.vy * o.vy);
+    o.p = o.rho * (gam - 1.0) * (o.en - .5 * VEL2);
+    o.t = ex::Recip(o.rho * FR).div(o.p, bad);
+    o.mach = ex::sqrt_nb(ex::Recip(o.t * gam * FR).div(VEL2, bad), bad);
+    return bad;
+}
 __device__ __forceinline__ unsigned node_finish_nb(int n, const double (&acc)[4], const double (&u)[4], double m, double gam,
                                                    unsigned fl, const double* __restrict__ WXa, const double* __restrict__ WYa,
                                                    const BcTab& bc, double rk_fact, double FR, double* __restrict__ U1,
                                                    double* __restrict__ RHO, double* __restrict__ VELX, double* __restrict__ VELY,
                                                    double* __restrict__ Ea, double* __restrict__ Pa, double* __restrict__ Ta,
                                                    double* __restrict__ RMACH) {
-    unsigned bad = 0;
-    double f = ex::Recip(m).div(rk_fact, bad);
-    double u1[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) u1[i] = u[i] - f * acc[i];
-    double rho = u1[0];
-    const ex::Recip dr(rho);
-    double vx = dr.div(u1[1], bad), vy = dr.div(u1[2], bad), en = dr.div(u1[3], bad);
-    double VEL2 = (vx * vx + vy * vy);
-    double p = rho * (gam - 1.0) * (en - .5 * VEL2);
-    double t = ex::Recip(rho * FR).div(p, bad);
-    double mach = ex::sqrt_nb(ex::Recip(t * gam * FR).div(VEL2, bad), bad);
-    if (bad) return bad;
-    node_bc_store(n, rho, vx, vy, en, p, t, mach, gam, fl, WXa, WYa, bc, FR, U1, RHO, VELX, VELY, Ea, Pa, Ta, RMACH);
+    NodePrims q;
+    if (node_prims_nb(acc, u, m, gam, rk_fact, FR, q)) return 1;
+    node_bc_store(n, q.rho, q.vx, q.vy, q.en, q.p, q.t, q.mach, gam, fl, WXa, WYa, bc, FR, U1, RHO, VELX, VELY, Ea, Pa, Ta, RMACH);
     return 0;
 }
 __device__ __noinline__ void node_finish_plain(int n, const double (&acc)[4], const double (&u)[4], double m, double gam,
@@ -1028,6 +1042,52 @@ __global__ void __launch_bounds__(CFDB_NODE_BS, CFDB_NODE_MINB) node_update(int 
     st4(RHS + 4 * (size_t)n, acc);
     if (!UPDATE) return;
     node_finish(n, acc, U, M, GAMM, WXa, WYa, bcflag, bc, rk_fact, FR, U1, RHO, VELX, VELY, Ea, Pa, Ta, RMACH);
+}
+
+// ADAMSB's nodal part (subrutinas.f90:894-1031): RHS = ordered sum; U1 = U - (55 RHS - 59 RHS1 + 37 RHS2 - 9 RHS3)/(24 M);
+// history shift RHS3 <- RHS2 <- RHS1 <- RHS; primitives; fixvel -> normalvel -> FIX; conservative.
+template <bool ALE>
+__global__ void __launch_bounds__(128, 8) node_update_adamsb(int npoin, const int* __restrict__ esup2, const int* __restrict__ eslot,
+                                                              const double* __restrict__ EC, const double* __restrict__ FC,
+                                                              const double* __restrict__ U, const double* __restrict__ M,
+                                                              const double* __restrict__ GAMM, const double* __restrict__ WXa,
+                                                              const double* __restrict__ WYa, const unsigned char* __restrict__ bcflag,
+                                                              BcTab bc, double FR, double* __restrict__ U1, double* __restrict__ RHS,
+                                                              double* __restrict__ R1, double* __restrict__ R2, double* __restrict__ R3,
+                                                              double* __restrict__ RHO, double* __restrict__ VELX, double* __restrict__ VELY,
+                                                              double* __restrict__ Ea, double* __restrict__ Pa, double* __restrict__ Ta,
+                                                              double* __restrict__ RMACH) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= npoin) return;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    const int k0 = esup2[n], k1 = esup2[n + 1];
+    for (int k = k0; k < k1; ++k) {
+        double c[4];
+        ld4(EC + 4 * (size_t)eslot[k], c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = acc[i] + c[i];
+    }
+    if (ALE) {
+        for (int k = k0; k < k1; ++k) {
+            double c[4];
+            ld4(FC + 4 * (size_t)eslot[k], c);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] = acc[i] + c[i];
+        }
+    }
+    double u[4], r1[4], r2[4], r3[4], u1[4];
+    ld4(U + 4 * (size_t)n, u);
+    ld4(R1 + 4 * (size_t)n, r1);
+    ld4(R2 + 4 * (size_t)n, r2);
+    ld4(R3 + 4 * (size_t)n, r3);
+    const double RL = 24.0 * M[n];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) u1[i] = u[i] - (55.0 * acc[i] - 59.0 * r1[i] + 37.0 * r2[i] - 9.0 * r3[i]) / RL;
+    st4(RHS + 4 * (size_t)n, acc);
+    st4(R3 + 4 * (size_t)n, r2);
+    st4(R2 + 4 * (size_t)n, r1);
+    st4(R1 + 4 * (size_t)n, acc);
+    node_from_u1(n, u1, GAMM[n], bcflag[n], WXa, WYa, bc, FR, U1, RHO, VELX, VELY, Ea, Pa, Ta, RMACH);
 }
 
 // rhs_out = ((rhs_in + c1) + c2) + ... in ascending element order (call-site mode of calcRHS / FUENTE, whose
@@ -1642,6 +1702,71 @@ __global__ void __launch_bounds__(128, 4) calcrhs_scatter(int nelem, const int* 
     for (int n = 0; n < 3; ++n)
 #pragma unroll
         for (int i = 0; i < 4; ++i) atomicAdd(RHS + 4 * (size_t)ip[n] + i, rt[n][i] * w);
+}
+// Coloured deterministic scatter (north_star's verification mode; SURVEY.md B.3 colouring): the elements of ONE colour share no
+// node, so their contributions are added to RHS with plain read-modify-writes, colour after colour -- a fixed summation order
+// (by colour, then nothing to order), reproducible from run to run, but not the reference's ascending-element order: results
+// agree with the default mode to round-off, not bit for bit.  Arithmetic: the exact calcrhs_body (this translation unit has no
+// FMA contraction).  elist = internal element positions of this colour.
+template <bool VISC, bool ALE>
+__global__ void __launch_bounds__(128, 4) calcrhs_colored(int ncol, const int* __restrict__ elist, int nelem, const int* __restrict__ inp,
+                                                           const double* __restrict__ U, const double* __restrict__ T,
+                                                           const double* __restrict__ WXa, const double* __restrict__ WYa,
+                                                           const double* __restrict__ dNx, const double* __restrict__ dNy,
+                                                           const double* __restrict__ area, const double* __restrict__ shoc,
+                                                           const double* __restrict__ dtl_arr, const double* __restrict__ dtl_sc,
+                                                           const double* __restrict__ ts1, const double* __restrict__ ts2,
+                                                           const double* __restrict__ ts3, Gas g, double* __restrict__ RHS) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= ncol) return;
+    const int e = elist[q];
+    const size_t NE = (size_t)nelem;
+    int ip[3] = {inp[e], inp[NE + e], inp[2 * NE + e]};
+    double Nx[3] = {dNx[e], dNx[NE + e], dNx[2 * NE + e]};
+    double Ny[3] = {dNy[e], dNy[NE + e], dNy[2 * NE + e]};
+    double Un[3][4], Th[3][4], Tn[3] = {0.0, 0.0, 0.0};
+    ld4(U + 4 * (size_t)ip[0], Un[0]);
+    ld4(U + 4 * (size_t)ip[1], Un[1]);
+    ld4(U + 4 * (size_t)ip[2], Un[2]);
+    if (VISC) { Tn[0] = T[ip[0]]; Tn[1] = T[ip[1]]; Tn[2] = T[ip[2]]; }
+    const double tau[3] = {ts1[e], ts2[e], ts3[e]};
+    const double dtl = dtl_arr ? dtl_arr[e] : *dtl_sc;
+    const double ar = area[e];
+    double Ux[4], Uy[4], rt[3][4];
+    calcrhs_body<VISC, false>(g, Un, Th, Tn, Nx, Ny, tau, shoc[e], Ux, Uy, rt);
+    double fc[3][4];
+    if (ALE) {   // FUENTE (subrutinas.f90:1060-1078) on the same element
+        const double sp[3][3] = {{.5, .5, 0.0}, {0.0, .5, .5}, {.5, 0.0, .5}};
+        double AR = ex::div3(ar * dtl);
+        double wx[3], wy[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double sx = 0.0, sy = 0.0;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                sx = ex::pfma(sp[c][r], WXa[ip[r]], sx);
+                sy = ex::pfma(sp[c][r], WYa[ip[r]], sy);
+            }
+            wx[c] = sx; wy[c] = sy;
+        }
+#pragma unroll
+        for (int n = 0; n < 3; ++n)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                fc[n][i] = -AR * ex::lin3(sp[0][n], Ux[i] * wx[0] + Uy[i] * wy[0], sp[1][n], Ux[i] * wx[1] + Uy[i] * wy[1],
+                                          sp[2][n], Ux[i] * wx[2] + Uy[i] * wy[2]);
+    }
+#pragma unroll
+    for (int n = 0; n < 3; ++n) {
+        double r[4];
+        ld4(RHS + 4 * (size_t)ip[n], r);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            r[i] = r[i] + ex::div3(rt[n][i] * ar * dtl);
+            if (ALE) r[i] = r[i] + fc[n][i];
+        }
+        st4(RHS + 4 * (size_t)ip[n], r);
+    }
 }
 __global__ void __launch_bounds__(256) node_update_rhs(int npoin, const double* __restrict__ RHS, const double* __restrict__ U,
                                                         const double* __restrict__ M, const double* __restrict__ GAMM,

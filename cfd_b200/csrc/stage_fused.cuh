@@ -23,6 +23,16 @@
 // Roofline: HBM traffic per element-stage falls from 404 B (220 algorithmic + 192 staging, measured 6.46 GB per stage on the
 // 16 M-triangle mesh) to ~230 B; the kernel is then bound by the fp64 pipe (~812 non-FMA fp64 instructions per element).
 #pragma once
+// build-time switches of the stage kernel (A/B builds: make ab ABFLAGS=-D...)
+#ifndef CFDB_NODE_ILP2
+#define CFDB_NODE_ILP2 0      // node warps: two nodes per lane in flight (needs CFDB_STAGE_RE <= 144)
+#endif
+#ifndef CFDB_NODE_NB
+#define CFDB_NODE_NB 1        // node warps: branch-free divisions / square root in the nodal chain
+#endif
+#ifndef CFDB_STAGE_RE
+#define CFDB_STAGE_RE 144     // registers per thread of the element warps; the auxiliary warps get 512 - 3 x this
+#endif
 
 namespace ptx {
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
@@ -76,7 +86,7 @@ template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setma
 // offsets of the static tile block (mirror of topo::TileLayout) and of the two shared-memory rings
 struct TileGeom {
     int TE, ntn_max, nint_max, nslot_max;
-    int off_lnode, off_tnode, off_nptr, off_slots, off_bcf, tb_bytes;
+    int off_lnode, off_tnode, off_nptr, off_slots, off_bcf, off_tch, off_bptr, off_bidx, tb_bytes;
     // A ring slot (static block + gathered nodal data), bytes from the slot base
     int a_static, a_u, a_t, a_m, a_g, a_bytes;
     int b_bytes;       // B ring slot: the element stream, nfields x TE doubles
@@ -99,18 +109,23 @@ struct StageArgs {
     double rk_fact, FR;
     Gas g;
     double *EC, *U1, *RHS, *RHO, *VELX, *VELY, *Ea, *Pa, *Ta, *RMACH;
+    int* cnt;                                      // per node: contributions-arrived counter of the tile-boundary nodes (null: they
+                                                   // are left to node_update over the list bnodes, launched after this kernel)
+    const unsigned char* bcflag;
     unsigned long long* stats;                     // optional (CFDB_STAGE_STATS): cycle counters, see stage_fused
 };
 enum { ST_E = 0, ST_N, ST_WAIT_IN, ST_WAIT_CE, ST_WAIT_CF, ST_LD_WB, ST_LD_WS, ST_LD_WA, ST_TILES, ST_COUNT };
 
-// The arithmetic of one element from shared memory: `sa` is the tile's A slot (connectivity + nodal state), `sbm` its B slot
-// (element stream).  v = the twelve contributions, ln = tile-local node of each vertex.
+// One element: inputs from shared memory -- `sa` is the tile's A slot (connectivity + nodal state), `sbm` its B slot (element
+// stream) -- the twelve contributions to C (and to the global staging buffer EC for tile-boundary nodes, finished by
+// node_update afterwards).  Stores happen as the values become ready; when the fast-path flag comes back raised the caller
+// runs the plain form, whose stores (same thread, same addresses, program order) replace these.
 template <bool VISC, bool NB>
-__device__ __forceinline__ unsigned fused_elem_math(const TileGeom& G, const StageArgs& A, const unsigned char* sa, const unsigned char* sbm,
-                                                    int k, double dtl_uniform, double (&v)[3][4], int (&ln)[3]) {
+__device__ __forceinline__ unsigned fused_elem(const TileGeom& G, const StageArgs& A, const unsigned char* sa, const unsigned char* sbm,
+                                               double* __restrict__ C, int k, int nint, long e_glob, double dtl_uniform) {
     const int TE = G.TE;
     const unsigned short* lnode = reinterpret_cast<const unsigned short*>(sa + G.a_static + G.off_lnode);
-    ln[0] = lnode[k]; ln[1] = lnode[TE + k]; ln[2] = lnode[2 * TE + k];
+    const int ln[3] = {lnode[k], lnode[TE + k], lnode[2 * TE + k]};
     const double* ut = reinterpret_cast<const double*>(sa + G.a_u);
     double Un[3][4], Th[3][4], Tn[3] = {0.0, 0.0, 0.0};
 #pragma unroll
@@ -130,19 +145,26 @@ __device__ __forceinline__ unsigned fused_elem_math(const TileGeom& G, const Sta
     const double shoc_e = sd[7 * TE + k];
     const double tau[3] = {sd[8 * TE + k], sd[9 * TE + k], sd[10 * TE + k]};
     const double dtl = G.nfields == 12 ? sd[11 * TE + k] : dtl_uniform;
+    const unsigned bmask = (ln[0] >= nint ? 1u : 0u) | (ln[1] >= nint ? 2u : 0u) | (ln[2] >= nint ? 4u : 0u);
     double Ux[4], Uy[4], rt[3][4];
     unsigned bad = 0;
     calcrhs_body<VISC, false, NB>(A.g, Un, Th, Tn, Nx, Ny, tau, shoc_e, Ux, Uy, rt, &bad);
 #pragma unroll
-    for (int n = 0; n < 3; ++n)
+    for (int n = 0; n < 3; ++n) {
+        double v[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[n][i] = NB ? ex::div3_nb(rt[n][i] * ar * dtl, bad) : ex::div3(rt[n][i] * ar * dtl);
+        for (int i = 0; i < 4; ++i) {
+            v[i] = NB ? ex::div3_nb(rt[n][i] * ar * dtl, bad) : ex::div3(rt[n][i] * ar * dtl);
+            C[(4 * n + i) * TE + k] = v[i];
+        }
+        if (bmask & (1u << n)) st4(A.EC + 12 * e_glob + 4 * n, v);
+    }
     return bad;
 }
 template <bool VISC>
-__device__ __noinline__ void fused_elem_plain(const TileGeom& G, const StageArgs& A, const unsigned char* sa, const unsigned char* sbm, int k,
-                                              double dtl_uniform, double (&v)[3][4], int (&ln)[3]) {
-    fused_elem_math<VISC, false>(G, A, sa, sbm, k, dtl_uniform, v, ln);
+__device__ __noinline__ void fused_elem_plain(const TileGeom& G, const StageArgs& A, const unsigned char* sa, const unsigned char* sbm,
+                                              double* __restrict__ C, int k, int nint, long e_glob, double dtl_uniform) {
+    fused_elem<VISC, false>(G, A, sa, sbm, C, k, nint, e_glob, dtl_uniform);
 }
 
 // Warp roles.  NCW element warps (a multiple of 4) + one auxiliary warpgroup: warp NCW is the loader, warps NCW+1..NCW+3 are
@@ -150,9 +172,9 @@ __device__ __noinline__ void fused_elem_plain(const TileGeom& G, const StageArgs
 //
 // Registers.  The register file is split over the four SM sub-partitions (16384 registers each, warps dealt round-robin), so
 // with 16 warps per CTA every sub-partition holds three element warps and one auxiliary warp, launched at 128 registers per
-// thread.  setmaxnreg then moves registers from the auxiliary warpgroup (56 each: the nodal chain needs ~48) to the element
-// warpgroups (152 each: the branch-free form of the element arithmetic runs without spills and its single-warp schedule is
-// within 40 % of the fp64 issue time, tools/sass_stalls.py).  3 x 152 + 56 = 4 x 128: what the element warps claim is exactly
+// thread.  setmaxnreg then moves registers from the auxiliary warpgroup (80 each: two nodes per lane in flight) to the element
+// warpgroups (144 each: the branch-free form of the element arithmetic runs without spills and its single-warp schedule is
+// within 40 % of the fp64 issue time, tools/sass_stalls.py).  3 x 144 + 80 = 4 x 128: what the element warps claim is exactly
 // what the auxiliary warpgroup released (the registers a warpgroup may claim come from its own CTA's pool).
 //
 // Pipeline (all hand-overs are mbarriers; no CTA-wide barrier in the steady state):
@@ -171,8 +193,8 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1) stage_fused(const __grid_co
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int NNW = 3;                       // node warps
     constexpr int NNT = NNW * 32;
-    constexpr int RE = (NCW == 12) ? 152 : 112;  // registers per thread of an element warp after the hand-over
-    constexpr int RAUX = (NCW == 12) ? 56 : 32;  //                  ... of an auxiliary warp      (NCW*RE + 4*RAUX == (NCW+4) * launch registers)
+    constexpr int RE = (NCW == 12) ? CFDB_STAGE_RE : 112;   // registers per thread of an element warp after the hand-over
+    constexpr int RAUX = (NCW == 12) ? 4 * 128 - 3 * CFDB_STAGE_RE : 32;  //                  ... of an auxiliary warp      (NCW*RE + 4*RAUX == (NCW+4) * launch registers)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // barriers (8 bytes each): astat[NA] static block landed (1 arrival + bytes); afull[NA] gathers landed (32 cp.async
     // arrivals); aempty[NA] (NCW + NNW arrivals); bfull[NBR] (1 + bytes); bempty[NBR] (NCW); cfull[2] (NCW); cempty[2] (NNW)
@@ -288,15 +310,107 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1) stage_fused(const __grid_co
             const int* tnode = reinterpret_cast<const int*>(ab + G.a_static + G.off_tnode);
             const unsigned short* nptr = reinterpret_cast<const unsigned short*>(ab + G.a_static + G.off_nptr);
             const unsigned short* slots = reinterpret_cast<const unsigned short*>(ab + G.a_static + G.off_slots);
+            // Tile-boundary nodes: this tile's contributions to them are in the global staging buffer EC (the element warps'
+            // stores, ordered before this point by the C-full barrier).  Announce them -- fence, then one atomic increment per
+            // node -- BEFORE the interior nodes, whose work hides the round trip; the tile whose increment completes the
+            // count (every tile touching the node has then published its contributions) finishes the node below.
+            const int nbd = hdr[1] - nint;
+            const unsigned char* tch = ab + G.a_static + G.off_tch;
+            unsigned lastmask = 0;
+            if (A.cnt) {
+                __threadfence();
+#pragma unroll 1
+                for (int jb = nt, r = 0; jb < nbd; jb += NNT, ++r) {
+                    const int old = atomicAdd(A.cnt + tnode[nint + jb], 1);
+                    const int tc = tch[jb];
+                    if ((old + 1) % tc == 0) lastmask |= 1u << r;
+                }
+            }
+#if CFDB_NODE_ILP2
+            // two nodes per lane at a time (j and j + NNT): their gather chains, reciprocal refinements and square roots are
+            // independent, so the two instruction streams overlap each other's latencies -- the node warps share the fp64
+            // pipe with three element warps per sub-partition and would otherwise wait on every dependent instruction
+#pragma unroll 1
+            for (int j0 = nt; j0 < nint; j0 += 2 * NNT) {
+                const int jj[2] = {j0, j0 + NNT};
+                const bool on[2] = {true, jj[1] < nint};
+                int n[2], q0[2], q1[2];
+                double acc[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
+#pragma unroll
+                for (int s2 = 0; s2 < 2; ++s2) {
+                    const int j = on[s2] ? jj[s2] : j0;
+                    n[s2] = tnode[j];
+                    q0[s2] = nptr[j];
+                    q1[s2] = on[s2] ? nptr[j + 1] : q0[s2];
+                }
+                const int len = max(q1[0] - q0[0], q1[1] - q0[1]);
+                for (int r = 0; r < len; ++r) {
+#pragma unroll
+                    for (int s2 = 0; s2 < 2; ++s2) {
+                        if (q0[s2] + r < q1[s2]) {
+                            const int sl = slots[q0[s2] + r];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) acc[s2][i] = acc[s2][i] + C[sl + i * TE];
+                        }
+                    }
+                }
+                double u[2][4], m[2], gam[2];
+                unsigned fl[2];
+#pragma unroll
+                for (int s2 = 0; s2 < 2; ++s2) {
+                    const int j = on[s2] ? jj[s2] : j0;
+                    if (on[s2]) st4(A.RHS + 4 * (size_t)n[s2], acc[s2]);
+                    if (A.U == A.Usrc) {   // the tile's copy of the state is the state the update starts from
+                        const double2* q = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(ab + G.a_u) + 4 * j);
+                        double2 a = q[0], b = q[1];
+                        u[s2][0] = a.x; u[s2][1] = a.y; u[s2][2] = b.x; u[s2][3] = b.y;
+                    } else {
+                        ld4(A.U + 4 * (size_t)n[s2], u[s2]);
+                    }
+                    m[s2] = reinterpret_cast<const double*>(ab + G.a_m)[j];
+                    gam[s2] = reinterpret_cast<const double*>(ab + G.a_g)[j];
+                    fl[s2] = (ab + G.a_static + G.off_bcf)[j];
+                }
+                NodePrims pr[2];
+                unsigned bad[2];
+#pragma unroll
+                for (int s2 = 0; s2 < 2; ++s2) bad[s2] = node_prims_nb(acc[s2], u[s2], m[s2], gam[s2], A.rk_fact, A.FR, pr[s2]);
+#pragma unroll
+                for (int s2 = 0; s2 < 2; ++s2) {
+                    if (!on[s2]) continue;
+                    if (bad[s2])
+                        node_finish_plain(n[s2], acc[s2], u[s2], m[s2], gam[s2], fl[s2], A.WXa, A.WYa, A.bc, A.rk_fact, A.FR, A.U1, A.RHO,
+                                          A.VELX, A.VELY, A.Ea, A.Pa, A.Ta, A.RMACH);
+                    else
+                        node_bc_store(n[s2], pr[s2].rho, pr[s2].vx, pr[s2].vy, pr[s2].en, pr[s2].p, pr[s2].t, pr[s2].mach, gam[s2], fl[s2],
+                                      A.WXa, A.WYa, A.bc, A.FR, A.U1, A.RHO, A.VELX, A.VELY, A.Ea, A.Pa, A.Ta, A.RMACH);
+                }
+            }
+#else
 #pragma unroll 1
             for (int j = nt; j < nint; j += NNT) {
                 const int n = tnode[j];
                 double acc[4] = {0.0, 0.0, 0.0, 0.0};
                 const int q1 = nptr[j + 1];
-                for (int q = nptr[j]; q < q1; ++q) {
-                    const int sl = slots[q];
+                // eight contributions at a time: all slot indices, then all 32 values, are requested before the first add, so
+                // the shared-memory latencies overlap and only the eight dependent additions per component remain in sequence
+                // (the order of the additions is the list's: ascending original element id)
+#pragma unroll 1
+                for (int q = nptr[j]; q < q1; q += 8) {
+                    int sl[8];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) acc[i] = acc[i] + C[sl + i * TE];
+                    for (int r = 0; r < 8; ++r) sl[r] = slots[min(q + r, q1 - 1)];
+                    double cv[8][4];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) cv[r][i] = C[sl[r] + i * TE];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)
+                        if (q + r < q1) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) acc[i] = acc[i] + cv[r][i];
+                        }
                 }
                 st4(A.RHS + 4 * (size_t)n, acc);
                 double u[4];
@@ -310,10 +424,51 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1) stage_fused(const __grid_co
                 const double m = reinterpret_cast<const double*>(ab + G.a_m)[j];
                 const double gam = reinterpret_cast<const double*>(ab + G.a_g)[j];
                 const unsigned fl = (ab + G.a_static + G.off_bcf)[j];
+#if CFDB_NODE_NB
                 if (node_finish_nb(n, acc, u, m, gam, fl, A.WXa, A.WYa, A.bc, A.rk_fact, A.FR, A.U1, A.RHO, A.VELX, A.VELY, A.Ea, A.Pa,
                                    A.Ta, A.RMACH))
                     node_finish_plain(n, acc, u, m, gam, fl, A.WXa, A.WYa, A.bc, A.rk_fact, A.FR, A.U1, A.RHO, A.VELX, A.VELY, A.Ea,
                                       A.Pa, A.Ta, A.RMACH);
+#else
+                node_finish_v(n, acc, u, m, gam, fl, A.WXa, A.WYa, A.bc, A.rk_fact, A.FR, A.U1, A.RHO, A.VELX, A.VELY, A.Ea, A.Pa,
+                              A.Ta, A.RMACH);
+#endif
+            }
+#endif
+            if (lastmask) {
+                // finish the tile-boundary nodes this tile completed: all their contributions, whichever CTA wrote them, in
+                // ascending original element order from EC (read past L1: other SMs wrote them), then the nodal chain
+                __threadfence();
+                const unsigned short* bptr = reinterpret_cast<const unsigned short*>(ab + G.a_static + G.off_bptr);
+                const unsigned* bidx = reinterpret_cast<const unsigned*>(ab + G.a_static + G.off_bidx);
+#pragma unroll 1
+                for (int jb = nt, r = 0; jb < nbd; jb += NNT, ++r) {
+                    if (!(lastmask & (1u << r))) continue;
+                    const int n = tnode[nint + jb];
+                    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+                    const int q1 = bptr[jb + 1];
+#pragma unroll 1
+                    for (int q = bptr[jb]; q < q1; q += 4) {
+                        double2 cv[4][2];
+#pragma unroll
+                        for (int r2 = 0; r2 < 4; ++r2) {
+                            const double2* src = reinterpret_cast<const double2*>(A.EC + 4 * (size_t)bidx[min(q + r2, q1 - 1)]);
+                            cv[r2][0] = __ldcg(src);
+                            cv[r2][1] = __ldcg(src + 1);
+                        }
+#pragma unroll
+                        for (int r2 = 0; r2 < 4; ++r2)
+                            if (q + r2 < q1) {
+                                acc[0] = acc[0] + cv[r2][0].x; acc[1] = acc[1] + cv[r2][0].y;
+                                acc[2] = acc[2] + cv[r2][1].x; acc[3] = acc[3] + cv[r2][1].y;
+                            }
+                    }
+                    st4(A.RHS + 4 * (size_t)n, acc);
+                    double u[4];
+                    ld4(A.U + 4 * (size_t)n, u);
+                    node_finish_v(n, acc, u, A.M[n], A.GAMM[n], A.bcflag[n], A.WXa, A.WYa, A.bc, A.rk_fact, A.FR, A.U1, A.RHO, A.VELX,
+                                  A.VELY, A.Ea, A.Pa, A.Ta, A.RMACH);
+                }
             }
             __syncwarp();
             if (lane == 0) {
@@ -339,27 +494,17 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1) stage_fused(const __grid_co
         const unsigned char* bb = smem + G.off_b + (size_t)sb * G.b_bytes;
         waitc(afull0 + 8 * sa, (it / NA) & 1, ST_WAIT_IN);
         waitc(bfull0 + 8 * sb, (it / NBR) & 1, ST_WAIT_IN);
+        waitc(cempty0 + 8 * c, ((it >> 1) & 1) ^ 1, ST_WAIT_CE);   // node phase it-2 is done: C[c] is free
         const long long t0 = stat ? clock64() : 0;
         const int* hdr = reinterpret_cast<const int*>(ab + G.a_static);
         const int ne = hdr[0], nint = hdr[2];
-        double v[3][4];
-        int ln[3] = {0, 0, 0};
-        if (k < ne) {
-            // branch-free divisions (exact.cuh) first; the plain form only if an operand left their range
-            if (fused_elem_math<VISC, true>(G, A, ab, bb, k, dtl_uniform, v, ln)) fused_elem_plain<VISC>(G, A, ab, bb, k, dtl_uniform, v, ln);
-        }
-        if (stat) st[ST_E] += (unsigned long long)(clock64() - t0);
-        waitc(cempty0 + 8 * c, ((it >> 1) & 1) ^ 1, ST_WAIT_CE);   // node phase it-2 is done: C[c] is free
         if (k < ne) {
             double* C = Cbase + (size_t)c * 12 * TE;
             const long e_glob = (long)t * TE + k;
-#pragma unroll
-            for (int n = 0; n < 3; ++n) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) C[(4 * n + i) * TE + k] = v[n][i];
-                if (ln[n] >= nint) st4(A.EC + 12 * e_glob + 4 * n, v[n]);   // tile-boundary node: finished by node_update afterwards
-            }
+            // branch-free divisions (exact.cuh) first; the plain form only if an operand left their range
+            if (fused_elem<VISC, true>(G, A, ab, bb, C, k, nint, e_glob, dtl_uniform)) fused_elem_plain<VISC>(G, A, ab, bb, C, k, nint, e_glob, dtl_uniform);
         }
+        if (stat) st[ST_E] += (unsigned long long)(clock64() - t0);
         __syncwarp();
         if (lane == 0) {
             ptx::mbar_arrive(cfull0 + 8 * c);

@@ -141,6 +141,13 @@ class NSComp2D:
         capi.check(self.L.cfdb_printflavia(self.h, str(path).encode(), int(it), np.asarray(flags, np.int32), int(append)))
 
     @staticmethod
+    def format_real(kind, v, w=0, d=0):
+        """one real as Fortran Ew.d ('E'), Fw.d ('F') or list-directed REAL(8) ('L')"""
+        buf = C.create_string_buffer(128)
+        capi.check(capi.lib().cfdb_format_real(ord(kind), float(v), int(w), int(d), buf, 128))
+        return buf.value.decode()
+
+    @staticmethod
     def cnv_record(it, time, r):
         """one line of <name>.cnv ('(I7, 5E14.6)')"""
         buf = C.create_string_buffer(128)

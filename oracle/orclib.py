@@ -187,6 +187,12 @@ class Oracle:
         self.L.orc_residual_norms(self.h, er, err)
         return er, err
 
+    def fluid_structure(self, dtmin, time):
+        self.L.orc_fluid_structure(self.h, float(dtmin), float(time))
+
+    def geometry(self, moving_step=0):
+        self.L.orc_geometry(self.h, int(moving_step))
+
     def step_norms(self):
         """ER, ERR as the time loop evaluated them on its last print step (before U = U1)."""
         return self.get("ER"), self.get("ERR")

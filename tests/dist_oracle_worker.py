@@ -35,14 +35,16 @@ def main():
 
     def exchange():
         reqs, rbuf = [], {}
-        views = {"U1": o.view("U1").reshape(-1, 4), "T": o.view("T"), "VEL_X": o.view("VEL_X"), "VEL_Y": o.view("VEL_Y")}
+        # the ghost message of libcfdb200 (kernels.cuh: halo_pack_state): U1(4), T, VEL_X, VEL_Y, E, P, RMACH; RHO = U1(1)
+        views = {"U1": o.view("U1").reshape(-1, 4), "T": o.view("T"), "VEL_X": o.view("VEL_X"), "VEL_Y": o.view("VEL_Y"),
+                 "E": o.view("E"), "P": o.view("P"), "RMACH": o.view("RMACH"), "RHO": o.view("RHO")}
         for s in part.neighbors:
             if s in part.send:
                 idx = part.send[s]
-                pack = np.concatenate([views["U1"][idx], views["T"][idx, None], views["VEL_X"][idx, None], views["VEL_Y"][idx, None]], 1)
+                pack = np.concatenate([views["U1"][idx]] + [views[k][idx, None] for k in ("T", "VEL_X", "VEL_Y", "E", "P", "RMACH")], 1)
                 reqs.append(dist.isend(torch.from_numpy(np.ascontiguousarray(pack)), dst=s))
             if s in part.recv:
-                rbuf[s] = torch.empty((part.recv[s].size, 7), dtype=torch.float64)
+                rbuf[s] = torch.empty((part.recv[s].size, 10), dtype=torch.float64)
                 reqs.append(dist.irecv(rbuf[s], src=s))
         for r in reqs:
             r.wait()
@@ -52,6 +54,8 @@ def main():
             views["T"][idx] = b[:, 4]
             views["VEL_X"][idx] = b[:, 5]
             views["VEL_Y"][idx] = b[:, 6]
+            views["E"][idx], views["P"][idx], views["RMACH"][idx] = b[:, 7], b[:, 8], b[:, 9]
+            views["RHO"][idx] = b[:, 0]
 
     for _ in range(steps):
         d = torch.tensor([o.step_part1()], dtype=torch.float64)
@@ -64,7 +68,10 @@ def main():
 
     box = [None] * world
     own = slice(0, part.n_owned)
-    dist.all_gather_object(box, (gid[own], o.get("U").reshape(-1, 4)[own], o.get("T")[own], o.scalar("DTMIN"), o.scalar("TIME")))
+    # ghosts carry every nodal array of the owner after the exchange (body forces read P at both ends of an edge)
+    gh = slice(part.n_owned, part.lc.npoin)
+    dist.all_gather_object(box, (gid[own], o.get("U").reshape(-1, 4)[own], o.get("T")[own], o.scalar("DTMIN"), o.scalar("TIME"),
+                                 gid[gh], o.get("P")[gh], o.get("RMACH")[gh]))
     if rank == 0:
         ref = Oracle(glc)
         ref.set("U", st["U"])
@@ -73,10 +80,12 @@ def main():
         ref.step(steps)
         U, T = np.zeros((glc.npoin, 4)), np.zeros(glc.npoin)
         seen = np.zeros(glc.npoin, int)
-        for g, u, t, dtmin, time in box:
+        for g, u, t, dtmin, time, gg, pg, mg_ in box:
             U[g], T[g] = u, t
             seen[g] += 1
             assert dtmin == ref.scalar("DTMIN") and time == ref.scalar("TIME")
+            assert np.array_equal(pg.view(np.uint64), ref.get("P")[gg].view(np.uint64)), "ghost P differs from the owner's"
+            assert np.array_equal(mg_.view(np.uint64), ref.get("RMACH")[gg].view(np.uint64)), "ghost RMACH differs"
         assert (seen == 1).all(), "every node must be owned exactly once"
         assert np.array_equal(U.view(np.uint64), ref.get("U").reshape(-1, 4).view(np.uint64)), "U differs"
         assert np.array_equal(T.view(np.uint64), ref.get("T").view(np.uint64)), "T differs"

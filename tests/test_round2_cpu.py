@@ -1,0 +1,128 @@
+"""Round-2 additions that need no GPU: list-directed REAL(8) layout, the greedy element colouring against a brute-force
+restatement, the oracle's ADAMSB pinned to the reference's own routine (interpreted from /root/reference), the static
+schedule tool on a built object."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import assert_bit_equal
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle.f90ref import refrun  # noqa: E402
+
+needs_ref = pytest.mark.skipif(not refrun.available(), reason="neither the reference sources nor oracle/_ref/refprog.py are here")
+
+
+def _fmt(kind, v, w=0, d=0):
+    from cfd_b200 import capi
+
+    buf = C.create_string_buffer(128)
+    capi.check(capi.lib().cfdb_format_real(ord(kind), float(v), w, d, buf, 128))
+    return buf.value.decode()
+
+
+def test_list_directed_real8_layout():
+    """gfortran's list-directed REAL(8): width 25, 17 significant digits, F editing with five trailing blanks inside
+    0.1 <= |x| < 1e17 and for zero, ES editing with a three-digit exponent outside (fortran/README.md build line)"""
+    want = {3.14: "   3.1400000000000001     ", 1e-3: "   1.0000000000000000E-003", 0.0: "   0.0000000000000000     ",
+            123456789.0: "   123456789.00000000     ", 1e20: "   1.0000000000000000E+020", -2.5e-7: "  -2.4999999999999999E-007",
+            0.1: "  0.10000000000000001     ", 1e16: "   10000000000000000.     ", 1.0: "   1.0000000000000000     "}
+    for v, s in want.items():
+        got = " " + _fmt("L", v)          # a record starts with one blank
+        assert got == s, (v, got, s)
+        assert float(got) == v            # 17 significant digits round-trip
+    rng = np.random.default_rng(0)
+    for v in np.concatenate([rng.normal(size=200) * 10.0 ** rng.integers(-30, 30, 200), [1e-310, -1e308]]):
+        s = _fmt("L", v)
+        assert len(s) == 25 and float(s) == v, (v, s)
+
+
+def test_greedy_element_colouring():
+    """first-fit in ascending element order with a forbidden mask per node"""
+    from cfd_b200 import capi, deck, meshgen
+
+    lc = deck.load(meshgen.channel(nx=41, ny=13))
+    col, nc = np.zeros(lc.nelem, np.int32), C.c_int32()
+    capi.check(capi.lib().cfdb_color_elements(lc.inpoel, lc.nelem, lc.npoin, col, C.byref(nc)))
+    used = [set() for _ in range(lc.npoin)]
+    for e, tri in enumerate(lc.inpoel):
+        forb = used[tri[0] - 1] | used[tri[1] - 1] | used[tri[2] - 1]
+        c = 0
+        while c in forb:
+            c += 1
+        assert col[e] == c, e
+        for n in tri:
+            used[n - 1].add(c)
+    assert nc.value == col.max() + 1 and 6 <= nc.value <= 12
+    for c in range(nc.value):                      # a colour class touches every node at most once
+        nodes = lc.inpoel[col == c].ravel()
+        assert np.unique(nodes).size == nodes.size
+
+
+@needs_ref
+def test_oracle_adamsb_equals_the_references_routine():
+    """ADAMSB (subrutinas.f90:851-1034) is never called by PROGRAM NSComp2D (the call at ns2DComp.ALE.f90:177 is commented
+    out): call the reference's subroutine on a post-run state, with NESTAB = 2 so that its CUARTO_ORDEN + ESTAB branch runs,
+    and compare every array it writes with the oracle's restatement."""
+    import importlib.util
+
+    from cfd_b200 import deck, meshgen
+    from oracle import orclib
+    from oracle.f90ref.refrun import Reference
+    from oracle.orclib import Oracle
+
+    spec = importlib.util.spec_from_file_location("make_golden_ref", os.path.join(ROOT, "tests", "golden", "make_golden_ref.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    name = "ref_channel_visc"
+    raw = mg.raw_case(name)
+    lc = deck.load(raw)
+    st = meshgen.density_bump(lc)
+    ref = Reference()
+    ref.run_program(raw, maxiter=3, initial_state=st)
+    md, g, var, vel, est = (ref.mod(m) for m in ("meshdata", "mvariabgen", "mvariables", "mvelocidades", "mestabilizacion"))
+    npoin, nelem = int(md.npoin), int(md.nelem)
+    orclib.lib().orc_smoothing(lc.X, lc.Y, lc.inpoel, lc.smooth_fix, lc.npoin, lc.nelem)
+    o = Oracle(lc)
+    for k, v in st.items():
+        o.set(k, v)
+    o.step(3)
+    assert_bit_equal(o.get("U"), g.u.T.ravel(), "state before ADAMSB")
+    dtmin = o.scalar("DTMIN")
+    rng = np.random.default_rng(11)
+    hist = [1e-3 * rng.normal(size=(4, npoin)) for _ in range(3)]       # some RHS history
+    for a, h in zip((g.rhs1, g.rhs2, g.rhs3), hist):
+        a[...] = h
+    for nm, h in zip(("RHS1", "RHS2", "RHS3"), hist):
+        o.set(nm, h.T.ravel())
+    g.u1[...] = g.u                                                        # ns2DComp.ALE.f90:168-172
+    gamm = np.full(npoin, float(ref.mod("inputdata").gama))
+    dtl = np.full(nelem, dtmin)
+    with np.errstate(all="ignore"):
+        ref.proc("adamsb")(np.float64(dtmin), 2, gamm, dtl)
+    o.set("DTL", dtl)
+    o.set("U1", o.get("U"))
+    o.set_scalar("NESTAB", 2)
+    o.L.orc_adamsb(o.h)
+    for nm, a in (("U1", g.u1), ("RHS", g.rhs), ("RHS1", g.rhs1), ("RHS2", g.rhs2), ("RHS3", g.rhs3), ("UN", g.un)):
+        assert_bit_equal(o.get(nm), a.T.ravel(), f"ADAMSB {nm}")
+    for nm, a in (("T", var.t), ("P", var.p), ("RHO", var.rho), ("E", var.e), ("RMACH", var.rmach), ("VEL_X", vel.vel_x),
+                  ("VEL_Y", vel.vel_y), ("SHOC", est.shoc), ("T_SUGN2", est.t_sugn2)):
+        assert_bit_equal(o.get(nm), a, f"ADAMSB {nm}")
+    assert np.max(np.abs(g.un)) > 0       # the CUARTO_ORDEN projection is kept here (no UN = 0.0 as in RK)
+
+
+def test_static_schedule_tool_runs_on_the_built_object():
+    import subprocess
+
+    obj = os.path.join(ROOT, "cfd_b200", "csrc", "cfdb.o")
+    if not os.path.exists(obj):
+        pytest.skip("cfdb.o not built here")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_stalls.py"), obj, "stage_fusedILb0ELi12"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "sum of stall fields" in r.stdout, r.stdout + r.stderr

@@ -92,7 +92,7 @@ fn("cfdb_write_skin", "int", [CTX, A("path", "cstr")],
 fn("cfdb_format_cnv", "int", [A("iter", "i32"), A("time", "d"), A("r", "cd[]", "(4)"), A("buf", "buf"), A("buflen", "i32")],
    "one record of <name>.cnv as '(I7, 5E14.6)' (the reference's '(I7, 4E14.6)' is one slot short, SURVEY.md F14)")
 fn("cfdb_format_real", "int", [A("kind", "i32"), A("v", "d"), A("w", "i32"), A("d", "i32"), A("buf", "buf"), A("buflen", "i32")],
-   "one real laid out as Fortran Ew.d (kind 'E') or Fw.d (kind 'F')")
+   "one real laid out as Fortran Ew.d (kind 'E'), Fw.d (kind 'F') or as a list-directed REAL(8) item (kind 'L'; w, d ignored)")
 fn("cfdb_step_norms", "int", [CTX, A("er", "d[]", "(4)"), A("err", "d[]", "(4)")],
    "the norms cfdb_step evaluated on its last print step (ITERPRINT==IPRINT or ITER==MAXITER, :186), i.e. before U=U1")
 fn("cfdb_get", "int", [CTX, A("name", "cstr"), A("host", "void"), A("count", "i64")],
