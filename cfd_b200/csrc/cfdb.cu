@@ -454,7 +454,10 @@ static int build_stage_tiles(cfdb_ctx* c, const int32_t* inpoel, const double* X
     // 112 / 32 is kept for experiments but needs more shared memory than an SM has once the mesh is large
     int TE = getenv("CFDB_TILE_TE") ? atoi(getenv("CFDB_TILE_TE")) : 384;
     if (TE != 384 && TE != 512) return fail("CFDB_TILE_TE must be 384 or 512");
-    const bool permute = getenv("CFDB_NO_PERM") == nullptr;
+    // CFDB_TILE_ORDER=morton: the round-2 mid-way order (Z-curve runs), kept for A/B timing
+    int order = getenv("CFDB_NO_PERM") ? topo::ORDER_FILE : topo::ORDER_RCB;
+    if (order != topo::ORDER_FILE && getenv("CFDB_TILE_ORDER") && !strcmp(getenv("CFDB_TILE_ORDER"), "morton")) order = topo::ORDER_MORTON;
+    const bool permute = order != topo::ORDER_FILE;
     // host copies of esup2 / eslot (file order)
     vector<int32_t> esup2(P + 1), eslot(3 * E), esup1(3 * E);
     if (c->host_topo_valid) {
@@ -466,7 +469,7 @@ static int build_stage_tiles(cfdb_ctx* c, const int32_t* inpoel, const double* X
         for (size_t k = 0; k < 3 * E; ++k) esup1[k] = eslot[k] / 3 + 1;
     }
     topo::Tiling T;
-    topo::build_tiling(inpoel, c->nelem, c->npoin, X, Y, esup1, esup2, eslot, c->h_bcflag, TE, permute, T);
+    topo::build_tiling(inpoel, c->nelem, c->npoin, X, Y, esup1, esup2, eslot, c->h_bcflag, TE, order, T);
     if (T.L.nint_max > 65535 || 12 * TE > 65535) return fail("tile too large for 16-bit slots");
     c->ntiles = T.ntiles;
     c->tile_ncw = TE / 32;
@@ -1029,6 +1032,11 @@ static int refresh_geo(cfdb_ctx* c) {
 // fused tile stage (stage_fused.cuh) + node_update over the tile-boundary nodes
 static bool fused_eligible(const cfdb_ctx* c) {
     static const bool off = getenv("CFDB_NO_FUSED") != nullptr;
+    // viscous flow: the element arithmetic needs ~200 registers to run without spills (tools/sass_stalls.py); at the 144 the
+    // stage kernel's element warps get it measured 2.26 ms + 0.35 ms per stage on the 16 M-triangle mesh against 1.67 + 0.55 ms
+    // for the two-kernel stage, so viscous flow keeps the two kernels unless CFDB_FUSED_VISC=1
+    static const bool fused_visc = getenv("CFDB_FUSED_VISC") != nullptr;
+    if (c->par.FMU > 2.2250738585072014e-308 && !fused_visc) return false;
     return !off && c->tiles_ok && !c->ale && !c->use_cuarto && !c->fast && !c->colored && !c->theta_nonzero && !c->dtl_force;
 }
 static int run_stage_fused(cfdb_ctx* c, const k::Gas& g, const double* dtl_arr, const double* dtl_sc, double rk_fact) {
@@ -2410,6 +2418,25 @@ extern "C" int cfdb_write_skin(cfdb_ctx* c, const char* path) {   // :833, :888 
     for (int k = 0; k < ne; ++k)
         std::fprintf(f, " %s%s%s\n", ffmt::list_r8(sk[k]).c_str(), ffmt::list_r8(sk[ne + k]).c_str(), ffmt::list_r8(sk[2 * (size_t)ne + k]).c_str());
     std::fclose(f);
+    return 0;
+}
+
+// host code, no GPU: the tile decomposition of the fused stage for a mesh (host_topology.h), for tests and mesh diagnostics
+extern "C" int cfdb_tile_elements(const int32_t* inpoel, int32_t nelem, int32_t npoin, const double* X, const double* Y, int32_t TE,
+                                  int32_t order, int32_t* i2e, double* stats) {
+    if (TE < 32 || TE % 32 || order < 0 || order > 2) return fail("cfdb_tile_elements: TE must be a multiple of 32, order 0..2");
+    for (size_t k = 0; k < 3 * (size_t)nelem; ++k)
+        if (inpoel[k] < 1 || inpoel[k] > npoin) return fail("cfdb_tile_elements: inpoel entry out of range");
+    vector<int32_t> esup1, esup2, eslot;
+    topo::build_esup(inpoel, nelem, npoin, esup1, esup2, &eslot);
+    vector<uint8_t> bcf((size_t)npoin, 0);
+    topo::Tiling T;
+    topo::build_tiling(inpoel, nelem, npoin, X, Y, esup1, esup2, eslot, bcf, TE, order, T);
+    if (i2e) std::copy(T.i2e.begin(), T.i2e.end(), i2e);
+    if (stats) {
+        stats[0] = T.interior_fraction; stats[1] = T.ntiles; stats[2] = T.L.ntn_max; stats[3] = T.L.nint_max;
+        stats[4] = T.L.nslot_max; stats[5] = T.L.tb_bytes; stats[6] = (double)T.bnodes.size(); stats[7] = (double)T.orphans.size();
+    }
     return 0;
 }
 

@@ -227,6 +227,12 @@ fn("cfdb_get_psup", "int", [A("inpoel", "ci32[]", E3), A("nelem", "i32"), A("npo
 fn("cfdb_color_elements", "int", [A("inpoel", "ci32[]", E3), A("nelem", "i32"), A("npoin", "i32"), A("color", "i32[]"), A("ncolors", "i32*")],
    "greedy first-fit colouring of the element list in ascending element order with a 64-bit forbidden mask per node\n"
    "(SURVEY.md B.3): color[e] = lowest colour not yet used at any of the element's three nodes; 0-based colours")
+fn("cfdb_tile_elements", "int", [A("inpoel", "ci32[]", E3), A("nelem", "i32"), A("npoin", "i32"), A("X", "cd[]"), A("Y", "cd[]"), A("TE", "i32"),
+                                 A("order", "i32"), A("i2e", "i32[]"), A("stats", "d[]")],
+   "the internal element order of the fused RK stage (host_topology.h): tiles of TE elements; order 0 = the file's,\n"
+   "1 = Morton runs, 2 = recursive coordinate bisection (the default of cfdb_create).  i2e[pos] = 0-based original element\n"
+   "at internal position pos; stats[8] = {fraction of nodes interior to one tile, tiles, max nodes touched per tile, max\n"
+   "interior nodes, max interior contributions, bytes of a tile's static block, tile-boundary nodes, orphans}.  No GPU.")
 
 FUNCS = [f for _, fs in SECTIONS for f in fs]
 
