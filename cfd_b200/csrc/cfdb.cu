@@ -107,6 +107,9 @@ static const char* kKernelNames[K_COUNT] = {"deriv", "masas", "normales", "delta
                                             "calcrhs_elem", "node_update", "dot", "norms", "spmv", "vec", "fixrows",
                                             "scalar", "laplace", "transf", "move_apply", "forces", "gcl", "layout", "fill", "halo", "stage_fused"};
 
+// one column of a nodal record array (kernels.cuh: CF / WF): col = &record[0][column], entries k::NREC doubles apart
+struct NodeField { k::Col col; };
+
 struct cfdb_ctx {
     int device = 0;
     cudaStream_t st = nullptr;
@@ -132,7 +135,10 @@ struct cfdb_ctx {
     DBuf<unsigned char> lpos, bcflag;
     DBuf<double> X, Y, X1, Y1, area, HH, HHX, HHY, dNx, dNy, M;
     // device: state
-    DBuf<double> U, U1, RHS, RHS1, RHS2, RHS3, UN, VEL_X, VEL_Y, W_X, W_Y, P, T, RHO, E, RMACH, GAMM;
+    DBuf<double> U, U1, RHS, RHS1, RHS2, RHS3, UN, W_X, W_Y;
+    // nodal records (kernels.cuh): NR1[n] = {T, GAMM, VEL_X, VEL_Y}, NR2[n] = {RHO, E, P, RMACH}; the named fields are columns
+    DBuf<double> NR1, NR2, ntmp;
+    NodeField T, GAMM, VEL_X, VEL_Y, RHO, E, P, RMACH;
     DBuf<double> SHOC, TS1, TS2, TS3, DT, DTL, EC, FC;
     // device: BC tables
     DBuf<int> bc_node, bc_kind, bc_wslot;
@@ -255,6 +261,33 @@ static int prof_resolve(cfdb_ctx* c) {
         TRY(prof_end(c, stream, id, _a, _b));                                 \
     } while (0)
 #define LAUNCH(id, kernel, grid, block, ...) LAUNCH_ON(c->st, id, kernel, grid, block, __VA_ARGS__)
+
+static int up_plain(cfdb_ctx* c, double* dev, const double* h, size_t n) {
+    if (n) CK(cudaMemcpyAsync(dev, h, n * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    return 0;
+}
+static int down_plain(cfdb_ctx* c, const double* dev, double* h, size_t n) {
+    if (n) CK(cudaMemcpyAsync(h, dev, n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    return 0;
+}
+// Columns of the nodal records cross the ABI as plain arrays: through the device scratch ntmp (stream-ordered, so
+// back-to-back calls may share it).
+static int col_from_plain(cfdb_ctx* c, NodeField f, const double* dev_plain, size_t n) {
+    if (n) LAUNCH(K_FILL, k::col_scatter, grid_for((long)n, 256), 256, (long)n, dev_plain, f.col);
+    return 0;
+}
+static int col_to_plain(cfdb_ctx* c, NodeField f, double* dev_plain, size_t n) {
+    if (n) LAUNCH(K_FILL, k::col_gather, grid_for((long)n, 256), 256, (long)n, f.col, dev_plain);
+    return 0;
+}
+static int up_node(cfdb_ctx* c, NodeField f, const double* h, size_t n) {
+    TRY(up_plain(c, c->ntmp.p, h, n));
+    return col_from_plain(c, f, c->ntmp.p, n);
+}
+static int down_node(cfdb_ctx* c, NodeField f, double* h, size_t n) {
+    TRY(col_to_plain(c, f, c->ntmp.p, n));
+    return down_plain(c, c->ntmp.p, h, n);
+}
 
 template <class T>
 static int upload(cfdb_ctx* c, DBuf<T>& d, const T* h, size_t n) {
@@ -633,8 +666,12 @@ extern "C" int cfdb_create(cfdb_ctx** out, const cfdb_params* par, int32_t npoin
     }
     B(upload(c, c->X, X, P));
     B(upload(c, c->Y, Y, P));
-    for (auto* d : {&c->X1, &c->Y1, &c->M, &c->VEL_X, &c->VEL_Y, &c->W_X, &c->W_Y, &c->P, &c->T, &c->RHO, &c->E, &c->RMACH,
-                    &c->GAMM, &c->lap_diag, &c->by, &c->bp, &c->bp2, &c->br, &c->bz, &c->bb, &c->xpos, &c->ypos, &c->dxpos,
+    B(zero(c, c->NR1, k::NREC * P));
+    B(zero(c, c->NR2, k::NREC * P));
+    B(zero(c, c->ntmp, P));
+    c->T.col.q = c->NR1.p + k::NR1_T; c->GAMM.col.q = c->NR1.p + k::NR1_GAMM; c->VEL_X.col.q = c->NR1.p + k::NR1_VX; c->VEL_Y.col.q = c->NR1.p + k::NR1_VY;
+    c->RHO.col.q = c->NR2.p + k::NR2_RHO; c->E.col.q = c->NR2.p + k::NR2_E; c->P.col.q = c->NR2.p + k::NR2_P; c->RMACH.col.q = c->NR2.p + k::NR2_RMACH;
+    for (auto* d : {&c->X1, &c->Y1, &c->M, &c->W_X, &c->W_Y, &c->lap_diag, &c->by, &c->bp, &c->bp2, &c->br, &c->bz, &c->bb, &c->xpos, &c->ypos, &c->dxpos,
                     &c->dypos, &c->pos_aux, &c->W_x_old, &c->W_y_old, &c->tmpA, &c->tmpB, &c->tmpC, &c->by2, &c->pos_aux2})
         B(zero(c, *d, P));
     for (auto* d : {&c->U, &c->U1, &c->RHS, &c->RHS1, &c->RHS2, &c->RHS3, &c->UN}) B(zero(c, *d, 4 * P));
@@ -695,8 +732,8 @@ extern "C" void cfdb_destroy(cfdb_ctx* c) {
     c->isfix.release();
     c->bp2.release(); c->by2.release(); c->pos_aux2.release();
     for (auto* d : {&c->X, &c->Y, &c->X1, &c->Y1, &c->area, &c->HH, &c->HHX, &c->HHY, &c->dNx, &c->dNy, &c->M, &c->U, &c->U1,
-                    &c->RHS, &c->RHS1, &c->RHS2, &c->RHS3, &c->UN, &c->VEL_X, &c->VEL_Y, &c->W_X, &c->W_Y, &c->P, &c->T,
-                    &c->RHO, &c->E, &c->RMACH, &c->GAMM, &c->SHOC, &c->TS1, &c->TS2, &c->TS3, &c->DT, &c->DTL, &c->EC, &c->FC,
+                    &c->RHS, &c->RHS1, &c->RHS2, &c->RHS3, &c->UN, &c->NR1, &c->NR2, &c->ntmp, &c->W_X, &c->W_Y,
+                    &c->SHOC, &c->TS1, &c->TS2, &c->TS3, &c->DT, &c->DTL, &c->EC, &c->FC,
                     &c->bc_vx, &c->bc_vy, &c->bc_rho, &c->bc_T, &c->wn_x, &c->wn_y, &c->lap_sparse, &c->lap_diag, &c->by,
                     &c->bp, &c->br, &c->bz, &c->bb, &c->xpos, &c->ypos, &c->dxpos, &c->dypos, &c->pos_aux, &c->xref, &c->yref,
                     &c->W_x_old, &c->W_y_old, &c->area_old, &c->redA, &c->redB, &c->tmpA, &c->tmpB, &c->tmpC})
@@ -798,10 +835,10 @@ static int halo_state(cfdb_ctx* c, cudaStream_t st = nullptr) {
     if (!nn) return 0;
     if (!st) st = c->st;
     int ms = c->send_ptr[nn], mr = c->recv_ptr[nn];
-    if (ms) LAUNCH_ON(st, K_HALO, k::halo_pack_state, grid_for(ms, 128), 128, ms, c->send_idx.p, c->U1.p, c->T.p, c->VEL_X.p, c->VEL_Y.p, c->E.p, c->P.p, c->RMACH.p, c->sendbuf.p);
+    if (ms) LAUNCH_ON(st, K_HALO, k::halo_pack_state, grid_for(ms, 128), 128, ms, c->send_idx.p, c->U1.p, c->T.col, c->VEL_X.col, c->VEL_Y.col, c->E.col, c->P.col, c->RMACH.col, c->sendbuf.p);
     TRY(halo_sendrecv(c, k::HALO_W, st));
-    if (mr) LAUNCH_ON(st, K_HALO, k::halo_unpack_state, grid_for(mr, 128), 128, mr, c->recv_idx.p, c->recvbuf.p, c->U1.p, c->T.p, c->VEL_X.p, c->VEL_Y.p,
-                      c->RHO.p, c->E.p, c->P.p, c->RMACH.p);
+    if (mr) LAUNCH_ON(st, K_HALO, k::halo_unpack_state, grid_for(mr, 128), 128, mr, c->recv_idx.p, c->recvbuf.p, c->U1.p, c->T.col, c->VEL_X.col, c->VEL_Y.col,
+                      c->RHO.col, c->E.col, c->P.col, c->RMACH.col);
     return 0;
 }
 static int allreduce(cfdb_ctx* c, double* dev, int count, ncclRedOp_t op) {
@@ -924,10 +961,10 @@ extern "C" int cfdb_init(cfdb_ctx* c) {
         u[4 * i] = RHOAMB; u[4 * i + 1] = RHOAMB * UAMB; u[4 * i + 2] = RHOAMB * VAMB; u[4 * i + 3] = ENERGIA * RHOAMB;
     }
     TRY(upload(c, c->U, u));
-    LAUNCH(K_FILL, k::fill_const, grid_for(P, 256), 256, (long)P, c->GAMM.p, p.GAMA);
-    LAUNCH(K_FILL, k::fill_const, grid_for(P, 256), 256, (long)P, c->VEL_X.p, UAMB);
-    LAUNCH(K_FILL, k::fill_const, grid_for(P, 256), 256, (long)P, c->VEL_Y.p, VAMB);
-    LAUNCH(K_FILL, k::fill_const, grid_for(P, 256), 256, (long)P, c->T.p, TAMB);
+    LAUNCH(K_FILL, k::fill_col, grid_for(P, 256), 256, (long)P, c->GAMM.col, p.GAMA);
+    LAUNCH(K_FILL, k::fill_col, grid_for(P, 256), 256, (long)P, c->VEL_X.col, UAMB);
+    LAUNCH(K_FILL, k::fill_col, grid_for(P, 256), 256, (long)P, c->VEL_Y.col, VAMB);
+    LAUNCH(K_FILL, k::fill_col, grid_for(P, 256), 256, (long)P, c->T.col, TAMB);
     LAUNCH(K_FILL, k::fill_const, grid_for(P, 256), 256, (long)P, c->W_X.p, -0.0);  // :121
     LAUNCH(K_FILL, k::fill_const, grid_for(P, 256), 256, (long)P, c->W_Y.p, 0.0);
     CK(cudaMemsetAsync(c->sc, 0, sizeof(k::Scal), c->st));
@@ -972,8 +1009,8 @@ static int run_estab(cfdb_ctx* c, const double* dtmin_dev) {
         else if (minb == 2) kern = k::estab<2, false>;
         else kern = k::estab<3, false>;
     }
-    LAUNCH(K_ESTAB, kern, grid_for(c->nelem, 256), 256, c->nelem, c->inp.p, c->U.p, c->T.p, c->VEL_X.p, c->VEL_Y.p,
-           c->W_X.p, c->W_Y.p, c->GAMM.p, c->dNx.p, c->dNy.p, p.FR, dtmin_dev, p.RHO_inf, p.T_inf, c->SHOC.p, c->TS1.p,
+    LAUNCH(K_ESTAB, kern, grid_for(c->nelem, 256), 256, c->nelem, c->inp.p, c->U.p, c->T.col, c->VEL_X.col, c->VEL_Y.col,
+           c->W_X.p, c->W_Y.p, c->GAMM.col, c->dNx.p, c->dNy.p, p.FR, dtmin_dev, p.RHO_inf, p.T_inf, c->SHOC.p, c->TS1.p,
            c->TS2.p, c->TS3.p);
     return 0;
 }
@@ -986,9 +1023,7 @@ static int run_calcrhs_elem(cfdb_ctx* c, const k::Gas& g, bool theta, bool ale, 
     const bool visc = g.mu_ref > 2.2250738585072014e-308;  // tiny(0d0), calcRHS.f90:119
     const int e0 = 0, e1 = c->nelem;
     const int B = 128, G = grid_for(e1 - e0, B);
-    void (*kern)(int, int, int, const int*, const double*, const double*, const double*, const double*, const double*, const double*,
-                 const double*, const double*, const double*, const double*, const double*, const double*, const double*,
-                 const double*, k::Gas, double*, double*) = nullptr;
+    decltype(&k::calcrhs_elem<false, false, false, 4>) kern = nullptr;
     switch ((visc ? 4 : 0) | (theta ? 2 : 0) | (ale ? 1 : 0)) {
         case 0: kern = k::calcrhs_elem<false, false, false, 4>; break;
         case 1: kern = k::calcrhs_elem<false, false, true, 4>; break;
@@ -999,7 +1034,7 @@ static int run_calcrhs_elem(cfdb_ctx* c, const k::Gas& g, bool theta, bool ale, 
         case 6: kern = k::calcrhs_elem<true, true, false, 3, 128, true>; break;
         default: kern = k::calcrhs_elem<true, true, true, 3, 128, true>; break;
     }
-    LAUNCH(K_CALCRHS, kern, G, B, e0, e1, c->nelem, c->inp.p, (c->Usrc ? c->Usrc : c->U.p), c->UN.p, c->T.p, c->W_X.p, c->W_Y.p,
+    LAUNCH(K_CALCRHS, kern, G, B, e0, e1, c->nelem, c->inp.p, (c->Usrc ? c->Usrc : c->U.p), c->UN.p, c->T.col, c->W_X.p, c->W_Y.p,
            c->dNx.p, c->dNy.p, c->area.p, c->SHOC.p, dtl_arr, dtl_sc, c->TS1.p, c->TS2.p, c->TS3.p, g, c->EC.p, c->FC.p);
     return 0;
 }
@@ -1009,9 +1044,9 @@ static int run_node(cfdb_ctx* c, cudaStream_t st, bool ale, bool update, double 
     if (n1 < 0) n1 = c->npoin;
     if (n1 <= n0) return 0;
     const int B = CFDB_NODE_BS, G = grid_for(n1 - n0, B);
-#define ARGS n0, n1, nlist, c->d_esup2.p, c->eslot.p, c->EC.p, c->FC.p, c->U.p, c->M.p, c->GAMM.p, c->W_X.p, c->W_Y.p, \
-             c->bcflag.p, bctab(c), rk_fact, c->par.FR, c->U1.p, c->RHS.p, c->RHO.p, c->VEL_X.p, c->VEL_Y.p, c->E.p, \
-             c->P.p, c->T.p, c->RMACH.p
+#define ARGS n0, n1, nlist, c->d_esup2.p, c->eslot.p, c->EC.p, c->FC.p, c->U.p, c->M.p, c->GAMM.col, c->W_X.p, c->W_Y.p, \
+             c->bcflag.p, bctab(c), rk_fact, c->par.FR, c->U1.p, c->RHS.p, c->RHO.col, c->VEL_X.col, c->VEL_Y.col, c->E.col, \
+             c->P.col, c->T.col, c->RMACH.col
     auto kern = k::node_update<false, true>;
     if (ale && update) kern = k::node_update<true, true>;
     else if (ale) kern = k::node_update<true, false>;
@@ -1044,10 +1079,10 @@ static int run_stage_fused(cfdb_ctx* c, const k::Gas& g, const double* dtl_arr, 
     k::StageArgs A{};
     A.ntiles = c->ntiles; A.TB = c->TB.p; A.geo = c->geo.p; A.Epad = c->Epad;
     A.shoc = c->SHOC.p; A.ts1 = c->TS1.p; A.ts2 = c->TS2.p; A.ts3 = c->TS3.p; A.dtl_arr = dtl_arr; A.dtl_sc = dtl_sc;
-    A.Usrc = c->Usrc ? c->Usrc : c->U.p; A.U = c->U.p; A.T = c->T.p; A.M = c->M.p; A.GAMM = c->GAMM.p; A.WXa = c->W_X.p; A.WYa = c->W_Y.p;
+    A.Usrc = c->Usrc ? c->Usrc : c->U.p; A.U = c->U.p; A.T = c->T.col; A.M = c->M.p; A.GAMM = c->GAMM.col; A.WXa = c->W_X.p; A.WYa = c->W_Y.p;
     A.bc = bctab(c); A.rk_fact = rk_fact; A.FR = c->par.FR; A.g = g;
-    A.EC = c->EC.p; A.U1 = c->U1.p; A.RHS = c->RHS.p; A.RHO = c->RHO.p; A.VELX = c->VEL_X.p; A.VELY = c->VEL_Y.p; A.Ea = c->E.p;
-    A.Pa = c->P.p; A.Ta = c->T.p; A.RMACH = c->RMACH.p;
+    A.EC = c->EC.p; A.U1 = c->U1.p; A.RHS = c->RHS.p; A.RHO = c->RHO.col; A.VELX = c->VEL_X.col; A.VELY = c->VEL_Y.col; A.Ea = c->E.col;
+    A.Pa = c->P.col; A.Ta = c->T.col; A.RMACH = c->RMACH.col;
     k::TileGeom G = c->tgeom;
     G.nfields = dtl_arr ? 12 : 11;
     if (G.nfields > c->tgeom.nfields) return fail("run_stage_fused: stage layout was sized without a local time step array");
@@ -1096,7 +1131,7 @@ extern "C" int cfdb_rk_stage(cfdb_ctx* c, int32_t irk) {
         if (c->use_cuarto) {
             // cuarto_orden(U1, UN, ...): the loop has just copied U1 = U (ns2DComp.ALE.f90:168-172; the copy itself is
             // elided here because every stage rewrites U1), so the projection is evaluated at U
-            LAUNCH(K_CALCRHS, k::cuarto_elem, grid_for(c->nelem, 128), 128, c->nelem, c->inp.p, c->U.p, c->GAMM.p, c->dNx.p,
+            LAUNCH(K_CALCRHS, k::cuarto_elem, grid_for(c->nelem, 128), 128, c->nelem, c->inp.p, c->U.p, c->GAMM.col, c->dNx.p,
                    c->dNy.p, c->area.p, c->EC.p);
             LAUNCH(K_NODE, k::cuarto_node, grid_for(c->npoin, 256), 256, c->npoin, c->d_esup2.p, c->eslot.p, c->EC.p, c->M.p, c->UN.p);
             TRY(halo_vec(c, c->UN.p, 4));
@@ -1117,7 +1152,7 @@ extern "C" int cfdb_rk_stage(cfdb_ctx* c, int32_t irk) {
         const bool visc = g.mu_ref > 2.2250738585072014e-308;
         cudaEvent_t _a = nullptr, _b = nullptr;
         TRY(prof_begin(c, c->st, K_CALCRHS, &_a, &_b));
-        if (fastmode::launch_calcrhs_staged_fma(visc, c->st, c->nelem, c->inp.p, c->U.p, c->T.p, c->dNx.p, c->dNy.p, c->area.p,
+        if (fastmode::launch_calcrhs_staged_fma(visc, c->st, c->nelem, c->inp.p, c->U.p, c->T.col.q, c->dNx.p, c->dNy.p, c->area.p,
                                                 c->SHOC.p, dtl_arr, &c->sc->DTMIN, c->TS1.p, c->TS2.p, c->TS3.p, g.Cv, g.lambda_ref,
                                                 g.mu_ref, g.gamma0, g.T_inf, g.cte, c->EC.p))
             return fail("calcrhs_staged_fma launch failed");
@@ -1136,11 +1171,11 @@ extern "C" int cfdb_rk_stage(cfdb_ctx* c, int32_t irk) {
         for (size_t col = 0; col + 1 < c->color_ptr.size(); ++col) {
             const int n0 = c->color_ptr[col], nc = c->color_ptr[col + 1] - n0;
             if (nc)
-                LAUNCH(K_CALCRHS, kc, grid_for(nc, 128), 128, nc, c->color_list.p + n0, c->nelem, c->inp.p, c->U.p, c->T.p, c->W_X.p, c->W_Y.p,
+                LAUNCH(K_CALCRHS, kc, grid_for(nc, 128), 128, nc, c->color_list.p + n0, c->nelem, c->inp.p, c->U.p, c->T.col, c->W_X.p, c->W_Y.p,
                        c->dNx.p, c->dNy.p, c->area.p, c->SHOC.p, dtl_arr, &c->sc->DTMIN, c->TS1.p, c->TS2.p, c->TS3.p, g, c->RHS.p);
         }
-        LAUNCH(K_NODE, k::node_update_rhs, grid_for(c->npoin, 256), 256, c->npoin, c->RHS.p, c->U.p, c->M.p, c->GAMM.p, c->W_X.p, c->W_Y.p,
-               c->bcflag.p, bctab(c), RK_FACT, c->par.FR, c->U1.p, c->RHO.p, c->VEL_X.p, c->VEL_Y.p, c->E.p, c->P.p, c->T.p, c->RMACH.p);
+        LAUNCH(K_NODE, k::node_update_rhs, grid_for(c->npoin, 256), 256, c->npoin, c->RHS.p, c->U.p, c->M.p, c->GAMM.col, c->W_X.p, c->W_Y.p,
+               c->bcflag.p, bctab(c), RK_FACT, c->par.FR, c->U1.p, c->RHO.col, c->VEL_X.col, c->VEL_Y.col, c->E.col, c->P.col, c->T.col, c->RMACH.col);
         TRY(halo_state(c));
         return 0;
     }
@@ -1150,17 +1185,17 @@ extern "C" int cfdb_rk_stage(cfdb_ctx* c, int32_t irk) {
         CK(cudaMemsetAsync(c->RHS.p, 0, 4 * (size_t)c->npoin * sizeof(double), c->st));
         cudaEvent_t _a = nullptr, _b = nullptr;
         TRY(prof_begin(c, c->st, K_CALCRHS, &_a, &_b));
-        if (fastmode::launch_calcrhs_scatter(visc, c->ale, c->st, c->nelem, c->inp.p, c->U.p, c->T.p, c->W_X.p, c->W_Y.p, c->dNx.p,
+        if (fastmode::launch_calcrhs_scatter(visc, c->ale, c->st, c->nelem, c->inp.p, c->U.p, c->T.col.q, c->W_X.p, c->W_Y.p, c->dNx.p,
                                              c->dNy.p, c->area.p, c->SHOC.p, dtl_arr, &c->sc->DTMIN, c->TS1.p, c->TS2.p, c->TS3.p,
                                              g.Cv, g.lambda_ref, g.mu_ref, g.gamma0, g.T_inf, g.cte, c->RHS.p))
             return fail("calcrhs_scatter launch failed");
         TRY(prof_end(c, c->st, K_CALCRHS, _a, _b));
         TRY(prof_begin(c, c->st, K_NODE, &_a, &_b));
         k::BcTab b = bctab(c);
-        if (fastmode::launch_node_update_rhs(c->st, c->npoin, c->RHS.p, c->U.p, c->M.p, c->GAMM.p, c->W_X.p, c->W_Y.p, c->bcflag.p,
+        if (fastmode::launch_node_update_rhs(c->st, c->npoin, c->RHS.p, c->U.p, c->M.p, c->GAMM.col.q, c->W_X.p, c->W_Y.p, c->bcflag.p,
                                              b.nb, b.node, b.kind, b.vx, b.vy, b.rho, b.Tfix, b.wslot, b.wn_x, b.wn_y, b.wn_valid,
-                                             RK_FACT, c->par.FR, c->U1.p, c->RHO.p, c->VEL_X.p, c->VEL_Y.p, c->E.p, c->P.p, c->T.p,
-                                             c->RMACH.p))
+                                             RK_FACT, c->par.FR, c->U1.p, c->RHO.col.q, c->VEL_X.col.q, c->VEL_Y.col.q, c->E.col.q, c->P.col.q, c->T.col.q,
+                                             c->RMACH.col.q))
             return fail("node_update_rhs launch failed");
         TRY(prof_end(c, c->st, K_NODE, _a, _b));
         TRY(halo_state(c));
@@ -1185,7 +1220,7 @@ static int run_adamsb(cfdb_ctx* c) {
     if (c->nestab == 4) c->nestab = 1;
     if (c->nestab == 2) {
         // cuarto_orden(U1, UN, ...) with U1 = U (ns2DComp.ALE.f90:168-172); no UN = 0.0 afterwards in this routine
-        LAUNCH(K_CALCRHS, k::cuarto_elem, grid_for(c->nelem, 128), 128, c->nelem, c->inp.p, c->U.p, c->GAMM.p, c->dNx.p, c->dNy.p,
+        LAUNCH(K_CALCRHS, k::cuarto_elem, grid_for(c->nelem, 128), 128, c->nelem, c->inp.p, c->U.p, c->GAMM.col, c->dNx.p, c->dNy.p,
                c->area.p, c->EC.p);
         LAUNCH(K_NODE, k::cuarto_node, grid_for(c->npoin, 256), 256, c->npoin, c->d_esup2.p, c->eslot.p, c->EC.p, c->M.p, c->UN.p);
         TRY(halo_vec(c, c->UN.p, 4));
@@ -1198,9 +1233,9 @@ static int run_adamsb(cfdb_ctx* c) {
     const double* dtl_arr = p.ITLOCAL != 0 ? c->DTL.p : nullptr;
     TRY(run_calcrhs_elem(c, g, true, c->ale, dtl_arr, &c->sc->DTMIN));
     auto kern = c->ale ? k::node_update_adamsb<true> : k::node_update_adamsb<false>;
-    LAUNCH(K_NODE, kern, grid_for(c->npoin, 128), 128, c->npoin, c->d_esup2.p, c->eslot.p, c->EC.p, c->FC.p, c->U.p, c->M.p, c->GAMM.p,
-           c->W_X.p, c->W_Y.p, c->bcflag.p, bctab(c), p.FR, c->U1.p, c->RHS.p, c->RHS1.p, c->RHS2.p, c->RHS3.p, c->RHO.p, c->VEL_X.p,
-           c->VEL_Y.p, c->E.p, c->P.p, c->T.p, c->RMACH.p);
+    LAUNCH(K_NODE, kern, grid_for(c->npoin, 128), 128, c->npoin, c->d_esup2.p, c->eslot.p, c->EC.p, c->FC.p, c->U.p, c->M.p, c->GAMM.col,
+           c->W_X.p, c->W_Y.p, c->bcflag.p, bctab(c), p.FR, c->U1.p, c->RHS.p, c->RHS1.p, c->RHS2.p, c->RHS3.p, c->RHO.col, c->VEL_X.col,
+           c->VEL_Y.col, c->E.col, c->P.col, c->T.col, c->RMACH.col);
     TRY(halo_state(c));
     // RHS1-3 at ghost nodes are never read (the history enters the update of owned nodes only)
     return 0;
@@ -1289,7 +1324,7 @@ extern "C" int cfdb_fluid_structure(cfdb_ctx* c, double dtmin, double time) {
     // XREF(2)=1.4, YREF(2)=0 are overwritten on every call (meshMove.f90:58): applied once in cfdb_create
     if (c->nset || (c->nranks > 1 && c->ale)) {  // every rank of a moving-mesh run joins the all-reduce, with or without body edges of its own
         CK(cudaMemsetAsync(c->sc->FX, 0, 30 * sizeof(double), c->st));
-        if (c->nset) LAUNCH(K_FORCES, k::forces, 1, 32, c->nset, c->n_owned, c->set_ptr.p, c->set_n1.p, c->set_n2.p, c->X.p, c->Y.p, c->P.p,
+        if (c->nset) LAUNCH(K_FORCES, k::forces, 1, 32, c->nset, c->n_owned, c->set_ptr.p, c->set_n1.p, c->set_n2.p, c->X.p, c->Y.p, c->P.col,
                c->xref.p, c->yref.p, c->sc);
         TRY(allreduce(c, c->sc->FX, 30, ncclSum));  // FX,FY,RM are contiguous in Scal
     }
@@ -1370,7 +1405,7 @@ extern "C" int cfdb_force_visc(cfdb_ctx* c) {
     CK(cudaMemsetAsync(c->fvisc.p, 0, 20 * sizeof(double), c->st));  // F_VX = 0; F_VY = 0 (:832)
     if (c->nset)
         LAUNCH(K_FORCES, k::force_visc, 1, 32, c->nset, c->n_owned, c->set_ptr.p, c->set_n1.p, c->set_n2.p, c->set_el.p, c->nelem,
-               c->inp.p, c->X.p, c->Y.p, c->P.p, c->T.p, c->VEL_X.p, c->VEL_Y.p, c->dNx.p, c->dNy.p, p.U_inf, p.V_inf, p.RHO_inf,
+               c->inp.p, c->X.p, c->Y.p, c->P.col, c->T.col, c->VEL_X.col, c->VEL_Y.col, c->dNx.p, c->dNy.p, p.U_inf, p.V_inf, p.RHO_inf,
                p.T_inf, c->fvisc.p, c->skin.p, c->nedges);
     if (c->nranks > 1) TRY(allreduce(c, c->fvisc.p, 20, ncclSum));
     return 0;
@@ -1396,10 +1431,11 @@ extern "C" int cfdb_printflavia(cfdb_ctx* c, const char* path, int32_t iter, con
     CK(cudaSetDevice(c->device));
     const size_t P = c->npoin;
     vector<double> rho(P), vx(P), vy(P), wx(P), wy(P), pr(P), tt(P), en(P), gm(P), x1(P), y1(P);
-    struct { double* h; const double* d; } cp[] = {{rho.data(), c->RHO.p}, {vx.data(), c->VEL_X.p}, {vy.data(), c->VEL_Y.p},
-        {wx.data(), c->W_X.p}, {wy.data(), c->W_Y.p}, {pr.data(), c->P.p}, {tt.data(), c->T.p}, {en.data(), c->E.p},
-        {gm.data(), c->GAMM.p}, {x1.data(), c->X1.p}, {y1.data(), c->Y1.p}};
+    struct { double* h; const double* d; } cp[] = {{wx.data(), c->W_X.p}, {wy.data(), c->W_Y.p}, {x1.data(), c->X1.p}, {y1.data(), c->Y1.p}};
     for (auto& q : cp) CK(cudaMemcpyAsync(q.h, q.d, P * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    struct { double* h; NodeField f; } cn[] = {{rho.data(), c->RHO}, {vx.data(), c->VEL_X}, {vy.data(), c->VEL_Y}, {pr.data(), c->P},
+        {tt.data(), c->T}, {en.data(), c->E}, {gm.data(), c->GAMM}};
+    for (auto& q : cn) TRY(down_node(c, q.f, q.h, P));
     CK(cudaStreamSynchronize(c->st));
     for (size_t i = 0; i < P; ++i) { vx[i] = vx[i] - wx[i]; vy[i] = vy[i] - wy[i]; }   // VEL_X - W_X, VEL_Y - W_Y (:225)
     std::FILE* f = std::fopen(path, append ? "a" : "w");
@@ -1475,7 +1511,7 @@ static int step_body(cfdb_ctx* c) {
         const bool moving = c->ale;  // as in run_estab
         auto kdt = p.ITLOCAL != 0 ? (moving ? k::deltat<true, true> : k::deltat<true, false>)
                                   : (moving ? k::deltat<false, true> : k::deltat<false, false>);
-        LAUNCH(K_DELTAT, kdt, grid_for(E, 256), 256, E, c->inp.p, c->area.p, c->T.p, c->VEL_X.p, c->VEL_Y.p,
+        LAUNCH(K_DELTAT, kdt, grid_for(E, 256), 256, E, c->inp.p, c->area.p, c->T.col, c->VEL_X.col, c->VEL_Y.col,
                c->W_X.p, c->W_Y.p, p.FSAFE, p.T_inf, c->DT.p, c->sc);
     }
     TRY(allreduce(c, &c->sc->dtmin_acc, 1, ncclMin));
@@ -1604,9 +1640,9 @@ extern "C" int cfdb_step_streamed(cfdb_ctx* c, const double* in_U, const double*
     // 2. compute stream: staging -> state, the step, state -> staging
     CK(cudaStreamWaitEvent(c->st, c->ev_in_done, 0));
     if (in_U) CK(cudaMemcpyAsync(c->U.p, c->sin_U.p, 4 * P * B, cudaMemcpyDeviceToDevice, c->st));
-    if (in_T) CK(cudaMemcpyAsync(c->T.p, c->sin_T.p, P * B, cudaMemcpyDeviceToDevice, c->st));
-    if (in_VEL_X) CK(cudaMemcpyAsync(c->VEL_X.p, c->sin_VX.p, P * B, cudaMemcpyDeviceToDevice, c->st));
-    if (in_VEL_Y) CK(cudaMemcpyAsync(c->VEL_Y.p, c->sin_VY.p, P * B, cudaMemcpyDeviceToDevice, c->st));
+    if (in_T) TRY(col_from_plain(c, c->T, c->sin_T.p, P));
+    if (in_VEL_X) TRY(col_from_plain(c, c->VEL_X, c->sin_VX.p, P));
+    if (in_VEL_Y) TRY(col_from_plain(c, c->VEL_Y, c->sin_VY.p, P));
     CK(cudaEventRecord(c->ev_in_used, c->st));
     TRY(step_once(c));
     if (c->streamed_any) CK(cudaStreamWaitEvent(c->st, c->ev_out_done, 0));   // the previous download has left the staging
@@ -1617,9 +1653,9 @@ extern "C" int cfdb_step_streamed(cfdb_ctx* c, const double* in_U, const double*
         CK(cudaMemcpyAsync(c->sout_N.p, c->sc->red, 8 * B, cudaMemcpyDeviceToDevice, c->st));
     }
     if (out_U) CK(cudaMemcpyAsync(c->sout_U.p, c->U.p, 4 * P * B, cudaMemcpyDeviceToDevice, c->st));
-    if (out_T) CK(cudaMemcpyAsync(c->sout_T.p, c->T.p, P * B, cudaMemcpyDeviceToDevice, c->st));
-    if (out_VEL_X) CK(cudaMemcpyAsync(c->sout_VX.p, c->VEL_X.p, P * B, cudaMemcpyDeviceToDevice, c->st));
-    if (out_VEL_Y) CK(cudaMemcpyAsync(c->sout_VY.p, c->VEL_Y.p, P * B, cudaMemcpyDeviceToDevice, c->st));
+    if (out_T) TRY(col_to_plain(c, c->T, c->sout_T.p, P));
+    if (out_VEL_X) TRY(col_to_plain(c, c->VEL_X, c->sout_VX.p, P));
+    if (out_VEL_Y) TRY(col_to_plain(c, c->VEL_Y, c->sout_VY.p, P));
     CK(cudaEventRecord(c->ev_step_done, c->st));
     // 3. download
     CK(cudaStreamWaitEvent(c->st_out, c->ev_step_done, 0));
@@ -1716,14 +1752,6 @@ extern "C" int64_t cfdb_launch_count(cfdb_ctx* c) { return c->launches; }
 
 // ---------------------------------------------------------------------------------------------
 // host <-> device transfers of nodal and element arrays
-static int up_plain(cfdb_ctx* c, double* dev, const double* h, size_t n) {
-    if (n) CK(cudaMemcpyAsync(dev, h, n * sizeof(double), cudaMemcpyHostToDevice, c->st));
-    return 0;
-}
-static int down_plain(cfdb_ctx* c, const double* dev, double* h, size_t n) {
-    if (n) CK(cudaMemcpyAsync(h, dev, n * sizeof(double), cudaMemcpyDeviceToHost, c->st));
-    return 0;
-}
 // Element arrays cross the ABI in the file's element order and live on the device in the internal (tile) order.
 // scratch: EC is free between calls (12 doubles per element); an array that IS EC goes through a temporary.
 static int up_elem(cfdb_ctx* c, double* dev, const double* h, int w = 1) {   // dev[p][q] = h[i2e[p]][q]
@@ -1777,7 +1805,7 @@ struct Field {
     void* dev = nullptr;          // device pointer (doubles or ints)
     const void* host = nullptr;   // or host-resident integer artefact
     int64_t count = 0;
-    int kind = 0;                 // 0 f64 plain, 1 f64 (3,E) stored [3][E], 2 int32 host (read-only), 3 computed
+    int kind = 0;                 // 0 f64 plain, 1 f64 (3,E) stored [3][E], 2 int32 host (read-only), 3 computed, 4 column of a nodal record array
     int ew = 0;                   // > 0: element-indexed, ew doubles per element, stored in the internal element order
 };
 static bool find_field(cfdb_ctx* c, const std::string& n, Field& f) {
@@ -1790,8 +1818,10 @@ static bool find_field(cfdb_ctx* c, const std::string& n, Field& f) {
     FE("HHX", HHX, 1) FE("HHY", HHY, 1) FS("dNx", dNx) FS("dNy", dNy)
     FD("U", U, 4 * P) FD("U1", U1, 4 * P) FD("RHS", RHS, 4 * P) FD("UN", UN, 4 * P)
     FD("RHS1", RHS1, 4 * P) FD("RHS2", RHS2, 4 * P) FD("RHS3", RHS3, 4 * P)
-    FD("VEL_X", VEL_X, P) FD("VEL_Y", VEL_Y, P) FD("W_X", W_X, P) FD("W_Y", W_Y, P) FD("P", P, P) FD("T", T, P)
-    FD("RHO", RHO, P) FD("E", E, P) FD("RMACH", RMACH, P) FD("GAMM", GAMM, P)
+#define FN(name, fld) if (n == name) { f.dev = c->fld.col.q; f.count = P; f.kind = 4; return true; }
+    FN("VEL_X", VEL_X) FN("VEL_Y", VEL_Y) FD("W_X", W_X, P) FD("W_Y", W_Y, P) FN("P", P) FN("T", T)
+    FN("RHO", RHO) FN("E", E) FN("RMACH", RMACH) FN("GAMM", GAMM)
+#undef FN
     FE("SHOC", SHOC, 1) FE("T_SUGN1", TS1, 1) FE("T_SUGN2", TS2, 1) FE("T_SUGN3", TS3, 1) FE("DT", DT, 1)
     FD("lap_sparse", lap_sparse, c->nnz) FD("lap_diag", lap_diag, P) FD("xpos", xpos, P) FD("ypos", ypos, P)
     FD("dxpos", dxpos, P) FD("dypos", dypos, P) FD("W_x_old", W_x_old, P) FD("W_y_old", W_y_old, P)
@@ -1820,7 +1850,14 @@ extern "C" int cfdb_halo_exchange(cfdb_ctx* c, const char* name) {
     CK(cudaSetDevice(c->device));
     Field f;
     std::string n(name);
-    if (!find_field(c, n, f) || f.kind != 0) return fail("cfdb_halo_exchange: not a nodal float64 field: " + n);
+    if (!find_field(c, n, f) || (f.kind != 0 && f.kind != 4)) return fail("cfdb_halo_exchange: not a nodal float64 field: " + n);
+    if (f.kind == 4) {   // a column of a nodal record array: through the plain scratch
+        TRY(col_to_plain(c, NodeField{k::Col{(double*)f.dev}}, c->ntmp.p, (size_t)c->npoin));
+        TRY(halo_vec(c, c->ntmp.p, 1));
+        TRY(col_from_plain(c, NodeField{k::Col{(double*)f.dev}}, c->ntmp.p, (size_t)c->npoin));
+        CK(cudaStreamSynchronize(c->st));
+        return 0;
+    }
     int w = f.count == 4 * (int64_t)c->npoin ? 4 : (f.count == c->npoin ? 1 : 0);
     if (!w) return fail("cfdb_halo_exchange: not a nodal field: " + n);
     TRY(halo_vec(c, (double*)f.dev, w));
@@ -1854,6 +1891,11 @@ extern "C" int cfdb_get(cfdb_ctx* c, const char* name, void* host, int64_t count
         return 0;
     }
     if (f.kind == 1) return down_soa3(c, (const double*)f.dev, (double*)host);
+    if (f.kind == 4) {
+        TRY(down_node(c, NodeField{k::Col{(double*)f.dev}}, (double*)host, (size_t)f.count));
+        CK(cudaStreamSynchronize(c->st));
+        return 0;
+    }
     if (n == "DTL") {  // ns2DComp.ALE.f90:159-164
         if (count < c->nelem) return fail("cfdb_get: host buffer too small for DTL");
         if (c->par.ITLOCAL != 0) {
@@ -1890,8 +1932,13 @@ extern "C" int cfdb_set(cfdb_ctx* c, const char* name, const void* host, int64_t
     Field f;
     std::string n(name);
     if (!find_field(c, n, f)) return fail("cfdb_set: unknown field " + n);
-    if (f.kind >= 2 || n == "dxpos" || n == "dypos") return fail("cfdb_set: field " + n + " is read-only");
+    if (f.kind == 2 || f.kind == 3 || n == "dxpos" || n == "dypos") return fail("cfdb_set: field " + n + " is read-only");
     if (count != f.count) return fail("cfdb_set: wrong element count for " + n);
+    if (f.kind == 4) {
+        TRY(up_node(c, NodeField{k::Col{(double*)f.dev}}, (const double*)host, (size_t)f.count));
+        CK(cudaStreamSynchronize(c->st));
+        return 0;
+    }
     if (f.kind == 0 && f.ew > 0) {
         TRY(up_elem(c, (double*)f.dev, (const double*)host, f.ew));
         CK(cudaStreamSynchronize(c->st));
@@ -1980,7 +2027,7 @@ extern "C" int cfdb_calcrhs(cfdb_ctx* c, double* rhs, const double* U, const dou
     TRY(up_soa3(c, c->dNy.p, dNy));
     TRY(up_plain(c, c->U.p, U, 4 * P));
     TRY(up_plain(c, c->UN.p, theta, 4 * P));
-    TRY(up_plain(c, c->T.p, T, P));
+    TRY(up_node(c, c->T, T, P));
     TRY(up_elem(c, c->area.p, area)); c->geo_dirty = true;
     TRY(up_elem(c, c->SHOC.p, shoc));
     TRY(up_elem(c, c->DTL.p, dtl));
@@ -2035,15 +2082,15 @@ extern "C" int cfdb_deltat(cfdb_ctx* c, double* dtmin, double* dt, const int32_t
     (void)inpoel; (void)FR; (void)GAMA;  // VC = sqrt(GAMA*FR*T) is dead in the reference (subrutinas.f90:179)
     const size_t P = npoin, E = nelem;
     TRY(up_elem(c, c->area.p, area)); c->geo_dirty = true;
-    TRY(up_plain(c, c->T.p, T, P));
-    TRY(up_plain(c, c->VEL_X.p, vel_x, P));
-    TRY(up_plain(c, c->VEL_Y.p, vel_y, P));
+    TRY(up_node(c, c->T, T, P));
+    TRY(up_node(c, c->VEL_X, vel_x, P));
+    TRY(up_node(c, c->VEL_Y, vel_y, P));
     TRY(up_plain(c, c->W_X.p, w_x, P));
     TRY(up_plain(c, c->W_Y.p, w_y, P));
     if (!c->ale) { c->ale = true; c->epoch++; TRY(zero(c, c->FC, 12 * E)); }   // caller's W is resident now (see cfdb_fuente)
     LAUNCH(K_SCALAR, k::set_double, 1, 1, &c->sc->dtmin_acc, 1.e20);
-    LAUNCH(K_DELTAT, k::deltat<true>, grid_for(nelem, 256), 256, nelem, c->inp.p, c->area.p, c->T.p, c->VEL_X.p,
-           c->VEL_Y.p, c->W_X.p, c->W_Y.p, FSAFE, T_inf, c->DT.p, c->sc);
+    LAUNCH(K_DELTAT, k::deltat<true>, grid_for(nelem, 256), 256, nelem, c->inp.p, c->area.p, c->T.col, c->VEL_X.col,
+           c->VEL_Y.col, c->W_X.p, c->W_Y.p, FSAFE, T_inf, c->DT.p, c->sc);
     LAUNCH(K_DTL, k::dtl_blend, grid_for(nelem, 256), 256, nelem, c->DT.p, c->DTL.p, c->sc, 0);
     TRY(down_elem(c, c->DT.p, dt));
     TRY(read_scal(c));
@@ -2062,16 +2109,16 @@ extern "C" int cfdb_estab(cfdb_ctx* c, const double* U, const double* T, const d
     TRY(up_soa3(c, c->dNx.p, dNx));
     TRY(up_soa3(c, c->dNy.p, dNy));
     TRY(up_plain(c, c->U.p, U, 4 * P));
-    TRY(up_plain(c, c->T.p, T, P));
-    TRY(up_plain(c, c->VEL_X.p, vel_x, P));
-    TRY(up_plain(c, c->VEL_Y.p, vel_y, P));
+    TRY(up_node(c, c->T, T, P));
+    TRY(up_node(c, c->VEL_X, vel_x, P));
+    TRY(up_node(c, c->VEL_Y, vel_y, P));
     TRY(up_plain(c, c->W_X.p, w_x, P));
     TRY(up_plain(c, c->W_Y.p, w_y, P));
-    TRY(up_plain(c, c->GAMM.p, GAMM, P));
+    TRY(up_node(c, c->GAMM, GAMM, P));
     if (!c->ale) { c->ale = true; c->epoch++; TRY(zero(c, c->FC, 12 * E)); }   // caller's W is resident now (see cfdb_fuente)
     LAUNCH(K_SCALAR, k::set_double, 1, 1, &c->sc->red[15], DTMIN);
-    LAUNCH(K_ESTAB, k::estab<3>, grid_for(nelem, 256), 256, nelem, c->inp.p, c->U.p, c->T.p, c->VEL_X.p, c->VEL_Y.p, c->W_X.p,
-           c->W_Y.p, c->GAMM.p, c->dNx.p, c->dNy.p, FR, &c->sc->red[15], RHOINF, TINF, c->SHOC.p, c->TS1.p, c->TS2.p,
+    LAUNCH(K_ESTAB, k::estab<3>, grid_for(nelem, 256), 256, nelem, c->inp.p, c->U.p, c->T.col, c->VEL_X.col, c->VEL_Y.col, c->W_X.p,
+           c->W_Y.p, c->GAMM.col, c->dNx.p, c->dNy.p, FR, &c->sc->red[15], RHOINF, TINF, c->SHOC.p, c->TS1.p, c->TS2.p,
            c->TS3.p);
     TRY(down_elem(c, c->SHOC.p, shoc));
     TRY(down_elem(c, c->TS1.p, ts1));
@@ -2297,10 +2344,10 @@ extern "C" int cfdb_rk(cfdb_ctx* c, double DTMIN, int32_t NRK, int32_t BANDERA, 
     if (NRK != 4) return fail("cfdb_rk: NRK must be 4 (ns2DComp.ALE.f90:111)");
     const size_t P_ = npoin;
     TRY(up_plain(c, c->U.p, U, 4 * P_));
-    TRY(up_plain(c, c->GAMM.p, GAMM, P_));
-    TRY(up_plain(c, c->T.p, T, P_));
-    TRY(up_plain(c, c->VEL_X.p, VEL_X, P_));
-    TRY(up_plain(c, c->VEL_Y.p, VEL_Y, P_));
+    TRY(up_node(c, c->GAMM, GAMM, P_));
+    TRY(up_node(c, c->T, T, P_));
+    TRY(up_node(c, c->VEL_X, VEL_X, P_));
+    TRY(up_node(c, c->VEL_Y, VEL_Y, P_));
     TRY(up_plain(c, c->W_X.p, W_X, P_));
     TRY(up_plain(c, c->W_Y.p, W_Y, P_));
     TRY(up_plain(c, c->RHS1.p, RHS1, 4 * P_));
@@ -2326,9 +2373,8 @@ extern "C" int cfdb_rk(cfdb_ctx* c, double DTMIN, int32_t NRK, int32_t BANDERA, 
     TRY(down_plain(c, c->RHS1.p, RHS1, 4 * P_));
     TRY(down_plain(c, c->RHS2.p, RHS2, 4 * P_));
     TRY(down_plain(c, c->RHS3.p, RHS3, 4 * P_));
-    struct { double* h; const double* d; } outs[] = {{T, c->T.p}, {P, c->P.p}, {RHO, c->RHO.p}, {E, c->E.p}, {RMACH, c->RMACH.p},
-                                                     {VEL_X, c->VEL_X.p}, {VEL_Y, c->VEL_Y.p}};
-    for (auto& o : outs) TRY(down_plain(c, o.d, o.h, P_));
+    struct { double* h; NodeField f; } outs[] = {{T, c->T}, {P, c->P}, {RHO, c->RHO}, {E, c->E}, {RMACH, c->RMACH}, {VEL_X, c->VEL_X}, {VEL_Y, c->VEL_Y}};
+    for (auto& o : outs) TRY(down_node(c, o.f, o.h, P_));
     CK(cudaStreamSynchronize(c->st));
     TRY(down_elem(c, c->SHOC.p, SHOC));
     TRY(down_elem(c, c->TS1.p, T_SUGN1));
@@ -2348,7 +2394,7 @@ extern "C" int cfdb_mesh_move(cfdb_ctx* c, double dtmin, double time, double* X,
     TRY(up_plain(c, c->Y.p, Y, P_));
     TRY(up_plain(c, c->X1.p, X1, P_));
     TRY(up_plain(c, c->Y1.p, Y1, P_));
-    TRY(up_plain(c, c->P.p, P, P_));
+    TRY(up_node(c, c->P, P, P_));
     TRY(up_plain(c, c->xpos.p, xpos, P_));
     TRY(up_plain(c, c->ypos.p, ypos, P_));
     if (!c->ale) { c->ale = true; TRY(zero(c, c->FC, 12 * (size_t)c->nelem)); }

@@ -3,7 +3,11 @@
 // calcRHS.  Data layout in HBM:
 //   nodal conserved vectors U,U1,RHS : node-interleaved (4 doubles = one 32-byte sector per
 //                                      node, so a connectivity gather costs one sector);
-//   nodal scalars                    : plain arrays;
+//   nodal scalars of the flow state  : two 32-byte records per node, NR1 = {T, GAMM, VEL_X, VEL_Y} (everything estab, deltat
+//                                      and the element gather read besides U) and NR2 = {RHO, E, P, RMACH} (written by the
+//                                      nodal update, read by the force integrals); a kernel sees one column of a record
+//                                      array as a CF / WF view (stride 4), the hot kernels move whole records;
+//   other nodal scalars (M, W, X, Y) : plain arrays;
 //   element arrays (3,E)             : structure-of-arrays [3][E] so a warp streams them coalesced;
 //   inpoel                           : [3][E] int32, 0-based;
 //   EC / FC                          : staged per-element contributions [E][3][4] (one sector
@@ -35,6 +39,27 @@ struct Scal {
     int ITER, BANDERA, bicg_k, bicg_state, bicg_xpend, pad_;
 };
 
+// One column of a nodal record array [npoin][4]: field[n] is record n's entry.  Built from the column's address
+// (record base + column index); indexing syntax is that of a plain array so the arithmetic of a kernel reads the same.
+constexpr int NREC = 4;
+struct Col { double* q = nullptr; };   // host-side handle: converts to a view and to nothing else
+struct CF {
+    const double* p;
+    __host__ __device__ CF() : p(nullptr) {}
+    __host__ __device__ CF(Col c) : p(c.q) {}
+    __host__ __device__ explicit CF(const double* q) : p(q) {}
+    __device__ __forceinline__ double operator[](size_t n) const { return p[NREC * n]; }
+};
+struct WF {
+    double* p;
+    __host__ __device__ WF() : p(nullptr) {}
+    __host__ __device__ WF(Col c) : p(c.q) {}
+    __host__ __device__ explicit WF(double* q) : p(q) {}
+    __device__ __forceinline__ double& operator[](size_t n) const { return p[NREC * n]; }
+};
+struct Rec1 { double t, gam, vx, vy; };
+enum { NR1_T = 0, NR1_GAMM = 1, NR1_VX = 2, NR1_VY = 3, NR2_RHO = 0, NR2_E = 1, NR2_P = 2, NR2_RMACH = 3 };
+
 struct Gas {
     double Cv, lambda_ref, mu_ref, gamma0, T_inf, cte;
 };
@@ -43,6 +68,12 @@ __device__ __forceinline__ void ld4(const double* __restrict__ p, double v[4]) {
     const double2* q = reinterpret_cast<const double2*>(p);
     double2 a = __ldg(q), b = __ldg(q + 1);
     v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+// record n of NR1 through its column 0 (T): one 32-byte sector, two 16-byte loads.  Only for kernels that do not write NR1.
+__device__ __forceinline__ Rec1 ld_rec1(CF T, size_t n) {
+    double v[4];
+    ld4(T.p + NREC * n, v);
+    return Rec1{v[NR1_T], v[NR1_GAMM], v[NR1_VX], v[NR1_VY]};
 }
 __device__ __forceinline__ void st4(double* p, const double v[4]) {
     double2* q = reinterpret_cast<double2*>(p);
@@ -154,16 +185,17 @@ __global__ void normales(int nwn, const int* __restrict__ wn_node, const int* __
 // Gathers first, MOVING as in estab; the kernel runs the branch-free forms (NB) and falls back per element like estab.
 template <bool MOVING, bool NB>
 __device__ __forceinline__ double deltat_elem(int e, int nelem, const int* __restrict__ inp, const double* __restrict__ area,
-                                              const double* __restrict__ T, const double* __restrict__ VX,
-                                              const double* __restrict__ VY, const double* __restrict__ WX,
+                                              CF T, CF VX,
+                                              CF VY, const double* __restrict__ WX,
                                               const double* __restrict__ WY, double FSAFE, double T_inf, unsigned& bad) {
     int n[3] = {inp[e], inp[nelem + e], inp[2 * (size_t)nelem + e]};
-    const double tsum = T[n[0]] + T[n[1]] + T[n[2]];
+    const Rec1 q[3] = {ld_rec1(T, n[0]), ld_rec1(T, n[1]), ld_rec1(T, n[2])};   // T, VEL_X, VEL_Y of a node: one record
+    const double tsum = q[0].t + q[1].t + q[2].t;
     double vu[3], vv[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        vu[i] = VX[n[i]];
-        vv[i] = VY[n[i]];
+        vu[i] = q[i].vx;
+        vv[i] = q[i].vy;
         if (MOVING) {
             vu[i] = vu[i] - WX[n[i]];
             vv[i] = vv[i] - WY[n[i]];
@@ -204,16 +236,16 @@ __device__ __forceinline__ double deltat_elem(int e, int nelem, const int* __res
 }
 template <bool MOVING>
 __device__ __noinline__ double deltat_plain(int e, int nelem, const int* __restrict__ inp, const double* __restrict__ area,
-                                            const double* __restrict__ T, const double* __restrict__ VX,
-                                            const double* __restrict__ VY, const double* __restrict__ WX,
+                                            CF T, CF VX,
+                                            CF VY, const double* __restrict__ WX,
                                             const double* __restrict__ WY, double FSAFE, double T_inf) {
     unsigned bad = 0;
     return deltat_elem<MOVING, false>(e, nelem, inp, area, T, VX, VY, WX, WY, FSAFE, T_inf, bad);
 }
 template <bool WRITE_DT, bool MOVING = true>
 __global__ void __launch_bounds__(256) deltat(int nelem, const int* __restrict__ inp, const double* __restrict__ area,
-                                               const double* __restrict__ T, const double* __restrict__ VX,
-                                               const double* __restrict__ VY, const double* __restrict__ WX,
+                                               CF T, CF VX,
+                                               CF VY, const double* __restrict__ WX,
                                                const double* __restrict__ WY, double FSAFE, double T_inf,
                                                double* __restrict__ DT, Scal* sc) {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -275,6 +307,19 @@ __global__ void fill_const(long n, double* __restrict__ a, double v) {
     long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (i < n) a[i] = v;
 }
+// columns of a nodal record array <-> plain arrays
+__global__ void fill_col(long n, WF a, double v) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i < n) a[i] = v;
+}
+__global__ void col_scatter(long n, const double* __restrict__ plain, WF col) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i < n) col[i] = plain[i];
+}
+__global__ void col_gather(long n, CF col, double* __restrict__ plain) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i < n) plain[i] = col[i];
+}
 
 // ---------------------------------------------------------------------------------------------
 // ESTAB (subrutinas.f90:349-443) : one thread per element
@@ -287,19 +332,20 @@ __global__ void fill_const(long n, double* __restrict__ a, double v) {
 // plain form (estab_plain, not inlined) when an operand left their fast path.  CFDB_BATCH_DIV=0: plain form only.
 template <bool MOVING>
 __device__ __forceinline__ void estab_one(int e, int nelem, const int* __restrict__ inp, const double* __restrict__ U,
-                                              const double* __restrict__ T, const double* __restrict__ VXa,
-                                              const double* __restrict__ VYa, const double* __restrict__ WXa,
-                                              const double* __restrict__ WYa, const double* __restrict__ GAMM,
+                                              CF T, CF VXa,
+                                              CF VYa, const double* __restrict__ WXa,
+                                              const double* __restrict__ WYa, CF GAMM,
                                               const double* __restrict__ dNx, const double* __restrict__ dNy,
                                               double FR, const double* __restrict__ dtmin_p, double RHOINF,
                                               double TINF, double* __restrict__ SHOC, double* __restrict__ TS1,
                                               double* __restrict__ TS2, double* __restrict__ TS3) {
     int N1 = inp[e], N2 = inp[nelem + e], N3 = inp[2 * (size_t)nelem + e];
     const double r1 = U[4 * (size_t)N1], r2 = U[4 * (size_t)N2], r3 = U[4 * (size_t)N3];
-    const double t1 = T[N1], t2 = T[N2], t3 = T[N3];
-    const double gsum = GAMM[N1] + GAMM[N2] + GAMM[N3];
-    const double vxsum = VXa[N1] + VXa[N2] + VXa[N3];
-    const double vysum = VYa[N1] + VYa[N2] + VYa[N3];
+    const Rec1 k1 = ld_rec1(T, N1), k2 = ld_rec1(T, N2), k3 = ld_rec1(T, N3);   // T, GAMM, VEL_X, VEL_Y of a node: one record
+    const double t1 = k1.t, t2 = k2.t, t3 = k3.t;
+    const double gsum = k1.gam + k2.gam + k3.gam;
+    const double vxsum = k1.vx + k2.vx + k3.vx;
+    const double vysum = k1.vy + k2.vy + k3.vy;
     double wxsum = 0.0, wysum = 0.0;
     if (MOVING) {
         wxsum = WXa[N1] + WXa[N2] + WXa[N3];
@@ -376,9 +422,9 @@ __device__ __forceinline__ void estab_one(int e, int nelem, const int* __restric
 
 template <bool MOVING>
 __device__ __noinline__ void estab_plain(int e, int nelem, const int* __restrict__ inp, const double* __restrict__ U,
-                                              const double* __restrict__ T, const double* __restrict__ VXa,
-                                              const double* __restrict__ VYa, const double* __restrict__ WXa,
-                                              const double* __restrict__ WYa, const double* __restrict__ GAMM,
+                                              CF T, CF VXa,
+                                              CF VYa, const double* __restrict__ WXa,
+                                              const double* __restrict__ WYa, CF GAMM,
                                               const double* __restrict__ dNx, const double* __restrict__ dNy,
                                               double FR, const double* __restrict__ dtmin_p, double RHOINF,
                                               double TINF, double* __restrict__ SHOC, double* __restrict__ TS1,
@@ -394,9 +440,9 @@ __device__ __forceinline__ bool is_pinf(double x) {
 // returns the fast-path flag; stores only when it is 0
 template <bool MOVING>
 __device__ __forceinline__ unsigned estab_fast(int e, int nelem, const int* __restrict__ inp, const double* __restrict__ U,
-                                              const double* __restrict__ T, const double* __restrict__ VXa,
-                                              const double* __restrict__ VYa, const double* __restrict__ WXa,
-                                              const double* __restrict__ WYa, const double* __restrict__ GAMM,
+                                              CF T, CF VXa,
+                                              CF VYa, const double* __restrict__ WXa,
+                                              const double* __restrict__ WYa, CF GAMM,
                                               const double* __restrict__ dNx, const double* __restrict__ dNy,
                                               double FR, const double* __restrict__ dtmin_p, double RHOINF,
                                               double TINF, double* __restrict__ SHOC, double* __restrict__ TS1,
@@ -404,10 +450,11 @@ __device__ __forceinline__ unsigned estab_fast(int e, int nelem, const int* __re
     unsigned bad = 0;
     int N1 = inp[e], N2 = inp[nelem + e], N3 = inp[2 * (size_t)nelem + e];
     const double r1 = U[4 * (size_t)N1], r2 = U[4 * (size_t)N2], r3 = U[4 * (size_t)N3];
-    const double t1 = T[N1], t2 = T[N2], t3 = T[N3];
-    const double gsum = GAMM[N1] + GAMM[N2] + GAMM[N3];
-    const double vxsum = VXa[N1] + VXa[N2] + VXa[N3];
-    const double vysum = VYa[N1] + VYa[N2] + VYa[N3];
+    const Rec1 k1 = ld_rec1(T, N1), k2 = ld_rec1(T, N2), k3 = ld_rec1(T, N3);   // T, GAMM, VEL_X, VEL_Y of a node: one record
+    const double t1 = k1.t, t2 = k2.t, t3 = k3.t;
+    const double gsum = k1.gam + k2.gam + k3.gam;
+    const double vxsum = k1.vx + k2.vx + k3.vx;
+    const double vysum = k1.vy + k2.vy + k3.vy;
     double wxsum = 0.0, wysum = 0.0;
     if (MOVING) {
         wxsum = WXa[N1] + WXa[N2] + WXa[N3];
@@ -499,9 +546,9 @@ __device__ __forceinline__ unsigned estab_fast(int e, int nelem, const int* __re
 }
 template <int MINB, bool MOVING = true>
 __global__ void __launch_bounds__(256, MINB) estab(int nelem, const int* __restrict__ inp, const double* __restrict__ U,
-                                              const double* __restrict__ T, const double* __restrict__ VXa,
-                                              const double* __restrict__ VYa, const double* __restrict__ WXa,
-                                              const double* __restrict__ WYa, const double* __restrict__ GAMM,
+                                              CF T, CF VXa,
+                                              CF VYa, const double* __restrict__ WXa,
+                                              const double* __restrict__ WYa, CF GAMM,
                                               const double* __restrict__ dNx, const double* __restrict__ dNy,
                                               double FR, const double* __restrict__ dtmin_p, double RHOINF,
                                               double TINF, double* __restrict__ SHOC, double* __restrict__ TS1,
@@ -699,7 +746,7 @@ __device__ __forceinline__ void calcrhs_body(const Gas& g, const double (&Un)[3]
 // flow (1.96 -> 1.67 ms per launch) and the plain form for Euler flow (1.10 against 1.14); CFDB_CALCRHS_NB overrides.
 #define CFDB_CALC_PARAMS                                                                                             \
     int nelem, const int* __restrict__ inp, const double* __restrict__ U, const double* __restrict__ TH,            \
-        const double* __restrict__ T, const double* __restrict__ WXa, const double* __restrict__ WYa,               \
+        CF T, const double* __restrict__ WXa, const double* __restrict__ WYa,               \
         const double* __restrict__ dNx, const double* __restrict__ dNy, const double* __restrict__ area,            \
         const double* __restrict__ shoc, const double* __restrict__ dtl_arr, const double* __restrict__ dtl_sc,     \
         const double* __restrict__ ts1, const double* __restrict__ ts2, const double* __restrict__ ts3, const Gas& g, \
@@ -778,7 +825,7 @@ __device__ __noinline__ void calcrhs_one_plain(int e, CFDB_CALC_PARAMS) {
 
 template <bool VISC, bool THETA, bool ALE, int MINB, int BS = 128, bool NB = false>
 __global__ void __launch_bounds__(BS, MINB) calcrhs_elem(int e0, int e1, int nelem, const int* __restrict__ inp, const double* __restrict__ U,
-                                                     const double* __restrict__ TH, const double* __restrict__ T,
+                                                     const double* __restrict__ TH, CF T,
                                                      const double* __restrict__ WXa, const double* __restrict__ WYa,
                                                      const double* __restrict__ dNx, const double* __restrict__ dNy,
                                                      const double* __restrict__ area, const double* __restrict__ shoc,
@@ -798,7 +845,7 @@ __global__ void __launch_bounds__(BS, MINB) calcrhs_elem(int e0, int e1, int nel
 // CUARTO_ORDEN (subrutinas.f90:243-327), "next" row N1: element part -> staging buffer, node part
 // U_n = -(ordered sum)/M.  Same ordered-gather scheme as calcRHS.
 __global__ void __launch_bounds__(128) cuarto_elem(int nelem, const int* __restrict__ inp, const double* __restrict__ U,
-                                                    const double* __restrict__ GAMM, const double* __restrict__ dNx,
+                                                    CF GAMM, const double* __restrict__ dNx,
                                                     const double* __restrict__ dNy, const double* __restrict__ area,
                                                     double* __restrict__ EC) {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -890,9 +937,9 @@ struct BcTab {
 // boundary conditions (fixvel -> normalvel -> FIX) and the conservative state, from the primitives of one node
 __device__ __forceinline__ void node_bc_store(int n, double rho, double vx, double vy, double en, double p, double t, double mach,
                                               double gam, unsigned fl, const double* __restrict__ WXa, const double* __restrict__ WYa,
-                                              const BcTab& bc, double FR, double* __restrict__ U1, double* __restrict__ RHO,
-                                              double* __restrict__ VELX, double* __restrict__ VELY, double* __restrict__ Ea,
-                                              double* __restrict__ Pa, double* __restrict__ Ta, double* __restrict__ RMACH) {
+                                              const BcTab& bc, double FR, double* __restrict__ U1, WF RHO,
+                                              WF VELX, WF VELY, WF Ea,
+                                              WF Pa, WF Ta, WF RMACH) {
     if (fl) {
         int lo = 0, hi = bc.nb - 1;
         while (lo < hi) {
@@ -920,14 +967,19 @@ __device__ __forceinline__ void node_bc_store(int n, double rho, double vx, doub
     }
     double o[4] = {rho, vx * rho, vy * rho, en * rho};
     st4(U1 + 4 * (size_t)n, o);
-    RHO[n] = rho; VELX[n] = vx; VELY[n] = vy; Ea[n] = en; Pa[n] = p; Ta[n] = t; RMACH[n] = mach;
+    // the two nodal records whole (Ta and RHO are column 0 of NR1 and NR2; GAMM is rewritten with the value it holds)
+    static_assert(NR1_T == 0 && NR1_GAMM == 1 && NR1_VX == 2 && NR1_VY == 3 && NR2_RHO == 0 && NR2_E == 1 && NR2_P == 2 && NR2_RMACH == 3,
+                  "record layout");
+    const double r1[4] = {t, gam, vx, vy}, r2[4] = {rho, en, p, mach};
+    st4(Ta.p + NREC * (size_t)n, r1);
+    st4(RHO.p + NREC * (size_t)n, r2);
 }
 // primitives (subrutinas.f90:708-717), boundary conditions, conservative state from the updated conserved vector u1
 __device__ __forceinline__ void node_from_u1(int n, const double (&u1)[4], double gam, unsigned fl, const double* __restrict__ WXa,
                                              const double* __restrict__ WYa, const BcTab& bc, double FR, double* __restrict__ U1,
-                                             double* __restrict__ RHO, double* __restrict__ VELX, double* __restrict__ VELY,
-                                             double* __restrict__ Ea, double* __restrict__ Pa, double* __restrict__ Ta,
-                                             double* __restrict__ RMACH) {
+                                             WF RHO, WF VELX, WF VELY,
+                                             WF Ea, WF Pa, WF Ta,
+                                             WF RMACH) {
     double rho = u1[0];
     double vx = u1[1] / rho, vy = u1[2] / rho, en = u1[3] / rho;
     double VEL2 = (vx * vx + vy * vy);
@@ -939,9 +991,9 @@ __device__ __forceinline__ void node_from_u1(int n, const double (&u1)[4], doubl
 __device__ __forceinline__ void node_finish_v(int n, const double (&acc)[4], const double (&u)[4], double m, double gam,
                                               unsigned fl, const double* __restrict__ WXa, const double* __restrict__ WYa,
                                               const BcTab& bc, double rk_fact, double FR, double* __restrict__ U1,
-                                              double* __restrict__ RHO, double* __restrict__ VELX, double* __restrict__ VELY,
-                                              double* __restrict__ Ea, double* __restrict__ Pa, double* __restrict__ Ta,
-                                              double* __restrict__ RMACH) {
+                                              WF RHO, WF VELX, WF VELY,
+                                              WF Ea, WF Pa, WF Ta,
+                                              WF RMACH) {
     double f = rk_fact / m;
     double u1[4];
 #pragma unroll
@@ -971,9 +1023,9 @@ __device__ __forceinline__ unsigned node_prims_nb(const double (&acc)[4], const 
 __device__ __forceinline__ unsigned node_finish_nb(int n, const double (&acc)[4], const double (&u)[4], double m, double gam,
                                                    unsigned fl, const double* __restrict__ WXa, const double* __restrict__ WYa,
                                                    const BcTab& bc, double rk_fact, double FR, double* __restrict__ U1,
-                                                   double* __restrict__ RHO, double* __restrict__ VELX, double* __restrict__ VELY,
-                                                   double* __restrict__ Ea, double* __restrict__ Pa, double* __restrict__ Ta,
-                                                   double* __restrict__ RMACH) {
+                                                   WF RHO, WF VELX, WF VELY,
+                                                   WF Ea, WF Pa, WF Ta,
+                                                   WF RMACH) {
     NodePrims q;
     if (node_prims_nb(acc, u, m, gam, rk_fact, FR, q)) return 1;
     node_bc_store(n, q.rho, q.vx, q.vy, q.en, q.p, q.t, q.mach, gam, fl, WXa, WYa, bc, FR, U1, RHO, VELX, VELY, Ea, Pa, Ta, RMACH);
@@ -982,18 +1034,18 @@ __device__ __forceinline__ unsigned node_finish_nb(int n, const double (&acc)[4]
 __device__ __noinline__ void node_finish_plain(int n, const double (&acc)[4], const double (&u)[4], double m, double gam,
                                                unsigned fl, const double* __restrict__ WXa, const double* __restrict__ WYa,
                                                const BcTab& bc, double rk_fact, double FR, double* __restrict__ U1,
-                                               double* __restrict__ RHO, double* __restrict__ VELX, double* __restrict__ VELY,
-                                               double* __restrict__ Ea, double* __restrict__ Pa, double* __restrict__ Ta,
-                                               double* __restrict__ RMACH) {
+                                               WF RHO, WF VELX, WF VELY,
+                                               WF Ea, WF Pa, WF Ta,
+                                               WF RMACH) {
     node_finish_v(n, acc, u, m, gam, fl, WXa, WYa, bc, rk_fact, FR, U1, RHO, VELX, VELY, Ea, Pa, Ta, RMACH);
 }
 __device__ __forceinline__ void node_finish(int n, const double (&acc)[4], const double* __restrict__ U,
-                                            const double* __restrict__ M, const double* __restrict__ GAMM,
+                                            const double* __restrict__ M, CF GAMM,
                                             const double* __restrict__ WXa, const double* __restrict__ WYa,
                                             const unsigned char* __restrict__ bcflag, const BcTab& bc, double rk_fact,
-                                            double FR, double* __restrict__ U1, double* __restrict__ RHO,
-                                            double* __restrict__ VELX, double* __restrict__ VELY, double* __restrict__ Ea,
-                                            double* __restrict__ Pa, double* __restrict__ Ta, double* __restrict__ RMACH) {
+                                            double FR, double* __restrict__ U1, WF RHO,
+                                            WF VELX, WF VELY, WF Ea,
+                                            WF Pa, WF Ta, WF RMACH) {
     double u[4];
     ld4(U + 4 * (size_t)n, u);
     node_finish_v(n, acc, u, M[n], GAMM[n], bcflag[n], WXa, WYa, bc, rk_fact, FR, U1, RHO, VELX, VELY, Ea, Pa, Ta, RMACH);
@@ -1013,13 +1065,13 @@ template <bool ALE, bool UPDATE>
 __global__ void __launch_bounds__(CFDB_NODE_BS, CFDB_NODE_MINB) node_update(int n0, int n1, const int* __restrict__ nlist, const int* __restrict__ esup2, const int* __restrict__ eslot,
                                                     const double* __restrict__ EC, const double* __restrict__ FC,
                                                     const double* __restrict__ U, const double* __restrict__ M,
-                                                    const double* __restrict__ GAMM, const double* __restrict__ WXa,
+                                                    CF GAMM, const double* __restrict__ WXa,
                                                     const double* __restrict__ WYa, const unsigned char* __restrict__ bcflag,
                                                     BcTab bc, double rk_fact, double FR, double* __restrict__ U1,
-                                                    double* __restrict__ RHS, double* __restrict__ RHO,
-                                                    double* __restrict__ VELX, double* __restrict__ VELY,
-                                                    double* __restrict__ Ea, double* __restrict__ Pa,
-                                                    double* __restrict__ Ta, double* __restrict__ RMACH) {
+                                                    double* __restrict__ RHS, WF RHO,
+                                                    WF VELX, WF VELY,
+                                                    WF Ea, WF Pa,
+                                                    WF Ta, WF RMACH) {
     int n = n0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= n1) return;
     if (nlist) n = nlist[n];  // [n0,n1) indexes a node list (the tile-boundary nodes of the fused stage)
@@ -1050,13 +1102,13 @@ template <bool ALE>
 __global__ void __launch_bounds__(128, 8) node_update_adamsb(int npoin, const int* __restrict__ esup2, const int* __restrict__ eslot,
                                                               const double* __restrict__ EC, const double* __restrict__ FC,
                                                               const double* __restrict__ U, const double* __restrict__ M,
-                                                              const double* __restrict__ GAMM, const double* __restrict__ WXa,
+                                                              CF GAMM, const double* __restrict__ WXa,
                                                               const double* __restrict__ WYa, const unsigned char* __restrict__ bcflag,
                                                               BcTab bc, double FR, double* __restrict__ U1, double* __restrict__ RHS,
                                                               double* __restrict__ R1, double* __restrict__ R2, double* __restrict__ R3,
-                                                              double* __restrict__ RHO, double* __restrict__ VELX, double* __restrict__ VELY,
-                                                              double* __restrict__ Ea, double* __restrict__ Pa, double* __restrict__ Ta,
-                                                              double* __restrict__ RMACH) {
+                                                              WF RHO, WF VELX, WF VELY,
+                                                              WF Ea, WF Pa, WF Ta,
+                                                              WF RMACH) {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= npoin) return;
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
@@ -1426,7 +1478,7 @@ __global__ void __launch_bounds__(256) move_apply(int npoin, const double* __res
 // FORCES (:171-192): sequential sums over the (few thousand) body edges of each set; one thread per
 // set keeps the reference order exactly.
 __global__ void forces(int nset, int n_owned, const int* __restrict__ sptr, const int* __restrict__ n1a, const int* __restrict__ n2a,
-                       const double* __restrict__ X, const double* __restrict__ Y, const double* __restrict__ P,
+                       const double* __restrict__ X, const double* __restrict__ Y, CF P,
                        const double* __restrict__ xref, const double* __restrict__ yref, Scal* sc) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nset) return;
@@ -1450,8 +1502,8 @@ __global__ void forces(int nset, int n_owned, const int* __restrict__ sptr, cons
 // summed per set in list order by one thread per set, like FORCES; skin[3][ne] = the three columns of SKIN.DAT.
 __global__ void force_visc(int nset, int n_owned, const int* __restrict__ sptr, const int* __restrict__ n1a, const int* __restrict__ n2a,
                            const int* __restrict__ ela, int nelem, const int* __restrict__ inp, const double* __restrict__ X,
-                           const double* __restrict__ Y, const double* __restrict__ P, const double* __restrict__ T,
-                           const double* __restrict__ VX, const double* __restrict__ VY, const double* __restrict__ dNx,
+                           const double* __restrict__ Y, CF P, CF T,
+                           CF VX, CF VY, const double* __restrict__ dNx,
                            const double* __restrict__ dNy, double U_inf, double V_inf, double RHO_inf, double T_inf,
                            double* __restrict__ fv, double* __restrict__ skin, int ne) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1528,9 +1580,9 @@ __global__ void __launch_bounds__(256) gcl(int npoin, int nelem, const int* __re
 // nodal array the reference's RK leaves behind is valid at ghost nodes too (FORCES / FORCE_VISC read P at both ends of a body
 // edge and at the three nodes of the element behind it, either of which can be a ghost); or one double
 constexpr int HALO_W = 10;
-__global__ void halo_pack_state(int m, const int* __restrict__ idx, const double* __restrict__ U1, const double* __restrict__ T,
-                                const double* __restrict__ VX, const double* __restrict__ VY, const double* __restrict__ Ea,
-                                const double* __restrict__ Pa, const double* __restrict__ RMACH, double* __restrict__ buf) {
+__global__ void halo_pack_state(int m, const int* __restrict__ idx, const double* __restrict__ U1, CF T,
+                                CF VX, CF VY, CF Ea,
+                                CF Pa, CF RMACH, double* __restrict__ buf) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     int n = idx[i];
@@ -1541,9 +1593,9 @@ __global__ void halo_pack_state(int m, const int* __restrict__ idx, const double
     b[7] = Ea[n]; b[8] = Pa[n]; b[9] = RMACH[n];
 }
 __global__ void halo_unpack_state(int m, const int* __restrict__ idx, const double* __restrict__ buf, double* __restrict__ U1,
-                                  double* __restrict__ T, double* __restrict__ VX, double* __restrict__ VY,
-                                  double* __restrict__ RHO, double* __restrict__ Ea, double* __restrict__ Pa,
-                                  double* __restrict__ RMACH) {
+                                  WF T, WF VX, WF VY,
+                                  WF RHO, WF Ea, WF Pa,
+                                  WF RMACH) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     int n = idx[i];
@@ -1659,7 +1711,7 @@ __global__ void soa_to_aos3(long nelem, const double* __restrict__ in, double* _
 // algorithm amplifies one-ulp differences.  Never used unless asked for.
 template <bool VISC, bool ALE>
 __global__ void __launch_bounds__(128, 4) calcrhs_scatter(int nelem, const int* __restrict__ inp, const double* __restrict__ U,
-                                                           const double* __restrict__ T, const double* __restrict__ WXa,
+                                                           CF T, const double* __restrict__ WXa,
                                                            const double* __restrict__ WYa, const double* __restrict__ dNx,
                                                            const double* __restrict__ dNy, const double* __restrict__ area,
                                                            const double* __restrict__ shoc, const double* __restrict__ dtl_arr,
@@ -1710,7 +1762,7 @@ __global__ void __launch_bounds__(128, 4) calcrhs_scatter(int nelem, const int* 
 // FMA contraction).  elist = internal element positions of this colour.
 template <bool VISC, bool ALE>
 __global__ void __launch_bounds__(128, 4) calcrhs_colored(int ncol, const int* __restrict__ elist, int nelem, const int* __restrict__ inp,
-                                                           const double* __restrict__ U, const double* __restrict__ T,
+                                                           const double* __restrict__ U, CF T,
                                                            const double* __restrict__ WXa, const double* __restrict__ WYa,
                                                            const double* __restrict__ dNx, const double* __restrict__ dNy,
                                                            const double* __restrict__ area, const double* __restrict__ shoc,
@@ -1769,12 +1821,12 @@ __global__ void __launch_bounds__(128, 4) calcrhs_colored(int ncol, const int* _
     }
 }
 __global__ void __launch_bounds__(256) node_update_rhs(int npoin, const double* __restrict__ RHS, const double* __restrict__ U,
-                                                        const double* __restrict__ M, const double* __restrict__ GAMM,
+                                                        const double* __restrict__ M, CF GAMM,
                                                         const double* __restrict__ WXa, const double* __restrict__ WYa,
                                                         const unsigned char* __restrict__ bcflag, BcTab bc, double rk_fact,
-                                                        double FR, double* __restrict__ U1, double* __restrict__ RHO,
-                                                        double* __restrict__ VELX, double* __restrict__ VELY, double* __restrict__ Ea,
-                                                        double* __restrict__ Pa, double* __restrict__ Ta, double* __restrict__ RMACH) {
+                                                        double FR, double* __restrict__ U1, WF RHO,
+                                                        WF VELX, WF VELY, WF Ea,
+                                                        WF Pa, WF Ta, WF RMACH) {
     int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= npoin) return;
     double acc[4];

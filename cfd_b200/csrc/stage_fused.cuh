@@ -103,12 +103,13 @@ struct StageArgs {
     const double* dtl_sc;
     const double* Usrc;                            // state calcRHS is evaluated at (U; U1 for true_rk stages 2..4)
     const double* U;                               // state the update starts from
-    const double* T;
-    const double *M, *GAMM, *WXa, *WYa;
+    CF T, GAMM;                                    // columns of the nodal record array NR1 (one 32-byte sector per node)
+    const double *M, *WXa, *WYa;
     BcTab bc;
     double rk_fact, FR;
     Gas g;
-    double *EC, *U1, *RHS, *RHO, *VELX, *VELY, *Ea, *Pa, *Ta, *RMACH;
+    double *EC, *U1, *RHS;
+    WF RHO, VELX, VELY, Ea, Pa, Ta, RMACH;
     int* cnt;                                      // per node: contributions-arrived counter of the tile-boundary nodes (null: they
                                                    // are left to node_update over the list bnodes, launched after this kernel)
     const unsigned char* bcflag;
@@ -278,13 +279,13 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1) stage_fused(const __grid_co
                     const double* u = A.Usrc + 4 * (size_t)n;
                     ptx::cp_async16(abu + G.a_u + 32 * j, u);
                     ptx::cp_async16(abu + G.a_u + 32 * j + 16, u + 2);
-                    if (VISC) ptx::cp_async8(abu + G.a_t + 8 * j, A.T + n);
+                    if (VISC) ptx::cp_async8(abu + G.a_t + 8 * j, A.T.p + NREC * (size_t)n);
                 }
 #pragma unroll 1
                 for (int j = lane; j < nint; j += 32) {
                     const int n = tnode[j];
                     ptx::cp_async8(abu + G.a_m + 8 * j, A.M + n);
-                    ptx::cp_async8(abu + G.a_g + 8 * j, A.GAMM + n);
+                    ptx::cp_async8(abu + G.a_g + 8 * j, A.GAMM.p + NREC * (size_t)n);
                 }
                 ptx::cp_async_arrive_noinc(afull0 + 8 * sa);
                 // static block of the next tile
