@@ -182,7 +182,7 @@ struct cfdb_ctx {
     k::TileGeom tgeom{};
     size_t stage_smem = 0;
     vector<int32_t> h_i2e, h_e2i;
-    DBuf<int> i2e, e2i, bnodes, orphans, bcnt;
+    DBuf<int> i2e, e2i, bnodes, bn_ptr, orphans;
     int norphans = 0;
     DBuf<unsigned char> TB;
     DBuf<double> geo;
@@ -504,6 +504,7 @@ static int build_stage_tiles(cfdb_ctx* c, const int32_t* inpoel, const double* X
     topo::Tiling T;
     topo::build_tiling(inpoel, c->nelem, c->npoin, X, Y, esup1, esup2, eslot, c->h_bcflag, TE, order, T);
     if (T.L.nint_max > 65535 || 12 * TE > 65535) return fail("tile too large for 16-bit slots");
+    if (T.rank_overflow) { c->tiles_ok = false; return 0; }   // a node with more than 256 elements: the two-kernel stage
     c->ntiles = T.ntiles;
     c->tile_ncw = TE / 32;
     c->tile_interior = T.interior_fraction;
@@ -511,9 +512,9 @@ static int build_stage_tiles(cfdb_ctx* c, const int32_t* inpoel, const double* X
     c->Epad = (long)T.ntiles * TE;
     TRY(upload(c, c->TB, T.blocks));
     TRY(upload(c, c->bnodes, T.bnodes));
+    TRY(upload(c, c->bn_ptr, T.bn_ptr));
     c->norphans = (int)T.orphans.size();
     TRY(upload(c, c->orphans, T.orphans));
-    TRY(zero(c, c->bcnt, P));
     TRY(zero(c, c->geo, 7 * (size_t)c->Epad));
     if (permute) {
         c->h_i2e = T.i2e;
@@ -540,7 +541,7 @@ static int build_stage_tiles(cfdb_ctx* c, const int32_t* inpoel, const double* X
     auto up128 = [](int v) { return (v + 127) & ~127; };
     G.TE = TE; G.ntn_max = L.ntn_max; G.nint_max = L.nint_max; G.nslot_max = L.nslot_max;
     G.off_lnode = L.off_lnode; G.off_tnode = L.off_tnode; G.off_nptr = L.off_nptr; G.off_slots = L.off_slots; G.off_bcf = L.off_bcf;
-    G.off_tch = L.off_tch; G.off_bptr = L.off_bptr; G.off_bidx = L.off_bidx;
+    G.off_brank = L.off_brank; G.off_bbase = L.off_bbase;
     G.tb_bytes = L.tb_bytes;
     G.nfields = c->par.ITLOCAL != 0 ? 12 : 11;
     G.a_static = 0;
@@ -727,7 +728,7 @@ extern "C" void cfdb_destroy(cfdb_ctx* c) {
     c->lpos.release();
     c->bcflag.release();
     c->color_list.release();
-    c->i2e.release(); c->e2i.release(); c->bnodes.release(); c->orphans.release(); c->bcnt.release(); c->TB.release(); c->geo.release();
+    c->i2e.release(); c->e2i.release(); c->bnodes.release(); c->orphans.release(); c->bn_ptr.release(); c->TB.release(); c->geo.release();
     if (c->stage_stats) cudaFree(c->stage_stats);
     c->isfix.release();
     c->bp2.release(); c->by2.release(); c->pos_aux2.release();
@@ -975,7 +976,6 @@ extern "C" int cfdb_init(cfdb_ctx* c) {
     CK(cudaMemcpyAsync(c->area_old.p, c->area.p, c->nelem * sizeof(double), cudaMemcpyDeviceToDevice, c->st));
     c->h_iter = 0;
     c->nestab = 1;   // ns2DComp.ALE.f90:134
-    if (c->bcnt.p) CK(cudaMemsetAsync(c->bcnt.p, 0, (size_t)c->npoin * sizeof(int), c->st));
     c->iterprint = 0;
     c->DISN[0] = c->DISN[1] = 0.0;
     c->theta_nonzero = false;
@@ -1081,7 +1081,7 @@ static int run_stage_fused(cfdb_ctx* c, const k::Gas& g, const double* dtl_arr, 
     A.shoc = c->SHOC.p; A.ts1 = c->TS1.p; A.ts2 = c->TS2.p; A.ts3 = c->TS3.p; A.dtl_arr = dtl_arr; A.dtl_sc = dtl_sc;
     A.Usrc = c->Usrc ? c->Usrc : c->U.p; A.U = c->U.p; A.T = c->T.col; A.M = c->M.p; A.GAMM = c->GAMM.col; A.WXa = c->W_X.p; A.WYa = c->W_Y.p;
     A.bc = bctab(c); A.rk_fact = rk_fact; A.FR = c->par.FR; A.g = g;
-    A.EC = c->EC.p; A.U1 = c->U1.p; A.RHS = c->RHS.p; A.RHO = c->RHO.col; A.VELX = c->VEL_X.col; A.VELY = c->VEL_Y.col; A.Ea = c->E.col;
+    A.ECB = c->EC.p; A.U1 = c->U1.p; A.RHS = c->RHS.p; A.RHO = c->RHO.col; A.VELX = c->VEL_X.col; A.VELY = c->VEL_Y.col; A.Ea = c->E.col;
     A.Pa = c->P.col; A.Ta = c->T.col; A.RMACH = c->RMACH.col;
     k::TileGeom G = c->tgeom;
     G.nfields = dtl_arr ? 12 : 11;
@@ -1089,18 +1089,9 @@ static int run_stage_fused(cfdb_ctx* c, const k::Gas& g, const double* dtl_arr, 
     void (*kern)(const k::TileGeom, const k::StageArgs) = nullptr;
     if (c->tile_ncw == 16) kern = visc ? k::stage_fused<true, 16, 3, 2> : k::stage_fused<false, 16, 3, 2>;
     else kern = visc ? k::stage_fused<true, 12, 3, 2> : k::stage_fused<false, 12, 3, 2>;
-    // tile-boundary nodes: finished inside the stage kernel by the last tile to contribute (default), or by node_update over
-    // the list bnodes after it (CFDB_BOUNDARY_PASS=1)
-    // The in-kernel completion writes T, U1, ... of a tile-boundary node while other tiles of the same launch may still
-    // gather that node's state: safe when nothing the kernel gathers is written by it -- Euler flow (T is not read) with
-    // calcRHS evaluated at U (U1 is written, U is read).  Viscous flow and true_rk keep the separate pass.
-    // Measured on B200 (16 M triangles): the in-kernel completion costs the node warps ~10 000 cycles per tile (fence + atomic
-    // round trips + L2 gather chains they cannot hide) against ~5 300 for the interior nodes alone: stage_fused 3.08 ms against
-    // 1.16 ms + 0.35 ms for the separate pass -- so the separate pass is the default and CFDB_BOUNDARY_INKERNEL=1 selects this.
-    static const bool inkernel_env = getenv("CFDB_BOUNDARY_INKERNEL") != nullptr;
-    const bool boundary_pass = !inkernel_env || visc || A.Usrc != A.U;
-    A.cnt = boundary_pass ? nullptr : c->bcnt.p;
-    A.bcflag = c->bcflag.p;
+    // tile-boundary nodes: their contributions go to the boundary records (the otherwise idle staging buffer EC), finished by
+    // boundary_update below.  (Finishing them inside the stage kernel -- last contributing tile, atomics + fences -- measured
+    // 3.08 ms against 1.16 + 0.35 ms on the 16 M-triangle mesh and was removed, profiles/r2_experiments.md.)
     A.stats = c->stage_stats;
     static std::map<const void*, size_t> attr_done;   // per kernel: the largest dynamic shared-memory size opted into so far
     if (attr_done[(const void*)kern] < c->stage_smem) {
@@ -1115,8 +1106,11 @@ static int run_stage_fused(cfdb_ctx* c, const k::Gas& g, const double* dtl_arr, 
     kern<<<grid, block, c->stage_smem, c->st>>>(G, A);
     CK(cudaGetLastError());
     TRY(prof_end(c, c->st, K_STAGE, _a, _b));
-    if (boundary_pass) TRY(run_node(c, c->st, false, true, rk_fact, 0, c->nbnodes, c->bnodes.p));
-    else if (c->norphans) TRY(run_node(c, c->st, false, true, rk_fact, 0, c->norphans, c->orphans.p));   // nodes no element touches
+    // tile-boundary nodes (and nodes no element touches: an empty run of records)
+    if (c->nbnodes)
+        LAUNCH(K_NODE, k::boundary_update, grid_for(c->nbnodes, CFDB_NODE_BS), CFDB_NODE_BS, c->nbnodes, c->bnodes.p, c->bn_ptr.p, c->EC.p, c->U.p,
+               c->M.p, c->GAMM.col, c->W_X.p, c->W_Y.p, c->bcflag.p, bctab(c), rk_fact, c->par.FR, c->U1.p, c->RHS.p, c->RHO.col, c->VEL_X.col,
+               c->VEL_Y.col, c->E.col, c->P.col, c->T.col, c->RMACH.col);
     return 0;
 }
 

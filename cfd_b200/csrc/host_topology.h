@@ -110,14 +110,15 @@ inline void build_lap_pos(const int32_t* inpoel, int npoin, const vector<int32_t
 //                              1-thread summation order); value = (4*local_vertex)*TE + position in tile, i.e. the index
 //                              of equation 0 of that contribution in the shared-memory array C[12][TE]
 //   bcf     uint8[nint_max]    bcflag of the interior nodes
-//   tch     uint8[nbd_max]     for each tile-boundary node of the tile (local index nint + jb): the number of tiles touching it
-//   bptr    uint16[nbd_max+1]  CSR over `bidx`
-//   bidx    uint32[nbidx_max]  ALL contributions of that node, tile by tile, in ascending ORIGINAL element order: index of
-//                              the 32-byte record in the global staging buffer EC (3*internal element + local vertex).  The
-//                              tile whose contributions arrive last finishes the node inside the stage kernel.
+//   brank   uint8[3][TE]       for an element vertex that is a tile-boundary node: the position of this element in the node's
+//                              element list (ascending ORIGINAL element id)
+//   bbase   uint32[nbd_max]    for each tile-boundary node of the tile (local index nint + jb): the first record of that node in
+//                              the boundary staging buffer ECB.  An element warp stores the contribution of (element, vertex)
+//                              at record bbase[lnode - nint] + brank, so the records of one node lie side by side in summation
+//                              order and the boundary pass (kernels.cuh: boundary_update) reads them as one contiguous run.
 struct TileLayout {
-    int TE = 0, ntn_max = 0, nint_max = 0, nslot_max = 0, nbd_max = 0, nbidx_max = 0;
-    int off_lnode = 0, off_tnode = 0, off_nptr = 0, off_slots = 0, off_bcf = 0, off_tch = 0, off_bptr = 0, off_bidx = 0, tb_bytes = 0;
+    int TE = 0, ntn_max = 0, nint_max = 0, nslot_max = 0, nbd_max = 0;
+    int off_lnode = 0, off_tnode = 0, off_nptr = 0, off_slots = 0, off_bcf = 0, off_brank = 0, off_bbase = 0, tb_bytes = 0;
 };
 struct Tiling {
     TileLayout L;
@@ -125,8 +126,10 @@ struct Tiling {
     vector<int32_t> i2e, e2i;      // 0-based
     vector<uint8_t> blocks;        // ntiles * L.tb_bytes
     vector<int32_t> bnodes;        // tile-boundary nodes, ascending
+    vector<int32_t> bn_ptr;        // CSR over the boundary staging buffer: contributions of bnodes[i] are records bn_ptr[i] .. bn_ptr[i+1]
     vector<int32_t> orphans;       // nodes touched by no element (never reached by the stage kernel), ascending
     double interior_fraction = 0;
+    bool rank_overflow = false;    // a tile-boundary node with more than 256 elements: the tiling cannot be used
 };
 inline uint32_t morton16(uint32_t x, uint32_t y) {
     auto spread = [](uint32_t v) {
@@ -233,20 +236,14 @@ inline void build_tiling(const int32_t* inpoel, int nelem, int npoin, const doub
     }
     T.bnodes.clear();
     T.orphans.clear();
-    vector<uint8_t> ntouch((size_t)npoin, 0);   // number of distinct tiles among the elements of a tile-boundary node
+    vector<int32_t> bpos((size_t)npoin, -1);
+    T.bn_ptr.assign(1, 0);
     for (int n = 0; n < npoin; ++n)
         if (owner[n] < 0) {
+            bpos[n] = (int32_t)T.bnodes.size();
             T.bnodes.push_back(n);
-            int k0 = esup2[n], k1 = esup2[n + 1];
-            if (k0 == k1) { T.orphans.push_back(n); continue; }
-            int seen[64], ns = 0;
-            for (int k = k0; k < k1; ++k) {
-                int tt = T.e2i[esup1[k] - 1] / TE;
-                bool f = false;
-                for (int q = 0; q < ns; ++q) f = f || seen[q] == tt;
-                if (!f && ns < 64) seen[ns++] = tt;
-            }
-            ntouch[n] = (uint8_t)ns;
+            if (esup2[n] == esup2[n + 1]) T.orphans.push_back(n);
+            T.bn_ptr.push_back(T.bn_ptr.back() + (esup2[n + 1] - esup2[n]));
         }
     T.interior_fraction = npoin ? (double)ninterior / npoin : 0.0;
     // pass 1: per-tile node lists (interior ascending, then the rest ascending) and the section sizes
@@ -255,7 +252,7 @@ inline void build_tiling(const int32_t* inpoel, int nelem, int npoin, const doub
     vector<int32_t> tn_nodes;
     tn_nodes.reserve((size_t)(0.7 * E) + 1024);
     vector<int32_t> a, b;
-    int ntn_max = 0, nint_max = 0, nslot_max = 0, nbd_max = 0, nbidx_max = 0;
+    int ntn_max = 0, nint_max = 0, nslot_max = 0, nbd_max = 0;
     for (int t = 0; t < nt; ++t) {
         size_t p0 = (size_t)t * TE, p1 = std::min(E, p0 + TE);
         a.clear(); b.clear();
@@ -278,24 +275,20 @@ inline void build_tiling(const int32_t* inpoel, int nelem, int npoin, const doub
         ntn_max = std::max(ntn_max, (int)(a.size() + b.size()));
         nint_max = std::max(nint_max, (int)a.size());
         nslot_max = std::max(nslot_max, ns);
-        int nbi = 0;
-        for (int n : b) nbi += esup2[n + 1] - esup2[n];
         nbd_max = std::max(nbd_max, (int)b.size());
-        nbidx_max = std::max(nbidx_max, nbi);
     }
     auto up16 = [](int v) { return (v + 15) & ~15; };
     TileLayout& L = T.L;
     L.TE = TE;
-    L.ntn_max = ntn_max; L.nint_max = nint_max; L.nslot_max = nslot_max; L.nbd_max = nbd_max; L.nbidx_max = nbidx_max;
+    L.ntn_max = ntn_max; L.nint_max = nint_max; L.nslot_max = nslot_max; L.nbd_max = nbd_max;
     L.off_lnode = 16;
     L.off_tnode = up16(L.off_lnode + 3 * TE * 2);
     L.off_nptr = up16(L.off_tnode + ntn_max * 4);
     L.off_slots = up16(L.off_nptr + (nint_max + 1) * 2);
     L.off_bcf = up16(L.off_slots + nslot_max * 2);
-    L.off_tch = up16(L.off_bcf + nint_max);
-    L.off_bptr = up16(L.off_tch + nbd_max);
-    L.off_bidx = up16(L.off_bptr + (nbd_max + 1) * 2);
-    L.tb_bytes = up16(L.off_bidx + nbidx_max * 4);
+    L.off_brank = up16(L.off_bcf + nint_max);
+    L.off_bbase = up16(L.off_brank + 3 * TE);
+    L.tb_bytes = up16(L.off_bbase + nbd_max * 4);
     // pass 2: fill the blocks
     T.blocks.assign((size_t)nt * L.tb_bytes, 0);
     for (int t = 0; t < nt; ++t) {
@@ -309,9 +302,8 @@ inline void build_tiling(const int32_t* inpoel, int nelem, int npoin, const doub
         size_t p0 = (size_t)t * TE, p1 = std::min(E, p0 + TE);
         const int ntn = tn_ptr[t + 1] - tn_ptr[t], nint = tn_nint[t];
         hdr[0] = (int32_t)(p1 - p0); hdr[1] = ntn; hdr[2] = nint; hdr[3] = 0;
-        uint8_t* tch = blk + L.off_tch;
-        uint16_t* bptr = reinterpret_cast<uint16_t*>(blk + L.off_bptr);
-        uint32_t* bidx = reinterpret_cast<uint32_t*>(blk + L.off_bidx);
+        uint8_t* brank = blk + L.off_brank;
+        uint32_t* bbase = reinterpret_cast<uint32_t*>(blk + L.off_bbase);
         for (int j = 0; j < ntn; ++j) {
             int n = tn_nodes[(size_t)tn_ptr[t] + j];
             tnode[j] = n;
@@ -319,7 +311,16 @@ inline void build_tiling(const int32_t* inpoel, int nelem, int npoin, const doub
         }
         for (size_t p = p0; p < p1; ++p) {
             const int32_t* el = inpoel + 3 * (size_t)T.i2e[p];
-            for (int i = 0; i < 3; ++i) lnode[(size_t)i * TE + (p - p0)] = (uint16_t)lidx[el[i] - 1];
+            for (int i = 0; i < 3; ++i) {
+                const int n = el[i] - 1;
+                lnode[(size_t)i * TE + (p - p0)] = (uint16_t)lidx[n];
+                if (bpos[n] >= 0) {   // rank of this element among the node's elements (the list is in ascending original id)
+                    int k = esup2[n];
+                    while (eslot[k] != 3 * T.i2e[p] + i) ++k;
+                    if (k - esup2[n] > 255) T.rank_overflow = true;
+                    brank[(size_t)i * TE + (p - p0)] = (uint8_t)(k - esup2[n]);
+                }
+            }
         }
         int q = 0;
         for (int j = 0; j < nint; ++j) {
@@ -332,14 +333,7 @@ inline void build_tiling(const int32_t* inpoel, int nelem, int npoin, const doub
             bcf[j] = bcflag[n];
         }
         nptr[nint] = (uint16_t)q;
-        int qb = 0;
-        for (int jb = 0; jb < ntn - nint; ++jb) {
-            int n = tnode[nint + jb];
-            tch[jb] = ntouch[n];
-            bptr[jb] = (uint16_t)qb;
-            for (int k = esup2[n]; k < esup2[n + 1]; ++k) bidx[qb++] = (uint32_t)(3 * T.e2i[esup1[k] - 1] + eslot[k] % 3);
-        }
-        bptr[ntn - nint] = (uint16_t)qb;
+        for (int jb = 0; jb < ntn - nint; ++jb) bbase[jb] = (uint32_t)T.bn_ptr[bpos[tnode[nint + jb]]];
     }
 }
 

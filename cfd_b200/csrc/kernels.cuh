@@ -1096,6 +1096,30 @@ __global__ void __launch_bounds__(CFDB_NODE_BS, CFDB_NODE_MINB) node_update(int 
     node_finish(n, acc, U, M, GAMM, WXa, WYa, bcflag, bc, rk_fact, FR, U1, RHO, VELX, VELY, Ea, Pa, Ta, RMACH);
 }
 
+// Tile-boundary nodes of the fused stage (stage_fused.cuh): node bnodes[i] owns records bn_ptr[i] .. bn_ptr[i+1] of the
+// boundary staging buffer, written by the element warps in the node's summation order (ascending original element id) --
+// the index loads are coalesced, the records of a node are one contiguous run, and the nodal chain is node_update's.
+__global__ void __launch_bounds__(CFDB_NODE_BS, CFDB_NODE_MINB) boundary_update(int nb, const int* __restrict__ bnodes, const int* __restrict__ bn_ptr,
+                                                    const double* __restrict__ ECB, const double* __restrict__ U,
+                                                    const double* __restrict__ M, CF GAMM, const double* __restrict__ WXa,
+                                                    const double* __restrict__ WYa, const unsigned char* __restrict__ bcflag,
+                                                    BcTab bc, double rk_fact, double FR, double* __restrict__ U1,
+                                                    double* __restrict__ RHS, WF RHO, WF VELX, WF VELY, WF Ea, WF Pa, WF Ta, WF RMACH) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb) return;
+    const int n = bnodes[i];
+    const int k0 = bn_ptr[i], k1 = bn_ptr[i + 1];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k = k0; k < k1; ++k) {
+        double c[4];
+        ld4(ECB + 4 * (size_t)k, c);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[q] = acc[q] + c[q];
+    }
+    st4(RHS + 4 * (size_t)n, acc);
+    node_finish(n, acc, U, M, GAMM, WXa, WYa, bcflag, bc, rk_fact, FR, U1, RHO, VELX, VELY, Ea, Pa, Ta, RMACH);
+}
+
 // ADAMSB's nodal part (subrutinas.f90:894-1031): RHS = ordered sum; U1 = U - (55 RHS - 59 RHS1 + 37 RHS2 - 9 RHS3)/(24 M);
 // history shift RHS3 <- RHS2 <- RHS1 <- RHS; primitives; fixvel -> normalvel -> FIX; conservative.
 template <bool ALE>

@@ -3,30 +3,28 @@
 // One RK stage of the reference is  RHS = 0 ; calcRHS ; U1 = U - rk/M*RHS ; primitives ; fixvel/normalvel/FIX ; conservative
 // (subrutinas.f90:667-826, calcRHS.f90:36-151).  The two-kernel stage (calcrhs_elem + node_update) pays for the reference's
 // summation order with a 96 B/element staging buffer written and read back through HBM.  This kernel keeps that buffer in
-// shared memory for ~80 % of the nodes:
+// shared memory for ~82 % of the nodes:
 //
 //   * the elements are stored in tile order (host_topology.h: build_tiling): tile t = TE consecutive internal elements, a
-//     compact patch of the mesh; a node all of whose elements lie in one tile is INTERIOR to it;
+//     compact patch of the mesh (recursive coordinate bisection); a node all of whose elements lie in one tile is INTERIOR
+//     to it;
 //   * a persistent CTA (one per SM) walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...;
-//   * warp specialisation: ONE loader warp brings everything a tile needs into a two-stage shared-memory ring while the
-//     NCW compute warps work on the previous tile -- the tile's static block and its element stream (geometry,
-//     stabilisation parameters) by cp.async.bulk (TMA bulk copies completing on an mbarrier's transaction count), the
-//     nodal state of the tile's nodes by cp.async gathers (one 32-byte sector per node) tracked by the same mbarrier.
-//     Compute warps therefore never wait for HBM: their inputs are in shared memory when full[stage] completes;
-//   * compute warps: thread = element; gradients and the 12 contributions in registers (calcrhs_body, unchanged
-//     arithmetic), results to the shared-memory array C[12][TE] (double-buffered); contributions to tile-boundary nodes
-//     ALSO go to the global staging buffer EC.  Each warp then takes its share of the PREVIOUS tile's interior nodes:
-//     node j sums its contributions from C in ascending ORIGINAL element order (the `slots` list of the static block) and
-//     runs the nodal chain (node_finish_v) -- same operations, same order, same bits as node_update;
-// Tile-boundary nodes (~20 %) are finished by node_update over the list `bnodes` right after this kernel.
+//   * warp specialisation (see stage_fused below): ONE loader warp brings everything a tile needs into shared-memory rings
+//     -- the tile's static block and its element stream (geometry, stabilisation parameters) by cp.async.bulk (TMA bulk
+//     copies completing on an mbarrier's transaction count), the nodal state of the tile's nodes by cp.async gathers (one
+//     32-byte sector per node) tracked by an mbarrier -- twelve ELEMENT warps do the element arithmetic (thread = element;
+//     calcrhs_body, unchanged arithmetic) into the shared-memory array C[12][TE] (double-buffered), three NODE warps sum
+//     each interior node's contributions from C in ascending ORIGINAL element order (the `slots` list of the static
+//     block) and run the nodal chain -- same operations, same order, same bits as node_update;
+//   * contributions to tile-boundary nodes (~18 % of the nodes) go to the boundary staging buffer ECB, laid out so that
+//     the records of one node are contiguous and in summation order; boundary_update finishes those nodes right after
+//     this kernel, reading each node's records as one run.
 //
 // Roofline: HBM traffic per element-stage falls from 404 B (220 algorithmic + 192 staging, measured 6.46 GB per stage on the
-// 16 M-triangle mesh) to ~230 B; the kernel is then bound by the fp64 pipe (~812 non-FMA fp64 instructions per element).
+// 16 M-triangle mesh) to ~290 B; the kernel is then bound by the fp64 pipe and the issue port together (819 fp64 + 762 other
+// instructions per element warp and tile: 2 x 819 pipe cycles against 1581 issue slots, profiles/r2_stage_mix.txt).
 #pragma once
 // build-time switches of the stage kernel (A/B builds: make ab ABFLAGS=-D...)
-#ifndef CFDB_NODE_ILP2
-#define CFDB_NODE_ILP2 0      // node warps: two nodes per lane in flight (needs CFDB_STAGE_RE <= 144)
-#endif
 #ifndef CFDB_NODE_NB
 #define CFDB_NODE_NB 1        // node warps: branch-free divisions / square root in the nodal chain
 #endif
@@ -51,12 +49,24 @@ __device__ __forceinline__ unsigned mbar_try_wait(unsigned bar, unsigned parity)
                  : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok;
 }
-// Bounded wait: a protocol bug must end in a trap (sticky error the host sees), never in a hung GPU.
+__device__ __forceinline__ unsigned mbar_try_wait_hint(unsigned bar, unsigned parity, unsigned ns) {
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity), "r"(ns) : "memory");
+    return ok;
+}
+// Bounded wait: a protocol bug must end in a trap (sticky error the host sees), never in a hung GPU.  A waiting warp shares
+// its scheduler with three element warps: the retry loop is four instructions (the clock is read every 1024th retry only)
+// and every attempt lets the hardware park the warp (suspend-time hint).
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s at 2 GHz
+    long long t0 = 0;
+    for (unsigned spins = 1;; ++spins) {
+        if (mbar_try_wait_hint(bar, parity, 2000u)) return;
+        if ((spins & 1023u) == 0) {
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s at 2 GHz
+        }
     }
 }
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
@@ -86,7 +96,7 @@ template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setma
 // offsets of the static tile block (mirror of topo::TileLayout) and of the two shared-memory rings
 struct TileGeom {
     int TE, ntn_max, nint_max, nslot_max;
-    int off_lnode, off_tnode, off_nptr, off_slots, off_bcf, off_tch, off_bptr, off_bidx, tb_bytes;
+    int off_lnode, off_tnode, off_nptr, off_slots, off_bcf, off_brank, off_bbase, tb_bytes;
     // A ring slot (static block + gathered nodal data), bytes from the slot base
     int a_static, a_u, a_t, a_m, a_g, a_bytes;
     int b_bytes;       // B ring slot: the element stream, nfields x TE doubles
@@ -108,11 +118,9 @@ struct StageArgs {
     BcTab bc;
     double rk_fact, FR;
     Gas g;
-    double *EC, *U1, *RHS;
+    double* ECB;                                   // boundary staging buffer: 32-byte records, the records of one node side by side
+    double *U1, *RHS;
     WF RHO, VELX, VELY, Ea, Pa, Ta, RMACH;
-    int* cnt;                                      // per node: contributions-arrived counter of the tile-boundary nodes (null: they
-                                                   // are left to node_update over the list bnodes, launched after this kernel)
-    const unsigned char* bcflag;
     unsigned long long* stats;                     // optional (CFDB_STAGE_STATS): cycle counters, see stage_fused
 };
 enum { ST_E = 0, ST_N, ST_WAIT_IN, ST_WAIT_CE, ST_WAIT_CF, ST_LD_WB, ST_LD_WS, ST_LD_WA, ST_TILES, ST_COUNT };
@@ -123,7 +131,7 @@ enum { ST_E = 0, ST_N, ST_WAIT_IN, ST_WAIT_CE, ST_WAIT_CF, ST_LD_WB, ST_LD_WS, S
 // runs the plain form, whose stores (same thread, same addresses, program order) replace these.
 template <bool VISC, bool NB>
 __device__ __forceinline__ unsigned fused_elem(const TileGeom& G, const StageArgs& A, const unsigned char* sa, const unsigned char* sbm,
-                                               double* __restrict__ C, int k, int nint, long e_glob, double dtl_uniform) {
+                                               double* __restrict__ C, int k, int nint, double dtl_uniform) {
     const int TE = G.TE;
     const unsigned short* lnode = reinterpret_cast<const unsigned short*>(sa + G.a_static + G.off_lnode);
     const int ln[3] = {lnode[k], lnode[TE + k], lnode[2 * TE + k]};
@@ -158,14 +166,18 @@ __device__ __forceinline__ unsigned fused_elem(const TileGeom& G, const StageArg
             v[i] = NB ? ex::div3_nb(rt[n][i] * ar * dtl, bad) : ex::div3(rt[n][i] * ar * dtl);
             C[(4 * n + i) * TE + k] = v[i];
         }
-        if (bmask & (1u << n)) st4(A.EC + 12 * e_glob + 4 * n, v);
+        if (bmask & (1u << n)) {   // tile-boundary node: record bbase[node] + (rank of this element in the node's list)
+            const unsigned rec = reinterpret_cast<const unsigned*>(sa + G.a_static + G.off_bbase)[ln[n] - nint] +
+                                 (sa + G.a_static + G.off_brank)[n * TE + k];
+            st4(A.ECB + 4 * (size_t)rec, v);
+        }
     }
     return bad;
 }
 template <bool VISC>
 __device__ __noinline__ void fused_elem_plain(const TileGeom& G, const StageArgs& A, const unsigned char* sa, const unsigned char* sbm,
-                                              double* __restrict__ C, int k, int nint, long e_glob, double dtl_uniform) {
-    fused_elem<VISC, false>(G, A, sa, sbm, C, k, nint, e_glob, dtl_uniform);
+                                              double* __restrict__ C, int k, int nint, double dtl_uniform) {
+    fused_elem<VISC, false>(G, A, sa, sbm, C, k, nint, dtl_uniform);
 }
 
 // Warp roles.  NCW element warps (a multiple of 4) + one auxiliary warpgroup: warp NCW is the loader, warps NCW+1..NCW+3 are
@@ -311,83 +323,6 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1) stage_fused(const __grid_co
             const int* tnode = reinterpret_cast<const int*>(ab + G.a_static + G.off_tnode);
             const unsigned short* nptr = reinterpret_cast<const unsigned short*>(ab + G.a_static + G.off_nptr);
             const unsigned short* slots = reinterpret_cast<const unsigned short*>(ab + G.a_static + G.off_slots);
-            // Tile-boundary nodes: this tile's contributions to them are in the global staging buffer EC (the element warps'
-            // stores, ordered before this point by the C-full barrier).  Announce them -- fence, then one atomic increment per
-            // node -- BEFORE the interior nodes, whose work hides the round trip; the tile whose increment completes the
-            // count (every tile touching the node has then published its contributions) finishes the node below.
-            const int nbd = hdr[1] - nint;
-            const unsigned char* tch = ab + G.a_static + G.off_tch;
-            unsigned lastmask = 0;
-            if (A.cnt) {
-                __threadfence();
-#pragma unroll 1
-                for (int jb = nt, r = 0; jb < nbd; jb += NNT, ++r) {
-                    const int old = atomicAdd(A.cnt + tnode[nint + jb], 1);
-                    const int tc = tch[jb];
-                    if ((old + 1) % tc == 0) lastmask |= 1u << r;
-                }
-            }
-#if CFDB_NODE_ILP2
-            // two nodes per lane at a time (j and j + NNT): their gather chains, reciprocal refinements and square roots are
-            // independent, so the two instruction streams overlap each other's latencies -- the node warps share the fp64
-            // pipe with three element warps per sub-partition and would otherwise wait on every dependent instruction
-#pragma unroll 1
-            for (int j0 = nt; j0 < nint; j0 += 2 * NNT) {
-                const int jj[2] = {j0, j0 + NNT};
-                const bool on[2] = {true, jj[1] < nint};
-                int n[2], q0[2], q1[2];
-                double acc[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}};
-#pragma unroll
-                for (int s2 = 0; s2 < 2; ++s2) {
-                    const int j = on[s2] ? jj[s2] : j0;
-                    n[s2] = tnode[j];
-                    q0[s2] = nptr[j];
-                    q1[s2] = on[s2] ? nptr[j + 1] : q0[s2];
-                }
-                const int len = max(q1[0] - q0[0], q1[1] - q0[1]);
-                for (int r = 0; r < len; ++r) {
-#pragma unroll
-                    for (int s2 = 0; s2 < 2; ++s2) {
-                        if (q0[s2] + r < q1[s2]) {
-                            const int sl = slots[q0[s2] + r];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) acc[s2][i] = acc[s2][i] + C[sl + i * TE];
-                        }
-                    }
-                }
-                double u[2][4], m[2], gam[2];
-                unsigned fl[2];
-#pragma unroll
-                for (int s2 = 0; s2 < 2; ++s2) {
-                    const int j = on[s2] ? jj[s2] : j0;
-                    if (on[s2]) st4(A.RHS + 4 * (size_t)n[s2], acc[s2]);
-                    if (A.U == A.Usrc) {   // the tile's copy of the state is the state the update starts from
-                        const double2* q = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(ab + G.a_u) + 4 * j);
-                        double2 a = q[0], b = q[1];
-                        u[s2][0] = a.x; u[s2][1] = a.y; u[s2][2] = b.x; u[s2][3] = b.y;
-                    } else {
-                        ld4(A.U + 4 * (size_t)n[s2], u[s2]);
-                    }
-                    m[s2] = reinterpret_cast<const double*>(ab + G.a_m)[j];
-                    gam[s2] = reinterpret_cast<const double*>(ab + G.a_g)[j];
-                    fl[s2] = (ab + G.a_static + G.off_bcf)[j];
-                }
-                NodePrims pr[2];
-                unsigned bad[2];
-#pragma unroll
-                for (int s2 = 0; s2 < 2; ++s2) bad[s2] = node_prims_nb(acc[s2], u[s2], m[s2], gam[s2], A.rk_fact, A.FR, pr[s2]);
-#pragma unroll
-                for (int s2 = 0; s2 < 2; ++s2) {
-                    if (!on[s2]) continue;
-                    if (bad[s2])
-                        node_finish_plain(n[s2], acc[s2], u[s2], m[s2], gam[s2], fl[s2], A.WXa, A.WYa, A.bc, A.rk_fact, A.FR, A.U1, A.RHO,
-                                          A.VELX, A.VELY, A.Ea, A.Pa, A.Ta, A.RMACH);
-                    else
-                        node_bc_store(n[s2], pr[s2].rho, pr[s2].vx, pr[s2].vy, pr[s2].en, pr[s2].p, pr[s2].t, pr[s2].mach, gam[s2], fl[s2],
-                                      A.WXa, A.WYa, A.bc, A.FR, A.U1, A.RHO, A.VELX, A.VELY, A.Ea, A.Pa, A.Ta, A.RMACH);
-                }
-            }
-#else
 #pragma unroll 1
             for (int j = nt; j < nint; j += NNT) {
                 const int n = tnode[j];
@@ -435,42 +370,6 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1) stage_fused(const __grid_co
                               A.Ta, A.RMACH);
 #endif
             }
-#endif
-            if (lastmask) {
-                // finish the tile-boundary nodes this tile completed: all their contributions, whichever CTA wrote them, in
-                // ascending original element order from EC (read past L1: other SMs wrote them), then the nodal chain
-                __threadfence();
-                const unsigned short* bptr = reinterpret_cast<const unsigned short*>(ab + G.a_static + G.off_bptr);
-                const unsigned* bidx = reinterpret_cast<const unsigned*>(ab + G.a_static + G.off_bidx);
-#pragma unroll 1
-                for (int jb = nt, r = 0; jb < nbd; jb += NNT, ++r) {
-                    if (!(lastmask & (1u << r))) continue;
-                    const int n = tnode[nint + jb];
-                    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-                    const int q1 = bptr[jb + 1];
-#pragma unroll 1
-                    for (int q = bptr[jb]; q < q1; q += 4) {
-                        double2 cv[4][2];
-#pragma unroll
-                        for (int r2 = 0; r2 < 4; ++r2) {
-                            const double2* src = reinterpret_cast<const double2*>(A.EC + 4 * (size_t)bidx[min(q + r2, q1 - 1)]);
-                            cv[r2][0] = __ldcg(src);
-                            cv[r2][1] = __ldcg(src + 1);
-                        }
-#pragma unroll
-                        for (int r2 = 0; r2 < 4; ++r2)
-                            if (q + r2 < q1) {
-                                acc[0] = acc[0] + cv[r2][0].x; acc[1] = acc[1] + cv[r2][0].y;
-                                acc[2] = acc[2] + cv[r2][1].x; acc[3] = acc[3] + cv[r2][1].y;
-                            }
-                    }
-                    st4(A.RHS + 4 * (size_t)n, acc);
-                    double u[4];
-                    ld4(A.U + 4 * (size_t)n, u);
-                    node_finish_v(n, acc, u, A.M[n], A.GAMM[n], A.bcflag[n], A.WXa, A.WYa, A.bc, A.rk_fact, A.FR, A.U1, A.RHO, A.VELX,
-                                  A.VELY, A.Ea, A.Pa, A.Ta, A.RMACH);
-                }
-            }
             __syncwarp();
             if (lane == 0) {
                 ptx::mbar_arrive(cempty0 + 8 * cj);
@@ -501,9 +400,8 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1) stage_fused(const __grid_co
         const int ne = hdr[0], nint = hdr[2];
         if (k < ne) {
             double* C = Cbase + (size_t)c * 12 * TE;
-            const long e_glob = (long)t * TE + k;
             // branch-free divisions (exact.cuh) first; the plain form only if an operand left their range
-            if (fused_elem<VISC, true>(G, A, ab, bb, C, k, nint, e_glob, dtl_uniform)) fused_elem_plain<VISC>(G, A, ab, bb, C, k, nint, e_glob, dtl_uniform);
+            if (fused_elem<VISC, true>(G, A, ab, bb, C, k, nint, dtl_uniform)) fused_elem_plain<VISC>(G, A, ab, bb, C, k, nint, dtl_uniform);
         }
         if (stat) st[ST_E] += (unsigned long long)(clock64() - t0);
         __syncwarp();
