@@ -363,9 +363,9 @@ def main():
     prof = kernel_profile(g)
     peak, peak_src = peaks()
     fused = "stage_fused" in prof
-    if fused:   # the RK stage = fused tile kernel + node_update over the tile-boundary nodes
+    if fused:   # the RK stage = fused tile kernel + boundary_update over the tile-boundary nodes (profile slot "node_update")
         stage_ms = prof["stage_fused"]["avg_ms"] + prof["node_update"]["avg_ms"]
-        stage_kernels = "stage_fused+node_update(tile-boundary nodes)"
+        stage_kernels = "stage_fused+boundary_update(tile-boundary nodes)"
         dom = "stage_fused"
     else:
         stage_ms = prof["calcrhs_elem"]["avg_ms"] + prof["node_update"]["avg_ms"]
@@ -378,7 +378,7 @@ def main():
     if cands:   # dram__bytes_read+write per launch from the newest committed ncu capture (NOT measured in this run)
         with open(cands[-1]) as f:
             tj = json.load(f)
-        traffic = sum(tj.get(k, 0) for k in (("stage_fused", "node_update") if fused else ("calcrhs_elem", "node_update")) if k in tj) or None
+        traffic = sum(tj.get(k, 0) for k in (("stage_fused", "boundary_update") if fused else ("calcrhs_elem", "node_update")) if k in tj) or None
         traffic_src = f"profiles/{os.path.basename(cands[-1])} (committed ncu --set full capture, bytes per stage; not measured in this run)"
     roofline = {
         "bound": "hbm", "kernel": stage_kernels, "achieved": stage_achieved, "peak": peak, "unit": "GB/s", "frac": stage_achieved / peak,

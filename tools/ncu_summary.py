@@ -34,6 +34,6 @@ for r in rows[2:]:
     ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
     traffic[name.split("<")[0]] = float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
 open(f"profiles/{tag}_stage.txt", "w").write(
-    "ncu --set full --clock-control none, bench.py --steps 2 --warmup 3 (16 M triangles), one launch per kernel\n" + "\n".join(out) + "\n")
+    "ncu --set full --clock-control none --import-source on, tools/exp_stage.py 2829 (the bench mesh: 16 M triangles), first captured launch of each kernel\n" + "\n".join(out) + "\n")
 json.dump(traffic, open(f"profiles/{tag}_traffic.json", "w"), indent=1)
 print("\n".join(out))
