@@ -1093,6 +1093,8 @@ static int run_stage_fused(cfdb_ctx* c, const k::Gas& g, const double* dtl_arr, 
     // boundary_update below.  (Finishing them inside the stage kernel -- last contributing tile, atomics + fences -- measured
     // 3.08 ms against 1.16 + 0.35 ms on the 16 M-triangle mesh and was removed, profiles/r2_experiments.md.)
     A.stats = c->stage_stats;
+    static const int stat_warp = getenv("CFDB_STAGE_STATS") ? std::max(0, atoi(getenv("CFDB_STAGE_STATS")) - 1) % 12 : 0;
+    A.stat_warp = stat_warp;
     static std::map<const void*, size_t> attr_done;   // per kernel: the largest dynamic shared-memory size opted into so far
     if (attr_done[(const void*)kern] < c->stage_smem) {
         CK(cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->stage_smem));

@@ -122,6 +122,7 @@ struct StageArgs {
     double *U1, *RHS;
     WF RHO, VELX, VELY, Ea, Pa, Ta, RMACH;
     unsigned long long* stats;                     // optional (CFDB_STAGE_STATS): cycle counters, see stage_fused
+    int stat_warp;                                 // the element warp that reports (CFDB_STAGE_STATS=k: warp k-1)
 };
 enum { ST_E = 0, ST_N, ST_WAIT_IN, ST_WAIT_CE, ST_WAIT_CF, ST_LD_WB, ST_LD_WS, ST_LD_WA, ST_TILES, ST_COUNT };
 
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1) stage_fused(const __grid_co
     unsigned long long* st = reinterpret_cast<unsigned long long*>(smem + 176);   // barriers end at byte 160 (NA = 4), C starts at 256
     if (threadIdx.x < ST_COUNT) st[threadIdx.x] = 0;
     __syncthreads();
-    const bool stat = A.stats != nullptr && lane == 0 && (warp == 0 || warp == NCW || warp == NCW + 1);
+    const bool stat = A.stats != nullptr && lane == 0 && (warp == A.stat_warp || warp == NCW || warp == NCW + 1);
     auto waitc = [&](unsigned bar, unsigned par, int slot) {   // wait, with the cycles charged to st[slot] on the reporting lanes
         if (ptx::mbar_try_wait(bar, par)) return;
         const long long t0 = clock64();
