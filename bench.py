@@ -65,52 +65,62 @@ def host_threads():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 20 ms during the timed region."""
+    """SM clock, power and clock-event (throttle) reasons of one GPU sampled every 5 ms during the timed region, through NVML
+    (nvidia_ml_py; an `nvidia-smi -lms` child takes longer to start than the timed region lasts on an 8-GPU box)."""
+
+    REASONS = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+               ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap"),
+               ("hw_power_brake", "nvmlClocksEventReasonHwPowerBrakeSlowdown"))
 
     def __init__(self, index):
         self.index = index
         self.rows = []
-        self.proc = None
-
-    def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+        self.h = None
+        self.stop_flag = threading.Event()
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            try:      # the device this rank computes on, whatever CUDA_VISIBLE_DEVICES says
+                import torch
+                pr = torch.cuda.get_device_properties(index)
+                bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+                self.h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:   # no NVML: say so in the line instead of inventing numbers
+            self.err = f"NVML unavailable: {e}"
+            self.h = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, pw, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
             try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-                pw.append(float(r[2]))
-                for n, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
+                self.rows.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)), nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0,
+                                  int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))))
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
+            time.sleep(0.005)
+
+    def start(self):
+        if self.h is None:
+            return
+        self.t = threading.Thread(target=self._loop, daemon=True)
+        self.t.start()
+
+    def stop(self):
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [getattr(self, "err", "NVML unavailable")], "samples": 0}
+        self.stop_flag.set()
+        self.t.join(timeout=2)
+        sm = [r[0] for r in self.rows]
+        mask = 0
+        for r in self.rows:
+            mask |= r[2]
+        reasons = sorted(n for n, const in self.REASONS if mask & int(getattr(self.nv, const, 0)))
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": min(sm) if sm else None, "sm_max_mhz": self.max_sm,
+                "power_w_max": max((r[1] for r in self.rows), default=None), "reasons": reasons, "samples": len(sm)}
 
 
 def bind_to_gpu_numa_node(local):

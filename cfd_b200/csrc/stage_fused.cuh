@@ -239,8 +239,8 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1) stage_fused(const __grid_co
     __syncthreads();
     const bool stat = A.stats != nullptr && lane == 0 && (warp == A.stat_warp || warp == NCW || warp == NCW + 1);
     auto waitc = [&](unsigned bar, unsigned par, int slot) {   // wait, with the cycles charged to st[slot] on the reporting lanes
-        if (ptx::mbar_try_wait(bar, par)) return;
-        const long long t0 = clock64();
+        if (A.stats == nullptr) { ptx::mbar_wait(bar, par); return; }
+        const long long t0 = clock64();                         // before the first attempt: try_wait itself may park the warp
         ptx::mbar_wait(bar, par);
         if (stat) st[slot] += (unsigned long long)(clock64() - t0);
     };

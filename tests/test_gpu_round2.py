@@ -225,3 +225,29 @@ def test_print_step_text_files(cases, tmp_path):
     for k in (0, skin.size - 1):
         assert sk[k] == " " + "".join(NSComp2D.format_real("L", v, 0, 0) for v in (skin[k], sx[k], sp[k]))
         assert [float(x) for x in sk[k].split()] == [skin[k], sx[k], sp[k]]     # 17 significant digits round-trip
+
+
+def test_spmv_row_runs_of_any_length(cases):
+    """k::spmv stages the entries of 32 consecutive rows in shared memory when they fit its window and walks the global arrays
+    otherwise: rows of 1..60 entries (mixed inside a warp), an empty row, a row count that is not a multiple of 32 — every
+    row's sum in the reference's order (biconjGrad.f90:171-190), checked against the oracle bit for bit."""
+    from cfd_b200.solver import NSComp2D
+    from oracle import orclib
+
+    lc = cases["channel"]
+    g = NSComp2D(lc)
+    P = lc.npoin - 7
+    rng = np.random.default_rng(12)
+    width = rng.integers(1, 13, P)
+    width[100:164] = rng.integers(30, 61, 64)        # two warps whose runs exceed the window
+    width[300:310] = 0
+    width[40] = 200
+    rowptr = np.zeros(P + 1, np.int32)
+    rowptr[1:] = np.cumsum(width)
+    nnz = int(rowptr[-1])
+    idx = rng.integers(1, P + 1, nnz).astype(np.int32)
+    A = rng.standard_normal(nnz)
+    v = rng.standard_normal(P)
+    y_o = np.zeros(P)
+    orclib.lib().orc_spmv(A, idx, rowptr, v, y_o, P)
+    assert_bit_equal(g.spmv(A, idx, rowptr, v), y_o, "spmv with mixed row lengths")

@@ -126,3 +126,46 @@ def test_static_schedule_tool_runs_on_the_built_object():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_stalls.py"), obj, "stage_fusedILb0ELi12"],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "sum of stall fields" in r.stdout, r.stdout + r.stderr
+
+
+def test_tile_decomposition_of_the_fused_stage():
+    """host_topology.h: rcb_split / build_tiling through the host-only entry cfdb_tile_elements.  The internal element order
+    is a permutation; every tile but the last is full; recursive coordinate bisection leaves more nodes interior to one
+    tile than runs of a Morton curve; the result does not depend on the number of OpenMP threads."""
+    from cfd_b200 import capi, deck, meshgen
+
+    lc = deck.load(meshgen.square(201))
+    L = capi.lib()
+    out = {}
+    for order in (0, 1, 2):
+        i2e, st = np.zeros(lc.nelem, np.int32), np.zeros(8)
+        capi.check(L.cfdb_tile_elements(lc.inpoel, lc.nelem, lc.npoin, lc.X, lc.Y, 384, order, i2e, st))
+        assert np.array_equal(np.sort(i2e), np.arange(lc.nelem)), "i2e must be a permutation"
+        assert st[1] == -(-lc.nelem // 384)
+        assert st[6] + round(st[0] * lc.npoin) == lc.npoin          # interior + tile-boundary (incl. orphans) = all nodes
+        out[order] = (i2e, st)
+    assert np.array_equal(out[0][0], np.arange(lc.nelem))            # order 0: the file's order
+    assert out[2][1][0] > out[1][1][0] > 0.7                         # rcb beats Morton runs; both keep most nodes interior
+    assert out[2][1][0] > 0.80
+    # a tile of the rcb order is a compact patch: its bounding box holds about as many element centroids as the tile has elements
+    i2e = out[2][0]
+    cx = lc.X[lc.inpoel - 1].mean(1)
+    cy = lc.Y[lc.inpoel - 1].mean(1)
+    worst = 0.0
+    for t in range(0, lc.nelem // 384, 7):
+        e = i2e[384 * t:384 * (t + 1)]
+        inside = ((cx >= cx[e].min()) & (cx <= cx[e].max()) & (cy >= cy[e].min()) & (cy <= cy[e].max())).sum()
+        worst = max(worst, inside / 384.0)
+    assert worst < 1.6, worst
+    # elements inside a tile are in ascending original id
+    for t in range(0, lc.nelem // 384, 11):
+        e = i2e[384 * t:384 * (t + 1)]
+        assert np.all(np.diff(e) > 0)
+    old = os.environ.get("OMP_NUM_THREADS")
+    again = np.zeros(lc.nelem, np.int32)
+    capi.check(L.cfdb_tile_elements(lc.inpoel, lc.nelem, lc.npoin, lc.X, lc.Y, 384, 2, again, np.zeros(8)))
+    assert np.array_equal(again, i2e)
+    if old is not None:
+        os.environ["OMP_NUM_THREADS"] = old
+    with pytest.raises(RuntimeError):
+        capi.check(L.cfdb_tile_elements(lc.inpoel, lc.nelem, lc.npoin, lc.X, lc.Y, 100, 2, again, np.zeros(8)))
