@@ -551,7 +551,7 @@ static int build_stage_tiles(cfdb_ctx* c, const int32_t* inpoel, const double* X
     G.a_g = G.a_m + up16(L.nint_max * 8);
     G.a_bytes = up128(G.a_g + up16(L.nint_max * 8));
     G.b_bytes = up128(G.nfields * TE * 8);
-    G.off_c = 256;
+    G.off_c = 384;   // barriers (<= 160 B) + the optional cycle counters (ST_COUNT x 8 B from byte 176)
     G.off_a = up128(G.off_c + 2 * 12 * TE * 8);
     c->tile_na = 3;
     G.off_b = G.off_a + c->tile_na * G.a_bytes;
@@ -1690,6 +1690,9 @@ extern "C" int cfdb_sync(cfdb_ctx* c) {
                         " | loader waits: stream slot %.0f  static landed %.0f  A slot %.0f  (tiles %.0f)\n",
                 h[k::ST_E] / tl, h[k::ST_N] / tl, h[k::ST_WAIT_IN] / tl, h[k::ST_WAIT_CE] / tl, h[k::ST_WAIT_CF] / tl, h[k::ST_LD_WB] / tl,
                 h[k::ST_LD_WS] / tl, h[k::ST_LD_WA] / tl, tl);
+        if (h[k::ST_LOOP_NS])
+            fprintf(stderr, "[stage_fused] the reporting element warp's tile loop: %.0f cycles per tile (hand-over after the arithmetic: %.0f), SM clock %.3f GHz while the kernel ran\n",
+                    h[k::ST_LOOP_CYC] / tl, h[k::ST_ARRIVE] / tl, (double)h[k::ST_LOOP_CYC] / (double)h[k::ST_LOOP_NS]);
     }
     return 0;
 }

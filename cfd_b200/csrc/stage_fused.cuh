@@ -124,7 +124,7 @@ struct StageArgs {
     unsigned long long* stats;                     // optional (CFDB_STAGE_STATS): cycle counters, see stage_fused
     int stat_warp;                                 // the element warp that reports (CFDB_STAGE_STATS=k: warp k-1)
 };
-enum { ST_E = 0, ST_N, ST_WAIT_IN, ST_WAIT_CE, ST_WAIT_CF, ST_LD_WB, ST_LD_WS, ST_LD_WA, ST_TILES, ST_COUNT };
+enum { ST_E = 0, ST_N, ST_WAIT_IN, ST_WAIT_CE, ST_WAIT_CF, ST_LD_WB, ST_LD_WS, ST_LD_WA, ST_TILES, ST_LOOP_CYC, ST_LOOP_NS, ST_ARRIVE, ST_COUNT };
 
 // One element: inputs from shared memory -- `sa` is the tile's A slot (connectivity + nodal state), `sbm` its B slot (element
 // stream) -- the twelve contributions to C (and to the global staging buffer EC for tile-boundary nodes, finished by
@@ -234,7 +234,8 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1) stage_fused(const __grid_co
     const int TE = G.TE;
     // optional cycle counters (CFDB_STAGE_STATS): element warp 0, node warp 0 and the loader report; kept in shared memory so
     // that they cost no registers
-    unsigned long long* st = reinterpret_cast<unsigned long long*>(smem + 176);   // barriers end at byte 160 (NA = 4), C starts at 256
+    unsigned long long* st = reinterpret_cast<unsigned long long*>(smem + 176);   // barriers end at byte 160 (NA = 4), C starts at 384
+    static_assert(176 + 8 * ST_COUNT <= 384, "the cycle counters must end before C");
     if (threadIdx.x < ST_COUNT) st[threadIdx.x] = 0;
     __syncthreads();
     const bool stat = A.stats != nullptr && lane == 0 && (warp == A.stat_warp || warp == NCW || warp == NCW + 1);
@@ -389,6 +390,9 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1) stage_fused(const __grid_co
     const double dtl_uniform = G.nfields == 12 ? 0.0 : *A.dtl_sc;
     const int k = threadIdx.x;   // element position in the tile
     int t = blockIdx.x;
+    long long loop_c0 = 0;
+    unsigned long long loop_n0 = 0;
+    if (stat) { loop_c0 = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(loop_n0)); }
     for (int it = 0; it < my_tiles; ++it, t += gridDim.x) {
         const int sa = it % NA, sb = it % NBR, c = it & 1;
         const unsigned char* ab = smem + G.off_a + (size_t)sa * G.a_bytes;
@@ -404,16 +408,23 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1) stage_fused(const __grid_co
             // branch-free divisions (exact.cuh) first; the plain form only if an operand left their range
             if (fused_elem<VISC, true>(G, A, ab, bb, C, k, nint, dtl_uniform)) fused_elem_plain<VISC>(G, A, ab, bb, C, k, nint, dtl_uniform);
         }
-        if (stat) st[ST_E] += (unsigned long long)(clock64() - t0);
+        const long long t1 = stat ? clock64() : 0;
+        if (stat) st[ST_E] += (unsigned long long)(t1 - t0);
         __syncwarp();
         if (lane == 0) {
             ptx::mbar_arrive(cfull0 + 8 * c);
             ptx::mbar_arrive(bempty0 + 8 * sb);
             ptx::mbar_arrive(aempty0 + 8 * sa);
         }
+        if (stat) st[ST_ARRIVE] += (unsigned long long)(clock64() - t1);
     }
     if (stat) {
+        unsigned long long n1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(n1));
+        atomicAdd(A.stats + ST_LOOP_CYC, (unsigned long long)(clock64() - loop_c0));   // the reporting warp's whole tile loop: cycles and ns,
+        atomicAdd(A.stats + ST_LOOP_NS, n1 - loop_n0);                                  // i.e. the SM clock the kernel actually ran at
         atomicAdd(A.stats + ST_E, st[ST_E]);
+        atomicAdd(A.stats + ST_ARRIVE, st[ST_ARRIVE]);
         atomicAdd(A.stats + ST_WAIT_IN, st[ST_WAIT_IN]);
         atomicAdd(A.stats + ST_WAIT_CE, st[ST_WAIT_CE]);
         atomicAdd(A.stats + ST_TILES, (unsigned long long)my_tiles);
