@@ -1,0 +1,8 @@
+#!/bin/bash
+# four node-data slots + gathers before the stream in the loader: parity, timing, counters
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+CFDB_VERBOSE=1 timeout 300 python tools/exp_stage.py 2829 2>&1 | grep "tiles:\|default\|VERBOSE" | tail -2
+CFDB_TILE_NA=3 timeout 300 python tools/exp_stage.py 2829 2>&1 | tail -1
+CFDB_STAGE_STATS=2 timeout 300 python tools/exp_stage.py 2829 2>&1 | grep "stage_fused\]" | tail -2
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/r2_c25_tests.txt 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r2_c25_tests.txt
