@@ -1320,7 +1320,7 @@ extern "C" int cfdb_fluid_structure(cfdb_ctx* c, double dtmin, double time) {
     // XREF(2)=1.4, YREF(2)=0 are overwritten on every call (meshMove.f90:58): applied once in cfdb_create
     if (c->nset || (c->nranks > 1 && c->ale)) {  // every rank of a moving-mesh run joins the all-reduce, with or without body edges of its own
         CK(cudaMemsetAsync(c->sc->FX, 0, 30 * sizeof(double), c->st));
-        if (c->nset) LAUNCH(K_FORCES, k::forces, 1, 32, c->nset, c->n_owned, c->set_ptr.p, c->set_n1.p, c->set_n2.p, c->X.p, c->Y.p, c->P.col,
+        if (c->nset) LAUNCH(K_FORCES, k::forces, c->nset, 256, c->nset, c->n_owned, c->set_ptr.p, c->set_n1.p, c->set_n2.p, c->X.p, c->Y.p, c->P.col,
                c->xref.p, c->yref.p, c->sc);
         TRY(allreduce(c, c->sc->FX, 30, ncclSum));  // FX,FY,RM are contiguous in Scal
     }

@@ -1499,27 +1499,70 @@ __global__ void __launch_bounds__(256) move_apply(int npoin, const double* __res
     X1[i] = X1[i] + d;
     W[i] = d / *dtmin_p;
 }
-// FORCES (:171-192): sequential sums over the (few thousand) body edges of each set; one thread per
-// set keeps the reference order exactly.
-__global__ void forces(int nset, int n_owned, const int* __restrict__ sptr, const int* __restrict__ n1a, const int* __restrict__ n2a,
-                       const double* __restrict__ X, const double* __restrict__ Y, CF P,
-                       const double* __restrict__ xref, const double* __restrict__ yref, Scal* sc) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
+// FORCES (meshMove.f90:171-192): per body set, sequential sums over its (few thousand) edges.  One CTA per set: all threads
+// evaluate the edge terms (the gathers of P, X, Y are the slow part: a single thread walking the list took 0.74 ms for 2 000
+// edges), thread 0 then adds them in list order -- the reference's order, three dependent chains of a few thousand additions.
+constexpr int FORCES_CHUNK = 512;
+__global__ void __launch_bounds__(256) forces(int nset, int n_owned, const int* __restrict__ sptr, const int* __restrict__ n1a, const int* __restrict__ n2a,
+                                               const double* __restrict__ X, const double* __restrict__ Y, CF P,
+                                               const double* __restrict__ xref, const double* __restrict__ yref, Scal* sc) {
+    __shared__ double tfx[FORCES_CHUNK], tfy[FORCES_CHUNK], tma[FORCES_CHUNK], tmb[FORCES_CHUNK];
+    __shared__ unsigned char live[FORCES_CHUNK];
+    const int s = blockIdx.x;
     if (s >= nset) return;
+    const double xr = xref[s], yr = yref[s];
     double fx = 0.0, fy = 0.0, rm = 0.0;
-    for (int k = sptr[s]; k < sptr[s + 1]; ++k) {
-        int N1 = n1a[k], N2 = n2a[k];
-        if (N1 >= n_owned) continue;  // multi-rank: an edge is summed by the rank owning its first node
-        double D_PRESS = (P[N1] + P[N2]) / 2.0;
-        double RLX = X[N1] - X[N2];
-        double RLY = Y[N2] - Y[N1];
-        double DFX = D_PRESS * RLY, DFY = D_PRESS * RLX;
-        fx = fx + DFX;
-        fy = fy + DFY;
-        double XC = (X[N1] + X[N2]) / 2.0, YC = (Y[N2] + Y[N1]) / 2.0;
-        rm = rm + DFY * (XC - xref[s]) - DFX * (YC - yref[s]);
+    const int kend = sptr[s + 1];
+    for (int k0 = sptr[s]; k0 < kend; k0 += FORCES_CHUNK) {
+        const int m = min(FORCES_CHUNK, kend - k0);
+        for (int j = threadIdx.x; j < m; j += blockDim.x) {
+            const int N1 = n1a[k0 + j], N2 = n2a[k0 + j];
+            const bool on = N1 < n_owned;  // multi-rank: an edge is summed by the rank owning its first node
+            live[j] = on;
+            if (!on) continue;
+            double D_PRESS = (P[N1] + P[N2]) / 2.0;
+            double RLX = X[N1] - X[N2];
+            double RLY = Y[N2] - Y[N1];
+            double DFX = D_PRESS * RLY, DFY = D_PRESS * RLX;
+            double XC = (X[N1] + X[N2]) / 2.0, YC = (Y[N2] + Y[N1]) / 2.0;
+            tfx[j] = DFX;
+            tfy[j] = DFY;
+            tma[j] = DFY * (XC - xr);
+            tmb[j] = DFX * (YC - yr);
+        }
+        __syncthreads();
+        // three sequential chains, one thread each (threads 0, 32, 64: three different warps), operands fetched four edges ahead
+        if (threadIdx.x == 0 || threadIdx.x == 32) {
+            const double* __restrict__ t = threadIdx.x == 0 ? tfx : tfy;
+            double acc = threadIdx.x == 0 ? fx : fy;
+            int j = 0;
+            for (; j + 4 <= m; j += 4) {
+                const double v0 = t[j], v1 = t[j + 1], v2 = t[j + 2], v3 = t[j + 3];
+                const bool l0 = live[j], l1 = live[j + 1], l2 = live[j + 2], l3 = live[j + 3];
+                if (l0) acc = acc + v0;
+                if (l1) acc = acc + v1;
+                if (l2) acc = acc + v2;
+                if (l3) acc = acc + v3;
+            }
+            for (; j < m; ++j)
+                if (live[j]) acc = acc + t[j];
+            if (threadIdx.x == 0) fx = acc; else fy = acc;
+        } else if (threadIdx.x == 64) {
+            int j = 0;
+            for (; j + 2 <= m; j += 2) {
+                const double a0 = tma[j], b0 = tmb[j], a1 = tma[j + 1], b1 = tmb[j + 1];
+                const bool l0 = live[j], l1 = live[j + 1];
+                if (l0) rm = rm + a0 - b0;   // RM = RM + DFY*(XC-XREF) - DFX*(YC-YREF), left to right
+                if (l1) rm = rm + a1 - b1;
+            }
+            for (; j < m; ++j)
+                if (live[j]) rm = rm + tma[j] - tmb[j];
+        }
+        __syncthreads();
     }
-    sc->FX[s] = fx; sc->FY[s] = fy; sc->RM[s] = rm;
+    if (threadIdx.x == 0) sc->FX[s] = fx;
+    if (threadIdx.x == 32) sc->FY[s] = fy;
+    if (threadIdx.x == 64) sc->RM[s] = rm;
 }
 
 // FORCE_VISC (ns2DComp.ALE.f90:819-893): traction of the element behind each body-set edge (pressure + viscous stress),

@@ -1,4 +1,4 @@
-"""GPU experiment helper: config 3 — pitching-body ALE case (meshMove Laplace biCG + geometry every step)."""
+"""GPU experiment helper: per-kernel event timings of the moving-mesh step (BASELINE configs[2]: O-mesh around a pitching ellipse)."""
 import os
 import sys
 import time
@@ -9,25 +9,27 @@ from cfd_b200.solver import NSComp2D  # noqa: E402
 
 nt = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
 nr = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
-gcl = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 lc = deck.load(meshgen.ale_body(nt=nt, nr=nr, IPRINT=10**9, MAXITER=10**9))
-g = NSComp2D(lc, use_gcl=gcl)
-g.step(2)
+g = NSComp2D(lc, use_gcl=1)
+g.step(3)
 g.sync()
 t0 = time.perf_counter()
-nst = 5
-its = []
-for _ in range(nst):
-    g.step(1)
-    its.append((int(g.scalar("bicg_x")), int(g.scalar("bicg_y"))))
+g.step(10)
 g.sync()
-dt = (time.perf_counter() - t0) / nst
+dt = (time.perf_counter() - t0) / 10
 g.profile(True)
-g.step(2)
+g.step(3)
 g.sync()
-out = [f"ALE E={lc.nelem} P={lc.npoin} ms/step={dt*1e3:.3f} elem/s={lc.nelem/dt:.3e} bicg_iters={its}"]
-for kn in ("calcrhs_elem", "node_update", "estab", "deltat", "spmv", "dot", "vec", "fixrows", "scalar", "laplace", "deriv", "masas", "gcl", "move_apply"):
-    ms, cnt = g.profile_get(kn)
+out = [f"E={lc.nelem} ms/step={dt*1e3:.3f} (wall, 10 steps in one call) bicg iters {g.scalar('bicg_x'):.0f}/{g.scalar('bicg_y'):.0f}"]
+tot = 0.0
+for kn in ("deriv", "masas", "normales", "deltat", "dt_logic", "dtl", "estab", "calcrhs_elem", "node_update", "dot", "norms", "spmv", "vec",
+           "fixrows", "scalar", "laplace", "transf", "move_apply", "forces", "gcl", "layout", "fill", "halo", "stage_fused"):
+    try:
+        ms, cnt = g.profile_get(kn)
+    except Exception:
+        continue
     if cnt:
-        out.append(f"{kn}={ms/cnt:.4f}ms x{cnt/2:.0f}")
+        out.append(f"{kn}={ms/cnt:.4f}ms x{cnt/3:.1f}")
+        tot += ms / 3
+out.append(f"sum={tot:.3f}ms/step")
 print(" ".join(out), flush=True)
