@@ -1681,6 +1681,15 @@ extern "C" int cfdb_sync(cfdb_ctx* c) {
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->st));
     TRY(prof_resolve(c));
+    static const bool verbose_fb = getenv("CFDB_VERBOSE") != nullptr;
+    if (verbose_fb) {   // elements / nodes recomputed in the plain form since the last call (kernels.cuh: g_fallbacks)
+        unsigned long long fb[k::FB_COUNT] = {}, zero[k::FB_COUNT] = {};
+        CK(cudaMemcpyFromSymbol(fb, k::g_fallbacks, sizeof fb));
+        CK(cudaMemcpyToSymbol(k::g_fallbacks, zero, sizeof zero));
+        if (fb[0] | fb[1] | fb[2] | fb[3] | fb[4])
+            fprintf(stderr, "[fallbacks] plain-form recomputations since the last sync: estab %llu, deltat %llu, stage elements %llu, stage nodes %llu, calcrhs_elem %llu\n",
+                    fb[k::FB_ESTAB], fb[k::FB_DELTAT], fb[k::FB_STAGE_ELEM], fb[k::FB_STAGE_NODE], fb[k::FB_CALCRHS]);
+    }
     if (c->stage_stats) {   // CFDB_STAGE_STATS: where the cycles of the fused stage went (sums over the 148 CTAs)
         unsigned long long h[k::ST_COUNT];
         CK(cudaMemcpy(h, c->stage_stats, sizeof h, cudaMemcpyDeviceToHost));

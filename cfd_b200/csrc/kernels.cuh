@@ -60,6 +60,11 @@ struct WF {
 struct Rec1 { double t, gam, vx, vy; };
 enum { NR1_T = 0, NR1_GAMM = 1, NR1_VX = 2, NR1_VY = 3, NR2_RHO = 0, NR2_E = 1, NR2_P = 2, NR2_RMACH = 3 };
 
+// Elements (or nodes) that left the branch-free fast path and were recomputed in the plain form, per kernel family: a
+// diagnostic (cfdb_sync prints it under CFDB_VERBOSE); in a physical run the counters stay at or near zero.
+enum { FB_ESTAB = 0, FB_DELTAT, FB_STAGE_ELEM, FB_STAGE_NODE, FB_CALCRHS, FB_COUNT };
+__device__ unsigned long long g_fallbacks[FB_COUNT];
+
 struct Gas {
     double Cv, lambda_ref, mu_ref, gamma0, T_inf, cte;
 };
@@ -254,7 +259,10 @@ __global__ void __launch_bounds__(256) deltat(int nelem, const int* __restrict__
         unsigned bad = 0;
 #if CFDB_BATCH_DIV
         double DTELEM = deltat_elem<MOVING, true>(e, nelem, inp, area, T, VX, VY, WX, WY, FSAFE, T_inf, bad);
-        if (bad) DTELEM = deltat_plain<MOVING>(e, nelem, inp, area, T, VX, VY, WX, WY, FSAFE, T_inf);
+        if (bad) {
+            atomicAdd(&g_fallbacks[FB_DELTAT], 1ull);
+            DTELEM = deltat_plain<MOVING>(e, nelem, inp, area, T, VX, VY, WX, WY, FSAFE, T_inf);
+        }
 #else
         double DTELEM = deltat_elem<MOVING, false>(e, nelem, inp, area, T, VX, VY, WX, WY, FSAFE, T_inf, bad);
 #endif
@@ -527,7 +535,13 @@ __device__ __forceinline__ unsigned estab_fast(int e, int nelem, const int* __re
     double den = ex::Recip(RHOINF).div(4.0 * fmu, bad);
     const ex::Recip dden(den);
     double TAU_SUNG3 = dden.div(H_RGN * H_RGN, bad);
-    double TAU_SUNG3_E = dden.div(H_RGNE * H_RGNE, bad);
+    // H_RGNE has no `> 10 -> 0` clamp in the source: an element with an exactly uniform temperature (free stream) carries
+    // H_RGNE = 2/0 = +Inf into this quotient, and Inf/den = +Inf for the positive den (select; the fast path sees a harmless 1)
+    const double hh = H_RGNE * H_RGNE;
+    const bool hinf = is_pinf(hh);
+    double TAU_SUNG3_E = dden.div(hinf ? 1.0 : hh, bad);
+    bad |= (hinf && !(den > 0.0)) ? 1u : 0u;
+    TAU_SUNG3_E = hinf ? CUDART_INF : TAU_SUNG3_E;
     double q2 = TAU_SUNG3 * TAU_SUNG3, q3 = TAU_SUNG3_E * TAU_SUNG3_E;
     // 1/q for a square q: 1/(+0) = +Inf, 1/(+Inf) = +0; then (RESUMEN + that)**(-.5), which is 0 at +Inf
     auto tail = [&](double q) {
@@ -556,7 +570,10 @@ __global__ void __launch_bounds__(256, MINB) estab(int nelem, const int* __restr
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nelem) return;
 #if CFDB_BATCH_DIV
-    if (estab_fast<MOVING>(e, nelem, inp, U, T, VXa, VYa, WXa, WYa, GAMM, dNx, dNy, FR, dtmin_p, RHOINF, TINF, SHOC, TS1, TS2, TS3)) estab_plain<MOVING>(e, nelem, inp, U, T, VXa, VYa, WXa, WYa, GAMM, dNx, dNy, FR, dtmin_p, RHOINF, TINF, SHOC, TS1, TS2, TS3);
+    if (estab_fast<MOVING>(e, nelem, inp, U, T, VXa, VYa, WXa, WYa, GAMM, dNx, dNy, FR, dtmin_p, RHOINF, TINF, SHOC, TS1, TS2, TS3)) {
+        atomicAdd(&g_fallbacks[FB_ESTAB], 1ull);
+        estab_plain<MOVING>(e, nelem, inp, U, T, VXa, VYa, WXa, WYa, GAMM, dNx, dNy, FR, dtmin_p, RHOINF, TINF, SHOC, TS1, TS2, TS3);
+    }
 #else
     estab_one<MOVING>(e, nelem, inp, U, T, VXa, VYa, WXa, WYa, GAMM, dNx, dNy, FR, dtmin_p, RHOINF, TINF, SHOC, TS1, TS2, TS3);
 #endif
@@ -836,7 +853,10 @@ __global__ void __launch_bounds__(BS, MINB) calcrhs_elem(int e0, int e1, int nel
     int e = e0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= e1) return;
     if (NB) {
-        if (calcrhs_one<VISC, THETA, ALE, true>(e, CFDB_CALC_ARGS)) calcrhs_one_plain<VISC, THETA, ALE>(e, CFDB_CALC_ARGS);
+        if (calcrhs_one<VISC, THETA, ALE, true>(e, CFDB_CALC_ARGS)) {
+            atomicAdd(&g_fallbacks[FB_CALCRHS], 1ull);
+            calcrhs_one_plain<VISC, THETA, ALE>(e, CFDB_CALC_ARGS);
+        }
     } else {
         calcrhs_one<VISC, THETA, ALE, false>(e, CFDB_CALC_ARGS);
     }

@@ -364,9 +364,11 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1) stage_fused(const __grid_co
                 const unsigned fl = (ab + G.a_static + G.off_bcf)[j];
 #if CFDB_NODE_NB
                 if (node_finish_nb(n, acc, u, m, gam, fl, A.WXa, A.WYa, A.bc, A.rk_fact, A.FR, A.U1, A.RHO, A.VELX, A.VELY, A.Ea, A.Pa,
-                                   A.Ta, A.RMACH))
+                                   A.Ta, A.RMACH)) {
+                    atomicAdd(&g_fallbacks[FB_STAGE_NODE], 1ull);
                     node_finish_plain(n, acc, u, m, gam, fl, A.WXa, A.WYa, A.bc, A.rk_fact, A.FR, A.U1, A.RHO, A.VELX, A.VELY, A.Ea,
                                       A.Pa, A.Ta, A.RMACH);
+                }
 #else
                 node_finish_v(n, acc, u, m, gam, fl, A.WXa, A.WYa, A.bc, A.rk_fact, A.FR, A.U1, A.RHO, A.VELX, A.VELY, A.Ea, A.Pa,
                               A.Ta, A.RMACH);
@@ -406,7 +408,10 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1) stage_fused(const __grid_co
         if (k < ne) {
             double* C = Cbase + (size_t)c * 12 * TE;
             // branch-free divisions (exact.cuh) first; the plain form only if an operand left their range
-            if (fused_elem<VISC, true>(G, A, ab, bb, C, k, nint, dtl_uniform)) fused_elem_plain<VISC>(G, A, ab, bb, C, k, nint, dtl_uniform);
+            if (fused_elem<VISC, true>(G, A, ab, bb, C, k, nint, dtl_uniform)) {
+                atomicAdd(&g_fallbacks[FB_STAGE_ELEM], 1ull);
+                fused_elem_plain<VISC>(G, A, ab, bb, C, k, nint, dtl_uniform);
+            }
         }
         const long long t1 = stat ? clock64() : 0;
         if (stat) st[ST_E] += (unsigned long long)(t1 - t0);

@@ -13,6 +13,8 @@ if len(sys.argv) > 2 and sys.argv[2] == "visc":
     kw = dict(FMU=1.8e-5, FK=0.0257)
 lc = deck.load(meshgen.square(n=n, IPRINT=10**9, MAXITER=10**9, **kw))
 g = NSComp2D(lc)
+if os.environ.get("ALE"):          # moving-mesh kernels (FUENTE, mesh-velocity terms) on the same mesh; W stays 0
+    g.set_option("ale", 1)
 if os.environ.get("FAST"):
     g.set_option("fast", int(os.environ["FAST"]))
 for k, v in meshgen.density_bump(lc).items():

@@ -1,0 +1,5 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/r2_c30_tests.txt 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r2_c30_tests.txt
+CFDB_VERBOSE=1 timeout 600 python tools/exp_ale.py 2>&1 | grep "fallbacks\|ms/step" | tail -4
