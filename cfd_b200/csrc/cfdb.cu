@@ -1088,6 +1088,7 @@ static int run_stage_fused(cfdb_ctx* c, const k::Gas& g, const double* dtl_arr, 
     if (G.nfields > c->tgeom.nfields) return fail("run_stage_fused: stage layout was sized without a local time step array");
     void (*kern)(const k::TileGeom, const k::StageArgs) = nullptr;
     if (c->tile_ncw == 16) kern = visc ? k::stage_fused<true, 16, 3, 2> : k::stage_fused<false, 16, 3, 2>;
+    else if (c->stage_stats) kern = visc ? k::stage_fused<true, 12, 3, 2, true> : k::stage_fused<false, 12, 3, 2, true>;   // CFDB_STAGE_STATS
     else kern = visc ? k::stage_fused<true, 12, 3, 2> : k::stage_fused<false, 12, 3, 2>;
     // tile-boundary nodes: their contributions go to the boundary records (the otherwise idle staging buffer EC), finished by
     // boundary_update below.  (Finishing them inside the stage kernel -- last contributing tile, atomics + fences -- measured

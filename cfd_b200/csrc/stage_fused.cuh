@@ -25,6 +25,9 @@
 // instructions per element warp and tile: 2 x 819 pipe cycles against 1581 issue slots, profiles/r2_stage_mix.txt).
 #pragma once
 // build-time switches of the stage kernel (A/B builds: make ab ABFLAGS=-D...)
+#ifndef CFDB_FB_COUNT
+#define CFDB_FB_COUNT 1        // count the plain-form recomputations of the stage kernel (kernels.cuh: g_fallbacks)
+#endif
 #ifndef CFDB_NODE_NB
 #define CFDB_NODE_NB 1        // node warps: branch-free divisions / square root in the nodal chain
 #endif
@@ -202,7 +205,7 @@ __device__ __noinline__ void fused_elem_plain(const TileGeom& G, const StageArgs
 //                  and runs the nodal chain; release C[i&1] and A(i).  Gather chains, four divisions and a square root per
 //                  node, scattered stores: latency-bound work that now runs beside the element arithmetic instead of
 //                  interrupting it.
-template <bool VISC, int NCW, int NA, int NBR>
+template <bool VISC, int NCW, int NA, int NBR, bool STATS = false>
 __global__ void __launch_bounds__((NCW + 4) * 32, 1) stage_fused(const __grid_constant__ TileGeom G, const __grid_constant__ StageArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int NNW = 3;                       // node warps
@@ -236,11 +239,12 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1) stage_fused(const __grid_co
     // that they cost no registers
     unsigned long long* st = reinterpret_cast<unsigned long long*>(smem + 176);   // barriers end at byte 160 (NA = 4), C starts at 384
     static_assert(176 + 8 * ST_COUNT <= 384, "the cycle counters must end before C");
-    if (threadIdx.x < ST_COUNT) st[threadIdx.x] = 0;
+    if (STATS && threadIdx.x < ST_COUNT) st[threadIdx.x] = 0;
     __syncthreads();
-    const bool stat = A.stats != nullptr && lane == 0 && (warp == A.stat_warp || warp == NCW || warp == NCW + 1);
+    // STATS is a template parameter: the production instantiation carries none of the counter code (a run-time flag cost 3 %)
+    const bool stat = STATS && A.stats != nullptr && lane == 0 && (warp == A.stat_warp || warp == NCW || warp == NCW + 1);
     auto waitc = [&](unsigned bar, unsigned par, int slot) {   // wait, with the cycles charged to st[slot] on the reporting lanes
-        if (A.stats == nullptr) { ptx::mbar_wait(bar, par); return; }
+        if (!STATS) { ptx::mbar_wait(bar, par); return; }
         const long long t0 = clock64();                         // before the first attempt: try_wait itself may park the warp
         ptx::mbar_wait(bar, par);
         if (stat) st[slot] += (unsigned long long)(clock64() - t0);
@@ -365,7 +369,7 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1) stage_fused(const __grid_co
 #if CFDB_NODE_NB
                 if (node_finish_nb(n, acc, u, m, gam, fl, A.WXa, A.WYa, A.bc, A.rk_fact, A.FR, A.U1, A.RHO, A.VELX, A.VELY, A.Ea, A.Pa,
                                    A.Ta, A.RMACH)) {
-                    atomicAdd(&g_fallbacks[FB_STAGE_NODE], 1ull);
+                    if (CFDB_FB_COUNT) atomicAdd(&g_fallbacks[FB_STAGE_NODE], 1ull);
                     node_finish_plain(n, acc, u, m, gam, fl, A.WXa, A.WYa, A.bc, A.rk_fact, A.FR, A.U1, A.RHO, A.VELX, A.VELY, A.Ea,
                                       A.Pa, A.Ta, A.RMACH);
                 }
@@ -392,9 +396,12 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1) stage_fused(const __grid_co
     const double dtl_uniform = G.nfields == 12 ? 0.0 : *A.dtl_sc;
     const int k = threadIdx.x;   // element position in the tile
     int t = blockIdx.x;
-    long long loop_c0 = 0;
-    unsigned long long loop_n0 = 0;
-    if (stat) { loop_c0 = clock64(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(loop_n0)); }
+    if (stat) {   // start stamps live in the shared-memory counters, not in registers the element arithmetic needs
+        unsigned long long n0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(n0));
+        st[ST_LOOP_CYC] = (unsigned long long)clock64();
+        st[ST_LOOP_NS] = n0;
+    }
     for (int it = 0; it < my_tiles; ++it, t += gridDim.x) {
         const int sa = it % NA, sb = it % NBR, c = it & 1;
         const unsigned char* ab = smem + G.off_a + (size_t)sa * G.a_bytes;
@@ -409,7 +416,7 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1) stage_fused(const __grid_co
             double* C = Cbase + (size_t)c * 12 * TE;
             // branch-free divisions (exact.cuh) first; the plain form only if an operand left their range
             if (fused_elem<VISC, true>(G, A, ab, bb, C, k, nint, dtl_uniform)) {
-                atomicAdd(&g_fallbacks[FB_STAGE_ELEM], 1ull);
+                if (CFDB_FB_COUNT) atomicAdd(&g_fallbacks[FB_STAGE_ELEM], 1ull);
                 fused_elem_plain<VISC>(G, A, ab, bb, C, k, nint, dtl_uniform);
             }
         }
@@ -426,8 +433,8 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1) stage_fused(const __grid_co
     if (stat) {
         unsigned long long n1;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(n1));
-        atomicAdd(A.stats + ST_LOOP_CYC, (unsigned long long)(clock64() - loop_c0));   // the reporting warp's whole tile loop: cycles and ns,
-        atomicAdd(A.stats + ST_LOOP_NS, n1 - loop_n0);                                  // i.e. the SM clock the kernel actually ran at
+        atomicAdd(A.stats + ST_LOOP_CYC, (unsigned long long)clock64() - st[ST_LOOP_CYC]);   // the reporting warp's whole tile loop: cycles and ns,
+        atomicAdd(A.stats + ST_LOOP_NS, n1 - st[ST_LOOP_NS]);                                 // i.e. the SM clock the kernel actually ran at
         atomicAdd(A.stats + ST_E, st[ST_E]);
         atomicAdd(A.stats + ST_ARRIVE, st[ST_ARRIVE]);
         atomicAdd(A.stats + ST_WAIT_IN, st[ST_WAIT_IN]);
