@@ -133,10 +133,10 @@ enum { ST_E = 0, ST_N, ST_WAIT_IN, ST_WAIT_CE, ST_WAIT_CF, ST_LD_WB, ST_LD_WS, S
 // stream) -- the twelve contributions to C (and to the global staging buffer EC for tile-boundary nodes, finished by
 // node_update afterwards).  Stores happen as the values become ready; when the fast-path flag comes back raised the caller
 // runs the plain form, whose stores (same thread, same addresses, program order) replace these.
-template <bool VISC, bool NB>
+template <bool VISC, bool NB, int TE>
 __device__ __forceinline__ unsigned fused_elem(const TileGeom& G, const StageArgs& A, const unsigned char* sa, const unsigned char* sbm,
                                                double* __restrict__ C, int k, int nint, double dtl_uniform) {
-    const int TE = G.TE;
+    // TE is a compile-time constant (32 x element warps): every stream operand is then base + immediate
     const unsigned short* lnode = reinterpret_cast<const unsigned short*>(sa + G.a_static + G.off_lnode);
     const int ln[3] = {lnode[k], lnode[TE + k], lnode[2 * TE + k]};
     const double* ut = reinterpret_cast<const double*>(sa + G.a_u);
@@ -178,10 +178,10 @@ __device__ __forceinline__ unsigned fused_elem(const TileGeom& G, const StageArg
     }
     return bad;
 }
-template <bool VISC>
+template <bool VISC, int TE>
 __device__ __noinline__ void fused_elem_plain(const TileGeom& G, const StageArgs& A, const unsigned char* sa, const unsigned char* sbm,
                                               double* __restrict__ C, int k, int nint, double dtl_uniform) {
-    fused_elem<VISC, false>(G, A, sa, sbm, C, k, nint, dtl_uniform);
+    fused_elem<VISC, false, TE>(G, A, sa, sbm, C, k, nint, dtl_uniform);
 }
 
 // Warp roles.  NCW element warps (a multiple of 4) + one auxiliary warpgroup: warp NCW is the loader, warps NCW+1..NCW+3 are
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1) stage_fused(const __grid_co
         }
         ptx::fence_barrier_init();
     }
-    const int TE = G.TE;
+    constexpr int TE = 32 * NCW;   // == G.TE (checked on the host)
     // optional cycle counters (CFDB_STAGE_STATS): element warp 0, node warp 0 and the loader report; kept in shared memory so
     // that they cost no registers
     unsigned long long* st = reinterpret_cast<unsigned long long*>(smem + 176);   // barriers end at byte 160 (NA = 4), C starts at 384
@@ -379,10 +379,7 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1) stage_fused(const __grid_co
 #endif
             }
             __syncwarp();
-            if (lane == 0) {
-                ptx::mbar_arrive(cempty0 + 8 * cj);
-                ptx::mbar_arrive(aempty0 + 8 * sa);
-            }
+            if (lane < 2) ptx::mbar_arrive(lane == 0 ? cempty0 + 8 * cj : aempty0 + 8 * sa);
             if (stat) st[ST_N] += (unsigned long long)(clock64() - t0);
         }
         if (stat) {
@@ -415,19 +412,16 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1) stage_fused(const __grid_co
         if (k < ne) {
             double* C = Cbase + (size_t)c * 12 * TE;
             // branch-free divisions (exact.cuh) first; the plain form only if an operand left their range
-            if (fused_elem<VISC, true>(G, A, ab, bb, C, k, nint, dtl_uniform)) {
+            if (fused_elem<VISC, true, TE>(G, A, ab, bb, C, k, nint, dtl_uniform)) {
                 if (CFDB_FB_COUNT) atomicAdd(&g_fallbacks[FB_STAGE_ELEM], 1ull);
-                fused_elem_plain<VISC>(G, A, ab, bb, C, k, nint, dtl_uniform);
+                fused_elem_plain<VISC, TE>(G, A, ab, bb, C, k, nint, dtl_uniform);
             }
         }
         const long long t1 = stat ? clock64() : 0;
         if (stat) st[ST_E] += (unsigned long long)(t1 - t0);
         __syncwarp();
-        if (lane == 0) {
-            ptx::mbar_arrive(cfull0 + 8 * c);
-            ptx::mbar_arrive(bempty0 + 8 * sb);
-            ptx::mbar_arrive(aempty0 + 8 * sa);
-        }
+        if (lane < 3)   // three arrivals as ONE instruction: lanes 0..2 each on their own barrier
+            ptx::mbar_arrive(lane == 0 ? cfull0 + 8 * c : lane == 1 ? bempty0 + 8 * sb : aempty0 + 8 * sa);
         if (stat) st[ST_ARRIVE] += (unsigned long long)(clock64() - t1);
     }
     if (stat) {
