@@ -1119,7 +1119,10 @@ __global__ void __launch_bounds__(CFDB_NODE_BS, CFDB_NODE_MINB) node_update(int 
 // Tile-boundary nodes of the fused stage (stage_fused.cuh): node bnodes[i] owns records bn_ptr[i] .. bn_ptr[i+1] of the
 // boundary staging buffer, written by the element warps in the node's summation order (ascending original element id) --
 // the index loads are coalesced, the records of a node are one contiguous run, and the nodal chain is node_update's.
-__global__ void __launch_bounds__(CFDB_NODE_BS, CFDB_NODE_MINB) boundary_update(int nb, const int* __restrict__ bnodes, const int* __restrict__ bn_ptr,
+#ifndef CFDB_BND_MINB
+#define CFDB_BND_MINB 6     // 80 registers: eight 32-byte records in flight per thread
+#endif
+__global__ void __launch_bounds__(CFDB_NODE_BS, CFDB_BND_MINB) boundary_update(int nb, const int* __restrict__ bnodes, const int* __restrict__ bn_ptr,
                                                     const double* __restrict__ ECB, const double* __restrict__ U,
                                                     const double* __restrict__ M, CF GAMM, const double* __restrict__ WXa,
                                                     const double* __restrict__ WYa, const unsigned char* __restrict__ bcflag,
@@ -1130,11 +1133,19 @@ __global__ void __launch_bounds__(CFDB_NODE_BS, CFDB_NODE_MINB) boundary_update(
     const int n = bnodes[i];
     const int k0 = bn_ptr[i], k1 = bn_ptr[i + 1];
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int k = k0; k < k1; ++k) {
-        double c[4];
-        ld4(ECB + 4 * (size_t)k, c);
+    // eight records at a time: all requested before the first add (the kernel is bound by the latency of these loads), then
+    // added in the run's order
+#pragma unroll 1
+    for (int k = k0; k < k1; k += 8) {
+        double c[8][4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) acc[q] = acc[q] + c[q];
+        for (int r = 0; r < 8; ++r) ld4(ECB + 4 * (size_t)min(k + r, k1 - 1), c[r]);
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            if (k + r < k1) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[q] = acc[q] + c[r][q];
+            }
     }
     st4(RHS + 4 * (size_t)n, acc);
     node_finish(n, acc, U, M, GAMM, WXa, WYa, bcflag, bc, rk_fact, FR, U1, RHO, VELX, VELY, Ea, Pa, Ta, RMACH);

@@ -251,3 +251,20 @@ def test_spmv_row_runs_of_any_length(cases):
     y_o = np.zeros(P)
     orclib.lib().orc_spmv(A, idx, rowptr, v, y_o, P)
     assert_bit_equal(g.spmv(A, idx, rowptr, v), y_o, "spmv with mixed row lengths")
+
+
+def test_forces_over_more_body_edges_than_one_chunk():
+    """k::forces evaluates the edge terms of a body set 512 at a time and adds them in list order (meshMove.f90:171-192):
+    a body with 1 300 edges (three chunks, the last one partial), two moving-mesh steps, forces and moment bit for bit."""
+    from cfd_b200 import deck, meshgen
+
+    lc = deck.load(meshgen.ale_body(nt=1300, nr=4))
+    g, o = _pair(lc)
+    _perturb(lc, g, o, amp=0.05)
+    g.step(2)
+    o.step(2)
+    for k in ("FX", "FY", "RM"):
+        assert_bit_equal(g.get(k), o.get(k), k)
+    assert abs(o.get("FX")[0]) > 0
+    for k in ("U", "X", "W_X"):
+        assert_bit_equal(g.get(k), o.get(k), k)
