@@ -188,9 +188,11 @@ struct cfdb_ctx {
     DBuf<double> geo;
     // cfdb_step_streamed: copy streams, device-side staging on both sides, and the events that order them
     cudaStream_t st_in = nullptr, st_out = nullptr;
-    cudaEvent_t ev_in_done = nullptr, ev_in_used = nullptr, ev_step_done = nullptr, ev_out_done = nullptr;
-    bool streamed_any = false;
-    DBuf<double> sin_U, sin_T, sin_VX, sin_VY, sout_U, sout_T, sout_VX, sout_VY, sout_N;
+    // two sets of device staging (call k uses set k & 1): neither the upload of call k+1 nor the staging of step k's results
+    // ever waits for the transfer of the neighbouring call
+    cudaEvent_t ev_in_done = nullptr, ev_step_done = nullptr, ev_in_used[2] = {nullptr, nullptr}, ev_out_done[2] = {nullptr, nullptr};
+    long streamed_calls = 0;
+    DBuf<double> sin[2], sout[2];   // [U(4P) | T(P) | VEL_X(P) | VEL_Y(P)] (+ 8 norms on the way out)
     // multi-GPU (one rank per context)
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
@@ -717,8 +719,8 @@ extern "C" void cfdb_destroy(cfdb_ctx* c) {
     for (int i = 0; i < 2; ++i) if (c->gexec[i]) cudaGraphExecDestroy(c->gexec[i]);
     if (c->st_in) { cudaStreamSynchronize(c->st_in); cudaStreamDestroy(c->st_in); }
     if (c->st_out) { cudaStreamSynchronize(c->st_out); cudaStreamDestroy(c->st_out); }
-    for (auto e : {c->ev_in_done, c->ev_in_used, c->ev_step_done, c->ev_out_done}) if (e) cudaEventDestroy(e);
-    for (auto* d : {&c->sin_U, &c->sin_T, &c->sin_VX, &c->sin_VY, &c->sout_U, &c->sout_T, &c->sout_VX, &c->sout_VY, &c->sout_N}) d->release();
+    for (auto e : {c->ev_in_done, c->ev_step_done, c->ev_in_used[0], c->ev_in_used[1], c->ev_out_done[0], c->ev_out_done[1]}) if (e) cudaEventDestroy(e);
+    for (auto* d : {&c->sin[0], &c->sin[1], &c->sout[0], &c->sout[1]}) d->release();
     if (c->comm) ncclCommDestroy(c->comm);
     c->send_idx.release(); c->recv_idx.release(); c->sendbuf.release(); c->recvbuf.release(); c->redG.release();
     for (auto* d : {&c->inp, &c->d_esup2, &c->eslot, &c->d_lap_idx, &c->d_lap_rowptr, &c->wall, &c->wn_node, &c->wn_ptr,
@@ -1616,10 +1618,12 @@ static int streamed_setup(cfdb_ctx* c) {
     const size_t P = c->npoin;
     CK(cudaStreamCreateWithFlags(&c->st_in, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->st_out, cudaStreamNonBlocking));
-    for (auto* e : {&c->ev_in_done, &c->ev_in_used, &c->ev_step_done, &c->ev_out_done}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
-    for (auto* d : {&c->sin_U, &c->sout_U}) TRY(d->alloc(4 * P));
-    for (auto* d : {&c->sin_T, &c->sin_VX, &c->sin_VY, &c->sout_T, &c->sout_VX, &c->sout_VY}) TRY(d->alloc(P));
-    TRY(c->sout_N.alloc(8));
+    for (auto* e : {&c->ev_in_done, &c->ev_step_done, &c->ev_in_used[0], &c->ev_in_used[1], &c->ev_out_done[0], &c->ev_out_done[1]})
+        CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    for (int s = 0; s < 2; ++s) {
+        TRY(c->sin[s].alloc(7 * P));
+        TRY(c->sout[s].alloc(7 * P + 8));
+    }
     return 0;
 }
 extern "C" int cfdb_step_streamed(cfdb_ctx* c, const double* in_U, const double* in_T, const double* in_VEL_X, const double* in_VEL_Y,
@@ -1627,42 +1631,45 @@ extern "C" int cfdb_step_streamed(cfdb_ctx* c, const double* in_U, const double*
     CK(cudaSetDevice(c->device));
     TRY(streamed_setup(c));
     const size_t P = c->npoin, B = sizeof(double);
-    // 1. upload into staging (waits until the previous call's staging has been consumed)
-    if (c->streamed_any) CK(cudaStreamWaitEvent(c->st_in, c->ev_in_used, 0));
-    if (in_U) CK(cudaMemcpyAsync(c->sin_U.p, in_U, 4 * P * B, cudaMemcpyHostToDevice, c->st_in));
-    if (in_T) CK(cudaMemcpyAsync(c->sin_T.p, in_T, P * B, cudaMemcpyHostToDevice, c->st_in));
-    if (in_VEL_X) CK(cudaMemcpyAsync(c->sin_VX.p, in_VEL_X, P * B, cudaMemcpyHostToDevice, c->st_in));
-    if (in_VEL_Y) CK(cudaMemcpyAsync(c->sin_VY.p, in_VEL_Y, P * B, cudaMemcpyHostToDevice, c->st_in));
+    const int set = (int)(c->streamed_calls & 1);
+    const bool reuse = c->streamed_calls >= 2;     // this set was used two calls ago
+    double *si = c->sin[set].p, *so = c->sout[set].p;
+    // 1. upload into this call's staging set (waits until the call before last has consumed it)
+    if (reuse) CK(cudaStreamWaitEvent(c->st_in, c->ev_in_used[set], 0));
+    if (in_U) CK(cudaMemcpyAsync(si, in_U, 4 * P * B, cudaMemcpyHostToDevice, c->st_in));
+    if (in_T) CK(cudaMemcpyAsync(si + 4 * P, in_T, P * B, cudaMemcpyHostToDevice, c->st_in));
+    if (in_VEL_X) CK(cudaMemcpyAsync(si + 5 * P, in_VEL_X, P * B, cudaMemcpyHostToDevice, c->st_in));
+    if (in_VEL_Y) CK(cudaMemcpyAsync(si + 6 * P, in_VEL_Y, P * B, cudaMemcpyHostToDevice, c->st_in));
     CK(cudaEventRecord(c->ev_in_done, c->st_in));
     // 2. compute stream: staging -> state, the step, state -> staging
     CK(cudaStreamWaitEvent(c->st, c->ev_in_done, 0));
-    if (in_U) CK(cudaMemcpyAsync(c->U.p, c->sin_U.p, 4 * P * B, cudaMemcpyDeviceToDevice, c->st));
-    if (in_T) TRY(col_from_plain(c, c->T, c->sin_T.p, P));
-    if (in_VEL_X) TRY(col_from_plain(c, c->VEL_X, c->sin_VX.p, P));
-    if (in_VEL_Y) TRY(col_from_plain(c, c->VEL_Y, c->sin_VY.p, P));
-    CK(cudaEventRecord(c->ev_in_used, c->st));
+    if (in_U) CK(cudaMemcpyAsync(c->U.p, si, 4 * P * B, cudaMemcpyDeviceToDevice, c->st));
+    if (in_T) TRY(col_from_plain(c, c->T, si + 4 * P, P));
+    if (in_VEL_X) TRY(col_from_plain(c, c->VEL_X, si + 5 * P, P));
+    if (in_VEL_Y) TRY(col_from_plain(c, c->VEL_Y, si + 6 * P, P));
+    CK(cudaEventRecord(c->ev_in_used[set], c->st));
     TRY(step_once(c));
-    if (c->streamed_any) CK(cudaStreamWaitEvent(c->st, c->ev_out_done, 0));   // the previous download has left the staging
+    if (reuse) CK(cudaStreamWaitEvent(c->st, c->ev_out_done[set], 0));   // the download of the call before last has left this set
     if (out_norms) {   // ER, ERR of this step (ns2DComp.ALE.f90:191-197): after the swap U1.p holds the state the step started from
         long m = ((long)c->n_owned + 4095) / 4096;
         LAUNCH(K_NORMS, k::norm_chunks, (int)std::min<long>(m, 148 * 8), 256, (long)c->n_owned, c->U1.p, c->U.p, c->redA.p);
         TRY(reduce_levels(c, 8, m, 0));
-        CK(cudaMemcpyAsync(c->sout_N.p, c->sc->red, 8 * B, cudaMemcpyDeviceToDevice, c->st));
+        CK(cudaMemcpyAsync(so + 7 * P, c->sc->red, 8 * B, cudaMemcpyDeviceToDevice, c->st));
     }
-    if (out_U) CK(cudaMemcpyAsync(c->sout_U.p, c->U.p, 4 * P * B, cudaMemcpyDeviceToDevice, c->st));
-    if (out_T) TRY(col_to_plain(c, c->T, c->sout_T.p, P));
-    if (out_VEL_X) TRY(col_to_plain(c, c->VEL_X, c->sout_VX.p, P));
-    if (out_VEL_Y) TRY(col_to_plain(c, c->VEL_Y, c->sout_VY.p, P));
+    if (out_U) CK(cudaMemcpyAsync(so, c->U.p, 4 * P * B, cudaMemcpyDeviceToDevice, c->st));
+    if (out_T) TRY(col_to_plain(c, c->T, so + 4 * P, P));
+    if (out_VEL_X) TRY(col_to_plain(c, c->VEL_X, so + 5 * P, P));
+    if (out_VEL_Y) TRY(col_to_plain(c, c->VEL_Y, so + 6 * P, P));
     CK(cudaEventRecord(c->ev_step_done, c->st));
     // 3. download
     CK(cudaStreamWaitEvent(c->st_out, c->ev_step_done, 0));
-    if (out_U) CK(cudaMemcpyAsync(out_U, c->sout_U.p, 4 * P * B, cudaMemcpyDeviceToHost, c->st_out));
-    if (out_T) CK(cudaMemcpyAsync(out_T, c->sout_T.p, P * B, cudaMemcpyDeviceToHost, c->st_out));
-    if (out_VEL_X) CK(cudaMemcpyAsync(out_VEL_X, c->sout_VX.p, P * B, cudaMemcpyDeviceToHost, c->st_out));
-    if (out_VEL_Y) CK(cudaMemcpyAsync(out_VEL_Y, c->sout_VY.p, P * B, cudaMemcpyDeviceToHost, c->st_out));
-    if (out_norms) CK(cudaMemcpyAsync(out_norms, c->sout_N.p, 8 * B, cudaMemcpyDeviceToHost, c->st_out));
-    CK(cudaEventRecord(c->ev_out_done, c->st_out));
-    c->streamed_any = true;
+    if (out_U) CK(cudaMemcpyAsync(out_U, so, 4 * P * B, cudaMemcpyDeviceToHost, c->st_out));
+    if (out_T) CK(cudaMemcpyAsync(out_T, so + 4 * P, P * B, cudaMemcpyDeviceToHost, c->st_out));
+    if (out_VEL_X) CK(cudaMemcpyAsync(out_VEL_X, so + 5 * P, P * B, cudaMemcpyDeviceToHost, c->st_out));
+    if (out_VEL_Y) CK(cudaMemcpyAsync(out_VEL_Y, so + 6 * P, P * B, cudaMemcpyDeviceToHost, c->st_out));
+    if (out_norms) CK(cudaMemcpyAsync(out_norms, so + 7 * P, 8 * B, cudaMemcpyDeviceToHost, c->st_out));
+    CK(cudaEventRecord(c->ev_out_done[set], c->st_out));
+    c->streamed_calls++;
     return 0;
 }
 extern "C" int cfdb_streamed_wait(cfdb_ctx* c) {
