@@ -225,7 +225,8 @@ inline void build_tiling(const int32_t* inpoel, int nelem, int npoin, const doub
     T.ntiles = nt;
     // interior tile of every node (-1: boundary)
     vector<int32_t> owner((size_t)npoin, -1);
-    size_t ninterior = 0;
+    long ninterior = 0;
+#pragma omp parallel for schedule(static) reduction(+ : ninterior)
     for (int n = 0; n < npoin; ++n) {
         int k0 = esup2[n], k1 = esup2[n + 1];
         if (k0 == k1) continue;
@@ -246,36 +247,36 @@ inline void build_tiling(const int32_t* inpoel, int nelem, int npoin, const doub
             T.bn_ptr.push_back(T.bn_ptr.back() + (esup2[n + 1] - esup2[n]));
         }
     T.interior_fraction = npoin ? (double)ninterior / npoin : 0.0;
-    // pass 1: per-tile node lists (interior ascending, then the rest ascending) and the section sizes
-    vector<int32_t> stamp((size_t)npoin, -1), lidx((size_t)npoin, 0);
-    vector<int32_t> tn_ptr((size_t)nt + 1, 0), tn_nint((size_t)nt, 0), tn_nslot((size_t)nt, 0);
-    vector<int32_t> tn_nodes;
-    tn_nodes.reserve((size_t)(0.7 * E) + 1024);
-    vector<int32_t> a, b;
-    int ntn_max = 0, nint_max = 0, nslot_max = 0, nbd_max = 0;
-    for (int t = 0; t < nt; ++t) {
+    // The tiles are independent of each other: both passes run over them in parallel (OpenMP).  A tile's node lists -- its
+    // interior nodes ascending, then the others ascending -- come from sorting its own <= 3*TE vertex ids, so no mesh-sized
+    // scratch array is shared between tiles.
+    auto tile_nodes = [&](int t, vector<int32_t>& a, vector<int32_t>& b, vector<int32_t>& all) {
         size_t p0 = (size_t)t * TE, p1 = std::min(E, p0 + TE);
-        a.clear(); b.clear();
+        all.clear();
         for (size_t p = p0; p < p1; ++p) {
             const int32_t* el = inpoel + 3 * (size_t)T.i2e[p];
-            for (int i = 0; i < 3; ++i) {
-                int n = el[i] - 1;
-                if (stamp[n] != t) { stamp[n] = t; (owner[n] == t ? a : b).push_back(n); }
-            }
+            all.push_back(el[0] - 1); all.push_back(el[1] - 1); all.push_back(el[2] - 1);
         }
-        std::sort(a.begin(), a.end());
-        std::sort(b.begin(), b.end());
-        int ns = 0;
-        for (int n : a) ns += esup2[n + 1] - esup2[n];
-        tn_nint[t] = (int)a.size();
-        tn_nslot[t] = ns;
-        tn_nodes.insert(tn_nodes.end(), a.begin(), a.end());
-        tn_nodes.insert(tn_nodes.end(), b.begin(), b.end());
-        tn_ptr[t + 1] = (int32_t)tn_nodes.size();
-        ntn_max = std::max(ntn_max, (int)(a.size() + b.size()));
-        nint_max = std::max(nint_max, (int)a.size());
-        nslot_max = std::max(nslot_max, ns);
-        nbd_max = std::max(nbd_max, (int)b.size());
+        std::sort(all.begin(), all.end());
+        all.erase(std::unique(all.begin(), all.end()), all.end());
+        a.clear(); b.clear();
+        for (int n : all) (owner[n] == t ? a : b).push_back(n);
+    };
+    // pass 1: the section sizes
+    int ntn_max = 0, nint_max = 0, nslot_max = 0, nbd_max = 0;
+#pragma omp parallel
+    {
+        vector<int32_t> a, b, all;
+#pragma omp for schedule(dynamic, 64) reduction(max : ntn_max, nint_max, nslot_max, nbd_max)
+        for (int t = 0; t < nt; ++t) {
+            tile_nodes(t, a, b, all);
+            int ns = 0;
+            for (int n : a) ns += esup2[n + 1] - esup2[n];
+            ntn_max = std::max(ntn_max, (int)(a.size() + b.size()));
+            nint_max = std::max(nint_max, (int)a.size());
+            nslot_max = std::max(nslot_max, ns);
+            nbd_max = std::max(nbd_max, (int)b.size());
+        }
     }
     auto up16 = [](int v) { return (v + 15) & ~15; };
     TileLayout& L = T.L;
@@ -291,50 +292,59 @@ inline void build_tiling(const int32_t* inpoel, int nelem, int npoin, const doub
     L.tb_bytes = up16(L.off_bbase + nbd_max * 4);
     // pass 2: fill the blocks
     T.blocks.assign((size_t)nt * L.tb_bytes, 0);
-    for (int t = 0; t < nt; ++t) {
-        uint8_t* blk = T.blocks.data() + (size_t)t * L.tb_bytes;
-        int32_t* hdr = reinterpret_cast<int32_t*>(blk);
-        uint16_t* lnode = reinterpret_cast<uint16_t*>(blk + L.off_lnode);
-        int32_t* tnode = reinterpret_cast<int32_t*>(blk + L.off_tnode);
-        uint16_t* nptr = reinterpret_cast<uint16_t*>(blk + L.off_nptr);
-        uint16_t* slots = reinterpret_cast<uint16_t*>(blk + L.off_slots);
-        uint8_t* bcf = blk + L.off_bcf;
-        size_t p0 = (size_t)t * TE, p1 = std::min(E, p0 + TE);
-        const int ntn = tn_ptr[t + 1] - tn_ptr[t], nint = tn_nint[t];
-        hdr[0] = (int32_t)(p1 - p0); hdr[1] = ntn; hdr[2] = nint; hdr[3] = 0;
-        uint8_t* brank = blk + L.off_brank;
-        uint32_t* bbase = reinterpret_cast<uint32_t*>(blk + L.off_bbase);
-        for (int j = 0; j < ntn; ++j) {
-            int n = tn_nodes[(size_t)tn_ptr[t] + j];
-            tnode[j] = n;
-            lidx[n] = j;
-        }
-        for (size_t p = p0; p < p1; ++p) {
-            const int32_t* el = inpoel + 3 * (size_t)T.i2e[p];
-            for (int i = 0; i < 3; ++i) {
-                const int n = el[i] - 1;
-                lnode[(size_t)i * TE + (p - p0)] = (uint16_t)lidx[n];
-                if (bpos[n] >= 0) {   // rank of this element among the node's elements (the list is in ascending original id)
-                    int k = esup2[n];
-                    while (eslot[k] != 3 * T.i2e[p] + i) ++k;
-                    if (k - esup2[n] > 255) T.rank_overflow = true;
-                    brank[(size_t)i * TE + (p - p0)] = (uint8_t)(k - esup2[n]);
+    bool overflow = false;
+#pragma omp parallel
+    {
+        vector<int32_t> a, b, all;
+#pragma omp for schedule(dynamic, 64) reduction(|| : overflow)
+        for (int t = 0; t < nt; ++t) {
+            tile_nodes(t, a, b, all);
+            uint8_t* blk = T.blocks.data() + (size_t)t * L.tb_bytes;
+            int32_t* hdr = reinterpret_cast<int32_t*>(blk);
+            uint16_t* lnode = reinterpret_cast<uint16_t*>(blk + L.off_lnode);
+            int32_t* tnode = reinterpret_cast<int32_t*>(blk + L.off_tnode);
+            uint16_t* nptr = reinterpret_cast<uint16_t*>(blk + L.off_nptr);
+            uint16_t* slots = reinterpret_cast<uint16_t*>(blk + L.off_slots);
+            uint8_t* bcf = blk + L.off_bcf;
+            uint8_t* brank = blk + L.off_brank;
+            uint32_t* bbase = reinterpret_cast<uint32_t*>(blk + L.off_bbase);
+            size_t p0 = (size_t)t * TE, p1 = std::min(E, p0 + TE);
+            const int nint = (int)a.size(), ntn = nint + (int)b.size();
+            hdr[0] = (int32_t)(p1 - p0); hdr[1] = ntn; hdr[2] = nint; hdr[3] = 0;
+            for (int j = 0; j < nint; ++j) tnode[j] = a[j];
+            for (int j = nint; j < ntn; ++j) tnode[j] = b[j - nint];
+            auto local = [&](int n) -> int {      // tile-local index of node n: position in a (interior) or nint + position in b
+                if (owner[n] == t) return (int)(std::lower_bound(a.begin(), a.end(), n) - a.begin());
+                return nint + (int)(std::lower_bound(b.begin(), b.end(), n) - b.begin());
+            };
+            for (size_t p = p0; p < p1; ++p) {
+                const int32_t* el = inpoel + 3 * (size_t)T.i2e[p];
+                for (int i = 0; i < 3; ++i) {
+                    const int n = el[i] - 1;
+                    lnode[(size_t)i * TE + (p - p0)] = (uint16_t)local(n);
+                    if (bpos[n] >= 0) {   // rank of this element among the node's elements (the list is in ascending original id)
+                        int k = esup2[n];
+                        while (eslot[k] != 3 * T.i2e[p] + i) ++k;
+                        if (k - esup2[n] > 255) overflow = true;
+                        brank[(size_t)i * TE + (p - p0)] = (uint8_t)(k - esup2[n]);
+                    }
                 }
             }
-        }
-        int q = 0;
-        for (int j = 0; j < nint; ++j) {
-            int n = tnode[j];
-            nptr[j] = (uint16_t)q;
-            for (int k = esup2[n]; k < esup2[n + 1]; ++k) {
-                int pos = T.e2i[esup1[k] - 1] - (int)p0, ln = eslot[k] % 3;
-                slots[q++] = (uint16_t)(4 * ln * TE + pos);
+            int q = 0;
+            for (int j = 0; j < nint; ++j) {
+                int n = tnode[j];
+                nptr[j] = (uint16_t)q;
+                for (int k = esup2[n]; k < esup2[n + 1]; ++k) {
+                    int pos = T.e2i[esup1[k] - 1] - (int)p0, ln = eslot[k] % 3;
+                    slots[q++] = (uint16_t)(4 * ln * TE + pos);
+                }
+                bcf[j] = bcflag[n];
             }
-            bcf[j] = bcflag[n];
+            nptr[nint] = (uint16_t)q;
+            for (int jb = 0; jb < ntn - nint; ++jb) bbase[jb] = (uint32_t)T.bn_ptr[bpos[tnode[nint + jb]]];
         }
-        nptr[nint] = (uint16_t)q;
-        for (int jb = 0; jb < ntn - nint; ++jb) bbase[jb] = (uint32_t)T.bn_ptr[bpos[tnode[nint + jb]]];
     }
+    T.rank_overflow = overflow;
 }
 
 // last[i] = index of the last entry of list[] naming the same node as entry i ("last entry wins",
