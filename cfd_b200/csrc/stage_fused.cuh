@@ -213,15 +213,16 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1) stage_fused(const __grid_co
     constexpr int RE = (NCW == 12) ? CFDB_STAGE_RE : 112;   // registers per thread of an element warp after the hand-over
     constexpr int RAUX = (NCW == 12) ? 4 * 128 - 3 * CFDB_STAGE_RE : 32;  //                  ... of an auxiliary warp      (NCW*RE + 4*RAUX == (NCW+4) * launch registers)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // barriers (8 bytes each): astat[NA] static block landed (1 arrival + bytes); afull[NA] gathers landed (32 cp.async
-    // arrivals); aempty[NA] (NCW + NNW arrivals); bfull[NBR] (1 + bytes); bempty[NBR] (NCW); cfull[2] (NCW); cempty[2] (NNW)
+    // barriers (8 bytes each): astat[NA] static block landed (1 arrival + bytes); afull[NA] the tile's inputs landed (32 cp.async
+    // arrivals of the gathers + 1 arrival with the stream's bytes); aempty[NA] (NCW + NNW arrivals); bfull[NBR] (unused: the
+    // stream completes on afull); bempty[NBR] (NCW); cfull[2] (NCW); cempty[2] (NNW)
     const unsigned bar0 = ptx::smem_u32(smem);
     const unsigned astat0 = bar0, afull0 = astat0 + 8 * NA, aempty0 = afull0 + 8 * NA, bfull0 = aempty0 + 8 * NA,
                    bempty0 = bfull0 + 8 * NBR, cfull0 = bempty0 + 8 * NBR, cempty0 = cfull0 + 16;
     if (threadIdx.x == 0) {
         for (int s = 0; s < NA; ++s) {
             ptx::mbar_init(astat0 + 8 * s, 1);
-            ptx::mbar_init(afull0 + 8 * s, 32);
+            ptx::mbar_init(afull0 + 8 * s, 33);   // 32 cp.async arrivals (gathers) + the stream's expect-tx arrival
             ptx::mbar_init(aempty0 + 8 * s, NCW + NNW);
         }
         for (int s = 0; s < NBR; ++s) {
@@ -272,9 +273,9 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1) stage_fused(const __grid_co
                 const int sb = it % NBR;
                 waitc(bempty0 + 8 * sb, ((it / NBR) & 1) ^ 1, ST_LD_WB);
                 if (lane == 0) {
-                    ptx::mbar_arrive_expect_tx(bfull0 + 8 * sb, stream_bytes);
+                    ptx::mbar_arrive_expect_tx(afull0 + 8 * (it % NA), stream_bytes);   // the stream completes on the tile's inputs-landed barrier too
                     const size_t e0 = (size_t)t * TE;
-                    const unsigned fb = (unsigned)(TE * 8), dst = ptx::smem_u32(smem + G.off_b + (size_t)sb * G.b_bytes), bar = bfull0 + 8 * sb;
+                    const unsigned fb = (unsigned)(TE * 8), dst = ptx::smem_u32(smem + G.off_b + (size_t)sb * G.b_bytes), bar = afull0 + 8 * (it % NA);
 #pragma unroll 1
                     for (int f = 0; f < 7; ++f) ptx::bulk_g2s(dst + f * fb, A.geo + (size_t)f * A.Epad + e0, fb, bar);
                     ptx::bulk_g2s(dst + 7 * fb, A.shoc + e0, fb, bar);
@@ -404,7 +405,6 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1) stage_fused(const __grid_co
         const unsigned char* ab = smem + G.off_a + (size_t)sa * G.a_bytes;
         const unsigned char* bb = smem + G.off_b + (size_t)sb * G.b_bytes;
         waitc(afull0 + 8 * sa, (it / NA) & 1, ST_WAIT_IN);
-        waitc(bfull0 + 8 * sb, (it / NBR) & 1, ST_WAIT_IN);
         waitc(cempty0 + 8 * c, ((it >> 1) & 1) ^ 1, ST_WAIT_CE);   // node phase it-2 is done: C[c] is free
         const long long t0 = stat ? clock64() : 0;
         const int* hdr = reinterpret_cast<const int*>(ab + G.a_static);
