@@ -155,7 +155,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("case,world", [("square_visc", 2), ("channel", 3)])
+@pytest.mark.parametrize("case,world", [("square_visc", 2), ("channel", 3), ("channel_last_stage_only", 2)])
 def test_gloo_exchange_protocol_matches_undivided_oracle(case, world):
     port = _free_port()
     procs = []
