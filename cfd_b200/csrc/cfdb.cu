@@ -2505,6 +2505,10 @@ extern "C" int cfdb_tile_elements(const int32_t* inpoel, int32_t nelem, int32_t 
     vector<uint8_t> bcf((size_t)npoin, 0);
     topo::Tiling T;
     topo::build_tiling(inpoel, nelem, npoin, X, Y, esup1, esup2, eslot, bcf, TE, order, T);
+    if (!T.rank_overflow) {   // independent check of the summation schedule against the mesh (host_topology.h: check_tiling)
+        const long bad = topo::check_tiling(inpoel, nelem, npoin, esup1, esup2, eslot, T);
+        if (bad) return fail("cfdb_tile_elements: the tiling is inconsistent with the mesh (" + std::to_string(bad) + " violations)");
+    }
     if (i2e) std::copy(T.i2e.begin(), T.i2e.end(), i2e);
     if (stats) {
         stats[0] = T.interior_fraction; stats[1] = T.ntiles; stats[2] = T.L.ntn_max; stats[3] = T.L.nint_max;

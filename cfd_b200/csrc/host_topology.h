@@ -347,6 +347,68 @@ inline void build_tiling(const int32_t* inpoel, int nelem, int npoin, const doub
     T.rank_overflow = overflow;
 }
 
+// Independent check of a tiling against the mesh it was built from (host code, used by cfdb_tile_elements and the CPU tests):
+// every element sits in exactly one tile position; lnode names the element's own vertices; an interior node's slot list is
+// its element list in ascending ORIGINAL element id with the right local vertex; the boundary records bbase + brank map the
+// contributions of every tile-boundary node one-to-one onto its run bn_ptr[i] .. bn_ptr[i+1], in ascending original element id.
+// Returns the number of violations (0 = consistent).
+inline long check_tiling(const int32_t* inpoel, int nelem, int npoin, const vector<int32_t>& esup1, const vector<int32_t>& esup2,
+                         const vector<int32_t>& eslot, const Tiling& T) {
+    const TileLayout& L = T.L;
+    const int TE = L.TE;
+    long bad = 0;
+    vector<uint8_t> seen((size_t)nelem, 0);
+    for (size_t p = 0; p < (size_t)nelem; ++p) {
+        if (T.i2e[p] < 0 || T.i2e[p] >= nelem || seen[T.i2e[p]]++) ++bad;
+        else if (T.e2i[T.i2e[p]] != (int32_t)p) ++bad;
+    }
+    vector<int32_t> bpos((size_t)npoin, -1);
+    for (size_t i = 0; i < T.bnodes.size(); ++i) bpos[T.bnodes[i]] = (int32_t)i;
+    vector<uint8_t> rec_hit(T.bn_ptr.empty() ? 0 : (size_t)T.bn_ptr.back(), 0);
+    vector<uint8_t> node_done((size_t)npoin, 0);
+    for (int t = 0; t < T.ntiles; ++t) {
+        const uint8_t* blk = T.blocks.data() + (size_t)t * L.tb_bytes;
+        const int32_t* hdr = reinterpret_cast<const int32_t*>(blk);
+        const uint16_t* lnode = reinterpret_cast<const uint16_t*>(blk + L.off_lnode);
+        const int32_t* tnode = reinterpret_cast<const int32_t*>(blk + L.off_tnode);
+        const uint16_t* nptr = reinterpret_cast<const uint16_t*>(blk + L.off_nptr);
+        const uint16_t* slots = reinterpret_cast<const uint16_t*>(blk + L.off_slots);
+        const uint8_t* brank = blk + L.off_brank;
+        const uint32_t* bbase = reinterpret_cast<const uint32_t*>(blk + L.off_bbase);
+        const size_t p0 = (size_t)t * TE;
+        const int ne = hdr[0], ntn = hdr[1], nint = hdr[2];
+        if (ne != (int)std::min((size_t)TE, (size_t)nelem - p0) || nint > ntn || ntn > L.ntn_max) ++bad;
+        for (int k = 0; k < ne; ++k)
+            for (int i = 0; i < 3; ++i) {
+                const int ln = lnode[(size_t)i * TE + k];
+                const int n = inpoel[3 * (size_t)T.i2e[p0 + k] + i] - 1;
+                if (ln >= ntn || tnode[ln] != n) { ++bad; continue; }
+                if (ln >= nint) {   // tile-boundary node: its record
+                    if (bpos[n] < 0) { ++bad; continue; }
+                    const long rec = (long)bbase[ln - nint] + brank[(size_t)i * TE + k];
+                    const int k0 = T.bn_ptr[bpos[n]], k1 = T.bn_ptr[bpos[n] + 1];
+                    if (bbase[ln - nint] != (uint32_t)k0 || rec < k0 || rec >= k1 || rec_hit[rec]++) { ++bad; continue; }
+                    // record position = position of this (element, vertex) in the node's list
+                    if (eslot[esup2[n] + (rec - k0)] != 3 * T.i2e[p0 + k] + i) ++bad;
+                }
+            }
+        for (int j = 0; j < nint; ++j) {
+            const int n = tnode[j];
+            if (bpos[n] >= 0 || node_done[n]++) ++bad;
+            if (nptr[j + 1] - nptr[j] != esup2[n + 1] - esup2[n]) { ++bad; continue; }
+            for (int q = nptr[j], k = esup2[n]; q < nptr[j + 1]; ++q, ++k) {
+                const int ln = slots[q] / (4 * TE), pos = slots[q] % (4 * TE);
+                if (pos >= ne || ln > 2) { ++bad; continue; }
+                if (T.i2e[p0 + pos] != esup1[k] - 1 || eslot[k] != 3 * (esup1[k] - 1) + ln) ++bad;
+            }
+        }
+    }
+    for (uint8_t h : rec_hit) bad += h != 1;
+    for (int n = 0; n < npoin; ++n)
+        if ((bpos[n] >= 0) == (node_done[n] != 0)) ++bad;     // every node is interior to one tile XOR in the boundary list
+    return bad;
+}
+
 // last[i] = index of the last entry of list[] naming the same node as entry i ("last entry wins",
 // SURVEY.md B.2, for list-driven writes whose OpenMP order is undefined in the reference)
 inline void last_wins(const int32_t* list, int m, int npoin, vector<int32_t>& last) {

@@ -169,3 +169,21 @@ def test_tile_decomposition_of_the_fused_stage():
         os.environ["OMP_NUM_THREADS"] = old
     with pytest.raises(RuntimeError):
         capi.check(L.cfdb_tile_elements(lc.inpoel, lc.nelem, lc.npoin, lc.X, lc.Y, 100, 2, again, np.zeros(8)))
+
+
+@pytest.mark.parametrize("mesh", ["channel", "ale", "wedge"])
+def test_tile_schedule_is_consistent_with_the_mesh(mesh):
+    """cfdb_tile_elements runs host_topology.h: check_tiling on what build_tiling produced and fails on any violation: every
+    element in exactly one tile position, lnode naming the element's own vertices, an interior node's slot list = its element
+    list in ascending original element id, the boundary records a one-to-one map onto each tile-boundary node's run in the
+    same order.  Unstructured-looking meshes (O-mesh around a body, wedge, channel), three element orders, three tile sizes."""
+    from cfd_b200 import capi, deck, meshgen
+
+    raw = {"channel": lambda: meshgen.channel(nx=61, ny=21), "ale": lambda: meshgen.ale_body(nt=96, nr=24),
+           "wedge": lambda: meshgen.wedge(nx=61, ny=31)}[mesh]()
+    lc = deck.load(raw)
+    for TE in (64, 384, 512):
+        for order in (0, 1, 2):
+            st, i2e = np.zeros(8), np.zeros(lc.nelem, np.int32)
+            capi.check(capi.lib().cfdb_tile_elements(lc.inpoel, lc.nelem, lc.npoin, lc.X, lc.Y, TE, order, i2e, st))
+            assert st[1] == -(-lc.nelem // TE) and 0.0 <= st[0] <= 1.0
