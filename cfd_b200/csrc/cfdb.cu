@@ -508,6 +508,10 @@ static int build_stage_tiles(cfdb_ctx* c, const int32_t* inpoel, const double* X
     topo::build_tiling(inpoel, c->nelem, c->npoin, X, Y, esup1, esup2, eslot, c->h_bcflag, TE, order, T);
     if (T.L.nint_max > 65535 || 12 * TE > 65535) return fail("tile too large for 16-bit slots");
     if (T.rank_overflow) { c->tiles_ok = false; return 0; }   // a node with more than 256 elements: the two-kernel stage
+    if (getenv("CFDB_CHECK_TILES")) {   // independent check of the summation schedule against the mesh (host_topology.h)
+        const long bad = topo::check_tiling(inpoel, c->nelem, c->npoin, esup1, esup2, eslot, T);
+        if (bad) return fail("cfdb_create: the tiling is inconsistent with the mesh (" + std::to_string(bad) + " violations)");
+    }
     c->ntiles = T.ntiles;
     c->tile_ncw = TE / 32;
     c->tile_interior = T.interior_fraction;

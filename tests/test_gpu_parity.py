@@ -410,7 +410,7 @@ def test_operands_outside_the_fast_paths_take_the_plain_form(cases):
     assert pathological.check(lc, g, o) == 16
 
 
-@pytest.mark.parametrize("env", ["CFDB_NO_GRAPH=1", "CFDB_NO_FUSED=1", "CFDB_NO_PERM=1", "CFDB_TILE_TE=512", "CFDB_TILE_ORDER=morton", "CFDB_FUSED_VISC=1", "CFDB_ESTAB_MINB=3", "CFDB_ESTAB_MINB=5", "CFDB_HOST_TOPO=1"])
+@pytest.mark.parametrize("env", ["CFDB_NO_GRAPH=1", "CFDB_NO_FUSED=1", "CFDB_NO_PERM=1", "CFDB_TILE_TE=512", "CFDB_TILE_ORDER=morton", "CFDB_FUSED_VISC=1", "CFDB_ESTAB_MINB=3", "CFDB_ESTAB_MINB=5", "CFDB_HOST_TOPO=1", "CFDB_CHECK_TILES=1"])
 def test_optional_paths_bit_exact(env):
     """Every alternative code path kept in the library (stream launches instead of the step's CUDA graph, the two-kernel RK
     stage instead of the fused tile kernel, host-built topology) produces the same bits as the default."""
