@@ -187,3 +187,41 @@ def test_tile_schedule_is_consistent_with_the_mesh(mesh):
             st, i2e = np.zeros(8), np.zeros(lc.nelem, np.int32)
             capi.check(capi.lib().cfdb_tile_elements(lc.inpoel, lc.nelem, lc.npoin, lc.X, lc.Y, TE, order, i2e, st))
             assert st[1] == -(-lc.nelem // TE) and 0.0 <= st[0] <= 1.0
+
+
+def test_committed_bench_lines_follow_the_contract():
+    """The JSON lines committed under profiles/ (produced by bench.py on the GPU boxes) carry every key of the bench contract,
+    with self-consistent numbers."""
+    import json
+
+    def line(name):
+        with open(os.path.join(ROOT, "profiles", name)) as f:
+            return json.loads(f.read().strip().split("\n")[-1])
+
+    d = line("r2_bench_n1.json")
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "roofline", "cpu_baseline", "e2e", "clocks", "gpu_launches"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["dtype"] == "f64" and d["data"] == "synthetic" and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert "workload" in d["config"] and "model" not in d["config"]
+    E = d["config"]["elements_per_gpu"]
+    assert abs(d["value"] - E / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
+    r = d["roofline"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "traffic_source"):
+        assert k in r, k
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert abs(r["achieved"] - 220 * E / (r["launch_ms"] * 1e-3) / 1e9) < 1e-6 * r["achieved"]
+    assert r["traffic"] is not None and 0.9 < r["traffic"] / (220 * E) < 1.5          # measured DRAM bytes per stage vs algorithmic
+    c = d["cpu_baseline"]
+    assert c["kind"] in ("port", "reference") and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] < d["value"]
+    assert d["gpu_launches"] > 0 and d["clocks"]["samples"] > 0
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    for name, n in (("r2_bench_n2.json", 2), ("r2_bench_n4.json", 4), ("r2_bench_n8.json", 8)):
+        m = line(name)
+        assert m["n_gpus"] == n and m["multi_gpu_parity"] == "bit-exact" and m["scaling"] == "weak"
+        assert 0.9 < m["value"] / (n * d["value"]) <= 1.02                             # weak-scaling efficiency of the committed lines
+    ref = line("r2_bench_ref_n1.json")
+    assert ref["impl"] == "reference" and ref["metric"] == d["metric"] and ref["unit"] == d["unit"]
+    assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["value"] == ref["value"]
