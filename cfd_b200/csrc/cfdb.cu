@@ -486,11 +486,11 @@ static int ensure_host_topology(cfdb_ctx* c) {
 //   CFDB_TILE_TE=384|512 tile size (384 default)
 static int build_stage_tiles(cfdb_ctx* c, const int32_t* inpoel, const double* X, const double* Y) {
     const size_t E = c->nelem, P = c->npoin;
-    // TE = 32 x element warps (stage_fused.cuh): 12 element warps at 152 registers + 4 auxiliary warps at 56; 16 + 4 at
+    // TE = 32 x element warps (stage_fused.cuh): 12 element warps at 144 registers + 4 auxiliary warps at 80; 16 + 4 at
     // 112 / 32 is kept for experiments but needs more shared memory than an SM has once the mesh is large
     int TE = getenv("CFDB_TILE_TE") ? atoi(getenv("CFDB_TILE_TE")) : 384;
     if (TE != 384 && TE != 512) return fail("CFDB_TILE_TE must be 384 or 512");
-    // CFDB_TILE_ORDER=morton: the round-2 mid-way order (Z-curve runs), kept for A/B timing
+    // CFDB_TILE_ORDER=morton: runs of a Z-curve instead of recursive coordinate bisection, kept for A/B timing
     int order = getenv("CFDB_NO_PERM") ? topo::ORDER_FILE : topo::ORDER_RCB;
     if (order != topo::ORDER_FILE && getenv("CFDB_TILE_ORDER") && !strcmp(getenv("CFDB_TILE_ORDER"), "morton")) order = topo::ORDER_MORTON;
     const bool permute = order != topo::ORDER_FILE;

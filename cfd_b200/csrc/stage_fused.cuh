@@ -189,17 +189,17 @@ __device__ __noinline__ void fused_elem_plain(const TileGeom& G, const StageArgs
 //
 // Registers.  The register file is split over the four SM sub-partitions (16384 registers each, warps dealt round-robin), so
 // with 16 warps per CTA every sub-partition holds three element warps and one auxiliary warp, launched at 128 registers per
-// thread.  setmaxnreg then moves registers from the auxiliary warpgroup (80 each: two nodes per lane in flight) to the element
+// thread.  setmaxnreg then moves registers from the auxiliary warpgroup (80 each: eight contributions of a node in flight) to the element
 // warpgroups (144 each: the branch-free form of the element arithmetic runs without spills and its single-warp schedule is
 // within 40 % of the fp64 issue time, tools/sass_stalls.py).  3 x 144 + 80 = 4 x 128: what the element warps claim is exactly
 // what the auxiliary warpgroup released (the registers a warpgroup may claim come from its own CTA's pool).
 //
 // Pipeline (all hand-overs are mbarriers; no CTA-wide barrier in the steady state):
-//   loader       : stream(i) -> B ring [NBR slots]; gathers(i) (U, T, M, GAMM of the tile's nodes, addresses from the static
+//   loader       : stream(i) -> B ring [NBR slots] (completing on tile i's inputs-landed barrier); gathers(i) (U, T, M, GAMM of the tile's nodes, addresses from the static
 //                  block that landed earlier) -> A ring [NA slots]; static block of tile i+1 -> A ring, one tile ahead of its
 //                  gathers so that the two dependent round trips to HBM never sit on an element warp's path;
 //   element warps: E(i): 32 elements each from A(i), B(i) -> registers; wait until C[i&1] is free (node phase i-2 done: long
-//                  ago); C[i&1] <- contributions (+ EC for tile-boundary nodes); release B(i), their share of A(i).  They do
+//                  ago); C[i&1] <- contributions (+ the ECB records of tile-boundary nodes); release B(i), their share of A(i).  They do
 //                  nothing else: with three of them per sub-partition the fp64 pipe sees a pure arithmetic stream;
 //   node warps   : N(i): wait C[i&1] full; interior node j sums its contributions from C in ascending ORIGINAL element order
 //                  and runs the nodal chain; release C[i&1] and A(i).  Gather chains, four divisions and a square root per
