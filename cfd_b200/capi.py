@@ -90,3 +90,10 @@ def smoothing(lc):
     n = C.c_int32()
     check(lib().cfdb_smoothing(lc.X, lc.Y, lc.inpoel, lc.smooth_fix, lc.npoin, lc.nelem, C.byref(n)))
     return n.value
+
+
+def smoothing_colored(lc):
+    """the parallel, colour-ordered variant of the mesh optimiser (opt-in: not the reference's node order); updates lc.X, lc.Y"""
+    n = C.c_int32()
+    check(lib().cfdb_smoothing_colored(lc.X, lc.Y, lc.inpoel, lc.smooth_fix, lc.npoin, lc.nelem, C.byref(n)))
+    return n.value

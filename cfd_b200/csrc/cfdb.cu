@@ -345,6 +345,15 @@ extern "C" int cfdb_smoothing(double* X, double* Y, const int32_t* inpoel, const
     *sweeps = sm.run(fixed);
     return 0;
 }
+extern "C" int cfdb_smoothing_colored(double* X, double* Y, const int32_t* inpoel, const unsigned char* fixed, int32_t npoin,
+                                      int32_t nelem, int32_t* sweeps) {
+    if (npoin < 1 || nelem < 1) return fail("cfdb_smoothing_colored: empty mesh");
+    for (size_t k = 0; k < 3 * (size_t)nelem; ++k)
+        if (inpoel[k] < 1 || inpoel[k] > npoin) return fail("cfdb_smoothing_colored: inpoel entry out of range");
+    host::MeshSmoother sm(X, Y, inpoel, npoin, nelem);
+    *sweeps = sm.run_colored(fixed);
+    return 0;
+}
 
 static int build_bc_tables(cfdb_ctx* c, const cfdb_bc* bc) {
     const int P = c->npoin;

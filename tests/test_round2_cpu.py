@@ -225,3 +225,53 @@ def test_committed_bench_lines_follow_the_contract():
     ref = line("r2_bench_ref_n1.json")
     assert ref["impl"] == "reference" and ref["metric"] == d["metric"] and ref["unit"] == d["unit"]
     assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["value"] == ref["value"]
+
+
+def _qualities(lc):
+    t = lc.inpoel - 1
+    x, y = lc.X[t], lc.Y[t]
+    a = x[:, 1] * y[:, 2] + x[:, 2] * y[:, 0] + x[:, 0] * y[:, 1] - (x[:, 1] * y[:, 0] + x[:, 2] * y[:, 1] + x[:, 0] * y[:, 2])
+    l = sum((x[:, i] - x[:, j]) ** 2 + (y[:, i] - y[:, j]) ** 2 for i, j in ((2, 1), (0, 2), (1, 0)))
+    return 3.46410161513775 * a / l          # mu of smoothing.f90:305-317 (1 = equilateral, <= 0 = inverted)
+
+
+def test_colour_ordered_smoothing_is_thread_independent_and_improves_the_mesh(tmp_path):
+    """cfdb_smoothing_colored runs the reference's per-node optimiser colour by colour on all host cores.  Its
+    result is bit-identical for 1 and 4 OpenMP threads, leaves the fixed nodes where they are, produces no inverted element and
+    improves the worst element about as much as the serial optimiser does (it is NOT the serial result: different node order)."""
+    import subprocess
+
+    from cfd_b200 import capi, deck, meshgen
+
+    script = tmp_path / "w.py"
+    script.write_text(
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "from cfd_b200 import capi, deck, meshgen\n"
+        "lc = deck.load(meshgen.channel(nx=41, ny=15, jitter=0.45, seed=4))\n"
+        "n = capi.smoothing_colored(lc)\n"
+        "np.savez(sys.argv[1], X=lc.X, Y=lc.Y, n=n)\n")
+    outs = []
+    for thr in ("1", "4"):
+        f = str(tmp_path / f"o{thr}.npz")
+        r = subprocess.run([sys.executable, str(script), f], env=dict(os.environ, OMP_NUM_THREADS=thr), capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append(np.load(f))
+    assert_bit_equal(outs[0]["X"], outs[1]["X"], "X: 1 thread vs 4 threads")
+    assert_bit_equal(outs[0]["Y"], outs[1]["Y"], "Y: 1 thread vs 4 threads")
+    assert int(outs[0]["n"]) >= 1
+
+    lc0 = deck.load(meshgen.channel(nx=41, ny=15, jitter=0.45, seed=4))
+    q0 = _qualities(lc0)
+    lcs = deck.load(meshgen.channel(nx=41, ny=15, jitter=0.45, seed=4))
+    capi.smoothing(lcs)
+    qs = _qualities(lcs)
+    lcc = deck.load(meshgen.channel(nx=41, ny=15, jitter=0.45, seed=4))
+    capi.smoothing_colored(lcc)
+    qc = _qualities(lcc)
+    assert_bit_equal(lcc.X, outs[0]["X"], "same result in this process")
+    fixed = lc0.smooth_fix.astype(bool)
+    assert np.array_equal(lcc.X[fixed], lc0.X[fixed]) and np.array_equal(lcc.Y[fixed], lc0.Y[fixed])
+    assert qc.min() > 0 and qc.min() > q0.min()                       # no inverted element, the worst element got better
+    assert qc.min() > 0.8 * qs.min() and np.mean(qc) > 0.98 * np.mean(qs)   # about as good as the serial optimiser
+    assert not np.array_equal(lcc.X, lcs.X)                          # ... but not the same mesh

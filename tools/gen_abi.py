@@ -212,6 +212,12 @@ fn("cfdb_smoothing", "int", [A("X", "d[]"), A("Y", "d[]"), A("inpoel", "ci32[]",
    "smoothing_mod::smoothing(X, Y, inpoel, fixed, npoin, nelem), smoothing.f90:21 -- the init-time mesh optimiser the\n"
    "driver applies once before the time loop (ns2DComp.ALE.f90:76).  Host code (serial Gauss-Seidel by construction);\n"
    "X, Y are updated in place, *sweeps returns the number of outer sweeps (0: nothing to smooth).")
+fn("cfdb_smoothing_colored", "int", [A("X", "d[]"), A("Y", "d[]"), A("inpoel", "ci32[]", E3), A("fixed", "cu8[]"), A("npoin", "i32"),
+                                     A("nelem", "i32"), A("sweeps", "i32*")],
+   "(new, SURVEY.md N4; opt-in: NOT the reference's results.)  The same optimiser with the nodes visited colour by colour\n"
+   "(greedy colouring, nodes sharing an element get different colours) instead of in ascending order: the nodes of one\n"
+   "colour are optimised concurrently on the host's cores (OpenMP) with the reference's per-node procedure, and the result\n"
+   "does not depend on the number of threads.  Same arguments as cfdb_smoothing.")
 
 sec("---- device self-test of the exact-arithmetic helpers (cfd_b200/csrc/exact.cuh) against the plain IEEE operations:\n"
     " * which = 0 shared-reciprocal division, 1 division by three, 2 zero-numerator division, 3 exact scalings by 0, 1/2, 2\n"
